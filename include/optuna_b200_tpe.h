@@ -1,0 +1,159 @@
+/*
+ * optuna_b200_tpe.h -- C ABI of the B200-native TPE suggestion engine (libtpe_b200.so).
+ *
+ * This is the drop-in boundary for the reference's TPE hot path.  Each entry point names the
+ * reference interface it replaces (paths relative to the optuna checkout @ 4df4b72).  The
+ * Python host (optuna_b200/sampler.py) binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative TPE_E_* code; the message is
+ *     retrievable with tpe_last_error(ctx) (per context, valid until the next call on it);
+ *   - the caller owns all host buffers; the library copies and retains no host pointer;
+ *   - the library owns all device memory; one context is bound to one CUDA device;
+ *   - no callbacks into the host: Python callables of the reference (gamma, weights,
+ *     constraints_func, categorical_distance_func) are evaluated by the host and passed as data;
+ *   - all entry points take a per-context mutex (ctypes releases the GIL, and the reference
+ *     shares one sampler across n_jobs threads: optuna/study/_optimize.py:87-121);
+ *   - doubles are IEEE fp64, indices int64, "internal representation" of a parameter is the
+ *     reference's (optuna/distributions.py:182,365,509): float value / int as float / choice index.
+ */
+#ifndef OPTUNA_B200_TPE_H_
+#define OPTUNA_B200_TPE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPE_ABI_VERSION 1
+
+enum {
+  TPE_OK = 0,
+  TPE_E_INVALID = -1,  /* bad argument (mirrors the reference's ValueError) */
+  TPE_E_CUDA = -2,     /* CUDA runtime failure */
+  TPE_E_STATE = -3,    /* call order violated (e.g. suggest before history/space are set) */
+  TPE_E_NOMEM = -4
+};
+
+/* optuna/distributions.py: FloatDistribution :109, IntDistribution :310, CategoricalDistribution :470 */
+enum { TPE_KIND_FLOAT = 0, TPE_KIND_INT = 1, TPE_KIND_CAT = 2 };
+
+/* Trial groups of TPESampler._split_trials (optuna/samplers/_tpe/sampler.py:686-722). */
+enum { TPE_CAT_COMPLETE = 0, TPE_CAT_PRUNED = 1, TPE_CAT_INFEASIBLE = 2, TPE_CAT_RUNNING = 3 };
+
+typedef struct tpe_ctx tpe_ctx;
+
+typedef struct {
+  int32_t kind;      /* TPE_KIND_* */
+  int32_t log;       /* 1 = log-scaled domain */
+  int32_t has_step;  /* 1 = discretised (always 1 for TPE_KIND_INT) */
+  int32_t n_choices; /* categorical only */
+  double low, high, step;
+} tpe_param_desc;
+
+/* TPESampler constructor arguments that reach the numeric path (sampler.py:305-360) plus the
+ * per-call values the host evaluates (gamma(n) -> n_below). */
+typedef struct {
+  double prior_weight;   /* _ParzenEstimatorParameters.prior_weight */
+  int32_t magic_clip;    /* consider_magic_clip */
+  int32_t endpoints;     /* consider_endpoints */
+  int32_t multivariate;  /* multivariate */
+  int32_t n_candidates;  /* n_ei_candidates */
+  int64_t n_below;       /* gamma(n_finished), evaluated by the host (sampler.py:538-542) */
+} tpe_cfg;
+
+/* Shapes of the two estimators after tpe_prepare. */
+typedef struct {
+  int64_t n_below_all;  /* |below| before dropping trials that lack a selected param */
+  int64_t n_below_obs;  /* observations in l(x) (kernels = +1 prior) */
+  int64_t n_above_obs;  /* observations in g(x) */
+} tpe_split_info;
+
+int tpe_abi_version(void);
+int tpe_ctx_create(int device, tpe_ctx** out);
+void tpe_ctx_destroy(tpe_ctx* ctx);
+const char* tpe_last_error(tpe_ctx* ctx);
+
+/* Search space = every parameter the study has seen, in the host's column order
+ * (replaces the dict[str, BaseDistribution] handed to sample_relative, samplers/_base.py:96).
+ * cat_dist: optional concatenation of row-major [n_choices, n_choices] distance tables for the
+ * categorical params that have a categorical_distance_func (parzen_estimator.py:152-160),
+ * cat_dist_offset[p] = offset into cat_dist or -1. */
+int tpe_space_set(tpe_ctx* ctx, const tpe_param_desc* params, int32_t n_params,
+                  const double* cat_dist, const int64_t* cat_dist_offset);
+
+/* Trial history (replaces the list[FrozenTrial] walk of _get_internal_repr / _split_trials,
+ * sampler.py:511-521, :686-722).
+ *   X        [n, n_params] row-major internal representation, NaN = parameter absent
+ *   category [n] TPE_CAT_*
+ *   key      [n, 2] the reference's sort key inside the category (sampler.py:735-742, :782-821):
+ *            COMPLETE (signed value, 0); PRUNED (-last_step, signed value); INFEASIBLE (violation, 0)
+ * tpe_history_set replaces everything; tpe_history_append adds rows (after_trial hook). */
+int tpe_history_set(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key,
+                    int64_t n);
+int tpe_history_append(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key,
+                       int64_t n);
+/* Same, with DEVICE pointers on ctx's device (used after an NCCL broadcast of the history). */
+int tpe_history_set_device(tpe_ctx* ctx, const double* dX, const int8_t* dcategory,
+                           const double* dkey, int64_t n, const uint8_t* col_has_missing);
+int64_t tpe_history_size(tpe_ctx* ctx);
+/* Device pointers of the resident history (for the NCCL broadcast done by the host plumbing). */
+int tpe_history_device_ptrs(tpe_ctx* ctx, double** dX, int8_t** dcategory, double** dkey);
+
+/* Stage 1: split + observation gathering for the selected columns.
+ * Replaces _split_trials + _get_internal_repr.  cols[n_cols] index into the space. */
+int tpe_prepare(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
+                tpe_split_info* info);
+
+/* Stage 2: build l(x) and g(x) (replaces _ParzenEstimator.__init__, parzen_estimator.py:39-78).
+ * w_below / w_above: raw per-observation weights (weights_func(n)[:n], or the MOTPE weights,
+ * sampler.py:574-576) or NULL for the reference's default_weights (sampler.py:61-69). */
+int tpe_build(tpe_ctx* ctx, const double* w_below, const double* w_above);
+
+/* Stage 3+4: draw candidates from l(x) with host-supplied uniforms and pick the best by
+ * log l(x) - log g(x) (replaces mpe_below.sample, _compute_acquisition_func, _compare;
+ * sampler.py:553-555).  n_asks independent suggestions share the estimators.
+ *   uniforms [n_asks, C * (1 + n_cat + n_num)] per ask in the reference's RNG order
+ *            (probability_distributions.py:87,100,138-144): C for rng.choice, then C per
+ *            categorical param in column order, then an [n_num, C] block.
+ *   out_x    [n_asks, n_cols] chosen candidate (internal representation)
+ *   out_acq  [n_asks] its acquisition value (may be NULL)
+ *   out_best [n_asks] its candidate index (may be NULL) */
+int tpe_sample_and_select(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x,
+                          double* out_acq, int64_t* out_best);
+
+/* One-call convenience = prepare + build + sample_and_select (TPESampler._sample, sampler.py:523-560). */
+int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
+                const double* w_below, const double* w_above, const double* uniforms,
+                int64_t n_asks, double* out_x, double* out_acq, int64_t* out_best);
+
+/* ---- parity / inspection entry points (used by tests and by custom _parzen_estimator_cls-style
+ * consumers, sampler.py:358-359) ------------------------------------------------------------- */
+/* Index lists produced by the last tpe_prepare (ascending trial order). */
+int tpe_get_split(tpe_ctx* ctx, int64_t* below_rows, int64_t* above_rows);
+/* Estimator parameters of the last tpe_build.  which: 0 = below, 1 = above.
+ * weights [K]; mu, sigma [K, n_cols] (categorical columns hold the observed choice index / 0);
+ * K = n_obs + 1.  Any pointer may be NULL. */
+int tpe_get_mixture(tpe_ctx* ctx, int which, double* weights, double* mu, double* sigma);
+/* Candidates / log-densities of the last tpe_sample_and_select (all asks).
+ * samples [n_asks * C, n_cols]; logl, logg [n_asks * C].  Any pointer may be NULL. */
+int tpe_get_candidates(tpe_ctx* ctx, double* samples, double* logl, double* logg);
+/* log-density of arbitrary points under the last-built estimator
+ * (replaces _ParzenEstimator.log_pdf, parzen_estimator.py:84-86).  x [n, n_cols]. */
+int tpe_logpdf(tpe_ctx* ctx, int which, const double* x, int64_t n, double* out);
+
+/* Timing of the last tpe_sample_and_select's kernels on the context stream, in milliseconds
+ * (CUDA events): [0] sample, [1] logpdf grid (below+above), [2] select; launches = kernel count. */
+int tpe_last_timing(tpe_ctx* ctx, float* ms3, int32_t* launches);
+/* Peak-probe: fp64 FMA throughput of this device (TFLOP/s), measured by a dependent-chain-free
+ * DFMA kernel; used by bench.py as the compute-roof denominator. */
+int tpe_probe_fp64_tflops(tpe_ctx* ctx, double* tflops);
+/* Which kernel variant the last log-density pass used (static string). */
+const char* tpe_last_logpdf_kernel(tpe_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTUNA_B200_TPE_H_ */

@@ -1,0 +1,817 @@
+// C ABI of libtpe_b200.so (see include/optuna_b200_tpe.h) -- host orchestration of the kernels in
+// tpe_kernels.cuh.  No torch types, no Python: plain pointers and sizes.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/optuna_b200_tpe.h"
+#include "tpe_kernels.cuh"
+
+using namespace tpe;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t want = std::max(bytes, cap + cap / 2);
+    want = (want + 255) & ~(size_t)255;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  // grow while keeping the first `keep` bytes
+  cudaError_t grow(size_t bytes, size_t keep, cudaStream_t st) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t want = std::max(bytes, cap * 2);
+    want = (want + 255) & ~(size_t)255;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess) return e;
+    if (p && keep) e = cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (p) cudaFree(p);
+    p = q;
+    cap = want;
+    return e;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Estimator {
+  int64_t n = 0, K = 0;
+  DevBuf rows, pos, wstage, w, logw, cdf, mu, sigma, cst_part, cst, kpf, tab, part, fix;
+  int nsplit = 0;
+  void release() {
+    for (DevBuf* b : {&rows, &pos, &wstage, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &kpf, &tab, &part, &fix})
+      b->release();
+  }
+};
+
+}  // namespace
+
+struct tpe_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::mutex mu;
+  std::string err;
+  int sm_count = 148;
+
+  // search space
+  std::vector<tpe_param_desc> space;
+  std::vector<double> cat_dist_h;
+  std::vector<int64_t> cat_dist_off;
+  DevBuf cat_dist;
+
+  // history
+  DevBuf X, cat, key;
+  int64_t N = 0;
+  std::vector<uint8_t> col_missing;
+  bool history_set = false;
+
+  // current call
+  bool prepared = false, built = false, sampled = false;
+  tpe_cfg cfg{};
+  std::vector<ColMeta> cols_h;
+  DevBuf cols;
+  int32_t pc = 0, ncont = 0, ndisc = 0, ncat = 0, nnum = 0, pb = 0;
+  int64_t tab_doubles = 0;
+  bool fast = false;
+  tpe_split_info info{};
+  DevBuf row_ok, member, cand_a, cand_b, counts;
+  Estimator est[2];
+  DevBuf sort_val, sort_idx;
+
+  // candidates
+  int64_t n_asks = 0, Ct = 0, ct_stride = 0;
+  DevBuf U, S, xT, oob, logl, logg, out_x, out_acq, out_best;
+  float ms[3] = {0, 0, 0};
+  int32_t launches = 0;
+  const char* last_kernel = "none";
+  int32_t launch_counter = 0;
+};
+
+namespace {
+
+int fail(tpe_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? TPE_E_NOMEM : TPE_E_CUDA, "%s failed: %s (%s:%d)", \
+                  #call, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
+  } while (0)
+
+inline int grid_for(int64_t work, int threads, int cap) {
+  int64_t g = (work + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+template <class T>
+constexpr T round_up(T v, T m) { return (v + m - 1) / m * m; }
+
+// ---- fast-kernel configuration table ------------------------------------------------------------
+struct FastCfg {
+  int pb, rc, nt, tk, st;
+  size_t smem;
+  void (*launch)(dim3, size_t, cudaStream_t, const double2*, const double*, int64_t, const double*, int64_t,
+                 int64_t, double2*);
+  cudaError_t (*prepare)();
+};
+
+template <int PB, int RC, int NT, int TK, int ST>
+struct FastInst {
+  static constexpr size_t smem = (size_t)ST * TK * PB * 16 + (size_t)ST * TK * 8 + (size_t)ST * 8;
+  static void launch(dim3 grid, size_t sm, cudaStream_t st, const double2* kpf, const double* cst, int64_t K,
+                     const double* xT, int64_t ct_stride, int64_t kps, double2* part) {
+    k_logpdf_fast<PB, RC, NT, TK, ST><<<grid, NT, sm, st>>>(kpf, cst, K, xT, ct_stride, kps, part);
+  }
+  static cudaError_t prepare() {
+    return cudaFuncSetAttribute(k_logpdf_fast<PB, RC, NT, TK, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem);
+  }
+  static FastCfg cfg() { return FastCfg{PB, RC, NT, TK, ST, smem, &launch, &prepare}; }
+};
+
+// "big": many candidates (c-tiles of NT*RC); "small": a single ask with few candidates, the whole
+// grid is spent on splitting the kernel axis.
+const FastCfg kFastBig[] = {
+    FastInst<1, 4, 256, 2048, 3>::cfg(),  FastInst<2, 4, 256, 1024, 3>::cfg(), FastInst<4, 4, 256, 512, 3>::cfg(),
+    FastInst<8, 4, 256, 256, 3>::cfg(),   FastInst<16, 2, 256, 128, 3>::cfg(), FastInst<32, 2, 256, 64, 3>::cfg(),
+    FastInst<64, 1, 256, 32, 3>::cfg(),
+};
+const FastCfg kFastSmall[] = {
+    FastInst<1, 1, 32, 512, 2>::cfg(), FastInst<2, 1, 32, 256, 2>::cfg(), FastInst<4, 1, 32, 128, 2>::cfg(),
+    FastInst<8, 1, 32, 64, 2>::cfg(),  FastInst<16, 1, 32, 32, 2>::cfg(), FastInst<32, 1, 32, 16, 2>::cfg(),
+    FastInst<64, 1, 32, 8, 2>::cfg(),
+};
+constexpr int kMaxFastP = 64;
+
+int pick_pb(int ncont) {
+  for (int pb : {1, 2, 4, 8, 16, 32, 64})
+    if (ncont <= pb) return pb;
+  return 0;
+}
+const FastCfg* pick_fast(int pb, int64_t Ct) {
+  const FastCfg* tabs = (Ct <= 128) ? kFastSmall : kFastBig;
+  for (int i = 0; i < 7; ++i)
+    if (tabs[i].pb == pb) return &tabs[i];
+  return nullptr;
+}
+
+int set_device(tpe_ctx* ctx) {
+  CU(cudaSetDevice(ctx->device));
+  return TPE_OK;
+}
+
+int upload_history(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key, int64_t n,
+                   int64_t at, bool device_src) {
+  const int64_t P = (int64_t)ctx->space.size();
+  const int64_t total = at + n;
+  CU(ctx->X.grow((size_t)std::max<int64_t>(total, 1) * P * 8, (size_t)at * P * 8, ctx->stream));
+  CU(ctx->cat.grow((size_t)std::max<int64_t>(total, 1), (size_t)at, ctx->stream));
+  CU(ctx->key.grow((size_t)std::max<int64_t>(total, 1) * 16, (size_t)at * 16, ctx->stream));
+  const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (n > 0) {
+    CU(cudaMemcpyAsync(ctx->X.as<double>() + at * P, X, (size_t)n * P * 8, kind, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->cat.as<int8_t>() + at, category, (size_t)n, kind, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->key.as<double>() + at * 2, key, (size_t)n * 16, kind, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->N = total;
+  ctx->history_set = true;
+  ctx->prepared = ctx->built = ctx->sampled = false;
+  return TPE_OK;
+}
+
+void scan_missing(tpe_ctx* ctx, const double* X, int64_t n) {
+  const int64_t P = (int64_t)ctx->space.size();
+  for (int64_t i = 0; i < n; ++i)
+    for (int64_t j = 0; j < P; ++j)
+      if (X[i * P + j] != X[i * P + j]) ctx->col_missing[j] = 1;
+}
+
+int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
+  Estimator& e = ctx->est[which];
+  const int64_t n = e.n, K = n + 1;
+  const int32_t pc = ctx->pc;
+  cudaStream_t st = ctx->stream;
+  const int cap = ctx->sm_count * 8;
+  e.K = K;
+  const int64_t k_alloc = round_up<int64_t>(K + 2, 2);
+  CU(e.mu.ensure((size_t)K * pc * 8));
+  CU(e.sigma.ensure((size_t)K * pc * 8));
+  CU(e.cst_part.ensure((size_t)K * 8));
+  CU(e.cst.ensure((size_t)k_alloc * 8));
+  CU(e.w.ensure((size_t)K * 8));
+  CU(e.logw.ensure((size_t)K * 8));
+  CU(e.cdf.ensure((size_t)K * 8));
+  if (ctx->fast) CU(e.kpf.ensure((size_t)K * ctx->pb * 16));
+  if (ctx->tab_doubles) CU(e.tab.ensure((size_t)ctx->tab_doubles * 8));
+
+  k_mu<<<grid_for(K * pc, 256, cap), 256, 0, st>>>(ctx->X.as<double>(), (int32_t)ctx->space.size(),
+                                                   e.rows.as<int64_t>(), n, ctx->cols.as<ColMeta>(), pc,
+                                                   e.mu.as<double>());
+  ctx->launch_counter++;
+  if (ctx->cfg.multivariate) {
+    k_sigma_mv<<<grid_for(K * pc, 256, cap), 256, 0, st>>>(ctx->cols.as<ColMeta>(), pc, n, ctx->cfg.magic_clip,
+                                                           e.sigma.as<double>());
+    ctx->launch_counter++;
+  } else {
+    // categorical columns: sigma unused; numeric columns: sort-based neighbour gaps
+    CU(cudaMemsetAsync(e.sigma.p, 0, (size_t)K * pc * 8, st));
+    int64_t m2 = 1;
+    while (m2 < K) m2 <<= 1;
+    CU(ctx->sort_idx.ensure((size_t)m2 * 4));
+    if (m2 > 4096) CU(ctx->sort_val.ensure((size_t)m2 * 8));
+    for (int j = 0; j < pc; ++j) {
+      if (ctx->cols_h[j].cls == COL_CAT) continue;
+      if (m2 <= 4096) {
+        k_sort_small<<<1, 1024, 0, st>>>(e.mu.as<double>(), pc, j, (int)K, (int)m2, ctx->sort_idx.as<int32_t>());
+        ctx->launch_counter++;
+      } else {
+        const int g = grid_for(m2, 256, cap);
+        k_sort_fill<<<g, 256, 0, st>>>(e.mu.as<double>(), pc, j, K, m2, ctx->sort_val.as<double>(),
+                                        ctx->sort_idx.as<int32_t>());
+        for (int64_t kk = 2; kk <= m2; kk <<= 1)
+          for (int64_t jj = kk >> 1; jj > 0; jj >>= 1) {
+            k_bitonic_step<<<g, 256, 0, st>>>(ctx->sort_val.as<double>(), ctx->sort_idx.as<int32_t>(), m2, jj, kk);
+            ctx->launch_counter++;
+          }
+      }
+      k_sigma_uni<<<grid_for(K, 256, cap), 256, 0, st>>>(e.mu.as<double>(), ctx->sort_idx.as<int32_t>(),
+                                                         ctx->cols.as<ColMeta>(), pc, j, n, ctx->cfg.magic_clip,
+                                                         ctx->cfg.endpoints, e.sigma.as<double>());
+      ctx->launch_counter++;
+    }
+  }
+  if (ctx->fast && ctx->pb > ctx->ncont) {
+    k_kpf_pad<<<grid_for(K * (ctx->pb - ctx->ncont), 256, cap), 256, 0, st>>>(e.kpf.as<double2>(), K, ctx->pb,
+                                                                              ctx->ncont);
+    ctx->launch_counter++;
+  }
+  k_const<<<grid_for(K * 32, 256, cap), 256, 0, st>>>(e.mu.as<double>(), e.sigma.as<double>(),
+                                                      ctx->cols.as<ColMeta>(), pc, K, ctx->pb,
+                                                      ctx->fast ? e.kpf.as<double2>() : nullptr,
+                                                      e.cst_part.as<double>());
+  ctx->launch_counter++;
+  const double* w_dev = nullptr;
+  if (w_host != nullptr && n > 0) {
+    CU(e.wstage.ensure((size_t)n * 8));
+    CU(cudaMemcpyAsync(e.wstage.p, w_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    w_dev = e.wstage.as<double>();
+  }
+  k_weights<<<1, 1024, 0, st>>>(w_dev, nullptr, n, ctx->cfg.prior_weight, e.w.as<double>(), e.logw.as<double>(),
+                                e.cst_part.as<double>(), e.cst.as<double>(), which == 0 ? e.cdf.as<double>() : nullptr,
+                                k_alloc);
+  ctx->launch_counter++;
+  if (ctx->ncat) {
+    k_cat_tables<<<pc, 64, 0, st>>>(ctx->cols.as<ColMeta>(), pc, n, ctx->cfg.prior_weight,
+                                    ctx->cat_dist.as<double>(), e.tab.as<double>());
+    ctx->launch_counter++;
+  }
+  CU(cudaGetLastError());
+  return TPE_OK;
+}
+
+// log-density of the Ct resident candidates under estimator `which`: fills e.part (k-split
+// partials) and, for out-of-support candidates, e.fix.
+int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct) {
+  Estimator& e = ctx->est[which];
+  cudaStream_t st = ctx->stream;
+  const int64_t K = e.K;
+  if (ctx->fast) {
+    const FastCfg* fc = pick_fast(ctx->pb, Ct);
+    const int tc = fc->nt * fc->rc;
+    const int64_t ctiles = (Ct + tc - 1) / tc;
+    // k-splits: fill the machine (one CTA per SM for the big configuration, several for small)
+    const int64_t ktiles = (K + fc->tk - 1) / fc->tk;
+    const int64_t target = (fc->nt >= 256) ? (int64_t)ctx->sm_count * 2 : (int64_t)ctx->sm_count * 8;
+    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>(ktiles, target / ctiles));
+    int64_t tiles_per = (ktiles + nsplit - 1) / nsplit;
+    nsplit = (ktiles + tiles_per - 1) / tiles_per;
+    const int64_t kps = tiles_per * fc->tk;
+    CU(e.part.ensure((size_t)nsplit * ctx->ct_stride * 16));
+    e.nsplit = (int)nsplit;
+    CU(fc->prepare());
+    fc->launch(dim3((unsigned)ctiles, (unsigned)nsplit), fc->smem, st, e.kpf.as<double2>(), e.cst.as<double>(), K,
+               ctx->xT.as<double>(), ctx->ct_stride, kps, e.part.as<double2>());
+    ctx->launch_counter++;
+    ctx->last_kernel = (fc->nt >= 256) ? "k_logpdf_fast<big>" : "k_logpdf_fast<small>";
+    // fix-up: exact evaluation for candidates outside [low, high] (rounding of ppf * sigma + mu)
+    CU(e.fix.ensure((size_t)ctx->ct_stride * 16));
+    k_logpdf_generic<<<dim3((unsigned)((Ct + 127) / 128), 1), 128, 0, st>>>(
+        ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
+        e.cst.as<double>(), K, K, e.tab.as<double>(), ctx->oob.as<uint8_t>(), e.fix.as<double2>(), ctx->ct_stride);
+    ctx->launch_counter++;
+  } else {
+    const int64_t cblocks = (Ct + 127) / 128;
+    const int64_t target = (int64_t)ctx->sm_count * 8;
+    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>((K + 31) / 32, target / cblocks));
+    const int64_t kps = (K + nsplit - 1) / nsplit;
+    nsplit = (K + kps - 1) / kps;
+    CU(e.part.ensure((size_t)nsplit * ctx->ct_stride * 16));
+    e.nsplit = (int)nsplit;
+    k_logpdf_generic<<<dim3((unsigned)cblocks, (unsigned)nsplit), 128, 0, st>>>(
+        ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
+        e.cst.as<double>(), K, kps, e.tab.as<double>(), nullptr, e.part.as<double2>(), ctx->ct_stride);
+    ctx->launch_counter++;
+    ctx->last_kernel = "k_logpdf_generic";
+  }
+  CU(cudaGetLastError());
+  return TPE_OK;
+}
+
+int ensure_candidate_buffers(tpe_ctx* ctx, int64_t Ct) {
+  ctx->Ct = Ct;
+  ctx->ct_stride = round_up<int64_t>(Ct, 1024);
+  CU(ctx->S.ensure((size_t)ctx->ct_stride * ctx->pc * 8));
+  CU(ctx->oob.ensure((size_t)ctx->ct_stride));
+  CU(ctx->logl.ensure((size_t)ctx->ct_stride * 8));
+  CU(ctx->logg.ensure((size_t)ctx->ct_stride * 8));
+  CU(cudaMemsetAsync(ctx->oob.p, 0, (size_t)ctx->ct_stride, ctx->stream));
+  if (ctx->fast) {
+    CU(ctx->xT.ensure((size_t)ctx->ct_stride * ctx->pb * 8));
+    CU(cudaMemsetAsync(ctx->xT.p, 0, (size_t)ctx->ct_stride * ctx->pb * 8, ctx->stream));
+  }
+  return TPE_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int tpe_abi_version(void) { return TPE_ABI_VERSION; }
+
+int tpe_ctx_create(int device, tpe_ctx** out) {
+  if (!out) return TPE_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return TPE_E_CUDA;
+  tpe_ctx* ctx = new tpe_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return TPE_E_CUDA;
+  }
+  for (auto& e : ctx->ev) cudaEventCreate(&e);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return TPE_OK;
+}
+
+void tpe_ctx_destroy(tpe_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (DevBuf* b : {&ctx->cat_dist, &ctx->X, &ctx->cat, &ctx->key, &ctx->cols, &ctx->row_ok, &ctx->member,
+                    &ctx->cand_a, &ctx->cand_b, &ctx->counts, &ctx->sort_val, &ctx->sort_idx, &ctx->U, &ctx->S,
+                    &ctx->xT, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
+    b->release();
+  ctx->est[0].release();
+  ctx->est[1].release();
+  for (auto& e : ctx->ev)
+    if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* tpe_last_error(tpe_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int tpe_space_set(tpe_ctx* ctx, const tpe_param_desc* params, int32_t n_params, const double* cat_dist,
+                  const int64_t* cat_dist_offset) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!params || n_params <= 0) return fail(ctx, TPE_E_INVALID, "space must hold at least one parameter");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  for (int i = 0; i < n_params; ++i) {
+    const tpe_param_desc& d = params[i];
+    if (d.kind == TPE_KIND_CAT) {
+      if (d.n_choices < 1) return fail(ctx, TPE_E_INVALID, "param %d: categorical needs n_choices >= 1", i);
+    } else if (d.kind == TPE_KIND_FLOAT || d.kind == TPE_KIND_INT) {
+      if (!(d.low <= d.high)) return fail(ctx, TPE_E_INVALID, "param %d: low <= high must hold", i);
+      if (d.kind == TPE_KIND_INT && !d.has_step) return fail(ctx, TPE_E_INVALID, "param %d: int needs a step", i);
+      if (d.has_step && !(d.step > 0)) return fail(ctx, TPE_E_INVALID, "param %d: step > 0 must hold", i);
+      if (d.log && d.kind == TPE_KIND_FLOAT && d.has_step)
+        return fail(ctx, TPE_E_INVALID, "param %d: step is not supported when log is true", i);
+      if (d.log && !(d.low - (d.has_step ? d.step / 2 : 0.0) > 0))
+        return fail(ctx, TPE_E_INVALID, "param %d: low > 0 must hold for log", i);
+    } else {
+      return fail(ctx, TPE_E_INVALID, "param %d: unknown kind %d", i, d.kind);
+    }
+  }
+  ctx->space.assign(params, params + n_params);
+  ctx->cat_dist_off.assign(n_params, -1);
+  ctx->cat_dist_h.clear();
+  if (cat_dist && cat_dist_offset) {
+    int64_t end = 0;
+    for (int i = 0; i < n_params; ++i) {
+      ctx->cat_dist_off[i] = cat_dist_offset[i];
+      if (cat_dist_offset[i] >= 0)
+        end = std::max<int64_t>(end, cat_dist_offset[i] + (int64_t)params[i].n_choices * params[i].n_choices);
+    }
+    ctx->cat_dist_h.assign(cat_dist, cat_dist + end);
+    CU(ctx->cat_dist.ensure((size_t)std::max<int64_t>(end, 1) * 8));
+    if (end) CU(cudaMemcpy(ctx->cat_dist.p, cat_dist, (size_t)end * 8, cudaMemcpyHostToDevice));
+  }
+  ctx->col_missing.assign(n_params, 0);
+  ctx->N = 0;
+  ctx->history_set = false;
+  ctx->prepared = ctx->built = ctx->sampled = false;
+  return TPE_OK;
+}
+
+int tpe_history_set(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key, int64_t n) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ctx->space.empty()) return fail(ctx, TPE_E_STATE, "tpe_space_set must precede tpe_history_set");
+  if (n < 0 || (n > 0 && (!X || !category || !key))) return fail(ctx, TPE_E_INVALID, "bad history arguments");
+  if (n >= (1ll << 31) - 4096) return fail(ctx, TPE_E_INVALID, "history too long");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  std::fill(ctx->col_missing.begin(), ctx->col_missing.end(), 0);
+  scan_missing(ctx, X, n);
+  return upload_history(ctx, X, category, key, n, 0, false);
+}
+
+int tpe_history_append(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key, int64_t n) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ctx->space.empty()) return fail(ctx, TPE_E_STATE, "tpe_space_set must precede tpe_history_append");
+  if (n < 0 || (n > 0 && (!X || !category || !key))) return fail(ctx, TPE_E_INVALID, "bad history arguments");
+  if (ctx->N + n >= (1ll << 31) - 4096) return fail(ctx, TPE_E_INVALID, "history too long");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  scan_missing(ctx, X, n);
+  return upload_history(ctx, X, category, key, n, ctx->N, false);
+}
+
+int tpe_history_set_device(tpe_ctx* ctx, const double* dX, const int8_t* dcategory, const double* dkey, int64_t n,
+                           const uint8_t* col_has_missing) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ctx->space.empty()) return fail(ctx, TPE_E_STATE, "tpe_space_set must precede tpe_history_set_device");
+  if (n < 0 || (n > 0 && (!dX || !dcategory || !dkey))) return fail(ctx, TPE_E_INVALID, "bad history arguments");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  for (size_t j = 0; j < ctx->col_missing.size(); ++j) ctx->col_missing[j] = col_has_missing ? col_has_missing[j] : 1;
+  return upload_history(ctx, dX, dcategory, dkey, n, 0, true);
+}
+
+int64_t tpe_history_size(tpe_ctx* ctx) { return ctx ? ctx->N : -1; }
+
+int tpe_history_device_ptrs(tpe_ctx* ctx, double** dX, int8_t** dcategory, double** dkey) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->history_set) return fail(ctx, TPE_E_STATE, "no history");
+  if (dX) *dX = ctx->X.as<double>();
+  if (dcategory) *dcategory = ctx->cat.as<int8_t>();
+  if (dkey) *dkey = ctx->key.as<double>();
+  return TPE_OK;
+}
+
+static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
+                          tpe_split_info* info) {
+  if (!ctx->history_set) return fail(ctx, TPE_E_STATE, "tpe_history_set must precede tpe_prepare");
+  if (!cfg || !cols || n_cols <= 0) return fail(ctx, TPE_E_INVALID, "bad prepare arguments");
+  if (cfg->prior_weight < 0)
+    return fail(ctx, TPE_E_INVALID, "A non-negative value must be specified for prior_weight, but got %g.",
+                cfg->prior_weight);
+  if (cfg->n_candidates <= 0) return fail(ctx, TPE_E_INVALID, "n_candidates must be positive");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  ctx->cfg = *cfg;
+  ctx->launch_counter = 0;
+  const int P = (int)ctx->space.size();
+  ctx->cols_h.clear();
+  ctx->ncont = ctx->ndisc = ctx->ncat = ctx->nnum = 0;
+  int64_t tab = 0;
+  bool need_rowok = false;
+  for (int j = 0; j < n_cols; ++j) {
+    const int src = cols[j];
+    if (src < 0 || src >= P) return fail(ctx, TPE_E_INVALID, "column %d out of range", src);
+    const tpe_param_desc& d = ctx->space[src];
+    ColMeta cm{};
+    cm.src = src;
+    cm.log = d.log;
+    cm.nch = d.n_choices;
+    cm.low = d.low;
+    cm.high = d.high;
+    cm.step = d.has_step ? d.step : 0.0;
+    cm.num_rank = cm.cat_rank = -1;
+    cm.dist_off = -1;
+    if (d.kind == TPE_KIND_CAT) {
+      cm.cls = COL_CAT;
+      cm.cat_rank = ctx->ncat++;
+      cm.slot = cm.cat_rank;
+      cm.tab_off = (int32_t)tab;
+      tab += 2ll * (d.n_choices + 1) * d.n_choices;
+      cm.dist_off = (int32_t)ctx->cat_dist_off[src];
+    } else {
+      cm.num_rank = ctx->nnum++;
+      double lo = d.low, hi = d.high;
+      if (d.has_step) {
+        lo -= d.step / 2;
+        hi += d.step / 2;
+      }
+      if (d.log) {
+        lo = log(lo);
+        hi = log(hi);
+      }
+      cm.klow = lo;
+      cm.khigh = hi;
+      if (d.has_step) {
+        cm.cls = COL_DISC;
+        cm.slot = ctx->ndisc++;
+      } else {
+        cm.cls = COL_CONT;
+        cm.slot = ctx->ncont++;
+      }
+    }
+    need_rowok = need_rowok || ctx->col_missing[src];
+    ctx->cols_h.push_back(cm);
+  }
+  ctx->pc = n_cols;
+  ctx->tab_doubles = tab;
+  ctx->fast = (ctx->ndisc == 0 && ctx->ncat == 0 && ctx->ncont <= kMaxFastP);
+  ctx->pb = ctx->fast ? pick_pb(ctx->ncont) : 0;
+  CU(ctx->cols.ensure(sizeof(ColMeta) * n_cols));
+  CU(cudaMemcpyAsync(ctx->cols.p, ctx->cols_h.data(), sizeof(ColMeta) * n_cols, cudaMemcpyHostToDevice, ctx->stream));
+
+  const int64_t N = ctx->N;
+  const int64_t nal = std::max<int64_t>(N, 1);
+  CU(ctx->member.ensure((size_t)nal));
+  CU(ctx->cand_a.ensure((size_t)nal * 4));
+  CU(ctx->cand_b.ensure((size_t)nal * 4));
+  CU(ctx->counts.ensure(64));
+  for (int w = 0; w < 2; ++w) {
+    CU(ctx->est[w].rows.ensure((size_t)nal * 8));
+  }
+  CU(ctx->est[0].pos.ensure((size_t)nal * 8));
+  const uint8_t* rowok = nullptr;
+  if (need_rowok && N > 0) {
+    CU(ctx->row_ok.ensure((size_t)nal));
+    k_rowok<<<grid_for(N, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+        ctx->X.as<double>(), N, P, ctx->cols.as<ColMeta>(), n_cols, ctx->row_ok.as<uint8_t>());
+    ctx->launch_counter++;
+    rowok = ctx->row_ok.as<uint8_t>();
+  }
+  k_split<<<1, 1024, 0, ctx->stream>>>((int)N, ctx->cat.as<int8_t>(), ctx->key.as<double>(), cfg->n_below, rowok,
+                                       ctx->member.as<uint8_t>(), ctx->cand_a.as<int>(), ctx->cand_b.as<int>(),
+                                       ctx->est[0].rows.as<int64_t>(), ctx->est[0].pos.as<int64_t>(),
+                                       ctx->est[1].rows.as<int64_t>(), ctx->counts.as<int64_t>());
+  ctx->launch_counter++;
+  CU(cudaGetLastError());
+  int64_t counts[3];
+  CU(cudaMemcpyAsync(counts, ctx->counts.p, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->info.n_below_all = counts[0];
+  ctx->info.n_below_obs = counts[1];
+  ctx->info.n_above_obs = counts[2];
+  ctx->est[0].n = counts[1];
+  ctx->est[1].n = counts[2];
+  if (info) *info = ctx->info;
+  ctx->prepared = true;
+  ctx->built = ctx->sampled = false;
+  return TPE_OK;
+}
+
+int tpe_prepare(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols, tpe_split_info* info) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return prepare_locked(ctx, cfg, cols, n_cols, info);
+}
+
+static int build_locked(tpe_ctx* ctx, const double* w_below, const double* w_above) {
+  if (!ctx->prepared) return fail(ctx, TPE_E_STATE, "tpe_prepare must precede tpe_build");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  for (int which = 0; which < 2; ++which) {
+    const double* w = which == 0 ? w_below : w_above;
+    const int64_t n = ctx->est[which].n;
+    if (w) {  // the reference's _call_weights_func checks (parzen_estimator.py:88-109)
+      double tot = 0;
+      for (int64_t i = 0; i < n; ++i) {
+        if (w[i] < 0) return fail(ctx, TPE_E_INVALID, "The `weights` function is not allowed to return negative values.");
+        if (!isfinite(w[i]))
+          return fail(ctx, TPE_E_INVALID, "The `weights`function is not allowed to return infinite or NaN values.");
+        tot += w[i];
+      }
+      if (n > 0 && tot <= 0)
+        return fail(ctx, TPE_E_INVALID, "The `weight` function is not allowed to return all-zero values.");
+    }
+    int rc = build_estimator(ctx, which, w);
+    if (rc) return rc;
+  }
+  ctx->built = true;
+  ctx->sampled = false;
+  return TPE_OK;
+}
+
+int tpe_build(tpe_ctx* ctx, const double* w_below, const double* w_above) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return build_locked(ctx, w_below, w_above);
+}
+
+static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x, double* out_acq,
+                                int64_t* out_best) {
+  if (!ctx->built) return fail(ctx, TPE_E_STATE, "tpe_build must precede tpe_sample_and_select");
+  if (!uniforms || n_asks <= 0 || !out_x) return fail(ctx, TPE_E_INVALID, "bad sample arguments");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  cudaStream_t st = ctx->stream;
+  const int32_t C = ctx->cfg.n_candidates;
+  const int64_t Ct = n_asks * C;
+  const int64_t per_ask = (int64_t)C * (1 + ctx->ncat + ctx->nnum);
+  ctx->n_asks = n_asks;
+  int rc = ensure_candidate_buffers(ctx, Ct);
+  if (rc) return rc;
+  CU(ctx->U.ensure((size_t)n_asks * per_ask * 8));
+  CU(ctx->out_x.ensure((size_t)n_asks * ctx->pc * 8));
+  CU(ctx->out_acq.ensure((size_t)n_asks * 8));
+  CU(ctx->out_best.ensure((size_t)n_asks * 8));
+  CU(cudaMemcpyAsync(ctx->U.p, uniforms, (size_t)n_asks * per_ask * 8, cudaMemcpyHostToDevice, st));
+  const int base_launches = ctx->launch_counter;
+
+  CU(cudaEventRecord(ctx->ev[0], st));
+  Estimator& eb = ctx->est[0];
+  k_sample<<<grid_for(Ct * ctx->pc, 128, ctx->sm_count * 16), 128, 0, st>>>(
+      ctx->U.as<double>(), n_asks, C, ctx->cols.as<ColMeta>(), ctx->pc, ctx->ncat, ctx->nnum, eb.cdf.as<double>(),
+      eb.K, eb.mu.as<double>(), eb.sigma.as<double>(), eb.tab.as<double>(), ctx->S.as<double>(),
+      ctx->fast ? ctx->xT.as<double>() : nullptr, ctx->ct_stride, ctx->oob.as<uint8_t>());
+  ctx->launch_counter++;
+  CU(cudaEventRecord(ctx->ev[1], st));
+  for (int which = 0; which < 2; ++which) {
+    rc = run_logpdf(ctx, which, Ct);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(ctx->ev[2], st));
+  k_select<<<(unsigned)n_asks, 256, 0, st>>>(
+      ctx->est[0].part.as<double2>(), ctx->est[0].nsplit, ctx->est[1].part.as<double2>(), ctx->est[1].nsplit,
+      ctx->ct_stride, ctx->fast ? ctx->oob.as<uint8_t>() : nullptr, ctx->est[0].fix.as<double2>(),
+      ctx->est[1].fix.as<double2>(), C, ctx->S.as<double>(), ctx->pc, ctx->logl.as<double>(), ctx->logg.as<double>(),
+      ctx->out_x.as<double>(), ctx->out_acq.as<double>(), ctx->out_best.as<int64_t>());
+  ctx->launch_counter++;
+  CU(cudaEventRecord(ctx->ev[3], st));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_asks * ctx->pc * 8, cudaMemcpyDeviceToHost, st));
+  if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
+  if (out_best) CU(cudaMemcpyAsync(out_best, ctx->out_best.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  ctx->launches = ctx->launch_counter - base_launches;
+  ctx->sampled = true;
+  return TPE_OK;
+}
+
+int tpe_sample_and_select(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x, double* out_acq,
+                          int64_t* out_best) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return sample_select_locked(ctx, uniforms, n_asks, out_x, out_acq, out_best);
+}
+
+int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols, const double* w_below,
+                const double* w_above, const double* uniforms, int64_t n_asks, double* out_x, double* out_acq,
+                int64_t* out_best) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int rc = prepare_locked(ctx, cfg, cols, n_cols, nullptr);
+  if (rc) return rc;
+  rc = build_locked(ctx, w_below, w_above);
+  if (rc) return rc;
+  return sample_select_locked(ctx, uniforms, n_asks, out_x, out_acq, out_best);
+}
+
+int tpe_get_split(tpe_ctx* ctx, int64_t* below_rows, int64_t* above_rows) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->prepared) return fail(ctx, TPE_E_STATE, "tpe_prepare must precede tpe_get_split");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  if (below_rows && ctx->est[0].n)
+    CU(cudaMemcpyAsync(below_rows, ctx->est[0].rows.p, (size_t)ctx->est[0].n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (above_rows && ctx->est[1].n)
+    CU(cudaMemcpyAsync(above_rows, ctx->est[1].rows.p, (size_t)ctx->est[1].n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TPE_OK;
+}
+
+int tpe_get_mixture(tpe_ctx* ctx, int which, double* weights, double* mu, double* sigma) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->built) return fail(ctx, TPE_E_STATE, "tpe_build must precede tpe_get_mixture");
+  if (which < 0 || which > 1) return fail(ctx, TPE_E_INVALID, "which must be 0 or 1");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  Estimator& e = ctx->est[which];
+  if (weights) CU(cudaMemcpyAsync(weights, e.w.p, (size_t)e.K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mu) CU(cudaMemcpyAsync(mu, e.mu.p, (size_t)e.K * ctx->pc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (sigma) CU(cudaMemcpyAsync(sigma, e.sigma.p, (size_t)e.K * ctx->pc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TPE_OK;
+}
+
+int tpe_get_candidates(tpe_ctx* ctx, double* samples, double* logl, double* logg) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->sampled) return fail(ctx, TPE_E_STATE, "tpe_sample_and_select must precede tpe_get_candidates");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  if (samples) CU(cudaMemcpyAsync(samples, ctx->S.p, (size_t)ctx->Ct * ctx->pc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (logl) CU(cudaMemcpyAsync(logl, ctx->logl.p, (size_t)ctx->Ct * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (logg) CU(cudaMemcpyAsync(logg, ctx->logg.p, (size_t)ctx->Ct * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TPE_OK;
+}
+
+int tpe_logpdf(tpe_ctx* ctx, int which, const double* x, int64_t n, double* out) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->built) return fail(ctx, TPE_E_STATE, "tpe_build must precede tpe_logpdf");
+  if (which < 0 || which > 1 || !x || !out || n <= 0) return fail(ctx, TPE_E_INVALID, "bad logpdf arguments");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  cudaStream_t st = ctx->stream;
+  int rc = ensure_candidate_buffers(ctx, n);
+  if (rc) return rc;
+  ctx->sampled = false;
+  CU(cudaMemcpyAsync(ctx->S.p, x, (size_t)n * ctx->pc * 8, cudaMemcpyHostToDevice, st));
+  if (ctx->fast) {
+    k_prep_points<<<grid_for(n * ctx->pc, 256, ctx->sm_count * 8), 256, 0, st>>>(
+        ctx->S.as<double>(), n, ctx->cols.as<ColMeta>(), ctx->pc, ctx->xT.as<double>(), ctx->ct_stride,
+        ctx->oob.as<uint8_t>());
+    ctx->launch_counter++;
+  }
+  rc = run_logpdf(ctx, which, n);
+  if (rc) return rc;
+  Estimator& e = ctx->est[which];
+  k_finish_logpdf<<<grid_for(n, 256, ctx->sm_count * 8), 256, 0, st>>>(
+      e.part.as<double2>(), e.nsplit, ctx->ct_stride, ctx->fast ? ctx->oob.as<uint8_t>() : nullptr,
+      e.fix.as<double2>(), n, ctx->logl.as<double>());
+  ctx->launch_counter++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, ctx->logl.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return TPE_OK;
+}
+
+int tpe_last_timing(tpe_ctx* ctx, float* ms3, int32_t* launches) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ms3)
+    for (int i = 0; i < 3; ++i) ms3[i] = ctx->ms[i];
+  if (launches) *launches = ctx->launches;
+  return TPE_OK;
+}
+
+int tpe_probe_fp64_tflops(tpe_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (set_device(ctx)) return TPE_E_CUDA;
+  const int blocks = ctx->sm_count * 4, threads = 512, iters = 20000;
+  DevBuf out;
+  CU(out.ensure((size_t)blocks * threads * 8));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    k_fp64_probe<<<blocks, threads, 0, ctx->stream>>>(out.as<double>(), iters);
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  out.release();
+  const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return TPE_OK;
+}
+
+const char* tpe_last_logpdf_kernel(tpe_ctx* ctx) { return ctx ? ctx->last_kernel : "none"; }
+
+}  // extern "C"

@@ -1,0 +1,786 @@
+// CUDA kernels of the TPE suggestion path (sm_100a).  Host orchestration lives in tpe_capi.cu.
+//
+// Stage map (reference file:line each kernel replaces):
+//   k_rowok / k_split        optuna/samplers/_tpe/sampler.py:511-521, :686-722, :735-742, :782-821
+//   k_mu / k_sigma_* / k_const / k_weights / k_cat_tables
+//                            optuna/samplers/_tpe/parzen_estimator.py:39-78, :132-251
+//   k_sample                 optuna/samplers/_tpe/probability_distributions.py:86-152
+//   k_logpdf_fast / k_logpdf_generic
+//                            optuna/samplers/_tpe/probability_distributions.py:154-223,
+//                            optuna/samplers/_tpe/_truncnorm.py:286-297
+//   k_select                 optuna/samplers/_tpe/sampler.py:591-618
+#pragma once
+#include "tpe_common.cuh"
+#include "tpe_math.cuh"
+
+namespace tpe {
+
+// ================================================================================================
+// split
+// ================================================================================================
+__global__ void k_rowok(const double* __restrict__ X, int64_t n, int32_t pall, const ColMeta* __restrict__ cols,
+                        int32_t pc, uint8_t* __restrict__ ok) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    bool good = true;
+    for (int j = 0; j < pc; ++j) {
+      const double v = X[i * pall + cols[j].src];
+      good = good && (v == v);
+    }
+    ok[i] = good ? 1 : 0;
+  }
+}
+
+__device__ __forceinline__ int key_digit(const double* __restrict__ key, int i, int d) {
+  const uint64_t u = order_bits(key[2 * (int64_t)i + (d >= 8 ? 0 : 1)]);
+  return (int)((u >> ((d & 7) * 8)) & 0xffull);
+}
+
+// counts: [0] |below| before the row filter, [1] below observations, [2] above observations
+// Single CTA of 1024 threads (N is 1e5-1e7: a handful of ordered sweeps).
+__global__ void __launch_bounds__(1024, 1)
+k_split(int n, const int8_t* __restrict__ cat, const double* __restrict__ key, int64_t n_below,
+        const uint8_t* __restrict__ row_ok, uint8_t* __restrict__ member, int* __restrict__ cand_a,
+        int* __restrict__ cand_b, int64_t* __restrict__ below_rows, int64_t* __restrict__ below_pos,
+        int64_t* __restrict__ above_rows, int64_t* __restrict__ counts) {
+  __shared__ int s_warp[32];
+  __shared__ int s_hist[256];
+  __shared__ int s_pick[3];  // digit, #less, #equal
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < n; i += 1024) member[i] = 0;
+  __syncthreads();
+
+  int64_t remaining = n_below < 0 ? 0 : n_below;
+  for (int c = 0; c < 3; ++c) {
+    // ordered list of this category's trials
+    int cnt = 0;
+    for (int base = 0; base < n; base += 1024) {
+      const int i = base + tid;
+      const bool f = i < n && cat[i] == c;
+      const int2 r = block_rank_1024(f, s_warp);
+      if (f) cand_a[cnt + r.x] = i;
+      cnt += r.y;
+    }
+    __syncthreads();
+    const int m = (int)(remaining < (int64_t)cnt ? remaining : (int64_t)cnt);
+    remaining -= m;
+    if (m == 0) continue;
+    if (m == cnt) {
+      for (int j = tid; j < cnt; j += 1024) member[cand_a[j]] = 1;
+      __syncthreads();
+      continue;
+    }
+    // radix select of the m smallest (key0, key1, index): most significant byte first
+    int* cur = cand_a;
+    int* nxt = cand_b;
+    int ncur = cnt, need = m;
+    for (int d = 15; d >= 0 && need > 0; --d) {
+      for (int b = tid; b < 256; b += 1024) s_hist[b] = 0;
+      __syncthreads();
+      for (int base = 0; base < ncur; base += 1024) {
+        const int j = base + tid;
+        const bool v = j < ncur;
+        const int dg = v ? key_digit(key, cur[j], d) : -1 - (tid & 31);
+        const unsigned peers = __match_any_sync(0xffffffffu, dg);
+        if (v && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&s_hist[dg], __popc(peers));
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, b = 0;
+        for (; b < 256; ++b) {
+          if (cum + s_hist[b] >= need) break;
+          cum += s_hist[b];
+        }
+        s_pick[0] = b;
+        s_pick[1] = cum;
+        s_pick[2] = s_hist[b];
+      }
+      __syncthreads();
+      const int D = s_pick[0], less = s_pick[1], eq = s_pick[2];
+      int nn = 0;
+      for (int base = 0; base < ncur; base += 1024) {
+        const int j = base + tid;
+        const bool v = j < ncur;
+        const int i = v ? cur[j] : 0;
+        const int dg = v ? key_digit(key, i, d) : 256;
+        if (v && dg < D) member[i] = 1;
+        const int2 r = block_rank_1024(v && dg == D, s_warp);
+        if (v && dg == D) nxt[nn + r.x] = i;
+        nn += r.y;
+      }
+      __syncthreads();
+      need -= less;
+      ncur = eq;
+      int* t = cur;
+      cur = nxt;
+      nxt = t;
+      if (need == ncur) {
+        for (int j = tid; j < ncur; j += 1024) member[cur[j]] = 1;
+        need = 0;
+      }
+      __syncthreads();
+    }
+    if (need > 0) {  // identical keys: earliest trials first (stable)
+      for (int j = tid; j < need; j += 1024) member[cur[j]] = 1;
+    }
+    __syncthreads();
+  }
+
+  // ordered partition (ascending trial number) + drop rows lacking a selected parameter
+  int nb_all = 0, nb = 0, na = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const bool v = i < n;
+    const bool isb = v && cat[i] != 3 && member[i] != 0;
+    const bool ok = v && (row_ok == nullptr || row_ok[i] != 0);
+    const int2 rb_all = block_rank_1024(isb, s_warp);
+    const int2 rb = block_rank_1024(isb && ok, s_warp);
+    const int2 ra = block_rank_1024(v && !isb && ok, s_warp);
+    if (isb && ok) {
+      below_rows[nb + rb.x] = i;
+      below_pos[nb + rb.x] = nb_all + rb_all.x;
+    }
+    if (v && !isb && ok) above_rows[na + ra.x] = i;
+    nb_all += rb_all.y;
+    nb += rb.y;
+    na += ra.y;
+  }
+  if (tid == 0) {
+    counts[0] = nb_all;
+    counts[1] = nb;
+    counts[2] = na;
+  }
+}
+
+// ================================================================================================
+// Parzen-estimator build
+// ================================================================================================
+// mu[k][j] for the n observation kernels and the prior kernel (k = n).  Categorical columns store
+// the observed choice index (prior: nch).
+__global__ void k_mu(const double* __restrict__ X, int32_t pall, const int64_t* __restrict__ rows, int64_t n,
+                     const ColMeta* __restrict__ cols, int32_t pc, double* __restrict__ mu) {
+  const int64_t total = (n + 1) * pc;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = t / pc;
+    const int j = (int)(t - k * pc);
+    const ColMeta cm = cols[j];
+    double v;
+    if (k < n) {
+      v = X[rows[k] * pall + cm.src];
+      if (cm.cls != COL_CAT && cm.log) v = log(v);
+    } else {
+      v = (cm.cls == COL_CAT) ? (double)cm.nch : TPE_MUL(0.5, TPE_ADD(cm.klow, cm.khigh));
+    }
+    mu[t] = v;
+  }
+}
+
+// Bandwidth limits of parzen_estimator.py:220-228.
+__device__ __forceinline__ void sigma_limits(const ColMeta& cm, int64_t n, bool magic_clip, double& lo, double& hi) {
+  hi = TPE_SUB(cm.khigh, cm.klow);
+  if (magic_clip) {
+    const double kk = 1.0 + (double)(n + 1);
+    lo = TPE_DIV(hi, kk < 100.0 ? kk : 100.0);
+  } else {
+    lo = 1e-12;
+  }
+}
+
+// multivariate: sigma = 0.2 * max(n,1)^(-1/(d+4)) * (high-low), clipped; prior: high-low.
+__global__ void k_sigma_mv(const ColMeta* __restrict__ cols, int32_t pc, int64_t n, int magic_clip,
+                           double* __restrict__ sigma) {
+  const int64_t total = (n + 1) * pc;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = t / pc;
+    const int j = (int)(t - k * pc);
+    const ColMeta cm = cols[j];
+    if (cm.cls == COL_CAT) {
+      sigma[t] = 0.0;
+      continue;
+    }
+    double lo, hi;
+    sigma_limits(cm, n, magic_clip != 0, lo, hi);
+    if (k == n) {
+      sigma[t] = hi;
+      continue;
+    }
+    const double e = TPE_DIV(-1.0, (double)(pc + 4));
+    const double base = (double)(n > 1 ? n : 1);
+    double s = TPE_MUL(TPE_MUL(0.2, pow(base, e)), hi);
+    s = fmin(fmax(s, lo), hi);
+    sigma[t] = s;
+  }
+}
+
+// univariate: neighbour gaps in the sorted order of mu U {prior mu} (parzen_estimator.py:196-218).
+// order[j] = index (0..n, n = prior) of the j-th smallest value of column `j_col`.
+__global__ void k_sigma_uni(const double* __restrict__ mu, const int32_t* __restrict__ order,
+                            const ColMeta* __restrict__ cols, int32_t pc, int j_col, int64_t n, int magic_clip,
+                            int endpoints, double* __restrict__ sigma) {
+  const ColMeta cm = cols[j_col];
+  double lo, hi;
+  sigma_limits(cm, n, magic_clip != 0, lo, hi);
+  const int64_t m = n + 1;  // sorted length
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t me = order[j];
+    const double v = mu[me * pc + j_col];
+    const double left = j == 0 ? cm.klow : mu[(int64_t)order[j - 1] * pc + j_col];
+    const double right = j == m - 1 ? cm.khigh : mu[(int64_t)order[j + 1] * pc + j_col];
+    double g = fmax(TPE_SUB(v, left), TPE_SUB(right, v));
+    if (!endpoints && m >= 2) {
+      if (j == 0) g = TPE_SUB(right, v);
+      if (j == m - 1) g = TPE_SUB(v, left);
+    }
+    g = fmin(fmax(g, lo), hi);
+    sigma[me * pc + j_col] = (me == n) ? hi : g;
+  }
+}
+
+// Bitonic sort network step on (value, index) pairs held in global memory; `m2` = padded length
+// (power of two); padded slots carry +inf / INT_MAX.  One launch per (k, j) step.
+__global__ void k_bitonic_step(double* __restrict__ val, int32_t* __restrict__ idx, int64_t m2, int64_t j, int64_t k) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m2; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = i ^ j;
+    if (l > i) {
+      const double a = val[i], b = val[l];
+      const int32_t ia = idx[i], ib = idx[l];
+      const bool a_gt_b = (a > b) || (a == b && ia > ib);
+      const bool up = (i & k) == 0;
+      if (up ? a_gt_b : !a_gt_b) {
+        val[i] = b; val[l] = a;
+        idx[i] = ib; idx[l] = ia;
+      }
+    }
+  }
+}
+__global__ void k_sort_fill(const double* __restrict__ mu, int32_t pc, int j_col, int64_t m, int64_t m2,
+                            double* __restrict__ val, int32_t* __restrict__ idx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m2; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < m) {
+      double v = mu[i * pc + j_col];
+      if (v == 0.0) v = 0.0;
+      val[i] = v;
+      idx[i] = (int32_t)i;
+    } else {
+      val[i] = INFINITY;
+      idx[i] = 0x7fffffff;
+    }
+  }
+}
+// Whole bitonic sort in shared memory for m2 <= 4096 (one CTA of 1024 threads).
+__global__ void __launch_bounds__(1024, 1)
+k_sort_small(const double* __restrict__ mu, int32_t pc, int j_col, int m, int m2, int32_t* __restrict__ order) {
+  __shared__ double sv[4096];
+  __shared__ int32_t si[4096];
+  for (int i = threadIdx.x; i < m2; i += 1024) {
+    if (i < m) {
+      double v = mu[(int64_t)i * pc + j_col];
+      if (v == 0.0) v = 0.0;
+      sv[i] = v;
+      si[i] = i;
+    } else {
+      sv[i] = INFINITY;
+      si[i] = 0x7fffffff;
+    }
+  }
+  __syncthreads();
+  for (int k = 2; k <= m2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < m2; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const double a = sv[i], b = sv[l];
+          const int ia = si[i], ib = si[l];
+          const bool a_gt_b = (a > b) || (a == b && ia > ib);
+          const bool up = (i & k) == 0;
+          if (up ? a_gt_b : !a_gt_b) {
+            sv[i] = b; sv[l] = a;
+            si[i] = ib; si[l] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < m; i += 1024) order[i] = si[i];
+}
+
+// Per-(kernel, column) constants.  One warp per kernel; lanes stride over columns.
+//   continuous: c = ln sqrt(2 pi) + M(a, b) + ln sigma      (a, b = normalised support)
+//   discrete  : c = M(a, b) over the half-step-extended support
+//   cst_part[k] = -sum_j c ;  kpf[k][slot] = (mu, 1 / sigma) for continuous columns.
+__global__ void k_const(const double* __restrict__ mu, const double* __restrict__ sigma,
+                        const ColMeta* __restrict__ cols, int32_t pc, int64_t K, int32_t pb,
+                        double2* __restrict__ kpf, double* __restrict__ cst_part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp; k < K; k += nwarps) {
+    double acc = 0.0;
+    for (int j = lane; j < pc; j += 32) {
+      const ColMeta cm = cols[j];
+      if (cm.cls == COL_CAT) continue;
+      const double m = mu[k * pc + j], s = sigma[k * pc + j];
+      const double a = TPE_DIV(TPE_SUB(cm.klow, m), s);
+      const double b = TPE_DIV(TPE_SUB(cm.khigh, m), s);
+      const double mass = log_gauss_mass(a, b);
+      if (cm.cls == COL_CONT) {
+        acc += kLogSqrt2Pi + mass + log(s);
+        if (kpf != nullptr) kpf[k * pb + cm.slot] = make_double2(m, TPE_DIV(1.0, s));
+      } else {
+        acc += mass;
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) cst_part[k] = -acc;
+  }
+}
+__global__ void k_kpf_pad(double2* __restrict__ kpf, int64_t K, int32_t pb, int32_t ncont) {
+  const int64_t total = K * (pb - ncont);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = t / (pb - ncont);
+    const int s = ncont + (int)(t - k * (pb - ncont));
+    kpf[k * pb + s] = make_double2(0.0, 0.0);
+  }
+}
+
+// Mixture weights (parzen_estimator.py:59-69, sampler.py:61-69).  Single CTA of 1024 threads.
+//   raw[k] = w_in[pos[k]] (or w_in[k] when pos == nullptr), or default_weights(n)[k] when w_in == nullptr;
+//   raw[n] = prior_weight;  w = raw / sum(raw);  logw = ln w;  cst = cst_part + logw;
+//   cdf (optional) = cumsum(w) / cumsum(w)[-1], sequential like numpy.cumsum.
+__global__ void __launch_bounds__(1024, 1)
+k_weights(const double* __restrict__ w_in, const int64_t* __restrict__ pos, int64_t n, double prior_weight,
+          double* __restrict__ w, double* __restrict__ logw, const double* __restrict__ cst_part,
+          double* __restrict__ cst, double* __restrict__ cdf, int64_t k_alloc) {
+  __shared__ double s_red[32];
+  __shared__ double s_total;
+  const int tid = threadIdx.x;
+  const int64_t K = n + 1;
+  // default_weights ramp: np.linspace(1/n, 1, n-25) = arange * step + start, last forced to 1
+  const int64_t nramp = n - 25;
+  const double start = n > 0 ? TPE_DIV(1.0, (double)n) : 0.0;
+  const double step = nramp > 1 ? TPE_DIV(TPE_SUB(1.0, start), (double)(nramp - 1)) : 0.0;
+  double part = 0.0;
+  for (int64_t k = tid; k < K; k += 1024) {
+    double r;
+    if (n == 0) r = 1.0;
+    else if (k == n) r = prior_weight;
+    else if (w_in != nullptr) r = w_in[pos != nullptr ? pos[k] : k];
+    else if (n < 25 || k >= nramp) r = 1.0;
+    else if (k == nramp - 1 && nramp > 1) r = 1.0;
+    else r = TPE_ADD(TPE_MUL((double)k, step), start);
+    w[k] = r;
+    part += r;
+  }
+  part = warp_sum(part);
+  if ((tid & 31) == 0) s_red[tid >> 5] = part;
+  __syncthreads();
+  if (tid < 32) {
+    double v = warp_sum(s_red[tid]);
+    if (tid == 0) s_total = v;
+  }
+  __syncthreads();
+  const double total = s_total;
+  for (int64_t k = tid; k < K; k += 1024) {
+    const double v = TPE_DIV(w[k], total);
+    w[k] = v;
+    const double lw = log(v);
+    logw[k] = lw;
+    cst[k] = cst_part[k] + lw;
+  }
+  for (int64_t k = K + tid; k < k_alloc; k += 1024) cst[k] = -INFINITY;  // padding read by bulk copies
+  __syncthreads();
+  if (cdf != nullptr && tid == 0) {
+    double run = 0.0;
+    for (int64_t k = 0; k < K; ++k) {
+      run = TPE_ADD(run, w[k]);
+      cdf[k] = run;
+    }
+    const double last = cdf[K - 1];
+    for (int64_t k = 0; k < K; ++k) cdf[k] = TPE_DIV(cdf[k], last);
+  }
+}
+
+// Categorical kernel rows (parzen_estimator.py:132-166): the row of kernel k depends only on its
+// observed choice, so a column needs (nch + 1) distinct rows (last = prior kernel).
+// tab layout per column: W[(nch+1) x nch] followed by lnW[(nch+1) x nch].
+__global__ void k_cat_tables(const ColMeta* __restrict__ cols, int32_t pc, int64_t n, double prior_weight,
+                             const double* __restrict__ cat_dist, double* __restrict__ tab) {
+  const int j = blockIdx.x;
+  const ColMeta cm = cols[j];
+  if (cm.cls != COL_CAT) return;
+  const int c = cm.nch;
+  double* W = tab + cm.tab_off;
+  double* LW = W + (int64_t)(c + 1) * c;
+  const double K = (double)(n + 1);
+  for (int r = threadIdx.x; r <= c; r += blockDim.x) {
+    double* row = W + (int64_t)r * c;
+    if (n == 0) {
+      for (int i = 0; i < c; ++i) row[i] = TPE_DIV(1.0, (double)c);
+    } else {
+      const double base = TPE_DIV(prior_weight, K);
+      if (r < c && cm.dist_off >= 0) {
+        const double* d = cat_dist + cm.dist_off + (int64_t)r * c;
+        double dmax = d[0];
+        for (int i = 1; i < c; ++i) dmax = fmax(dmax, d[i]);
+        const double coef = TPE_DIV(TPE_MUL(log(TPE_DIV(K, prior_weight)), log((double)c)), log(6.0));
+        for (int i = 0; i < c; ++i) {
+          const double q = TPE_DIV(d[i], dmax);
+          row[i] = exp(TPE_MUL(-TPE_MUL(q, q), coef));
+        }
+      } else {
+        for (int i = 0; i < c; ++i) row[i] = (i == r) ? TPE_ADD(base, 1.0) : base;
+      }
+      double tot = np_pairwise_sum(row, c);
+      if (tot == 0.0) tot = 1.0;
+      for (int i = 0; i < c; ++i) row[i] = TPE_DIV(row[i], tot);
+    }
+    for (int i = 0; i < c; ++i) LW[(int64_t)r * c + i] = log(row[i]);
+  }
+}
+
+// ================================================================================================
+// candidate sampling from l(x)
+// ================================================================================================
+// One thread per (candidate, column).  S[ct][j] = sampled value (internal representation),
+// xT[slot][ct] = kernel-space value of continuous columns (ln x for log columns) for the fast
+// log-density kernel, oob[ct] = 1 if a continuous value left [low, high] through rounding.
+__global__ void k_sample(const double* __restrict__ U, int64_t n_asks, int32_t C, const ColMeta* __restrict__ cols,
+                         int32_t pc, int32_t ncat, int32_t nnum, const double* __restrict__ cdf, int64_t Kb,
+                         const double* __restrict__ mu, const double* __restrict__ sigma,
+                         const double* __restrict__ tab, double* __restrict__ S, double* __restrict__ xT,
+                         int64_t ct_stride, uint8_t* __restrict__ oob) {
+  const int64_t total = n_asks * C * pc;
+  const int64_t per_ask = (int64_t)C * (1 + ncat + nnum);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ct = t / pc;
+    const int j = (int)(t - ct * pc);
+    const int64_t ask = ct / C;
+    const int c = (int)(ct - ask * C);
+    const double* Ua = U + ask * per_ask;
+    // active kernel: cdf.searchsorted(u, side="right")
+    const double u0 = Ua[c];
+    int64_t lo = 0, hi = Kb;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (u0 < cdf[mid]) hi = mid; else lo = mid + 1;
+    }
+    const int64_t k = lo < Kb ? lo : Kb - 1;
+    const ColMeta cm = cols[j];
+    double out;
+    if (cm.cls == COL_CAT) {
+      const double u = Ua[(int64_t)C * (1 + cm.cat_rank) + c];
+      const int nch = cm.nch;
+      const int row = (k == Kb - 1) ? nch : (int)mu[k * pc + j];
+      const double* w = tab + cm.tab_off + (int64_t)row * nch;
+      double run = 0.0;
+      int cnt = 0;
+      for (int i = 0; i < nch; ++i) {
+        run = TPE_ADD(run, w[i]);
+        const double cp = (i == nch - 1) ? 1.0 : run;
+        cnt += (cp < u) ? 1 : 0;
+      }
+      out = (double)cnt;
+    } else {
+      const double u = Ua[(int64_t)C * (1 + ncat) + (int64_t)cm.num_rank * C + c];
+      const double m = mu[k * pc + j], s = sigma[k * pc + j];
+      const double a = TPE_DIV(TPE_SUB(cm.klow, m), s);
+      const double b = TPE_DIV(TPE_SUB(cm.khigh, m), s);
+      double x = TPE_ADD(TPE_MUL(trunc_ppf(u, a, b), s), m);
+      if (cm.log) x = exp(x);
+      if (cm.cls == COL_DISC) {
+        x = TPE_ADD(cm.low, TPE_MUL(rint(TPE_DIV(TPE_SUB(x, cm.low), cm.step)), cm.step));
+        x = fmin(fmax(x, cm.low), cm.high);
+      } else {
+        if (xT != nullptr) xT[(int64_t)cm.slot * ct_stride + ct] = cm.log ? log(x) : x;
+        if (!(x >= cm.low && x <= cm.high)) oob[ct] = 1;
+      }
+      out = x;
+    }
+    S[ct * pc + j] = out;
+  }
+}
+
+// For tpe_logpdf on caller-supplied points: fill xT / oob from S.
+__global__ void k_prep_points(const double* __restrict__ S, int64_t n, const ColMeta* __restrict__ cols, int32_t pc,
+                              double* __restrict__ xT, int64_t ct_stride, uint8_t* __restrict__ oob) {
+  const int64_t total = n * pc;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ct = t / pc;
+    const int j = (int)(t - ct * pc);
+    const ColMeta cm = cols[j];
+    if (cm.cls != COL_CONT) continue;
+    const double x = S[t];
+    if (xT != nullptr) xT[(int64_t)cm.slot * ct_stride + ct] = cm.log ? log(x) : x;
+    if (!(x >= cm.low && x <= cm.high)) oob[ct] = 1;
+  }
+}
+
+// ================================================================================================
+// log-density grid
+// ================================================================================================
+// Exact, any-kind evaluation of one (candidate, kernel) cell sum -- follows the reference's
+// operation order (division by sigma, support test on normalised coordinates).
+__device__ __forceinline__ double cell_sum_exact(const double* __restrict__ xrow, const double* __restrict__ mu_k,
+                                                 const double* __restrict__ sg_k, const ColMeta* __restrict__ cols,
+                                                 int32_t pc, bool is_prior, const double* __restrict__ tab) {
+  double acc = 0.0;
+  for (int j = 0; j < pc; ++j) {
+    const ColMeta cm = cols[j];
+    const double x = xrow[j];
+    if (cm.cls == COL_CAT) {
+      const int nch = cm.nch;
+      const int row = is_prior ? nch : (int)mu_k[j];
+      const double* LW = tab + cm.tab_off + (int64_t)(nch + 1) * nch;
+      acc += LW[(int64_t)row * nch + (int)x];
+    } else if (cm.cls == COL_CONT) {
+      const double m = mu_k[j], s = sg_k[j];
+      const double xv = cm.log ? log(x) : x;
+      const double z = TPE_DIV(TPE_SUB(xv, m), s);
+      const double a = TPE_DIV(TPE_SUB(cm.klow, m), s);
+      const double b = TPE_DIV(TPE_SUB(cm.khigh, m), s);
+      if (a == b) acc += NAN;
+      else if (z < a || z > b) acc += -INFINITY;
+      else acc += TPE_DIV(-TPE_MUL(z, z), 2.0);
+    } else {
+      const double m = mu_k[j], s = sg_k[j];
+      const double h = TPE_DIV(cm.step, 2.0);
+      double lo = TPE_SUB(x, h), hi = TPE_ADD(x, h);
+      if (cm.log) { lo = log(lo); hi = log(hi); }
+      acc += log_gauss_mass(TPE_DIV(TPE_SUB(lo, m), s), TPE_DIV(TPE_SUB(hi, m), s));
+    }
+  }
+  return acc;
+}
+
+// Generic path: one thread per candidate, kernels [k0, k1) of split blockIdx.y.
+// only_flagged != nullptr restricts the work to candidates with only_flagged[ct] != 0 (fix-up pass).
+__global__ void k_logpdf_generic(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols, int32_t pc,
+                                 const double* __restrict__ mu, const double* __restrict__ sigma,
+                                 const double* __restrict__ cst, int64_t K, int64_t kps, const double* __restrict__ tab,
+                                 const uint8_t* __restrict__ only_flagged, double2* __restrict__ part,
+                                 int64_t ct_stride) {
+  const int64_t ct = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (ct >= Ct) return;
+  double m = -INFINITY, s = 0.0;
+  if (only_flagged == nullptr || only_flagged[ct] != 0) {
+    const int64_t k0 = blockIdx.y * kps;
+    const int64_t k1 = (k0 + kps < K) ? k0 + kps : K;
+    const double* xrow = S + ct * pc;
+    for (int64_t k = k0; k < k1; ++k) {
+      const double L = cst[k] + cell_sum_exact(xrow, mu + k * pc, sigma + k * pc, cols, pc, k == K - 1, tab);
+      lse_push(L, m, s);
+    }
+  }
+  part[blockIdx.y * ct_stride + ct] = make_double2(m, s);
+}
+
+// Fast path: every selected column continuous.  lane = candidate, kernels streamed through shared
+// memory by TMA bulk copies (mbarrier completion), online log-sum-exp in registers.
+//   kpf  [K][PB]  (mu, 1/sigma), zero padded;  cst [K(+pad)]
+//   xT   [PB][ct_stride] kernel-space candidate coordinates (zero padded)
+//   part [gridDim.y][ct_stride] (running max, running sum)
+template <int PB, int RC, int NT, int TK, int ST>
+__global__ void __launch_bounds__(NT, 1)
+k_logpdf_fast(const double2* __restrict__ kpf, const double* __restrict__ cst, int64_t K,
+              const double* __restrict__ xT, int64_t ct_stride, int64_t kps, double2* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2* tiles = reinterpret_cast<double2*>(smem_raw);                       // ST * TK * PB
+  double* csts = reinterpret_cast<double*>(tiles + (size_t)ST * TK * PB);      // ST * TK
+  uint64_t* full = reinterpret_cast<uint64_t*>(csts + (size_t)ST * TK);        // ST
+  const int tid = threadIdx.x;
+  const int64_t k0 = blockIdx.y * kps;
+  const int64_t k1 = (k0 + kps < K) ? k0 + kps : K;
+  const int ntiles = (k1 > k0) ? (int)((k1 - k0 + TK - 1) / TK) : 0;
+  const int64_t cbase = (int64_t)blockIdx.x * (NT * RC);
+
+  if (tid == 0) {
+    for (int s = 0; s < ST; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int t) {
+    const int st = t % ST;
+    const int64_t ks = k0 + (int64_t)t * TK;
+    const int tk = (int)((k1 - ks < TK) ? (k1 - ks) : TK);
+    const uint32_t b_tile = (uint32_t)tk * PB * 16u;
+    const uint32_t b_cst = (uint32_t)(((tk + 1) & ~1) * 8);
+    fence_proxy_async();
+    mbar_expect_tx(&full[st], b_tile + b_cst);
+    bulk_g2s(tiles + (size_t)st * TK * PB, kpf + ks * PB, b_tile, &full[st]);
+    bulk_g2s(csts + (size_t)st * TK, cst + ks, b_cst, &full[st]);
+  };
+  if (tid == 0) {
+    for (int t = 0; t < ST - 1 && t < ntiles; ++t) issue(t);
+  }
+
+  double x[RC][PB];
+#pragma unroll
+  for (int r = 0; r < RC; ++r) {
+    const int64_t ct = cbase + (int64_t)r * NT + tid;
+#pragma unroll
+    for (int p = 0; p < PB; ++p) x[r][p] = xT[(int64_t)p * ct_stride + ct];
+  }
+  double mx[RC], sm[RC];
+#pragma unroll
+  for (int r = 0; r < RC; ++r) {
+    mx[r] = -INFINITY;
+    sm[r] = 0.0;
+  }
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int st = t % ST;
+    if (tid == 0 && t + ST - 1 < ntiles) issue(t + ST - 1);
+    mbar_wait(&full[st], (uint32_t)((t / ST) & 1));
+    const int64_t ks = k0 + (int64_t)t * TK;
+    const int tk = (int)((k1 - ks < TK) ? (k1 - ks) : TK);
+    const double2* tile = tiles + (size_t)st * TK * PB;
+    const double* ctile = csts + (size_t)st * TK;
+    for (int kk = 0; kk < tk; ++kk) {
+      const double2* row = tile + (size_t)kk * PB;
+      double acc0[RC], acc1[RC];
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        acc0[r] = 0.0;
+        acc1[r] = 0.0;
+      }
+#pragma unroll
+      for (int p = 0; p < PB; ++p) {
+        const double2 v = row[p];
+#pragma unroll
+        for (int r = 0; r < RC; ++r) {
+          const double d = (x[r][p] - v.x) * v.y;
+          if (p & 1) acc1[r] = fma(d, d, acc1[r]);
+          else acc0[r] = fma(d, d, acc0[r]);
+        }
+      }
+      const double c = ctile[kk];
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        const double L = fma(-0.5, acc0[r] + acc1[r], c);
+        lse_push(L, mx[r], sm[r]);
+      }
+    }
+    __syncthreads();  // stage `st` may be refilled by the next iteration's issue()
+  }
+#pragma unroll
+  for (int r = 0; r < RC; ++r) {
+    const int64_t ct = cbase + (int64_t)r * NT + tid;
+    part[blockIdx.y * ct_stride + ct] = make_double2(mx[r], sm[r]);
+  }
+}
+
+// ================================================================================================
+// acquisition + argmax
+// ================================================================================================
+// One CTA per ask.  logl/logg = merge of the k-split partials (or the fix-up value for
+// out-of-support candidates), acq = logl - logg, best = first maximum (NaN wins, like np.argmax).
+__global__ void __launch_bounds__(256)
+k_select(const double2* __restrict__ part_l, int nsl, const double2* __restrict__ part_g, int nsg,
+         int64_t ct_stride, const uint8_t* __restrict__ oob, const double2* __restrict__ fix_l,
+         const double2* __restrict__ fix_g, int32_t C, const double* __restrict__ S, int32_t pc,
+         double* __restrict__ logl, double* __restrict__ logg, double* __restrict__ out_x,
+         double* __restrict__ out_acq, int64_t* __restrict__ out_best) {
+  __shared__ double s_val[256];
+  __shared__ int s_idx[256];
+  const int64_t ask = blockIdx.x;
+  const int tid = threadIdx.x;
+  double best = 0.0;
+  int besti = -1;
+  bool best_nan = false;
+  for (int c = tid; c < C; c += 256) {
+    const int64_t ct = ask * C + c;
+    double ml = -INFINITY, sl = 0.0, mg = -INFINITY, sg = 0.0;
+    if (oob != nullptr && oob[ct]) {
+      ml = fix_l[ct].x; sl = fix_l[ct].y;
+      mg = fix_g[ct].x; sg = fix_g[ct].y;
+    } else {
+      for (int s = 0; s < nsl; ++s) {
+        const double2 v = part_l[(int64_t)s * ct_stride + ct];
+        lse_merge(v.x, v.y, ml, sl);
+      }
+      for (int s = 0; s < nsg; ++s) {
+        const double2 v = part_g[(int64_t)s * ct_stride + ct];
+        lse_merge(v.x, v.y, mg, sg);
+      }
+    }
+    // np.log(sum exp(L - max)) + max, with max := 0 when it is -inf
+    const double ll = (ml == -INFINITY) ? -INFINITY : log(sl) + ml;
+    const double lg = (mg == -INFINITY) ? -INFINITY : log(sg) + mg;
+    logl[ct] = ll;
+    logg[ct] = lg;
+    const double a = ll - lg;
+    const bool a_nan = a != a;
+    if (besti < 0 || (!best_nan && (a_nan || a > best))) {
+      best = a;
+      besti = c;
+      best_nan = a_nan;
+    }
+  }
+  s_val[tid] = best;
+  s_idx[tid] = besti;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      const double a = s_val[tid], b = s_val[tid + o];
+      const int ia = s_idx[tid], ib = s_idx[tid + o];
+      bool take_b;
+      if (ib < 0) take_b = false;
+      else if (ia < 0) take_b = true;
+      else {
+        const bool an = a != a, bn = b != b;
+        if (an && bn) take_b = ib < ia;
+        else if (an) take_b = false;
+        else if (bn) take_b = true;
+        else take_b = (b > a) || (b == a && ib < ia);
+      }
+      if (take_b) {
+        s_val[tid] = b;
+        s_idx[tid] = ib;
+      }
+    }
+    __syncthreads();
+  }
+  const int bi = s_idx[0];
+  if (tid == 0) {
+    if (out_best) out_best[ask] = bi;
+    if (out_acq) out_acq[ask] = s_val[0];
+  }
+  for (int j = tid; j < pc; j += 256) out_x[ask * pc + j] = S[(ask * C + bi) * pc + j];
+}
+
+// Merge k-split partials into final log-densities (tpe_logpdf entry point).
+__global__ void k_finish_logpdf(const double2* __restrict__ part, int ns, int64_t ct_stride,
+                                const uint8_t* __restrict__ oob, const double2* __restrict__ fix, int64_t n,
+                                double* __restrict__ out) {
+  for (int64_t ct = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ct < n; ct += (int64_t)gridDim.x * blockDim.x) {
+    double m = -INFINITY, s = 0.0;
+    if (oob != nullptr && oob[ct]) {
+      m = fix[ct].x;
+      s = fix[ct].y;
+    } else {
+      for (int i = 0; i < ns; ++i) {
+        const double2 v = part[(int64_t)i * ct_stride + ct];
+        lse_merge(v.x, v.y, m, s);
+      }
+    }
+    out[ct] = (m == -INFINITY) ? -INFINITY : log(s) + m;
+  }
+}
+
+// ================================================================================================
+// fp64 FMA peak probe (roofline denominator for the compute-bound grid kernel)
+// ================================================================================================
+__global__ void k_fp64_probe(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace tpe

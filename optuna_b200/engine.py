@@ -1,0 +1,230 @@
+"""Array-level Python face of the C ABI: one ``TPEEngine`` = one ``tpe_ctx`` on one GPU.
+
+This is the thin layer ``B200TPESampler`` (sampler.py) drives; it is also what the parity tests
+call so that every check goes through the C ABI.  It holds no algorithmic logic: inputs are
+validated and copied by the library (include/optuna_b200_tpe.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass(frozen=True)
+class ParamSpec:
+    """One column of the search space (mirror of optuna.distributions.*Distribution fields)."""
+
+    kind: int  # _lib.KIND_*
+    low: float = 0.0
+    high: float = 0.0
+    step: float | None = None
+    log: bool = False
+    n_choices: int = 0
+    dist_table: np.ndarray | None = None  # categorical_distance_func evaluated on all pairs
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape=None) -> np.ndarray:
+    out = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        out = out.reshape(shape)
+    return out
+
+
+class TPEEngine:
+    def __init__(self, device: int = 0) -> None:
+        self._lib = _lib.load()
+        handle = C.c_void_p()
+        rc = self._lib.tpe_ctx_create(int(device), C.byref(handle))
+        if rc != 0:
+            raise RuntimeError(f"tpe_ctx_create(device={device}) failed with code {rc}: a CUDA device is required")
+        self._h = handle
+        self.device = int(device)
+        self.n_params = 0
+        self._cfg = None
+        self._pc = 0
+        self._ncat = self._nnum = 0
+        self._specs: list[ParamSpec] = []
+        self._cols: list[int] = []
+
+    # -- lifecycle -----------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.tpe_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc == 0:
+            return
+        msg = self._lib.tpe_last_error(self._h).decode()
+        if rc == _lib.TPE_E_INVALID:
+            raise ValueError(msg)
+        raise RuntimeError(f"libtpe_b200 error {rc}: {msg}")
+
+    # -- space / history -------------------------------------------------------------------------
+    def set_space(self, specs: Sequence[ParamSpec]) -> None:
+        n = len(specs)
+        arr = (_lib.ParamDesc * max(n, 1))()
+        offs = np.full(max(n, 1), -1, dtype=np.int64)
+        tables = []
+        at = 0
+        for i, s in enumerate(specs):
+            arr[i].kind = s.kind
+            arr[i].log = int(bool(s.log))
+            arr[i].has_step = int(s.step is not None)
+            arr[i].n_choices = int(s.n_choices)
+            arr[i].low = float(s.low)
+            arr[i].high = float(s.high)
+            arr[i].step = float(s.step) if s.step is not None else 0.0
+            if s.dist_table is not None:
+                t = _f64(s.dist_table, (s.n_choices, s.n_choices))
+                tables.append(t.ravel())
+                offs[i] = at
+                at += t.size
+        flat = np.concatenate(tables) if tables else None
+        self._check(self._lib.tpe_space_set(self._h, arr, n, _ptr(flat), _ptr(offs) if tables else None))
+        self._specs = list(specs)
+        self.n_params = n
+
+    def set_history(self, X, category, key) -> None:
+        X = _f64(X, (-1, self.n_params))
+        cat = np.ascontiguousarray(category, dtype=np.int8)
+        key = _f64(key, (-1, 2))
+        assert X.shape[0] == cat.shape[0] == key.shape[0]
+        self._check(self._lib.tpe_history_set(self._h, _ptr(X), _ptr(cat), _ptr(key), X.shape[0]))
+
+    def append_history(self, X, category, key) -> None:
+        X = _f64(X, (-1, self.n_params))
+        cat = np.ascontiguousarray(category, dtype=np.int8).reshape(-1)
+        key = _f64(key, (-1, 2))
+        self._check(self._lib.tpe_history_append(self._h, _ptr(X), _ptr(cat), _ptr(key), X.shape[0]))
+
+    def set_history_device(self, dX: int, dcat: int, dkey: int, n: int, col_has_missing=None) -> None:
+        miss = None if col_has_missing is None else np.ascontiguousarray(col_has_missing, dtype=np.uint8)
+        self._check(self._lib.tpe_history_set_device(self._h, C.c_void_p(dX), C.c_void_p(dcat), C.c_void_p(dkey),
+                                                     int(n), _ptr(miss)))
+
+    def history_device_ptrs(self) -> tuple[int, int, int]:
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._lib.tpe_history_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    @property
+    def history_size(self) -> int:
+        return int(self._lib.tpe_history_size(self._h))
+
+    # -- stages ------------------------------------------------------------------------------------
+    def _make_cfg(self, *, n_below: int, n_candidates: int, multivariate: bool, prior_weight: float = 1.0,
+                  magic_clip: bool = True, endpoints: bool = False) -> _lib.Cfg:
+        return _lib.Cfg(float(prior_weight), int(magic_clip), int(endpoints), int(multivariate),
+                        int(n_candidates), int(n_below))
+
+    def _note_cols(self, cols: Sequence[int], n_candidates: int) -> np.ndarray:
+        self._cols = [int(c) for c in cols]
+        self._pc = len(self._cols)
+        self._ncat = sum(1 for c in self._cols if 0 <= c < self.n_params and self._specs[c].kind == _lib.KIND_CAT)
+        self._nnum = self._pc - self._ncat
+        self._C = int(n_candidates)
+        return np.ascontiguousarray(self._cols, dtype=np.int32)
+
+    def uniforms_per_ask(self) -> int:
+        return self._C * (1 + self._ncat + self._nnum)
+
+    def prepare(self, cols: Sequence[int], **cfg) -> tuple[int, int, int]:
+        c = self._make_cfg(**cfg)
+        cols_a = self._note_cols(cols, c.n_candidates)
+        info = _lib.SplitInfo()
+        self._check(self._lib.tpe_prepare(self._h, C.byref(c), _ptr(cols_a), len(cols_a), C.byref(info)))
+        self._info = (int(info.n_below_all), int(info.n_below_obs), int(info.n_above_obs))
+        return self._info
+
+    def build(self, w_below=None, w_above=None) -> None:
+        wb = None if w_below is None else _f64(w_below)
+        wa = None if w_above is None else _f64(w_above)
+        if wb is not None:
+            assert wb.size == self._info[1], (wb.size, self._info)
+        if wa is not None:
+            assert wa.size == self._info[2], (wa.size, self._info)
+        self._check(self._lib.tpe_build(self._h, _ptr(wb), _ptr(wa)))
+
+    def sample_and_select(self, uniforms, n_asks: int = 1):
+        u = _f64(uniforms).reshape(-1)
+        assert u.size == n_asks * self.uniforms_per_ask(), (u.size, n_asks, self.uniforms_per_ask())
+        x = np.empty((n_asks, self._pc), dtype=np.float64)
+        acq = np.empty(n_asks, dtype=np.float64)
+        best = np.empty(n_asks, dtype=np.int64)
+        self._check(self._lib.tpe_sample_and_select(self._h, _ptr(u), int(n_asks), _ptr(x), _ptr(acq), _ptr(best)))
+        self._last_asks = n_asks
+        return x, acq, best
+
+    def suggest(self, cols: Sequence[int], uniforms, n_asks: int = 1, w_below=None, w_above=None, **cfg):
+        c = self._make_cfg(**cfg)
+        cols_a = self._note_cols(cols, c.n_candidates)
+        u = _f64(uniforms).reshape(-1)
+        assert u.size == n_asks * self.uniforms_per_ask()
+        wb = None if w_below is None else _f64(w_below)
+        wa = None if w_above is None else _f64(w_above)
+        x = np.empty((n_asks, self._pc), dtype=np.float64)
+        acq = np.empty(n_asks, dtype=np.float64)
+        best = np.empty(n_asks, dtype=np.int64)
+        self._check(self._lib.tpe_suggest(self._h, C.byref(c), _ptr(cols_a), len(cols_a), _ptr(wb), _ptr(wa),
+                                          _ptr(u), int(n_asks), _ptr(x), _ptr(acq), _ptr(best)))
+        self._last_asks = n_asks
+        return x, acq, best
+
+    # -- inspection --------------------------------------------------------------------------------
+    def get_split(self) -> tuple[np.ndarray, np.ndarray]:
+        below = np.empty(self._info[1], dtype=np.int64)
+        above = np.empty(self._info[2], dtype=np.int64)
+        self._check(self._lib.tpe_get_split(self._h, _ptr(below), _ptr(above)))
+        return below, above
+
+    def get_mixture(self, which: int):
+        K = self._info[1 + which] + 1
+        w = np.empty(K)
+        mu = np.empty((K, self._pc))
+        sg = np.empty((K, self._pc))
+        self._check(self._lib.tpe_get_mixture(self._h, int(which), _ptr(w), _ptr(mu), _ptr(sg)))
+        return w, mu, sg
+
+    def get_candidates(self):
+        ct = self._last_asks * self._C
+        s = np.empty((ct, self._pc))
+        ll = np.empty(ct)
+        lg = np.empty(ct)
+        self._check(self._lib.tpe_get_candidates(self._h, _ptr(s), _ptr(ll), _ptr(lg)))
+        return s, ll, lg
+
+    def logpdf(self, which: int, x) -> np.ndarray:
+        x = _f64(x, (-1, self._pc))
+        out = np.empty(x.shape[0])
+        self._check(self._lib.tpe_logpdf(self._h, int(which), _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def last_timing(self) -> tuple[np.ndarray, int]:
+        ms = np.zeros(3, dtype=np.float32)
+        n = C.c_int32()
+        self._check(self._lib.tpe_last_timing(self._h, _ptr(ms), C.byref(n)))
+        return ms, int(n.value)
+
+    def probe_fp64_tflops(self) -> float:
+        v = C.c_double()
+        self._check(self._lib.tpe_probe_fp64_tflops(self._h, C.byref(v)))
+        return float(v.value)
+
+    def last_logpdf_kernel(self) -> str:
+        return self._lib.tpe_last_logpdf_kernel(self._h).decode()

@@ -1,0 +1,276 @@
+"""CUDA path (through the C ABI) vs the oracle and the live-reference golden vectors.
+
+Tolerances: split indices and categorical / integer draws exact;
+mu / sigma / weights <= 1e-15 relative (sigma of multivariate kernels goes through device pow():
+<= 2 ulp); sampled floats <= 1e-12 relative; log_pdf <= 1e-12 absolute for continuous and
+categorical columns; discrete columns carry the reference's own ill-conditioning
+ so they get 1e-9.
+"""
+import numpy as np
+import pytest
+
+from oracle import tpe_oracle as orc
+from tests._util import decode_space, draw_uniforms, kinds_of, load, specs_from_space
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from optuna_b200 import TPEEngine
+    e = TPEEngine(0)
+    yield e
+    e.close()
+
+
+def close(a, b, rtol, atol=0.0):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    both_nan = np.isnan(a) & np.isnan(b)
+    skip = both_inf | both_nan
+    err = np.abs(a - b)
+    lim = atol + rtol * np.abs(b)
+    bad = ~skip & ~(err <= lim)
+    assert not bad.any(), f"max err {np.nanmax(np.where(skip, 0, err))} at {np.argwhere(bad)[:5].tolist()}"
+
+
+def has_discrete(params):
+    return any((not p.is_cat) and p.step is not None for p in params)
+
+
+def test_parzen_build_sample_logpdf(eng):
+    g = load("parzen.npz")
+    for i in range(int(g["n_cases"])):
+        t = f"pz{i}/"
+        params = decode_space(g[t + "space"])
+        mv, clip, endp, pw, C, seed = g[t + "flags"]
+        C = int(C)
+        obs = g[t + "obs"]
+        n = obs.shape[0]
+        eng.set_space(specs_from_space(g[t + "space"]))
+        eng.set_history(obs, np.zeros(n, np.int8), np.stack([np.arange(n, dtype=float), np.zeros(n)], 1))
+        cfg = dict(n_candidates=C, multivariate=bool(mv), prior_weight=float(pw), magic_clip=bool(clip),
+                   endpoints=bool(endp))
+        cols = list(range(len(params)))
+        # everything "below" -> est[0] is the estimator of the golden case
+        info = eng.prepare(cols, n_below=n, **cfg)
+        assert info == (n, n, 0)
+        eng.build()
+        w, mu, sg = eng.get_mixture(0)
+        close(w, g[t + "w"], 1e-15)
+        for j, p in enumerate(params):
+            if p.is_cat:
+                continue
+            close(mu[:, j], g[f"{t}mu{j}"], 1e-15, 1e-300)
+            # ties in np.argsort(unstable) only matter for duplicate observations (discrete columns)
+            if p.step is None or bool(mv):
+                close(sg[:, j], g[f"{t}sigma{j}"], 1e-15)
+        ncat, nnum = kinds_of(params)
+        u = draw_uniforms(np.random.RandomState(int(seed) + 1000), C, ncat, nnum)
+        eng.sample_and_select(u, 1)
+        smp, _, _ = eng.get_candidates()
+        ref = g[t + "samples"]
+        for j, p in enumerate(params):
+            if p.is_cat or p.step is not None:
+                if p.step is None or bool(mv) or n <= 1:
+                    assert np.array_equal(smp[:, j], ref[:, j]), (i, j)
+            else:
+                close(smp[:, j], ref[:, j], 1e-12, 1e-12)
+        tol = 1e-9 if has_discrete(params) else 1e-12
+        if bool(mv) or n <= 1:
+            close(eng.logpdf(0, ref), g[t + "logpdf"], 0, tol)
+            close(eng.logpdf(0, g[t + "samples2"]), g[t + "logpdf2"], 0, tol)
+
+
+def _run_case(eng, g, t, cols, rng, mv, C, n_below):
+    params_all = decode_space(g[t + "space"])
+    params = [params_all[c] for c in cols]
+    ncat, nnum = kinds_of(params)
+    u = draw_uniforms(rng, C, ncat, nnum)
+    x, acq, best = eng.suggest(cols, u, 1, n_below=n_below, n_candidates=C, multivariate=mv)
+    smp, ll, lg = eng.get_candidates()
+    return params, x[0], acq[0], int(best[0]), smp, ll, lg
+
+
+def test_suggest_against_reference_goldens(eng):
+    g = load("suggest.npz")
+    for ci in range(int(g["n_cases"])):
+        t = f"sg{ci}/"
+        mv, C, seed, n_below = g[t + "cfg"]
+        mv, C, n_below = bool(mv), int(C), int(n_below)
+        X, cat, key = g[t + "X"], g[t + "category"], g[t + "key"]
+        P = X.shape[1]
+        eng.set_space(specs_from_space(g[t + "space"]))
+        eng.set_history(X, cat, key)
+        rng = np.random.RandomState(int(seed))
+        if mv:
+            cols = list(range(P))
+            params, x, acq, best, smp, ll, lg = _run_case(eng, g, t, cols, rng, True, C, n_below)
+            below, above = eng.get_split()
+            ob, keep_b = orc.observations(X, g[t + "below"], cols)
+            oa, keep_a = orc.observations(X, g[t + "above"], cols)
+            assert np.array_equal(below, g[t + "below"][keep_b])
+            assert np.array_equal(above, g[t + "above"][keep_a])
+            ref = g[t + "samples"]
+            for j, p in enumerate(params):
+                if p.is_cat or p.step is not None:
+                    assert np.array_equal(smp[:, j], ref[:, j]), (ci, j)
+                else:
+                    close(smp[:, j], ref[:, j], 1e-12, 1e-12)
+            tol = 1e-9 if has_discrete(params) else 1e-12
+            close(ll, g[t + "ll"], 0, tol)
+            close(lg, g[t + "lg"], 0, tol)
+            assert best == int(np.argmax(g[t + "ll"] - g[t + "lg"]))
+            want = g[t + "ret_internal"]
+            for j, p in enumerate(params):
+                if p.is_cat or p.step is not None:
+                    assert x[j] == want[j]
+                else:
+                    close(x[j], want[j], 1e-12, 1e-12)
+        else:
+            for j in range(P):
+                params, x, acq, best, smp, ll, lg = _run_case(eng, g, t, [j], rng, False, C, n_below)
+                p = params[0]
+                ref = g[f"{t}u{j}/samples"]
+                dup = (not p.is_cat) and p.step is not None  # duplicate observations: argsort tie order
+                if p.is_cat:
+                    assert np.array_equal(smp, ref)
+                    close(ll, g[f"{t}u{j}/ll"], 0, 1e-12)
+                    close(lg, g[f"{t}u{j}/lg"], 0, 1e-12)
+                elif not dup:
+                    close(smp, ref, 1e-12, 1e-12)
+                    close(ll, g[f"{t}u{j}/ll"], 0, 1e-12)
+                    close(lg, g[f"{t}u{j}/lg"], 0, 1e-12)
+                    close(x[0], g[t + "ret_internal"][j], 1e-12, 1e-12)
+
+
+def test_univariate_duplicates_match_stable_oracle(eng):
+    """Discrete columns in univariate mode: the reference's bandwidths depend on np.argsort's
+    (unstable) tie order; the CUDA path uses the stable order, so compare with the oracle run with
+    stable_sort=True on the same inputs."""
+    g = load("suggest.npz")
+    t = "sg3/"
+    mv, C, seed, n_below = g[t + "cfg"]
+    C, n_below = int(C), int(n_below)
+    X, cat, key = g[t + "X"], g[t + "category"], g[t + "key"]
+    params_all = decode_space(g[t + "space"])
+    eng.set_space(specs_from_space(g[t + "space"]))
+    eng.set_history(X, cat, key)
+    cfg = orc.Config(multivariate=False, stable_sort=True)
+    for j, p in enumerate(params_all):
+        if p.is_cat or p.step is None:
+            continue
+        rng_o = np.random.RandomState(100 + j)
+        s = orc.suggest(X, cat, key, params_all, [j], cfg, n_below, C, rng_o)
+        u = draw_uniforms(np.random.RandomState(100 + j), C, 0, 1)
+        x, acq, best = eng.suggest([j], u, 1, n_below=n_below, n_candidates=C, multivariate=False)
+        smp, ll, lg = eng.get_candidates()
+        wb, mub, sgb = eng.get_mixture(0)
+        wa, mua, sga = eng.get_mixture(1)
+        close(sgb[:, 0], s.mix_below.sigma[0], 1e-15)
+        close(sga[:, 0], s.mix_above.sigma[0], 1e-15)
+        assert np.array_equal(smp[:, 0], s.samples[:, 0])
+        close(ll, s.logl, 0, 1e-9)
+        close(lg, s.logg, 0, 1e-9)
+        assert int(best[0]) == s.best
+        assert x[0, 0] == s.x[0]
+
+
+def test_split_edge_cases(eng):
+    """+-inf values, ties (stable), pruned ordering, infeasible, running (sampler.py:686-821)."""
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(5)
+    eng.set_space([ParamSpec(kind=0, low=0.0, high=1.0)])
+    for trial in range(30):
+        n = int(rs.randint(1, 400))
+        cat = rs.choice([0, 0, 0, 1, 2, 3], size=n).astype(np.int8)
+        key = np.zeros((n, 2))
+        key[:, 0] = rs.choice([-np.inf, np.inf, 0.0, -0.0, 1.0, 2.0, 3.5], size=n) if trial % 2 else rs.normal(size=n)
+        pr = cat == 1
+        key[pr, 0] = -rs.randint(0, 3, size=pr.sum())
+        key[pr, 1] = rs.choice([0.5, 1.5, np.inf], size=pr.sum())
+        X = rs.uniform(size=(n, 1))
+        eng.set_history(X, cat, key)
+        for n_below in (0, 1, n // 3, n, n + 5):
+            eng.prepare([0], n_below=n_below, n_candidates=4, multivariate=True)
+            below, above = eng.get_split()
+            ob, oa = orc.split_trials(cat, key, n_below)
+            assert np.array_equal(below, ob), (trial, n_below)
+            assert np.array_equal(above, oa), (trial, n_below)
+
+
+def test_config2_shape_against_chunked_oracle(eng):
+    """BASELINE config 2 at full size (N=100k, P=32, C=4096, multivariate): every stage vs the
+    oracle, the log-density on a slice of candidates (the oracle needs ~1 s per 4 candidates)."""
+    from optuna_b200.engine import ParamSpec
+    N, P, C = 100_000, 32, 4096
+    rs = np.random.RandomState(0)
+    X = rs.uniform(0, 1, (N, P))
+    loss = ((X - 0.5) ** 2).sum(1)
+    cat = np.zeros(N, np.int8)
+    key = np.stack([loss, np.zeros(N)], 1)
+    eng.set_space([ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(P)])
+    eng.set_history(X, cat, key)
+    n_below = orc.default_gamma(N)
+    rng = np.random.RandomState(1)
+    u = draw_uniforms(rng, C, 0, P)
+    x, acq, best = eng.suggest(list(range(P)), u, 1, n_below=n_below, n_candidates=C, multivariate=True)
+    assert eng.last_logpdf_kernel().startswith("k_logpdf_fast")
+    smp, ll, lg = eng.get_candidates()
+    params = [orc.Param("float", 0.0, 1.0) for _ in range(P)]
+    cfg = orc.Config(multivariate=True)
+    ob, oa = orc.split_trials(cat, key, n_below)
+    below, above = eng.get_split()
+    assert np.array_equal(below, ob) and np.array_equal(above, oa)
+    mb = orc.build_mixture(X[ob], params, cfg)
+    ma = orc.build_mixture(X[oa], params, cfg)
+    osmp = orc.mixture_sample(mb, np.random.RandomState(1), C)
+    close(smp, osmp, 1e-12, 1e-12)
+    wa, mua, sga = eng.get_mixture(1)
+    close(wa, ma.weights, 1e-15)
+    close(sga[:, 0], ma.sigma[0], 1e-15)
+    pick = np.concatenate([np.arange(8), [int(best[0])], rs.randint(0, C, 7)])
+    close(ll[pick], orc.mixture_log_pdf(mb, osmp[pick]), 0, 1e-12)
+    close(lg[pick], orc.mixture_log_pdf_chunked(ma, osmp[pick], rows=4), 0, 1e-12)
+    # size-independent properties on the whole batch
+    assert np.all((smp >= 0) & (smp <= 1))
+    assert int(best[0]) == int(np.argmax(ll - lg))
+    assert np.array_equal(x[0], smp[int(best[0])])
+    assert np.isfinite(ll).all() and np.isfinite(lg).all()
+    # tpe_logpdf entry point == values produced inside sample_and_select
+    close(eng.logpdf(1, smp[:64]), lg[:64], 0, 1e-13)
+
+
+def test_batched_asks_equal_sequential(eng):
+    """n_asks suggestions in one call == the same asks one by one (config 5 semantics)."""
+    g = load("suggest.npz")
+    t = "sg7/"
+    X, cat, key = g[t + "X"], g[t + "category"], g[t + "key"]
+    P = X.shape[1]
+    eng.set_space(specs_from_space(g[t + "space"]))
+    eng.set_history(X, cat, key)
+    C, n_asks = 24, 37
+    rng = np.random.RandomState(3)
+    us = [draw_uniforms(rng, C, 0, P) for _ in range(n_asks)]
+    cols = list(range(P))
+    xb, ab, bb = eng.suggest(cols, np.concatenate(us), n_asks, n_below=25, n_candidates=C, multivariate=True)
+    for a in range(n_asks):
+        x1, a1, b1 = eng.suggest(cols, us[a], 1, n_below=25, n_candidates=C, multivariate=True)
+        assert np.array_equal(x1[0], xb[a]) and b1[0] == bb[a]
+        close(a1[0], ab[a], 0, 1e-13)
+
+
+def test_error_contract(eng):
+    from optuna_b200.engine import ParamSpec
+    eng.set_space([ParamSpec(kind=0, low=0.0, high=1.0)])
+    eng.set_history(np.random.RandomState(0).uniform(size=(20, 1)), np.zeros(20, np.int8), np.zeros((20, 2)))
+    with pytest.raises(ValueError):
+        eng.prepare([0], n_below=3, n_candidates=8, multivariate=True, prior_weight=-1.0)
+    eng.prepare([0], n_below=3, n_candidates=8, multivariate=True)
+    with pytest.raises(ValueError):
+        eng.build(w_above=-np.ones(17))
+    with pytest.raises(ValueError):
+        eng.build(w_above=np.zeros(17))
+    with pytest.raises(ValueError):
+        eng.set_space([ParamSpec(kind=0, low=2.0, high=1.0)])
