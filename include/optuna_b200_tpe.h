@@ -131,6 +131,8 @@ int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n
 
 /* ---- parity / inspection entry points (used by tests and by custom _parzen_estimator_cls-style
  * consumers, sampler.py:358-359) ------------------------------------------------------------- */
+/* Shapes of the last tpe_prepare / tpe_suggest. */
+int tpe_get_split_info(tpe_ctx* ctx, tpe_split_info* info);
 /* Index lists produced by the last tpe_prepare (ascending trial order). */
 int tpe_get_split(tpe_ctx* ctx, int64_t* below_rows, int64_t* above_rows);
 /* Estimator parameters of the last tpe_build.  which: 0 = below, 1 = above.

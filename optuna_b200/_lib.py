@@ -47,6 +47,7 @@ SYMBOLS = {
     "tpe_build": (C.c_int, [_P, _P, _P]),
     "tpe_sample_and_select": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     "tpe_suggest": (C.c_int, [_P, C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P]),
+    "tpe_get_split_info": (C.c_int, [_P, C.POINTER(SplitInfo)]),
     "tpe_get_split": (C.c_int, [_P, _P, _P]),
     "tpe_get_mixture": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "tpe_get_candidates": (C.c_int, [_P, _P, _P, _P]),

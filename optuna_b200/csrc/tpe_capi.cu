@@ -711,6 +711,14 @@ int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n
   return sample_select_locked(ctx, uniforms, n_asks, out_x, out_acq, out_best);
 }
 
+int tpe_get_split_info(tpe_ctx* ctx, tpe_split_info* info) {
+  if (!ctx || !info) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->prepared) return fail(ctx, TPE_E_STATE, "tpe_prepare must precede tpe_get_split_info");
+  *info = ctx->info;
+  return TPE_OK;
+}
+
 int tpe_get_split(tpe_ctx* ctx, int64_t* below_rows, int64_t* above_rows) {
   if (!ctx) return TPE_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);

@@ -184,7 +184,13 @@ class TPEEngine:
         self._check(self._lib.tpe_suggest(self._h, C.byref(c), _ptr(cols_a), len(cols_a), _ptr(wb), _ptr(wa),
                                           _ptr(u), int(n_asks), _ptr(x), _ptr(acq), _ptr(best)))
         self._last_asks = n_asks
+        self._info = self.split_info()
         return x, acq, best
+
+    def split_info(self) -> tuple[int, int, int]:
+        info = _lib.SplitInfo()
+        self._check(self._lib.tpe_get_split_info(self._h, C.byref(info)))
+        return int(info.n_below_all), int(info.n_below_obs), int(info.n_above_obs)
 
     # -- inspection --------------------------------------------------------------------------------
     def get_split(self) -> tuple[np.ndarray, np.ndarray]:
