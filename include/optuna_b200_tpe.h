@@ -146,9 +146,11 @@ int tpe_get_candidates(tpe_ctx* ctx, double* samples, double* logl, double* logg
  * (replaces _ParzenEstimator.log_pdf, parzen_estimator.py:84-86).  x [n, n_cols]. */
 int tpe_logpdf(tpe_ctx* ctx, int which, const double* x, int64_t n, double* out);
 
-/* Timing of the last tpe_sample_and_select's kernels on the context stream, in milliseconds
- * (CUDA events): [0] sample, [1] logpdf grid (below+above), [2] select; launches = kernel count. */
-int tpe_last_timing(tpe_ctx* ctx, float* ms3, int32_t* launches);
+/* CUDA-event timing (ms, on the context stream) of the stages of the last prepare / build /
+ * sample_and_select sequence: [0] split, [1] estimator build, [2] uniforms H2D, [3] sample,
+ * [4] log-density under l(x), [5] main log-density kernel under g(x), [6] its fix-up pass,
+ * [7] select, [8] first-to-last span.  launches = kernels launched by the sequence. */
+int tpe_last_timing(tpe_ctx* ctx, float* ms9, int32_t* launches);
 /* Peak-probe: fp64 FMA throughput of this device (TFLOP/s), measured by a dependent-chain-free
  * DFMA kernel; used by bench.py as the compute-roof denominator. */
 int tpe_probe_fp64_tflops(tpe_ctx* ctx, double* tflops);

@@ -71,7 +71,7 @@ struct Estimator {
 struct tpe_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;
   std::string err;
   int sm_count = 148;
@@ -104,7 +104,7 @@ struct tpe_ctx {
   // candidates
   int64_t n_asks = 0, Ct = 0, ct_stride = 0;
   DevBuf U, S, xT, oob, logl, logg, out_x, out_acq, out_best;
-  float ms[3] = {0, 0, 0};
+  float ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   int32_t launches = 0;
   const char* last_kernel = "none";
   int32_t launch_counter = 0;
@@ -306,7 +306,7 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
 
 // log-density of the Ct resident candidates under estimator `which`: fills e.part (k-split
 // partials) and, for out-of-support candidates, e.fix.
-int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct) {
+int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nullptr) {
   Estimator& e = ctx->est[which];
   cudaStream_t st = ctx->stream;
   const int64_t K = e.K;
@@ -328,6 +328,7 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct) {
                ctx->xT.as<double>(), ctx->ct_stride, kps, e.part.as<double2>());
     ctx->launch_counter++;
     ctx->last_kernel = (fc->nt >= 256) ? "k_logpdf_fast<big>" : "k_logpdf_fast<small>";
+    if (after_main) CU(cudaEventRecord(after_main, st));
     // fix-up: exact evaluation for candidates outside [low, high] (rounding of ppf * sigma + mu)
     CU(e.fix.ensure((size_t)ctx->ct_stride * 16));
     k_logpdf_generic<<<dim3((unsigned)((Ct + 127) / 128), 1), 128, 0, st>>>(
@@ -347,6 +348,7 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct) {
         e.cst.as<double>(), K, kps, e.tab.as<double>(), nullptr, e.part.as<double2>(), ctx->ct_stride);
     ctx->launch_counter++;
     ctx->last_kernel = "k_logpdf_generic";
+    if (after_main) CU(cudaEventRecord(after_main, st));
   }
   CU(cudaGetLastError());
   return TPE_OK;
@@ -511,6 +513,7 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
   if (set_device(ctx)) return TPE_E_CUDA;
   ctx->cfg = *cfg;
   ctx->launch_counter = 0;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   const int P = (int)ctx->space.size();
   ctx->cols_h.clear();
   ctx->ncont = ctx->ndisc = ctx->ncat = ctx->nnum = 0;
@@ -591,6 +594,7 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
                                        ctx->est[1].rows.as<int64_t>(), ctx->counts.as<int64_t>());
   ctx->launch_counter++;
   CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   int64_t counts[3];
   CU(cudaMemcpyAsync(counts, ctx->counts.p, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -631,6 +635,7 @@ static int build_locked(tpe_ctx* ctx, const double* w_below, const double* w_abo
     int rc = build_estimator(ctx, which, w);
     if (rc) return rc;
   }
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   ctx->built = true;
   ctx->sampled = false;
   return TPE_OK;
@@ -661,33 +666,36 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   CU(cudaMemcpyAsync(ctx->U.p, uniforms, (size_t)n_asks * per_ask * 8, cudaMemcpyHostToDevice, st));
   const int base_launches = ctx->launch_counter;
 
-  CU(cudaEventRecord(ctx->ev[0], st));
+  CU(cudaEventRecord(ctx->ev[3], st));
   Estimator& eb = ctx->est[0];
   k_sample<<<grid_for(Ct * ctx->pc, 128, ctx->sm_count * 16), 128, 0, st>>>(
       ctx->U.as<double>(), n_asks, C, ctx->cols.as<ColMeta>(), ctx->pc, ctx->ncat, ctx->nnum, eb.cdf.as<double>(),
       eb.K, eb.mu.as<double>(), eb.sigma.as<double>(), eb.tab.as<double>(), ctx->S.as<double>(),
       ctx->fast ? ctx->xT.as<double>() : nullptr, ctx->ct_stride, ctx->oob.as<uint8_t>());
   ctx->launch_counter++;
-  CU(cudaEventRecord(ctx->ev[1], st));
-  for (int which = 0; which < 2; ++which) {
-    rc = run_logpdf(ctx, which, Ct);
-    if (rc) return rc;
-  }
-  CU(cudaEventRecord(ctx->ev[2], st));
+  CU(cudaEventRecord(ctx->ev[4], st));
+  rc = run_logpdf(ctx, 0, Ct);
+  if (rc) return rc;
+  CU(cudaEventRecord(ctx->ev[5], st));
+  rc = run_logpdf(ctx, 1, Ct, ctx->ev[6]);
+  if (rc) return rc;
+  CU(cudaEventRecord(ctx->ev[7], st));
   k_select<<<(unsigned)n_asks, 256, 0, st>>>(
       ctx->est[0].part.as<double2>(), ctx->est[0].nsplit, ctx->est[1].part.as<double2>(), ctx->est[1].nsplit,
       ctx->ct_stride, ctx->fast ? ctx->oob.as<uint8_t>() : nullptr, ctx->est[0].fix.as<double2>(),
       ctx->est[1].fix.as<double2>(), C, ctx->S.as<double>(), ctx->pc, ctx->logl.as<double>(), ctx->logg.as<double>(),
       ctx->out_x.as<double>(), ctx->out_acq.as<double>(), ctx->out_best.as<int64_t>());
   ctx->launch_counter++;
-  CU(cudaEventRecord(ctx->ev[3], st));
+  CU(cudaEventRecord(ctx->ev[8], st));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_asks * ctx->pc * 8, cudaMemcpyDeviceToHost, st));
   if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
   if (out_best) CU(cudaMemcpyAsync(out_best, ctx->out_best.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
-  ctx->launches = ctx->launch_counter - base_launches;
+  for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  cudaEventElapsedTime(&ctx->ms[8], ctx->ev[0], ctx->ev[8]);
+  ctx->launches = ctx->launch_counter;
+  (void)base_launches;
   ctx->sampled = true;
   return TPE_OK;
 }
@@ -788,11 +796,11 @@ int tpe_logpdf(tpe_ctx* ctx, int which, const double* x, int64_t n, double* out)
   return TPE_OK;
 }
 
-int tpe_last_timing(tpe_ctx* ctx, float* ms3, int32_t* launches) {
+int tpe_last_timing(tpe_ctx* ctx, float* ms9, int32_t* launches) {
   if (!ctx) return TPE_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  if (ms3)
-    for (int i = 0; i < 3; ++i) ms3[i] = ctx->ms[i];
+  if (ms9)
+    for (int i = 0; i < 9; ++i) ms9[i] = ctx->ms[i];
   if (launches) *launches = ctx->launches;
   return TPE_OK;
 }

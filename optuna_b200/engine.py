@@ -222,7 +222,7 @@ class TPEEngine:
         return out
 
     def last_timing(self) -> tuple[np.ndarray, int]:
-        ms = np.zeros(3, dtype=np.float32)
+        ms = np.zeros(9, dtype=np.float32)
         n = C.c_int32()
         self._check(self._lib.tpe_last_timing(self._h, _ptr(ms), C.byref(n)))
         return ms, int(n.value)

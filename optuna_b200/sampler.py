@@ -1,0 +1,381 @@
+"""B200TPESampler -- drop-in for optuna.samplers.TPESampler backed by libtpe_b200.so.
+
+Mirrors the reference's plugin surface (optuna/samplers/_base.py:31-228) and constructor
+(optuna/samplers/_tpe/sampler.py:305-385).  What stays on the host is exactly what the reference
+can only do in Python: walking FrozenTrial objects once (incrementally) into arrays, evaluating the
+user's callables (gamma, weights, constraints_func, categorical_distance_func), drawing the
+uniforms from the sampler's own numpy RandomState in the reference's order
+(probability_distributions.py:87,100,138-144) and converting the winner back with
+``to_external_repr``.  Split, estimator build, candidate sampling, the log-density grid and the
+argmax run on the GPU through the C ABI (include/optuna_b200_tpe.h).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import json
+import math
+import threading
+import warnings
+from typing import Any, Callable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._compat import (CONSTRAINTS_KEY, RELATIVE_PARAMS_KEY, SYSTEM_ATTR_MAX_LENGTH, BaseDistribution,
+                      BaseSampler, CategoricalDistribution, FloatDistribution, IntDistribution,
+                      LazyRandomState, StudyDirection, TrialState, random_independent)
+from .engine import ParamSpec, TPEEngine
+
+EPS = 1e-12
+
+
+def default_gamma(x: int) -> int:
+    """sampler.py:53-54"""
+    return min(math.ceil(0.1 * x), 25)
+
+
+def hyperopt_default_gamma(x: int) -> int:
+    """sampler.py:57-58"""
+    return min(math.ceil(0.25 * x**0.5), 25)
+
+
+def default_weights(x: int) -> np.ndarray:
+    """sampler.py:61-69.  When this very function is the sampler's ``weights`` the library
+    evaluates it on the device (k_weights); the host version serves custom compositions."""
+    if x == 0:
+        return np.asarray([])
+    if x < 25:
+        return np.ones(x)
+    return np.concatenate([np.linspace(1.0 / x, 1.0, num=x - 25), np.ones(25)], axis=0)
+
+
+def _checked_weights(func: Callable[[int], np.ndarray], n: int) -> np.ndarray:
+    """parzen_estimator.py:88-109"""
+    w = np.array(func(n))[:n]
+    if np.any(w < 0):
+        raise ValueError(f"The `weights` function is not allowed to return negative values {w}. "
+                         f"The argument of the `weights` function is {n}.")
+    if len(w) > 0 and np.sum(w) <= 0:
+        raise ValueError(f"The `weight` function is not allowed to return all-zero values {w}."
+                         f" The argument of the `weights` function is {n}.")
+    if not np.all(np.isfinite(w)):
+        raise ValueError("The `weights`function is not allowed to return infinite or NaN values "
+                         f"{w}. The argument of the `weights` function is {n}.")
+    return np.asarray(w, dtype=np.float64)
+
+
+def _pruned_key(trial, sign: float) -> tuple[float, float]:
+    """sampler.py:782-792"""
+    if len(trial.intermediate_values) > 0:
+        step, v = max(trial.intermediate_values.items())
+        if math.isnan(v):
+            return -step, float("inf")
+        return -step, sign * v
+    return 1, 0.0
+
+
+def _infeasible_score(trial) -> float:
+    """sampler.py:803-813"""
+    con = trial.system_attrs.get(CONSTRAINTS_KEY)
+    if con is None:
+        warnings.warn(f"Trial {trial.number} does not have constraint values."
+                      " It will be treated as a lower priority than other trials.")
+        return float("inf")
+    return sum(v for v in con if v > 0)
+
+
+def _spec_of(name: str, d: BaseDistribution, dist_funcs: dict) -> ParamSpec:
+    if isinstance(d, CategoricalDistribution):
+        table = None
+        if name in dist_funcs:
+            f = dist_funcs[name]
+            table = np.asarray([[f(a, b) for b in d.choices] for a in d.choices], dtype=np.float64)
+        return ParamSpec(kind=_lib.KIND_CAT, n_choices=len(d.choices), dist_table=table)
+    if isinstance(d, IntDistribution):
+        return ParamSpec(kind=_lib.KIND_INT, low=float(d.low), high=float(d.high), step=float(d.step), log=bool(d.log))
+    assert isinstance(d, FloatDistribution), d
+    return ParamSpec(kind=_lib.KIND_FLOAT, low=d.low, high=d.high, step=d.step, log=bool(d.log))
+
+
+class _History:
+    """Device-resident trial history kept in step with the study (replaces the per-call
+    FrozenTrial walks of sampler.py:511-521 and :686-722)."""
+
+    def __init__(self) -> None:
+        self.columns: dict[str, int] = {}
+        self.dists: list[BaseDistribution] = []
+        self.n = 0
+        self.last_number = -1
+        self.sign = 1.0
+        self.token: tuple | None = None
+        self.n_finished = 0
+        # incremental intersection search space (optuna/search_space/intersection.py:14-55)
+        self.inter: dict[str, BaseDistribution] | None = None
+        self.inter_n = 0
+        self.inter_last = -1
+
+
+class B200TPESampler(BaseSampler):
+    def __init__(
+        self,
+        *,
+        consider_prior: bool = True,
+        prior_weight: float = 1.0,
+        consider_magic_clip: bool = True,
+        consider_endpoints: bool = False,
+        n_startup_trials: int = 10,
+        n_ei_candidates: int = 24,
+        gamma: Callable[[int], int] = default_gamma,
+        weights: Callable[[int], np.ndarray] = default_weights,
+        seed: int | None = None,
+        multivariate: bool = False,
+        group: bool = False,
+        warn_independent_sampling: bool = True,
+        constant_liar: bool = False,
+        constraints_func: Callable[[Any], Sequence[float]] | None = None,
+        categorical_distance_func: dict[str, Callable[[Any, Any], float]] | None = None,
+        device: int = 0,
+    ) -> None:
+        if not consider_prior:
+            warnings.warn("`consider_prior` is deprecated; it falls back to `True`.", FutureWarning)
+        if group and not multivariate:
+            raise ValueError("``group`` option can only be enabled when ``multivariate`` is enabled.")
+        if group:
+            raise NotImplementedError("group=True is not built yet (SURVEY.md section 8f rank 3).")
+        self._prior_weight = prior_weight
+        self._magic_clip = consider_magic_clip
+        self._endpoints = consider_endpoints
+        self._n_startup_trials = n_startup_trials
+        self._n_ei_candidates = n_ei_candidates
+        self._gamma = gamma
+        self._weights = weights
+        self._multivariate = multivariate
+        self._group = group
+        self._warn_independent_sampling = warn_independent_sampling
+        self._constant_liar = constant_liar
+        self._constraints_func = constraints_func
+        self._cat_dist_funcs = categorical_distance_func or {}
+        self._rng = LazyRandomState(seed)
+        self._startup_rng = LazyRandomState(seed)  # the embedded RandomSampler's own state (sampler.py:348-349)
+        self._device = device
+        self._engine: TPEEngine | None = None
+        self._hist = _History()
+        self._lock = threading.RLock()
+
+    # -- pickling: device state is a cache re-creatable from the study ----------
+    def __getstate__(self) -> dict:
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_hist"] = _History()
+        del state["_lock"]
+        return state
+
+    def __setstate__(self, state: dict) -> None:
+        self.__dict__.update(state)
+        self._lock = threading.RLock()
+
+    @staticmethod
+    def hyperopt_parameters() -> dict[str, Any]:
+        return {"consider_prior": True, "prior_weight": 1.0, "consider_magic_clip": True,
+                "consider_endpoints": False, "n_startup_trials": 20, "n_ei_candidates": 24,
+                "gamma": hyperopt_default_gamma, "weights": default_weights}
+
+    def reseed_rng(self) -> None:
+        self._rng.rng.seed()
+        self._startup_rng.rng.seed()
+
+    # -- plugin surface -------------------------------------------------------------------------------
+    def infer_relative_search_space(self, study, trial) -> dict[str, BaseDistribution]:
+        if not self._multivariate:
+            return {}
+        with self._lock:
+            space = self._intersection(study)
+        return {k: d for k, d in space.items() if not d.single()}
+
+    def sample_relative(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
+        params = self._sample_relative(study, trial, search_space)
+        if params != {} and self._constant_liar:
+            text = json.dumps(params)
+            for i in range(0, len(text), SYSTEM_ATTR_MAX_LENGTH):
+                study._storage.set_trial_system_attr(trial._trial_id,
+                                                     f"{RELATIVE_PARAMS_KEY}:{i // SYSTEM_ATTR_MAX_LENGTH}",
+                                                     text[i: i + SYSTEM_ATTR_MAX_LENGTH])
+        return params
+
+    def _sample_relative(self, study, trial, search_space) -> dict[str, Any]:
+        if search_space == {}:
+            return {}
+        trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
+        if len(trials) < self._n_startup_trials:
+            return {}
+        return self._sample(study, trial, search_space)
+
+    def sample_independent(self, study, trial, param_name: str, param_distribution: BaseDistribution) -> Any:
+        trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
+        if len(trials) < self._n_startup_trials:
+            return random_independent(self._startup_rng.rng, param_distribution)
+        if self._warn_independent_sampling and self._multivariate:
+            if any(param_name in t.params for t in trials):
+                warnings.warn(f"The parameter '{param_name}' in trial#{trial.number} is sampled independently "
+                              "instead of being sampled by multivariate TPE sampler (dynamic search space is "
+                              "not supported for `multivariate=True`).")
+        return self._sample(study, trial, {param_name: param_distribution})[param_name]
+
+    def before_trial(self, study, trial) -> None:
+        pass
+
+    def after_trial(self, study, trial, state, values) -> None:
+        assert state in (TrialState.COMPLETE, TrialState.FAIL, TrialState.PRUNED)
+        if self._constraints_func is None or state not in (TrialState.COMPLETE, TrialState.PRUNED):
+            return
+        con = None
+        try:
+            out = self._constraints_func(trial)
+            if not isinstance(out, (tuple, list)):
+                warnings.warn("Constraints should be a sequence of floats.")
+            con = tuple(out)
+        finally:
+            study._storage.set_trial_system_attr(trial._trial_id, CONSTRAINTS_KEY, con)
+
+    # -- host glue -------------------------------------------------------------------------------------
+    def _eng(self) -> TPEEngine:
+        if self._engine is None:
+            self._engine = TPEEngine(self._device)
+        return self._engine
+
+    def _get_params(self, trial) -> dict[str, Any]:
+        """sampler.py:493-509"""
+        if trial.state.is_finished() or not self._multivariate:
+            return trial.params
+        chunks = []
+        i = 0
+        while (c := trial.system_attrs.get(f"{RELATIVE_PARAMS_KEY}:{i}")):
+            chunks.append(c)
+            i += 1
+        if not chunks:
+            return trial.params
+        params = json.loads("".join(chunks))
+        params.update(trial.params)
+        return params
+
+    def _intersection(self, study) -> dict[str, BaseDistribution]:
+        h = self._hist
+        trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
+        fresh = not (h.inter_n <= len(trials) and (h.inter_n == 0 or trials[h.inter_n - 1].number == h.inter_last))
+        if fresh:
+            h.inter, h.inter_n = None, 0
+        for t in trials[h.inter_n:]:
+            if h.inter is None:
+                h.inter = dict(t.distributions)
+            else:
+                h.inter = {k: d for k, d in h.inter.items() if k in t.distributions and d == t.distributions[k]}
+        h.inter_n = len(trials)
+        h.inter_last = trials[-1].number if trials else -1
+        return dict(sorted((h.inter or {}).items(), key=lambda kv: kv[0]))
+
+    def _rows(self, study, trials, names: list[str], dists: list[BaseDistribution]):
+        sign = -1.0 if (not study._is_multi_objective() and study.direction == StudyDirection.MAXIMIZE) else 1.0
+        n, p = len(trials), len(names)
+        X = np.full((n, p), np.nan)
+        cat = np.zeros(n, dtype=np.int8)
+        key = np.zeros((n, 2))
+        for i, t in enumerate(trials):
+            params = self._get_params(t)
+            for j, name in enumerate(names):
+                if name in params:
+                    X[i, j] = dists[j].to_internal_repr(params[name])
+            if t.state == TrialState.RUNNING:
+                cat[i] = _lib.CAT_RUNNING
+            elif self._constraints_func is not None and (score := _infeasible_score(t)) > 0:
+                cat[i] = _lib.CAT_INFEASIBLE
+                key[i, 0] = score
+            elif t.state == TrialState.COMPLETE:
+                cat[i] = _lib.CAT_COMPLETE
+                key[i, 0] = sign * t.value if not study._is_multi_objective() else 0.0
+            else:
+                cat[i] = _lib.CAT_PRUNED
+                key[i] = _pruned_key(t, sign)
+        return X, cat, key
+
+    def _sync(self, study, trial, search_space: dict[str, BaseDistribution]) -> tuple[int, list[int]]:
+        """Bring the device history up to date; returns (#finished trials, device columns)."""
+        h = self._hist
+        eng = self._eng()
+        if self._constant_liar:
+            states = (TrialState.COMPLETE, TrialState.PRUNED, TrialState.RUNNING)
+            trials = [t for t in study._get_trials(deepcopy=False, states=states, use_cache=False)
+                      if t.number != trial.number]
+        else:
+            trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
+        token = (getattr(study, "_study_id", None), id(getattr(study, "_storage", None)),
+                 tuple(getattr(study, "directions", ())))
+        rebuild = self._constant_liar or h.token != token
+        for name, d in search_space.items():
+            j = h.columns.get(name)
+            if j is None or h.dists[j] != d:
+                rebuild = True
+        if not rebuild:
+            if not (h.n <= len(trials) and (h.n == 0 or trials[h.n - 1].number == h.last_number)):
+                rebuild = True
+        if rebuild:
+            names = list(h.columns) if h.token == token else []
+            dists = list(h.dists) if h.token == token else []
+            for name, d in search_space.items():
+                if name in names:
+                    dists[names.index(name)] = d
+                else:
+                    names.append(name)
+                    dists.append(d)
+            h.columns = {name: j for j, name in enumerate(names)}
+            h.dists = dists
+            h.token = token
+            eng.set_space([_spec_of(nm, d, self._cat_dist_funcs) for nm, d in zip(names, dists)])
+            X, cat, key = self._rows(study, trials, names, dists)
+            eng.set_history(X, cat, key)
+        elif len(trials) > h.n:
+            names = list(h.columns)
+            X, cat, key = self._rows(study, trials[h.n:], names, h.dists)
+            eng.append_history(X, cat, key)
+        h.n = len(trials)
+        h.last_number = trials[-1].number if trials else -1
+        h.n_finished = sum(t.state != TrialState.RUNNING for t in trials) if self._constant_liar else len(trials)
+        return h.n_finished, [h.columns[name] for name in search_space]
+
+    def _draw_uniforms(self, search_space: dict[str, BaseDistribution]) -> np.ndarray:
+        rng = self._rng.rng
+        c = self._n_ei_candidates
+        parts = [rng.rand(c)]
+        n_num = 0
+        for d in search_space.values():
+            if isinstance(d, CategoricalDistribution):
+                parts.append(rng.rand(c))
+            else:
+                n_num += 1
+        if n_num:
+            parts.append(rng.uniform(low=0, high=1, size=(n_num, c)).ravel())
+        return np.concatenate(parts)
+
+    def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
+        """TPESampler._sample (sampler.py:523-560)."""
+        if study._is_multi_objective():
+            raise NotImplementedError("multi-objective TPE is not built yet (SURVEY.md section 8 a13/a14).")
+        with self._lock:
+            n_finished, cols = self._sync(study, trial, search_space)
+            n_below = self._gamma(n_finished)
+            cfg = dict(n_below=int(n_below), n_candidates=self._n_ei_candidates, multivariate=self._multivariate,
+                       prior_weight=self._prior_weight, magic_clip=self._magic_clip, endpoints=self._endpoints)
+            if self._prior_weight < 0:
+                raise ValueError("A non-negative value must be specified for prior_weight,"
+                                 f" but got {self._prior_weight}.")
+            eng = self._eng()
+            if self._weights is default_weights:
+                u = self._draw_uniforms(search_space)
+                x, _, _ = eng.suggest(cols, u, 1, **cfg)
+            else:
+                _, nb, na = eng.prepare(cols, **cfg)
+                eng.build(_checked_weights(self._weights, nb), _checked_weights(self._weights, na))
+                u = self._draw_uniforms(search_space)
+                x, _, _ = eng.sample_and_select(u, 1)
+        out = {}
+        for j, (name, d) in enumerate(search_space.items()):
+            out[name] = d.to_external_repr(float(x[0, j]))
+        return out

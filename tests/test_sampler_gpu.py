@@ -1,0 +1,96 @@
+"""B200TPESampler driven the way the reference drives its sampler (study.optimize / ask+tell),
+checked against live-reference golden trajectories (tests/golden/branin.npz, suggest.npz)."""
+import math
+import pickle
+
+import numpy as np
+import pytest
+
+from tests._util import load
+
+pytestmark = pytest.mark.gpu
+
+
+def branin(t):
+    x = t.suggest_float("x", -5, 10)
+    y = t.suggest_float("y", 0, 15)
+    return ((y - 5.1 / (4 * math.pi**2) * x * x + 5 / math.pi * x - 6) ** 2
+            + 10 * (1 - 1 / (8 * math.pi)) * math.cos(x) + 10)
+
+
+@pytest.mark.parametrize("mv", [False, True])
+def test_branin_200_trials_matches_reference_trajectory(mv):
+    """BASELINE config 1: same seed => same 200-trial trajectory as optuna.samplers.TPESampler."""
+    from optuna_b200 import B200TPESampler, mini
+    g = load("branin.npz")
+    tag = "mv" if mv else "uni"
+    study = mini.create_study(sampler=B200TPESampler(seed=0, multivariate=mv))
+    study.optimize(branin, n_trials=200)
+    xy = np.asarray([[t.params["x"], t.params["y"]] for t in study.trials])
+    ref = g[f"branin_{tag}/xy"]
+    # startup trials (RandomSampler stream) are bit-identical
+    assert np.array_equal(xy[:10], ref[:10])
+    np.testing.assert_allclose(xy, ref, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose([t.value for t in study.trials], g[f"branin_{tag}/values"], rtol=1e-8, atol=1e-8)
+    if not mv:
+        assert abs(study.best_value - 0.4069652013131506) < 1e-9
+
+
+def test_sampler_contract_types_and_ranges():
+    """optuna/testing/pytest_samplers.py:81-491 in miniature: python-native return types, values in
+    range for every distribution kind, uni- and multivariate, n_startup_trials=0."""
+    from optuna_b200 import B200TPESampler, mini
+
+    def obj(t):
+        a = t.suggest_float("a", -1.0, 1.0)
+        b = t.suggest_float("b", 1e-3, 10.0, log=True)
+        c = t.suggest_float("c", 0.0, 2.0, step=0.25)
+        d = t.suggest_int("d", -3, 7)
+        e = t.suggest_int("e", 1, 64, log=True)
+        f = t.suggest_int("f", 0, 30, step=5)
+        g = t.suggest_categorical("g", ["p", "q", None, 3])
+        assert type(a) is float and type(b) is float and type(c) is float
+        assert type(d) is int and type(e) is int and type(f) is int
+        assert -1 <= a <= 1 and 1e-3 <= b <= 10 and c in np.arange(0, 2.01, 0.25)
+        assert -3 <= d <= 7 and 1 <= e <= 64 and f in range(0, 31, 5) and g in ["p", "q", None, 3]
+        return a * a + math.log(b) ** 2 + c + d * 0.1 + (g == "p")
+
+    for mv in (False, True):
+        s = mini.create_study(sampler=B200TPESampler(seed=3, multivariate=mv, n_startup_trials=0))
+        s.optimize(obj, n_trials=25)
+        assert len(s.trials) == 25
+
+
+def test_reproducible_and_picklable():
+    from optuna_b200 import B200TPESampler, mini
+
+    def run(sampler):
+        s = mini.create_study(sampler=sampler, direction="maximize")
+        s.optimize(lambda t: -(t.suggest_float("x", 0, 1) - 0.3) ** 2 + t.suggest_int("k", 0, 5) * 0.0, n_trials=30)
+        return [t.params for t in s.trials]
+
+    a = run(B200TPESampler(seed=11))
+    b = run(pickle.loads(pickle.dumps(B200TPESampler(seed=11))))
+    assert a == b
+    assert run(B200TPESampler(seed=12)) != a
+
+
+def test_custom_weights_gamma_pruned_constraints_run():
+    from optuna_b200 import B200TPESampler, mini
+
+    def obj(t):
+        x = t.suggest_float("x", -3, 3)
+        t.set_user_attr("c", x - 1.0)
+        if t.number % 5 == 4:
+            t.report(abs(x), 1)
+            raise mini.TrialPruned()
+        return x * x
+
+    sampler = B200TPESampler(seed=1, gamma=lambda n: max(1, n // 4), weights=lambda n: np.arange(1, n + 1) ** 0.5,
+                             constraints_func=lambda tr: (tr.user_attrs["c"],), n_startup_trials=5)
+    s = mini.create_study(sampler=sampler)
+    s.optimize(obj, n_trials=40)
+    assert len(s.trials) == 40
+    with pytest.raises(ValueError):
+        bad = mini.create_study(sampler=B200TPESampler(seed=1, weights=lambda n: -np.ones(n), n_startup_trials=2))
+        bad.optimize(lambda t: t.suggest_float("x", 0, 1), n_trials=5)
