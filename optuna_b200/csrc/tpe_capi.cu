@@ -58,10 +58,11 @@ struct DevBuf {
 
 struct Estimator {
   int64_t n = 0, K = 0;
-  DevBuf rows, pos, wstage, w, logw, cdf, mu, sigma, cst_part, cst, kpf, tab, part, fix;
+  DevBuf rows, pos, wstage, w, logw, cdf, mu, sigma, cst_part, cst, tabp, tabc, colprm, tab, part, fix;
   int nsplit = 0;
   void release() {
-    for (DevBuf* b : {&rows, &pos, &wstage, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &kpf, &tab, &part, &fix})
+    for (DevBuf* b : {&rows, &pos, &wstage, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
+                      &part, &fix})
       b->release();
   }
 };
@@ -96,6 +97,7 @@ struct tpe_ctx {
   int32_t pc = 0, ncont = 0, ndisc = 0, ncat = 0, nnum = 0, pb = 0;
   int64_t tab_doubles = 0;
   bool fast = false;
+  int fast_mode = 0;  // 0 generic, 1 PAIR (sigma per kernel), 2 CONST (sigma per column)
   tpe_split_info info{};
   DevBuf row_ok, member, cand_a, cand_b, counts;
   Estimator est[2];
@@ -142,38 +144,53 @@ constexpr T round_up(T v, T m) { return (v + m - 1) / m * m; }
 
 // ---- fast-kernel configuration table ------------------------------------------------------------
 struct FastCfg {
-  int pb, rc, nt, tk, st;
+  int pb, rc, nt, tk, st, minb;
   size_t smem;
-  void (*launch)(dim3, size_t, cudaStream_t, const double2*, const double*, int64_t, const double*, int64_t,
-                 int64_t, double2*);
+  void (*launch)(dim3, size_t, cudaStream_t, const void*, const double*, int64_t, const double2*, const double*,
+                 int64_t, int64_t, double2*);
   cudaError_t (*prepare)();
 };
 
-template <int PB, int RC, int NT, int TK, int ST>
+template <int PB, int RC, int NT, int TK, int ST, bool PAIR, int MINB>
 struct FastInst {
-  static constexpr size_t smem = (size_t)ST * TK * PB * 16 + (size_t)ST * TK * 8 + (size_t)ST * 8;
-  static void launch(dim3 grid, size_t sm, cudaStream_t st, const double2* kpf, const double* cst, int64_t K,
-                     const double* xT, int64_t ct_stride, int64_t kps, double2* part) {
-    k_logpdf_fast<PB, RC, NT, TK, ST><<<grid, NT, sm, st>>>(kpf, cst, K, xT, ct_stride, kps, part);
+  static constexpr size_t smem = (size_t)ST * TK * PB * (PAIR ? 16 : 8) + (size_t)ST * TK * 8 + (size_t)ST * 8;
+  static void launch(dim3 grid, size_t sm, cudaStream_t st, const void* tab, const double* cst, int64_t Kf,
+                     const double2* colprm, const double* xT, int64_t ct_stride, int64_t kps, double2* part) {
+    k_logpdf_fast<PB, RC, NT, TK, ST, PAIR, MINB><<<grid, NT, sm, st>>>(tab, cst, Kf, colprm, xT, ct_stride, kps, part);
   }
   static cudaError_t prepare() {
-    return cudaFuncSetAttribute(k_logpdf_fast<PB, RC, NT, TK, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem);
+    return cudaFuncSetAttribute(k_logpdf_fast<PB, RC, NT, TK, ST, PAIR, MINB>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  static FastCfg cfg() { return FastCfg{PB, RC, NT, TK, ST, smem, &launch, &prepare}; }
+  static FastCfg cfg() { return FastCfg{PB, RC, NT, TK, ST, MINB, smem, &launch, &prepare}; }
 };
 
-// "big": many candidates (c-tiles of NT*RC); "small": a single ask with few candidates, the whole
-// grid is spent on splitting the kernel axis.
-const FastCfg kFastBig[] = {
-    FastInst<1, 4, 256, 2048, 3>::cfg(),  FastInst<2, 4, 256, 1024, 3>::cfg(), FastInst<4, 4, 256, 512, 3>::cfg(),
-    FastInst<8, 4, 256, 256, 3>::cfg(),   FastInst<16, 2, 256, 128, 3>::cfg(), FastInst<32, 2, 256, 64, 3>::cfg(),
-    FastInst<64, 1, 256, 32, 3>::cfg(),
+// "big": many candidates (c-tiles of NT*RC candidates, kernels split over blockIdx.y);
+// "small": a single ask with few candidates -- one warp per CTA, the grid splits the kernel axis.
+// CONST = one sigma per column (multivariate TPE), PAIR = sigma per kernel (univariate TPE).
+const FastCfg kConstBig[] = {
+    FastInst<1, 4, 256, 2048, 3, false, 2>::cfg(), FastInst<2, 4, 256, 1024, 3, false, 2>::cfg(),
+    FastInst<4, 4, 256, 1024, 3, false, 2>::cfg(), FastInst<8, 4, 256, 512, 3, false, 2>::cfg(),
+    FastInst<16, 2, 256, 256, 3, false, 2>::cfg(), FastInst<32, 1, 256, 128, 3, false, 2>::cfg(),
+    FastInst<64, 1, 256, 64, 3, false, 1>::cfg(),
 };
-const FastCfg kFastSmall[] = {
-    FastInst<1, 1, 32, 512, 2>::cfg(), FastInst<2, 1, 32, 256, 2>::cfg(), FastInst<4, 1, 32, 128, 2>::cfg(),
-    FastInst<8, 1, 32, 64, 2>::cfg(),  FastInst<16, 1, 32, 32, 2>::cfg(), FastInst<32, 1, 32, 16, 2>::cfg(),
-    FastInst<64, 1, 32, 8, 2>::cfg(),
+const FastCfg kPairBig[] = {
+    FastInst<1, 4, 256, 1024, 3, true, 2>::cfg(), FastInst<2, 4, 256, 1024, 3, true, 1>::cfg(),
+    FastInst<4, 4, 256, 512, 3, true, 2>::cfg(),  FastInst<8, 4, 256, 256, 3, true, 2>::cfg(),
+    FastInst<16, 2, 256, 128, 3, true, 2>::cfg(), FastInst<32, 2, 256, 64, 3, true, 1>::cfg(),
+    FastInst<64, 1, 256, 32, 3, true, 1>::cfg(),
+};
+const FastCfg kConstSmall[] = {
+    FastInst<1, 1, 32, 1024, 2, false, 1>::cfg(), FastInst<2, 1, 32, 512, 2, false, 1>::cfg(),
+    FastInst<4, 1, 32, 256, 2, false, 1>::cfg(),  FastInst<8, 1, 32, 128, 2, false, 1>::cfg(),
+    FastInst<16, 1, 32, 64, 2, false, 1>::cfg(),  FastInst<32, 1, 32, 32, 2, false, 1>::cfg(),
+    FastInst<64, 1, 32, 16, 2, false, 1>::cfg(),
+};
+const FastCfg kPairSmall[] = {
+    FastInst<1, 1, 32, 512, 2, true, 1>::cfg(), FastInst<2, 1, 32, 256, 2, true, 1>::cfg(),
+    FastInst<4, 1, 32, 128, 2, true, 1>::cfg(), FastInst<8, 1, 32, 64, 2, true, 1>::cfg(),
+    FastInst<16, 1, 32, 32, 2, true, 1>::cfg(), FastInst<32, 1, 32, 16, 2, true, 1>::cfg(),
+    FastInst<64, 1, 32, 8, 2, true, 1>::cfg(),
 };
 constexpr int kMaxFastP = 64;
 
@@ -182,8 +199,9 @@ int pick_pb(int ncont) {
     if (ncont <= pb) return pb;
   return 0;
 }
-const FastCfg* pick_fast(int pb, int64_t Ct) {
-  const FastCfg* tabs = (Ct <= 128) ? kFastSmall : kFastBig;
+const FastCfg* pick_fast(int mode, int pb, int64_t Ct) {
+  const bool small = Ct <= 128;
+  const FastCfg* tabs = (mode == 2) ? (small ? kConstSmall : kConstBig) : (small ? kPairSmall : kPairBig);
   for (int i = 0; i < 7; ++i)
     if (tabs[i].pb == pb) return &tabs[i];
   return nullptr;
@@ -236,7 +254,9 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
   CU(e.w.ensure((size_t)K * 8));
   CU(e.logw.ensure((size_t)K * 8));
   CU(e.cdf.ensure((size_t)K * 8));
-  if (ctx->fast) CU(e.kpf.ensure((size_t)K * ctx->pb * 16));
+  if (ctx->fast_mode == 1) CU(e.tabp.ensure((size_t)K * ctx->pb * 16 + 16));
+  if (ctx->fast_mode == 2) CU(e.tabc.ensure((size_t)K * ctx->pb * 8 + 16));
+  if (ctx->fast) CU(e.colprm.ensure((size_t)ctx->pb * 16));
   if (ctx->tab_doubles) CU(e.tab.ensure((size_t)ctx->tab_doubles * 8));
 
   k_mu<<<grid_for(K * pc, 256, cap), 256, 0, st>>>(ctx->X.as<double>(), (int32_t)ctx->space.size(),
@@ -276,14 +296,15 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
     }
   }
   if (ctx->fast && ctx->pb > ctx->ncont) {
-    k_kpf_pad<<<grid_for(K * (ctx->pb - ctx->ncont), 256, cap), 256, 0, st>>>(e.kpf.as<double2>(), K, ctx->pb,
-                                                                              ctx->ncont);
+    k_tab_pad<<<grid_for(K * (ctx->pb - ctx->ncont), 256, cap), 256, 0, st>>>(
+        ctx->fast_mode == 1 ? e.tabp.as<double2>() : nullptr, ctx->fast_mode == 2 ? e.tabc.as<double>() : nullptr,
+        e.colprm.as<double2>(), ctx->fast_mode == 2 ? K - 1 : K, ctx->pb, ctx->ncont);
     ctx->launch_counter++;
   }
   k_const<<<grid_for(K * 32, 256, cap), 256, 0, st>>>(e.mu.as<double>(), e.sigma.as<double>(),
-                                                      ctx->cols.as<ColMeta>(), pc, K, ctx->pb,
-                                                      ctx->fast ? e.kpf.as<double2>() : nullptr,
-                                                      e.cst_part.as<double>());
+                                                      ctx->cols.as<ColMeta>(), pc, K, ctx->pb, ctx->fast_mode,
+                                                      e.tabp.as<double2>(), e.tabc.as<double>(),
+                                                      e.colprm.as<double2>(), e.cst_part.as<double>());
   ctx->launch_counter++;
   const double* w_dev = nullptr;
   if (w_host != nullptr && n > 0) {
@@ -311,29 +332,46 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
   cudaStream_t st = ctx->stream;
   const int64_t K = e.K;
   if (ctx->fast) {
-    const FastCfg* fc = pick_fast(ctx->pb, Ct);
+    const FastCfg* fc = pick_fast(ctx->fast_mode, ctx->pb, Ct);
+    const bool cst_mode = ctx->fast_mode == 2;
+    const int64_t Kf = cst_mode ? K - 1 : K;  // CONST tables exclude the prior kernel (its sigma differs)
     const int tc = fc->nt * fc->rc;
     const int64_t ctiles = (Ct + tc - 1) / tc;
-    // k-splits: fill the machine (one CTA per SM for the big configuration, several for small)
-    const int64_t ktiles = (K + fc->tk - 1) / fc->tk;
-    const int64_t target = (fc->nt >= 256) ? (int64_t)ctx->sm_count * 2 : (int64_t)ctx->sm_count * 8;
-    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>(ktiles, target / ctiles));
-    int64_t tiles_per = (ktiles + nsplit - 1) / nsplit;
-    nsplit = (ktiles + tiles_per - 1) / tiles_per;
-    const int64_t kps = tiles_per * fc->tk;
-    CU(e.part.ensure((size_t)nsplit * ctx->ct_stride * 16));
-    e.nsplit = (int)nsplit;
-    CU(fc->prepare());
-    fc->launch(dim3((unsigned)ctiles, (unsigned)nsplit), fc->smem, st, e.kpf.as<double2>(), e.cst.as<double>(), K,
-               ctx->xT.as<double>(), ctx->ct_stride, kps, e.part.as<double2>());
-    ctx->launch_counter++;
-    ctx->last_kernel = (fc->nt >= 256) ? "k_logpdf_fast<big>" : "k_logpdf_fast<small>";
+    // k-splits: two full waves of resident CTAs for the big configurations
+    const int64_t ktiles = (Kf + fc->tk - 1) / fc->tk;
+    const int64_t target = (fc->nt >= 256) ? (int64_t)ctx->sm_count * fc->minb * 2 : (int64_t)ctx->sm_count * 8;
+    int64_t nsplit = 0, kps = fc->tk;
+    if (ktiles > 0) {
+      nsplit = std::max<int64_t>(1, std::min<int64_t>(ktiles, target / ctiles));
+      const int64_t tiles_per = (ktiles + nsplit - 1) / nsplit;
+      nsplit = (ktiles + tiles_per - 1) / tiles_per;
+      kps = tiles_per * fc->tk;
+    }
+    CU(e.part.ensure((size_t)(nsplit + 1) * ctx->ct_stride * 16));
+    if (nsplit > 0) {
+      CU(fc->prepare());
+      fc->launch(dim3((unsigned)ctiles, (unsigned)nsplit), fc->smem, st,
+                 cst_mode ? (const void*)e.tabc.p : (const void*)e.tabp.p, e.cst.as<double>(), Kf,
+                 e.colprm.as<double2>(), ctx->xT.as<double>(), ctx->ct_stride, kps, e.part.as<double2>());
+      ctx->launch_counter++;
+    }
+    ctx->last_kernel = cst_mode ? ((fc->nt >= 256) ? "k_logpdf_fast<const,big>" : "k_logpdf_fast<const,small>")
+                                : ((fc->nt >= 256) ? "k_logpdf_fast<pair,big>" : "k_logpdf_fast<pair,small>");
     if (after_main) CU(cudaEventRecord(after_main, st));
+    if (cst_mode) {  // the prior kernel, evaluated exactly, becomes one more partial row
+      k_logpdf_generic<<<dim3((unsigned)((Ct + 127) / 128), 1), 128, 0, st>>>(
+          ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
+          e.cst.as<double>(), K, K - 1, 1, e.tab.as<double>(), nullptr, e.part.as<double2>() + nsplit * ctx->ct_stride,
+          ctx->ct_stride);
+      ctx->launch_counter++;
+      nsplit += 1;
+    }
+    e.nsplit = (int)nsplit;
     // fix-up: exact evaluation for candidates outside [low, high] (rounding of ppf * sigma + mu)
     CU(e.fix.ensure((size_t)ctx->ct_stride * 16));
     k_logpdf_generic<<<dim3((unsigned)((Ct + 127) / 128), 1), 128, 0, st>>>(
         ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
-        e.cst.as<double>(), K, K, e.tab.as<double>(), ctx->oob.as<uint8_t>(), e.fix.as<double2>(), ctx->ct_stride);
+        e.cst.as<double>(), K, 0, K, e.tab.as<double>(), ctx->oob.as<uint8_t>(), e.fix.as<double2>(), ctx->ct_stride);
     ctx->launch_counter++;
   } else {
     const int64_t cblocks = (Ct + 127) / 128;
@@ -345,7 +383,7 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     e.nsplit = (int)nsplit;
     k_logpdf_generic<<<dim3((unsigned)cblocks, (unsigned)nsplit), 128, 0, st>>>(
         ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
-        e.cst.as<double>(), K, kps, e.tab.as<double>(), nullptr, e.part.as<double2>(), ctx->ct_stride);
+        e.cst.as<double>(), K, 0, kps, e.tab.as<double>(), nullptr, e.part.as<double2>(), ctx->ct_stride);
     ctx->launch_counter++;
     ctx->last_kernel = "k_logpdf_generic";
     if (after_main) CU(cudaEventRecord(after_main, st));
@@ -567,6 +605,7 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
   ctx->tab_doubles = tab;
   ctx->fast = (ctx->ndisc == 0 && ctx->ncat == 0 && ctx->ncont <= kMaxFastP);
   ctx->pb = ctx->fast ? pick_pb(ctx->ncont) : 0;
+  ctx->fast_mode = ctx->fast ? (cfg->multivariate ? 2 : 1) : 0;
   CU(ctx->cols.ensure(sizeof(ColMeta) * n_cols));
   CU(cudaMemcpyAsync(ctx->cols.p, ctx->cols_h.data(), sizeof(ColMeta) * n_cols, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -680,12 +719,14 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   rc = run_logpdf(ctx, 1, Ct, ctx->ev[6]);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->ev[7], st));
-  k_select<<<(unsigned)n_asks, 256, 0, st>>>(
+  k_acq<<<grid_for(Ct, 256, ctx->sm_count * 8), 256, 0, st>>>(
       ctx->est[0].part.as<double2>(), ctx->est[0].nsplit, ctx->est[1].part.as<double2>(), ctx->est[1].nsplit,
       ctx->ct_stride, ctx->fast ? ctx->oob.as<uint8_t>() : nullptr, ctx->est[0].fix.as<double2>(),
-      ctx->est[1].fix.as<double2>(), C, ctx->S.as<double>(), ctx->pc, ctx->logl.as<double>(), ctx->logg.as<double>(),
-      ctx->out_x.as<double>(), ctx->out_acq.as<double>(), ctx->out_best.as<int64_t>());
-  ctx->launch_counter++;
+      ctx->est[1].fix.as<double2>(), Ct, ctx->logl.as<double>(), ctx->logg.as<double>());
+  k_select<<<(unsigned)n_asks, 256, 0, st>>>(ctx->logl.as<double>(), ctx->logg.as<double>(), C, ctx->S.as<double>(),
+                                             ctx->pc, ctx->out_x.as<double>(), ctx->out_acq.as<double>(),
+                                             ctx->out_best.as<int64_t>());
+  ctx->launch_counter += 2;
   CU(cudaEventRecord(ctx->ev[8], st));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_asks * ctx->pc * 8, cudaMemcpyDeviceToHost, st));

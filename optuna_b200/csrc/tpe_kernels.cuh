@@ -10,6 +10,8 @@
 //                            optuna/samplers/_tpe/_truncnorm.py:286-297
 //   k_select                 optuna/samplers/_tpe/sampler.py:591-618
 #pragma once
+#include <type_traits>
+
 #include "tpe_common.cuh"
 #include "tpe_math.cuh"
 
@@ -190,6 +192,9 @@ __device__ __forceinline__ void sigma_limits(const ColMeta& cm, int64_t n, bool 
 __global__ void k_sigma_mv(const ColMeta* __restrict__ cols, int32_t pc, int64_t n, int magic_clip,
                            double* __restrict__ sigma) {
   const int64_t total = (n + 1) * pc;
+  // the bandwidth factor is the same for every cell: one pow() per thread, not per cell
+  const double e = TPE_DIV(-1.0, (double)(pc + 4));
+  const double factor = TPE_MUL(0.2, pow((double)(n > 1 ? n : 1), e));
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t k = t / pc;
     const int j = (int)(t - k * pc);
@@ -200,15 +205,7 @@ __global__ void k_sigma_mv(const ColMeta* __restrict__ cols, int32_t pc, int64_t
     }
     double lo, hi;
     sigma_limits(cm, n, magic_clip != 0, lo, hi);
-    if (k == n) {
-      sigma[t] = hi;
-      continue;
-    }
-    const double e = TPE_DIV(-1.0, (double)(pc + 4));
-    const double base = (double)(n > 1 ? n : 1);
-    double s = TPE_MUL(TPE_MUL(0.2, pow(base, e)), hi);
-    s = fmin(fmax(s, lo), hi);
-    sigma[t] = s;
+    sigma[t] = (k == n) ? hi : fmin(fmax(TPE_MUL(factor, hi), lo), hi);
   }
 }
 
@@ -308,10 +305,17 @@ k_sort_small(const double* __restrict__ mu, int32_t pc, int j_col, int m, int m2
 // Per-(kernel, column) constants.  One warp per kernel; lanes stride over columns.
 //   continuous: c = ln sqrt(2 pi) + M(a, b) + ln sigma      (a, b = normalised support)
 //   discrete  : c = M(a, b) over the half-step-extended support
-//   cst_part[k] = -sum_j c ;  kpf[k][slot] = (mu, 1 / sigma) for continuous columns.
+//   cst_part[k] = -sum_j c
+// Fast-kernel tables, in coordinates centred on the column midpoint c_p (so that magnitudes are
+// bounded by range / sigma and the scaled difference keeps ~1e-15 absolute accuracy):
+//   mode 1 (PAIR,  sigma varies per kernel): tabp[k][slot] = ((mu - c_p) / sigma_kp, 1 / sigma_kp)
+//   mode 2 (CONST, sigma_p shared by all observation kernels -- multivariate TPE):
+//                                            tabc[k][slot] = (mu - c_p) / sigma_p   for k < K - 1
+//   colprm[slot] = (c_p, 1 / sigma_p) (CONST) or (c_p, 1) (PAIR); padded slots are zero.
 __global__ void k_const(const double* __restrict__ mu, const double* __restrict__ sigma,
-                        const ColMeta* __restrict__ cols, int32_t pc, int64_t K, int32_t pb,
-                        double2* __restrict__ kpf, double* __restrict__ cst_part) {
+                        const ColMeta* __restrict__ cols, int32_t pc, int64_t K, int32_t pb, int mode,
+                        double2* __restrict__ tabp, double* __restrict__ tabc, double2* __restrict__ colprm,
+                        double* __restrict__ cst_part) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -326,7 +330,17 @@ __global__ void k_const(const double* __restrict__ mu, const double* __restrict_
       const double mass = log_gauss_mass(a, b);
       if (cm.cls == COL_CONT) {
         acc += kLogSqrt2Pi + mass + log(s);
-        if (kpf != nullptr) kpf[k * pb + cm.slot] = make_double2(m, TPE_DIV(1.0, s));
+        if (mode != 0) {
+          const double ctr = TPE_MUL(0.5, TPE_ADD(cm.klow, cm.khigh));
+          const double inv = TPE_DIV(1.0, s);
+          if (mode == 1) {
+            tabp[k * pb + cm.slot] = make_double2(TPE_MUL(TPE_SUB(m, ctr), inv), inv);
+            if (k == 0) colprm[cm.slot] = make_double2(ctr, 1.0);
+          } else {
+            if (k < K - 1) tabc[k * pb + cm.slot] = TPE_MUL(TPE_SUB(m, ctr), inv);
+            if (k == 0) colprm[cm.slot] = make_double2(ctr, inv);
+          }
+        }
       } else {
         acc += mass;
       }
@@ -335,13 +349,19 @@ __global__ void k_const(const double* __restrict__ mu, const double* __restrict_
     if (lane == 0) cst_part[k] = -acc;
   }
 }
-__global__ void k_kpf_pad(double2* __restrict__ kpf, int64_t K, int32_t pb, int32_t ncont) {
-  const int64_t total = K * (pb - ncont);
+// zero the padded slots [ncont, pb) of the fast tables
+__global__ void k_tab_pad(double2* __restrict__ tabp, double* __restrict__ tabc, double2* __restrict__ colprm,
+                          int64_t rows, int32_t pb, int32_t ncont) {
+  const int w = pb - ncont;
+  const int64_t total = rows * w;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t k = t / (pb - ncont);
-    const int s = ncont + (int)(t - k * (pb - ncont));
-    kpf[k * pb + s] = make_double2(0.0, 0.0);
+    const int64_t k = t / w;
+    const int sl = ncont + (int)(t - k * w);
+    if (tabp) tabp[k * pb + sl] = make_double2(0.0, 0.0);
+    if (tabc) tabc[k * pb + sl] = 0.0;
   }
+  if (blockIdx.x == 0)
+    for (int sl = ncont + threadIdx.x; sl < pb; sl += blockDim.x) colprm[sl] = make_double2(0.0, 0.0);
 }
 
 // Mixture weights (parzen_estimator.py:59-69, sampler.py:61-69).  Single CTA of 1024 threads.
@@ -557,14 +577,14 @@ __device__ __forceinline__ double cell_sum_exact(const double* __restrict__ xrow
 // only_flagged != nullptr restricts the work to candidates with only_flagged[ct] != 0 (fix-up pass).
 __global__ void k_logpdf_generic(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols, int32_t pc,
                                  const double* __restrict__ mu, const double* __restrict__ sigma,
-                                 const double* __restrict__ cst, int64_t K, int64_t kps, const double* __restrict__ tab,
-                                 const uint8_t* __restrict__ only_flagged, double2* __restrict__ part,
-                                 int64_t ct_stride) {
+                                 const double* __restrict__ cst, int64_t K, int64_t k_begin, int64_t kps,
+                                 const double* __restrict__ tab, const uint8_t* __restrict__ only_flagged,
+                                 double2* __restrict__ part, int64_t ct_stride) {
   const int64_t ct = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (ct >= Ct) return;
   double m = -INFINITY, s = 0.0;
   if (only_flagged == nullptr || only_flagged[ct] != 0) {
-    const int64_t k0 = blockIdx.y * kps;
+    const int64_t k0 = k_begin + blockIdx.y * kps;
     const int64_t k1 = (k0 + kps < K) ? k0 + kps : K;
     const double* xrow = S + ct * pc;
     for (int64_t k = k0; k < k1; ++k) {
@@ -577,20 +597,27 @@ __global__ void k_logpdf_generic(const double* __restrict__ S, int64_t Ct, const
 
 // Fast path: every selected column continuous.  lane = candidate, kernels streamed through shared
 // memory by TMA bulk copies (mbarrier completion), online log-sum-exp in registers.
-//   kpf  [K][PB]  (mu, 1/sigma), zero padded;  cst [K(+pad)]
+// Two fp64 instructions per (candidate, kernel, param) cell:
+//   PAIR : t = fma(x', s_kp, -mu_s)      CONST: t = x'' - mu_s       then acc = fma(t, t, acc)
+// with x' = x - c_p, x'' = (x - c_p) / sigma_p prepared once per candidate in the prologue.
+//   tab  [Kf][PB]  double2 (PAIR) or double (CONST), zero padded;  cst [Kf(+pad)]
 //   xT   [PB][ct_stride] kernel-space candidate coordinates (zero padded)
 //   part [gridDim.y][ct_stride] (running max, running sum)
-template <int PB, int RC, int NT, int TK, int ST>
-__global__ void __launch_bounds__(NT, 1)
-k_logpdf_fast(const double2* __restrict__ kpf, const double* __restrict__ cst, int64_t K,
-              const double* __restrict__ xT, int64_t ct_stride, int64_t kps, double2* __restrict__ part) {
+template <int PB, int RC, int NT, int TK, int ST, bool PAIR, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_logpdf_fast(const void* __restrict__ tab_v, const double* __restrict__ cst, int64_t Kf,
+              const double2* __restrict__ colprm, const double* __restrict__ xT, int64_t ct_stride, int64_t kps,
+              double2* __restrict__ part) {
+  using Elem = typename std::conditional<PAIR, double2, double>::type;
+  constexpr int ES = PAIR ? 16 : 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double2* tiles = reinterpret_cast<double2*>(smem_raw);                       // ST * TK * PB
-  double* csts = reinterpret_cast<double*>(tiles + (size_t)ST * TK * PB);      // ST * TK
-  uint64_t* full = reinterpret_cast<uint64_t*>(csts + (size_t)ST * TK);        // ST
+  Elem* tiles = reinterpret_cast<Elem*>(smem_raw);                                 // ST * TK * PB
+  double* csts = reinterpret_cast<double*>(smem_raw + (size_t)ST * TK * PB * ES);  // ST * TK
+  uint64_t* full = reinterpret_cast<uint64_t*>(csts + (size_t)ST * TK);            // ST
+  const Elem* tab = reinterpret_cast<const Elem*>(tab_v);
   const int tid = threadIdx.x;
   const int64_t k0 = blockIdx.y * kps;
-  const int64_t k1 = (k0 + kps < K) ? k0 + kps : K;
+  const int64_t k1 = (k0 + kps < Kf) ? k0 + kps : Kf;
   const int ntiles = (k1 > k0) ? (int)((k1 - k0 + TK - 1) / TK) : 0;
   const int64_t cbase = (int64_t)blockIdx.x * (NT * RC);
 
@@ -604,11 +631,11 @@ k_logpdf_fast(const double2* __restrict__ kpf, const double* __restrict__ cst, i
     const int st = t % ST;
     const int64_t ks = k0 + (int64_t)t * TK;
     const int tk = (int)((k1 - ks < TK) ? (k1 - ks) : TK);
-    const uint32_t b_tile = (uint32_t)tk * PB * 16u;
+    const uint32_t b_tile = (uint32_t)(((size_t)tk * PB * ES + 15) & ~(size_t)15);
     const uint32_t b_cst = (uint32_t)(((tk + 1) & ~1) * 8);
     fence_proxy_async();
     mbar_expect_tx(&full[st], b_tile + b_cst);
-    bulk_g2s(tiles + (size_t)st * TK * PB, kpf + ks * PB, b_tile, &full[st]);
+    bulk_g2s(tiles + (size_t)st * TK * PB, tab + ks * PB, b_tile, &full[st]);
     bulk_g2s(csts + (size_t)st * TK, cst + ks, b_cst, &full[st]);
   };
   if (tid == 0) {
@@ -617,16 +644,20 @@ k_logpdf_fast(const double2* __restrict__ kpf, const double* __restrict__ cst, i
 
   double x[RC][PB];
 #pragma unroll
-  for (int r = 0; r < RC; ++r) {
-    const int64_t ct = cbase + (int64_t)r * NT + tid;
+  for (int p = 0; p < PB; ++p) {
+    const double2 cp = colprm[p];
 #pragma unroll
-    for (int p = 0; p < PB; ++p) x[r][p] = xT[(int64_t)p * ct_stride + ct];
+    for (int r = 0; r < RC; ++r) {
+      const int64_t ct = cbase + (int64_t)r * NT + tid;
+      x[r][p] = (xT[(int64_t)p * ct_stride + ct] - cp.x) * cp.y;
+    }
   }
-  double mx[RC], sm[RC];
+  double mx[RC], sm[RC], thr[RC];
 #pragma unroll
   for (int r = 0; r < RC; ++r) {
     mx[r] = -INFINITY;
     sm[r] = 0.0;
+    thr[r] = -INFINITY;
   }
 
   for (int t = 0; t < ntiles; ++t) {
@@ -635,31 +666,62 @@ k_logpdf_fast(const double2* __restrict__ kpf, const double* __restrict__ cst, i
     mbar_wait(&full[st], (uint32_t)((t / ST) & 1));
     const int64_t ks = k0 + (int64_t)t * TK;
     const int tk = (int)((k1 - ks < TK) ? (k1 - ks) : TK);
-    const double2* tile = tiles + (size_t)st * TK * PB;
+    const Elem* tile = tiles + (size_t)st * TK * PB;
     const double* ctile = csts + (size_t)st * TK;
     for (int kk = 0; kk < tk; ++kk) {
-      const double2* row = tile + (size_t)kk * PB;
       double acc0[RC], acc1[RC];
 #pragma unroll
       for (int r = 0; r < RC; ++r) {
         acc0[r] = 0.0;
         acc1[r] = 0.0;
       }
+      if constexpr (PAIR) {
+        const double2* row = reinterpret_cast<const double2*>(tile) + (size_t)kk * PB;
 #pragma unroll
-      for (int p = 0; p < PB; ++p) {
-        const double2 v = row[p];
+        for (int p = 0; p < PB; ++p) {
+          const double2 v = row[p];
+#pragma unroll
+          for (int r = 0; r < RC; ++r) {
+            const double d = fma(x[r][p], v.y, -v.x);
+            if (p & 1) acc1[r] = fma(d, d, acc1[r]);
+            else acc0[r] = fma(d, d, acc0[r]);
+          }
+        }
+      } else if constexpr (PB == 1) {
+        const double v = reinterpret_cast<const double*>(tile)[kk];
 #pragma unroll
         for (int r = 0; r < RC; ++r) {
-          const double d = (x[r][p] - v.x) * v.y;
-          if (p & 1) acc1[r] = fma(d, d, acc1[r]);
-          else acc0[r] = fma(d, d, acc0[r]);
+          const double d = x[r][0] - v;
+          acc0[r] = d * d;
+        }
+      } else {
+        const double2* row =
+            reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tile) + (size_t)kk * PB);
+#pragma unroll
+        for (int q = 0; q < PB / 2; ++q) {
+          const double2 v = row[q];
+#pragma unroll
+          for (int r = 0; r < RC; ++r) {
+            const double d0 = x[r][2 * q] - v.x;
+            const double d1 = x[r][2 * q + 1] - v.y;
+            acc0[r] = fma(d0, d0, acc0[r]);
+            acc1[r] = fma(d1, d1, acc1[r]);
+          }
         }
       }
       const double c = ctile[kk];
 #pragma unroll
       for (int r = 0; r < RC; ++r) {
         const double L = fma(-0.5, acc0[r] + acc1[r], c);
-        lse_push(L, mx[r], sm[r]);
+        if (L > thr[r]) {  // within kLseSkip of the running max (or a new max)
+          if (L > mx[r]) {
+            sm[r] = sm[r] * exp(mx[r] - L) + 1.0;
+            mx[r] = L;
+            thr[r] = L - kLseSkip;
+          } else {
+            sm[r] += exp(L - mx[r]);
+          }
+        }
       }
     }
     __syncthreads();  // stage `st` may be refilled by the next iteration's issue()
@@ -674,23 +736,13 @@ k_logpdf_fast(const double2* __restrict__ kpf, const double* __restrict__ cst, i
 // ================================================================================================
 // acquisition + argmax
 // ================================================================================================
-// One CTA per ask.  logl/logg = merge of the k-split partials (or the fix-up value for
-// out-of-support candidates), acq = logl - logg, best = first maximum (NaN wins, like np.argmax).
-__global__ void __launch_bounds__(256)
-k_select(const double2* __restrict__ part_l, int nsl, const double2* __restrict__ part_g, int nsg,
-         int64_t ct_stride, const uint8_t* __restrict__ oob, const double2* __restrict__ fix_l,
-         const double2* __restrict__ fix_g, int32_t C, const double* __restrict__ S, int32_t pc,
-         double* __restrict__ logl, double* __restrict__ logg, double* __restrict__ out_x,
-         double* __restrict__ out_acq, int64_t* __restrict__ out_best) {
-  __shared__ double s_val[256];
-  __shared__ int s_idx[256];
-  const int64_t ask = blockIdx.x;
-  const int tid = threadIdx.x;
-  double best = 0.0;
-  int besti = -1;
-  bool best_nan = false;
-  for (int c = tid; c < C; c += 256) {
-    const int64_t ct = ask * C + c;
+// Grid-wide pass: logl/logg = merge of the k-split partials (or the fix-up value for
+// out-of-support candidates), written for every candidate.
+__global__ void k_acq(const double2* __restrict__ part_l, int nsl, const double2* __restrict__ part_g, int nsg,
+                      int64_t ct_stride, const uint8_t* __restrict__ oob, const double2* __restrict__ fix_l,
+                      const double2* __restrict__ fix_g, int64_t Ct, double* __restrict__ logl,
+                      double* __restrict__ logg) {
+  for (int64_t ct = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ct < Ct; ct += (int64_t)gridDim.x * blockDim.x) {
     double ml = -INFINITY, sl = 0.0, mg = -INFINITY, sg = 0.0;
     if (oob != nullptr && oob[ct]) {
       ml = fix_l[ct].x; sl = fix_l[ct].y;
@@ -706,11 +758,25 @@ k_select(const double2* __restrict__ part_l, int nsl, const double2* __restrict_
       }
     }
     // np.log(sum exp(L - max)) + max, with max := 0 when it is -inf
-    const double ll = (ml == -INFINITY) ? -INFINITY : log(sl) + ml;
-    const double lg = (mg == -INFINITY) ? -INFINITY : log(sg) + mg;
-    logl[ct] = ll;
-    logg[ct] = lg;
-    const double a = ll - lg;
+    logl[ct] = (ml == -INFINITY) ? -INFINITY : log(sl) + ml;
+    logg[ct] = (mg == -INFINITY) ? -INFINITY : log(sg) + mg;
+  }
+}
+
+// One CTA per ask: acq = logl - logg, best = first maximum (NaN wins, like np.argmax).
+__global__ void __launch_bounds__(256)
+k_select(const double* __restrict__ logl, const double* __restrict__ logg, int32_t C, const double* __restrict__ S,
+         int32_t pc, double* __restrict__ out_x, double* __restrict__ out_acq, int64_t* __restrict__ out_best) {
+  __shared__ double s_val[256];
+  __shared__ int s_idx[256];
+  const int64_t ask = blockIdx.x;
+  const int tid = threadIdx.x;
+  double best = 0.0;
+  int besti = -1;
+  bool best_nan = false;
+  for (int c = tid; c < C; c += 256) {
+    const int64_t ct = ask * C + c;
+    const double a = logl[ct] - logg[ct];
     const bool a_nan = a != a;
     if (besti < 0 || (!best_nan && (a_nan || a > best))) {
       best = a;
