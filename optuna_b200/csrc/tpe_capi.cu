@@ -144,53 +144,55 @@ constexpr T round_up(T v, T m) { return (v + m - 1) / m * m; }
 
 // ---- fast-kernel configuration table ------------------------------------------------------------
 struct FastCfg {
-  int pb, rc, nt, tk, st, minb;
+  int pb, cands_per_cta, nt, tk, st, minb;
   size_t smem;
   void (*launch)(dim3, size_t, cudaStream_t, const void*, const double*, int64_t, const double2*, const double*,
                  int64_t, int64_t, double2*);
   cudaError_t (*prepare)();
 };
 
-template <int PB, int RC, int NT, int TK, int ST, bool PAIR, int MINB>
+template <int PB, int PS, int RC, int NT, int TK, int ST, bool PAIR, int MINB>
 struct FastInst {
   static constexpr size_t smem = (size_t)ST * TK * PB * (PAIR ? 16 : 8) + (size_t)ST * TK * 8 + (size_t)ST * 8;
   static void launch(dim3 grid, size_t sm, cudaStream_t st, const void* tab, const double* cst, int64_t Kf,
                      const double2* colprm, const double* xT, int64_t ct_stride, int64_t kps, double2* part) {
-    k_logpdf_fast<PB, RC, NT, TK, ST, PAIR, MINB><<<grid, NT, sm, st>>>(tab, cst, Kf, colprm, xT, ct_stride, kps, part);
+    k_logpdf_fast<PB, PS, RC, NT, TK, ST, PAIR, MINB>
+        <<<grid, NT, sm, st>>>(tab, cst, Kf, colprm, xT, ct_stride, kps, part);
   }
   static cudaError_t prepare() {
-    return cudaFuncSetAttribute(k_logpdf_fast<PB, RC, NT, TK, ST, PAIR, MINB>,
+    return cudaFuncSetAttribute(k_logpdf_fast<PB, PS, RC, NT, TK, ST, PAIR, MINB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  static FastCfg cfg() { return FastCfg{PB, RC, NT, TK, ST, MINB, smem, &launch, &prepare}; }
+  static FastCfg cfg() { return FastCfg{PB, (NT / 32) * (32 / PS) * RC, NT, TK, ST, MINB, smem, &launch, &prepare}; }
 };
 
-// "big": many candidates (c-tiles of NT*RC candidates, kernels split over blockIdx.y);
+// "big": many candidates (c-tiles of `cands_per_cta`, kernels split over blockIdx.y);
 // "small": a single ask with few candidates -- one warp per CTA, the grid splits the kernel axis.
 // CONST = one sigma per column (multivariate TPE), PAIR = sigma per kernel (univariate TPE).
+//                 PB PS RC  NT    TK ST  PAIR MINB
 const FastCfg kConstBig[] = {
-    FastInst<1, 4, 256, 2048, 3, false, 2>::cfg(), FastInst<2, 4, 256, 1024, 3, false, 2>::cfg(),
-    FastInst<4, 4, 256, 1024, 3, false, 2>::cfg(), FastInst<8, 4, 256, 512, 3, false, 2>::cfg(),
-    FastInst<16, 2, 256, 256, 3, false, 2>::cfg(), FastInst<32, 1, 256, 128, 3, false, 2>::cfg(),
-    FastInst<64, 1, 256, 64, 3, false, 1>::cfg(),
+    FastInst<1, 1, 4, 256, 2048, 3, false, 2>::cfg(), FastInst<2, 1, 4, 256, 1024, 3, false, 2>::cfg(),
+    FastInst<4, 1, 4, 256, 1024, 3, false, 1>::cfg(), FastInst<8, 1, 4, 256, 512, 3, false, 1>::cfg(),
+    FastInst<16, 1, 4, 256, 256, 3, false, 1>::cfg(), FastInst<32, 2, 4, 256, 128, 3, false, 1>::cfg(),
+    FastInst<64, 4, 4, 256, 64, 3, false, 1>::cfg(),
 };
 const FastCfg kPairBig[] = {
-    FastInst<1, 4, 256, 1024, 3, true, 2>::cfg(), FastInst<2, 4, 256, 1024, 3, true, 1>::cfg(),
-    FastInst<4, 4, 256, 512, 3, true, 2>::cfg(),  FastInst<8, 4, 256, 256, 3, true, 2>::cfg(),
-    FastInst<16, 2, 256, 128, 3, true, 2>::cfg(), FastInst<32, 2, 256, 64, 3, true, 1>::cfg(),
-    FastInst<64, 1, 256, 32, 3, true, 1>::cfg(),
+    FastInst<1, 1, 4, 256, 1024, 3, true, 2>::cfg(), FastInst<2, 1, 4, 256, 1024, 3, true, 1>::cfg(),
+    FastInst<4, 1, 4, 256, 512, 3, true, 1>::cfg(),  FastInst<8, 1, 4, 256, 256, 3, true, 1>::cfg(),
+    FastInst<16, 1, 4, 256, 128, 3, true, 1>::cfg(), FastInst<32, 1, 2, 256, 64, 3, true, 1>::cfg(),
+    FastInst<64, 1, 1, 256, 32, 3, true, 1>::cfg(),
 };
 const FastCfg kConstSmall[] = {
-    FastInst<1, 1, 32, 1024, 2, false, 1>::cfg(), FastInst<2, 1, 32, 512, 2, false, 1>::cfg(),
-    FastInst<4, 1, 32, 256, 2, false, 1>::cfg(),  FastInst<8, 1, 32, 128, 2, false, 1>::cfg(),
-    FastInst<16, 1, 32, 64, 2, false, 1>::cfg(),  FastInst<32, 1, 32, 32, 2, false, 1>::cfg(),
-    FastInst<64, 1, 32, 16, 2, false, 1>::cfg(),
+    FastInst<1, 1, 1, 32, 1024, 2, false, 1>::cfg(), FastInst<2, 1, 1, 32, 512, 2, false, 1>::cfg(),
+    FastInst<4, 1, 1, 32, 256, 2, false, 1>::cfg(),  FastInst<8, 1, 1, 32, 128, 2, false, 1>::cfg(),
+    FastInst<16, 1, 1, 32, 64, 2, false, 1>::cfg(),  FastInst<32, 1, 1, 32, 32, 2, false, 1>::cfg(),
+    FastInst<64, 1, 1, 32, 16, 2, false, 1>::cfg(),
 };
 const FastCfg kPairSmall[] = {
-    FastInst<1, 1, 32, 512, 2, true, 1>::cfg(), FastInst<2, 1, 32, 256, 2, true, 1>::cfg(),
-    FastInst<4, 1, 32, 128, 2, true, 1>::cfg(), FastInst<8, 1, 32, 64, 2, true, 1>::cfg(),
-    FastInst<16, 1, 32, 32, 2, true, 1>::cfg(), FastInst<32, 1, 32, 16, 2, true, 1>::cfg(),
-    FastInst<64, 1, 32, 8, 2, true, 1>::cfg(),
+    FastInst<1, 1, 1, 32, 512, 2, true, 1>::cfg(), FastInst<2, 1, 1, 32, 256, 2, true, 1>::cfg(),
+    FastInst<4, 1, 1, 32, 128, 2, true, 1>::cfg(), FastInst<8, 1, 1, 32, 64, 2, true, 1>::cfg(),
+    FastInst<16, 1, 1, 32, 32, 2, true, 1>::cfg(), FastInst<32, 1, 1, 32, 16, 2, true, 1>::cfg(),
+    FastInst<64, 1, 1, 32, 8, 2, true, 1>::cfg(),
 };
 constexpr int kMaxFastP = 64;
 
@@ -335,7 +337,7 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     const FastCfg* fc = pick_fast(ctx->fast_mode, ctx->pb, Ct);
     const bool cst_mode = ctx->fast_mode == 2;
     const int64_t Kf = cst_mode ? K - 1 : K;  // CONST tables exclude the prior kernel (its sigma differs)
-    const int tc = fc->nt * fc->rc;
+    const int tc = fc->cands_per_cta;
     const int64_t ctiles = (Ct + tc - 1) / tc;
     // k-splits: two full waves of resident CTAs for the big configurations
     const int64_t ktiles = (Kf + fc->tk - 1) / fc->tk;

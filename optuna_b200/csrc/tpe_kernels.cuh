@@ -595,19 +595,74 @@ __global__ void k_logpdf_generic(const double* __restrict__ S, int64_t Ct, const
   part[blockIdx.y * ct_stride + ct] = make_double2(m, s);
 }
 
-// Fast path: every selected column continuous.  lane = candidate, kernels streamed through shared
-// memory by TMA bulk copies (mbarrier completion), online log-sum-exp in registers.
+// Fast path: every selected column continuous.  Kernels are streamed through shared memory by TMA
+// bulk copies (mbarrier completion); candidates live in registers; online log-sum-exp per candidate.
 // Two fp64 instructions per (candidate, kernel, param) cell:
 //   PAIR : t = fma(x', s_kp, -mu_s)      CONST: t = x'' - mu_s       then acc = fma(t, t, acc)
 // with x' = x - c_p, x'' = (x - c_p) / sigma_p prepared once per candidate in the prologue.
+//
+// Register tiling.  Every table element fetched from shared memory (the LDS return path moves
+// 128 B/clk/SM, broadcast or not) must feed enough fp64 work, so a thread owns RC candidates; for
+// wide spaces the P axis is additionally split over PS adjacent lanes (PL = PB / PS params per lane)
+// and the per-kernel partial sums are reduce-scattered with shuffles: lane h of a group ends up
+// with the full sums of candidates [h * RC / PS, (h + 1) * RC / PS) and runs their log-sum-exp.
+//
+// Deferred exp.  Only terms within kLseSkip of the running max matter; they are rare (~1 %) but a
+// warp diverges if any lane has one.  Such terms are parked in a 4-deep per-candidate register
+// buffer and folded in at tile boundaries (or when a buffer fills), where all lanes do it together.
+//
 //   tab  [Kf][PB]  double2 (PAIR) or double (CONST), zero padded;  cst [Kf(+pad)]
 //   xT   [PB][ct_stride] kernel-space candidate coordinates (zero padded)
 //   part [gridDim.y][ct_stride] (running max, running sum)
-template <int PB, int RC, int NT, int TK, int ST, bool PAIR, int MINB>
+struct LseAcc {
+  double m, s, thr, b0, b1, b2, b3;
+  int cnt;
+  __device__ __forceinline__ void init() {
+    m = -INFINITY; s = 0.0; thr = -INFINITY; b0 = b1 = b2 = b3 = 0.0; cnt = 0;
+  }
+  // branch-free fold of one parked term (valid == false leaves the accumulator untouched)
+  __device__ __forceinline__ void fold(double L, bool valid) {
+    const double d = L - m;
+    const double e = exp(-fabs(d));  // m = -inf, L finite: d = +inf -> e = 0 -> s = 1
+    const bool bigger = valid && (d > 0.0);
+    const double grown = fma(s, e, 1.0);
+    const double added = s + e;
+    s = bigger ? grown : ((valid && d == d) ? added : s);
+    m = bigger ? L : m;
+  }
+  // executed by the whole warp together (see push_sync)
+  __device__ __forceinline__ void flush() {
+    fold(b0, cnt > 0);
+    fold(b1, cnt > 1);
+    fold(b2, cnt > 2);
+    fold(b3, cnt > 3);
+    cnt = 0;
+    thr = m - kLseSkip;
+  }
+  // Park L if it is within kLseSkip of the (possibly stale, i.e. lower) running max; when any lane's
+  // buffer is full every lane folds its parked terms -- one converged pass instead of 32 diverged ones.
+  __device__ __forceinline__ void push_sync(double L) {
+    const bool hit = L > thr;
+    b3 = hit ? b2 : b3;
+    b2 = hit ? b1 : b2;
+    b1 = hit ? b0 : b1;
+    b0 = hit ? L : b0;
+    cnt += hit ? 1 : 0;
+    if (__any_sync(0xffffffffu, cnt == 4)) flush();
+  }
+};
+
+template <int PB, int PS, int RC, int NT, int TK, int ST, bool PAIR, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_logpdf_fast(const void* __restrict__ tab_v, const double* __restrict__ cst, int64_t Kf,
               const double2* __restrict__ colprm, const double* __restrict__ xT, int64_t ct_stride, int64_t kps,
               double2* __restrict__ part) {
+  static_assert(PB % PS == 0 && RC % PS == 0, "bad tiling");
+  static_assert(!PAIR || PS == 1, "PAIR tables are not split over lanes");
+  constexpr int PL = PB / PS;   // params per lane
+  constexpr int RL = RC / PS;   // candidates whose log-sum-exp this lane owns
+  constexpr int GW = 32 / PS;   // candidate groups per warp
+  constexpr int CW = GW * RC;   // candidates per warp
   using Elem = typename std::conditional<PAIR, double2, double>::type;
   constexpr int ES = PAIR ? 16 : 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -616,10 +671,14 @@ k_logpdf_fast(const void* __restrict__ tab_v, const double* __restrict__ cst, in
   uint64_t* full = reinterpret_cast<uint64_t*>(csts + (size_t)ST * TK);            // ST
   const Elem* tab = reinterpret_cast<const Elem*>(tab_v);
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int h = lane % PS;      // which slice of the params
+  const int g = lane / PS;      // candidate group inside the warp
   const int64_t k0 = blockIdx.y * kps;
   const int64_t k1 = (k0 + kps < Kf) ? k0 + kps : Kf;
   const int ntiles = (k1 > k0) ? (int)((k1 - k0 + TK - 1) / TK) : 0;
-  const int64_t cbase = (int64_t)blockIdx.x * (NT * RC);
+  // candidate r of this lane's group: wbase + r * GW + g
+  const int64_t wbase = (int64_t)blockIdx.x * ((NT / 32) * CW) + (int64_t)(tid >> 5) * CW;
 
   if (tid == 0) {
     for (int s = 0; s < ST; ++s) mbar_init(&full[s], 1);
@@ -642,23 +701,22 @@ k_logpdf_fast(const void* __restrict__ tab_v, const double* __restrict__ cst, in
     for (int t = 0; t < ST - 1 && t < ntiles; ++t) issue(t);
   }
 
-  double x[RC][PB];
+  double x[RC][PL];
+  // lane h of a group owns the 16-byte slot pairs (q * PS + h): adjacent lanes read adjacent
+  // shared-memory chunks (no bank conflicts); the sum over params does not care about the order
 #pragma unroll
-  for (int p = 0; p < PB; ++p) {
-    const double2 cp = colprm[p];
+  for (int p = 0; p < PL; ++p) {
+    const int slot = (PL == 1) ? h : 2 * ((p >> 1) * PS + h) + (p & 1);
+    const double2 cp = colprm[slot];
 #pragma unroll
     for (int r = 0; r < RC; ++r) {
-      const int64_t ct = cbase + (int64_t)r * NT + tid;
-      x[r][p] = (xT[(int64_t)p * ct_stride + ct] - cp.x) * cp.y;
+      const int64_t ct = wbase + (int64_t)r * GW + g;
+      x[r][p] = (xT[(int64_t)slot * ct_stride + ct] - cp.x) * cp.y;
     }
   }
-  double mx[RC], sm[RC], thr[RC];
+  LseAcc acc[RL];
 #pragma unroll
-  for (int r = 0; r < RC; ++r) {
-    mx[r] = -INFINITY;
-    sm[r] = 0.0;
-    thr[r] = -INFINITY;
-  }
+  for (int r = 0; r < RL; ++r) acc[r].init();
 
   for (int t = 0; t < ntiles; ++t) {
     const int st = t % ST;
@@ -669,67 +727,87 @@ k_logpdf_fast(const void* __restrict__ tab_v, const double* __restrict__ cst, in
     const Elem* tile = tiles + (size_t)st * TK * PB;
     const double* ctile = csts + (size_t)st * TK;
     for (int kk = 0; kk < tk; ++kk) {
-      double acc0[RC], acc1[RC];
+      double a0[RC], a1[RC];
 #pragma unroll
       for (int r = 0; r < RC; ++r) {
-        acc0[r] = 0.0;
-        acc1[r] = 0.0;
+        a0[r] = 0.0;
+        a1[r] = 0.0;
       }
       if constexpr (PAIR) {
         const double2* row = reinterpret_cast<const double2*>(tile) + (size_t)kk * PB;
 #pragma unroll
-        for (int p = 0; p < PB; ++p) {
+        for (int p = 0; p < PL; ++p) {
           const double2 v = row[p];
 #pragma unroll
           for (int r = 0; r < RC; ++r) {
             const double d = fma(x[r][p], v.y, -v.x);
-            if (p & 1) acc1[r] = fma(d, d, acc1[r]);
-            else acc0[r] = fma(d, d, acc0[r]);
+            if (p & 1) a1[r] = fma(d, d, a1[r]);
+            else a0[r] = fma(d, d, a0[r]);
           }
         }
-      } else if constexpr (PB == 1) {
-        const double v = reinterpret_cast<const double*>(tile)[kk];
+      } else if constexpr (PL == 1) {
+        const double v = reinterpret_cast<const double*>(tile)[(size_t)kk * PB + h];
 #pragma unroll
         for (int r = 0; r < RC; ++r) {
           const double d = x[r][0] - v;
-          acc0[r] = d * d;
+          a0[r] = d * d;
         }
       } else {
         const double2* row =
-            reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tile) + (size_t)kk * PB);
+            reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tile) + (size_t)kk * PB) + h;
 #pragma unroll
-        for (int q = 0; q < PB / 2; ++q) {
-          const double2 v = row[q];
+        for (int q = 0; q < PL / 2; ++q) {
+          const double2 v = row[q * PS];
 #pragma unroll
           for (int r = 0; r < RC; ++r) {
             const double d0 = x[r][2 * q] - v.x;
             const double d1 = x[r][2 * q + 1] - v.y;
-            acc0[r] = fma(d0, d0, acc0[r]);
-            acc1[r] = fma(d1, d1, acc1[r]);
+            a0[r] = fma(d0, d0, a0[r]);
+            a1[r] = fma(d1, d1, a1[r]);
           }
+        }
+      }
+      double sum[RC];
+#pragma unroll
+      for (int r = 0; r < RC; ++r) sum[r] = a0[r] + a1[r];
+      // reduce-scatter over the PS lanes of the group
+      if constexpr (PS == 2) {
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+          const double mine = h ? sum[RL + r] : sum[r];
+          const double send = h ? sum[r] : sum[RL + r];
+          sum[r] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+      } else if constexpr (PS == 4) {
+        // step 1 (xor 2): keep the half of the candidates selected by bit 1 of h
+        double half[RC / 2];
+#pragma unroll
+        for (int r = 0; r < RC / 2; ++r) {
+          const double mine = (h & 2) ? sum[RC / 2 + r] : sum[r];
+          const double send = (h & 2) ? sum[r] : sum[RC / 2 + r];
+          half[r] = mine + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        // step 2 (xor 1): keep the quarter selected by bit 0 of h
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+          const double mine = (h & 1) ? half[RL + r] : half[r];
+          const double send = (h & 1) ? half[r] : half[RL + r];
+          sum[r] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
         }
       }
       const double c = ctile[kk];
 #pragma unroll
-      for (int r = 0; r < RC; ++r) {
-        const double L = fma(-0.5, acc0[r] + acc1[r], c);
-        if (L > thr[r]) {  // within kLseSkip of the running max (or a new max)
-          if (L > mx[r]) {
-            sm[r] = sm[r] * exp(mx[r] - L) + 1.0;
-            mx[r] = L;
-            thr[r] = L - kLseSkip;
-          } else {
-            sm[r] += exp(L - mx[r]);
-          }
-        }
-      }
+      for (int r = 0; r < RL; ++r) acc[r].push_sync(fma(-0.5, sum[r], c));
     }
     __syncthreads();  // stage `st` may be refilled by the next iteration's issue()
   }
 #pragma unroll
-  for (int r = 0; r < RC; ++r) {
-    const int64_t ct = cbase + (int64_t)r * NT + tid;
-    part[blockIdx.y * ct_stride + ct] = make_double2(mx[r], sm[r]);
+  for (int r = 0; r < RL; ++r) acc[r].flush();
+  // lane h owns candidates r = h * RL + r' of its group
+#pragma unroll
+  for (int r = 0; r < RL; ++r) {
+    const int64_t ct = wbase + (int64_t)(h * RL + r) * GW + g;
+    part[blockIdx.y * ct_stride + ct] = make_double2(acc[r].m, acc[r].s);
   }
 }
 
