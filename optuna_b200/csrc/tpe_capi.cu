@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -147,7 +148,7 @@ struct FastCfg {
   int pb, cands_per_cta, nt, tk, st, minb;
   size_t smem;
   void (*launch)(dim3, size_t, cudaStream_t, const void*, const double*, int64_t, const double2*, const double*,
-                 int64_t, int64_t, double2*);
+                 int64_t, int64_t, double, double2*);
   cudaError_t (*prepare)();
 };
 
@@ -155,9 +156,10 @@ template <int PB, int PS, int RC, int NT, int TK, int ST, bool PAIR, int MINB>
 struct FastInst {
   static constexpr size_t smem = (size_t)ST * TK * PB * (PAIR ? 16 : 8) + (size_t)ST * TK * 8 + (size_t)ST * 8;
   static void launch(dim3 grid, size_t sm, cudaStream_t st, const void* tab, const double* cst, int64_t Kf,
-                     const double2* colprm, const double* xT, int64_t ct_stride, int64_t kps, double2* part) {
+                     const double2* colprm, const double* xT, int64_t ct_stride, int64_t kps, double skip,
+                     double2* part) {
     k_logpdf_fast<PB, PS, RC, NT, TK, ST, PAIR, MINB>
-        <<<grid, NT, sm, st>>>(tab, cst, Kf, colprm, xT, ct_stride, kps, part);
+        <<<grid, NT, sm, st>>>(tab, cst, Kf, colprm, xT, ct_stride, kps, skip, part);
   }
   static cudaError_t prepare() {
     return cudaFuncSetAttribute(k_logpdf_fast<PB, PS, RC, NT, TK, ST, PAIR, MINB>,
@@ -170,11 +172,14 @@ struct FastInst {
 // "small": a single ask with few candidates -- one warp per CTA, the grid splits the kernel axis.
 // CONST = one sigma per column (multivariate TPE), PAIR = sigma per kernel (univariate TPE).
 //                 PB PS RC  NT    TK ST  PAIR MINB
+// Measured at config 2 (profiles/r1_variants.md): one candidate per lane with 16 warps/SM beats the
+// lane-split tilings (shuffles cost ~6 clk each on the shared pipe) and the 2-candidate tiling
+// (8 warps/SM cannot hide the DADD->DFMA latency).
 const FastCfg kConstBig[] = {
     FastInst<1, 1, 4, 256, 2048, 3, false, 2>::cfg(), FastInst<2, 1, 4, 256, 1024, 3, false, 2>::cfg(),
-    FastInst<4, 1, 4, 256, 1024, 3, false, 1>::cfg(), FastInst<8, 1, 4, 256, 512, 3, false, 1>::cfg(),
-    FastInst<16, 1, 4, 256, 256, 3, false, 1>::cfg(), FastInst<32, 2, 4, 256, 128, 3, false, 1>::cfg(),
-    FastInst<64, 4, 4, 256, 64, 3, false, 1>::cfg(),
+    FastInst<4, 1, 4, 256, 1024, 3, false, 2>::cfg(), FastInst<8, 1, 4, 256, 512, 3, false, 1>::cfg(),
+    FastInst<16, 1, 2, 256, 256, 3, false, 2>::cfg(), FastInst<32, 1, 1, 256, 128, 3, false, 2>::cfg(),
+    FastInst<64, 1, 1, 256, 64, 3, false, 1>::cfg(),
 };
 const FastCfg kPairBig[] = {
     FastInst<1, 1, 4, 256, 1024, 3, true, 2>::cfg(), FastInst<2, 1, 4, 256, 1024, 3, true, 1>::cfg(),
@@ -194,6 +199,16 @@ const FastCfg kPairSmall[] = {
     FastInst<16, 1, 1, 32, 32, 2, true, 1>::cfg(), FastInst<32, 1, 1, 32, 16, 2, true, 1>::cfg(),
     FastInst<64, 1, 1, 32, 8, 2, true, 1>::cfg(),
 };
+// tuning variants of the P = 32 CONST kernel, selectable with TPE_FAST_VARIANT=0..3 (experiments)
+const FastCfg kConst32Variants[] = {
+    FastInst<32, 1, 1, 256, 128, 3, false, 2>::cfg(),  // 0: 1 candidate / lane, 16 warps / SM
+    FastInst<32, 1, 2, 256, 128, 3, false, 1>::cfg(),  // 1: 2 candidates / lane, 8 warps / SM
+    FastInst<32, 2, 4, 256, 128, 3, false, 1>::cfg(),  // 2: params split over 2 lanes, 4 candidates
+    FastInst<32, 4, 4, 256, 128, 3, false, 2>::cfg(),  // 3: params split over 4 lanes, 4 candidates
+    FastInst<32, 1, 2, 320, 128, 3, false, 1>::cfg(),  // 4: 2 candidates / lane, 10 warps / SM
+    FastInst<32, 1, 2, 384, 128, 3, false, 1>::cfg(),  // 5: 2 candidates / lane, 12 warps / SM
+    FastInst<32, 1, 2, 128, 64, 3, false, 2>::cfg(),   // 6: 2 candidates / lane, 2 CTAs x 4 warps
+};
 constexpr int kMaxFastP = 64;
 
 int pick_pb(int ncont) {
@@ -203,6 +218,10 @@ int pick_pb(int ncont) {
 }
 const FastCfg* pick_fast(int mode, int pb, int64_t Ct) {
   const bool small = Ct <= 128;
+  if (mode == 2 && pb == 32 && !small) {
+    const char* v = getenv("TPE_FAST_VARIANT");
+    if (v && v[0] >= '0' && v[0] <= '6') return &kConst32Variants[v[0] - '0'];
+  }
   const FastCfg* tabs = (mode == 2) ? (small ? kConstSmall : kConstBig) : (small ? kPairSmall : kPairBig);
   for (int i = 0; i < 7; ++i)
     if (tabs[i].pb == pb) return &tabs[i];
@@ -354,7 +373,8 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
       CU(fc->prepare());
       fc->launch(dim3((unsigned)ctiles, (unsigned)nsplit), fc->smem, st,
                  cst_mode ? (const void*)e.tabc.p : (const void*)e.tabp.p, e.cst.as<double>(), Kf,
-                 e.colprm.as<double2>(), ctx->xT.as<double>(), ctx->ct_stride, kps, e.part.as<double2>());
+                 e.colprm.as<double2>(), ctx->xT.as<double>(), ctx->ct_stride, kps,
+                 std::min(46.0, log((double)std::max<int64_t>(K, 1)) + 30.0), e.part.as<double2>());
       ctx->launch_counter++;
     }
     ctx->last_kernel = cst_mode ? ((fc->nt >= 256) ? "k_logpdf_fast<const,big>" : "k_logpdf_fast<const,small>")

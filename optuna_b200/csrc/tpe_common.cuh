@@ -107,7 +107,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Terms more than kLseSkip below the running max are dropped: each is < e^-kLseSkip of the
 // largest term, so with K <= 1e9 kernels the relative change of the sum is < 6e-10 * e^-... see
 // DESIGN.md "log-sum-exp truncation" (bound: K * e^-46 = 1e5 * 1.05e-20 ~ 1e-15).
-constexpr double kLseSkip = 46.0;
+constexpr double kLseSkip = 46.0;  // generic kernel; the fast kernel gets ln(K) + 30 from the host
 __device__ __forceinline__ void lse_push(double L, double& m, double& s) {
   if (L > m) {
     s = s * exp(m - L) + 1.0;

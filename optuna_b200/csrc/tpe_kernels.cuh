@@ -620,6 +620,10 @@ struct LseAcc {
   __device__ __forceinline__ void init() {
     m = -INFINITY; s = 0.0; thr = -INFINITY; b0 = b1 = b2 = b3 = 0.0; cnt = 0;
   }
+  static __device__ __forceinline__ double& skip() {
+    static __shared__ double s_skip;  // per-launch truncation distance (see k_logpdf_fast)
+    return s_skip;
+  }
   // branch-free fold of one parked term (valid == false leaves the accumulator untouched)
   __device__ __forceinline__ void fold(double L, bool valid) {
     const double d = L - m;
@@ -637,7 +641,7 @@ struct LseAcc {
     fold(b2, cnt > 2);
     fold(b3, cnt > 3);
     cnt = 0;
-    thr = m - kLseSkip;
+    thr = m - skip();
   }
   // Park L if it is within kLseSkip of the (possibly stale, i.e. lower) running max; when any lane's
   // buffer is full every lane folds its parked terms -- one converged pass instead of 32 diverged ones.
@@ -656,7 +660,7 @@ template <int PB, int PS, int RC, int NT, int TK, int ST, bool PAIR, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_logpdf_fast(const void* __restrict__ tab_v, const double* __restrict__ cst, int64_t Kf,
               const double2* __restrict__ colprm, const double* __restrict__ xT, int64_t ct_stride, int64_t kps,
-              double2* __restrict__ part) {
+              double lse_skip, double2* __restrict__ part) {
   static_assert(PB % PS == 0 && RC % PS == 0, "bad tiling");
   static_assert(!PAIR || PS == 1, "PAIR tables are not split over lanes");
   constexpr int PL = PB / PS;   // params per lane
@@ -683,6 +687,7 @@ k_logpdf_fast(const void* __restrict__ tab_v, const double* __restrict__ cst, in
   if (tid == 0) {
     for (int s = 0; s < ST; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
+    LseAcc::skip() = lse_skip;
   }
   __syncthreads();
 
