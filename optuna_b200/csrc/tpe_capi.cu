@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -59,10 +60,10 @@ struct DevBuf {
 
 struct Estimator {
   int64_t n = 0, K = 0;
-  DevBuf rows, pos, wstage, w, logw, cdf, mu, sigma, cst_part, cst, tabp, tabc, colprm, tab, part, fix;
+  DevBuf rows, pos, wstage, wpart, w, logw, cdf, mu, sigma, cst_part, cst, tabp, tabc, colprm, tab, part, fix;
   int nsplit = 0;
   void release() {
-    for (DevBuf* b : {&rows, &pos, &wstage, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
+    for (DevBuf* b : {&rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
                       &part, &fix})
       b->release();
   }
@@ -100,7 +101,7 @@ struct tpe_ctx {
   bool fast = false;
   int fast_mode = 0;  // 0 generic, 1 PAIR (sigma per kernel), 2 CONST (sigma per column)
   tpe_split_info info{};
-  DevBuf row_ok, member, cand_a, cand_b, counts;
+  DevBuf row_ok, member, cand_a, cand_b, counts, split_work;
   Estimator est[2];
   DevBuf sort_val, sort_idx;
 
@@ -111,6 +112,7 @@ struct tpe_ctx {
   int32_t launches = 0;
   const char* last_kernel = "none";
   int32_t launch_counter = 0;
+  std::set<const void*> prepared_cfgs;
 };
 
 namespace {
@@ -280,15 +282,23 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
   if (ctx->fast) CU(e.colprm.ensure((size_t)ctx->pb * 16));
   if (ctx->tab_doubles) CU(e.tab.ensure((size_t)ctx->tab_doubles * 8));
 
-  k_mu<<<grid_for(K * pc, 256, cap), 256, 0, st>>>(ctx->X.as<double>(), (int32_t)ctx->space.size(),
-                                                   e.rows.as<int64_t>(), n, ctx->cols.as<ColMeta>(), pc,
-                                                   e.mu.as<double>());
-  ctx->launch_counter++;
+  if (ctx->fast && ctx->pb > ctx->ncont) {
+    k_tab_pad<<<grid_for(K * (ctx->pb - ctx->ncont), 256, cap), 256, 0, st>>>(
+        ctx->fast_mode == 1 ? e.tabp.as<double2>() : nullptr, ctx->fast_mode == 2 ? e.tabc.as<double>() : nullptr,
+        e.colprm.as<double2>(), ctx->fast_mode == 2 ? K - 1 : K, ctx->pb, ctx->ncont);
+    ctx->launch_counter++;
+  }
   if (ctx->cfg.multivariate) {
-    k_sigma_mv<<<grid_for(K * pc, 256, cap), 256, 0, st>>>(ctx->cols.as<ColMeta>(), pc, n, ctx->cfg.magic_clip,
-                                                           e.sigma.as<double>());
+    k_build_mv<<<grid_for(K * 32, 256, cap), 256, 0, st>>>(
+        ctx->X.as<double>(), (int32_t)ctx->space.size(), e.rows.as<int64_t>(), n, ctx->cols.as<ColMeta>(), pc,
+        ctx->cfg.magic_clip, ctx->pb, ctx->fast_mode, e.mu.as<double>(), e.sigma.as<double>(), e.tabp.as<double2>(),
+        e.tabc.as<double>(), e.colprm.as<double2>(), e.cst_part.as<double>());
     ctx->launch_counter++;
   } else {
+    k_mu<<<grid_for(K * pc, 256, cap), 256, 0, st>>>(ctx->X.as<double>(), (int32_t)ctx->space.size(),
+                                                     e.rows.as<int64_t>(), n, ctx->cols.as<ColMeta>(), pc,
+                                                     e.mu.as<double>());
+    ctx->launch_counter++;
     // categorical columns: sigma unused; numeric columns: sort-based neighbour gaps
     CU(cudaMemsetAsync(e.sigma.p, 0, (size_t)K * pc * 8, st));
     int64_t m2 = 1;
@@ -315,28 +325,28 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
                                                          ctx->cfg.endpoints, e.sigma.as<double>());
       ctx->launch_counter++;
     }
-  }
-  if (ctx->fast && ctx->pb > ctx->ncont) {
-    k_tab_pad<<<grid_for(K * (ctx->pb - ctx->ncont), 256, cap), 256, 0, st>>>(
-        ctx->fast_mode == 1 ? e.tabp.as<double2>() : nullptr, ctx->fast_mode == 2 ? e.tabc.as<double>() : nullptr,
-        e.colprm.as<double2>(), ctx->fast_mode == 2 ? K - 1 : K, ctx->pb, ctx->ncont);
+    k_const<<<grid_for(K * 32, 256, cap), 256, 0, st>>>(e.mu.as<double>(), e.sigma.as<double>(),
+                                                        ctx->cols.as<ColMeta>(), pc, K, ctx->pb, ctx->fast_mode,
+                                                        e.tabp.as<double2>(), e.tabc.as<double>(),
+                                                        e.colprm.as<double2>(), e.cst_part.as<double>());
     ctx->launch_counter++;
   }
-  k_const<<<grid_for(K * 32, 256, cap), 256, 0, st>>>(e.mu.as<double>(), e.sigma.as<double>(),
-                                                      ctx->cols.as<ColMeta>(), pc, K, ctx->pb, ctx->fast_mode,
-                                                      e.tabp.as<double2>(), e.tabc.as<double>(),
-                                                      e.colprm.as<double2>(), e.cst_part.as<double>());
-  ctx->launch_counter++;
   const double* w_dev = nullptr;
   if (w_host != nullptr && n > 0) {
     CU(e.wstage.ensure((size_t)n * 8));
     CU(cudaMemcpyAsync(e.wstage.p, w_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     w_dev = e.wstage.as<double>();
   }
-  k_weights<<<1, 1024, 0, st>>>(w_dev, nullptr, n, ctx->cfg.prior_weight, e.w.as<double>(), e.logw.as<double>(),
-                                e.cst_part.as<double>(), e.cst.as<double>(), which == 0 ? e.cdf.as<double>() : nullptr,
-                                k_alloc);
-  ctx->launch_counter++;
+  {
+    const int nparts = grid_for(K, 2048, ctx->sm_count * 2);
+    CU(e.wpart.ensure((size_t)nparts * 8));
+    k_wraw<<<nparts, 256, 0, st>>>(w_dev, n, ctx->cfg.prior_weight, e.w.as<double>(), e.wpart.as<double>());
+    k_wfinal<<<grid_for(k_alloc, 256, ctx->sm_count * 4), 256, 0, st>>>(
+        e.wpart.as<double>(), nparts, n, e.w.as<double>(), e.logw.as<double>(), e.cst_part.as<double>(),
+        e.cst.as<double>(), which == 0 ? e.cdf.as<double>() : nullptr, k_alloc);
+    k_wnorm<<<grid_for(K, 256, ctx->sm_count * 4), 256, 0, st>>>(e.wpart.as<double>(), nparts, K, e.w.as<double>());
+    ctx->launch_counter += 3;
+  }
   if (ctx->ncat) {
     k_cat_tables<<<pc, 64, 0, st>>>(ctx->cols.as<ColMeta>(), pc, n, ctx->cfg.prior_weight,
                                     ctx->cat_dist.as<double>(), e.tab.as<double>());
@@ -370,7 +380,10 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     }
     CU(e.part.ensure((size_t)(nsplit + 1) * ctx->ct_stride * 16));
     if (nsplit > 0) {
-      CU(fc->prepare());
+      if (!ctx->prepared_cfgs.count(fc)) {
+        CU(fc->prepare());
+        ctx->prepared_cfgs.insert(fc);
+      }
       fc->launch(dim3((unsigned)ctiles, (unsigned)nsplit), fc->smem, st,
                  cst_mode ? (const void*)e.tabc.p : (const void*)e.tabp.p, e.cst.as<double>(), Kf,
                  e.colprm.as<double2>(), ctx->xT.as<double>(), ctx->ct_stride, kps,
@@ -460,7 +473,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->cat_dist, &ctx->X, &ctx->cat, &ctx->key, &ctx->cols, &ctx->row_ok, &ctx->member,
-                    &ctx->cand_a, &ctx->cand_b, &ctx->counts, &ctx->sort_val, &ctx->sort_idx, &ctx->U, &ctx->S,
+                    &ctx->cand_a, &ctx->cand_b, &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
@@ -649,10 +662,22 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
     ctx->launch_counter++;
     rowok = ctx->row_ok.as<uint8_t>();
   }
-  k_split<<<1, 1024, 0, ctx->stream>>>((int)N, ctx->cat.as<int8_t>(), ctx->key.as<double>(), cfg->n_below, rowok,
-                                       ctx->member.as<uint8_t>(), ctx->cand_a.as<int>(), ctx->cand_b.as<int>(),
-                                       ctx->est[0].rows.as<int64_t>(), ctx->est[0].pos.as<int64_t>(),
-                                       ctx->est[1].rows.as<int64_t>(), ctx->counts.as<int64_t>());
+  {
+    CU(ctx->split_work.ensure(sizeof(SplitWork)));
+    CU(cudaMemsetAsync(ctx->split_work.p, 0, sizeof(SplitWork), ctx->stream));
+    int n_i = (int)N;
+    int64_t nb = cfg->n_below;
+    const int8_t* d_cat = ctx->cat.as<int8_t>();
+    const double* d_key = ctx->key.as<double>();
+    SplitWork* d_wk = ctx->split_work.as<SplitWork>();
+    int64_t* d_b = ctx->est[0].rows.as<int64_t>();
+    int64_t* d_p = ctx->est[0].pos.as<int64_t>();
+    int64_t* d_a = ctx->est[1].rows.as<int64_t>();
+    int64_t* d_c = ctx->counts.as<int64_t>();
+    void* args[] = {&n_i, &d_cat, &d_key, &nb, &rowok, &d_wk, &d_b, &d_p, &d_a, &d_c};
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (N + 2047) / 2048));
+    CU(cudaLaunchCooperativeKernel((const void*)k_split_coop, dim3(G), dim3(512), args, 0, ctx->stream));
+  }
   ctx->launch_counter++;
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -741,7 +766,7 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   rc = run_logpdf(ctx, 1, Ct, ctx->ev[6]);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->ev[7], st));
-  k_acq<<<grid_for(Ct, 256, ctx->sm_count * 8), 256, 0, st>>>(
+  k_acq<<<grid_for(Ct * 32, 256, ctx->sm_count * 8), 256, 0, st>>>(
       ctx->est[0].part.as<double2>(), ctx->est[0].nsplit, ctx->est[1].part.as<double2>(), ctx->est[1].nsplit,
       ctx->ct_stride, ctx->fast ? ctx->oob.as<uint8_t>() : nullptr, ctx->est[0].fix.as<double2>(),
       ctx->est[1].fix.as<double2>(), Ct, ctx->logl.as<double>(), ctx->logg.as<double>());

@@ -10,6 +10,8 @@
 //                            optuna/samplers/_tpe/_truncnorm.py:286-297
 //   k_select                 optuna/samplers/_tpe/sampler.py:591-618
 #pragma once
+#include <cooperative_groups.h>
+
 #include <type_traits>
 
 #include "tpe_common.cuh"
@@ -151,6 +153,207 @@ k_split(int n, const int8_t* __restrict__ cat, const double* __restrict__ key, i
     counts[0] = nb_all;
     counts[1] = nb;
     counts[2] = na;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-CTA split (cooperative launch): the same selection as k_split, spread over the whole GPU.
+// No candidate lists: every radix pass re-scans the (tiny: 17 B/trial) key arrays with all CTAs and
+// histograms the next byte of the trials that still match the 128-bit prefix; grid.sync() between
+// passes.  Ordered (stable) outputs come from per-CTA contiguous chunks + a prefix over CTA counts.
+// ------------------------------------------------------------------------------------------------
+struct SplitWork {        // global scratch, zeroed by the host before the launch
+  int cat_count[4];       // trials per category
+  int hist[16][256];      // one histogram per radix pass
+  int cta_tie[1024];      // per-CTA number of boundary ties
+  int cta_cnt[1024][3];   // per-CTA (below_all, below_ok, above_ok)
+};
+
+__device__ __forceinline__ void key_u128(const double* __restrict__ key, int i, uint64_t& hi, uint64_t& lo) {
+  hi = order_bits(key[2 * (int64_t)i]);
+  lo = order_bits(key[2 * (int64_t)i + 1]);
+}
+// keep the top `nb` bytes of a 128-bit value
+__device__ __forceinline__ void top_bytes(int nb, uint64_t& hi, uint64_t& lo) {
+  if (nb <= 0) { hi = 0; lo = 0; }
+  else if (nb < 8) { hi &= ~0ull << (8 * (8 - nb)); lo = 0; }
+  else if (nb == 8) { lo = 0; }
+  else if (nb < 16) { lo &= ~0ull << (8 * (16 - nb)); }
+}
+
+__global__ void __launch_bounds__(512, 1)
+k_split_coop(int n, const int8_t* __restrict__ cat, const double* __restrict__ key, int64_t n_below,
+             const uint8_t* __restrict__ row_ok, SplitWork* __restrict__ wk, int64_t* __restrict__ below_rows,
+             int64_t* __restrict__ below_pos, int64_t* __restrict__ above_rows, int64_t* __restrict__ counts) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ int s_hist[256];
+  __shared__ int s_pick[3];
+  __shared__ int s_warp[32];
+  __shared__ int s_base[4];
+  const int tid = threadIdx.x;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int chunk = (n + G - 1) / G;
+  const int lo_i = min(n, b * chunk), hi_i = min(n, lo_i + chunk);
+
+  // ---- category sizes ---------------------------------------------------------------------------
+  if (tid < 4) s_base[tid] = 0;
+  __syncthreads();
+  for (int i = lo_i + tid; i < hi_i; i += blockDim.x) atomicAdd(&s_base[cat[i] & 3], 1);
+  __syncthreads();
+  if (tid < 4 && s_base[tid]) atomicAdd(&wk->cat_count[tid], s_base[tid]);
+  grid.sync();
+
+  // which category holds the cut?  (earlier ones are entirely below, later ones entirely above)
+  int64_t remaining = n_below < 0 ? 0 : n_below;
+  int thr_cat = 3, need = 0;
+  for (int c = 0; c < 3; ++c) {
+    const int cnt = wk->cat_count[c];
+    if (remaining >= cnt) { remaining -= cnt; continue; }
+    thr_cat = c;
+    need = (int)remaining;
+    break;
+  }
+  // categories < thr_cat: all below; == thr_cat: the `need` smallest keys; > thr_cat: above.
+  uint64_t p_hi = 0, p_lo = 0;  // selected key prefix
+  int nb = 0;                   // number of leading bytes of the prefix that are fixed
+  bool take_all_eq = false;     // every trial equal to the prefix on `nb` bytes is below
+  if (thr_cat < 3 && need > 0) {
+    for (int d = 15; d >= 0; --d) {
+      for (int t = tid; t < 256; t += blockDim.x) s_hist[t] = 0;
+      __syncthreads();
+      for (int i = lo_i + tid; i < hi_i + ((32 - ((hi_i - lo_i) & 31)) & 31); i += blockDim.x) {
+        bool v = i < hi_i && cat[i] == thr_cat;
+        int dg = -1 - (tid & 31);
+        if (v) {
+          uint64_t h, l, mh, ml;
+          key_u128(key, i, h, l);
+          mh = h; ml = l;
+          top_bytes(15 - d, mh, ml);
+          v = (mh == p_hi && ml == p_lo);
+          if (v) dg = (int)(((d >= 8 ? h : l) >> ((d & 7) * 8)) & 0xffull);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, dg);
+        if (v && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&s_hist[dg], __popc(peers));
+      }
+      __syncthreads();
+      for (int t = tid; t < 256; t += blockDim.x)
+        if (s_hist[t]) atomicAdd(&wk->hist[d][t], s_hist[t]);
+      grid.sync();
+      if (tid == 0) {
+        int cum = 0, q = 0;
+        for (; q < 256; ++q) {
+          const int hq = wk->hist[d][q];
+          if (cum + hq >= need) break;
+          cum += hq;
+        }
+        s_pick[0] = q;
+        s_pick[1] = cum;
+        s_pick[2] = wk->hist[d][q];
+      }
+      __syncthreads();
+      const int D = s_pick[0], less = s_pick[1], eq = s_pick[2];
+      __syncthreads();
+      if (d >= 8) p_hi |= (uint64_t)D << ((d & 7) * 8);
+      else p_lo |= (uint64_t)D << ((d & 7) * 8);
+      nb = 16 - d;
+      need -= less;
+      if (need == eq) { take_all_eq = true; break; }
+    }
+  }
+  // classification of trial i: 2 = below, 1 = boundary tie (identical 128-bit key), 0 = above
+  auto classify = [&](int i) -> int {
+    const int c = cat[i];
+    if (c >= 3 || c > thr_cat) return 0;
+    if (c < thr_cat) return 2;
+    if (need <= 0 && !take_all_eq) return 0;
+    uint64_t h, l;
+    key_u128(key, i, h, l);
+    top_bytes(nb, h, l);
+    if (h < p_hi || (h == p_hi && l < p_lo)) return 2;
+    if (h == p_hi && l == p_lo) return take_all_eq ? 2 : 1;
+    return 0;
+  };
+  const bool have_ties = (thr_cat < 3) && !take_all_eq && need > 0;  // nb == 16 here
+
+  // ---- ordered partition ------------------------------------------------------------------------------
+  // pass A: boundary ties per CTA (earliest trials win, sampler.py stable sort)
+  int tie_before = 0;
+  if (have_ties) {
+    int mine = 0;
+    for (int i = lo_i + tid; i < hi_i; i += blockDim.x) mine += classify(i) == 1;
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((tid & 31) == 0) s_warp[tid >> 5] = mine;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_warp[w];
+      wk->cta_tie[b] = t;
+    }
+    grid.sync();
+    for (int q = 0; q < b; ++q) tie_before += wk->cta_tie[q];
+  }
+  // pass B: per-CTA counts with tie membership resolved; pass C: write.  Both walk the chunk in
+  // tiles of blockDim with an ordered block scan.
+  auto walk = [&](bool write, int base_all, int base_b, int base_a) {
+    int tie_seen = tie_before, nb_all = base_all, nbo = base_b, nao = base_a;
+    for (int t0 = lo_i; t0 < hi_i; t0 += blockDim.x) {
+      const int i = t0 + tid;
+      const bool v = i < hi_i;
+      const int cls = v ? classify(i) : 0;
+      const bool ok = v && (row_ok == nullptr || row_ok[i] != 0);
+      // ordered rank helpers (512 threads = 16 warps)
+      auto rank = [&](bool f, int& total) -> int {
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        const int lane = tid & 31, w = tid >> 5;
+        const int wpos = __popc(m & ((1u << lane) - 1u));
+        __syncthreads();
+        if (lane == 0) s_warp[w] = __popc(m);
+        __syncthreads();
+        int vv = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0, incl = vv;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        return __shfl_sync(0xffffffffu, incl - vv, w) + wpos;
+      };
+      int tot_t = 0, tot_all = 0, tot_b = 0, tot_a = 0;
+      bool isb = cls == 2;
+      if (have_ties) {
+        const int tr = rank(cls == 1, tot_t);
+        if (cls == 1 && tie_seen + tr < need) isb = true;
+        tie_seen += tot_t;
+      }
+      const int r_all = rank(isb, tot_all);
+      const int r_b = rank(isb && ok, tot_b);
+      const int r_a = rank(v && !isb && ok, tot_a);
+      if (write) {
+        if (isb && ok) {
+          below_rows[nbo + r_b] = i;
+          below_pos[nbo + r_b] = nb_all + r_all;
+        }
+        if (v && !isb && ok) above_rows[nao + r_a] = i;
+      }
+      nb_all += tot_all;
+      nbo += tot_b;
+      nao += tot_a;
+    }
+    if (!write && tid == 0) {
+      wk->cta_cnt[b][0] = nb_all;
+      wk->cta_cnt[b][1] = nbo;
+      wk->cta_cnt[b][2] = nao;
+    }
+  };
+  walk(false, 0, 0, 0);
+  grid.sync();
+  int base[3] = {0, 0, 0};
+  for (int q = 0; q < b; ++q)
+    for (int e = 0; e < 3; ++e) base[e] += wk->cta_cnt[q][e];
+  walk(true, base[0], base[1], base[2]);
+  if (b == G - 1 && tid == 0) {
+    counts[0] = base[0] + wk->cta_cnt[b][0];
+    counts[1] = base[1] + wk->cta_cnt[b][1];
+    counts[2] = base[2] + wk->cta_cnt[b][2];
   }
 }
 
@@ -327,7 +530,7 @@ __global__ void k_const(const double* __restrict__ mu, const double* __restrict_
       const double m = mu[k * pc + j], s = sigma[k * pc + j];
       const double a = TPE_DIV(TPE_SUB(cm.klow, m), s);
       const double b = TPE_DIV(TPE_SUB(cm.khigh, m), s);
-      const double mass = log_gauss_mass(a, b);
+      const double mass = log_gauss_mass_fast(a, b);
       if (cm.cls == COL_CONT) {
         acc += kLogSqrt2Pi + mass + log(s);
         if (mode != 0) {
@@ -419,6 +622,153 @@ k_weights(const double* __restrict__ w_in, const int64_t* __restrict__ pos, int6
     const double last = cdf[K - 1];
     for (int64_t k = 0; k < K; ++k) cdf[k] = TPE_DIV(cdf[k], last);
   }
+}
+
+// Fused multivariate build: k_mu + k_sigma_mv + k_const in one pass (one warp per kernel, lanes over
+// columns).  mode / tables as in k_const.
+__global__ void k_build_mv(const double* __restrict__ X, int32_t pall, const int64_t* __restrict__ rows, int64_t n,
+                           const ColMeta* __restrict__ cols, int32_t pc, int magic_clip, int32_t pb, int mode,
+                           double* __restrict__ mu, double* __restrict__ sigma, double2* __restrict__ tabp,
+                           double* __restrict__ tabc, double2* __restrict__ colprm, double* __restrict__ cst_part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t K = n + 1;
+  const double e = TPE_DIV(-1.0, (double)(pc + 4));
+  const double factor = TPE_MUL(0.2, pow((double)(n > 1 ? n : 1), e));
+  for (int64_t k = warp; k < K; k += nwarps) {
+    const int64_t row = (k < n) ? rows[k] : 0;
+    double acc = 0.0;
+    for (int j = lane; j < pc; j += 32) {
+      const ColMeta cm = cols[j];
+      if (cm.cls == COL_CAT) {
+        mu[k * pc + j] = (k < n) ? X[row * pall + cm.src] : (double)cm.nch;
+        sigma[k * pc + j] = 0.0;
+        continue;
+      }
+      double lo, hi;
+      sigma_limits(cm, n, magic_clip != 0, lo, hi);
+      const double ctr = TPE_MUL(0.5, TPE_ADD(cm.klow, cm.khigh));
+      double m, s;
+      if (k < n) {
+        m = X[row * pall + cm.src];
+        if (cm.log) m = log(m);
+        s = fmin(fmax(TPE_MUL(factor, hi), lo), hi);
+      } else {
+        m = ctr;
+        s = hi;
+      }
+      mu[k * pc + j] = m;
+      sigma[k * pc + j] = s;
+      const double a = TPE_DIV(TPE_SUB(cm.klow, m), s);
+      const double b = TPE_DIV(TPE_SUB(cm.khigh, m), s);
+      const double mass = log_gauss_mass_fast(a, b);
+      if (cm.cls == COL_CONT) {
+        acc += kLogSqrt2Pi + mass + log(s);
+        if (mode != 0) {
+          const double inv = TPE_DIV(1.0, s);
+          if (mode == 1) {
+            tabp[k * pb + cm.slot] = make_double2(TPE_MUL(TPE_SUB(m, ctr), inv), inv);
+            if (k == 0) colprm[cm.slot] = make_double2(ctr, 1.0);
+          } else {
+            if (k < K - 1) tabc[k * pb + cm.slot] = TPE_MUL(TPE_SUB(m, ctr), inv);
+            if (k == 0) colprm[cm.slot] = make_double2(ctr, inv);
+          }
+        }
+      } else {
+        acc += mass;
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) cst_part[k] = -acc;
+  }
+}
+
+// Multi-CTA version of k_weights: raw weights + per-block partial sums, then normalisation.
+// Partial sums are combined in a fixed order, so the result is deterministic.
+__device__ __forceinline__ double raw_weight(const double* __restrict__ w_in, int64_t n, int64_t k,
+                                             double prior_weight) {
+  if (n == 0) return 1.0;
+  if (k == n) return prior_weight;
+  if (w_in != nullptr) return w_in[k];
+  const int64_t nramp = n - 25;
+  if (n < 25 || k >= nramp) return 1.0;
+  if (k == nramp - 1 && nramp > 1) return 1.0;
+  const double start = TPE_DIV(1.0, (double)n);
+  const double step = nramp > 1 ? TPE_DIV(TPE_SUB(1.0, start), (double)(nramp - 1)) : 0.0;
+  return TPE_ADD(TPE_MUL((double)k, step), start);
+}
+__global__ void __launch_bounds__(256)
+k_wraw(const double* __restrict__ w_in, int64_t n, double prior_weight, double* __restrict__ w,
+       double* __restrict__ part) {
+  __shared__ double s_red[8];
+  const int64_t K = n + 1;
+  const int64_t chunk = (K + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = blockIdx.x * chunk, hi = (lo + chunk < K) ? lo + chunk : K;
+  double acc = 0.0;
+  for (int64_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
+    const double r = raw_weight(w_in, n, k, prior_weight);
+    w[k] = r;
+    acc += r;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += s_red[i];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_wfinal(const double* __restrict__ part, int nparts, int64_t n, double* __restrict__ w, double* __restrict__ logw,
+         const double* __restrict__ cst_part, double* __restrict__ cst, double* __restrict__ cdf, int64_t k_alloc) {
+  __shared__ double s_total;
+  const int64_t K = n + 1;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nparts; ++i) t += part[i];
+    s_total = t;
+  }
+  __syncthreads();
+  const double total = s_total;
+  if (cdf != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    // cumsum(w / total) / last, sequential like numpy.cumsum (rng.choice, probability_distributions.py:87)
+    double run = 0.0;
+    for (int64_t k = 0; k < K; ++k) {
+      run = TPE_ADD(run, TPE_DIV(w[k], total));
+      cdf[k] = run;
+    }
+    const double last = run;
+    for (int64_t k = 0; k < K; ++k) cdf[k] = TPE_DIV(cdf[k], last);
+  }
+  __syncthreads();
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < k_alloc; k += (int64_t)gridDim.x * blockDim.x) {
+    if (k < K) {
+      if (cdf != nullptr && blockIdx.x == 0) {
+        // block 0 normalises its own elements only after thread 0 has read the raw values (sync above)
+      }
+      const double v = TPE_DIV(w[k], total);
+      const double lw = log(v);
+      logw[k] = lw;
+      cst[k] = cst_part[k] + lw;
+    } else {
+      cst[k] = -INFINITY;  // padding read by the bulk copies
+    }
+  }
+}
+// w is kept raw by k_wfinal (other blocks may still read it); this pass stores the normalised values.
+__global__ void k_wnorm(const double* __restrict__ part, int nparts, int64_t K, double* __restrict__ w) {
+  __shared__ double s_total;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nparts; ++i) t += part[i];
+    s_total = t;
+  }
+  __syncthreads();
+  const double total = s_total;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < K; k += (int64_t)gridDim.x * blockDim.x)
+    w[k] = TPE_DIV(w[k], total);
 }
 
 // Categorical kernel rows (parzen_estimator.py:132-166): the row of kernel k depends only on its
@@ -820,29 +1170,42 @@ k_logpdf_fast(const void* __restrict__ tab_v, const double* __restrict__ cst, in
 // acquisition + argmax
 // ================================================================================================
 // Grid-wide pass: logl/logg = merge of the k-split partials (or the fix-up value for
-// out-of-support candidates), written for every candidate.
+// out-of-support candidates), written for every candidate.  One warp per candidate: lanes stride
+// over the partial rows (a single small ask has > 1000 of them), then a shuffle merge.
 __global__ void k_acq(const double2* __restrict__ part_l, int nsl, const double2* __restrict__ part_g, int nsg,
                       int64_t ct_stride, const uint8_t* __restrict__ oob, const double2* __restrict__ fix_l,
                       const double2* __restrict__ fix_g, int64_t Ct, double* __restrict__ logl,
                       double* __restrict__ logg) {
-  for (int64_t ct = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ct < Ct; ct += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t ct = warp; ct < Ct; ct += nwarps) {
     double ml = -INFINITY, sl = 0.0, mg = -INFINITY, sg = 0.0;
     if (oob != nullptr && oob[ct]) {
       ml = fix_l[ct].x; sl = fix_l[ct].y;
       mg = fix_g[ct].x; sg = fix_g[ct].y;
     } else {
-      for (int s = 0; s < nsl; ++s) {
+      for (int s = lane; s < nsl; s += 32) {
         const double2 v = part_l[(int64_t)s * ct_stride + ct];
         lse_merge(v.x, v.y, ml, sl);
       }
-      for (int s = 0; s < nsg; ++s) {
+      for (int s = lane; s < nsg; s += 32) {
         const double2 v = part_g[(int64_t)s * ct_stride + ct];
         lse_merge(v.x, v.y, mg, sg);
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double m2 = __shfl_xor_sync(0xffffffffu, ml, o), s2 = __shfl_xor_sync(0xffffffffu, sl, o);
+        lse_merge(m2, s2, ml, sl);
+        const double m3 = __shfl_xor_sync(0xffffffffu, mg, o), s3 = __shfl_xor_sync(0xffffffffu, sg, o);
+        lse_merge(m3, s3, mg, sg);
+      }
     }
-    // np.log(sum exp(L - max)) + max, with max := 0 when it is -inf
-    logl[ct] = (ml == -INFINITY) ? -INFINITY : log(sl) + ml;
-    logg[ct] = (mg == -INFINITY) ? -INFINITY : log(sg) + mg;
+    if (lane == 0) {
+      // np.log(sum exp(L - max)) + max, with max := 0 when it is -inf
+      logl[ct] = (ml == -INFINITY) ? -INFINITY : log(sl) + ml;
+      logg[ct] = (mg == -INFINITY) ? -INFINITY : log(sg) + mg;
+    }
   }
 }
 

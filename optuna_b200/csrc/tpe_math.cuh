@@ -235,6 +235,15 @@ TPE_HD double log_gauss_mass(double a, double b) {
   return log1p(TPE_SUB(-ndtr_vec(a), ndtr_vec(-b)));
 }
 
+// Same quantity with the library erf() for the central case (used for the (K, P) normalisers of
+// the estimator build, where a <= 0 < b and the mass is O(1): |difference| <= ~3e-16 absolute).
+TPE_HD double log_gauss_mass_fast(double a, double b) {
+  if (b <= 0.0 || a > 0.0 || a != a || b != b) return log_gauss_mass(a, b);
+  const double pa = 0.5 + 0.5 * erf(a * 0.7071067811865476);
+  const double pb = 0.5 + 0.5 * erf(-b * 0.7071067811865476);
+  return log1p(-pa - pb);
+}
+
 TPE_HD double logaddexp(double p, double q) {  // numpy.logaddexp
   if (p == q) return p + 0.6931471805599453;
   const double d = p - q;

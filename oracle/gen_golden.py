@@ -291,8 +291,114 @@ def gold_branin() -> dict:
     return out
 
 
+def gold_mo() -> dict:
+    """Multi-objective pieces straight from the reference: ranks, hypervolumes, HSSP, the MOTPE
+    split, the hypervolume weights, and full MOTPE _sample traces."""
+    from unittest.mock import patch
+    from optuna._hypervolume import compute_hypervolume
+    from optuna._hypervolume.hssp import _solve_hssp
+    from optuna.samplers._tpe.sampler import (_calculate_weights_below_for_multi_objective,
+                                              _get_reference_point, _split_complete_trials_multi_objective)
+    from optuna.study._multi_objective import _fast_non_domination_rank
+    out = {}
+    rs = np.random.RandomState(21)
+    # hypervolume / rank / hssp on raw point sets
+    ci = 0
+    for m in (2, 3, 4, 5):
+        for n in (1, 2, 3, 7, 40):
+            v = rs.uniform(0, 1, (n, m))
+            if n >= 7:
+                v[1] = v[0]  # duplicate
+                v = np.round(v, 1) if (n == 40 and m == 3) else v  # many ties
+            ref = _get_reference_point(v)
+            out[f"hv{ci}/v"], out[f"hv{ci}/ref"] = v, ref
+            out[f"hv{ci}/hv"] = np.asarray(compute_hypervolume(v, ref))
+            out[f"hv{ci}/rank"] = _fast_non_domination_rank(v)
+            nb = max(1, n // 3)
+            out[f"hv{ci}/rank_nb"] = _fast_non_domination_rank(v, n_below=nb)
+            k = max(1, n // 2)
+            out[f"hv{ci}/hssp"] = _solve_hssp(v, np.arange(n) * 3, k, ref)
+            ci += 1
+    out["hv_n"] = np.asarray(ci)
+
+    class _S:  # the split / weights helpers only read directions
+        def __init__(self, m):
+            self.directions = [optuna.study.StudyDirection.MINIMIZE] * m
+    ci = 0
+    for m, n, nb in ((2, 60, 7), (3, 200, 25), (4, 300, 25), (4, 300, 60), (2, 50, 20), (3, 40, 39), (4, 30, 0)):
+        v = rs.normal(size=(n, m))
+        if ci == 4:
+            v = np.round(v, 0)  # heavy duplication
+        if ci == 1:
+            v[5, 0] = np.inf
+            v[9, 1] = -np.inf
+        trials = [create_trial(values=list(map(float, v[i])), params={}, distributions={}) for i in range(n)]
+        for i, t in enumerate(trials):
+            t.number = i
+        below, above = _split_complete_trials_multi_objective(trials, _S(m), nb)
+        bidx = np.asarray([t.number for t in below], dtype=np.int64)
+        out[f"mo{ci}/v"], out[f"mo{ci}/nb"], out[f"mo{ci}/below"] = v, np.asarray(nb), bidx
+        out[f"mo{ci}/w"] = _calculate_weights_below_for_multi_objective(_S(m), below, None)
+        ci += 1
+    out["mo_n"] = np.asarray(ci)
+
+    # full MOTPE suggestions (multivariate and univariate)
+    ci = 0
+    for m, n, mv, C, seed, gamma in ((4, 400, True, 24, 31, None), (2, 300, True, 32, 32, None),
+                                     (3, 300, False, 24, 33, None),
+                                     (4, 500, True, 24, 34, lambda x: math.ceil(0.1 * x))):
+        space = {f"x{j}": FloatDistribution(0, 1) for j in range(8 if mv else 3)}
+        kw = {} if gamma is None else {"gamma": gamma}
+        sampler = TPESampler(seed=seed, n_ei_candidates=C, multivariate=mv, n_startup_trials=0, **kw)
+        study = optuna.create_study(directions=["minimize"] * m, sampler=sampler)
+        r2 = np.random.RandomState(seed + 1)
+        X = r2.uniform(0, 1, (n, len(space)))
+        cs = np.linspace(0.2, 0.8, m)
+        vals = np.stack([((X - c) ** 2).sum(1) for c in cs], 1)
+        trials = []
+        for i in range(n):
+            t = create_trial(values=list(map(float, vals[i])), params=dict(zip(space, X[i].tolist())),
+                             distributions=space)
+            t.number = i
+            t._trial_id = i
+            trials.append(t)
+        captured = {}
+        orig_acq = TPESampler._compute_acquisition_func
+
+        def spy(self, samples, mpe_below, mpe_above):
+            captured.setdefault("calls", []).append(
+                ({k: v.copy() for k, v in samples.items()}, mpe_below.log_pdf(samples), mpe_above.log_pdf(samples),
+                 np.asarray(mpe_below._mixture_distribution.weights)))
+            return orig_acq(self, samples, mpe_below, mpe_above)
+
+        frozen = create_trial(state=TrialState.RUNNING, params={}, distributions={})
+        frozen.number = n
+        frozen._trial_id = n
+        t = f"mosg{ci}/"
+        out[t + "X"], out[t + "values"] = X, vals
+        out[t + "cfg"] = np.asarray([mv, C, seed, sampler._gamma(n), m], dtype=float)
+        with patch.object(study._storage, "get_all_trials", return_value=trials), \
+                patch.object(TPESampler, "_compute_acquisition_func", spy):
+            if mv:
+                res = sampler._sample(study, frozen, dict(space))
+                out[t + "ret"] = np.asarray([res[k] for k in space])
+            else:
+                ret = []
+                for name, d in space.items():
+                    ret.append(sampler._sample(study, frozen, {name: d})[name])
+                out[t + "ret"] = np.asarray(ret)
+        for q, (smp, ll, lg, wb) in enumerate(captured["calls"]):
+            out[f"{t}c{q}/samples"] = np.asarray([smp[k] for k in smp]).T
+            out[f"{t}c{q}/ll"], out[f"{t}c{q}/lg"], out[f"{t}c{q}/wb"] = ll, lg, wb
+        out[t + "ncalls"] = np.asarray(len(captured["calls"]))
+        ci += 1
+    out["mosg_n"] = np.asarray(ci)
+    return out
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "motpe.npz"), **gold_mo())
     np.savez_compressed(os.path.join(OUT, "math.npz"), **gold_math())
 
     pz = {}

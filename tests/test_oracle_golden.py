@@ -89,3 +89,56 @@ def test_chunked_logpdf_matches_unchunked_for_continuous():
     full = orc.mixture_log_pdf(mix, g[t + "samples"][:32])
     same(orc.mixture_log_pdf_chunked(mix, g[t + "samples"][:32], rows=5), full)
     same(full, g[t + "lg"][:32])
+
+
+def test_motpe_primitives_bit_exact():
+    from oracle import motpe as mo
+    g = load("motpe.npz")
+    for ci in range(int(g["hv_n"])):
+        t = f"hv{ci}/"
+        v, ref = g[t + "v"], g[t + "ref"]
+        same(mo.reference_point(v), ref)
+        same(mo.hypervolume(v, ref), g[t + "hv"])
+        assert np.array_equal(mo.nondomination_rank(v), g[t + "rank"])
+        n = v.shape[0]
+        assert np.array_equal(mo.nondomination_rank(v, n_below=max(1, n // 3)), g[t + "rank_nb"])
+        assert np.array_equal(mo.solve_hssp(v, np.arange(n) * 3, max(1, n // 2), ref), g[t + "hssp"])
+
+
+def test_motpe_split_and_weights_bit_exact():
+    from oracle import motpe as mo
+    g = load("motpe.npz")
+    for ci in range(int(g["mo_n"])):
+        t = f"mo{ci}/"
+        v, nb = g[t + "v"], int(g[t + "nb"])
+        below = mo.split_complete_mo(v, nb)
+        assert np.array_equal(below, g[t + "below"]), ci
+        same(mo.weights_below_mo(v[below]), g[t + "w"])
+
+
+def test_motpe_suggest_bit_exact():
+    from oracle import motpe as mo
+    g = load("motpe.npz")
+    for ci in range(int(g["mosg_n"])):
+        t = f"mosg{ci}/"
+        mv, C, seed, n_below, m = g[t + "cfg"]
+        X, vals = g[t + "X"], g[t + "values"]
+        n, P = X.shape
+        params = [orc.Param("float", 0.0, 1.0) for _ in range(P)]
+        cat, key = np.zeros(n, np.int8), np.zeros((n, 2))
+        cfg = orc.Config(multivariate=bool(mv))
+        rng = np.random.RandomState(int(seed))
+        sel = lambda comp, k: comp[mo.split_complete_mo(vals[comp], k)]  # noqa: E731
+        below, _ = orc.split_trials(cat, key, int(n_below), sel)
+        wb = mo.weights_below_mo(vals[below])
+        calls = [list(range(P))] if mv else [[j] for j in range(P)]
+        ret = []
+        for q, cols in enumerate(calls):
+            s = orc.suggest(X, cat, key, params, cols, cfg, int(n_below), int(C), rng, weights_below=wb,
+                            complete_selector=sel)
+            same(s.mix_below.weights, g[f"{t}c{q}/wb"])
+            same(s.samples, g[f"{t}c{q}/samples"])
+            same(s.logl, g[f"{t}c{q}/ll"])
+            same(s.logg, g[f"{t}c{q}/lg"])
+            ret.extend(s.x.tolist())
+        same(np.asarray(ret), g[t + "ret"])
