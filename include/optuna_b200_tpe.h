@@ -98,6 +98,12 @@ int tpe_history_append(tpe_ctx* ctx, const double* X, const int8_t* category, co
 /* Same, with DEVICE pointers on ctx's device (used after an NCCL broadcast of the history). */
 int tpe_history_set_device(tpe_ctx* ctx, const double* dX, const int8_t* dcategory,
                            const double* dkey, int64_t n, const uint8_t* col_has_missing);
+/* Multi-objective studies: objective values of rows [at_row, at_row + n), sign-normalised so that
+ * every objective is minimised (sampler.py:755).  values [n, n_objectives] row-major.  With
+ * n_objectives >= 2 the COMPLETE group is split by non-domination rank + greedy hypervolume subset
+ * selection (sampler.py:745-779) and l(x) is weighted by hypervolume contributions (:824-863)
+ * unless tpe_build is given explicit below-weights.  n_objectives <= 8; at most 64 below trials. */
+int tpe_history_set_values(tpe_ctx* ctx, const double* values, int64_t n, int32_t n_objectives, int64_t at_row);
 int64_t tpe_history_size(tpe_ctx* ctx);
 /* Device pointers of the resident history (for the NCCL broadcast done by the host plumbing). */
 int tpe_history_device_ptrs(tpe_ctx* ctx, double** dX, int8_t** dcategory, double** dkey);
@@ -139,6 +145,8 @@ int tpe_get_split(tpe_ctx* ctx, int64_t* below_rows, int64_t* above_rows);
  * weights [K]; mu, sigma [K, n_cols] (categorical columns hold the observed choice index / 0);
  * K = n_obs + 1.  Any pointer may be NULL. */
 int tpe_get_mixture(tpe_ctx* ctx, int which, double* weights, double* mu, double* sigma);
+/* MOTPE: raw hypervolume weights of ALL below trials (length n_below_all) of the last tpe_build. */
+int tpe_get_mo_weights(tpe_ctx* ctx, double* weights);
 /* Candidates / log-densities of the last tpe_sample_and_select (all asks).
  * samples [n_asks * C, n_cols]; logl, logg [n_asks * C].  Any pointer may be NULL. */
 int tpe_get_candidates(tpe_ctx* ctx, double* samples, double* logl, double* logg);

@@ -41,6 +41,7 @@ SYMBOLS = {
     "tpe_history_set": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "tpe_history_append": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "tpe_history_set_device": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
+    "tpe_history_set_values": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64]),
     "tpe_history_size": (C.c_int64, [_P]),
     "tpe_history_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "tpe_prepare": (C.c_int, [_P, C.POINTER(Cfg), _P, C.c_int32, C.POINTER(SplitInfo)]),
@@ -50,6 +51,7 @@ SYMBOLS = {
     "tpe_get_split_info": (C.c_int, [_P, C.POINTER(SplitInfo)]),
     "tpe_get_split": (C.c_int, [_P, _P, _P]),
     "tpe_get_mixture": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "tpe_get_mo_weights": (C.c_int, [_P, _P]),
     "tpe_get_candidates": (C.c_int, [_P, _P, _P, _P]),
     "tpe_logpdf": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P]),
     "tpe_last_timing": (C.c_int, [_P, _P, _P]),

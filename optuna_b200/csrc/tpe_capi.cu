@@ -3,11 +3,13 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <set>
 #include <string>
@@ -15,6 +17,7 @@
 
 #include "../../include/optuna_b200_tpe.h"
 #include "tpe_kernels.cuh"
+#include "tpe_motpe_kernels.cuh"
 
 using namespace tpe;
 
@@ -86,8 +89,14 @@ struct tpe_ctx {
   DevBuf cat_dist;
 
   // history
-  DevBuf X, cat, key;
+  DevBuf X, cat, key, vals;
+  int32_t M = 1;                 // objectives (>= 2: MOTPE)
+  std::vector<int8_t> cat_h;     // host mirror of the categories (MOTPE list building)
   int64_t N = 0;
+  // MOTPE scratch
+  DevBuf mo_list, mo_alive, mo_dom, mo_first, mo_rank, mo_ctr, mo_tie, mo_ntie, mo_lexpos, mo_isdup, mo_sorted,
+      mo_uniq, mo_nuniq, mo_ref, mo_removed, mo_contrib, mo_state, mo_arena, mo_chosen, mo_diag, mo_w;
+  bool mo_weights_ready = false;
   std::vector<uint8_t> col_missing;
   bool history_set = false;
 
@@ -249,9 +258,168 @@ int upload_history(tpe_ctx* ctx, const double* X, const int8_t* category, const 
     CU(cudaMemcpyAsync(ctx->key.as<double>() + at * 2, key, (size_t)n * 16, kind, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  ctx->cat_h.resize((size_t)total);
+  if (n > 0) {
+    if (device_src) CU(cudaMemcpy(ctx->cat_h.data() + at, category, (size_t)n, cudaMemcpyDeviceToHost));
+    else memcpy(ctx->cat_h.data() + at, category, (size_t)n);
+  }
+  if (at == 0) ctx->M = 1;  // a fresh history is single-objective until values are supplied
   ctx->N = total;
   ctx->history_set = true;
   ctx->prepared = ctx->built = ctx->sampled = false;
+  return TPE_OK;
+}
+
+// ---- MOTPE: selection of the below part of the COMPLETE group (sampler.py:745-779) ----------------
+// Fills ctx->member (u8 per history row) and returns how many COMPLETE trials went below.
+int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
+  cudaStream_t st = ctx->stream;
+  const int M = ctx->M;
+  const int64_t N = ctx->N;
+  std::vector<int64_t> list;
+  for (int64_t i = 0; i < N; ++i)
+    if (ctx->cat_h[i] == TPE_CAT_COMPLETE) list.push_back(i);
+  const int nc = (int)list.size();
+  const int64_t m = std::min<int64_t>(std::max<int64_t>(n_below, 0), nc);
+  *taken = m;
+  CU(ctx->member.ensure((size_t)std::max<int64_t>(N, 1)));
+  CU(cudaMemsetAsync(ctx->member.p, 0, (size_t)std::max<int64_t>(N, 1), st));
+  if (m == 0) return TPE_OK;
+  if (m > kMoMaxSet)
+    return fail(ctx, TPE_E_INVALID, "MOTPE supports at most %d below trials (got %lld)", kMoMaxSet, (long long)m);
+  if (m == nc) {
+    std::vector<uint8_t> mem((size_t)N, 0);
+    for (int64_t r : list) mem[(size_t)r] = 1;
+    CU(cudaMemcpyAsync(ctx->member.p, mem.data(), (size_t)N, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return TPE_OK;
+  }
+  CU(ctx->mo_list.ensure((size_t)nc * 8));
+  CU(cudaMemcpyAsync(ctx->mo_list.p, list.data(), (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+  for (DevBuf* b : {&ctx->mo_alive, &ctx->mo_dom, &ctx->mo_first, &ctx->mo_isdup, &ctx->mo_removed})
+    CU(b->ensure((size_t)nc));
+  for (DevBuf* b : {&ctx->mo_rank, &ctx->mo_tie, &ctx->mo_lexpos, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_chosen})
+    CU(b->ensure((size_t)nc * 4));
+  CU(ctx->mo_ctr.ensure(sizeof(MoCounters)));
+  CU(ctx->mo_ntie.ensure(16));
+  CU(ctx->mo_nuniq.ensure(16));
+  CU(ctx->mo_ref.ensure(kMoMaxM * 8));
+  CU(ctx->mo_contrib.ensure((size_t)nc * 8));
+  CU(ctx->mo_diag.ensure((size_t)nc * 16));
+  CU(ctx->mo_state.ensure(sizeof(HsspState)));
+  CU(cudaMemsetAsync(ctx->mo_alive.p, 1, (size_t)nc, st));
+  CU(cudaMemsetAsync(ctx->mo_rank.p, 0, (size_t)nc * 4, st));
+  CU(cudaMemsetAsync(ctx->mo_ctr.p, 0, sizeof(MoCounters), st));
+  const double* vals = ctx->vals.as<double>();
+  const int64_t* dlist = ctx->mo_list.as<int64_t>();
+  const int gb = (nc + 255) / 256;
+  // peel Pareto fronts until n_below unique vectors are ranked
+  std::vector<int64_t> rank_count;
+  MoCounters ctr{};
+  int r = 0;
+  int64_t prev_all = 0;
+  for (;;) {
+    k_mo_peel<<<gb, 256, 256 * M * 8, st>>>(vals, M, dlist, nc, ctx->mo_alive.as<uint8_t>(), ctx->mo_dom.as<uint8_t>(),
+                                             r == 0 ? ctx->mo_first.as<uint8_t>() : nullptr, ctx->mo_ctr.as<MoCounters>());
+    k_mo_commit<<<gb, 256, 0, st>>>(nc, ctx->mo_alive.as<uint8_t>(), ctx->mo_dom.as<uint8_t>(),
+                                     ctx->mo_first.as<uint8_t>(), ctx->mo_rank.as<int32_t>(), r,
+                                     ctx->mo_ctr.as<MoCounters>());
+    ctx->launch_counter += 2;
+    CU(cudaMemcpyAsync(&ctr, ctx->mo_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    rank_count.push_back(ctr.covered_all - prev_all);
+    prev_all = ctr.covered_all;
+    ++r;
+    const int64_t goal = std::min<int64_t>(m, ctr.n_unique);
+    if (ctr.covered_unique >= goal || ctr.covered_all >= nc) break;
+    if (rank_count.back() == 0) return fail(ctx, TPE_E_INVALID, "MOTPE rank peeling made no progress (NaN objective values?)");
+  }
+  if (ctr.covered_all < nc) {
+    k_mo_fill_rank<<<gb, 256, 0, st>>>(nc, ctx->mo_alive.as<uint8_t>(), ctx->mo_rank.as<int32_t>(), r);
+    ctx->launch_counter++;
+    rank_count.push_back(nc - ctr.covered_all);
+  }
+  // whole ranks that fit
+  int64_t cum = 0;
+  int last = -1;
+  for (size_t q = 0; q < rank_count.size(); ++q) {
+    if (cum + rank_count[q] > m) break;
+    cum += rank_count[q];
+    last = (int)q;
+  }
+  k_mo_gather_rank<<<1, 1024, 0, st>>>(nc, ctx->mo_rank.as<int32_t>(), last, dlist, ctx->member.as<uint8_t>(),
+                                       ctx->mo_tie.as<int32_t>(), ctx->mo_ntie.as<int>());
+  ctx->launch_counter++;
+  const int subset = (int)(m - cum);
+  if (subset > 0) {
+    int n_tie = 0;
+    CU(cudaMemcpyAsync(&n_tie, ctx->mo_ntie.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    k_mo_refpoint<<<1, 256, 0, st>>>(vals, M, dlist, ctx->mo_tie.as<int32_t>(), n_tie, ctx->mo_ref.as<double>());
+    double ref[kMoMaxM];
+    CU(cudaMemcpyAsync(ref, ctx->mo_ref.p, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->launch_counter += 1;
+    bool finite = true;
+    for (int j = 0; j < M; ++j) finite = finite && std::isfinite(ref[j]);
+    std::vector<int32_t> chosen;
+    int n_chosen = subset;
+    bool chosen_on_device = false;
+    if (!finite) {
+      for (int i = 0; i < subset; ++i) chosen.push_back(i);  // rank_i_indices[:subset_size] (hssp.py:106-107)
+    } else {
+      k_mo_lexrank<<<(n_tie + 127) / 128, 128, 0, st>>>(vals, M, dlist, ctx->mo_tie.as<int32_t>(), n_tie,
+                                                         ctx->mo_lexpos.as<int32_t>(), ctx->mo_isdup.as<uint8_t>());
+      k_mo_unique<<<1, 1024, 0, st>>>(n_tie, ctx->mo_lexpos.as<int32_t>(), ctx->mo_isdup.as<uint8_t>(),
+                                      ctx->mo_sorted.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), ctx->mo_nuniq.as<int>());
+      ctx->launch_counter += 2;
+      int nu = 0;
+      CU(cudaMemcpyAsync(&nu, ctx->mo_nuniq.p, 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      chosen_on_device = true;
+      if (nu <= subset) {
+        // every unique vector, then the first duplicates in trial order (hssp.py:162-171)
+        CU(cudaMemcpyAsync(ctx->mo_chosen.p, ctx->mo_uniq.p, (size_t)nu * 4, cudaMemcpyDeviceToDevice, st));
+        if (nu < subset) {
+          k_mo_fill_dups<<<1, 1024, 0, st>>>(n_tie, ctx->mo_isdup.as<uint8_t>(), subset - nu,
+                                             ctx->mo_chosen.as<int32_t>(), nu);
+          ctx->launch_counter++;
+        }
+      } else {
+        CU(cudaMemsetAsync(ctx->mo_state.p, 0, sizeof(HsspState), st));
+        CU(cudaMemsetAsync(ctx->mo_removed.p, 0, (size_t)nc, st));
+        if (M == 2) {
+          k_hssp_2d<<<1, 256, 0, st>>>(vals, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu, subset,
+                                       ctx->mo_ref.as<double>(), ctx->mo_diag.as<double>(),
+                                       ctx->mo_removed.as<uint8_t>(), ctx->mo_state.as<HsspState>());
+          ctx->launch_counter++;
+        } else {
+          const size_t stride = (size_t)(subset + 2) * M + hv_arena_doubles(subset + 1, M);
+          CU(ctx->mo_arena.ensure((size_t)nu * stride * 8));
+          for (int t = 0; t < subset; ++t) {
+            k_hssp_contrib<<<(nu + 63) / 64, 64, 0, st>>>(vals, M, dlist, ctx->mo_tie.as<int32_t>(),
+                                                          ctx->mo_uniq.as<int32_t>(), nu, ctx->mo_removed.as<uint8_t>(),
+                                                          ctx->mo_ref.as<double>(), ctx->mo_state.as<HsspState>(),
+                                                          ctx->mo_contrib.as<double>(), ctx->mo_arena.as<double>(),
+                                                          stride);
+            k_hssp_pick<<<1, 256, 0, st>>>(vals, M, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu,
+                                           ctx->mo_removed.as<uint8_t>(), ctx->mo_contrib.as<double>(),
+                                           ctx->mo_state.as<HsspState>());
+            ctx->launch_counter += 2;
+          }
+        }
+        CU(cudaMemcpyAsync(ctx->mo_chosen.p, (char*)ctx->mo_state.p + offsetof(HsspState, pick), (size_t)subset * 4,
+                           cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    if (!chosen_on_device)
+      CU(cudaMemcpyAsync(ctx->mo_chosen.p, chosen.data(), (size_t)n_chosen * 4, cudaMemcpyHostToDevice, st));
+    k_mo_mark<<<(n_chosen + 127) / 128, 128, 0, st>>>(dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_chosen.as<int32_t>(),
+                                                      n_chosen, ctx->member.as<uint8_t>());
+    ctx->launch_counter++;
+    CU(cudaStreamSynchronize(st));
+  }
+  CU(cudaGetLastError());
   return TPE_OK;
 }
 
@@ -332,15 +500,32 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
     ctx->launch_counter++;
   }
   const double* w_dev = nullptr;
+  const int64_t* w_pos = nullptr;
   if (w_host != nullptr && n > 0) {
     CU(e.wstage.ensure((size_t)n * 8));
     CU(cudaMemcpyAsync(e.wstage.p, w_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     w_dev = e.wstage.as<double>();
+  } else if (which == 0 && ctx->M >= 2 && n > 0) {
+    // MOTPE: hypervolume weights of ALL below trials, then the rows holding every selected param
+    // pick theirs through `pos` (weights_below[param_mask_below], sampler.py:570-576)
+    const int nba = (int)ctx->info.n_below_all;
+    if (nba > kMoMaxSet)
+      return fail(ctx, TPE_E_INVALID, "MOTPE supports at most %d below trials (got %d)", kMoMaxSet, nba);
+    if (nba != n) return fail(ctx, TPE_E_INVALID, "MOTPE with partially missing parameters in the below set is not supported yet");
+    const size_t stride = (size_t)(nba + 2) * ctx->M + hv_arena_doubles(nba + 1, ctx->M);
+    CU(ctx->mo_arena.ensure((size_t)(nba + 1) * stride * 8));
+    CU(ctx->mo_w.ensure((size_t)kMoMaxSet * 8));
+    k_mo_weights<<<1, kMoMaxSet, 0, st>>>(ctx->vals.as<double>(), ctx->M, e.rows.as<int64_t>(), nba,
+                                          ctx->cat.as<int8_t>(), ctx->mo_w.as<double>(), ctx->mo_arena.as<double>(),
+                                          stride);
+    ctx->launch_counter++;
+    ctx->mo_weights_ready = true;
+    w_dev = ctx->mo_w.as<double>();
   }
   {
     const int nparts = grid_for(K, 2048, ctx->sm_count * 2);
     CU(e.wpart.ensure((size_t)nparts * 8));
-    k_wraw<<<nparts, 256, 0, st>>>(w_dev, n, ctx->cfg.prior_weight, e.w.as<double>(), e.wpart.as<double>());
+    k_wraw<<<nparts, 256, 0, st>>>(w_dev, w_pos, n, ctx->cfg.prior_weight, e.w.as<double>(), e.wpart.as<double>());
     k_wfinal<<<grid_for(k_alloc, 256, ctx->sm_count * 4), 256, 0, st>>>(
         e.wpart.as<double>(), nparts, n, e.w.as<double>(), e.logw.as<double>(), e.cst_part.as<double>(),
         e.cst.as<double>(), which == 0 ? e.cdf.as<double>() : nullptr, k_alloc);
@@ -472,7 +657,10 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (DevBuf* b : {&ctx->cat_dist, &ctx->X, &ctx->cat, &ctx->key, &ctx->cols, &ctx->row_ok, &ctx->member,
+  for (DevBuf* b : {&ctx->cat_dist, &ctx->X, &ctx->cat, &ctx->key, &ctx->vals, &ctx->mo_list, &ctx->mo_alive, &ctx->mo_dom,
+                    &ctx->mo_first, &ctx->mo_rank, &ctx->mo_ctr, &ctx->mo_tie, &ctx->mo_ntie, &ctx->mo_lexpos,
+                    &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed,
+                    &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
                     &ctx->cand_a, &ctx->cand_b, &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
@@ -561,6 +749,36 @@ int tpe_history_set_device(tpe_ctx* ctx, const double* dX, const int8_t* dcatego
   if (set_device(ctx)) return TPE_E_CUDA;
   for (size_t j = 0; j < ctx->col_missing.size(); ++j) ctx->col_missing[j] = col_has_missing ? col_has_missing[j] : 1;
   return upload_history(ctx, dX, dcategory, dkey, n, 0, true);
+}
+
+int tpe_history_set_values(tpe_ctx* ctx, const double* values, int64_t n, int32_t n_objectives, int64_t at_row) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->history_set) return fail(ctx, TPE_E_STATE, "tpe_history_set must precede tpe_history_set_values");
+  if (n_objectives < 1 || n_objectives > kMoMaxM)
+    return fail(ctx, TPE_E_INVALID, "n_objectives must be in [1, %d]", kMoMaxM);
+  if (n < 0 || at_row < 0 || at_row + n > ctx->N || (n > 0 && !values))
+    return fail(ctx, TPE_E_INVALID, "bad values range");
+  if (at_row > 0 && n_objectives != ctx->M) return fail(ctx, TPE_E_INVALID, "n_objectives changed");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  CU(ctx->vals.grow((size_t)std::max<int64_t>(ctx->N, 1) * n_objectives * 8, (size_t)at_row * n_objectives * 8,
+                    ctx->stream));
+  if (n > 0)
+    CU(cudaMemcpyAsync(ctx->vals.as<double>() + at_row * n_objectives, values, (size_t)n * n_objectives * 8,
+                       cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->M = n_objectives;
+  ctx->prepared = ctx->built = ctx->sampled = false;
+  return TPE_OK;
+}
+
+int tpe_get_mo_weights(tpe_ctx* ctx, double* weights) {
+  if (!ctx || !weights) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->built || !ctx->mo_weights_ready) return fail(ctx, TPE_E_STATE, "no MOTPE weights available");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  CU(cudaMemcpy(weights, ctx->mo_w.p, (size_t)ctx->info.n_below_all * 8, cudaMemcpyDeviceToHost));
+  return TPE_OK;
 }
 
 int64_t tpe_history_size(tpe_ctx* ctx) { return ctx ? ctx->N : -1; }
@@ -662,11 +880,21 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
     ctx->launch_counter++;
     rowok = ctx->row_ok.as<uint8_t>();
   }
+  const uint8_t* pre_member = nullptr;
+  int64_t nb_rest = cfg->n_below;
+  ctx->mo_weights_ready = false;
+  if (ctx->M >= 2) {
+    int64_t taken = 0;
+    int rc = mo_select_complete(ctx, cfg->n_below, &taken);
+    if (rc) return rc;
+    pre_member = ctx->member.as<uint8_t>();
+    nb_rest = std::max<int64_t>(0, cfg->n_below - taken);
+  }
   {
     CU(ctx->split_work.ensure(sizeof(SplitWork)));
     CU(cudaMemsetAsync(ctx->split_work.p, 0, sizeof(SplitWork), ctx->stream));
     int n_i = (int)N;
-    int64_t nb = cfg->n_below;
+    int64_t nb = nb_rest;
     const int8_t* d_cat = ctx->cat.as<int8_t>();
     const double* d_key = ctx->key.as<double>();
     SplitWork* d_wk = ctx->split_work.as<SplitWork>();
@@ -674,7 +902,7 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
     int64_t* d_p = ctx->est[0].pos.as<int64_t>();
     int64_t* d_a = ctx->est[1].rows.as<int64_t>();
     int64_t* d_c = ctx->counts.as<int64_t>();
-    void* args[] = {&n_i, &d_cat, &d_key, &nb, &rowok, &d_wk, &d_b, &d_p, &d_a, &d_c};
+    void* args[] = {&n_i, &d_cat, &d_key, &nb, &rowok, &pre_member, &d_wk, &d_b, &d_p, &d_a, &d_c};
     const int G = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (N + 2047) / 2048));
     CU(cudaLaunchCooperativeKernel((const void*)k_split_coop, dim3(G), dim3(512), args, 0, ctx->stream));
   }

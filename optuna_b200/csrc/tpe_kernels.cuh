@@ -183,7 +183,8 @@ __device__ __forceinline__ void top_bytes(int nb, uint64_t& hi, uint64_t& lo) {
 
 __global__ void __launch_bounds__(512, 1)
 k_split_coop(int n, const int8_t* __restrict__ cat, const double* __restrict__ key, int64_t n_below,
-             const uint8_t* __restrict__ row_ok, SplitWork* __restrict__ wk, int64_t* __restrict__ below_rows,
+             const uint8_t* __restrict__ row_ok, const uint8_t* __restrict__ pre_member, SplitWork* __restrict__ wk,
+             int64_t* __restrict__ below_rows,
              int64_t* __restrict__ below_pos, int64_t* __restrict__ above_rows, int64_t* __restrict__ counts) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   __shared__ int s_hist[256];
@@ -204,9 +205,11 @@ k_split_coop(int n, const int8_t* __restrict__ cat, const double* __restrict__ k
   grid.sync();
 
   // which category holds the cut?  (earlier ones are entirely below, later ones entirely above)
+  // pre_member != nullptr: the COMPLETE group was selected elsewhere (multi-objective split); n_below
+  // is what is left for the PRUNED / infeasible groups.
   int64_t remaining = n_below < 0 ? 0 : n_below;
   int thr_cat = 3, need = 0;
-  for (int c = 0; c < 3; ++c) {
+  for (int c = (pre_member != nullptr ? 1 : 0); c < 3; ++c) {
     const int cnt = wk->cat_count[c];
     if (remaining >= cnt) { remaining -= cnt; continue; }
     thr_cat = c;
@@ -263,6 +266,7 @@ k_split_coop(int n, const int8_t* __restrict__ cat, const double* __restrict__ k
   // classification of trial i: 2 = below, 1 = boundary tie (identical 128-bit key), 0 = above
   auto classify = [&](int i) -> int {
     const int c = cat[i];
+    if (c == 0 && pre_member != nullptr) return pre_member[i] ? 2 : 0;
     if (c >= 3 || c > thr_cat) return 0;
     if (c < thr_cat) return 2;
     if (need <= 0 && !take_all_eq) return 0;
@@ -686,11 +690,11 @@ __global__ void k_build_mv(const double* __restrict__ X, int32_t pall, const int
 
 // Multi-CTA version of k_weights: raw weights + per-block partial sums, then normalisation.
 // Partial sums are combined in a fixed order, so the result is deterministic.
-__device__ __forceinline__ double raw_weight(const double* __restrict__ w_in, int64_t n, int64_t k,
-                                             double prior_weight) {
+__device__ __forceinline__ double raw_weight(const double* __restrict__ w_in, const int64_t* __restrict__ pos,
+                                             int64_t n, int64_t k, double prior_weight) {
   if (n == 0) return 1.0;
   if (k == n) return prior_weight;
-  if (w_in != nullptr) return w_in[k];
+  if (w_in != nullptr) return w_in[pos != nullptr ? pos[k] : k];
   const int64_t nramp = n - 25;
   if (n < 25 || k >= nramp) return 1.0;
   if (k == nramp - 1 && nramp > 1) return 1.0;
@@ -699,15 +703,15 @@ __device__ __forceinline__ double raw_weight(const double* __restrict__ w_in, in
   return TPE_ADD(TPE_MUL((double)k, step), start);
 }
 __global__ void __launch_bounds__(256)
-k_wraw(const double* __restrict__ w_in, int64_t n, double prior_weight, double* __restrict__ w,
-       double* __restrict__ part) {
+k_wraw(const double* __restrict__ w_in, const int64_t* __restrict__ pos, int64_t n, double prior_weight,
+       double* __restrict__ w, double* __restrict__ part) {
   __shared__ double s_red[8];
   const int64_t K = n + 1;
   const int64_t chunk = (K + gridDim.x - 1) / gridDim.x;
   const int64_t lo = blockIdx.x * chunk, hi = (lo + chunk < K) ? lo + chunk : K;
   double acc = 0.0;
   for (int64_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
-    const double r = raw_weight(w_in, n, k, prior_weight);
+    const double r = raw_weight(w_in, pos, n, k, prior_weight);
     w[k] = r;
     acc += r;
   }

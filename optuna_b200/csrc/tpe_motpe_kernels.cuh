@@ -1,0 +1,453 @@
+// MOTPE kernels: non-domination ranks, greedy hypervolume subset selection, hypervolume weights.
+//   k_mo_peel / k_mo_commit      optuna/study/_multi_objective.py:187-219 (_calculate_nondomination_rank)
+//   k_mo_refpoint                optuna/samplers/_tpe/sampler.py:679-683 (_get_reference_point)
+//   k_mo_lexrank / k_hssp_*      optuna/_hypervolume/hssp.py:10-176 (_solve_hssp)
+//   k_mo_weights                 optuna/samplers/_tpe/sampler.py:824-863
+// vals: [N, M] sign-normalised objective values of the whole history; lists index into it.
+#pragma once
+#include "tpe_common.cuh"
+#include "tpe_motpe.cuh"
+
+namespace tpe {
+
+constexpr int kMoMaxM = 8;       // objectives
+constexpr int kMoMaxSet = 64;    // points entering an exact hypervolume (below set / selected set)
+
+struct MoCounters {
+  int covered_unique, covered_all, n_unique, pad;
+};
+
+// does a dominate b (a <= b everywhere, a != b)?
+__device__ __forceinline__ bool dominates(const double* a, const double* b, int M) {
+  bool le = true, lt = false;
+  for (int j = 0; j < M; ++j) {
+    le = le && (a[j] <= b[j]);
+    lt = lt || (a[j] < b[j]);
+  }
+  return le && lt;
+}
+
+// One peel: dominated[i] = some alive j dominates i.  On the first call also is_first[i] = no
+// earlier trial has the identical vector (np.unique semantics: duplicates share a rank and count once).
+__global__ void k_mo_peel(const double* __restrict__ vals, int M, const int64_t* __restrict__ list, int nc,
+                          const uint8_t* __restrict__ alive, uint8_t* __restrict__ dominated,
+                          uint8_t* __restrict__ is_first, MoCounters* __restrict__ ctr) {
+  extern __shared__ double s_tile[];  // 256 * M
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double me[kMoMaxM];
+  const bool act = i < nc && alive[i];
+  if (i < nc)
+    for (int j = 0; j < M; ++j) me[j] = vals[list[i] * M + j];
+  bool dom = false, dup_before = false;
+  for (int t0 = 0; t0 < nc; t0 += blockDim.x) {
+    const int q = t0 + threadIdx.x;
+    __syncthreads();
+    if (q < nc)
+      for (int j = 0; j < M; ++j) s_tile[threadIdx.x * M + j] = vals[list[q] * M + j];
+    __syncthreads();
+    const int lim = min((int)blockDim.x, nc - t0);
+    if (i < nc) {
+      for (int r = 0; r < lim; ++r) {
+        const int jdx = t0 + r;
+        const double* o = s_tile + r * M;
+        if (act && alive[jdx]) dom = dom || dominates(o, me, M);
+        if (is_first != nullptr && jdx < i) {
+          bool eq = true;
+          for (int j = 0; j < M; ++j) eq = eq && (o[j] == me[j]);
+          dup_before = dup_before || eq;
+        }
+      }
+    }
+  }
+  if (i < nc) {
+    dominated[i] = dom ? 1 : 0;
+    if (is_first != nullptr) {
+      is_first[i] = dup_before ? 0 : 1;
+      if (!dup_before) atomicAdd(&ctr->n_unique, 1);
+    }
+  }
+}
+// front = alive & !dominated gets rank r
+__global__ void k_mo_commit(int nc, uint8_t* __restrict__ alive, const uint8_t* __restrict__ dominated,
+                            const uint8_t* __restrict__ is_first, int32_t* __restrict__ rank, int r,
+                            MoCounters* __restrict__ ctr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc || !alive[i] || dominated[i]) return;
+  rank[i] = r;
+  alive[i] = 0;
+  atomicAdd(&ctr->covered_all, 1);
+  if (is_first[i]) atomicAdd(&ctr->covered_unique, 1);
+}
+__global__ void k_mo_fill_rank(int nc, const uint8_t* __restrict__ alive, int32_t* __restrict__ rank, int r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nc && alive[i]) rank[i] = r;
+}
+
+// Ordered list of the positions with rank == r (single CTA of 1024 threads) and the membership
+// flags of ranks <= last.
+__global__ void __launch_bounds__(1024, 1)
+k_mo_gather_rank(int nc, const int32_t* __restrict__ rank, int last, const int64_t* __restrict__ list,
+                 uint8_t* __restrict__ member /*[N] by history row*/, int32_t* __restrict__ tie_pos, int* n_tie) {
+  __shared__ int s_warp[32];
+  int cnt = 0;
+  for (int base = 0; base < nc; base += 1024) {
+    const int i = base + threadIdx.x;
+    const bool v = i < nc;
+    if (v && rank[i] <= last) member[list[i]] = 1;
+    const bool f = v && rank[i] == last + 1;
+    const int2 rr = block_rank_1024(f, s_warp);
+    if (f) tie_pos[cnt + rr.x] = i;
+    cnt += rr.y;
+  }
+  if (threadIdx.x == 0) *n_tie = cnt;
+}
+
+// reference point of a point list: max(1.1 w, 0.9 w), 0 -> EPS
+__global__ void __launch_bounds__(256)
+k_mo_refpoint(const double* __restrict__ vals, int M, const int64_t* __restrict__ list, const int32_t* __restrict__ sub,
+              int n, double* __restrict__ ref) {
+  __shared__ double s_red[256];
+  for (int j = 0; j < M; ++j) {
+    double w = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const double v = vals[list[sub ? sub[i] : i] * M + j];
+      w = (v > w || v != v) ? v : w;
+    }
+    s_red[threadIdx.x] = w;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        const double a = s_red[threadIdx.x], b = s_red[threadIdx.x + o];
+        s_red[threadIdx.x] = (b > a || b != b) ? b : a;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const double worst = s_red[0];
+      double r = fmax(TPE_MUL(1.1, worst), TPE_MUL(0.9, worst));
+      if (r == 0.0) r = 1e-12;
+      ref[j] = r;
+    }
+    __syncthreads();
+  }
+}
+
+// Lexicographic position of every tie point among the tie points (duplicates ordered by original
+// position) + duplicate flag (an identical vector occurs earlier).  O(n^2), n = |tie rank|.
+__global__ void k_mo_lexrank(const double* __restrict__ vals, int M, const int64_t* __restrict__ list,
+                             const int32_t* __restrict__ tie_pos, int n, int32_t* __restrict__ lexpos,
+                             uint8_t* __restrict__ is_dup) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double me[kMoMaxM];
+  for (int j = 0; j < M; ++j) me[j] = vals[list[tie_pos[i]] * M + j];
+  int before = 0;
+  bool dup = false;
+  for (int q = 0; q < n; ++q) {
+    const double* o = vals + list[tie_pos[q]] * M;
+    const int c = lex_cmp(o, me, M);
+    if (c < 0 || (c == 0 && q < i)) ++before;
+    if (c == 0 && q < i) dup = true;
+  }
+  lexpos[i] = before;
+  is_dup[i] = dup ? 1 : 0;
+}
+// sorted[lexpos[i]] = i ; then the unique list in lexicographic order (single CTA)
+__global__ void __launch_bounds__(1024, 1)
+k_mo_unique(int n, const int32_t* __restrict__ lexpos, const uint8_t* __restrict__ is_dup,
+            int32_t* __restrict__ sorted, int32_t* __restrict__ uniq /*tie-local index of first occurrences*/,
+            int* n_unique) {
+  __shared__ int s_warp[32];
+  for (int i = threadIdx.x; i < n; i += 1024) sorted[lexpos[i]] = i;
+  __syncthreads();
+  int cnt = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int p = base + threadIdx.x;
+    const bool f = p < n && !is_dup[sorted[p]];
+    const int2 rr = block_rank_1024(f, s_warp);
+    if (f) uniq[cnt + rr.x] = sorted[p];
+    cnt += rr.y;
+  }
+  if (threadIdx.x == 0) *n_unique = cnt;
+}
+
+struct HsspState {
+  double hv;            // hypervolume of the selected set (running sum of picked contributions)
+  int n_sel;
+  int pad;
+  double sel[kMoMaxSet * kMoMaxM];  // selected vectors, pick order
+  int32_t pick[kMoMaxSet];          // tie-local index of the picks
+};
+
+// Exact contribution of every remaining unique candidate given the selected set
+// (hssp.py:45-97 evaluated without the lazy skipping, which cannot change the argmax).
+__global__ void k_hssp_contrib(const double* __restrict__ vals, int M, const int64_t* __restrict__ list,
+                               const int32_t* __restrict__ tie_pos, const int32_t* __restrict__ uniq, int nu,
+                               const uint8_t* __restrict__ removed, const double* __restrict__ ref,
+                               const HsspState* __restrict__ st, double* __restrict__ contrib,
+                               double* __restrict__ arena, size_t arena_stride) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nu) return;
+  if (removed[u]) {
+    contrib[u] = -INFINITY;
+    return;
+  }
+  const double* me = vals + list[tie_pos[uniq[u]]] * M;
+  double incl = 1.0;
+  for (int j = 0; j < M; ++j) incl = TPE_MUL(incl, TPE_SUB(ref[j], me[j]));
+  const int t = st->n_sel;
+  if (t == 0 || isinf(incl)) {
+    contrib[u] = incl;
+    return;
+  }
+  if (isinf(st->hv)) {
+    contrib[u] = INFINITY;
+    return;
+  }
+  double* a = arena + (size_t)u * arena_stride;
+  double* pts = a;  // (t + 1) * M
+  double* rest = a + (size_t)(t + 1) * M;
+  if (M <= 3) {
+    // H(S + {i}) - H(S), assume_pareto (points of one non-domination rank are mutually non-dominated)
+    for (int s = 0; s < t; ++s)
+      for (int j = 0; j < M; ++j) pts[s * M + j] = st->sel[s * M + j];
+    for (int j = 0; j < M; ++j) pts[t * M + j] = me[j];
+    contrib[u] = TPE_SUB(hypervolume(pts, t + 1, M, ref, true, rest), st->hv);
+  } else {
+    // H({i}) - H(S limited by i)
+    for (int s = 0; s < t; ++s)
+      for (int j = 0; j < M; ++j) {
+        const double b = st->sel[s * M + j];
+        pts[s * M + j] = me[j] > b ? me[j] : b;
+      }
+    contrib[u] = TPE_SUB(incl, hypervolume(pts, t, M, ref, false, rest));
+  }
+}
+// first argmax (lexicographic order of the unique list), append to the selected set
+__global__ void __launch_bounds__(256)
+k_hssp_pick(const double* __restrict__ vals, int M, const int64_t* __restrict__ list,
+            const int32_t* __restrict__ tie_pos, const int32_t* __restrict__ uniq, int nu,
+            uint8_t* __restrict__ removed, const double* __restrict__ contrib, HsspState* __restrict__ st) {
+  __shared__ double s_val[256];
+  __shared__ int s_idx[256];
+  double best = -INFINITY;
+  int bi = -1;
+  bool bnan = false;
+  for (int u = threadIdx.x; u < nu; u += 256) {
+    if (removed[u]) continue;
+    const double c = contrib[u];
+    const bool cn = c != c;
+    if (bi < 0 || (!bnan && (cn || c > best))) { best = c; bi = u; bnan = cn; }
+  }
+  s_val[threadIdx.x] = best;
+  s_idx[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double a = s_val[threadIdx.x], b = s_val[threadIdx.x + o];
+      const int ia = s_idx[threadIdx.x], ib = s_idx[threadIdx.x + o];
+      bool take_b;
+      if (ib < 0) take_b = false;
+      else if (ia < 0) take_b = true;
+      else {
+        const bool an = a != a, bn = b != b;
+        if (an && bn) take_b = ib < ia;
+        else if (an) take_b = false;
+        else if (bn) take_b = true;
+        else take_b = (b > a) || (b == a && ib < ia);
+      }
+      if (take_b) { s_val[threadIdx.x] = b; s_idx[threadIdx.x] = ib; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int u = s_idx[0];
+    const int t = st->n_sel;
+    st->hv = TPE_ADD(st->hv, s_val[0]);
+    st->pick[t] = uniq[u];
+    const double* me = vals + list[tie_pos[uniq[u]]] * M;
+    for (int j = 0; j < M; ++j) st->sel[t * M + j] = me[j];
+    st->n_sel = t + 1;
+    removed[u] = 1;
+  }
+}
+// 2-objective greedy (_solve_hssp_2d, hssp.py:10-42): one CTA, the unique list is lexsorted.
+__global__ void __launch_bounds__(256)
+k_hssp_2d(const double* __restrict__ vals, const int64_t* __restrict__ list, const int32_t* __restrict__ tie_pos,
+          const int32_t* __restrict__ uniq, int nu, int k, const double* __restrict__ ref,
+          double* __restrict__ diag /*[nu, 2] scratch*/, uint8_t* __restrict__ removed, HsspState* __restrict__ st) {
+  __shared__ double s_val[256];
+  __shared__ int s_idx[256];
+  for (int u = threadIdx.x; u < nu; u += 256) {
+    diag[2 * u] = ref[0];
+    diag[2 * u + 1] = ref[1];
+    removed[u] = 0;
+  }
+  __syncthreads();
+  for (int t = 0; t < k; ++t) {
+    double best = -INFINITY;
+    int bi = -1;
+    bool bnan = false;
+    for (int u = threadIdx.x; u < nu; u += 256) {
+      if (removed[u]) continue;
+      const double* p = vals + list[tie_pos[uniq[u]]] * 2;
+      const double c = TPE_MUL(TPE_SUB(diag[2 * u], p[0]), TPE_SUB(diag[2 * u + 1], p[1]));
+      const bool cn = c != c;
+      if (bi < 0 || (!bnan && (cn || c > best))) { best = c; bi = u; bnan = cn; }
+    }
+    s_val[threadIdx.x] = best;
+    s_idx[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        const double a = s_val[threadIdx.x], b = s_val[threadIdx.x + o];
+        const int ia = s_idx[threadIdx.x], ib = s_idx[threadIdx.x + o];
+        bool take_b;
+        if (ib < 0) take_b = false;
+        else if (ia < 0) take_b = true;
+        else {
+          const bool an = a != a, bn = b != b;
+          if (an && bn) take_b = ib < ia;
+          else if (an) take_b = false;
+          else if (bn) take_b = true;
+          else take_b = (b > a) || (b == a && ib < ia);
+        }
+        if (take_b) { s_val[threadIdx.x] = b; s_idx[threadIdx.x] = ib; }
+      }
+      __syncthreads();
+    }
+    const int j = s_idx[0];
+    const double* pj = vals + list[tie_pos[uniq[j]]] * 2;
+    const double px = pj[0], py = pj[1];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      st->pick[t] = uniq[j];
+      st->n_sel = t + 1;
+      removed[j] = 1;
+    }
+    // rows before j (lexicographically): clip x; rows after: clip y
+    for (int u = threadIdx.x; u < nu; u += 256) {
+      if (u == j || removed[u]) continue;
+      if (u < j) diag[2 * u] = fmin(px, diag[2 * u]);
+      else diag[2 * u + 1] = fmin(py, diag[2 * u + 1]);
+    }
+    __syncthreads();
+  }
+}
+// mark the selected tie points (and, when there are fewer unique vectors than slots, the first
+// duplicates in trial order) in the membership array
+__global__ void k_mo_mark(const int64_t* __restrict__ list, const int32_t* __restrict__ tie_pos,
+                          const int32_t* __restrict__ chosen, int n, uint8_t* __restrict__ member) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) member[list[tie_pos[chosen[i]]]] = 1;
+}
+__global__ void __launch_bounds__(1024, 1)
+k_mo_fill_dups(int n, const uint8_t* __restrict__ is_dup, int want, int32_t* __restrict__ chosen, int at) {
+  __shared__ int s_warp[32];
+  int cnt = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const bool f = i < n && is_dup[i];
+    const int2 rr = block_rank_1024(f, s_warp);
+    if (f && cnt + rr.x < want) chosen[at + cnt + rr.x] = i;
+    cnt += rr.y;
+  }
+}
+
+// Hypervolume weights of the below set (sampler.py:824-863).  One CTA; thread p evaluates the
+// leave-one-out term of below point p.  rows: history rows of the below trials (trial order),
+// cat: category per history row (INFEASIBLE -> EPS weight).
+__global__ void __launch_bounds__(kMoMaxSet)
+k_mo_weights(const double* __restrict__ vals, int M, const int64_t* __restrict__ rows, int n,
+             const int8_t* __restrict__ cat, double* __restrict__ w, double* __restrict__ arena, size_t arena_stride) {
+  __shared__ double s_v[kMoMaxSet * kMoMaxM];   // feasible points, trial order
+  __shared__ double s_ps[kMoMaxSet * kMoMaxM];  // Pareto points, trial order
+  __shared__ double s_ref[kMoMaxM];
+  __shared__ double s_contrib[kMoMaxSet];
+  __shared__ int s_map[kMoMaxSet];      // feasible index -> below index
+  __shared__ int s_front[kMoMaxSet];    // front index -> feasible index
+  __shared__ int s_nf, s_np;
+  __shared__ double s_hv, s_max;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int nf = 0;
+    for (int i = 0; i < n; ++i) {
+      const bool feas = cat[rows[i]] != 2;
+      w[i] = feas ? 1.0 : 1e-12;
+      if (feas) {
+        for (int j = 0; j < M; ++j) s_v[nf * M + j] = vals[rows[i] * M + j];
+        s_map[nf++] = i;
+      }
+    }
+    s_nf = nf;
+    if (nf > 1) {
+      for (int j = 0; j < M; ++j) {
+        double worst = s_v[j];
+        for (int i = 1; i < nf; ++i) {
+          const double v = s_v[i * M + j];
+          worst = (v > worst || v != v) ? v : worst;
+        }
+        double r = fmax(TPE_MUL(1.1, worst), TPE_MUL(0.9, worst));
+        if (r == 0.0) r = 1e-12;
+        s_ref[j] = r;
+      }
+      int np = 0;
+      for (int i = 0; i < nf; ++i) {
+        bool dom = false;
+        for (int q = 0; q < nf && !dom; ++q) dom = (q != i) && dominates(s_v + q * M, s_v + i * M, M);
+        if (!dom) {
+          for (int j = 0; j < M; ++j) s_ps[np * M + j] = s_v[i * M + j];
+          s_front[np++] = i;
+        }
+      }
+      s_np = np;
+      s_hv = hypervolume(s_ps, np, M, s_ref, true, arena);
+    }
+  }
+  __syncthreads();
+  const int nf = s_nf;
+  if (nf <= 1) return;
+  const int np = s_np;
+  const double hv = s_hv;
+  if (isinf(hv)) return;
+  if (tid < nf) s_contrib[tid] = 0.0;
+  __syncthreads();
+  if (tid < np) {
+    double* a = arena + (size_t)tid * arena_stride;
+    double* pts = a;
+    double* rest = a + (size_t)np * M;
+    int c = 0;
+    double val;
+    if (M <= 3) {
+      for (int q = 0; q < np; ++q) {
+        if (q == tid) continue;
+        for (int j = 0; j < M; ++j) pts[c * M + j] = s_ps[q * M + j];
+        ++c;
+      }
+      val = TPE_SUB(hv, hypervolume(pts, c, M, s_ref, true, rest));
+    } else {
+      double incl = 1.0;
+      for (int j = 0; j < M; ++j) incl = TPE_MUL(incl, TPE_SUB(s_ref[j], s_ps[tid * M + j]));
+      for (int q = 0; q < np; ++q) {
+        if (q == tid) continue;
+        for (int j = 0; j < M; ++j) {
+          const double x = s_ps[q * M + j], y = s_ps[tid * M + j];
+          pts[c * M + j] = x > y ? x : y;
+        }
+        ++c;
+      }
+      val = TPE_SUB(incl, hypervolume(pts, c, M, s_ref, false, rest));
+    }
+    s_contrib[s_front[tid]] = val;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mx = s_contrib[0];
+    for (int i = 1; i < nf; ++i) mx = (s_contrib[i] > mx || s_contrib[i] != s_contrib[i]) ? s_contrib[i] : mx;
+    s_max = fmax(mx, 1e-12);
+  }
+  __syncthreads();
+  if (tid < nf) w[s_map[tid]] = fmax(TPE_DIV(s_contrib[tid], s_max), 1e-12);
+}
+
+}  // namespace tpe

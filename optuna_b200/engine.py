@@ -113,6 +113,12 @@ class TPEEngine:
         key = _f64(key, (-1, 2))
         self._check(self._lib.tpe_history_append(self._h, _ptr(X), _ptr(cat), _ptr(key), X.shape[0]))
 
+    def set_values(self, values, at_row: int = 0) -> None:
+        """Sign-normalised objective values [n, M] of history rows [at_row, at_row + n) (MOTPE)."""
+        v = _f64(values)
+        v = v.reshape(v.shape[0], -1)
+        self._check(self._lib.tpe_history_set_values(self._h, _ptr(v), v.shape[0], v.shape[1], int(at_row)))
+
     def set_history_device(self, dX: int, dcat: int, dkey: int, n: int, col_has_missing=None) -> None:
         miss = None if col_has_missing is None else np.ascontiguousarray(col_has_missing, dtype=np.uint8)
         self._check(self._lib.tpe_history_set_device(self._h, C.c_void_p(dX), C.c_void_p(dcat), C.c_void_p(dkey),
@@ -206,6 +212,11 @@ class TPEEngine:
         sg = np.empty((K, self._pc))
         self._check(self._lib.tpe_get_mixture(self._h, int(which), _ptr(w), _ptr(mu), _ptr(sg)))
         return w, mu, sg
+
+    def get_mo_weights(self) -> np.ndarray:
+        w = np.empty(self._info[0])
+        self._check(self._lib.tpe_get_mo_weights(self._h, _ptr(w)))
+        return w
 
     def get_candidates(self):
         ct = self._last_asks * self._C

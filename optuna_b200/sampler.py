@@ -278,6 +278,9 @@ class B200TPESampler(BaseSampler):
         X = np.full((n, p), np.nan)
         cat = np.zeros(n, dtype=np.int8)
         key = np.zeros((n, 2))
+        multi = study._is_multi_objective()
+        signs = np.asarray([-1.0 if d == StudyDirection.MAXIMIZE else 1.0 for d in study.directions])
+        vals = np.full((n, len(signs)), np.inf) if multi else None
         for i, t in enumerate(trials):
             params = self._get_params(t)
             for j, name in enumerate(names):
@@ -290,11 +293,13 @@ class B200TPESampler(BaseSampler):
                 key[i, 0] = score
             elif t.state == TrialState.COMPLETE:
                 cat[i] = _lib.CAT_COMPLETE
-                key[i, 0] = sign * t.value if not study._is_multi_objective() else 0.0
+                key[i, 0] = sign * t.value if not multi else 0.0
             else:
                 cat[i] = _lib.CAT_PRUNED
-                key[i] = _pruned_key(t, sign)
-        return X, cat, key
+                key[i] = _pruned_key(t, sign) if not multi else (1, 0.0)
+            if multi and t.values is not None:
+                vals[i] = signs * np.asarray(t.values, dtype=float)
+        return X, cat, key, vals
 
     def _sync(self, study, trial, search_space: dict[str, BaseDistribution]) -> tuple[int, list[int]]:
         """Bring the device history up to date; returns (#finished trials, device columns)."""
@@ -329,12 +334,16 @@ class B200TPESampler(BaseSampler):
             h.dists = dists
             h.token = token
             eng.set_space([_spec_of(nm, d, self._cat_dist_funcs) for nm, d in zip(names, dists)])
-            X, cat, key = self._rows(study, trials, names, dists)
+            X, cat, key, vals = self._rows(study, trials, names, dists)
             eng.set_history(X, cat, key)
+            if vals is not None:
+                eng.set_values(vals, 0)
         elif len(trials) > h.n:
             names = list(h.columns)
-            X, cat, key = self._rows(study, trials[h.n:], names, h.dists)
+            X, cat, key, vals = self._rows(study, trials[h.n:], names, h.dists)
             eng.append_history(X, cat, key)
+            if vals is not None:
+                eng.set_values(vals, h.n)
         h.n = len(trials)
         h.last_number = trials[-1].number if trials else -1
         h.n_finished = sum(t.state != TrialState.RUNNING for t in trials) if self._constant_liar else len(trials)
@@ -356,8 +365,6 @@ class B200TPESampler(BaseSampler):
 
     def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
         """TPESampler._sample (sampler.py:523-560)."""
-        if study._is_multi_objective():
-            raise NotImplementedError("multi-objective TPE is not built yet (SURVEY.md section 8 a13/a14).")
         with self._lock:
             n_finished, cols = self._sync(study, trial, search_space)
             n_below = self._gamma(n_finished)
@@ -372,7 +379,10 @@ class B200TPESampler(BaseSampler):
                 x, _, _ = eng.suggest(cols, u, 1, **cfg)
             else:
                 _, nb, na = eng.prepare(cols, **cfg)
-                eng.build(_checked_weights(self._weights, nb), _checked_weights(self._weights, na))
+                # multi-objective studies weight l(x) by hypervolume contributions (computed by the
+                # library); the user's weights function then only shapes g(x) (sampler.py:570-584)
+                wb = None if study._is_multi_objective() else _checked_weights(self._weights, nb)
+                eng.build(wb, _checked_weights(self._weights, na))
                 u = self._draw_uniforms(search_space)
                 x, _, _ = eng.sample_and_select(u, 1)
         out = {}

@@ -1,6 +1,8 @@
 // TEST-ONLY host instantiation of optuna_b200/csrc/tpe_math.cuh (the product never links this).
 // Lets `pytest -m "not gpu"` check the special-function logic against the oracle without a GPU.
 #include "../../optuna_b200/csrc/tpe_math.cuh"
+#include "../../optuna_b200/csrc/tpe_motpe.cuh"
+#include <vector>
 
 extern "C" {
 #define MAP1(name, fn) void name(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = fn(x[i]); }
@@ -16,6 +18,10 @@ void shim_log_gauss_mass(const double* a, const double* b, double* y, long n) {
 }
 void shim_trunc_ppf(const double* q, const double* a, const double* b, double* y, long n) {
   for (long i = 0; i < n; ++i) y[i] = tpe::trunc_ppf(q[i], a[i], b[i]);
+}
+double shim_hypervolume(const double* v, int n, int m, const double* ref, int assume_pareto) {
+  std::vector<double> arena(tpe::hv_arena_doubles(n, m) + 16);
+  return tpe::hypervolume(v, n, m, ref, assume_pareto != 0, arena.data());
 }
 double shim_pairwise(const double* x, long n) {
   return tpe::np_pairwise_sum(x, (int)n);

@@ -99,3 +99,35 @@ def test_pairwise_sum_matches_numpy(shim):
         x = rs.normal(size=n) * 10 ** rs.uniform(-3, 3, size=n)
         got = shim.shim_pairwise(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(n))
         assert got == float(np.sum(x)), n
+
+
+def test_hypervolume_host_instantiation_vs_reference_goldens(shim):
+    """csrc/tpe_motpe.cuh (WFG / 2-D / 3-D hypervolume) against live-reference values."""
+    import ctypes as C
+    from oracle import motpe as mo
+    shim.shim_hypervolume.restype = C.c_double
+    g = load("motpe.npz")
+
+    def hv(v, ref, assume_pareto=False):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        ref = np.ascontiguousarray(ref, dtype=np.float64)
+        return shim.shim_hypervolume(v.ctypes.data_as(C.c_void_p), C.c_int(v.shape[0]), C.c_int(v.shape[1]),
+                                     ref.ctypes.data_as(C.c_void_p), C.c_int(int(assume_pareto)))
+
+    for ci in range(int(g["hv_n"])):
+        v, ref, want = g[f"hv{ci}/v"], g[f"hv{ci}/ref"], float(g[f"hv{ci}/hv"])
+        got = hv(v, ref)
+        assert abs(got - want) <= 4e-16 * abs(want), (ci, got, want)
+    # random Pareto subsets in 2..6 dims vs the oracle (itself pinned to the reference)
+    rs = np.random.RandomState(5)
+    for m in (2, 3, 4, 5, 6):
+        for n in (1, 2, 3, 4, 9, 25):
+            v = rs.uniform(0, 1, (n, m))
+            ref = mo.reference_point(v)
+            want = mo.hypervolume(v, ref)
+            assert abs(hv(v, ref) - want) <= 1e-15 * abs(want), (m, n)
+            ps = v[mo.is_pareto_front(v, False)]
+            want = mo.hypervolume(ps, ref, assume_pareto=True)
+            assert abs(hv(ps, ref, True) - want) <= 1e-15 * abs(want), (m, n)
+    inf_ref = np.array([1.0, np.inf, 1.0, 1.0])
+    assert hv(rs.uniform(0, 1, (5, 4)), inf_ref) == np.inf

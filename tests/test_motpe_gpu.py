@@ -1,0 +1,109 @@
+"""MOTPE on the CUDA path vs live-reference goldens (tests/golden/motpe.npz):
+split by non-domination rank + greedy HSSP, hypervolume weights, full suggestions."""
+import numpy as np
+import pytest
+
+from oracle import motpe as mo
+from tests._util import draw_uniforms, load
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from optuna_b200 import TPEEngine
+    e = TPEEngine(0)
+    yield e
+    e.close()
+
+
+def _setup(eng, X, vals):
+    from optuna_b200.engine import ParamSpec
+    n, P = X.shape
+    eng.set_space([ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(P)])
+    eng.set_history(X, np.zeros(n, np.int8), np.zeros((n, 2)))
+    eng.set_values(vals, 0)
+
+
+def test_mo_split_and_weights_match_reference(eng):
+    g = load("motpe.npz")
+    rs = np.random.RandomState(0)
+    for ci in range(int(g["mo_n"])):
+        t = f"mo{ci}/"
+        v, nb, want = g[t + "v"], int(g[t + "nb"]), g[t + "below"]
+        if not np.isfinite(v).all():
+            v = v.copy()  # +-inf objective values are legal (test_sampler.py:811-861)
+        n = v.shape[0]
+        _setup(eng, rs.uniform(0, 1, (n, 2)), v)
+        info = eng.prepare([0, 1], n_below=nb, n_candidates=8, multivariate=True)
+        below, above = eng.get_split()
+        assert np.array_equal(below, want), (ci, below, want)
+        assert info[0] == want.size
+        if 0 < want.size <= 64:
+            eng.build()
+            w = eng.get_mo_weights()
+            ref = g[t + "w"]
+            np.testing.assert_allclose(w, ref, rtol=1e-12, atol=1e-15, err_msg=str(ci))
+
+
+def test_motpe_suggestions_match_reference(eng):
+    g = load("motpe.npz")
+    for ci in range(int(g["mosg_n"])):
+        t = f"mosg{ci}/"
+        mv, C, seed, n_below, m = g[t + "cfg"]
+        mv, C, n_below = bool(mv), int(C), int(n_below)
+        X, vals = g[t + "X"], g[t + "values"]
+        P = X.shape[1]
+        _setup(eng, X, vals)
+        if n_below > 64:
+            with pytest.raises(ValueError):
+                eng.prepare(list(range(P)), n_below=n_below, n_candidates=C, multivariate=mv)
+            continue
+        rng = np.random.RandomState(int(seed))
+        calls = [list(range(P))] if mv else [[j] for j in range(P)]
+        ret = []
+        for q, cols in enumerate(calls):
+            u = draw_uniforms(rng, C, 0, len(cols))
+            x, acq, best = eng.suggest(cols, u, 1, n_below=n_below, n_candidates=C, multivariate=mv)
+            smp, ll, lg = eng.get_candidates()
+            wb = eng.get_mixture(0)[0]
+            np.testing.assert_allclose(wb, g[f"{t}c{q}/wb"], rtol=1e-12)
+            np.testing.assert_allclose(smp, g[f"{t}c{q}/samples"], rtol=1e-11, atol=1e-12)
+            np.testing.assert_allclose(ll, g[f"{t}c{q}/ll"], rtol=0, atol=1e-11)
+            np.testing.assert_allclose(lg, g[f"{t}c{q}/lg"], rtol=0, atol=1e-12)
+            assert int(best[0]) == int(np.argmax(g[f"{t}c{q}/ll"] - g[f"{t}c{q}/lg"]))
+            ret.extend(x[0].tolist())
+        np.testing.assert_allclose(ret, g[t + "ret"], rtol=1e-11, atol=1e-12)
+
+
+def test_motpe_through_the_sampler_plugin():
+    """4-objective study driven by study.optimize (BASELINE config 4 in miniature)."""
+    from optuna_b200 import B200TPESampler, mini
+
+    def obj(t):
+        x = [t.suggest_float(f"x{j}", 0, 1) for j in range(4)]
+        return [sum((xi - c) ** 2 for xi in x) for c in (0.2, 0.4, 0.6, 0.8)]
+
+    for mv in (False, True):
+        s = mini.create_study(sampler=B200TPESampler(seed=5, multivariate=mv), directions=["minimize"] * 4)
+        s.optimize(obj, n_trials=40)
+        assert len(s.trials) == 40
+        assert all(0 <= v <= 1 for t in s.trials for v in t.params.values())
+
+
+def test_mo_rank_properties_at_scale(eng):
+    """Config-4 shape (N = 20 000, 4 objectives): the selected below set is exactly what the oracle
+    selects (ranks by peeling + HSSP on the tie rank)."""
+    rs = np.random.RandomState(3)
+    n = 20000
+    X = rs.uniform(0, 1, (n, 8))
+    cs = np.array([0.2, 0.4, 0.6, 0.8])
+    vals = np.stack([((X - c) ** 2).sum(1) for c in cs], 1)
+    _setup(eng, X, vals)
+    eng.prepare(list(range(8)), n_below=25, n_candidates=24, multivariate=True)
+    below, above = eng.get_split()
+    want = mo.split_complete_mo(vals, 25)
+    assert np.array_equal(below, want)
+    assert below.size + above.size == n
+    eng.build()
+    np.testing.assert_allclose(eng.get_mo_weights(), mo.weights_below_mo(vals[want]), rtol=1e-12)
