@@ -1,0 +1,99 @@
+"""Multi-GPU plumbing for a batch of concurrent asks (BASELINE config 5).
+
+One process per GPU (torchrun), one TPEEngine per process.  Concurrent asks against a frozen history
+are independent -- same split, same mixtures, different uniforms -- so the batch is block-partitioned
+over ranks with NO collective on the data path:
+
+  1. rank 0 holds the history; ONE broadcast replicates it (NCCL over NVLink for CUDA tensors);
+  2. every rank builds the two estimators redundantly (cheaper than shipping mu / sigma);
+  3. rank r evaluates asks [start_r, start_r + count_r) with its slice of the host-drawn uniforms;
+  4. results are gathered (all_gather of [count, P] doubles) or simply read per rank.
+
+torch.distributed is used for the plumbing only; the library never sees a torch type.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+
+
+def shard_asks(n_asks: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block partition: (start, count) of rank's share; sizes differ by at most one."""
+    base, extra = divmod(int(n_asks), int(world))
+    count = base + (1 if rank < extra else 0)
+    start = rank * base + min(rank, extra)
+    return start, count
+
+
+def broadcast_history(X, category, key, values=None, *, src: int = 0, device=None):
+    """Replicate the history arrays from `src` to every rank with one broadcast per dtype.
+
+    On `src` the arguments are numpy arrays; on the other ranks they may be None.  Returns torch
+    tensors (on `device` when given, else CPU) as (X, category, key, values-or-None).  The float
+    arrays travel as ONE flat fp64 tensor so that a 100k x 32 history is a single 26 MB collective.
+    """
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank()
+    dev = torch.device("cpu") if device is None else device
+    meta = torch.zeros(4, dtype=torch.int64, device=dev)
+    if rank == src:
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        m = 0 if values is None else np.asarray(values).reshape(X.shape[0], -1).shape[1]
+        meta = torch.tensor([X.shape[0], X.shape[1], m, 0], dtype=torch.int64, device=dev)
+    dist.broadcast(meta, src)
+    n, p, m = int(meta[0]), int(meta[1]), int(meta[2])
+    flat = torch.empty(n * (p + 2 + m), dtype=torch.float64, device=dev)
+    cat = torch.empty(n, dtype=torch.int8, device=dev)
+    if rank == src:
+        parts = [X.ravel(), np.ascontiguousarray(key, dtype=np.float64).ravel()]
+        if m:
+            parts.append(np.ascontiguousarray(values, dtype=np.float64).ravel())
+        flat.copy_(torch.from_numpy(np.concatenate(parts)))
+        cat.copy_(torch.from_numpy(np.ascontiguousarray(category, dtype=np.int8)))
+    dist.broadcast(flat, src)
+    dist.broadcast(cat, src)
+    tX = flat[: n * p].view(n, p)
+    tk = flat[n * p: n * (p + 2)].view(n, 2)
+    tv = flat[n * (p + 2):].view(n, m) if m else None
+    return tX, cat, tk, tv
+
+
+def adopt_history(engine, tX, tcat, tkey, tvals=None) -> None:
+    """Hand broadcast CUDA tensors to the engine (device-to-device copy inside the library)."""
+    import torch
+    assert tX.is_cuda and tX.is_contiguous() and tkey.is_contiguous() and tcat.is_contiguous()
+    torch.cuda.synchronize(tX.device)
+    engine.set_history_device(tX.data_ptr(), tcat.data_ptr(), tkey.data_ptr(), tX.shape[0],
+                              np.isnan(tX.sum(dim=0).cpu().numpy()).astype(np.uint8))
+    if tvals is not None:
+        engine.set_values(tvals.cpu().numpy(), 0)
+
+
+def sharded_asks(n_asks: int, per_ask: int, uniforms, compute: Callable[[np.ndarray, int], np.ndarray],
+                 gather: bool = True):
+    """Run `compute(uniforms_slice, count) -> [count, P]` on this rank's block of asks and (optionally)
+    all_gather the results in ask order.  `uniforms` is the full [n_asks, per_ask] host array (every
+    rank draws the same stream from the shared seed, or rank 0 broadcasts it)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    start, count = shard_asks(n_asks, world, rank)
+    u = np.asarray(uniforms, dtype=np.float64).reshape(n_asks, per_ask)[start:start + count]
+    mine = np.asarray(compute(u, count), dtype=np.float64).reshape(count, -1)
+    if not gather:
+        return mine
+    width = mine.shape[1]
+    most = shard_asks(n_asks, world, 0)[1]
+    pad = torch.zeros((most, width), dtype=torch.float64)
+    pad[:count] = torch.from_numpy(mine)
+    backend = dist.get_backend()
+    if backend == "nccl":
+        pad = pad.cuda()
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad)
+    rows = [outs[r][: shard_asks(n_asks, world, r)[1]].cpu().numpy() for r in range(world)]
+    return np.concatenate(rows, axis=0)

@@ -1,0 +1,63 @@
+"""Host-side multi-GPU plumbing (optuna_b200/dist.py) on CPU: gloo backend, world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from optuna_b200.dist import shard_asks
+
+
+def test_shard_asks_partitions_exactly():
+    for n in (0, 1, 7, 8, 8192, 8193):
+        for world in (1, 2, 3, 8):
+            spans = [shard_asks(n, world, r) for r in range(world)]
+            assert sum(c for _, c in spans) == n
+            at = 0
+            for s, c in spans:
+                assert s == at
+                at += c
+            sizes = [c for _, c in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    import torch.distributed as dist
+    from optuna_b200.dist import broadcast_history, sharded_asks
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rs = np.random.RandomState(0)
+    n, p, m = 1000, 5, 3
+    X = rs.uniform(size=(n, p))
+    X[3, 2] = np.nan
+    cat = rs.randint(0, 3, size=n).astype(np.int8)
+    key = rs.normal(size=(n, 2))
+    vals = rs.normal(size=(n, m))
+    if rank == 0:
+        tX, tc, tk, tv = broadcast_history(X, cat, key, vals)
+    else:
+        tX, tc, tk, tv = broadcast_history(None, None, None, None)
+    assert np.array_equal(tX.numpy(), X, equal_nan=True) and np.array_equal(tc.numpy(), cat)
+    assert np.array_equal(tk.numpy(), key) and np.array_equal(tv.numpy(), vals)
+    n_asks, per_ask = 37, 11
+    U = np.random.RandomState(1).uniform(size=(n_asks, per_ask))
+
+    def compute(u, count):  # stand-in for engine.sample_and_select: one row per ask
+        assert u.shape == (count, per_ask)
+        return np.stack([u.sum(1), u[:, 0]], 1)
+
+    got = sharded_asks(n_asks, per_ask, U, compute)
+    assert np.allclose(got, np.stack([U.sum(1), U[:, 0]], 1))
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), got)
+    dist.destroy_process_group()
+
+
+def test_broadcast_and_sharded_asks_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "r0.npy"), np.load(tmp_path / "r1.npy")
+    assert np.array_equal(a, b) and a.shape == (37, 2)
