@@ -777,7 +777,8 @@ int tpe_get_mo_weights(tpe_ctx* ctx, double* weights) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->built || !ctx->mo_weights_ready) return fail(ctx, TPE_E_STATE, "no MOTPE weights available");
   if (set_device(ctx)) return TPE_E_CUDA;
-  CU(cudaMemcpy(weights, ctx->mo_w.p, (size_t)ctx->info.n_below_all * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpyAsync(weights, ctx->mo_w.p, (size_t)ctx->info.n_below_all * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return TPE_OK;
 }
 

@@ -21,6 +21,7 @@ void shim_trunc_ppf(const double* q, const double* a, const double* b, double* y
 }
 double shim_hypervolume(const double* v, int n, int m, const double* ref, int assume_pareto) {
   std::vector<double> arena(tpe::hv_arena_doubles(n, m) + 16);
+  memset(arena.data(), 0xFF, arena.size() * 8);  // the device arena is not zeroed either
   return tpe::hypervolume(v, n, m, ref, assume_pareto != 0, arena.data());
 }
 double shim_pairwise(const double* x, long n) {
