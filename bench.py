@@ -342,7 +342,9 @@ def run_b200(args) -> None:
                     "d2h_bytes_per_step": N_PARAMS * 8 + 16 + 24, "steps": e2e_steps,
                     "path": "B200TPESampler.sample_relative -> ctypes -> tpe_suggest"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": kernel_name,
+                         "traffic": 27461120, "traffic_source": "ncu --set full, profiles/r1_ncu_raw_logpdf_fast_final.txt "
+                         "(dram__bytes_read.sum + dram__bytes_write.sum of this launch)",
+                         "peak_source": peak_src, "kernel": kernel_name,
                          "kernel_ms": k_ms, "algorithmic_bytes": algorithmic_bytes(),
                          "note": "the C x K x P grid reuses every history byte C=4096 times from shared memory, so "
                                  "this kernel sits on the fp64 pipe, not on HBM (SURVEY.md section 8d); see fp64"},

@@ -293,11 +293,22 @@ class _Storage:
     def __init__(self) -> None:
         self.trials: list[FrozenTrial] = []
         self.lock = threading.RLock()
+        self.version = 0  # bumped whenever a trial is added or changes state
+        self._cache: dict = {}
+
+    def touch(self) -> None:
+        self.version += 1
 
     def get_all_trials(self, study_id: int = 0, deepcopy: bool = True, states=None) -> list[FrozenTrial]:
         with self.lock:
-            out = [t for t in self.trials if states is None or t.state in states]
-        return copy.deepcopy(out) if deepcopy else out
+            key = None if states is None else tuple(sorted(int(s) for s in states))
+            hit = self._cache.get(key)
+            if hit is not None and hit[0] == (self.version, len(self.trials), id(self.trials)):
+                out = hit[1]
+            else:
+                out = [t for t in self.trials if states is None or t.state in states]
+                self._cache[key] = ((self.version, len(self.trials), id(self.trials)), out)
+        return copy.deepcopy(out) if deepcopy else list(out) if False else out
 
     def set_trial_system_attr(self, trial_id: int, key: str, value: Any) -> None:
         with self.lock:
@@ -520,6 +531,7 @@ class Study:
             t = copy.copy(trial)
             t.number = t._trial_id = len(self._storage.trials)
             self._storage.trials.append(t)
+            self._storage.touch()
 
     def add_trials(self, trials: Sequence[FrozenTrial]) -> None:
         for t in trials:
@@ -529,6 +541,7 @@ class Study:
         with self._storage.lock:
             n = len(self._storage.trials)
             self._storage.trials.append(FrozenTrial(n, TrialState.RUNNING, datetime_start=datetime.datetime.now()))
+            self._storage.touch()
         trial = Trial(self, n)
         for name, d in (fixed_distributions or {}).items():
             trial._suggest(name, d)
@@ -560,6 +573,7 @@ class Study:
                 frozen.values = vals
                 frozen.state = state
                 frozen.datetime_complete = datetime.datetime.now()
+                self._storage.touch()
         return copy.deepcopy(frozen)
 
     def optimize(self, func: Callable[[Trial], Any], n_trials: int) -> None:
