@@ -308,7 +308,7 @@ class _Storage:
             else:
                 out = [t for t in self.trials if states is None or t.state in states]
                 self._cache[key] = ((self.version, len(self.trials), id(self.trials)), out)
-        return copy.deepcopy(out) if deepcopy else list(out) if False else out
+        return copy.deepcopy(out) if deepcopy else out
 
     def set_trial_system_attr(self, trial_id: int, key: str, value: Any) -> None:
         with self.lock:

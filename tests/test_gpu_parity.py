@@ -274,3 +274,84 @@ def test_error_contract(eng):
         eng.build(w_above=np.zeros(17))
     with pytest.raises(ValueError):
         eng.set_space([ParamSpec(kind=0, low=2.0, high=1.0)])
+
+
+def test_config3_shape_mixed_64_params_against_oracle(eng):
+    """BASELINE config 3 layout (24 float + 8 log-float + 8 step-float + 8 int + 4 log-int +
+    12 categorical, multivariate) at N = 4000 so that the oracle finishes in seconds."""
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(0)
+    n, C = 4000, 24
+    specs, params, cols = [], [], []
+    for _ in range(24):
+        specs.append(ParamSpec(kind=0, low=0.0, high=1.0)); params.append(orc.Param("float", 0.0, 1.0))
+        cols.append(rs.uniform(0, 1, n))
+    for _ in range(8):
+        specs.append(ParamSpec(kind=0, low=1e-5, high=1.0, log=True)); params.append(orc.Param("float", 1e-5, 1.0, None, True))
+        cols.append(np.exp(rs.uniform(np.log(1e-5), 0, n)))
+    for _ in range(8):
+        specs.append(ParamSpec(kind=0, low=0.0, high=10.0, step=0.5)); params.append(orc.Param("float", 0.0, 10.0, 0.5))
+        cols.append(rs.randint(0, 21, n) * 0.5)
+    for _ in range(8):
+        specs.append(ParamSpec(kind=1, low=0, high=100, step=1)); params.append(orc.Param("int", 0.0, 100.0, 1.0))
+        cols.append(rs.randint(0, 101, n).astype(float))
+    for _ in range(4):
+        specs.append(ParamSpec(kind=1, low=1, high=1024, step=1, log=True)); params.append(orc.Param("int", 1.0, 1024.0, 1.0, True))
+        cols.append(np.round(np.exp(rs.uniform(0, np.log(1024), n))))
+    for k in range(12):
+        nch = 4 + k % 5
+        specs.append(ParamSpec(kind=2, n_choices=nch)); params.append(orc.Param("cat", n_choices=nch))
+        cols.append(rs.randint(0, nch, n).astype(float))
+    X = np.stack(cols, 1)
+    cat = np.zeros(n, np.int8)
+    key = np.stack([rs.normal(size=n), np.zeros(n)], 1)
+    eng.set_space(specs)
+    eng.set_history(X, cat, key)
+    u = draw_uniforms(np.random.RandomState(9), C, 12, 52)
+    x, acq, best = eng.suggest(list(range(64)), u, 1, n_below=25, n_candidates=C, multivariate=True)
+    smp, ll, lg = eng.get_candidates()
+    s = orc.suggest(X, cat, key, params, list(range(64)), orc.Config(multivariate=True), 25, C,
+                    np.random.RandomState(9))
+    for j, p in enumerate(params):
+        if p.is_cat or p.step is not None:
+            assert np.array_equal(smp[:, j], s.samples[:, j]), j
+        else:
+            close(smp[:, j], s.samples[:, j], 1e-12, 1e-12)
+    # integer ranges up to 1024 steps: the reference's own _log_diff conditioning (SURVEY.md section 7)
+    close(ll, s.logl, 0, 1e-8)
+    close(lg, s.logg, 0, 1e-8)
+    assert int(best[0]) == s.best
+    for j, p in enumerate(params):
+        if p.is_cat or p.step is not None:
+            assert x[0, j] == s.x[j]
+
+
+def test_categorical_distance_func_tables(eng):
+    """categorical_distance_func (parzen_estimator.py:152-160): rows exp(-(d / max d)^2 * coef)."""
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(4)
+    nch, n, C = 5, 300, 32
+    table = np.abs(np.subtract.outer(np.arange(nch), np.arange(nch))).astype(float) + 0.25 * (1 - np.eye(nch))
+    eng.set_space([ParamSpec(kind=2, n_choices=nch, dist_table=table), ParamSpec(kind=0, low=-1.0, high=1.0)])
+    X = np.stack([rs.randint(0, nch, n).astype(float), rs.uniform(-1, 1, n)], 1)
+    cat = np.zeros(n, np.int8)
+    key = np.stack([rs.normal(size=n), np.zeros(n)], 1)
+    eng.set_history(X, cat, key)
+    params = [orc.Param("cat", n_choices=nch, dist_table=table), orc.Param("float", -1.0, 1.0)]
+    for mv in (True, False):
+        calls = [[0, 1]] if mv else [[0], [1]]
+        for cols in calls:
+            sub = [params[c] for c in cols]
+            ncat, nnum = kinds_of(sub)
+            u = draw_uniforms(np.random.RandomState(6), C, ncat, nnum)
+            x, acq, best = eng.suggest(cols, u, 1, n_below=20, n_candidates=C, multivariate=mv)
+            smp, ll, lg = eng.get_candidates()
+            s = orc.suggest(X, cat, key, params, cols, orc.Config(multivariate=mv), 20, C, np.random.RandomState(6))
+            for jj, c in enumerate(cols):
+                if params[c].is_cat:
+                    assert np.array_equal(smp[:, jj], s.samples[:, jj])
+                else:
+                    close(smp[:, jj], s.samples[:, jj], 1e-12, 1e-12)
+            close(ll, s.logl, 0, 1e-12)
+            close(lg, s.logg, 0, 1e-12)
+            assert int(best[0]) == s.best

@@ -94,3 +94,24 @@ def test_custom_weights_gamma_pruned_constraints_run():
     with pytest.raises(ValueError):
         bad = mini.create_study(sampler=B200TPESampler(seed=1, weights=lambda n: -np.ones(n), n_startup_trials=2))
         bad.optimize(lambda t: t.suggest_float("x", 0, 1), n_trials=5)
+
+
+def test_constant_liar_and_categorical_distance_through_plugin():
+    from optuna_b200 import B200TPESampler, mini
+
+    def obj(t):
+        a = t.suggest_categorical("a", [0, 1, 2, 3])
+        x = t.suggest_float("x", -2, 2)
+        return (a - 2) ** 2 + x * x
+
+    sampler = B200TPESampler(seed=2, multivariate=True, constant_liar=True, n_startup_trials=4,
+                             categorical_distance_func={"a": lambda p, q: abs(p - q)})
+    s = mini.create_study(sampler=sampler)
+    # a batch of asks before any tell: later asks see earlier RUNNING trials in g(x) (sampler.py:526-535)
+    s.optimize(obj, n_trials=8)
+    batch = [s.ask() for _ in range(4)]
+    vals = [obj(t) for t in batch]
+    for t, v in zip(batch, vals):
+        s.tell(t, v)
+    assert len(s.trials) == 12 and all(t.state == mini.TrialState.COMPLETE for t in s.trials)
+    assert any("tpe:relative_params:0" in t.system_attrs for t in s.trials[8:])
