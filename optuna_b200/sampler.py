@@ -112,6 +112,10 @@ class _History:
         self.inter: dict[str, BaseDistribution] | None = None
         self.inter_n = 0
         self.inter_last = -1
+        # incremental group decomposition (optuna/search_space/group_decomposed.py:14-68)
+        self.groups: list[dict[str, BaseDistribution]] = []
+        self.groups_n = 0
+        self.groups_last = -1
 
 
 class B200TPESampler(BaseSampler):
@@ -139,8 +143,6 @@ class B200TPESampler(BaseSampler):
             warnings.warn("`consider_prior` is deprecated; it falls back to `True`.", FutureWarning)
         if group and not multivariate:
             raise ValueError("``group`` option can only be enabled when ``multivariate`` is enabled.")
-        if group:
-            raise NotImplementedError("group=True is not built yet (SURVEY.md section 8f rank 3).")
         self._prior_weight = prior_weight
         self._magic_clip = consider_magic_clip
         self._endpoints = consider_endpoints
@@ -187,12 +189,30 @@ class B200TPESampler(BaseSampler):
     def infer_relative_search_space(self, study, trial) -> dict[str, BaseDistribution]:
         if not self._multivariate:
             return {}
+        if self._group:
+            with self._lock:
+                groups = self._group_spaces(study)
+            out: dict[str, BaseDistribution] = {}
+            for sub in groups:
+                for name, d in sorted(sub.items()):
+                    if not d.single():
+                        out[name] = d
+            return out
         with self._lock:
             space = self._intersection(study)
         return {k: d for k, d in space.items() if not d.single()}
 
     def sample_relative(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
-        params = self._sample_relative(study, trial, search_space)
+        if self._group:
+            # one joint suggestion per group of parameters that always appear together (sampler.py:417-431)
+            with self._lock:
+                groups = [dict(g) for g in self._hist.groups]
+            params: dict[str, Any] = {}
+            for sub in groups:
+                part = {name: d for name, d in sorted(sub.items()) if not d.single() and name in search_space}
+                params.update(self._sample_relative(study, trial, part))
+        else:
+            params = self._sample_relative(study, trial, search_space)
         if params != {} and self._constant_liar:
             text = json.dumps(params)
             for i in range(0, len(text), SYSTEM_ATTR_MAX_LENGTH):
@@ -271,6 +291,59 @@ class B200TPESampler(BaseSampler):
         h.inter_n = len(trials)
         h.inter_last = trials[-1].number if trials else -1
         return dict(sorted((h.inter or {}).items(), key=lambda kv: kv[0]))
+
+    def _group_spaces(self, study) -> list[dict[str, BaseDistribution]]:
+        h = self._hist
+        trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
+        if not (h.groups_n <= len(trials) and (h.groups_n == 0 or trials[h.groups_n - 1].number == h.groups_last)):
+            h.groups, h.groups_n = [], 0
+        for t in trials[h.groups_n:]:
+            left = set(t.distributions)
+            nxt: list[dict[str, BaseDistribution]] = []
+            for sub in h.groups:
+                keys = set(sub)
+                nxt.append({name: sub[name] for name in keys & left})
+                nxt.append({name: sub[name] for name in keys - left})
+                left -= keys
+            nxt.append({name: t.distributions[name] for name in left})
+            h.groups = [g for g in nxt if g]
+        h.groups_n = len(trials)
+        h.groups_last = trials[-1].number if trials else -1
+        return [dict(g) for g in h.groups]
+
+    def sample_relative_batch(self, study, search_space: dict[str, BaseDistribution], n_asks: int) -> list[dict]:
+        """`n_asks` joint suggestions against the current (frozen) history in ONE device call.
+
+        Equivalent to calling ``sample_relative`` n_asks times without a ``tell`` in between
+        (the reference idiom is a Python loop of ``study.ask()``; with
+        ``constant_liar=False`` every such ask sees the same split and the same two mixtures and
+        only the RNG position differs).  The uniforms are drawn ask by ask from the sampler's own
+        RandomState, so the results are those of the sequential loop."""
+        if self._group or self._constant_liar:
+            raise ValueError("sample_relative_batch needs group=False and constant_liar=False "
+                             "(constant-liar asks depend on each other)")
+        if search_space == {} or n_asks <= 0:
+            return [{} for _ in range(max(n_asks, 0))]
+        trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
+        if len(trials) < self._n_startup_trials:
+            return [{} for _ in range(n_asks)]
+        with self._lock:
+            n_finished, cols = self._sync(study, None, search_space)
+            cfg = dict(n_below=int(self._gamma(n_finished)), n_candidates=self._n_ei_candidates,
+                       multivariate=self._multivariate, prior_weight=self._prior_weight,
+                       magic_clip=self._magic_clip, endpoints=self._endpoints)
+            eng = self._eng()
+            multi = study._is_multi_objective()
+            _, nb, na = eng.prepare(cols, **cfg)
+            if self._weights is default_weights:
+                eng.build()
+            else:
+                eng.build(None if multi else _checked_weights(self._weights, nb), _checked_weights(self._weights, na))
+            u = np.concatenate([self._draw_uniforms(search_space) for _ in range(n_asks)])
+            x, _, _ = eng.sample_and_select(u, n_asks)
+        names = list(search_space)
+        return [{name: search_space[name].to_external_repr(float(x[a, j])) for j, name in enumerate(names)}
+                for a in range(n_asks)]
 
     def _rows(self, study, trials, names: list[str], dists: list[BaseDistribution]):
         sign = -1.0 if (not study._is_multi_objective() and study.direction == StudyDirection.MAXIMIZE) else 1.0

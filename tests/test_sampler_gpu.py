@@ -115,3 +115,47 @@ def test_constant_liar_and_categorical_distance_through_plugin():
         s.tell(t, v)
     assert len(s.trials) == 12 and all(t.state == mini.TrialState.COMPLETE for t in s.trials)
     assert any("tpe:relative_params:0" in t.system_attrs for t in s.trials[8:])
+
+
+def test_batched_ask_equals_sequential_asks():
+    """BASELINE config 5 semantics: ask_batch(n) == n sequential study.ask() with no tell between."""
+    from optuna_b200 import B200TPESampler, mini
+    from optuna_b200.batch import ask_batch
+
+    def obj(t):
+        return sum((t.suggest_float(f"x{j}", 0, 1) - 0.3) ** 2 for j in range(5)) + t.suggest_int("k", 0, 9) * 0.01
+
+    def warm(seed):
+        s = mini.create_study(sampler=B200TPESampler(seed=seed, multivariate=True, n_ei_candidates=32))
+        s.optimize(obj, n_trials=30)
+        return s
+
+    a, b = warm(7), warm(7)
+    batch = ask_batch(a, 50)
+    seq = [b.ask() for _ in range(50)]
+    pa = [[t.suggest_float(f"x{j}", 0, 1) for j in range(5)] + [t.suggest_int("k", 0, 9)] for t in batch]
+    pb = [[t.suggest_float(f"x{j}", 0, 1) for j in range(5)] + [t.suggest_int("k", 0, 9)] for t in seq]
+    assert pa == pb
+    assert len({tuple(p) for p in pa}) > 40  # different uniforms per ask
+
+
+def test_group_decomposed_search_space():
+    """group=True: conditional parameters are sampled jointly within the groups that co-occur
+    (sampler.py:394-405, :417-431)."""
+    from optuna_b200 import B200TPESampler, mini
+
+    def obj(t):
+        kind = t.suggest_categorical("kind", ["a", "b"])
+        x = t.suggest_float("x", -1, 1)
+        if kind == "a":
+            return x * x + t.suggest_float("ya", 0, 2)
+        return x * x + (t.suggest_int("yb", 0, 5) - 2) ** 2 + t.suggest_float("zb", 1e-2, 1, log=True)
+
+    s = mini.create_study(sampler=B200TPESampler(seed=4, multivariate=True, group=True, n_startup_trials=6))
+    s.optimize(obj, n_trials=40)
+    assert len(s.trials) == 40
+    groups = s.sampler._hist.groups
+    names = sorted(sorted(g) for g in groups)
+    assert names == [["kind", "x"], ["ya"], ["yb", "zb"]]
+    with pytest.raises(ValueError):
+        B200TPESampler(group=True)
