@@ -18,6 +18,7 @@
 #include "../../include/optuna_b200_tpe.h"
 #include "tpe_kernels.cuh"
 #include "tpe_motpe_kernels.cuh"
+#include "tpe_screen.cuh"
 
 using namespace tpe;
 
@@ -64,9 +65,11 @@ struct DevBuf {
 struct Estimator {
   int64_t n = 0, K = 0;
   DevBuf rows, pos, wstage, wpart, w, logw, cdf, mu, sigma, cst_part, cst, tabp, tabc, colprm, tab, part, fix;
+  DevBuf tab32, tab64p, d32;   // fp32-screening copies (tpe_screen.cuh)
+  bool screen_ready = false;
   int nsplit = 0;
   void release() {
-    for (DevBuf* b : {&rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
+    for (DevBuf* b : {&tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
                       &part, &fix})
       b->release();
   }
@@ -116,7 +119,8 @@ struct tpe_ctx {
 
   // candidates
   int64_t n_asks = 0, Ct = 0, ct_stride = 0;
-  DevBuf U, S, xT, oob, logl, logg, out_x, out_acq, out_best;
+  DevBuf U, S, xT, oob, logl, logg, out_x, out_acq, out_best, x64s, x32s, e32s, gmax;
+  bool screen_attr_set = false;
   float ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   int32_t launches = 0;
   const char* last_kernel = "none";
@@ -432,6 +436,7 @@ void scan_missing(tpe_ctx* ctx, const double* X, int64_t n) {
 
 int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
   Estimator& e = ctx->est[which];
+  e.screen_ready = false;
   const int64_t n = e.n, K = n + 1;
   const int32_t pc = ctx->pc;
   cudaStream_t st = ctx->stream;
@@ -563,8 +568,59 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
       nsplit = (ktiles + tiles_per - 1) / tiles_per;
       kps = tiles_per * fc->tk;
     }
-    CU(e.part.ensure((size_t)(nsplit + 1) * ctx->ct_stride * 16));
-    if (nsplit > 0) {
+    // fp32-screened variant (tpe_screen.cuh): multivariate, 17..32 continuous columns, many candidates
+    // Experimental and OFF by default: correct (same parity tests) but 2.62 ms vs 2.40 ms for the exact
+    // kernel at config 2 -- see profiles/r1_variants.md.  TPE_SCREEN=1 enables it.
+    static const bool screen_on = [] { const char* v = getenv("TPE_SCREEN"); return v && v[0] == '1'; }();
+    const bool use_screen = cst_mode && ctx->pb == kScrP && Ct > 128 && Kf > 0 && screen_on;
+    if (use_screen) {
+      const int64_t sctiles = (Ct + kScrCands - 1) / kScrCands;
+      const int64_t sktiles = (Kf + kScrTK - 1) / kScrTK;
+      int64_t sns = std::max<int64_t>(1, std::min<int64_t>(sktiles, (int64_t)ctx->sm_count * 2 / sctiles));
+      const int64_t tiles_per = (sktiles + sns - 1) / sns;
+      sns = (sktiles + tiles_per - 1) / tiles_per;
+      const int64_t skps = tiles_per * kScrTK;
+      CU(e.part.ensure((size_t)(sns + 1) * ctx->ct_stride * 16));
+      if (!e.screen_ready) {
+        CU(e.tab32.ensure((size_t)Kf * kScrP * 4 + 64));
+        CU(e.tab64p.ensure((size_t)Kf * kScrStride * 8 + 64));
+        CU(e.d32.ensure((size_t)Kf * 4 + 64));
+        k_screen_tabprep<<<grid_for(Kf * 32, 256, ctx->sm_count * 8), 256, 0, st>>>(
+            e.tabc.as<double>(), e.cst.as<double>(), Kf, e.tab32.as<float>(), e.tab64p.as<double>(), e.d32.as<float>());
+        ctx->launch_counter++;
+        e.screen_ready = true;
+      }
+      CU(ctx->x64s.ensure((size_t)ctx->ct_stride * kScrP * 8));
+      CU(ctx->x32s.ensure((size_t)ctx->ct_stride * kScrP * 4));
+      CU(ctx->e32s.ensure((size_t)ctx->ct_stride * 4));
+      CU(ctx->gmax.ensure((size_t)ctx->ct_stride * 4));
+      k_screen_xprep<<<grid_for(ctx->ct_stride, 256, 1 << 20), 256, 0, st>>>(
+          ctx->xT.as<double>(), e.colprm.as<double2>(), ctx->ct_stride, ctx->x64s.as<double>(), ctx->x32s.as<float>(),
+          ctx->e32s.as<float>(), ctx->gmax.as<float>());
+      ctx->launch_counter++;
+      if (!ctx->screen_attr_set) {
+        CU(cudaFuncSetAttribute(k_logpdf_screen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScreenSmem)));
+        ctx->screen_attr_set = true;
+      }
+      // fp32 error bound of the screening value: dot product of P terms + input rounding, over
+      // |x''|, |mu''| <= rho = (range / 2) / sigma (identical for every column of a multivariate estimator)
+      const double nobs = (double)std::max<int64_t>(e.n, 1);
+      double fac = 0.2 * pow(nobs, -1.0 / (ctx->pc + 4));
+      if (ctx->cfg.magic_clip) fac = std::max(fac, 1.0 / std::min(100.0, 1.0 + (double)K));
+      fac = std::min(std::max(fac, 1e-9), 1.0);
+      const double rho = 0.5 / fac;
+      const float margin = (float)(0.5 + 8e-6 * kScrP * rho * rho);
+      k_logpdf_screen<<<dim3((unsigned)sctiles, (unsigned)sns), kScrNT, sizeof(ScreenSmem), st>>>(
+          e.tab32.as<float>(), e.tab64p.as<double>(), e.cst.as<double>(), e.d32.as<float>(), Kf,
+          ctx->x64s.as<double>(), ctx->x32s.as<float>(), ctx->e32s.as<float>(), ctx->gmax.as<float>(),
+          ctx->ct_stride, skps,
+          std::min(46.0, log((double)std::max<int64_t>(K, 1)) + 30.0), margin, e.part.as<double2>());
+      ctx->launch_counter++;
+      nsplit = sns;
+      ctx->last_kernel = "k_logpdf_screen<fp32 screen + fp64 exact>";
+    }
+    if (!use_screen) CU(e.part.ensure((size_t)(nsplit + 1) * ctx->ct_stride * 16));
+    if (nsplit > 0 && !use_screen) {
       if (!ctx->prepared_cfgs.count(fc)) {
         CU(fc->prepare());
         ctx->prepared_cfgs.insert(fc);
@@ -575,8 +631,9 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
                  std::min(46.0, log((double)std::max<int64_t>(K, 1)) + 30.0), e.part.as<double2>());
       ctx->launch_counter++;
     }
-    ctx->last_kernel = cst_mode ? ((fc->nt >= 256) ? "k_logpdf_fast<const,big>" : "k_logpdf_fast<const,small>")
-                                : ((fc->nt >= 256) ? "k_logpdf_fast<pair,big>" : "k_logpdf_fast<pair,small>");
+    if (!use_screen)
+      ctx->last_kernel = cst_mode ? ((fc->nt >= 256) ? "k_logpdf_fast<const,big>" : "k_logpdf_fast<const,small>")
+                                  : ((fc->nt >= 256) ? "k_logpdf_fast<pair,big>" : "k_logpdf_fast<pair,small>");
     if (after_main) CU(cudaEventRecord(after_main, st));
     if (cst_mode) {  // the prior kernel, evaluated exactly, becomes one more partial row
       k_logpdf_generic<<<dim3((unsigned)((Ct + 127) / 128), 1), 128, 0, st>>>(
@@ -662,7 +719,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
                     &ctx->cand_a, &ctx->cand_b, &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->U, &ctx->S,
-                    &ctx->xT, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
+                    &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
   ctx->est[1].release();
