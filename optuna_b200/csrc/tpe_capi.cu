@@ -115,7 +115,7 @@ struct tpe_ctx {
   tpe_split_info info{};
   DevBuf row_ok, member, cand_a, cand_b, counts, split_work;
   Estimator est[2];
-  DevBuf sort_val, sort_idx;
+  DevBuf sort_val, sort_idx, sort_work;
 
   // candidates
   int64_t n_asks = 0, Ct = 0, ct_stride = 0;
@@ -476,22 +476,30 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
     CU(cudaMemsetAsync(e.sigma.p, 0, (size_t)K * pc * 8, st));
     int64_t m2 = 1;
     while (m2 < K) m2 <<= 1;
-    CU(ctx->sort_idx.ensure((size_t)m2 * 4));
-    if (m2 > 4096) CU(ctx->sort_val.ensure((size_t)m2 * 8));
+    CU(ctx->sort_idx.ensure((size_t)std::max<int64_t>(m2, K * 3) * 4));
     for (int j = 0; j < pc; ++j) {
       if (ctx->cols_h[j].cls == COL_CAT) continue;
       if (m2 <= 4096) {
         k_sort_small<<<1, 1024, 0, st>>>(e.mu.as<double>(), pc, j, (int)K, (int)m2, ctx->sort_idx.as<int32_t>());
         ctx->launch_counter++;
       } else {
-        const int g = grid_for(m2, 256, cap);
-        k_sort_fill<<<g, 256, 0, st>>>(e.mu.as<double>(), pc, j, K, m2, ctx->sort_val.as<double>(),
-                                        ctx->sort_idx.as<int32_t>());
-        for (int64_t kk = 2; kk <= m2; kk <<= 1)
-          for (int64_t jj = kk >> 1; jj > 0; jj >>= 1) {
-            k_bitonic_step<<<g, 256, 0, st>>>(ctx->sort_val.as<double>(), ctx->sort_idx.as<int32_t>(), m2, jj, kk);
-            ctx->launch_counter++;
-          }
+        // cooperative stable radix sort (one launch instead of ~150 bitonic steps)
+        CU(ctx->sort_val.ensure((size_t)K * 8 * 2));
+        CU(ctx->sort_idx.ensure((size_t)K * 4 * 3));
+        CU(ctx->sort_work.ensure(sizeof(SortWork)));
+        const double* d_mu = e.mu.as<double>();
+        int32_t pc_i = pc;
+        int j_i = j, n_i = (int)K;
+        uint64_t* ka = ctx->sort_val.as<uint64_t>();
+        uint64_t* kb = ka + K;
+        int32_t* order = ctx->sort_idx.as<int32_t>();
+        int32_t* ia = order + K;
+        int32_t* ib = ia + K;
+        SortWork* wk = ctx->sort_work.as<SortWork>();
+        void* args[] = {&d_mu, &pc_i, &j_i, &n_i, &ka, &kb, &ia, &ib, &wk, &order};
+        const int G = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(ctx->sm_count, 160), (K + 1023) / 1024));
+        CU(cudaLaunchCooperativeKernel((const void*)k_radix_sort_coop, dim3(G), dim3(512), args, 0, st));
+        ctx->launch_counter++;
       }
       k_sigma_uni<<<grid_for(K, 256, cap), 256, 0, st>>>(e.mu.as<double>(), ctx->sort_idx.as<int32_t>(),
                                                          ctx->cols.as<ColMeta>(), pc, j, n, ctx->cfg.magic_clip,
@@ -718,7 +726,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_first, &ctx->mo_rank, &ctx->mo_ctr, &ctx->mo_tie, &ctx->mo_ntie, &ctx->mo_lexpos,
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
-                    &ctx->cand_a, &ctx->cand_b, &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->U, &ctx->S,
+                    &ctx->cand_a, &ctx->cand_b, &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();

@@ -471,6 +471,98 @@ __global__ void k_sort_fill(const double* __restrict__ mu, int32_t pc, int j_col
     }
   }
 }
+// Stable LSD radix sort of one estimator column (cooperative launch, 8 passes of 8 bits) for the
+// univariate bandwidths: order[j] = index of the j-th smallest (value, index).  Each CTA owns a
+// contiguous chunk; per pass: chunk histogram -> grid.sync -> global digit offsets (digit-major,
+// CTA-minor) -> stable scatter by warp match + per-warp digit counts.  Ping-pong buffers.
+struct SortWork {
+  int hist[256][160];  // [digit][cta]
+};
+__global__ void __launch_bounds__(512, 1)
+k_radix_sort_coop(const double* __restrict__ mu, int32_t pc, int j_col, int n, uint64_t* __restrict__ key_a,
+                  uint64_t* __restrict__ key_b, int32_t* __restrict__ idx_a, int32_t* __restrict__ idx_b,
+                  SortWork* __restrict__ wk, int32_t* __restrict__ order) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ int s_hist[256];
+  __shared__ int s_base[256];
+  __shared__ int s_wcnt[16][256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int chunk = (n + G - 1) / G;
+  const int lo = min(n, b * chunk), hi = min(n, lo + chunk);
+  for (int i = lo + tid; i < hi; i += blockDim.x) {
+    key_a[i] = order_bits(mu[(int64_t)i * pc + j_col]);
+    idx_a[i] = i;
+  }
+  uint64_t* kin = key_a;
+  uint64_t* kout = key_b;
+  int32_t* iin = idx_a;
+  int32_t* iout = idx_b;
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = pass * 8;
+    for (int t = tid; t < 256; t += blockDim.x) s_hist[t] = 0;
+    __syncthreads();
+    for (int i = lo + tid; i < hi; i += blockDim.x) atomicAdd(&s_hist[(int)((kin[i] >> shift) & 0xff)], 1);
+    __syncthreads();
+    for (int t = tid; t < 256; t += blockDim.x) wk->hist[t][b] = s_hist[t];
+    grid.sync();
+    // global offset of this CTA's first element of every digit
+    if (tid < 256) {
+      int tot = 0, pre = 0;
+      for (int c = 0; c < G; ++c) {
+        const int v = wk->hist[tid][c];
+        if (c < b) pre += v;
+        tot += v;
+      }
+      s_hist[tid] = tot;
+      s_base[tid] = pre;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int d = 0; d < 256; ++d) {
+        const int t = s_hist[d];
+        s_hist[d] = run;
+        run += t;
+      }
+    }
+    __syncthreads();
+    if (tid < 256) s_base[tid] += s_hist[tid];
+    __syncthreads();
+    // stable scatter, 512 elements at a time
+    for (int t0 = lo; t0 < hi; t0 += blockDim.x) {
+      const int i = t0 + tid;
+      const bool v = i < hi;
+      for (int t = tid; t < 16 * 256; t += blockDim.x) (&s_wcnt[0][0])[t] = 0;
+      __syncthreads();
+      const uint64_t kv = v ? kin[i] : 0;
+      const int d = v ? (int)((kv >> shift) & 0xff) : -1 - lane;
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const int rank_w = __popc(peers & ((1u << lane) - 1u));
+      if (v && rank_w == 0) s_wcnt[warp][d] = __popc(peers);
+      __syncthreads();
+      int off = 0;
+      if (v) {
+        for (int w = 0; w < warp; ++w) off += s_wcnt[w][d];
+        const int pos = s_base[d] + off + rank_w;
+        kout[pos] = kv;
+        iout[pos] = iin[i];
+      }
+      __syncthreads();
+      if (tid < 256) {
+        int tot = 0;
+        for (int w = 0; w < 16; ++w) tot += s_wcnt[w][tid];
+        s_base[tid] += tot;
+      }
+      __syncthreads();
+    }
+    grid.sync();
+    uint64_t* tk = kin; kin = kout; kout = tk;
+    int32_t* ti = iin; iin = iout; iout = ti;
+  }
+  for (int i = lo + tid; i < hi; i += blockDim.x) order[i] = iin[i];
+}
+
 // Whole bitonic sort in shared memory for m2 <= 4096 (one CTA of 1024 threads).
 __global__ void __launch_bounds__(1024, 1)
 k_sort_small(const double* __restrict__ mu, int32_t pc, int j_col, int m, int m2, int32_t* __restrict__ order) {

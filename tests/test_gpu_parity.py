@@ -355,3 +355,40 @@ def test_categorical_distance_func_tables(eng):
             close(ll, s.logl, 0, 1e-12)
             close(lg, s.logg, 0, 1e-12)
             assert int(best[0]) == s.best
+
+
+def test_univariate_large_history_radix_sorted_bandwidths(eng):
+    """Univariate bandwidths above 4096 kernels go through the cooperative radix sort; compare
+    sigma / samples / log_pdf with the oracle (stable order, so duplicates are well defined)."""
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(8)
+    n, C = 9000, 64
+    specs = [ParamSpec(kind=0, low=-2.0, high=3.0), ParamSpec(kind=0, low=1e-3, high=10.0, log=True),
+             ParamSpec(kind=1, low=0, high=40, step=1)]
+    params = [orc.Param("float", -2.0, 3.0), orc.Param("float", 1e-3, 10.0, None, True), orc.Param("int", 0.0, 40.0, 1.0)]
+    X = np.stack([rs.uniform(-2, 3, n), np.exp(rs.uniform(np.log(1e-3), np.log(10), n)),
+                  rs.randint(0, 41, n).astype(float)], 1)
+    X[:50, 0] = X[50:100, 0]  # exact duplicates in a continuous column too
+    cat = np.zeros(n, np.int8)
+    key = np.stack([rs.normal(size=n), np.zeros(n)], 1)
+    eng.set_space(specs)
+    eng.set_history(X, cat, key)
+    for magic_clip in (True, False):
+        cfg = orc.Config(multivariate=False, stable_sort=True, magic_clip=magic_clip)
+        for j in range(3):
+            u = draw_uniforms(np.random.RandomState(40 + j), C, 0, 1)
+            x, acq, best = eng.suggest([j], u, 1, n_below=25, n_candidates=C, multivariate=False,
+                                       magic_clip=magic_clip)
+            smp, ll, lg = eng.get_candidates()
+            s = orc.suggest(X, cat, key, params, [j], cfg, 25, C, np.random.RandomState(40 + j))
+            wa, mua, sga = eng.get_mixture(1)
+            close(sga[:, 0], s.mix_above.sigma[0], 1e-15, 1e-300)
+            if params[j].step is None:
+                close(smp[:, 0], s.samples[:, 0], 1e-12, 1e-12)
+                tol = 1e-12 if magic_clip else 1e-9  # without the clip sigma reaches 1e-12 * range
+            else:
+                assert np.array_equal(smp[:, 0], s.samples[:, 0])
+                tol = 1e-9
+            close(ll, s.logl, 0, tol)
+            close(lg, s.logg, 0, tol)
+            assert int(best[0]) == s.best
