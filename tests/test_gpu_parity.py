@@ -382,7 +382,8 @@ def test_univariate_large_history_radix_sorted_bandwidths(eng):
             smp, ll, lg = eng.get_candidates()
             s = orc.suggest(X, cat, key, params, [j], cfg, 25, C, np.random.RandomState(40 + j))
             wa, mua, sga = eng.get_mixture(1)
-            close(sga[:, 0], s.mix_above.sigma[0], 1e-15, 1e-300)
+            # gaps of log-transformed values inherit the 1-ulp difference between device and NumPy log()
+            close(sga[:, 0], s.mix_above.sigma[0], 1e-15, 2e-15 if params[j].log else 1e-300)
             if params[j].step is None:
                 close(smp[:, 0], s.samples[:, 0], 1e-12, 1e-12)
                 tol = 1e-12 if magic_clip else 1e-9  # without the clip sigma reaches 1e-12 * range
