@@ -314,6 +314,34 @@ def run_b200(args) -> None:
     e2e_value = world * e2e_steps / e2e_wall
     assert len(out) == N_PARAMS and all(0.0 <= v <= 1.0 for v in out.values())
 
+    # ---- extras (rank 0, N=1 only): other shapes of the same path, not the headline ------------------
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        # cold suggestion: history upload (25.6 MB H2D) + everything else
+        t0 = time.perf_counter()
+        eng.set_history(X, cat, key)
+        eng.suggest(cols, Unp[0], 1, **cfg)
+        extras["cold_suggestion_ms"] = (time.perf_counter() - t0) * 1e3
+        # univariate TPE (the reference default): 32 sample_independent-style calls per trial
+        ucfg = dict(cfg, multivariate=False)
+        ru = np.random.RandomState(5)
+        for rep in range(2):
+            t0 = time.perf_counter()
+            for j in range(N_PARAMS):
+                eng.suggest([j], ru.random_sample(N_CAND * 2), 1, **ucfg)
+            uni = time.perf_counter() - t0
+        extras["univariate_trial_ms"] = uni * 1e3
+        extras["univariate_suggestions_per_s"] = 1.0 / uni
+        # config-5 shape: 8192 concurrent asks with the default n_ei_candidates = 24, one device call
+        bcfg = dict(cfg, n_candidates=24)
+        n_asks = 8192
+        ub = np.random.RandomState(6).random_sample(n_asks * 24 * (1 + N_PARAMS))
+        for rep in range(2):
+            t0 = time.perf_counter()
+            eng.suggest(cols, ub, n_asks, **bcfg)
+            bt = time.perf_counter() - t0
+        extras["batched_asks"] = {"n_asks": n_asks, "n_ei_candidates": 24, "ms": bt * 1e3,
+                                  "suggestions_per_s": n_asks / bt}
     if rank == 0:
         peak, peak_src = measured_peaks()
         k_ms = float(stage[5]) / args.steps  # main log-density kernel under g(x)
@@ -352,6 +380,8 @@ def run_b200(args) -> None:
                      "frac": (fl / (k_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
                      "algorithmic_flops": fl, "peak_source": "tpe_probe_fp64_tflops (DFMA microbenchmark, this run)"},
         }
+        if extras:
+            line["extras"] = extras
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(X, loss)
         print(json.dumps(line), flush=True)
@@ -367,6 +397,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the univariate / batched / cold extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

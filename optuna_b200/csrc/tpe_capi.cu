@@ -193,7 +193,7 @@ struct FastInst {
 const FastCfg kConstBig[] = {
     FastInst<1, 1, 4, 256, 2048, 3, false, 2>::cfg(), FastInst<2, 1, 4, 256, 1024, 3, false, 2>::cfg(),
     FastInst<4, 1, 4, 256, 1024, 3, false, 2>::cfg(), FastInst<8, 1, 4, 256, 512, 3, false, 1>::cfg(),
-    FastInst<16, 1, 2, 256, 256, 3, false, 2>::cfg(), FastInst<32, 1, 1, 256, 128, 3, false, 2>::cfg(),
+    FastInst<16, 1, 2, 256, 256, 3, false, 2>::cfg(), FastInst<32, 1, 1, 512, 128, 3, false, 1>::cfg(),
     FastInst<64, 1, 1, 256, 64, 3, false, 1>::cfg(),
 };
 const FastCfg kPairBig[] = {
@@ -223,6 +223,9 @@ const FastCfg kConst32Variants[] = {
     FastInst<32, 1, 2, 320, 128, 3, false, 1>::cfg(),  // 4: 2 candidates / lane, 10 warps / SM
     FastInst<32, 1, 2, 384, 128, 3, false, 1>::cfg(),  // 5: 2 candidates / lane, 12 warps / SM
     FastInst<32, 1, 2, 128, 64, 3, false, 2>::cfg(),   // 6: 2 candidates / lane, 2 CTAs x 4 warps
+    FastInst<32, 1, 1, 128, 64, 3, false, 4>::cfg(),   // 7: 4 CTAs x 4 warps
+    FastInst<32, 1, 1, 256, 128, 2, false, 2>::cfg(),  // 8: 2 stages
+    FastInst<32, 1, 1, 512, 128, 3, false, 1>::cfg(),  // 9: 1 CTA x 16 warps
 };
 constexpr int kMaxFastP = 64;
 
@@ -235,7 +238,7 @@ const FastCfg* pick_fast(int mode, int pb, int64_t Ct) {
   const bool small = Ct <= 128;
   if (mode == 2 && pb == 32 && !small) {
     const char* v = getenv("TPE_FAST_VARIANT");
-    if (v && v[0] >= '0' && v[0] <= '6') return &kConst32Variants[v[0] - '0'];
+    if (v && v[0] >= '0' && v[0] <= '9') return &kConst32Variants[v[0] - '0'];
   }
   const FastCfg* tabs = (mode == 2) ? (small ? kConstSmall : kConstBig) : (small ? kPairSmall : kPairBig);
   for (int i = 0; i < 7; ++i)
