@@ -423,18 +423,12 @@ class B200TPESampler(BaseSampler):
         return h.n_finished, [h.columns[name] for name in search_space]
 
     def _draw_uniforms(self, search_space: dict[str, BaseDistribution]) -> np.ndarray:
-        rng = self._rng.rng
+        """The uniforms one reference `_sample` consumes, in its order: C for `rng.choice`, C per
+        categorical column, then an (n_numeric, C) block (probability_distributions.py:87,100,138-144).
+        `rand`, `choice` and `uniform(0, 1)` all take consecutive `random_sample` outputs unchanged, so
+        ONE call yields the identical stream (checked in tests/test_host_glue.py) at half the cost."""
         c = self._n_ei_candidates
-        parts = [rng.rand(c)]
-        n_num = 0
-        for d in search_space.values():
-            if isinstance(d, CategoricalDistribution):
-                parts.append(rng.rand(c))
-            else:
-                n_num += 1
-        if n_num:
-            parts.append(rng.uniform(low=0, high=1, size=(n_num, c)).ravel())
-        return np.concatenate(parts)
+        return self._rng.rng.random_sample(c * (1 + len(search_space)))
 
     def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
         """TPESampler._sample (sampler.py:523-560)."""
