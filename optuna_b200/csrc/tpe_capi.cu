@@ -662,18 +662,19 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
         e.cst.as<double>(), K, 0, K, e.tab.as<double>(), ctx->oob.as<uint8_t>(), e.fix.as<double2>(), ctx->ct_stride);
     ctx->launch_counter++;
   } else {
-    const int64_t cblocks = (Ct + 127) / 128;
-    const int64_t target = (int64_t)ctx->sm_count * 8;
-    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>((K + 31) / 32, target / cblocks));
-    const int64_t kps = (K + nsplit - 1) / nsplit;
-    nsplit = (K + kps - 1) / kps;
+    // pair-parallel generic kernel: grid = (candidates, kernel chunks of 256 * kpt)
+    int kpt = 1;
+    while ((K + 256ll * kpt - 1) / (256ll * kpt) > 65535 ||
+           ((K + 256ll * kpt - 1) / (256ll * kpt)) * Ct > (1ll << 22) * 4)
+      kpt *= 2;  // keep the partial table (nsplit x Ct) and the grid within bounds
+    const int64_t nsplit = (K + 256ll * kpt - 1) / (256ll * kpt);
     CU(e.part.ensure((size_t)nsplit * ctx->ct_stride * 16));
     e.nsplit = (int)nsplit;
-    k_logpdf_generic<<<dim3((unsigned)cblocks, (unsigned)nsplit), 128, 0, st>>>(
+    k_logpdf_pairs<<<dim3((unsigned)Ct, (unsigned)nsplit), 256, (size_t)ctx->pc * 8, st>>>(
         ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
-        e.cst.as<double>(), K, 0, kps, e.tab.as<double>(), nullptr, e.part.as<double2>(), ctx->ct_stride);
+        e.cst.as<double>(), K, kpt, e.tab.as<double>(), e.part.as<double2>(), ctx->ct_stride);
     ctx->launch_counter++;
-    ctx->last_kernel = "k_logpdf_generic";
+    ctx->last_kernel = "k_logpdf_pairs";
     if (after_main) CU(cudaEventRecord(after_main, st));
   }
   CU(cudaGetLastError());

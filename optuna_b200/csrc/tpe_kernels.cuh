@@ -1041,6 +1041,44 @@ __global__ void k_logpdf_generic(const double* __restrict__ S, int64_t Ct, const
   part[blockIdx.y * ct_stride + ct] = make_double2(m, s);
 }
 
+// Generic path, pair-parallel: one CTA = one candidate x (256 * kpt) kernels, one thread evaluates
+// whole (candidate, kernel) cell sums with the reference's operation order, block-level log-sum-exp.
+// Used for spaces with discrete / categorical columns (every thread of a warp walks the same column
+// kinds, so the special-function branches are the only divergence).
+__global__ void __launch_bounds__(256)
+k_logpdf_pairs(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols, int32_t pc,
+               const double* __restrict__ mu, const double* __restrict__ sigma, const double* __restrict__ cst,
+               int64_t K, int kpt, const double* __restrict__ tab, double2* __restrict__ part, int64_t ct_stride) {
+  extern __shared__ double s_x[];  // pc doubles + 16 reduction slots
+  __shared__ double s_m[8], s_s[8];
+  const int64_t ct = blockIdx.x;
+  const int64_t k0 = (int64_t)blockIdx.y * 256 * kpt;
+  for (int j = threadIdx.x; j < pc; j += 256) s_x[j] = S[ct * pc + j];
+  __syncthreads();
+  double m = -INFINITY, s = 0.0;
+  for (int q = 0; q < kpt; ++q) {
+    const int64_t k = k0 + (int64_t)q * 256 + threadIdx.x;
+    if (k < K) {
+      const double L = cst[k] + cell_sum_exact(s_x, mu + k * pc, sigma + k * pc, cols, pc, k == K - 1, tab);
+      lse_push(L, m, s);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    lse_merge(m2, s2, m, s);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_m[threadIdx.x >> 5] = m;
+    s_s[threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) lse_merge(s_m[w], s_s[w], m, s);
+    part[(int64_t)blockIdx.y * ct_stride + ct] = make_double2(m, s);
+  }
+}
+
 // Fast path: every selected column continuous.  Kernels are streamed through shared memory by TMA
 // bulk copies (mbarrier completion); candidates live in registers; online log-sum-exp per candidate.
 // Two fp64 instructions per (candidate, kernel, param) cell:
