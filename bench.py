@@ -59,7 +59,8 @@ def algorithmic_flops(n=N_TRIALS, p=N_PARAMS, c=N_CAND, n_below=25) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, ~1 kHz; nvidia-smi
+    subprocesses are too slow for a 50 ms region and remain only as a fallback)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -67,36 +68,66 @@ class ClockSampler:
 
     def __init__(self, index: int) -> None:
         self.index = index
-        self.rows: list[list[str]] = []
+        self.sm: list[float] = []
+        self.max_sm = None
+        self.reasons: set[str] = set()
         self._stop = threading.Event()
         self._t: threading.Thread | None = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
 
-    def _run(self) -> None:
+    def _poll_nvml(self) -> None:
+        n = self._nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    def _poll_smi(self) -> None:
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
                 for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
+                    c = [v.strip() for v in line.split(",")]
+                    self.sm.append(float(c[0]))
+                    self.max_sm = float(c[1])
+                    for i, nm in enumerate(names):
+                        if len(c) > 3 + i and c[3 + i].lower().startswith("active"):
+                            self.reasons.add(nm)
             except Exception:
                 pass
             self._stop.wait(0.2)
 
     def start(self) -> None:
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t = threading.Thread(target=self._poll_nvml if self._nvml else self._poll_smi, daemon=True)
         self._t.start()
 
     def stop(self) -> dict:
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active")
-                                                          for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 def measured_peaks() -> tuple[float, str]:
