@@ -113,7 +113,7 @@ struct tpe_ctx {
   bool fast = false;
   int fast_mode = 0;  // 0 generic, 1 PAIR (sigma per kernel), 2 CONST (sigma per column)
   tpe_split_info info{};
-  DevBuf row_ok, member, cand_a, cand_b, counts, split_work;
+  DevBuf row_ok, member, counts, split_work;
   Estimator est[2];
   DevBuf sort_val, sort_idx, sort_work;
 
@@ -730,7 +730,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_first, &ctx->mo_rank, &ctx->mo_ctr, &ctx->mo_tie, &ctx->mo_ntie, &ctx->mo_lexpos,
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
-                    &ctx->cand_a, &ctx->cand_b, &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
+                    &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
@@ -934,9 +934,6 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
 
   const int64_t N = ctx->N;
   const int64_t nal = std::max<int64_t>(N, 1);
-  CU(ctx->member.ensure((size_t)nal));
-  CU(ctx->cand_a.ensure((size_t)nal * 4));
-  CU(ctx->cand_b.ensure((size_t)nal * 4));
   CU(ctx->counts.ensure(64));
   for (int w = 0; w < 2; ++w) {
     CU(ctx->est[w].rows.ensure((size_t)nal * 8));

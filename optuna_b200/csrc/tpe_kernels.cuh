@@ -1,8 +1,8 @@
 // CUDA kernels of the TPE suggestion path (sm_100a).  Host orchestration lives in tpe_capi.cu.
 //
 // Stage map (reference file:line each kernel replaces):
-//   k_rowok / k_split        optuna/samplers/_tpe/sampler.py:511-521, :686-722, :735-742, :782-821
-//   k_mu / k_sigma_* / k_const / k_weights / k_cat_tables
+//   k_rowok / k_split_coop   optuna/samplers/_tpe/sampler.py:511-521, :686-722, :735-742, :782-821
+//   k_build_mv / k_mu / k_sigma_* / k_const / k_wraw..k_wnorm / k_cat_tables
 //                            optuna/samplers/_tpe/parzen_estimator.py:39-78, :132-251
 //   k_sample                 optuna/samplers/_tpe/probability_distributions.py:86-152
 //   k_logpdf_fast / k_logpdf_generic
@@ -34,128 +34,7 @@ __global__ void k_rowok(const double* __restrict__ X, int64_t n, int32_t pall, c
   }
 }
 
-__device__ __forceinline__ int key_digit(const double* __restrict__ key, int i, int d) {
-  const uint64_t u = order_bits(key[2 * (int64_t)i + (d >= 8 ? 0 : 1)]);
-  return (int)((u >> ((d & 7) * 8)) & 0xffull);
-}
-
-// counts: [0] |below| before the row filter, [1] below observations, [2] above observations
-// Single CTA of 1024 threads (N is 1e5-1e7: a handful of ordered sweeps).
-__global__ void __launch_bounds__(1024, 1)
-k_split(int n, const int8_t* __restrict__ cat, const double* __restrict__ key, int64_t n_below,
-        const uint8_t* __restrict__ row_ok, uint8_t* __restrict__ member, int* __restrict__ cand_a,
-        int* __restrict__ cand_b, int64_t* __restrict__ below_rows, int64_t* __restrict__ below_pos,
-        int64_t* __restrict__ above_rows, int64_t* __restrict__ counts) {
-  __shared__ int s_warp[32];
-  __shared__ int s_hist[256];
-  __shared__ int s_pick[3];  // digit, #less, #equal
-  const int tid = threadIdx.x;
-
-  for (int i = tid; i < n; i += 1024) member[i] = 0;
-  __syncthreads();
-
-  int64_t remaining = n_below < 0 ? 0 : n_below;
-  for (int c = 0; c < 3; ++c) {
-    // ordered list of this category's trials
-    int cnt = 0;
-    for (int base = 0; base < n; base += 1024) {
-      const int i = base + tid;
-      const bool f = i < n && cat[i] == c;
-      const int2 r = block_rank_1024(f, s_warp);
-      if (f) cand_a[cnt + r.x] = i;
-      cnt += r.y;
-    }
-    __syncthreads();
-    const int m = (int)(remaining < (int64_t)cnt ? remaining : (int64_t)cnt);
-    remaining -= m;
-    if (m == 0) continue;
-    if (m == cnt) {
-      for (int j = tid; j < cnt; j += 1024) member[cand_a[j]] = 1;
-      __syncthreads();
-      continue;
-    }
-    // radix select of the m smallest (key0, key1, index): most significant byte first
-    int* cur = cand_a;
-    int* nxt = cand_b;
-    int ncur = cnt, need = m;
-    for (int d = 15; d >= 0 && need > 0; --d) {
-      for (int b = tid; b < 256; b += 1024) s_hist[b] = 0;
-      __syncthreads();
-      for (int base = 0; base < ncur; base += 1024) {
-        const int j = base + tid;
-        const bool v = j < ncur;
-        const int dg = v ? key_digit(key, cur[j], d) : -1 - (tid & 31);
-        const unsigned peers = __match_any_sync(0xffffffffu, dg);
-        if (v && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&s_hist[dg], __popc(peers));
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int cum = 0, b = 0;
-        for (; b < 256; ++b) {
-          if (cum + s_hist[b] >= need) break;
-          cum += s_hist[b];
-        }
-        s_pick[0] = b;
-        s_pick[1] = cum;
-        s_pick[2] = s_hist[b];
-      }
-      __syncthreads();
-      const int D = s_pick[0], less = s_pick[1], eq = s_pick[2];
-      int nn = 0;
-      for (int base = 0; base < ncur; base += 1024) {
-        const int j = base + tid;
-        const bool v = j < ncur;
-        const int i = v ? cur[j] : 0;
-        const int dg = v ? key_digit(key, i, d) : 256;
-        if (v && dg < D) member[i] = 1;
-        const int2 r = block_rank_1024(v && dg == D, s_warp);
-        if (v && dg == D) nxt[nn + r.x] = i;
-        nn += r.y;
-      }
-      __syncthreads();
-      need -= less;
-      ncur = eq;
-      int* t = cur;
-      cur = nxt;
-      nxt = t;
-      if (need == ncur) {
-        for (int j = tid; j < ncur; j += 1024) member[cur[j]] = 1;
-        need = 0;
-      }
-      __syncthreads();
-    }
-    if (need > 0) {  // identical keys: earliest trials first (stable)
-      for (int j = tid; j < need; j += 1024) member[cur[j]] = 1;
-    }
-    __syncthreads();
-  }
-
-  // ordered partition (ascending trial number) + drop rows lacking a selected parameter
-  int nb_all = 0, nb = 0, na = 0;
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + tid;
-    const bool v = i < n;
-    const bool isb = v && cat[i] != 3 && member[i] != 0;
-    const bool ok = v && (row_ok == nullptr || row_ok[i] != 0);
-    const int2 rb_all = block_rank_1024(isb, s_warp);
-    const int2 rb = block_rank_1024(isb && ok, s_warp);
-    const int2 ra = block_rank_1024(v && !isb && ok, s_warp);
-    if (isb && ok) {
-      below_rows[nb + rb.x] = i;
-      below_pos[nb + rb.x] = nb_all + rb_all.x;
-    }
-    if (v && !isb && ok) above_rows[na + ra.x] = i;
-    nb_all += rb_all.y;
-    nb += rb.y;
-    na += ra.y;
-  }
-  if (tid == 0) {
-    counts[0] = nb_all;
-    counts[1] = nb;
-    counts[2] = na;
-  }
-}
-
+// counts written by the split: [0] |below| before the row filter, [1] below observations, [2] above observations
 // ------------------------------------------------------------------------------------------------
 // Multi-CTA split (cooperative launch): the same selection as k_split, spread over the whole GPU.
 // No candidate lists: every radix pass re-scans the (tiny: 17 B/trial) key arrays with all CTAs and
@@ -440,37 +319,6 @@ __global__ void k_sigma_uni(const double* __restrict__ mu, const int32_t* __rest
   }
 }
 
-// Bitonic sort network step on (value, index) pairs held in global memory; `m2` = padded length
-// (power of two); padded slots carry +inf / INT_MAX.  One launch per (k, j) step.
-__global__ void k_bitonic_step(double* __restrict__ val, int32_t* __restrict__ idx, int64_t m2, int64_t j, int64_t k) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m2; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t l = i ^ j;
-    if (l > i) {
-      const double a = val[i], b = val[l];
-      const int32_t ia = idx[i], ib = idx[l];
-      const bool a_gt_b = (a > b) || (a == b && ia > ib);
-      const bool up = (i & k) == 0;
-      if (up ? a_gt_b : !a_gt_b) {
-        val[i] = b; val[l] = a;
-        idx[i] = ib; idx[l] = ia;
-      }
-    }
-  }
-}
-__global__ void k_sort_fill(const double* __restrict__ mu, int32_t pc, int j_col, int64_t m, int64_t m2,
-                            double* __restrict__ val, int32_t* __restrict__ idx) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m2; i += (int64_t)gridDim.x * blockDim.x) {
-    if (i < m) {
-      double v = mu[i * pc + j_col];
-      if (v == 0.0) v = 0.0;
-      val[i] = v;
-      idx[i] = (int32_t)i;
-    } else {
-      val[i] = INFINITY;
-      idx[i] = 0x7fffffff;
-    }
-  }
-}
 // Stable LSD radix sort of one estimator column (cooperative launch, 8 passes of 8 bits) for the
 // univariate bandwidths: order[j] = index of the j-th smallest (value, index).  Each CTA owns a
 // contiguous chunk; per pass: chunk histogram -> grid.sync -> global digit offsets (digit-major,
@@ -663,63 +511,6 @@ __global__ void k_tab_pad(double2* __restrict__ tabp, double* __restrict__ tabc,
     for (int sl = ncont + threadIdx.x; sl < pb; sl += blockDim.x) colprm[sl] = make_double2(0.0, 0.0);
 }
 
-// Mixture weights (parzen_estimator.py:59-69, sampler.py:61-69).  Single CTA of 1024 threads.
-//   raw[k] = w_in[pos[k]] (or w_in[k] when pos == nullptr), or default_weights(n)[k] when w_in == nullptr;
-//   raw[n] = prior_weight;  w = raw / sum(raw);  logw = ln w;  cst = cst_part + logw;
-//   cdf (optional) = cumsum(w) / cumsum(w)[-1], sequential like numpy.cumsum.
-__global__ void __launch_bounds__(1024, 1)
-k_weights(const double* __restrict__ w_in, const int64_t* __restrict__ pos, int64_t n, double prior_weight,
-          double* __restrict__ w, double* __restrict__ logw, const double* __restrict__ cst_part,
-          double* __restrict__ cst, double* __restrict__ cdf, int64_t k_alloc) {
-  __shared__ double s_red[32];
-  __shared__ double s_total;
-  const int tid = threadIdx.x;
-  const int64_t K = n + 1;
-  // default_weights ramp: np.linspace(1/n, 1, n-25) = arange * step + start, last forced to 1
-  const int64_t nramp = n - 25;
-  const double start = n > 0 ? TPE_DIV(1.0, (double)n) : 0.0;
-  const double step = nramp > 1 ? TPE_DIV(TPE_SUB(1.0, start), (double)(nramp - 1)) : 0.0;
-  double part = 0.0;
-  for (int64_t k = tid; k < K; k += 1024) {
-    double r;
-    if (n == 0) r = 1.0;
-    else if (k == n) r = prior_weight;
-    else if (w_in != nullptr) r = w_in[pos != nullptr ? pos[k] : k];
-    else if (n < 25 || k >= nramp) r = 1.0;
-    else if (k == nramp - 1 && nramp > 1) r = 1.0;
-    else r = TPE_ADD(TPE_MUL((double)k, step), start);
-    w[k] = r;
-    part += r;
-  }
-  part = warp_sum(part);
-  if ((tid & 31) == 0) s_red[tid >> 5] = part;
-  __syncthreads();
-  if (tid < 32) {
-    double v = warp_sum(s_red[tid]);
-    if (tid == 0) s_total = v;
-  }
-  __syncthreads();
-  const double total = s_total;
-  for (int64_t k = tid; k < K; k += 1024) {
-    const double v = TPE_DIV(w[k], total);
-    w[k] = v;
-    const double lw = log(v);
-    logw[k] = lw;
-    cst[k] = cst_part[k] + lw;
-  }
-  for (int64_t k = K + tid; k < k_alloc; k += 1024) cst[k] = -INFINITY;  // padding read by bulk copies
-  __syncthreads();
-  if (cdf != nullptr && tid == 0) {
-    double run = 0.0;
-    for (int64_t k = 0; k < K; ++k) {
-      run = TPE_ADD(run, w[k]);
-      cdf[k] = run;
-    }
-    const double last = cdf[K - 1];
-    for (int64_t k = 0; k < K; ++k) cdf[k] = TPE_DIV(cdf[k], last);
-  }
-}
-
 // Fused multivariate build: k_mu + k_sigma_mv + k_const in one pass (one warp per kernel, lanes over
 // columns).  mode / tables as in k_const.
 __global__ void k_build_mv(const double* __restrict__ X, int32_t pall, const int64_t* __restrict__ rows, int64_t n,
@@ -780,7 +571,9 @@ __global__ void k_build_mv(const double* __restrict__ X, int32_t pall, const int
   }
 }
 
-// Multi-CTA version of k_weights: raw weights + per-block partial sums, then normalisation.
+// Mixture weights (parzen_estimator.py:59-69, sampler.py:61-69): raw weights (default ramp computed
+// here, or host-evaluated) + per-block partial sums, then normalisation, log-weights, cst and the
+// sequential cumulative sum used by rng.choice.
 // Partial sums are combined in a fixed order, so the result is deterministic.
 __device__ __forceinline__ double raw_weight(const double* __restrict__ w_in, const int64_t* __restrict__ pos,
                                              int64_t n, int64_t k, double prior_weight) {
