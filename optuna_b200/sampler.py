@@ -442,8 +442,12 @@ class B200TPESampler(BaseSampler):
                                  f" but got {self._prior_weight}.")
             eng = self._eng()
             if self._weights is default_weights:
+                # split + estimator builds are queued on the GPU first; the host draws the uniforms
+                # (the reference's RNG stream, ~0.5 ms for 4096 x 33 doubles) while they run
+                eng.prepare(cols, **cfg)
+                eng.build()
                 u = self._draw_uniforms(search_space)
-                x, _, _ = eng.suggest(cols, u, 1, **cfg)
+                x, _, _ = eng.sample_and_select(u, 1)
             else:
                 _, nb, na = eng.prepare(cols, **cfg)
                 # multi-objective studies weight l(x) by hypervolume contributions (computed by the
