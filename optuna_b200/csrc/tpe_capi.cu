@@ -66,10 +66,11 @@ struct Estimator {
   int64_t n = 0, K = 0;
   DevBuf rows, pos, wstage, wpart, w, logw, cdf, mu, sigma, cst_part, cst, tabp, tabc, colprm, tab, part, fix;
   DevBuf tab32, tab64p, d32;   // fp32-screening copies (tpe_screen.cuh)
+  DevBuf cls, dtab, offgrid;   // tabulated discrete columns (multivariate)
   bool screen_ready = false;
   int nsplit = 0;
   void release() {
-    for (DevBuf* b : {&tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
+    for (DevBuf* b : {&cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
                       &part, &fix})
       b->release();
   }
@@ -110,6 +111,7 @@ struct tpe_ctx {
   DevBuf cols;
   int32_t pc = 0, ncont = 0, ndisc = 0, ncat = 0, nnum = 0, pb = 0;
   int64_t tab_doubles = 0;
+  int64_t dtab_doubles = 0;  // cell-mass tables of tabulated discrete columns
   bool fast = false;
   int fast_mode = 0;  // 0 generic, 1 PAIR (sigma per kernel), 2 CONST (sigma per column)
   tpe_split_info info{};
@@ -457,6 +459,12 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
   if (ctx->fast_mode == 2) CU(e.tabc.ensure((size_t)K * ctx->pb * 8 + 16));
   if (ctx->fast) CU(e.colprm.ensure((size_t)ctx->pb * 16));
   if (ctx->tab_doubles) CU(e.tab.ensure((size_t)ctx->tab_doubles * 8));
+  if (ctx->dtab_doubles) {
+    CU(e.dtab.ensure((size_t)ctx->dtab_doubles * 8));
+    CU(e.cls.ensure((size_t)K * pc * 4));
+    CU(e.offgrid.ensure(16));
+    CU(cudaMemsetAsync(e.offgrid.p, 0, 16, st));
+  }
 
   if (ctx->fast && ctx->pb > ctx->ncont) {
     k_tab_pad<<<grid_for(K * (ctx->pb - ctx->ncont), 256, cap), 256, 0, st>>>(
@@ -468,7 +476,8 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
     k_build_mv<<<grid_for(K * 32, 256, cap), 256, 0, st>>>(
         ctx->X.as<double>(), (int32_t)ctx->space.size(), e.rows.as<int64_t>(), n, ctx->cols.as<ColMeta>(), pc,
         ctx->cfg.magic_clip, ctx->pb, ctx->fast_mode, e.mu.as<double>(), e.sigma.as<double>(), e.tabp.as<double2>(),
-        e.tabc.as<double>(), e.colprm.as<double2>(), e.cst_part.as<double>());
+        e.tabc.as<double>(), e.colprm.as<double2>(), e.cst_part.as<double>(),
+        ctx->dtab_doubles ? e.cls.as<int32_t>() : nullptr, ctx->dtab_doubles ? e.offgrid.as<int>() : nullptr);
     ctx->launch_counter++;
   } else {
     k_mu<<<grid_for(K * pc, 256, cap), 256, 0, st>>>(ctx->X.as<double>(), (int32_t)ctx->space.size(),
@@ -670,9 +679,21 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     const int64_t nsplit = (K + 256ll * kpt - 1) / (256ll * kpt);
     CU(e.part.ensure((size_t)nsplit * ctx->ct_stride * 16));
     e.nsplit = (int)nsplit;
-    k_logpdf_pairs<<<dim3((unsigned)Ct, (unsigned)nsplit), 256, (size_t)ctx->pc * 8, st>>>(
+    if (ctx->dtab_doubles) {
+      int64_t rows_max = 1;
+      for (const ColMeta& cm : ctx->cols_h)
+        if (cm.grid > 0) rows_max = std::max<int64_t>(rows_max, (int64_t)std::min<int64_t>(Ct, cm.grid) * (cm.grid + 1));
+      const unsigned gx = (unsigned)std::min<int64_t>((rows_max + 255) / 256, ctx->sm_count * 4);
+      k_disc_tables<<<dim3(gx, (unsigned)ctx->pc), 256, 0, st>>>(ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(),
+                                                                 e.sigma.as<double>(), K, ctx->S.as<double>(), Ct,
+                                                                 e.dtab.as<double>());
+      ctx->launch_counter++;
+    }
+    k_logpdf_pairs<<<dim3((unsigned)Ct, (unsigned)nsplit), 256, (size_t)ctx->pc * sizeof(PairCol), st>>>(
         ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
-        e.cst.as<double>(), K, kpt, e.tab.as<double>(), e.part.as<double2>(), ctx->ct_stride);
+        e.cst.as<double>(), K, kpt, e.tab.as<double>(), ctx->dtab_doubles ? e.cls.as<int32_t>() : nullptr,
+        ctx->dtab_doubles ? e.dtab.as<double>() : nullptr, ctx->dtab_doubles ? e.offgrid.as<int>() : nullptr,
+        ctx->oob.as<uint8_t>(), e.part.as<double2>(), ctx->ct_stride);
     ctx->launch_counter++;
     ctx->last_kernel = "k_logpdf_pairs";
     if (after_main) CU(cudaEventRecord(after_main, st));
@@ -878,7 +899,7 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
   const int P = (int)ctx->space.size();
   ctx->cols_h.clear();
   ctx->ncont = ctx->ndisc = ctx->ncat = ctx->nnum = 0;
-  int64_t tab = 0;
+  int64_t tab = 0, dtab = 0;
   bool need_rowok = false;
   for (int j = 0; j < n_cols; ++j) {
     const int src = cols[j];
@@ -916,6 +937,12 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
       if (d.has_step) {
         cm.cls = COL_DISC;
         cm.slot = ctx->ndisc++;
+        const double gsz = floor((d.high - d.low) / d.step + 0.5) + 1.0;
+        if (cfg->multivariate && gsz >= 1.0 && gsz <= 4096.0 && dtab + (int64_t)(gsz + 1) * (int64_t)gsz <= (1ll << 24)) {
+          cm.grid = (int32_t)gsz;
+          cm.dtab_off = dtab;
+          dtab += (int64_t)(gsz + 1) * (int64_t)gsz;
+        }
       } else {
         cm.cls = COL_CONT;
         cm.slot = ctx->ncont++;
@@ -926,6 +953,7 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
   }
   ctx->pc = n_cols;
   ctx->tab_doubles = tab;
+  ctx->dtab_doubles = dtab;
   ctx->fast = (ctx->ndisc == 0 && ctx->ncat == 0 && ctx->ncont <= kMaxFastP);
   ctx->pb = ctx->fast ? pick_pb(ctx->ncont) : 0;
   ctx->fast_mode = ctx->fast ? (cfg->multivariate ? 2 : 1) : 0;
@@ -1160,12 +1188,10 @@ int tpe_logpdf(tpe_ctx* ctx, int which, const double* x, int64_t n, double* out)
   if (rc) return rc;
   ctx->sampled = false;
   CU(cudaMemcpyAsync(ctx->S.p, x, (size_t)n * ctx->pc * 8, cudaMemcpyHostToDevice, st));
-  if (ctx->fast) {
-    k_prep_points<<<grid_for(n * ctx->pc, 256, ctx->sm_count * 8), 256, 0, st>>>(
-        ctx->S.as<double>(), n, ctx->cols.as<ColMeta>(), ctx->pc, ctx->xT.as<double>(), ctx->ct_stride,
-        ctx->oob.as<uint8_t>());
-    ctx->launch_counter++;
-  }
+  k_prep_points<<<grid_for(n * ctx->pc, 256, ctx->sm_count * 8), 256, 0, st>>>(
+      ctx->S.as<double>(), n, ctx->cols.as<ColMeta>(), ctx->pc, ctx->fast ? ctx->xT.as<double>() : nullptr,
+      ctx->ct_stride, ctx->oob.as<uint8_t>());
+  ctx->launch_counter++;
   rc = run_logpdf(ctx, which, n);
   if (rc) return rc;
   Estimator& e = ctx->est[which];

@@ -18,7 +18,8 @@ struct ColMeta {
   int32_t cat_rank;   // rank among categorical columns, -1 otherwise
   int32_t tab_off;    // categorical: offset (in doubles) of this column's (nch+1) x nch table
   int32_t dist_off;   // categorical distance table offset in ctx->cat_dist or -1
-  int32_t pad_;
+  int32_t grid;       // discrete column tabulated over its grid: number of grid values, else 0
+  int64_t dtab_off;   // offset (doubles) of its grid x (grid + 1) table of cell masses
   double low, high, step;  // as given by the distribution (step = 0 when continuous)
   double klow, khigh;      // kernel-space support: (low - step/2, high + step/2), log applied
 };

@@ -516,7 +516,8 @@ __global__ void k_tab_pad(double2* __restrict__ tabp, double* __restrict__ tabc,
 __global__ void k_build_mv(const double* __restrict__ X, int32_t pall, const int64_t* __restrict__ rows, int64_t n,
                            const ColMeta* __restrict__ cols, int32_t pc, int magic_clip, int32_t pb, int mode,
                            double* __restrict__ mu, double* __restrict__ sigma, double2* __restrict__ tabp,
-                           double* __restrict__ tabc, double2* __restrict__ colprm, double* __restrict__ cst_part) {
+                           double* __restrict__ tabc, double2* __restrict__ colprm, double* __restrict__ cst_part,
+                           int32_t* __restrict__ cls, int* __restrict__ offgrid) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -539,6 +540,14 @@ __global__ void k_build_mv(const double* __restrict__ X, int32_t pall, const int
       double m, s;
       if (k < n) {
         m = X[row * pall + cm.src];
+        if (cm.grid > 0 && cls != nullptr) {
+          // kernel class of a tabulated discrete column = grid index of the observation; the table is
+          // only valid if the observation sits on the grid exactly
+          const double g = rint(TPE_DIV(TPE_SUB(m, cm.low), cm.step));
+          const bool on = g >= 0.0 && g < (double)cm.grid && TPE_ADD(cm.low, TPE_MUL(g, cm.step)) == m;
+          cls[k * pc + j] = on ? (int32_t)g : 0;
+          if (!on) atomicOr(offgrid, 1);
+        }
         if (cm.log) m = log(m);
         s = fmin(fmax(TPE_MUL(factor, hi), lo), hi);
       } else {
@@ -778,37 +787,72 @@ __global__ void k_prep_points(const double* __restrict__ S, int64_t n, const Col
 // ================================================================================================
 // log-density grid
 // ================================================================================================
+// Cell-mass tables of the tabulated discrete columns (multivariate TPE: one sigma per column):
+//   T[r][g] = M((x_r -+ step/2 - mu_g) / sigma_g),  g = grid index of the kernel's observation (g = G: prior).
+// Rows: with fewer candidates than grid values (Ct < G) row r is candidate r (any x, on the grid or
+// not); otherwise row r is grid value low + r * step.  One candidate reads one contiguous row of
+// G + 1 doubles.  Same expression as the direct evaluation, so identical values.
+// grid = (chunks, pc); a block exits at once for a column that is not tabulated.
+__global__ void k_disc_tables(const ColMeta* __restrict__ cols, int32_t pc, const double* __restrict__ mu,
+                              const double* __restrict__ sigma, int64_t K, const double* __restrict__ S, int64_t Ct,
+                              double* __restrict__ dtab) {
+  const int j = blockIdx.y;
+  const ColMeta cm = cols[j];
+  if (cm.cls != COL_DISC || cm.grid <= 0) return;
+  const int G = cm.grid;
+  const bool by_cand = Ct < G;
+  const int64_t total = (by_cand ? Ct : (int64_t)G) * (G + 1);
+  const double sg_obs = sigma[j];  // kernel 0 (any observation kernel; unused when K == 1)
+  const double mu_prior = mu[(K - 1) * pc + j], sg_prior = sigma[(K - 1) * pc + j];
+  const double half = TPE_DIV(cm.step, 2.0);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / (G + 1);
+    const int g = (int)(t - r * (G + 1));
+    double m, s;
+    if (g < G) {
+      m = TPE_ADD(cm.low, TPE_MUL((double)g, cm.step));
+      if (cm.log) m = log(m);
+      s = sg_obs;
+    } else {
+      m = mu_prior;
+      s = sg_prior;
+    }
+    const double x = by_cand ? S[r * pc + j] : TPE_ADD(cm.low, TPE_MUL((double)r, cm.step));
+    double lo = TPE_SUB(x, half), hi = TPE_ADD(x, half);
+    if (cm.log) { lo = log(lo); hi = log(hi); }
+    dtab[cm.dtab_off + t] = log_gauss_mass(TPE_DIV(TPE_SUB(lo, m), s), TPE_DIV(TPE_SUB(hi, m), s));
+  }
+}
+
 // Exact, any-kind evaluation of one (candidate, kernel) cell sum -- follows the reference's
 // operation order (division by sigma, support test on normalised coordinates).
+__device__ __forceinline__ double cell_one_exact(const ColMeta& cm, double x, double m, double s, bool is_prior,
+                                                 const double* __restrict__ tab) {
+  if (cm.cls == COL_CAT) {
+    const int nch = cm.nch;
+    const int row = is_prior ? nch : (int)m;
+    const double* LW = tab + cm.tab_off + (int64_t)(nch + 1) * nch;
+    return LW[(int64_t)row * nch + (int)x];
+  }
+  if (cm.cls == COL_CONT) {
+    const double xv = cm.log ? log(x) : x;
+    const double z = TPE_DIV(TPE_SUB(xv, m), s);
+    const double a = TPE_DIV(TPE_SUB(cm.klow, m), s);
+    const double b = TPE_DIV(TPE_SUB(cm.khigh, m), s);
+    if (a == b) return NAN;
+    if (z < a || z > b) return -INFINITY;
+    return TPE_DIV(-TPE_MUL(z, z), 2.0);
+  }
+  const double h = TPE_DIV(cm.step, 2.0);
+  double lo = TPE_SUB(x, h), hi = TPE_ADD(x, h);
+  if (cm.log) { lo = log(lo); hi = log(hi); }
+  return log_gauss_mass(TPE_DIV(TPE_SUB(lo, m), s), TPE_DIV(TPE_SUB(hi, m), s));
+}
 __device__ __forceinline__ double cell_sum_exact(const double* __restrict__ xrow, const double* __restrict__ mu_k,
                                                  const double* __restrict__ sg_k, const ColMeta* __restrict__ cols,
                                                  int32_t pc, bool is_prior, const double* __restrict__ tab) {
   double acc = 0.0;
-  for (int j = 0; j < pc; ++j) {
-    const ColMeta cm = cols[j];
-    const double x = xrow[j];
-    if (cm.cls == COL_CAT) {
-      const int nch = cm.nch;
-      const int row = is_prior ? nch : (int)mu_k[j];
-      const double* LW = tab + cm.tab_off + (int64_t)(nch + 1) * nch;
-      acc += LW[(int64_t)row * nch + (int)x];
-    } else if (cm.cls == COL_CONT) {
-      const double m = mu_k[j], s = sg_k[j];
-      const double xv = cm.log ? log(x) : x;
-      const double z = TPE_DIV(TPE_SUB(xv, m), s);
-      const double a = TPE_DIV(TPE_SUB(cm.klow, m), s);
-      const double b = TPE_DIV(TPE_SUB(cm.khigh, m), s);
-      if (a == b) acc += NAN;
-      else if (z < a || z > b) acc += -INFINITY;
-      else acc += TPE_DIV(-TPE_MUL(z, z), 2.0);
-    } else {
-      const double m = mu_k[j], s = sg_k[j];
-      const double h = TPE_DIV(cm.step, 2.0);
-      double lo = TPE_SUB(x, h), hi = TPE_ADD(x, h);
-      if (cm.log) { lo = log(lo); hi = log(hi); }
-      acc += log_gauss_mass(TPE_DIV(TPE_SUB(lo, m), s), TPE_DIV(TPE_SUB(hi, m), s));
-    }
-  }
+  for (int j = 0; j < pc; ++j) acc += cell_one_exact(cols[j], xrow[j], mu_k[j], sg_k[j], is_prior, tab);
   return acc;
 }
 
@@ -838,21 +882,86 @@ __global__ void k_logpdf_generic(const double* __restrict__ S, int64_t Ct, const
 // whole (candidate, kernel) cell sums with the reference's operation order, block-level log-sum-exp.
 // Used for spaces with discrete / categorical columns (every thread of a warp walks the same column
 // kinds, so the special-function branches are the only divergence).
+// Pair-parallel evaluation for spaces the fast kernel does not take (discrete / categorical columns,
+// wide spaces): block = one candidate x one chunk of kernels, thread = one (candidate, kernel) cell sum.
+// The candidate's columns are decoded once per block into shared descriptors:
+//   kind 0  continuous, candidate inside [low, high]: -z^2/2 (the support test cannot fire)
+//   kind 1  tabulated discrete: one load from the candidate's row of the cell-mass table
+//   kind 3  categorical: one load from the log-weight table (row = the kernel's observed choice)
+//   kind 2  anything else: the direct formula
+struct PairCol {
+  int kind, stride, gprior, pad;
+  double xv;
+  const double* base;
+};
 __global__ void __launch_bounds__(256)
 k_logpdf_pairs(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols, int32_t pc,
                const double* __restrict__ mu, const double* __restrict__ sigma, const double* __restrict__ cst,
-               int64_t K, int kpt, const double* __restrict__ tab, double2* __restrict__ part, int64_t ct_stride) {
-  extern __shared__ double s_x[];  // pc doubles + 16 reduction slots
+               int64_t K, int kpt, const double* __restrict__ tab, const int32_t* __restrict__ cls,
+               const double* __restrict__ dtab, const int* __restrict__ offgrid, const uint8_t* __restrict__ oob,
+               double2* __restrict__ part, int64_t ct_stride) {
+  extern __shared__ double s_dyn[];  // pc PairCol descriptors
   __shared__ double s_m[8], s_s[8];
+  PairCol* s_col = reinterpret_cast<PairCol*>(s_dyn);
   const int64_t ct = blockIdx.x;
   const int64_t k0 = (int64_t)blockIdx.y * 256 * kpt;
-  for (int j = threadIdx.x; j < pc; j += 256) s_x[j] = S[ct * pc + j];
+  const bool tables_ok = dtab != nullptr && offgrid != nullptr && *offgrid == 0;
+  const bool in_support = oob != nullptr && oob[ct] == 0;
+  for (int j = threadIdx.x; j < pc; j += 256) {
+    const double x = S[ct * pc + j];
+    const ColMeta cm = cols[j];
+    PairCol pcj;
+    pcj.kind = 2; pcj.stride = 0; pcj.gprior = 0; pcj.pad = 0; pcj.xv = x; pcj.base = nullptr;
+    if (cm.cls == COL_CAT) {
+      pcj.kind = 3;
+      pcj.stride = cm.nch;
+      pcj.gprior = cm.nch;
+      pcj.base = tab + cm.tab_off + (int64_t)(cm.nch + 1) * cm.nch + (int)x;
+    } else if (cm.cls == COL_CONT) {
+      if (in_support && cm.klow < cm.khigh) {
+        pcj.kind = 0;
+        pcj.xv = cm.log ? log(x) : x;
+      }
+    } else if (cm.grid > 0 && tables_ok) {
+      int64_t row = -1;
+      if (Ct < cm.grid) {
+        row = ct;  // candidate-indexed table
+      } else {
+        const double h = rint(TPE_DIV(TPE_SUB(x, cm.low), cm.step));
+        if (h >= 0.0 && h < (double)cm.grid && TPE_ADD(cm.low, TPE_MUL(h, cm.step)) == x) row = (int64_t)h;
+      }
+      if (row >= 0) {
+        pcj.kind = 1;
+        pcj.stride = 1;
+        pcj.gprior = cm.grid;
+        pcj.base = dtab + cm.dtab_off + row * (cm.grid + 1);
+      }
+    }
+    s_col[j] = pcj;
+  }
   __syncthreads();
   double m = -INFINITY, s = 0.0;
   for (int q = 0; q < kpt; ++q) {
     const int64_t k = k0 + (int64_t)q * 256 + threadIdx.x;
     if (k < K) {
-      const double L = cst[k] + cell_sum_exact(s_x, mu + k * pc, sigma + k * pc, cols, pc, k == K - 1, tab);
+      const bool is_prior = k == K - 1;
+      const double* mu_k = mu + k * pc;
+      const double* sg_k = sigma + k * pc;
+      double acc = 0.0;
+      for (int j = 0; j < pc; ++j) {
+        const PairCol c = s_col[j];
+        if (c.kind == 0) {
+          const double z = TPE_DIV(TPE_SUB(c.xv, mu_k[j]), sg_k[j]);
+          acc += TPE_DIV(-TPE_MUL(z, z), 2.0);
+        } else if (c.kind == 1) {
+          acc += c.base[is_prior ? c.gprior : cls[k * pc + j]];
+        } else if (c.kind == 3) {
+          acc += c.base[(int64_t)(is_prior ? c.gprior : (int)mu_k[j]) * c.stride];
+        } else {
+          acc += cell_one_exact(cols[j], c.xv, mu_k[j], sg_k[j], is_prior, tab);
+        }
+      }
+      const double L = cst[k] + acc;
       lse_push(L, m, s);
     }
   }

@@ -326,6 +326,44 @@ def test_config3_shape_mixed_64_params_against_oracle(eng):
             assert x[0, j] == s.x[j]
 
 
+@pytest.mark.parametrize("C,offgrid", [(8, False), (64, False), (64, True)])
+def test_tabulated_discrete_columns(eng, C, offgrid):
+    """Discrete columns evaluated through the cell-mass tables (candidate-indexed when C < grid size,
+    grid-indexed otherwise) and through the direct formula when an observation is off the grid."""
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(5)
+    n = 700
+    specs = [ParamSpec(kind=0, low=-1.0, high=2.0, step=0.25), ParamSpec(kind=1, low=2, high=40, step=2),
+             ParamSpec(kind=1, low=1, high=300, step=1, log=True), ParamSpec(kind=0, low=0.0, high=1.0)]
+    params = [orc.Param("float", -1.0, 2.0, 0.25), orc.Param("int", 2.0, 40.0, 2.0),
+              orc.Param("int", 1.0, 300.0, 1.0, True), orc.Param("float", 0.0, 1.0)]
+    X = np.stack([rs.randint(0, 13, n) * 0.25 - 1.0, rs.randint(1, 21, n) * 2.0,
+                  np.round(np.exp(rs.uniform(0, np.log(300), n))), rs.uniform(0, 1, n)], 1)
+    if offgrid:
+        X[17, 0] = 0.3
+        X[400, 1] = 7.0
+    cat = np.zeros(n, np.int8)
+    key = np.stack([rs.normal(size=n), np.zeros(n)], 1)
+    eng.set_space(specs)
+    eng.set_history(X, cat, key)
+    u = draw_uniforms(np.random.RandomState(3), C, 0, 4)
+    x, acq, best = eng.suggest([0, 1, 2, 3], u, 1, n_below=40, n_candidates=C, multivariate=True)
+    smp, ll, lg = eng.get_candidates()
+    s = orc.suggest(X, cat, key, params, [0, 1, 2, 3], orc.Config(multivariate=True), 40, C,
+                    np.random.RandomState(3))
+    for j in range(3):
+        assert np.array_equal(smp[:, j], s.samples[:, j]), j
+    close(smp[:, 3], s.samples[:, 3], 1e-12, 1e-12)
+    close(ll, s.logl, 0, 1e-9)
+    close(lg, s.logg, 0, 1e-9)
+    assert int(best[0]) == s.best
+    # user points off the grid: direct formula (grid-indexed tables) or their own row (candidate-indexed)
+    pts = s.samples.copy()
+    pts[::3, 0] += 0.01
+    close(eng.logpdf(1, pts), orc.mixture_log_pdf(s.mix_above, pts), 0, 1e-9)
+    close(eng.logpdf(0, pts), orc.mixture_log_pdf(s.mix_below, pts), 0, 1e-9)
+
+
 def test_categorical_distance_func_tables(eng):
     """categorical_distance_func (parzen_estimator.py:152-160): rows exp(-(d / max d)^2 * coef)."""
     from optuna_b200.engine import ParamSpec
