@@ -67,10 +67,12 @@ struct Estimator {
   DevBuf rows, pos, wstage, wpart, w, logw, cdf, mu, sigma, cst_part, cst, tabp, tabc, colprm, tab, part, fix;
   DevBuf tab32, tab64p, d32;   // fp32-screening copies (tpe_screen.cuh)
   DevBuf cls, dtab, offgrid;   // tabulated discrete columns (multivariate)
+  DevBuf tabm, hb, ckk;        // tensor-core kernel: fragment-major table, |mu''|^2 / 2, cst - |mu''|^2 / 2
+  bool mma = false;            // tables above are valid for this build
   bool screen_ready = false;
   int nsplit = 0;
   void release() {
-    for (DevBuf* b : {&cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
+    for (DevBuf* b : {&tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
                       &part, &fix})
       b->release();
   }
@@ -121,7 +123,7 @@ struct tpe_ctx {
 
   // candidates
   int64_t n_asks = 0, Ct = 0, ct_stride = 0;
-  DevBuf U, S, xT, oob, logl, logg, out_x, out_acq, out_best, x64s, x32s, e32s, gmax;
+  DevBuf U, S, xT, oob, logl, logg, out_x, out_acq, out_best, x64s, x32s, e32s, gmax, lse_gmax;
   bool screen_attr_set = false;
   float ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   int32_t launches = 0;
@@ -165,7 +167,7 @@ struct FastCfg {
   int pb, cands_per_cta, nt, tk, st, minb;
   size_t smem;
   void (*launch)(dim3, size_t, cudaStream_t, const void*, const double*, int64_t, const double2*, const double*,
-                 int64_t, int64_t, double, double2*);
+                 int64_t, int64_t, double, double2*, unsigned long long*);
   cudaError_t (*prepare)();
 };
 
@@ -174,7 +176,7 @@ struct FastInst {
   static constexpr size_t smem = (size_t)ST * TK * PB * (PAIR ? 16 : 8) + (size_t)ST * TK * 8 + (size_t)ST * 8;
   static void launch(dim3 grid, size_t sm, cudaStream_t st, const void* tab, const double* cst, int64_t Kf,
                      const double2* colprm, const double* xT, int64_t ct_stride, int64_t kps, double skip,
-                     double2* part) {
+                     double2* part, unsigned long long*) {
     k_logpdf_fast<PB, PS, RC, NT, TK, ST, PAIR, MINB>
         <<<grid, NT, sm, st>>>(tab, cst, Kf, colprm, xT, ct_stride, kps, skip, part);
   }
@@ -184,6 +186,49 @@ struct FastInst {
   }
   static FastCfg cfg() { return FastCfg{PB, (NT / 32) * (32 / PS) * RC, NT, TK, ST, MINB, smem, &launch, &prepare}; }
 };
+
+// Tensor-core (DMMA) instances of the CONST kernel: same launch signature (tab = fragment-major table,
+// cst = ckk, Kf = kernels rounded up to 8).
+template <int PB, int M, int NT, int TK, int ST>
+struct MmaInst {
+  static constexpr size_t smem = (size_t)ST * TK * PB * 8 + (size_t)ST * TK * 8 + (size_t)ST * 8;
+  static void launch(dim3 grid, size_t sm, cudaStream_t st, const void* tab, const double* cst, int64_t Kf,
+                     const double2* colprm, const double* xT, int64_t ct_stride, int64_t kps, double skip,
+                     double2* part, unsigned long long* gmax) {
+    k_logpdf_mma<PB, M, NT, TK, ST><<<grid, NT, sm, st>>>(static_cast<const double*>(tab), cst, Kf, colprm, xT,
+                                                         ct_stride, kps, skip, part, gmax);
+  }
+  static cudaError_t prepare() {
+    return cudaFuncSetAttribute(k_logpdf_mma<PB, M, NT, TK, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem);
+  }
+  static FastCfg cfg(int minb) { return FastCfg{PB, (NT / 32) * 8 * M, NT, TK, ST, minb, smem, &launch, &prepare}; }
+};
+//                                   PB M  NT   TK ST
+const FastCfg kMmaBig[] = {
+    MmaInst<8, 2, 256, 512, 3>::cfg(2), MmaInst<16, 2, 256, 256, 3>::cfg(2), MmaInst<32, 2, 256, 128, 3>::cfg(2),
+    MmaInst<64, 2, 256, 64, 3>::cfg(1),
+};
+const FastCfg kMmaSmall[] = {
+    MmaInst<8, 2, 64, 512, 3>::cfg(4), MmaInst<16, 2, 64, 256, 3>::cfg(4), MmaInst<32, 2, 64, 128, 3>::cfg(4),
+    MmaInst<64, 2, 64, 64, 3>::cfg(4),
+};
+const FastCfg kMma32Variants[] = {
+    MmaInst<32, 2, 256, 128, 3>::cfg(2), MmaInst<32, 1, 1024, 128, 2>::cfg(1), MmaInst<32, 1, 256, 128, 3>::cfg(2),
+    MmaInst<32, 2, 128, 128, 3>::cfg(4), MmaInst<32, 1, 512, 128, 3>::cfg(2), MmaInst<32, 2, 512, 128, 2>::cfg(1),
+    MmaInst<32, 2, 256, 64, 4>::cfg(2),  MmaInst<32, 1, 512, 128, 2>::cfg(2),
+};
+const FastCfg* pick_mma(int pb, int64_t Ct) {
+  const bool small = Ct <= 64;
+  if (pb == 32 && !small) {
+    const char* v = getenv("TPE_MMA_VARIANT");
+    if (v && v[0] >= '0' && v[0] <= '7') return &kMma32Variants[v[0] - '0'];
+  }
+  const FastCfg* tabs = small ? kMmaSmall : kMmaBig;
+  for (int i = 0; i < 4; ++i)
+    if (tabs[i].pb == pb) return &tabs[i];
+  return nullptr;
+}
 
 // "big": many candidates (c-tiles of `cands_per_cta`, kernels split over blockIdx.y);
 // "small": a single ask with few candidates -- one warp per CTA, the grid splits the kernel axis.
@@ -439,6 +484,11 @@ void scan_missing(tpe_ctx* ctx, const double* X, int64_t n) {
       if (X[i * P + j] != X[i * P + j]) ctx->col_missing[j] = 1;
 }
 
+bool mma_enabled() {
+  static const bool on = [] { const char* v = getenv("TPE_MMA"); return !(v && v[0] == '0'); }();
+  return on;
+}
+
 int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
   Estimator& e = ctx->est[which];
   e.screen_ready = false;
@@ -447,7 +497,7 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
   cudaStream_t st = ctx->stream;
   const int cap = ctx->sm_count * 8;
   e.K = K;
-  const int64_t k_alloc = round_up<int64_t>(K + 2, 2);
+  const int64_t k_alloc = round_up<int64_t>(K + 8, 8);
   CU(e.mu.ensure((size_t)K * pc * 8));
   CU(e.sigma.ensure((size_t)K * pc * 8));
   CU(e.cst_part.ensure((size_t)K * 8));
@@ -458,6 +508,13 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
   if (ctx->fast_mode == 1) CU(e.tabp.ensure((size_t)K * ctx->pb * 16 + 16));
   if (ctx->fast_mode == 2) CU(e.tabc.ensure((size_t)K * ctx->pb * 8 + 16));
   if (ctx->fast) CU(e.colprm.ensure((size_t)ctx->pb * 16));
+  e.mma = ctx->fast_mode == 2 && ctx->pb >= 8 && mma_enabled();
+  if (e.mma) {
+    CU(e.tabm.ensure((size_t)k_alloc * ctx->pb * 8));
+    CU(e.hb.ensure((size_t)k_alloc * 8));
+    CU(e.ckk.ensure((size_t)k_alloc * 8));
+    CU(cudaMemsetAsync(e.tabm.p, 0, (size_t)k_alloc * ctx->pb * 8, st));  // padded slots, last group, prior row
+  }
   if (ctx->tab_doubles) CU(e.tab.ensure((size_t)ctx->tab_doubles * 8));
   if (ctx->dtab_doubles) {
     CU(e.dtab.ensure((size_t)ctx->dtab_doubles * 8));
@@ -477,7 +534,8 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
         ctx->X.as<double>(), (int32_t)ctx->space.size(), e.rows.as<int64_t>(), n, ctx->cols.as<ColMeta>(), pc,
         ctx->cfg.magic_clip, ctx->pb, ctx->fast_mode, e.mu.as<double>(), e.sigma.as<double>(), e.tabp.as<double2>(),
         e.tabc.as<double>(), e.colprm.as<double2>(), e.cst_part.as<double>(),
-        ctx->dtab_doubles ? e.cls.as<int32_t>() : nullptr, ctx->dtab_doubles ? e.offgrid.as<int>() : nullptr);
+        ctx->dtab_doubles ? e.cls.as<int32_t>() : nullptr, ctx->dtab_doubles ? e.offgrid.as<int>() : nullptr,
+        e.mma ? e.tabm.as<double>() : nullptr, e.mma ? e.hb.as<double>() : nullptr);
     ctx->launch_counter++;
   } else {
     k_mu<<<grid_for(K * pc, 256, cap), 256, 0, st>>>(ctx->X.as<double>(), (int32_t)ctx->space.size(),
@@ -553,7 +611,8 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
     k_wraw<<<nparts, 256, 0, st>>>(w_dev, w_pos, n, ctx->cfg.prior_weight, e.w.as<double>(), e.wpart.as<double>());
     k_wfinal<<<grid_for(k_alloc, 256, ctx->sm_count * 4), 256, 0, st>>>(
         e.wpart.as<double>(), nparts, n, e.w.as<double>(), e.logw.as<double>(), e.cst_part.as<double>(),
-        e.cst.as<double>(), which == 0 ? e.cdf.as<double>() : nullptr, k_alloc);
+        e.cst.as<double>(), which == 0 ? e.cdf.as<double>() : nullptr, k_alloc,
+        e.mma ? e.hb.as<double>() : nullptr, e.mma ? e.ckk.as<double>() : nullptr);
     k_wnorm<<<grid_for(K, 256, ctx->sm_count * 4), 256, 0, st>>>(e.wpart.as<double>(), nparts, K, e.w.as<double>());
     ctx->launch_counter += 3;
   }
@@ -573,9 +632,20 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
   cudaStream_t st = ctx->stream;
   const int64_t K = e.K;
   if (ctx->fast) {
-    const FastCfg* fc = pick_fast(ctx->fast_mode, ctx->pb, Ct);
     const bool cst_mode = ctx->fast_mode == 2;
-    const int64_t Kf = cst_mode ? K - 1 : K;  // CONST tables exclude the prior kernel (its sigma differs)
+    // tensor-core kernel unless the expanded square would lose more than 5e-13 (see k_logpdf_mma)
+    bool use_mma = false;
+    if (e.mma && K > 1) {
+      const double nobs = (double)std::max<int64_t>(e.n, 1);
+      double fac = 0.2 * pow(nobs, -1.0 / (ctx->pc + 4));
+      if (ctx->cfg.magic_clip) fac = std::max(fac, 1.0 / std::min(100.0, 1.0 + (double)K));
+      fac = std::min(std::max(fac, 1e-9), 1.0);
+      const double rho = 0.5 / fac;
+      use_mma = ctx->pb * rho * rho * 2.3e-16 <= 5e-13 && pick_mma(ctx->pb, Ct) != nullptr;
+    }
+    const FastCfg* fc = use_mma ? pick_mma(ctx->pb, Ct) : pick_fast(ctx->fast_mode, ctx->pb, Ct);
+    // CONST tables exclude the prior kernel (its sigma differs); the mma table is padded to groups of 8
+    const int64_t Kf = use_mma ? round_up<int64_t>(K - 1, 8) : (cst_mode ? K - 1 : K);
     const int tc = fc->cands_per_cta;
     const int64_t ctiles = (Ct + tc - 1) / tc;
     // k-splits: two full waves of resident CTAs for the big configurations
@@ -592,7 +662,7 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     // Experimental and OFF by default: correct (same parity tests) but 2.62 ms vs 2.40 ms for the exact
     // kernel at config 2 -- see profiles/r1_variants.md.  TPE_SCREEN=1 enables it.
     static const bool screen_on = [] { const char* v = getenv("TPE_SCREEN"); return v && v[0] == '1'; }();
-    const bool use_screen = cst_mode && ctx->pb == kScrP && Ct > 128 && Kf > 0 && screen_on;
+    const bool use_screen = cst_mode && !use_mma && ctx->pb == kScrP && Ct > 128 && Kf > 0 && screen_on;
     if (use_screen) {
       const int64_t sctiles = (Ct + kScrCands - 1) / kScrCands;
       const int64_t sktiles = (Kf + kScrTK - 1) / kScrTK;
@@ -645,13 +715,21 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
         CU(fc->prepare());
         ctx->prepared_cfgs.insert(fc);
       }
+      if (use_mma) {
+        CU(ctx->lse_gmax.ensure((size_t)ctx->ct_stride * 8));
+        CU(cudaMemsetAsync(ctx->lse_gmax.p, 0, (size_t)ctx->ct_stride * 8, st));
+      }
       fc->launch(dim3((unsigned)ctiles, (unsigned)nsplit), fc->smem, st,
-                 cst_mode ? (const void*)e.tabc.p : (const void*)e.tabp.p, e.cst.as<double>(), Kf,
+                 use_mma ? (const void*)e.tabm.p : (cst_mode ? (const void*)e.tabc.p : (const void*)e.tabp.p),
+                 use_mma ? e.ckk.as<double>() : e.cst.as<double>(), Kf,
                  e.colprm.as<double2>(), ctx->xT.as<double>(), ctx->ct_stride, kps,
-                 std::min(46.0, log((double)std::max<int64_t>(K, 1)) + 30.0), e.part.as<double2>());
+                 std::min(46.0, log((double)std::max<int64_t>(K, 1)) + 30.0), e.part.as<double2>(),
+                 use_mma ? ctx->lse_gmax.as<unsigned long long>() : nullptr);
       ctx->launch_counter++;
     }
-    if (!use_screen)
+    if (use_mma && !use_screen)
+      ctx->last_kernel = (fc->nt >= 256) ? "k_logpdf_mma<big>" : "k_logpdf_mma<small>";
+    else if (!use_screen)
       ctx->last_kernel = cst_mode ? ((fc->nt >= 256) ? "k_logpdf_fast<const,big>" : "k_logpdf_fast<const,small>")
                                   : ((fc->nt >= 256) ? "k_logpdf_fast<pair,big>" : "k_logpdf_fast<pair,small>");
     if (after_main) CU(cudaEventRecord(after_main, st));
@@ -752,7 +830,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
                     &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
-                    &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
+                    &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
   ctx->est[1].release();

@@ -76,6 +76,13 @@ __device__ __forceinline__ uint64_t order_bits(double v) {
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
+// inverse of order_bits; the all-zero pattern (a freshly cleared slot) reads as -inf
+__device__ __forceinline__ double from_order_bits(uint64_t b) {
+  if (b == 0) return -INFINITY;
+  const uint64_t u = (b >> 63) ? (b & 0x7fffffffffffffffull) : ~b;
+  return __longlong_as_double(static_cast<long long>(u));
+}
+
 // ---- block-wide (1024 threads) ordered rank of flagged threads --------------------------------------
 // Returns {exclusive rank of this thread among flagged threads, number flagged in the block}.
 // s_warp: 32 ints of shared memory.  Two __syncthreads per call; blockDim.x must be 1024.

@@ -511,13 +511,24 @@ __global__ void k_tab_pad(double2* __restrict__ tabp, double* __restrict__ tabc,
     for (int sl = ncont + threadIdx.x; sl < pb; sl += blockDim.x) colprm[sl] = make_double2(0.0, 0.0);
 }
 
+// Fragment-major layout of the CONST table for the tensor-core kernel (k_logpdf_mma): kernels in
+// groups of 8, inside a group the order in which the 32 lanes of a warp read their B fragments of
+// mma.m8n8k4 (lane = 4 * (k % 8) + slot % 4 holds B[row = slot % 4][col = k % 8] of k-step slot / 4),
+// two k-steps interleaved so that one LDS.128 per lane fetches both.
+__host__ __device__ __forceinline__ int64_t mma_tab_index(int64_t k, int slot, int pb) {
+  const int i = slot >> 2;
+  const int lane = (int)(k & 7) * 4 + (slot & 3);
+  return (k >> 3) * (8 * (int64_t)pb) + ((int64_t)(i >> 1) * 32 + lane) * 2 + (i & 1);
+}
+
 // Fused multivariate build: k_mu + k_sigma_mv + k_const in one pass (one warp per kernel, lanes over
 // columns).  mode / tables as in k_const.
 __global__ void k_build_mv(const double* __restrict__ X, int32_t pall, const int64_t* __restrict__ rows, int64_t n,
                            const ColMeta* __restrict__ cols, int32_t pc, int magic_clip, int32_t pb, int mode,
                            double* __restrict__ mu, double* __restrict__ sigma, double2* __restrict__ tabp,
                            double* __restrict__ tabc, double2* __restrict__ colprm, double* __restrict__ cst_part,
-                           int32_t* __restrict__ cls, int* __restrict__ offgrid) {
+                           int32_t* __restrict__ cls, int* __restrict__ offgrid, double* __restrict__ tabm,
+                           double* __restrict__ hb) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -526,7 +537,7 @@ __global__ void k_build_mv(const double* __restrict__ X, int32_t pall, const int
   const double factor = TPE_MUL(0.2, pow((double)(n > 1 ? n : 1), e));
   for (int64_t k = warp; k < K; k += nwarps) {
     const int64_t row = (k < n) ? rows[k] : 0;
-    double acc = 0.0;
+    double acc = 0.0, sq = 0.0;
     for (int j = lane; j < pc; j += 32) {
       const ColMeta cm = cols[j];
       if (cm.cls == COL_CAT) {
@@ -567,7 +578,14 @@ __global__ void k_build_mv(const double* __restrict__ X, int32_t pall, const int
             tabp[k * pb + cm.slot] = make_double2(TPE_MUL(TPE_SUB(m, ctr), inv), inv);
             if (k == 0) colprm[cm.slot] = make_double2(ctr, 1.0);
           } else {
-            if (k < K - 1) tabc[k * pb + cm.slot] = TPE_MUL(TPE_SUB(m, ctr), inv);
+            const double t = TPE_MUL(TPE_SUB(m, ctr), inv);
+            if (k < K - 1) {
+              tabc[k * pb + cm.slot] = t;
+              if (tabm != nullptr) {
+                tabm[mma_tab_index(k, cm.slot, pb)] = t;
+                sq = fma(t, t, sq);
+              }
+            }
             if (k == 0) colprm[cm.slot] = make_double2(ctr, inv);
           }
         }
@@ -577,6 +595,10 @@ __global__ void k_build_mv(const double* __restrict__ X, int32_t pall, const int
     }
     acc = warp_sum(acc);
     if (lane == 0) cst_part[k] = -acc;
+    if (hb != nullptr) {
+      sq = warp_sum(sq);
+      if (lane == 0) hb[k] = 0.5 * sq;
+    }
   }
 }
 
@@ -620,7 +642,8 @@ k_wraw(const double* __restrict__ w_in, const int64_t* __restrict__ pos, int64_t
 }
 __global__ void __launch_bounds__(256)
 k_wfinal(const double* __restrict__ part, int nparts, int64_t n, double* __restrict__ w, double* __restrict__ logw,
-         const double* __restrict__ cst_part, double* __restrict__ cst, double* __restrict__ cdf, int64_t k_alloc) {
+         const double* __restrict__ cst_part, double* __restrict__ cst, double* __restrict__ cdf, int64_t k_alloc,
+         const double* __restrict__ hb, double* __restrict__ ckk) {
   __shared__ double s_total;
   const int64_t K = n + 1;
   if (threadIdx.x == 0) {
@@ -649,9 +672,13 @@ k_wfinal(const double* __restrict__ part, int nparts, int64_t n, double* __restr
       const double v = TPE_DIV(w[k], total);
       const double lw = log(v);
       logw[k] = lw;
-      cst[k] = cst_part[k] + lw;
+      const double c = cst_part[k] + lw;
+      cst[k] = c;
+      // tensor-core kernel: constant of the expanded square, cst - |mu''|^2 / 2 (prior kernel excluded)
+      if (ckk != nullptr) ckk[k] = (k < K - 1) ? c - hb[k] : -INFINITY;
     } else {
       cst[k] = -INFINITY;  // padding read by the bulk copies
+      if (ckk != nullptr) ckk[k] = -INFINITY;
     }
   }
 }
@@ -1002,9 +1029,21 @@ k_logpdf_pairs(const double* __restrict__ S, int64_t Ct, const ColMeta* __restri
 //   part [gridDim.y][ct_stride] (running max, running sum)
 struct LseAcc {
   double m, s, thr, b0, b1, b2, b3;
+  double gm;  // best running max any CTA has published for this candidate (a lower bound of the true max)
   int cnt;
   __device__ __forceinline__ void init() {
-    m = -INFINITY; s = 0.0; thr = -INFINITY; b0 = b1 = b2 = b3 = 0.0; cnt = 0;
+    m = -INFINITY; s = 0.0; thr = -INFINITY; b0 = b1 = b2 = b3 = 0.0; cnt = 0; gm = -INFINITY;
+  }
+  // Truncation against the max over ALL kernels seen so far by any CTA / lane working on this
+  // candidate, not just this lane's slice: the k-splits and the lanes of a candidate publish their
+  // running max in `slot` (ordered-integer atomicMax) and read the others'.  Any published value is
+  // some kernel's L, hence <= the true max: thresholds derived from it only drop terms that the
+  // final log-sum-exp could drop as well.
+  __device__ __forceinline__ void sync_global(unsigned long long* slot) {
+    if (m > gm) atomicMax(slot, static_cast<unsigned long long>(order_bits(m)));
+    const double seen = from_order_bits(*reinterpret_cast<volatile unsigned long long*>(slot));
+    gm = fmax(gm, seen);
+    thr = fmax(m, gm) - skip();
   }
   static __device__ __forceinline__ double& skip() {
     static __shared__ double s_skip;  // per-launch truncation distance (see k_logpdf_fast)
@@ -1027,7 +1066,7 @@ struct LseAcc {
     fold(b2, cnt > 2);
     fold(b3, cnt > 3);
     cnt = 0;
-    thr = m - skip();
+    thr = fmax(m, gm) - skip();
   }
   // Park L if it is within kLseSkip of the (possibly stale, i.e. lower) running max; when any lane's
   // buffer is full every lane folds its parked terms -- one converged pass instead of 32 diverged ones.
@@ -1199,6 +1238,152 @@ k_logpdf_fast(const void* __restrict__ tab_v, const double* __restrict__ cst, in
   for (int r = 0; r < RL; ++r) {
     const int64_t ct = wbase + (int64_t)(h * RL + r) * GW + g;
     part[blockIdx.y * ct_stride + ct] = make_double2(acc[r].m, acc[r].s);
+  }
+}
+
+// ================================================================================================
+// Tensor-core variant of the CONST kernel (multivariate TPE, continuous columns).
+//
+// With one sigma per column the cell sum is a squared distance in scaled coordinates
+//   a_cp = (x_cp - ctr_p) / sigma_p,  b_kp = (mu_kp - ctr_p) / sigma_p,
+//   L[c,k] = cst_k - |a_c - b_k|^2 / 2 = (cst_k - |b_k|^2 / 2) + a_c . b_k - |a_c|^2 / 2,
+// i.e. ONE fma per cell instead of two, and the a . b part is a [C x P] x [P x K] fp64 GEMM: it runs
+// on the fp64 tensor-core path (mma.sync m8n8k4, SASS DMMA.8x8x4 -- same 37 TFLOP/s pipe as DFMA on
+// B200, but 256 fma per warp instruction with the operands shared in registers, so neither the
+// issue slots nor the shared-memory pipe limit it).  The accumulator fragment is initialised with
+// cst_k - |b_k|^2 / 2 (host side of the build), so L - ha_c falls out of the mma chain directly and
+// -|a_c|^2 / 2 is added once per candidate after the log-sum-exp (shift invariance).
+// Rounding: |a|, |b| <= rho = range / (2 sigma); the expanded form loses ~P * rho^2 * 2^-52 absolute
+// (8e-14 at config 2); the host falls back to k_logpdf_fast when that bound exceeds 5e-13.
+//
+//   rows of A = candidates (8 per mma, M groups per warp), columns of B = kernels (8 per mma);
+//   lane (g = lane / 4, q = lane % 4) holds C[candidate g][kernels 2q, 2q + 1]: it owns one
+//   log-sum-exp state per candidate group and the 4 lanes of a candidate are merged at the end.
+//   tabm: fragment-major table (mma_tab_index), ckk: per-kernel constants (-inf padded to 8).
+// ================================================================================================
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+template <int PB, int M, int NT, int TK, int ST>
+__global__ void __launch_bounds__(NT)
+k_logpdf_mma(const double* __restrict__ tabm, const double* __restrict__ ckk, int64_t Kf8,
+             const double2* __restrict__ colprm, const double* __restrict__ xT, int64_t ct_stride, int64_t kps,
+             double lse_skip, double2* __restrict__ part, unsigned long long* __restrict__ gmax) {
+  static_assert(PB % 8 == 0 && TK % 8 == 0, "bad tiling");
+  constexpr int NI = PB / 4;        // k-steps of the mma chain
+  constexpr int CW = 8 * M;         // candidates per warp
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* tiles = reinterpret_cast<double*>(smem_raw);                             // ST * TK * PB
+  double* csts = tiles + (size_t)ST * TK * PB;                                     // ST * TK
+  uint64_t* full = reinterpret_cast<uint64_t*>(csts + (size_t)ST * TK);            // ST
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int64_t k0 = blockIdx.y * kps;
+  const int64_t k1 = (k0 + kps < Kf8) ? k0 + kps : Kf8;
+  const int ntiles = (k1 > k0) ? (int)((k1 - k0 + TK - 1) / TK) : 0;
+  const int64_t wbase = (int64_t)blockIdx.x * ((NT / 32) * CW) + (int64_t)(tid >> 5) * CW;
+
+  if (tid == 0) {
+    for (int s = 0; s < ST; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+    LseAcc::skip() = lse_skip;
+  }
+  __syncthreads();
+  auto issue = [&](int t) {
+    const int st = t % ST;
+    const int64_t ks = k0 + (int64_t)t * TK;
+    const int tk = (int)((k1 - ks < TK) ? (k1 - ks) : TK);  // multiple of 8
+    const uint32_t b_tile = (uint32_t)((size_t)tk * PB * 8);
+    const uint32_t b_cst = (uint32_t)(tk * 8);
+    fence_proxy_async();
+    mbar_expect_tx(&full[st], b_tile + b_cst);
+    bulk_g2s(tiles + (size_t)st * TK * PB, tabm + ks * PB, b_tile, &full[st]);
+    bulk_g2s(csts + (size_t)st * TK, ckk + ks, b_cst, &full[st]);
+  };
+  if (tid == 0) {
+    for (int t = 0; t < ST - 1 && t < ntiles; ++t) issue(t);
+  }
+
+  // A fragments: a[m][i] = A[row g][col q] of k-step i = scaled coordinate 4 i + q of candidate 8 m + g
+  double a[M][NI];
+  double ha[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) ha[m] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int slot = 4 * i + q;
+    const double2 cp = colprm[slot];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const int64_t ct = wbase + 8 * m + g;
+      const double v = (xT[(int64_t)slot * ct_stride + ct] - cp.x) * cp.y;
+      a[m][i] = v;
+      ha[m] = fma(v, v, ha[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    ha[m] += __shfl_xor_sync(0xffffffffu, ha[m], 1);
+    ha[m] += __shfl_xor_sync(0xffffffffu, ha[m], 2);
+    ha[m] *= -0.5;
+  }
+  LseAcc acc[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m].init();
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int st = t % ST;
+    if (tid == 0 && t + ST - 1 < ntiles) issue(t + ST - 1);
+    mbar_wait(&full[st], (uint32_t)((t / ST) & 1));
+    const int64_t ks = k0 + (int64_t)t * TK;
+    const int tk = (int)((k1 - ks < TK) ? (k1 - ks) : TK);
+    const double* tile = tiles + (size_t)st * TK * PB;
+    const double* ctile = csts + (size_t)st * TK;
+    for (int kg = 0; kg < tk / 8; ++kg) {
+      if (kg == 0 || t == 0) {  // every tile, and every group of the CTA's first tile (cold start)
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[m].sync_global(gmax + wbase + 8 * m + g);
+      }
+      const double2* fb = reinterpret_cast<const double2*>(tile + (size_t)kg * 8 * PB) + lane;
+      double b[NI];
+#pragma unroll
+      for (int i2 = 0; i2 < NI / 2; ++i2) {
+        const double2 v = fb[i2 * 32];
+        b[2 * i2] = v.x;
+        b[2 * i2 + 1] = v.y;
+      }
+      const double2 cc = reinterpret_cast<const double2*>(ctile + kg * 8)[q];
+      double d0[M], d1[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        d0[m] = cc.x;
+        d1[m] = cc.y;
+      }
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+#pragma unroll
+        for (int m = 0; m < M; ++m) dmma_8x8x4(d0[m], d1[m], a[m][i], b[i]);
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        acc[m].push_sync(d0[m]);
+        acc[m].push_sync(d1[m]);
+      }
+    }
+    __syncthreads();  // stage `st` may be refilled by the next iteration's issue()
+  }
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    acc[m].flush();
+    double mm = acc[m].m, ss = acc[m].s;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const double m2 = __shfl_xor_sync(0xffffffffu, mm, o), s2 = __shfl_xor_sync(0xffffffffu, ss, o);
+      lse_merge(m2, s2, mm, ss);
+    }
+    if (q == 0) part[blockIdx.y * ct_stride + wbase + 8 * m + g] = make_double2(mm + ha[m], ss);
   }
 }
 

@@ -216,7 +216,7 @@ def test_config2_shape_against_chunked_oracle(eng):
     rng = np.random.RandomState(1)
     u = draw_uniforms(rng, C, 0, P)
     x, acq, best = eng.suggest(list(range(P)), u, 1, n_below=n_below, n_candidates=C, multivariate=True)
-    assert eng.last_logpdf_kernel().startswith(("k_logpdf_fast", "k_logpdf_screen"))
+    assert eng.last_logpdf_kernel().startswith(("k_logpdf_mma", "k_logpdf_fast", "k_logpdf_screen"))
     smp, ll, lg = eng.get_candidates()
     params = [orc.Param("float", 0.0, 1.0) for _ in range(P)]
     cfg = orc.Config(multivariate=True)
