@@ -58,6 +58,11 @@ def algorithmic_flops(n=N_TRIALS, p=N_PARAMS, c=N_CAND, n_below=25) -> float:
     return float(c) * (n + 2) * (4 * p + 25)
 
 
+def executed_flops(n=N_TRIALS, p=N_PARAMS, c=N_CAND) -> float:
+    """fp64 flops the g(x) grid kernel issues: C x K_above x P fma on the tensor-core path."""
+    return 2.0 * c * (n - 25) * p
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region (NVML, ~1 kHz; nvidia-smi
     subprocesses are too slow for a 50 ms region and remain only as a fallback)."""
@@ -406,10 +411,19 @@ def run_b200(args) -> None:
                          "peak_source": peak_src, "kernel": kernel_name,
                          "kernel_ms": k_ms, "algorithmic_bytes": algorithmic_bytes(),
                          "note": "the C x K x P grid reuses every history byte C=4096 times from shared memory, so "
-                                 "this kernel sits on the fp64 pipe, not on HBM (SURVEY.md section 8d); see fp64"},
+                                 "this kernel sits on the fp64 (DMMA) pipe, not on HBM (SURVEY.md section 8d); see fp64"},
+            # algorithmic = the reference's operation count (4P + 25 flops per cell);
+            # executed = what the tensor-core kernel issues after expanding the square: one fma per
+            # cell on mma.m8n8k4.f64 (DMMA and DFMA share the 37 TFLOP/s fp64 peak on B200)
             "fp64": {"achieved_tflops": fl / (k_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
                      "frac": (fl / (k_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
-                     "algorithmic_flops": fl, "peak_source": "tpe_probe_fp64_tflops (DFMA microbenchmark, this run)"},
+                     "algorithmic_flops": fl,
+                     "executed_flops": executed_flops(),
+                     "executed_tflops": executed_flops() / (k_ms * 1e-3) / 1e12,
+                     "executed_frac": (executed_flops() / (k_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
+                     "kernel": eng.last_logpdf_kernel(),
+                     "peak_source": "tpe_probe_fp64_tflops (DFMA microbenchmark, this run; tools/probe_dmma.cu "
+                                    "measures the same 37.1 TFLOP/s for DMMA.8x8x4)"},
         }
         if extras:
             line["extras"] = extras

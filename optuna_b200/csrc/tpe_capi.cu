@@ -83,6 +83,11 @@ struct Estimator {
 struct tpe_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // the above-set estimator is built on a second stream while the main stream builds l(x), samples
+  // the candidates and evaluates them under l(x); joined before the first consumer of est[1]
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool above_pending = false;
   cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;
   std::string err;
@@ -189,35 +194,42 @@ struct FastInst {
 
 // Tensor-core (DMMA) instances of the CONST kernel: same launch signature (tab = fragment-major table,
 // cst = ckk, Kf = kernels rounded up to 8).
-template <int PB, int M, int NT, int TK, int ST>
+constexpr int kMmaKPad = 32;  // kernels are padded to 8 * KG (KG <= 4)
+template <int PB, int M, int KG, int NT, int TK, int ST, int MINB, int DBG = 0>
 struct MmaInst {
-  static constexpr size_t smem = (size_t)ST * TK * PB * 8 + (size_t)ST * TK * 8 + (size_t)ST * 8;
+  static constexpr size_t smem = (size_t)ST * TK * PB * 8 + (size_t)ST * TK * 8 + (size_t)ST * 16;
   static void launch(dim3 grid, size_t sm, cudaStream_t st, const void* tab, const double* cst, int64_t Kf,
                      const double2* colprm, const double* xT, int64_t ct_stride, int64_t kps, double skip,
                      double2* part, unsigned long long* gmax) {
-    k_logpdf_mma<PB, M, NT, TK, ST><<<grid, NT, sm, st>>>(static_cast<const double*>(tab), cst, Kf, colprm, xT,
-                                                         ct_stride, kps, skip, part, gmax);
+    k_logpdf_mma<PB, M, KG, NT, TK, ST, MINB, DBG><<<grid, NT, sm, st>>>(static_cast<const double*>(tab), cst, Kf, colprm,
+                                                                   xT, ct_stride, kps, skip, part, gmax);
   }
   static cudaError_t prepare() {
-    return cudaFuncSetAttribute(k_logpdf_mma<PB, M, NT, TK, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem);
+    return cudaFuncSetAttribute(k_logpdf_mma<PB, M, KG, NT, TK, ST, MINB, DBG>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  static FastCfg cfg(int minb) { return FastCfg{PB, (NT / 32) * 8 * M, NT, TK, ST, minb, smem, &launch, &prepare}; }
+  static FastCfg cfg() { return FastCfg{PB, (NT / 32) * 8 * M, NT, TK, ST, MINB, smem, &launch, &prepare}; }
 };
-//                                   PB M  NT   TK ST
+// Measured at config 2 (profiles/r1_variants.md): 32 warps/SM with two kernel groups in flight per
+// warp is the best of the tilings tried (1.17 ms); two candidate groups per warp (M = 2) halve the
+// CTA count and lose.
+//                                   PB M KG  NT   TK ST MINB
 const FastCfg kMmaBig[] = {
-    MmaInst<8, 2, 256, 512, 3>::cfg(2), MmaInst<16, 2, 256, 256, 3>::cfg(2), MmaInst<32, 2, 256, 128, 3>::cfg(2),
-    MmaInst<64, 2, 256, 64, 3>::cfg(1),
+    MmaInst<8, 1, 4, 256, 512, 3, 2>::cfg(), MmaInst<16, 1, 4, 256, 256, 3, 2>::cfg(),
+    MmaInst<32, 1, 2, 512, 128, 3, 2>::cfg(), MmaInst<64, 1, 2, 256, 64, 3, 1>::cfg(),
 };
 const FastCfg kMmaSmall[] = {
-    MmaInst<8, 2, 64, 512, 3>::cfg(4), MmaInst<16, 2, 64, 256, 3>::cfg(4), MmaInst<32, 2, 64, 128, 3>::cfg(4),
-    MmaInst<64, 2, 64, 64, 3>::cfg(4),
+    MmaInst<8, 1, 4, 64, 512, 3, 4>::cfg(), MmaInst<16, 1, 4, 64, 256, 3, 4>::cfg(),
+    MmaInst<32, 1, 4, 64, 128, 3, 4>::cfg(), MmaInst<64, 1, 2, 64, 64, 3, 3>::cfg(),
 };
 const FastCfg kMma32Variants[] = {
-    MmaInst<32, 2, 256, 128, 3>::cfg(2), MmaInst<32, 1, 1024, 128, 2>::cfg(1), MmaInst<32, 1, 256, 128, 3>::cfg(2),
-    MmaInst<32, 2, 128, 128, 3>::cfg(4), MmaInst<32, 1, 512, 128, 3>::cfg(2), MmaInst<32, 2, 512, 128, 2>::cfg(1),
-    MmaInst<32, 2, 256, 64, 4>::cfg(2),  MmaInst<32, 1, 512, 128, 2>::cfg(2),
+    MmaInst<32, 1, 4, 256, 128, 3, 2>::cfg(), MmaInst<32, 1, 2, 256, 128, 3, 2>::cfg(),
+    MmaInst<32, 1, 1, 512, 128, 3, 2>::cfg(), MmaInst<32, 1, 2, 256, 128, 2, 3>::cfg(),
+    MmaInst<32, 1, 2, 512, 128, 3, 2>::cfg(), MmaInst<32, 1, 2, 512, 128, 3, 2, 1>::cfg(),
+    MmaInst<32, 1, 2, 512, 128, 3, 2, 2>::cfg(), MmaInst<32, 1, 4, 256, 128, 3, 2, 1>::cfg(),
 };
+
+
 const FastCfg* pick_mma(int pb, int64_t Ct) {
   const bool small = Ct <= 64;
   if (pb == 32 && !small) {
@@ -293,8 +305,16 @@ const FastCfg* pick_fast(int mode, int pb, int64_t Ct) {
   return nullptr;
 }
 
-int set_device(tpe_ctx* ctx) {
+int join_above(tpe_ctx* ctx) {
+  if (ctx->above_pending) {
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    ctx->above_pending = false;
+  }
+  return TPE_OK;
+}
+int set_device(tpe_ctx* ctx, bool join = true) {
   CU(cudaSetDevice(ctx->device));
+  if (join) return join_above(ctx);
   return TPE_OK;
 }
 
@@ -489,15 +509,14 @@ bool mma_enabled() {
   return on;
 }
 
-int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
+int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t st) {
   Estimator& e = ctx->est[which];
   e.screen_ready = false;
   const int64_t n = e.n, K = n + 1;
   const int32_t pc = ctx->pc;
-  cudaStream_t st = ctx->stream;
   const int cap = ctx->sm_count * 8;
   e.K = K;
-  const int64_t k_alloc = round_up<int64_t>(K + 8, 8);
+  const int64_t k_alloc = round_up<int64_t>(K + 32, 32);  // >= round_up(K - 1, kMmaKPad), bulk-copy padding
   CU(e.mu.ensure((size_t)K * pc * 8));
   CU(e.sigma.ensure((size_t)K * pc * 8));
   CU(e.cst_part.ensure((size_t)K * 8));
@@ -630,6 +649,7 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host) {
 int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nullptr) {
   Estimator& e = ctx->est[which];
   cudaStream_t st = ctx->stream;
+  if (which == 1 && join_above(ctx)) return TPE_E_CUDA;
   const int64_t K = e.K;
   if (ctx->fast) {
     const bool cst_mode = ctx->fast_mode == 2;
@@ -645,7 +665,7 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     }
     const FastCfg* fc = use_mma ? pick_mma(ctx->pb, Ct) : pick_fast(ctx->fast_mode, ctx->pb, Ct);
     // CONST tables exclude the prior kernel (its sigma differs); the mma table is padded to groups of 8
-    const int64_t Kf = use_mma ? round_up<int64_t>(K - 1, 8) : (cst_mode ? K - 1 : K);
+    const int64_t Kf = use_mma ? round_up<int64_t>(K - 1, kMmaKPad) : (cst_mode ? K - 1 : K);
     const int tc = fc->cands_per_cta;
     const int64_t ctiles = (Ct + tc - 1) / tc;
     // k-splits: two full waves of resident CTAs for the big configurations
@@ -734,10 +754,9 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
                                   : ((fc->nt >= 256) ? "k_logpdf_fast<pair,big>" : "k_logpdf_fast<pair,small>");
     if (after_main) CU(cudaEventRecord(after_main, st));
     if (cst_mode) {  // the prior kernel, evaluated exactly, becomes one more partial row
-      k_logpdf_generic<<<dim3((unsigned)((Ct + 127) / 128), 1), 128, 0, st>>>(
+      k_logpdf_prior<<<(unsigned)((Ct * 32 + 255) / 256), 256, 0, st>>>(
           ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
-          e.cst.as<double>(), K, K - 1, 1, e.tab.as<double>(), nullptr, e.part.as<double2>() + nsplit * ctx->ct_stride,
-          ctx->ct_stride);
+          e.cst.as<double>(), K, e.tab.as<double>(), e.part.as<double2>() + nsplit * ctx->ct_stride);
       ctx->launch_counter++;
       nsplit += 1;
     }
@@ -810,11 +829,14 @@ int tpe_ctx_create(int device, tpe_ctx** out) {
   tpe_ctx* ctx = new tpe_ctx();
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return TPE_E_CUDA;
   }
   for (auto& e : ctx->ev) cudaEventCreate(&e);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   *out = ctx;
@@ -825,6 +847,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   for (DevBuf* b : {&ctx->cat_dist, &ctx->X, &ctx->cat, &ctx->key, &ctx->vals, &ctx->mo_list, &ctx->mo_alive, &ctx->mo_dom,
                     &ctx->mo_first, &ctx->mo_rank, &ctx->mo_ctr, &ctx->mo_tie, &ctx->mo_ntie, &ctx->mo_lexpos,
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed,
@@ -836,6 +859,9 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   ctx->est[1].release();
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1119,8 +1145,23 @@ static int build_locked(tpe_ctx* ctx, const double* w_below, const double* w_abo
       if (n > 0 && tot <= 0)
         return fail(ctx, TPE_E_INVALID, "The `weight` function is not allowed to return all-zero values.");
     }
-    int rc = build_estimator(ctx, which, w);
+  }
+  // multivariate builds share no scratch: g(x)'s estimator (the big one) goes to the second stream
+  const bool fork = ctx->cfg.multivariate != 0;
+  if (fork) {
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    int rc = build_estimator(ctx, 1, w_above, ctx->stream2);
     if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    ctx->above_pending = true;
+    rc = build_estimator(ctx, 0, w_below, ctx->stream);
+    if (rc) return rc;
+  } else {
+    for (int which = 0; which < 2; ++which) {
+      int rc = build_estimator(ctx, which, which == 0 ? w_below : w_above, ctx->stream);
+      if (rc) return rc;
+    }
   }
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   ctx->built = true;
@@ -1138,7 +1179,7 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
                                 int64_t* out_best) {
   if (!ctx->built) return fail(ctx, TPE_E_STATE, "tpe_build must precede tpe_sample_and_select");
   if (!uniforms || n_asks <= 0 || !out_x) return fail(ctx, TPE_E_INVALID, "bad sample arguments");
-  if (set_device(ctx)) return TPE_E_CUDA;
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;  // est[1] is joined by run_logpdf(ctx, 1)
   cudaStream_t st = ctx->stream;
   const int32_t C = ctx->cfg.n_candidates;
   const int64_t Ct = n_asks * C;

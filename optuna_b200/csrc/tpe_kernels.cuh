@@ -905,6 +905,23 @@ __global__ void k_logpdf_generic(const double* __restrict__ S, int64_t Ct, const
   part[blockIdx.y * ct_stride + ct] = make_double2(m, s);
 }
 
+// The prior kernel alone (CONST tables leave it out: its sigma differs), one warp per candidate with
+// the lanes over the columns; same cell formula as the generic path, summed by a shuffle tree.
+__global__ void k_logpdf_prior(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols, int32_t pc,
+                               const double* __restrict__ mu, const double* __restrict__ sigma,
+                               const double* __restrict__ cst, int64_t K, const double* __restrict__ tab,
+                               double2* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ct = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (ct >= Ct) return;
+  const int64_t k = K - 1;
+  double acc = 0.0;
+  for (int j = lane; j < pc; j += 32)
+    acc += cell_one_exact(cols[j], S[ct * pc + j], mu[k * pc + j], sigma[k * pc + j], true, tab);
+  acc = warp_sum(acc);
+  if (lane == 0) part[ct] = make_double2(cst[k] + acc, 1.0);
+}
+
 // Generic path, pair-parallel: one CTA = one candidate x (256 * kpt) kernels, one thread evaluates
 // whole (candidate, kernel) cell sums with the reference's operation order, block-level log-sum-exp.
 // Used for spaces with discrete / categorical columns (every thread of a warp walks the same column
@@ -1241,6 +1258,134 @@ k_logpdf_fast(const void* __restrict__ tab_v, const double* __restrict__ cst, in
   }
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Two-tier log-sum-exp for the tensor-core kernel.  Terms are classified against a reference `base`
+// (a lower bound of the candidate's true max: the lane's own max or one published by another lane /
+// CTA):
+//   near  L - base > -tnear           parked and folded exactly in fp64 (as LseAcc)
+//   far   -skip < L - base <= -tnear  exp() evaluated at once with the fp32 SFU path (MUFU.EX2) and summed
+//                                     relative to base: no parking, no fp64 work, branch-free
+//   else  dropped
+// With tnear = ln K + 17.5 and skip = ln K + 30 the result stays inside the fp64-parity budget
+// whatever the data: each far term is <= e^-tnear of the max term, there are <= K of them and each
+// carries <= 6e-6 relative error (fp32 rounding of L - base, MUFU, <= 32-term fp32 runs), so the
+// far tier adds <= 6e-6 * K * e^-tnear = 1.5e-13 relative to the sum; dropped terms add <= 1e-13.
+// At config 2 ~80 % of the terms inside the skip window are far: the exact folds (a full fp64 exp
+// each, executed by the whole warp) become ~5x rarer.
+struct LseTier {
+  double m, s, base, gm, fsum, b0, b1, b2, b3;
+  float ffar;
+  int cnt;
+  __device__ __forceinline__ void init() {
+    m = -INFINITY; s = 0.0; base = -INFINITY; gm = -INFINITY; fsum = 0.0;
+    b0 = b1 = b2 = b3 = 0.0; ffar = 0.0f; cnt = 0;
+  }
+  // e^x for x <= 0 (the only arguments a running log-sum-exp needs): one range reduction, a
+  // degree-12 Taylor polynomial on |r| <= ln2 / 2 (truncation 2e-16) and an exponent add -- ~20
+  // instructions instead of the ~45 of the general exp().  x < -700 (incl. -inf) returns 0.
+  static __device__ __forceinline__ double exp_neg(double x) {
+    const double xc = fmax(x, -700.0);
+    const double t = fma(xc, 1.4426950408889634074, 6755399441055744.0);
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double r = fma(nf, -6.93147180369123816490e-01, xc);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    double p = 2.08767569878680989792e-09;           // 1 / 12!
+    p = fma(p, r, 2.50521083854417187751e-08);       // 1 / 11!
+    p = fma(p, r, 2.75573192239858906526e-07);
+    p = fma(p, r, 2.75573192239858906526e-06);
+    p = fma(p, r, 2.48015873015873015873e-05);
+    p = fma(p, r, 1.98412698412698412698e-04);
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double y = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    return (x < -700.0) ? 0.0 : y;
+  }
+  // fold the parked terms: new max first, then the rescale factor and the (up to 4) terms are
+  // independent exps.  Then bring the far-tier sum (relative to base) into (m, s) and move base up
+  // to the best max known.  Executed by the whole warp together.
+  __device__ __forceinline__ void flush() {
+    const bool v0 = cnt > 0, v1 = cnt > 1, v2 = cnt > 2, v3 = cnt > 3;
+    double nm = m;
+    nm = (v0 && b0 > nm) ? b0 : nm;
+    nm = (v1 && b1 > nm) ? b1 : nm;
+    nm = (v2 && b2 > nm) ? b2 : nm;
+    nm = (v3 && b3 > nm) ? b3 : nm;
+    // m = -inf (nothing folded yet): s = 0 and exp_neg(-inf or NaN) is finite, so the product is 0
+    double t = s * exp_neg(m - nm);
+    const double e0 = exp_neg(b0 - nm), e1 = exp_neg(b1 - nm), e2 = exp_neg(b2 - nm), e3 = exp_neg(b3 - nm);
+    t += (v0 ? e0 : 0.0) + (v1 ? e1 : 0.0);
+    t += (v2 ? e2 : 0.0) + (v3 ? e3 : 0.0);
+    s = t;
+    m = nm;
+    cnt = 0;
+    const double fs = fsum + (double)ffar;
+    fsum = 0.0;
+    ffar = 0.0f;
+    const bool own = m >= base;                    // also the cold start (base = -inf)
+    const bool adopt = !own && fs != 0.0;          // only far terms so far: take base as the reference
+    const double ex = exp_neg(-fabs(m - base));    // m or base = -inf: 0
+    const double s_own = (fs != 0.0) ? fma(fs, ex, s) : s;   // base = -inf implies fs = 0
+    const double s_adopt = fma(s, ex, fs);
+    s = own ? s_own : (adopt ? s_adopt : s);
+    m = adopt ? base : m;
+    base = fmax(m, gm);
+  }
+  __device__ __forceinline__ void roll() {  // bounds the length of the fp32 runs (once per tile)
+    fsum += (double)ffar;
+    ffar = 0.0f;
+  }
+  __device__ __forceinline__ void sync_global(unsigned long long* slot) {
+    if (m > gm) atomicMax(slot, static_cast<unsigned long long>(order_bits(m)));
+    const double seen = from_order_bits(*reinterpret_cast<volatile unsigned long long*>(slot));
+    gm = fmax(gm, seen);
+    if (__any_sync(0xffffffffu, gm > base)) flush();
+  }
+  __device__ __forceinline__ void park(double L, bool near) {
+    b3 = near ? b2 : b3;
+    b2 = near ? b1 : b2;
+    b1 = near ? b0 : b1;
+    b0 = near ? L : b0;
+    cnt += near ? 1 : 0;
+    if (__any_sync(0xffffffffu, cnt == 4)) flush();
+  }
+  // N terms at once: the classification and the far-tier exps of all of them are independent
+  // (pipelined through the fp64 / SFU / fp32 pipes), one vote decides whether any lane has a near
+  // term at all -- rare once base has converged (< 1 % of the terms are near).
+  template <int N, bool EXACT>
+  __device__ __forceinline__ void push_batch(const double (&L)[N], float skip, float tnear) {
+    bool near[N];
+    bool any = false;
+    float add = 0.0f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float df = __double2float_rn(L[i] - base);  // base = -inf -> +inf -> near
+      near[i] = df > -tnear;
+      const bool far = !near[i] && df > -skip;
+      const float e = ex2_approx(df * 1.44269504f);
+      add += far ? e : 0.0f;
+      any = any || near[i];
+    }
+    ffar += add;
+    if (EXACT && __any_sync(0xffffffffu, any)) {
+      // note: terms of this batch that were classified far against the old base stay far (exact
+      // enough by construction) even if a flush inside this loop raises base
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (__any_sync(0xffffffffu, near[i])) park(L[i], near[i]);
+    }
+  }
+};
+
 // ================================================================================================
 // Tensor-core variant of the CONST kernel (multivariate TPE, continuous columns).
 //
@@ -1266,36 +1411,41 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
 }
-template <int PB, int M, int NT, int TK, int ST>
-__global__ void __launch_bounds__(NT)
-k_logpdf_mma(const double* __restrict__ tabm, const double* __restrict__ ckk, int64_t Kf8,
+// KG kernel groups (8 kernels each) are in flight per warp: KG * M independent mma chains, which is
+// what keeps the DMMA pipe fed (a chain of 8 dependent DMMAs alone leaves it ~45 % idle).
+template <int PB, int M, int KG, int NT, int TK, int ST, int MINB, int DBG = 0>
+__global__ void __launch_bounds__(NT, MINB)
+k_logpdf_mma(const double* __restrict__ tabm, const double* __restrict__ ckk, int64_t Kfp,
              const double2* __restrict__ colprm, const double* __restrict__ xT, int64_t ct_stride, int64_t kps,
              double lse_skip, double2* __restrict__ part, unsigned long long* __restrict__ gmax) {
-  static_assert(PB % 8 == 0 && TK % 8 == 0, "bad tiling");
+  static_assert(PB % 8 == 0 && TK % (8 * KG) == 0, "bad tiling");
   constexpr int NI = PB / 4;        // k-steps of the mma chain
   constexpr int CW = 8 * M;         // candidates per warp
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* tiles = reinterpret_cast<double*>(smem_raw);                             // ST * TK * PB
   double* csts = tiles + (size_t)ST * TK * PB;                                     // ST * TK
   uint64_t* full = reinterpret_cast<uint64_t*>(csts + (size_t)ST * TK);            // ST
+  uint64_t* empty = full + ST;                                                     // ST
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int g = lane >> 2, q = lane & 3;
   const int64_t k0 = blockIdx.y * kps;
-  const int64_t k1 = (k0 + kps < Kf8) ? k0 + kps : Kf8;
+  const int64_t k1 = (k0 + kps < Kfp) ? k0 + kps : Kfp;   // Kfp, kps: multiples of 8 * KG
   const int ntiles = (k1 > k0) ? (int)((k1 - k0 + TK - 1) / TK) : 0;
   const int64_t wbase = (int64_t)blockIdx.x * ((NT / 32) * CW) + (int64_t)(tid >> 5) * CW;
 
   if (tid == 0) {
-    for (int s = 0; s < ST; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NT / 32);
+    }
     mbar_fence_init();
-    LseAcc::skip() = lse_skip;
   }
   __syncthreads();
   auto issue = [&](int t) {
     const int st = t % ST;
     const int64_t ks = k0 + (int64_t)t * TK;
-    const int tk = (int)((k1 - ks < TK) ? (k1 - ks) : TK);  // multiple of 8
+    const int tk = (int)((k1 - ks < TK) ? (k1 - ks) : TK);
     const uint32_t b_tile = (uint32_t)((size_t)tk * PB * 8);
     const uint32_t b_cst = (uint32_t)(tk * 8);
     fence_proxy_async();
@@ -1330,49 +1480,80 @@ k_logpdf_mma(const double* __restrict__ tabm, const double* __restrict__ ckk, in
     ha[m] += __shfl_xor_sync(0xffffffffu, ha[m], 2);
     ha[m] *= -0.5;
   }
-  LseAcc acc[M];
+  LseTier acc[M];
 #pragma unroll
   for (int m = 0; m < M; ++m) acc[m].init();
+  const float lim_skip = (float)lse_skip, lim_near = (float)(lse_skip - 12.5);
 
   for (int t = 0; t < ntiles; ++t) {
     const int st = t % ST;
-    if (tid == 0 && t + ST - 1 < ntiles) issue(t + ST - 1);
+    if (tid == 0 && t + ST - 1 < ntiles) {
+      // the stage being refilled held tile t - 1: wait until every warp has released it
+      if (t > 0) mbar_wait(&empty[(t - 1) % ST], (uint32_t)(((t - 1) / ST) & 1));
+      issue(t + ST - 1);
+    }
     mbar_wait(&full[st], (uint32_t)((t / ST) & 1));
     const int64_t ks = k0 + (int64_t)t * TK;
     const int tk = (int)((k1 - ks < TK) ? (k1 - ks) : TK);
     const double* tile = tiles + (size_t)st * TK * PB;
     const double* ctile = csts + (size_t)st * TK;
-    for (int kg = 0; kg < tk / 8; ++kg) {
-      if (kg == 0 || t == 0) {  // every tile, and every group of the CTA's first tile (cold start)
+    for (int kg = 0; kg < tk / 8; kg += KG) {
+      if (kg == 0 || t == 0) {  // every tile, and every iteration of the CTA's first tile (cold start)
 #pragma unroll
-        for (int m = 0; m < M; ++m) acc[m].sync_global(gmax + wbase + 8 * m + g);
+        for (int m = 0; m < M; ++m) {
+          acc[m].roll();
+          acc[m].sync_global(gmax + wbase + 8 * m + g);
+        }
       }
       const double2* fb = reinterpret_cast<const double2*>(tile + (size_t)kg * 8 * PB) + lane;
-      double b[NI];
+      double d0[KG][M], d1[KG][M];
+#pragma unroll
+      for (int u = 0; u < KG; ++u) {
+        const double2 cc = reinterpret_cast<const double2*>(ctile + (kg + u) * 8)[q];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          d0[u][m] = cc.x;
+          d1[u][m] = cc.y;
+        }
+      }
+      double2 v[2][KG];
+#pragma unroll
+      for (int u = 0; u < KG; ++u) v[0][u] = fb[u * (4 * PB)];   // one kernel group = 8 * PB doubles
 #pragma unroll
       for (int i2 = 0; i2 < NI / 2; ++i2) {
-        const double2 v = fb[i2 * 32];
-        b[2 * i2] = v.x;
-        b[2 * i2 + 1] = v.y;
+        if (i2 + 1 < NI / 2) {
+#pragma unroll
+          for (int u = 0; u < KG; ++u) v[(i2 + 1) & 1][u] = fb[u * (4 * PB) + (i2 + 1) * 32];
+        }
+#pragma unroll
+        for (int u = 0; u < KG; ++u)
+#pragma unroll
+          for (int m = 0; m < M; ++m) dmma_8x8x4(d0[u][m], d1[u][m], a[m][2 * i2], v[i2 & 1][u].x);
+#pragma unroll
+        for (int u = 0; u < KG; ++u)
+#pragma unroll
+          for (int m = 0; m < M; ++m) dmma_8x8x4(d0[u][m], d1[u][m], a[m][2 * i2 + 1], v[i2 & 1][u].y);
       }
-      const double2 cc = reinterpret_cast<const double2*>(ctile + kg * 8)[q];
-      double d0[M], d1[M];
 #pragma unroll
       for (int m = 0; m < M; ++m) {
-        d0[m] = cc.x;
-        d1[m] = cc.y;
-      }
+        double vals[2 * KG];
 #pragma unroll
-      for (int i = 0; i < NI; ++i)
+        for (int u = 0; u < KG; ++u) {
+          vals[2 * u] = d0[u][m];
+          vals[2 * u + 1] = d1[u][m];
+        }
+        if constexpr (DBG == 1) {  // timing experiment: no log-sum-exp work at all
 #pragma unroll
-        for (int m = 0; m < M; ++m) dmma_8x8x4(d0[m], d1[m], a[m][i], b[i]);
-#pragma unroll
-      for (int m = 0; m < M; ++m) {
-        acc[m].push_sync(d0[m]);
-        acc[m].push_sync(d1[m]);
+          for (int u = 0; u < 2 * KG; ++u) acc[m].fsum += vals[u];
+        } else if constexpr (DBG == 2) {  // timing experiment: classification + far tier only
+          acc[m].template push_batch<2 * KG, false>(vals, lim_skip, lim_near);
+        } else {
+          acc[m].template push_batch<2 * KG, true>(vals, lim_skip, lim_near);
+        }
       }
     }
-    __syncthreads();  // stage `st` may be refilled by the next iteration's issue()
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with stage `st`
   }
 #pragma unroll
   for (int m = 0; m < M; ++m) {
