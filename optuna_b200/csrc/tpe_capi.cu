@@ -106,7 +106,8 @@ struct tpe_ctx {
   int64_t N = 0;
   // MOTPE scratch
   DevBuf mo_list, mo_alive, mo_dom, mo_first, mo_rank, mo_ctr, mo_tie, mo_ntie, mo_lexpos, mo_isdup, mo_sorted,
-      mo_uniq, mo_nuniq, mo_ref, mo_removed, mo_contrib, mo_state, mo_arena, mo_chosen, mo_diag, mo_w;
+      mo_uniq, mo_nuniq, mo_ref, mo_removed, mo_contrib, mo_state, mo_arena, mo_chosen, mo_diag, mo_w, mo_table, mo_sample,
+      mo_surv, mo_nsurv;
   bool mo_weights_ready = false;
   std::vector<uint8_t> col_missing;
   bool history_set = false;
@@ -346,6 +347,15 @@ int upload_history(tpe_ctx* ctx, const double* X, const int8_t* category, const 
 
 // ---- MOTPE: selection of the below part of the COMPLETE group (sampler.py:745-779) ----------------
 // Fills ctx->member (u8 per history row) and returns how many COMPLETE trials went below.
+// Per-thread scratch (doubles, odd so that the threads spread over the banks) of an M <= 3
+// hypervolume of up to n points held in shared memory: caller's point list + hypervolume()'s copy,
+// tmp row and order / mask words.  0 = does not fit (or M > 3, where hv_nd needs the O(n^2) arena).
+int mo_smem_stride(int n, int M) {
+  if (M > 3) return 0;
+  const int stride = (2 * n * M + M + n + 9) | 1;
+  return ((size_t)kMoMaxSet * stride * 8 <= 160 * 1024) ? stride : 0;
+}
+
 int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
   cudaStream_t st = ctx->stream;
   const int M = ctx->M;
@@ -381,6 +391,9 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
   CU(ctx->mo_contrib.ensure((size_t)nc * 8));
   CU(ctx->mo_diag.ensure((size_t)nc * 16));
   CU(ctx->mo_state.ensure(sizeof(HsspState)));
+  CU(ctx->mo_sample.ensure(256 * 4));
+  CU(ctx->mo_surv.ensure((size_t)nc * 4));
+  CU(ctx->mo_nsurv.ensure(16));
   CU(cudaMemsetAsync(ctx->mo_alive.p, 1, (size_t)nc, st));
   CU(cudaMemsetAsync(ctx->mo_rank.p, 0, (size_t)nc * 4, st));
   CU(cudaMemsetAsync(ctx->mo_ctr.p, 0, sizeof(MoCounters), st));
@@ -393,8 +406,26 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
   int r = 0;
   int64_t prev_all = 0;
   for (;;) {
-    k_mo_peel<<<gb, 256, 256 * M * 8, st>>>(vals, M, dlist, nc, ctx->mo_alive.as<uint8_t>(), ctx->mo_dom.as<uint8_t>(),
-                                             r == 0 ? ctx->mo_first.as<uint8_t>() : nullptr, ctx->mo_ctr.as<MoCounters>());
+    if (r == 0) {  // duplicates of the whole complete set, once
+      uint32_t tsize = 1024;
+      while (tsize < 2u * (uint32_t)nc) tsize <<= 1;
+      CU(ctx->mo_table.ensure((size_t)tsize * 4));
+      CU(cudaMemsetAsync(ctx->mo_table.p, 0x7f, (size_t)tsize * 4, st));
+      k_mo_first_insert<<<gb, 256, 0, st>>>(vals, M, dlist, nc, ctx->mo_table.as<int>(), tsize - 1);
+      k_mo_first_lookup<<<gb, 256, 0, st>>>(vals, M, dlist, nc, ctx->mo_table.as<int>(), tsize - 1,
+                                            ctx->mo_first.as<uint8_t>(), ctx->mo_ctr.as<MoCounters>());
+      ctx->launch_counter += 2;
+    }
+    k_mo_sample<<<1, 1024, 0, st>>>(nc, ctx->mo_alive.as<uint8_t>(), ctx->mo_sample.as<int32_t>(),
+                                    ctx->mo_nsurv.as<int>(), ctx->mo_nsurv.as<int>() + 1);
+    k_mo_peel_a<<<gb, 256, 256 * M * 8, st>>>(vals, M, dlist, nc, ctx->mo_alive.as<uint8_t>(),
+                                               ctx->mo_sample.as<int32_t>(), ctx->mo_nsurv.as<int>(),
+                                               ctx->mo_dom.as<uint8_t>(), ctx->mo_surv.as<int32_t>(),
+                                               ctx->mo_nsurv.as<int>() + 1);
+    k_mo_peel_b<<<std::min(nc, ctx->sm_count * 8), 256, 0, st>>>(vals, M, dlist, nc, ctx->mo_alive.as<uint8_t>(),
+                                                                  ctx->mo_surv.as<int32_t>(), ctx->mo_nsurv.as<int>() + 1,
+                                                                  ctx->mo_dom.as<uint8_t>());
+    ctx->launch_counter += 1;
     k_mo_commit<<<gb, 256, 0, st>>>(nc, ctx->mo_alive.as<uint8_t>(), ctx->mo_dom.as<uint8_t>(),
                                      ctx->mo_first.as<uint8_t>(), ctx->mo_rank.as<int32_t>(), r,
                                      ctx->mo_ctr.as<MoCounters>());
@@ -469,13 +500,17 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
           ctx->launch_counter++;
         } else {
           const size_t stride = (size_t)(subset + 2) * M + hv_arena_doubles(subset + 1, M);
-          CU(ctx->mo_arena.ensure((size_t)nu * stride * 8));
+          const int sstride = mo_smem_stride(subset + 1, M);
+          const int cthreads = sstride ? 32 : 64;
+          const size_t csmem = sstride ? (size_t)cthreads * sstride * 8 : 0;
+          if (!sstride) CU(ctx->mo_arena.ensure((size_t)nu * stride * 8));
+          if (csmem > 48 * 1024)
+            CU(cudaFuncSetAttribute(k_hssp_contrib, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
           for (int t = 0; t < subset; ++t) {
-            k_hssp_contrib<<<(nu + 63) / 64, 64, 0, st>>>(vals, M, dlist, ctx->mo_tie.as<int32_t>(),
-                                                          ctx->mo_uniq.as<int32_t>(), nu, ctx->mo_removed.as<uint8_t>(),
-                                                          ctx->mo_ref.as<double>(), ctx->mo_state.as<HsspState>(),
-                                                          ctx->mo_contrib.as<double>(), ctx->mo_arena.as<double>(),
-                                                          stride);
+            k_hssp_contrib<<<(nu + cthreads - 1) / cthreads, cthreads, csmem, st>>>(
+                vals, M, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu,
+                ctx->mo_removed.as<uint8_t>(), ctx->mo_ref.as<double>(), ctx->mo_state.as<HsspState>(),
+                ctx->mo_contrib.as<double>(), ctx->mo_arena.as<double>(), stride, sstride);
             k_hssp_pick<<<1, 256, 0, st>>>(vals, M, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu,
                                            ctx->mo_removed.as<uint8_t>(), ctx->mo_contrib.as<double>(),
                                            ctx->mo_state.as<HsspState>());
@@ -615,11 +650,15 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
       return fail(ctx, TPE_E_INVALID, "MOTPE supports at most %d below trials (got %d)", kMoMaxSet, nba);
     if (nba != n) return fail(ctx, TPE_E_INVALID, "MOTPE with partially missing parameters in the below set is not supported yet");
     const size_t stride = (size_t)(nba + 2) * ctx->M + hv_arena_doubles(nba + 1, ctx->M);
-    CU(ctx->mo_arena.ensure((size_t)(nba + 1) * stride * 8));
+    const int sstride = mo_smem_stride(nba + 1, ctx->M);
+    const size_t wsmem = sstride ? (size_t)kMoMaxSet * sstride * 8 : 0;
+    if (!sstride) CU(ctx->mo_arena.ensure((size_t)(nba + 1) * stride * 8));
+    if (wsmem > 32 * 1024)
+      CU(cudaFuncSetAttribute(k_mo_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
     CU(ctx->mo_w.ensure((size_t)kMoMaxSet * 8));
-    k_mo_weights<<<1, kMoMaxSet, 0, st>>>(ctx->vals.as<double>(), ctx->M, e.rows.as<int64_t>(), nba,
-                                          ctx->cat.as<int8_t>(), ctx->mo_w.as<double>(), ctx->mo_arena.as<double>(),
-                                          stride);
+    k_mo_weights<<<1, kMoMaxSet, wsmem, st>>>(ctx->vals.as<double>(), ctx->M, e.rows.as<int64_t>(), nba,
+                                              ctx->cat.as<int8_t>(), ctx->mo_w.as<double>(), ctx->mo_arena.as<double>(),
+                                              stride, sstride);
     ctx->launch_counter++;
     ctx->mo_weights_ready = true;
     w_dev = ctx->mo_w.as<double>();
@@ -850,7 +889,8 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   for (DevBuf* b : {&ctx->cat_dist, &ctx->X, &ctx->cat, &ctx->key, &ctx->vals, &ctx->mo_list, &ctx->mo_alive, &ctx->mo_dom,
                     &ctx->mo_first, &ctx->mo_rank, &ctx->mo_ctr, &ctx->mo_tie, &ctx->mo_ntie, &ctx->mo_lexpos,
-                    &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed,
+                    &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed, &ctx->mo_table,
+                    &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
                     &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})

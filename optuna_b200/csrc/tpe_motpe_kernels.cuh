@@ -27,44 +27,125 @@ __device__ __forceinline__ bool dominates(const double* a, const double* b, int 
   return le && lt;
 }
 
-// One peel: dominated[i] = some alive j dominates i.  On the first call also is_first[i] = no
-// earlier trial has the identical vector (np.unique semantics: duplicates share a rank and count once).
-__global__ void k_mo_peel(const double* __restrict__ vals, int M, const int64_t* __restrict__ list, int nc,
-                          const uint8_t* __restrict__ alive, uint8_t* __restrict__ dominated,
-                          uint8_t* __restrict__ is_first, MoCounters* __restrict__ ctr) {
-  extern __shared__ double s_tile[];  // 256 * M
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double me[kMoMaxM];
-  const bool act = i < nc && alive[i];
-  if (i < nc)
-    for (int j = 0; j < M; ++j) me[j] = vals[list[i] * M + j];
-  bool dom = false, dup_before = false;
-  for (int t0 = 0; t0 < nc; t0 += blockDim.x) {
-    const int q = t0 + threadIdx.x;
-    __syncthreads();
-    if (q < nc)
-      for (int j = 0; j < M; ++j) s_tile[threadIdx.x * M + j] = vals[list[q] * M + j];
-    __syncthreads();
-    const int lim = min((int)blockDim.x, nc - t0);
-    if (i < nc) {
-      for (int r = 0; r < lim; ++r) {
-        const int jdx = t0 + r;
-        const double* o = s_tile + r * M;
-        if (act && alive[jdx]) dom = dom || dominates(o, me, M);
-        if (is_first != nullptr && jdx < i) {
-          bool eq = true;
-          for (int j = 0; j < M; ++j) eq = eq && (o[j] == me[j]);
-          dup_before = dup_before || eq;
-        }
-      }
-    }
+// ---- duplicates (np.unique semantics: identical vectors share a rank and count once) ---------------
+// is_first[i] = no earlier trial has the identical objective vector.  Open-addressing table of trial
+// positions keyed by a hash of the vector (-0.0 folded onto +0.0 like ==); a slot keeps the smallest
+// position among the identical vectors that landed in it.
+constexpr int kMoEmpty = 0x7f7f7f7f;  // cudaMemset(0x7f)
+__device__ __forceinline__ uint64_t mo_hash(const double* v, int M) {
+  uint64_t h = 0x9e3779b97f4a7c15ull;
+  for (int j = 0; j < M; ++j) {
+    double x = v[j];
+    if (x == 0.0) x = 0.0;
+    uint64_t z = static_cast<uint64_t>(__double_as_longlong(x)) + h;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    h = z ^ (z >> 31);
   }
-  if (i < nc) {
-    dominated[i] = dom ? 1 : 0;
-    if (is_first != nullptr) {
-      is_first[i] = dup_before ? 0 : 1;
-      if (!dup_before) atomicAdd(&ctr->n_unique, 1);
+  return h;
+}
+__device__ __forceinline__ bool mo_same(const double* a, const double* b, int M) {
+  bool eq = true;
+  for (int j = 0; j < M; ++j) eq = eq && (a[j] == b[j]);
+  return eq;
+}
+__global__ void k_mo_first_insert(const double* __restrict__ vals, int M, const int64_t* __restrict__ list, int nc,
+                                  int* __restrict__ table, uint32_t mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  const double* me = vals + list[i] * M;
+  uint32_t slot = (uint32_t)mo_hash(me, M) & mask;
+  for (;;) {
+    int cur = *reinterpret_cast<volatile int*>(table + slot);
+    if (cur == kMoEmpty) {
+      const int old = atomicCAS(table + slot, kMoEmpty, i);
+      if (old == kMoEmpty) return;
+      cur = old;
     }
+    if (mo_same(vals + list[cur] * M, me, M)) {
+      atomicMin(table + slot, i);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+__global__ void k_mo_first_lookup(const double* __restrict__ vals, int M, const int64_t* __restrict__ list, int nc,
+                                  const int* __restrict__ table, uint32_t mask, uint8_t* __restrict__ is_first,
+                                  MoCounters* __restrict__ ctr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool first = false;
+  if (i < nc) {
+    const double* me = vals + list[i] * M;
+    uint32_t slot = (uint32_t)mo_hash(me, M) & mask;
+    for (;;) {
+      const int cur = table[slot];
+      if (mo_same(vals + list[cur] * M, me, M)) {
+        first = cur == i;
+        break;
+      }
+      slot = (slot + 1) & mask;
+    }
+    is_first[i] = first ? 1 : 0;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, first);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ctr->n_unique, __popc(b));
+}
+
+// ---- one peel of the non-domination ranking ---------------------------------------------------------
+// dominated[i] = some alive j dominates i.  All-pairs is O(n^2); instead every alive point is first
+// tested against a sample of <= 256 alive points (a point dominated by the sample is dominated,
+// whoever does it), and only the survivors -- a few per cent for 2-4 objectives -- are tested
+// against every alive point.
+__global__ void __launch_bounds__(1024, 1)
+k_mo_sample(int nc, const uint8_t* __restrict__ alive, int32_t* __restrict__ sample, int* __restrict__ n_sample,
+            int* __restrict__ n_surv) {
+  __shared__ int s_warp[32];
+  int base = 0;
+  for (int t0 = 0; t0 < nc && base < 256; t0 += 1024) {
+    const int i = t0 + threadIdx.x;
+    const bool f = i < nc && alive[i];
+    const int2 rk = block_rank_1024(f, s_warp);
+    if (f && base + rk.x < 256) sample[base + rk.x] = i;
+    base += rk.y;
+  }
+  if (threadIdx.x == 0) {
+    *n_sample = base < 256 ? base : 256;
+    *n_surv = 0;
+  }
+}
+__global__ void k_mo_peel_a(const double* __restrict__ vals, int M, const int64_t* __restrict__ list, int nc,
+                            const uint8_t* __restrict__ alive, const int32_t* __restrict__ sample,
+                            const int* __restrict__ n_sample, uint8_t* __restrict__ dominated,
+                            int32_t* __restrict__ surv, int* __restrict__ n_surv) {
+  extern __shared__ double s_tile[];  // 256 * M
+  const int ns = *n_sample;
+  if (threadIdx.x < ns)
+    for (int j = 0; j < M; ++j) s_tile[threadIdx.x * M + j] = vals[list[sample[threadIdx.x]] * M + j];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  bool dom = false;
+  if (alive[i]) {
+    double me[kMoMaxM];
+    for (int j = 0; j < M; ++j) me[j] = vals[list[i] * M + j];
+    for (int r = 0; r < ns && !dom; ++r) dom = dominates(s_tile + r * M, me, M);
+    if (!dom) surv[atomicAdd(n_surv, 1)] = i;
+  }
+  dominated[i] = dom ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+k_mo_peel_b(const double* __restrict__ vals, int M, const int64_t* __restrict__ list, int nc,
+            const uint8_t* __restrict__ alive, const int32_t* __restrict__ surv, const int* __restrict__ n_surv,
+            uint8_t* __restrict__ dominated) {
+  const int ns = *n_surv;
+  for (int s = blockIdx.x; s < ns; s += gridDim.x) {
+    const int i = surv[s];
+    double me[kMoMaxM];
+    for (int j = 0; j < M; ++j) me[j] = vals[list[i] * M + j];
+    bool dom = false;
+    for (int q = threadIdx.x; q < nc && !dom; q += 256)
+      if (alive[q]) dom = dominates(vals + list[q] * M, me, M);
+    if (__syncthreads_or(dom) && threadIdx.x == 0) dominated[i] = 1;
   }
 }
 // front = alive & !dominated gets rank r
@@ -185,7 +266,10 @@ __global__ void k_hssp_contrib(const double* __restrict__ vals, int M, const int
                                const int32_t* __restrict__ tie_pos, const int32_t* __restrict__ uniq, int nu,
                                const uint8_t* __restrict__ removed, const double* __restrict__ ref,
                                const HsspState* __restrict__ st, double* __restrict__ contrib,
-                               double* __restrict__ arena, size_t arena_stride) {
+                               double* __restrict__ arena, size_t arena_stride, int smem_stride) {
+  // smem_stride != 0 (M <= 3, where the scratch is a few hundred doubles per thread): the scratch
+  // lives in shared memory instead of the global arena
+  extern __shared__ double s_arena[];
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= nu) return;
   if (removed[u]) {
@@ -204,7 +288,7 @@ __global__ void k_hssp_contrib(const double* __restrict__ vals, int M, const int
     contrib[u] = INFINITY;
     return;
   }
-  double* a = arena + (size_t)u * arena_stride;
+  double* a = smem_stride ? s_arena + (size_t)threadIdx.x * smem_stride : arena + (size_t)u * arena_stride;
   double* pts = a;  // (t + 1) * M
   double* rest = a + (size_t)(t + 1) * M;
   if (M <= 3) {
@@ -359,7 +443,9 @@ k_mo_fill_dups(int n, const uint8_t* __restrict__ is_dup, int want, int32_t* __r
 // cat: category per history row (INFEASIBLE -> EPS weight).
 __global__ void __launch_bounds__(kMoMaxSet)
 k_mo_weights(const double* __restrict__ vals, int M, const int64_t* __restrict__ rows, int n,
-             const int8_t* __restrict__ cat, double* __restrict__ w, double* __restrict__ arena, size_t arena_stride) {
+             const int8_t* __restrict__ cat, double* __restrict__ w, double* __restrict__ arena, size_t arena_stride,
+             int smem_stride) {
+  extern __shared__ double s_arena[];           // per-thread scratch when smem_stride != 0 (M <= 3)
   __shared__ double s_v[kMoMaxSet * kMoMaxM];   // feasible points, trial order
   __shared__ double s_ps[kMoMaxSet * kMoMaxM];  // Pareto points, trial order
   __shared__ double s_ref[kMoMaxM];
@@ -401,7 +487,7 @@ k_mo_weights(const double* __restrict__ vals, int M, const int64_t* __restrict__
         }
       }
       s_np = np;
-      s_hv = hypervolume(s_ps, np, M, s_ref, true, arena);
+      s_hv = hypervolume(s_ps, np, M, s_ref, true, smem_stride ? s_arena : arena);
     }
   }
   __syncthreads();
@@ -413,7 +499,7 @@ k_mo_weights(const double* __restrict__ vals, int M, const int64_t* __restrict__
   if (tid < nf) s_contrib[tid] = 0.0;
   __syncthreads();
   if (tid < np) {
-    double* a = arena + (size_t)tid * arena_stride;
+    double* a = smem_stride ? s_arena + (size_t)tid * smem_stride : arena + (size_t)tid * arena_stride;
     double* pts = a;
     double* rest = a + (size_t)np * M;
     int c = 0;
