@@ -507,10 +507,16 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
           if (csmem > 48 * 1024)
             CU(cudaFuncSetAttribute(k_hssp_contrib, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
           for (int t = 0; t < subset; ++t) {
-            k_hssp_contrib<<<(nu + cthreads - 1) / cthreads, cthreads, csmem, st>>>(
-                vals, M, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu,
-                ctx->mo_removed.as<uint8_t>(), ctx->mo_ref.as<double>(), ctx->mo_state.as<HsspState>(),
-                ctx->mo_contrib.as<double>(), ctx->mo_arena.as<double>(), stride, sstride);
+            if (M == 3)
+              k_hssp_contrib3<<<(nu + 3) / 4, 128, 0, st>>>(vals, dlist, ctx->mo_tie.as<int32_t>(),
+                                                            ctx->mo_uniq.as<int32_t>(), nu,
+                                                            ctx->mo_removed.as<uint8_t>(), ctx->mo_ref.as<double>(),
+                                                            ctx->mo_state.as<HsspState>(), ctx->mo_contrib.as<double>());
+            else
+              k_hssp_contrib<<<(nu + cthreads - 1) / cthreads, cthreads, csmem, st>>>(
+                  vals, M, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu,
+                  ctx->mo_removed.as<uint8_t>(), ctx->mo_ref.as<double>(), ctx->mo_state.as<HsspState>(),
+                  ctx->mo_contrib.as<double>(), ctx->mo_arena.as<double>(), stride, sstride);
             k_hssp_pick<<<1, 256, 0, st>>>(vals, M, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu,
                                            ctx->mo_removed.as<uint8_t>(), ctx->mo_contrib.as<double>(),
                                            ctx->mo_state.as<HsspState>());
@@ -656,9 +662,16 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
     if (wsmem > 32 * 1024)
       CU(cudaFuncSetAttribute(k_mo_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
     CU(ctx->mo_w.ensure((size_t)kMoMaxSet * 8));
-    k_mo_weights<<<1, kMoMaxSet, wsmem, st>>>(ctx->vals.as<double>(), ctx->M, e.rows.as<int64_t>(), nba,
-                                              ctx->cat.as<int8_t>(), ctx->mo_w.as<double>(), ctx->mo_arena.as<double>(),
-                                              stride, sstride);
+    if (ctx->M == 3) {
+      static const size_t w3smem = (size_t)32 * kHv3Scratch * 8;
+      CU(cudaFuncSetAttribute(k_mo_weights3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w3smem));
+      k_mo_weights3<<<1, 1024, w3smem, st>>>(ctx->vals.as<double>(), e.rows.as<int64_t>(), nba, ctx->cat.as<int8_t>(),
+                                             ctx->mo_w.as<double>());
+    } else {
+      k_mo_weights<<<1, kMoMaxSet, wsmem, st>>>(ctx->vals.as<double>(), ctx->M, e.rows.as<int64_t>(), nba,
+                                                ctx->cat.as<int8_t>(), ctx->mo_w.as<double>(),
+                                                ctx->mo_arena.as<double>(), stride, sstride);
+    }
     ctx->launch_counter++;
     ctx->mo_weights_ready = true;
     w_dev = ctx->mo_w.as<double>();

@@ -260,6 +260,98 @@ struct HsspState {
   int32_t pick[kMoMaxSet];          // tie-local index of the picks
 };
 
+// Warp-cooperative exact 3-D hypervolume of n <= kMoMaxSet + 1 mutually non-dominated points
+// (the assume_pareto branch of hypervolume()), bit-identical to it: the two stable insertion sorts
+// become ranks by counting, every row's inner sum is evaluated by one lane exactly as hv_3d does,
+// and the row terms are added in row order by lane 0.
+//   pts [n,3]; scratch: s [n,3] (rows sorted by x), term [n], ord [n]
+__device__ double hv3_warp(const double* pts, int n, const double* ref, double* s, double* term, int* ord) {
+  const int lane = threadIdx.x & 31;
+  if (!isfinite(ref[0]) || !isfinite(ref[1]) || !isfinite(ref[2])) return INFINITY;
+  if (n == 0) return 0.0;
+  for (int i = lane; i < n; i += 32) {
+    const double x = pts[i * 3];
+    int r = 0;
+    for (int j = 0; j < n; ++j) {
+      const double xj = pts[j * 3];
+      r += (xj < x || (xj == x && j < i)) ? 1 : 0;
+    }
+    s[r * 3] = x;
+    s[r * 3 + 1] = pts[i * 3 + 1];
+    s[r * 3 + 2] = pts[i * 3 + 2];
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const double y = s[i * 3 + 1];
+    int r = 0;
+    for (int j = 0; j < n; ++j) {
+      const double yj = s[j * 3 + 1];
+      r += (yj < y || (yj == y && j < i)) ? 1 : 0;
+    }
+    ord[r] = i;
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const double dx = TPE_SUB(i + 1 < n ? s[(i + 1) * 3] : ref[0], s[i * 3]);
+    double run = 0.0, inner = 0.0;
+    for (int j = 0; j < n; ++j) {
+      const int o = ord[j];
+      if (o <= i) {
+        const double z = TPE_SUB(ref[2], s[o * 3 + 2]);
+        run = z > run ? z : run;
+      }
+      const double dy = TPE_SUB(j + 1 < n ? s[ord[j + 1] * 3 + 1] : ref[1], s[o * 3 + 1]);
+      inner = TPE_ADD(inner, TPE_MUL(run, dy));
+    }
+    term[i] = TPE_MUL(inner, dx);
+  }
+  __syncwarp();
+  double total = 0.0;
+  if (lane == 0)
+    for (int i = 0; i < n; ++i) total = TPE_ADD(total, term[i]);
+  total = __shfl_sync(0xffffffffu, total, 0);
+  __syncwarp();
+  return isfinite(total) ? total : INFINITY;
+}
+constexpr int kHv3Scratch = (kMoMaxSet + 1) * 8;  // doubles per warp: pts 3n + s 3n + term n + ord n/2 (+ slack)
+
+// k_hssp_contrib for three objectives: one warp per remaining candidate.
+__global__ void __launch_bounds__(128)
+k_hssp_contrib3(const double* __restrict__ vals, const int64_t* __restrict__ list,
+                const int32_t* __restrict__ tie_pos, const int32_t* __restrict__ uniq, int nu,
+                const uint8_t* __restrict__ removed, const double* __restrict__ ref,
+                const HsspState* __restrict__ st, double* __restrict__ contrib) {
+  __shared__ double s_scr[4][kHv3Scratch];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int u = blockIdx.x * 4 + w;
+  if (u >= nu) return;
+  if (removed[u]) {
+    if (lane == 0) contrib[u] = -INFINITY;
+    return;
+  }
+  const double* me = vals + list[tie_pos[uniq[u]]] * 3;
+  double incl = 1.0;
+  for (int j = 0; j < 3; ++j) incl = TPE_MUL(incl, TPE_SUB(ref[j], me[j]));
+  const int t = st->n_sel;
+  if (t == 0 || isinf(incl)) {
+    if (lane == 0) contrib[u] = incl;
+    return;
+  }
+  if (isinf(st->hv)) {
+    if (lane == 0) contrib[u] = INFINITY;
+    return;
+  }
+  double* pts = s_scr[w];
+  double* srt = pts + (t + 1) * 3;
+  double* term = srt + (t + 1) * 3;
+  int* ord = reinterpret_cast<int*>(term + (t + 1));
+  for (int q = lane; q < t * 3; q += 32) pts[q] = st->sel[q];
+  if (lane < 3) pts[t * 3 + lane] = me[lane];
+  __syncwarp();
+  const double hv = hv3_warp(pts, t + 1, ref, srt, term, ord);
+  if (lane == 0) contrib[u] = TPE_SUB(hv, st->hv);
+}
+
 // Exact contribution of every remaining unique candidate given the selected set
 // (hssp.py:45-97 evaluated without the lazy skipping, which cannot change the argmax).
 __global__ void k_hssp_contrib(const double* __restrict__ vals, int M, const int64_t* __restrict__ list,
@@ -525,6 +617,103 @@ k_mo_weights(const double* __restrict__ vals, int M, const int64_t* __restrict__
       val = TPE_SUB(incl, hypervolume(pts, c, M, s_ref, false, rest));
     }
     s_contrib[s_front[tid]] = val;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mx = s_contrib[0];
+    for (int i = 1; i < nf; ++i) mx = (s_contrib[i] > mx || s_contrib[i] != s_contrib[i]) ? s_contrib[i] : mx;
+    s_max = fmax(mx, 1e-12);
+  }
+  __syncthreads();
+  if (tid < nf) w[s_map[tid]] = fmax(TPE_DIV(s_contrib[tid], s_max), 1e-12);
+}
+
+// k_mo_weights for three objectives: same result, the Pareto filter is evaluated by one thread per
+// point and every hypervolume by one warp (32 warps: the front's, then the leave-one-out terms).
+__global__ void __launch_bounds__(1024, 1)
+k_mo_weights3(const double* __restrict__ vals, const int64_t* __restrict__ rows, int n,
+              const int8_t* __restrict__ cat, double* __restrict__ w) {
+  constexpr int M = 3;
+  __shared__ double s_v[kMoMaxSet * M];   // feasible points, trial order
+  __shared__ double s_ps[kMoMaxSet * M];  // Pareto points, trial order
+  __shared__ double s_ref[M];
+  __shared__ double s_contrib[kMoMaxSet];
+  __shared__ int s_map[kMoMaxSet];        // feasible index -> below index
+  __shared__ int s_front[kMoMaxSet];      // front index -> feasible index
+  __shared__ uint8_t s_nd[kMoMaxSet];
+  __shared__ int s_nf, s_np;
+  __shared__ double s_hv, s_max;
+  extern __shared__ double s_scr_dyn[];  // 32 warps x kHv3Scratch doubles
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    int nf = 0;
+    for (int i = 0; i < n; ++i) {
+      const bool feas = cat[rows[i]] != 2;
+      w[i] = feas ? 1.0 : 1e-12;
+      if (feas) {
+        for (int j = 0; j < M; ++j) s_v[nf * M + j] = vals[rows[i] * M + j];
+        s_map[nf++] = i;
+      }
+    }
+    s_nf = nf;
+    if (nf > 1) {
+      for (int j = 0; j < M; ++j) {
+        double worst = s_v[j];
+        for (int i = 1; i < nf; ++i) {
+          const double v = s_v[i * M + j];
+          worst = (v > worst || v != v) ? v : worst;
+        }
+        double r = fmax(TPE_MUL(1.1, worst), TPE_MUL(0.9, worst));
+        if (r == 0.0) r = 1e-12;
+        s_ref[j] = r;
+      }
+    }
+  }
+  __syncthreads();
+  const int nf = s_nf;
+  if (nf <= 1) return;
+  if (tid < nf) {
+    bool dom = false;
+    for (int q = 0; q < nf && !dom; ++q) dom = (q != tid) && dominates(s_v + q * M, s_v + tid * M, M);
+    s_nd[tid] = dom ? 0 : 1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int np = 0;
+    for (int i = 0; i < nf; ++i)
+      if (s_nd[i]) {
+        for (int j = 0; j < M; ++j) s_ps[np * M + j] = s_v[i * M + j];
+        s_front[np++] = i;
+      }
+    s_np = np;
+  }
+  if (tid < nf) s_contrib[tid] = 0.0;
+  __syncthreads();
+  const int np = s_np;
+  {
+    double* scr = s_scr_dyn + (size_t)wid * kHv3Scratch;
+    if (wid == 0) {
+      const double hv = hv3_warp(s_ps, np, s_ref, scr, scr + np * 3, reinterpret_cast<int*>(scr + np * 4));
+      if (lane == 0) s_hv = hv;
+    }
+  }
+  __syncthreads();
+  const double hv = s_hv;
+  if (isinf(hv)) return;
+  for (int p = wid; p < np; p += 32) {
+    double* pts = s_scr_dyn + (size_t)wid * kHv3Scratch;
+    const int c = np - 1;
+    for (int q = lane; q < np; q += 32) {
+      if (q == p) continue;
+      const int d = q < p ? q : q - 1;
+      for (int j = 0; j < M; ++j) pts[d * M + j] = s_ps[q * M + j];
+    }
+    __syncwarp();
+    double* srt = pts + c * 3;
+    double* term = srt + c * 3;
+    const double h = hv3_warp(pts, c, s_ref, srt, term, reinterpret_cast<int*>(term + c));
+    if (lane == 0) s_contrib[s_front[p]] = TPE_SUB(hv, h);
+    __syncwarp();
   }
   __syncthreads();
   if (tid == 0) {
