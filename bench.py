@@ -406,7 +406,7 @@ def run_b200(args) -> None:
                     "d2h_bytes_per_step": N_PARAMS * 8 + 16 + 24, "steps": e2e_steps,
                     "path": "B200TPESampler.sample_relative -> ctypes -> tpe_suggest"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": 27461120, "traffic_source": "ncu --set full, profiles/r1_ncu_raw_logpdf_fast_final.txt "
+                         "traffic": 27532800, "traffic_source": "ncu --set full, profiles/r1_ncu_raw_logpdf_mma_final.txt "
                          "(dram__bytes_read.sum + dram__bytes_write.sum of this launch)",
                          "peak_source": peak_src, "kernel": kernel_name,
                          "kernel_ms": k_ms, "algorithmic_bytes": algorithmic_bytes(),
