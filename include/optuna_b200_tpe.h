@@ -135,6 +135,19 @@ int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n
                 const double* w_below, const double* w_above, const double* uniforms,
                 int64_t n_asks, double* out_x, double* out_acq, int64_t* out_best);
 
+/* Optional: start the upload of the uniforms of the NEXT tpe_sample_and_select early (e.g. right
+ * after tpe_prepare, so that the copy overlaps tpe_build).  `count` doubles are copied from
+ * `uniforms` on a side stream; tpe_sample_and_select called with the same pointer and the matching
+ * count then skips its own copy.  Purely a latency hint: no effect on results.  The reference has no
+ * counterpart (its uniforms never leave the host, probability_distributions.py:86-152). */
+int tpe_stage_uniforms(tpe_ctx* ctx, const double* uniforms, int64_t count);
+
+/* Page-locked host memory for buffers handed to tpe_sample_and_select / tpe_suggest (uniforms): a copy
+ * from pinned memory is a true asynchronous DMA, a copy from pageable memory is staged by the host
+ * thread first.  Optional; any host pointer is accepted everywhere. */
+int tpe_host_alloc(tpe_ctx* ctx, size_t bytes, void** out);
+int tpe_host_free(tpe_ctx* ctx, void* p);
+
 /* ---- parity / inspection entry points (used by tests and by custom _parzen_estimator_cls-style
  * consumers, sampler.py:358-359) ------------------------------------------------------------- */
 /* Shapes of the last tpe_prepare / tpe_suggest. */

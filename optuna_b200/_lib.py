@@ -47,6 +47,9 @@ SYMBOLS = {
     "tpe_prepare": (C.c_int, [_P, C.POINTER(Cfg), _P, C.c_int32, C.POINTER(SplitInfo)]),
     "tpe_build": (C.c_int, [_P, _P, _P]),
     "tpe_sample_and_select": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    "tpe_stage_uniforms": (C.c_int, [_P, _P, C.c_int64]),
+    "tpe_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "tpe_host_free": (C.c_int, [_P, _P]),
     "tpe_suggest": (C.c_int, [_P, C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P]),
     "tpe_get_split_info": (C.c_int, [_P, C.POINTER(SplitInfo)]),
     "tpe_get_split": (C.c_int, [_P, _P, _P]),

@@ -88,6 +88,11 @@ struct tpe_ctx {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool above_pending = false;
+  // tpe_suggest uploads the uniforms on a third stream before the split starts
+  cudaStream_t stream3 = nullptr;
+  cudaEvent_t ev_u = nullptr;
+  const double* u_staged = nullptr;
+  int64_t u_staged_count = 0;
   cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;
   std::string err;
@@ -678,14 +683,22 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
   }
   {
     const int nparts = grid_for(K, 2048, ctx->sm_count * 2);
-    CU(e.wpart.ensure((size_t)nparts * 8));
-    k_wraw<<<nparts, 256, 0, st>>>(w_dev, w_pos, n, ctx->cfg.prior_weight, e.w.as<double>(), e.wpart.as<double>());
-    k_wfinal<<<grid_for(k_alloc, 256, ctx->sm_count * 4), 256, 0, st>>>(
-        e.wpart.as<double>(), nparts, n, e.w.as<double>(), e.logw.as<double>(), e.cst_part.as<double>(),
-        e.cst.as<double>(), which == 0 ? e.cdf.as<double>() : nullptr, k_alloc,
-        e.mma ? e.hb.as<double>() : nullptr, e.mma ? e.ckk.as<double>() : nullptr);
-    k_wnorm<<<grid_for(K, 256, ctx->sm_count * 4), 256, 0, st>>>(e.wpart.as<double>(), nparts, K, e.w.as<double>());
-    ctx->launch_counter += 3;
+    if (nparts == 1) {
+      k_weights_one<<<1, 256, 0, st>>>(w_dev, w_pos, n, ctx->cfg.prior_weight, e.w.as<double>(), e.logw.as<double>(),
+                                       e.cst_part.as<double>(), e.cst.as<double>(),
+                                       which == 0 ? e.cdf.as<double>() : nullptr, k_alloc,
+                                       e.mma ? e.hb.as<double>() : nullptr, e.mma ? e.ckk.as<double>() : nullptr);
+      ctx->launch_counter += 1;
+    } else {
+      CU(e.wpart.ensure((size_t)nparts * 8));
+      k_wraw<<<nparts, 256, 0, st>>>(w_dev, w_pos, n, ctx->cfg.prior_weight, e.w.as<double>(), e.wpart.as<double>());
+      k_wfinal<<<grid_for(k_alloc, 256, ctx->sm_count * 4), 256, 0, st>>>(
+          e.wpart.as<double>(), nparts, n, e.w.as<double>(), e.logw.as<double>(), e.cst_part.as<double>(),
+          e.cst.as<double>(), which == 0 ? e.cdf.as<double>() : nullptr, k_alloc,
+          e.mma ? e.hb.as<double>() : nullptr, e.mma ? e.ckk.as<double>() : nullptr);
+      k_wnorm<<<grid_for(K, 256, ctx->sm_count * 4), 256, 0, st>>>(e.wpart.as<double>(), nparts, K, e.w.as<double>());
+      ctx->launch_counter += 3;
+    }
   }
   if (ctx->ncat) {
     k_cat_tables<<<pc, 64, 0, st>>>(ctx->cols.as<ColMeta>(), pc, n, ctx->cfg.prior_weight,
@@ -805,20 +818,17 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
       ctx->last_kernel = cst_mode ? ((fc->nt >= 256) ? "k_logpdf_fast<const,big>" : "k_logpdf_fast<const,small>")
                                   : ((fc->nt >= 256) ? "k_logpdf_fast<pair,big>" : "k_logpdf_fast<pair,small>");
     if (after_main) CU(cudaEventRecord(after_main, st));
-    if (cst_mode) {  // the prior kernel, evaluated exactly, becomes one more partial row
-      k_logpdf_prior<<<(unsigned)((Ct * 32 + 255) / 256), 256, 0, st>>>(
-          ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
-          e.cst.as<double>(), K, e.tab.as<double>(), e.part.as<double2>() + nsplit * ctx->ct_stride);
-      ctx->launch_counter++;
-      nsplit += 1;
-    }
-    e.nsplit = (int)nsplit;
-    // fix-up: exact evaluation for candidates outside [low, high] (rounding of ppf * sigma + mu)
+    // the prior kernel of CONST tables (one more partial row) and the exact fix-up of the candidates
+    // outside [low, high], one launch
     CU(e.fix.ensure((size_t)ctx->ct_stride * 16));
-    k_logpdf_generic<<<dim3((unsigned)((Ct + 127) / 128), 1), 128, 0, st>>>(
+    k_logpdf_prior_fix<<<(unsigned)((Ct * 32 + 255) / 256), 256, 0, st>>>(
         ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
-        e.cst.as<double>(), K, 0, K, e.tab.as<double>(), ctx->oob.as<uint8_t>(), e.fix.as<double2>(), ctx->ct_stride);
+        e.cst.as<double>(), K, e.tab.as<double>(),
+        cst_mode ? e.part.as<double2>() + nsplit * ctx->ct_stride : nullptr, ctx->oob.as<uint8_t>(),
+        e.fix.as<double2>());
     ctx->launch_counter++;
+    if (cst_mode) nsplit += 1;
+    e.nsplit = (int)nsplit;
   } else {
     // pair-parallel generic kernel: grid = (candidates, kernel chunks of 256 * kpt)
     int kpt = 1;
@@ -882,13 +892,15 @@ int tpe_ctx_create(int device, tpe_ctx** out) {
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return TPE_E_CUDA;
   }
   for (auto& e : ctx->ev) cudaEventCreate(&e);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_u, cudaEventDisableTiming);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   *out = ctx;
@@ -900,6 +912,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+  if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
   for (DevBuf* b : {&ctx->cat_dist, &ctx->X, &ctx->cat, &ctx->key, &ctx->vals, &ctx->mo_list, &ctx->mo_alive, &ctx->mo_dom,
                     &ctx->mo_first, &ctx->mo_rank, &ctx->mo_ctr, &ctx->mo_tie, &ctx->mo_ntie, &ctx->mo_lexpos,
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed, &ctx->mo_table,
@@ -914,7 +927,9 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_u) cudaEventDestroy(ctx->ev_u);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1244,7 +1259,12 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   CU(ctx->out_x.ensure((size_t)n_asks * ctx->pc * 8));
   CU(ctx->out_acq.ensure((size_t)n_asks * 8));
   CU(ctx->out_best.ensure((size_t)n_asks * 8));
-  CU(cudaMemcpyAsync(ctx->U.p, uniforms, (size_t)n_asks * per_ask * 8, cudaMemcpyHostToDevice, st));
+  if (ctx->u_staged == uniforms && ctx->u_staged_count == n_asks * per_ask) {
+    CU(cudaStreamWaitEvent(st, ctx->ev_u, 0));  // uploaded by tpe_suggest while the split ran
+  } else {
+    CU(cudaMemcpyAsync(ctx->U.p, uniforms, (size_t)n_asks * per_ask * 8, cudaMemcpyHostToDevice, st));
+  }
+  ctx->u_staged = nullptr;
   const int base_launches = ctx->launch_counter;
 
   CU(cudaEventRecord(ctx->ev[3], st));
@@ -1290,16 +1310,62 @@ int tpe_sample_and_select(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, 
   return sample_select_locked(ctx, uniforms, n_asks, out_x, out_acq, out_best);
 }
 
+int tpe_host_alloc(tpe_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out || bytes == 0) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  *out = nullptr;
+  CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return TPE_OK;
+}
+int tpe_host_free(tpe_ctx* ctx, void* p) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!p) return TPE_OK;
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  CU(cudaFreeHost(p));
+  return TPE_OK;
+}
+
+int tpe_stage_uniforms(tpe_ctx* ctx, const double* uniforms, int64_t count) {
+  if (!ctx || !uniforms || count <= 0) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  ctx->u_staged = nullptr;
+  CU(cudaStreamSynchronize(ctx->stream3));  // a previous, unconsumed staging
+  CU(ctx->U.ensure((size_t)count * 8));
+  CU(cudaMemcpyAsync(ctx->U.p, uniforms, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream3));
+  CU(cudaEventRecord(ctx->ev_u, ctx->stream3));
+  ctx->u_staged = uniforms;
+  ctx->u_staged_count = count;
+  return TPE_OK;
+}
+
 int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols, const double* w_below,
                 const double* w_above, const double* uniforms, int64_t n_asks, double* out_x, double* out_acq,
                 int64_t* out_best) {
   if (!ctx) return TPE_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->u_staged = nullptr;
+  if (cfg && uniforms && n_asks > 0 && n_cols > 0 && cfg->n_candidates > 0) {
+    // every selected column consumes C uniforms, plus C for the kernel choice: the count is known
+    // before the split, so the upload overlaps it
+    const int64_t count = n_asks * (int64_t)cfg->n_candidates * (1 + n_cols);
+    if (set_device(ctx)) return TPE_E_CUDA;
+    CU(ctx->U.ensure((size_t)count * 8));
+    CU(cudaMemcpyAsync(ctx->U.p, uniforms, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream3));
+    CU(cudaEventRecord(ctx->ev_u, ctx->stream3));
+    ctx->u_staged = uniforms;
+    ctx->u_staged_count = count;
+  }
   int rc = prepare_locked(ctx, cfg, cols, n_cols, nullptr);
-  if (rc) return rc;
-  rc = build_locked(ctx, w_below, w_above);
-  if (rc) return rc;
-  return sample_select_locked(ctx, uniforms, n_asks, out_x, out_acq, out_best);
+  if (!rc) rc = build_locked(ctx, w_below, w_above);
+  if (!rc) rc = sample_select_locked(ctx, uniforms, n_asks, out_x, out_acq, out_best);
+  if (ctx->u_staged) {  // an early error left the upload in flight: the caller's buffer must be free on return
+    cudaStreamSynchronize(ctx->stream3);
+    ctx->u_staged = nullptr;
+  }
+  return rc;
 }
 
 int tpe_get_split_info(tpe_ctx* ctx, tpe_split_info* info) {

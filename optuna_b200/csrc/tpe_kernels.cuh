@@ -905,21 +905,93 @@ __global__ void k_logpdf_generic(const double* __restrict__ S, int64_t Ct, const
   part[blockIdx.y * ct_stride + ct] = make_double2(m, s);
 }
 
-// The prior kernel alone (CONST tables leave it out: its sigma differs), one warp per candidate with
-// the lanes over the columns; same cell formula as the generic path, summed by a shuffle tree.
-__global__ void k_logpdf_prior(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols, int32_t pc,
-                               const double* __restrict__ mu, const double* __restrict__ sigma,
-                               const double* __restrict__ cst, int64_t K, const double* __restrict__ tab,
-                               double2* __restrict__ part) {
+// One warp per candidate, after the grid kernel:
+//  * the prior kernel alone (CONST tables leave it out: its sigma differs), lanes over the columns,
+//    same cell formula as the generic path, summed by a shuffle tree -> one more partial row;
+//  * fix-up: a candidate outside [low, high] (rounding of ppf * sigma + mu; flagged by k_sample) is
+//    re-evaluated exactly against every kernel, lanes over the kernels.
+__global__ void k_logpdf_prior_fix(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols,
+                                   int32_t pc, const double* __restrict__ mu, const double* __restrict__ sigma,
+                                   const double* __restrict__ cst, int64_t K, const double* __restrict__ tab,
+                                   double2* __restrict__ part_prior, const uint8_t* __restrict__ oob,
+                                   double2* __restrict__ fix) {
   const int lane = threadIdx.x & 31;
   const int64_t ct = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (ct >= Ct) return;
-  const int64_t k = K - 1;
+  if (part_prior != nullptr) {
+    const int64_t k = K - 1;
+    double acc = 0.0;
+    for (int j = lane; j < pc; j += 32)
+      acc += cell_one_exact(cols[j], S[ct * pc + j], mu[k * pc + j], sigma[k * pc + j], true, tab);
+    acc = warp_sum(acc);
+    if (lane == 0) part_prior[ct] = make_double2(cst[k] + acc, 1.0);
+  }
+  if (oob[ct] != 0) {
+    double m = -INFINITY, s = 0.0;
+    const double* xrow = S + ct * pc;
+    for (int64_t k = lane; k < K; k += 32) {
+      const double L = cst[k] + cell_sum_exact(xrow, mu + k * pc, sigma + k * pc, cols, pc, k == K - 1, tab);
+      lse_push(L, m, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      lse_merge(m2, s2, m, s);
+    }
+    if (lane == 0) fix[ct] = make_double2(m, s);
+  }
+}
+
+// Mixture weights of a small estimator (K <= 2048, i.e. the below set) in ONE launch: the bodies of
+// k_wraw, k_wfinal and k_wnorm with a single CTA (same summation order as their one-part case).
+__global__ void __launch_bounds__(256)
+k_weights_one(const double* __restrict__ w_in, const int64_t* __restrict__ pos, int64_t n, double prior_weight,
+              double* __restrict__ w, double* __restrict__ logw, const double* __restrict__ cst_part,
+              double* __restrict__ cst, double* __restrict__ cdf, int64_t k_alloc, const double* __restrict__ hb,
+              double* __restrict__ ckk) {
+  __shared__ double s_red[8];
+  __shared__ double s_total;
+  const int64_t K = n + 1;
   double acc = 0.0;
-  for (int j = lane; j < pc; j += 32)
-    acc += cell_one_exact(cols[j], S[ct * pc + j], mu[k * pc + j], sigma[k * pc + j], true, tab);
+  for (int64_t k = threadIdx.x; k < K; k += 256) {
+    const double r = raw_weight(w_in, pos, n, k, prior_weight);
+    w[k] = r;
+    acc += r;
+  }
   acc = warp_sum(acc);
-  if (lane == 0) part[ct] = make_double2(cst[k] + acc, 1.0);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += s_red[i];
+    s_total = 0.0 + t;  // k_wfinal adds the (single) part to 0.0
+  }
+  __syncthreads();
+  const double total = s_total;
+  if (cdf != nullptr && threadIdx.x == 0) {
+    double run = 0.0;
+    for (int64_t k = 0; k < K; ++k) {
+      run = TPE_ADD(run, TPE_DIV(w[k], total));
+      cdf[k] = run;
+    }
+    const double last = run;
+    for (int64_t k = 0; k < K; ++k) cdf[k] = TPE_DIV(cdf[k], last);
+  }
+  __syncthreads();
+  for (int64_t k = threadIdx.x; k < k_alloc; k += 256) {
+    if (k < K) {
+      const double v = TPE_DIV(w[k], total);
+      const double lw = log(v);
+      logw[k] = lw;
+      const double c = cst_part[k] + lw;
+      cst[k] = c;
+      if (ckk != nullptr) ckk[k] = (k < K - 1) ? c - hb[k] : -INFINITY;
+      w[k] = v;
+    } else {
+      cst[k] = -INFINITY;
+      if (ckk != nullptr) ckk[k] = -INFINITY;
+    }
+  }
 }
 
 // Generic path, pair-parallel: one CTA = one candidate x (256 * kpt) kernels, one thread evaluates

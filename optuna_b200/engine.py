@@ -58,6 +58,9 @@ class TPEEngine:
     # -- lifecycle -----------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None):
+            for p in getattr(self, "_pinned", []):
+                self._lib.tpe_host_free(self._h, C.c_void_p(p))
+            self._pinned = []
             self._lib.tpe_ctx_destroy(self._h)
             self._h = None
 
@@ -176,6 +179,22 @@ class TPEEngine:
         self._check(self._lib.tpe_sample_and_select(self._h, _ptr(u), int(n_asks), _ptr(x), _ptr(acq), _ptr(best)))
         self._last_asks = n_asks
         return x, acq, best
+
+    def pinned_empty(self, n: int) -> np.ndarray:
+        """float64[n] in page-locked host memory (freed with the engine): copies from it are async DMAs."""
+        p = C.c_void_p()
+        self._check(self._lib.tpe_host_alloc(self._h, C.c_size_t(int(n) * 8), C.byref(p)))
+        if not hasattr(self, "_pinned"):
+            self._pinned = []
+        self._pinned.append(p.value)
+        return np.ctypeslib.as_array((C.c_double * int(n)).from_address(p.value))
+
+    def stage_uniforms(self, uniforms: np.ndarray) -> np.ndarray:
+        """Start uploading the uniforms of the next `sample_and_select` now (latency hint); pass the
+        returned array (same memory) to `sample_and_select`."""
+        u = _f64(uniforms).reshape(-1)
+        self._check(self._lib.tpe_stage_uniforms(self._h, _ptr(u), int(u.size)))
+        return u
 
     def suggest(self, cols: Sequence[int], uniforms, n_asks: int = 1, w_below=None, w_above=None, **cfg):
         c = self._make_cfg(**cfg)

@@ -126,46 +126,75 @@ class _UniformPrefetch:
     next ask, the sampler's generator is still exactly in the state the clone started from (nobody
     else consumed from it) and the same count is needed; the generator is then moved to the clone's
     end state.  Otherwise the speculation is dropped and the uniforms are drawn as usual -- either
-    way the stream is the reference's."""
+    way the stream is the reference's.  With `alloc` (page-locked memory from the engine) the
+    numbers land in one of two alternating pinned buffers, so the upload is an asynchronous DMA."""
 
     MIN_COUNT = 1 << 14  # below this a draw is cheaper than the hand-over
 
-    def __init__(self) -> None:
-        from concurrent.futures import ThreadPoolExecutor
-        self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="tpe-rng")
+    def __init__(self, alloc=None) -> None:
+        self._alloc = alloc
+        self._bufs: list[np.ndarray | None] = [None, None]
+        self._which = 0
         self._clone = np.random.RandomState(0)
-        self._fut = None
-        self._start = None
-        self._n = 0
+        self._job = None           # (start_state, n, buffer index)
+        self._result = None        # (uniforms, end_state)
+        self._pending = False
+        self._go = threading.Event()
+        self._done = threading.Event()
+        self._stop = False
+        self._thread = threading.Thread(target=self._loop, name="tpe-rng", daemon=True)
+        self._thread.start()
 
     @staticmethod
     def _same(a, b) -> bool:
         return a[0] == b[0] and a[2:] == b[2:] and np.array_equal(a[1], b[1])
 
-    def _work(self, n: int):
-        u = self._clone.random_sample(n)
-        return u, self._clone.get_state()
+    def _loop(self) -> None:
+        while True:
+            self._go.wait()
+            self._go.clear()
+            if self._stop:
+                return
+            start, n, bi = self._job
+            self._clone.set_state(start)
+            u = self._clone.random_sample(n)
+            if self._alloc is not None:
+                buf = self._bufs[bi]
+                if buf is None or buf.size < n:
+                    buf = self._bufs[bi] = self._alloc(n)
+                out = buf[:n]
+                out[:] = u
+                u = out
+            self._result = (u, self._clone.get_state())
+            self._done.set()
 
     def take(self, rng: np.random.RandomState, n: int):
-        fut, self._fut = self._fut, None
-        if fut is None:
+        if not self._pending:
             return None
-        u, end = fut.result()
-        if self._n != n or not self._same(rng.get_state(), self._start):
+        self._done.wait()
+        self._pending = False
+        u, end = self._result
+        start, n_job, _ = self._job
+        if n_job != n or not self._same(rng.get_state(), start):
             return None
         rng.set_state(end)
         return u
 
     def launch(self, rng: np.random.RandomState, n: int) -> None:
-        if self._fut is not None:
-            self._fut.result()
-        self._start = rng.get_state()
-        self._clone.set_state(self._start)
-        self._n = n
-        self._fut = self._pool.submit(self._work, n)
+        if self._pending:
+            self._done.wait()
+        self._which ^= 1
+        self._job = (rng.get_state(), n, self._which)
+        self._done.clear()
+        self._pending = True
+        self._go.set()
 
     def close(self) -> None:
-        self._pool.shutdown(wait=True)
+        if self._pending:
+            self._done.wait()
+        self._stop = True
+        self._go.set()
+        self._thread.join(timeout=5)
 
 
 class B200TPESampler(BaseSampler):
@@ -226,6 +255,22 @@ class B200TPESampler(BaseSampler):
     def __setstate__(self, state: dict) -> None:
         self.__dict__.update(state)
         self._lock = threading.RLock()
+
+    def close(self) -> None:
+        """Stop the helper thread and release the device context (both are re-created on demand)."""
+        pf, self._prefetch = getattr(self, "_prefetch", None), None
+        if pf is not None:
+            pf.close()  # before the engine frees the pinned buffers the thread writes into
+        eng, self._engine = getattr(self, "_engine", None), None
+        if eng is not None:
+            eng.close()
+        self._hist = _History()
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
     @staticmethod
     def hyperopt_parameters() -> dict[str, Any]:
@@ -484,13 +529,25 @@ class B200TPESampler(BaseSampler):
         rng = self._rng.rng
         if n < _UniformPrefetch.MIN_COUNT:
             return rng.random_sample(n)
-        if self._prefetch is None:
-            self._prefetch = _UniformPrefetch()
-        u = self._prefetch.take(rng, n)
+        u = self._prefetched_uniforms(search_space)
         if u is None:
             u = rng.random_sample(n)
-        # the next ask most often needs the same count: draw it while the device works on this one
-        self._prefetch.launch(rng, n)
+            # the next ask most often needs the same count: draw it while the device works on this one
+            self._prefetch.launch(rng, n)
+        return u
+
+    def _prefetched_uniforms(self, search_space: dict[str, BaseDistribution],
+                             relaunch: bool = True) -> np.ndarray | None:
+        """The uniforms of this ask if the speculative draw made during the previous ask is valid."""
+        n = self._n_ei_candidates * (1 + len(search_space))
+        if n < _UniformPrefetch.MIN_COUNT:
+            return None
+        if self._prefetch is None:
+            self._prefetch = _UniformPrefetch(self._eng().pinned_empty)
+        rng = self._rng.rng
+        u = self._prefetch.take(rng, n)
+        if u is not None and relaunch:
+            self._prefetch.launch(rng, n)
         return u
 
     def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
@@ -507,6 +564,8 @@ class B200TPESampler(BaseSampler):
             if self._weights is default_weights:
                 # split + estimator builds are queued on the GPU first; the host draws the uniforms
                 # (the reference's RNG stream, ~0.5 ms for 4096 x 33 doubles) while they run
+                # split (one host sync), then the estimator builds are queued; the uniforms were drawn
+                # speculatively during the previous ask (else: drawn now, while the builds run)
                 eng.prepare(cols, **cfg)
                 eng.build()
                 u = self._draw_uniforms(search_space)
