@@ -508,20 +508,32 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
           const int sstride = mo_smem_stride(subset + 1, M);
           const int cthreads = sstride ? 32 : 64;
           const size_t csmem = sstride ? (size_t)cthreads * sstride * 8 : 0;
-          if (!sstride) CU(ctx->mo_arena.ensure((size_t)nu * stride * 8));
+          // more than three objectives: one warp per candidate, a private WFG arena per lane (global memory);
+          // falls back to one thread per candidate when that would need more than 2 GB
+          const size_t nd_lane_stride = hv_lane_doubles(subset, M);
+          const size_t nd_warp_stride = hv_warp_scratch_doubles(subset, M) + 32 * nd_lane_stride;
+          const bool nd_warp = M > 3 && (size_t)nu * nd_warp_stride * 8 <= ((size_t)2 << 30);
+          if (nd_warp) CU(ctx->mo_arena.ensure((size_t)nu * nd_warp_stride * 8));
+          else if (!sstride) CU(ctx->mo_arena.ensure((size_t)nu * stride * 8));
           if (csmem > 48 * 1024)
             CU(cudaFuncSetAttribute(k_hssp_contrib, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
           for (int t = 0; t < subset; ++t) {
-            if (M == 3)
+            if (M == 3) {
               k_hssp_contrib3<<<(nu + 3) / 4, 128, 0, st>>>(vals, dlist, ctx->mo_tie.as<int32_t>(),
                                                             ctx->mo_uniq.as<int32_t>(), nu,
                                                             ctx->mo_removed.as<uint8_t>(), ctx->mo_ref.as<double>(),
                                                             ctx->mo_state.as<HsspState>(), ctx->mo_contrib.as<double>());
-            else
+            } else if (nd_warp) {
+              k_hssp_contrib_nd<<<(nu + 3) / 4, 128, 0, st>>>(
+                  vals, M, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu,
+                  ctx->mo_removed.as<uint8_t>(), ctx->mo_ref.as<double>(), ctx->mo_state.as<HsspState>(),
+                  ctx->mo_contrib.as<double>(), ctx->mo_arena.as<double>(), nd_warp_stride, nd_lane_stride);
+            } else {
               k_hssp_contrib<<<(nu + cthreads - 1) / cthreads, cthreads, csmem, st>>>(
                   vals, M, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu,
                   ctx->mo_removed.as<uint8_t>(), ctx->mo_ref.as<double>(), ctx->mo_state.as<HsspState>(),
                   ctx->mo_contrib.as<double>(), ctx->mo_arena.as<double>(), stride, sstride);
+            }
             k_hssp_pick<<<1, 256, 0, st>>>(vals, M, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu,
                                            ctx->mo_removed.as<uint8_t>(), ctx->mo_contrib.as<double>(),
                                            ctx->mo_state.as<HsspState>());
@@ -672,6 +684,13 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
       CU(cudaFuncSetAttribute(k_mo_weights3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w3smem));
       k_mo_weights3<<<1, 1024, w3smem, st>>>(ctx->vals.as<double>(), e.rows.as<int64_t>(), nba, ctx->cat.as<int8_t>(),
                                              ctx->mo_w.as<double>());
+    } else if (ctx->M > 3) {
+      const size_t lane_stride = hv_lane_doubles(nba + 1, ctx->M);
+      const size_t warp_stride = hv_warp_scratch_doubles(nba + 1, ctx->M) + 32 * lane_stride;
+      CU(ctx->mo_arena.ensure((size_t)32 * warp_stride * 8));
+      k_mo_weights_nd<<<1, 1024, 0, st>>>(ctx->vals.as<double>(), ctx->M, e.rows.as<int64_t>(), nba,
+                                          ctx->cat.as<int8_t>(), ctx->mo_w.as<double>(), ctx->mo_arena.as<double>(),
+                                          warp_stride, lane_stride);
     } else {
       k_mo_weights<<<1, kMoMaxSet, wsmem, st>>>(ctx->vals.as<double>(), ctx->M, e.rows.as<int64_t>(), nba,
                                                 ctx->cat.as<int8_t>(), ctx->mo_w.as<double>(),

@@ -352,6 +352,169 @@ k_hssp_contrib3(const double* __restrict__ vals, const int64_t* __restrict__ lis
   if (lane == 0) contrib[u] = TPE_SUB(hv, st->hv);
 }
 
+// Warp-cooperative exact N-D (M > 3) hypervolume of n <= kMoMaxSet + 1 points, bit-identical to
+// hypervolume(): the lexicographic insertion sort + duplicate removal become ranks by counting, the
+// sequential front sweep becomes "no earlier point is <= in coordinates 1..M-1" (equivalent by
+// transitivity), and the top level of the WFG recursion
+//     HV(S) = incl(last) + sum_i [ incl(i) - HV(front(limit(S_{>i}, i))) ]
+// gives every lane one i: its exclusive part is evaluated by the sequential hv_nd() in a private
+// arena, and lane 0 adds the terms in index order, as the frame loop of hv_nd() does.
+//   pts [n, M] input (not modified); ws: warp scratch, >= 2 n M + 2 n doubles;
+//   lane_arena: private arena of this lane, >= hv_lane_doubles(n, M)
+__host__ __device__ inline size_t hv_lane_doubles(int n, int M) { return hv_arena_doubles(n, M) + (size_t)n * M + 32; }
+__device__ double hv_nd_warp(const double* pts, int n, int M, const double* ref, bool assume_pareto, double* ws,
+                             double* lane_arena) {
+  const int lane = threadIdx.x & 31;
+  for (int j = 0; j < M; ++j)
+    if (!isfinite(ref[j])) return INFINITY;
+  if (n == 0) return 0.0;
+  double* srt = ws;                       // n * M, sorted rows
+  double* s = ws + (size_t)n * M;         // n * M, compacted rows
+  int* flag = reinterpret_cast<int*>(s + (size_t)n * M);   // n ints
+  int* cntp = flag + n;                   // 1 int
+  // stable sort: by all coordinates (+ duplicates flagged) or by coordinate 0 only (assume_pareto)
+  for (int i = lane; i < n; i += 32) {
+    const double* me = pts + (size_t)i * M;
+    int r = 0;
+    bool dup = false;
+    for (int q = 0; q < n; ++q) {
+      const double* o = pts + (size_t)q * M;
+      int c;
+      if (assume_pareto) c = (o[0] < me[0]) ? -1 : ((o[0] > me[0]) ? 1 : 0);
+      else c = lex_cmp(o, me, M);
+      r += (c < 0 || (c == 0 && q < i)) ? 1 : 0;
+      dup = dup || (!assume_pareto && c == 0 && q < i);
+    }
+    for (int j = 0; j < M; ++j) srt[(size_t)r * M + j] = me[j];
+    flag[r] = dup ? 0 : 1;   // keep flag
+  }
+  __syncwarp();
+  int m;
+  if (!assume_pareto) {
+    // front filter on the unique rows: row i survives unless an earlier kept row is <= in coords 1..M-1
+    for (int i = lane; i < n; i += 32) {
+      if (!flag[i]) continue;
+      const double* me = srt + (size_t)i * M;
+      bool killed = false;
+      for (int h = 0; h < i && !killed; ++h) {
+        if (!flag[h]) continue;   // duplicates of an earlier row: the earlier row decides
+        const double* o = srt + (size_t)h * M;
+        bool better = false;
+        for (int j = 1; j < M; ++j) better = better || (me[j] < o[j]);
+        killed = !better;
+      }
+      if (killed) flag[i] = 2;   // dominated (2 keeps the duplicate test of later rows intact)
+    }
+    __syncwarp();
+    if (lane == 0) {
+      int w = 0;
+      for (int i = 0; i < n; ++i) {
+        if (flag[i] != 1) continue;
+        for (int j = 0; j < M; ++j) s[(size_t)w * M + j] = srt[(size_t)i * M + j];
+        ++w;
+      }
+      *cntp = w;
+    }
+    __syncwarp();
+    m = *cntp;
+  } else {
+    for (int q = lane; q < n * M; q += 32) s[q] = srt[q];
+    __syncwarp();
+    m = n;
+  }
+  double total;
+  if (m <= 2) {
+    total = 0.0;
+    if (lane == 0) total = hv_nd(s, m, M, ref, lane_arena);
+    total = __shfl_sync(0xffffffffu, total, 0);
+  } else {
+    double* term = srt;   // reuse: m doubles
+    for (int i = lane; i < m - 1; i += 32) {
+      double incl = 1.0;
+      for (int j = 0; j < M; ++j) incl = TPE_MUL(incl, TPE_SUB(ref[j], s[(size_t)i * M + j]));
+      double* lim = lane_arena;
+      int cnt = m - 1 - i;
+      for (int r = 0; r < cnt; ++r)
+        for (int j = 0; j < M; ++j) {
+          const double a = s[(size_t)i * M + j], b = s[(size_t)(i + 1 + r) * M + j];
+          lim[r * M + j] = a > b ? a : b;
+        }
+      uint8_t* fl = reinterpret_cast<uint8_t*>(lim + (size_t)(m - 1) * M);
+      if (cnt > 3) {
+        uint8_t* mask = fl;
+        uint8_t* alive = fl + m;
+        front_sorted(lim, cnt, M, mask, alive);
+        int w = 0;
+        for (int r = 0; r < cnt; ++r) {
+          if (!mask[r]) continue;
+          if (w != r)
+            for (int j = 0; j < M; ++j) lim[w * M + j] = lim[r * M + j];
+          ++w;
+        }
+        cnt = w;
+      }
+      double* sub = lim + (size_t)(m - 1) * M + (2 * m + 7) / 8 + 1;
+      const double child = hv_nd(lim, cnt, M, ref, sub);
+      term[i] = TPE_SUB(incl, child);
+    }
+    __syncwarp();
+    total = 0.0;
+    if (lane == 0) {
+      double sum = 0.0;
+      for (int i = 0; i < m - 1; ++i) sum = TPE_ADD(sum, term[i]);
+      double last = 1.0;
+      for (int j = 0; j < M; ++j) last = TPE_MUL(last, TPE_SUB(ref[j], s[(size_t)(m - 1) * M + j]));
+      total = TPE_ADD(last, sum);
+    }
+    total = __shfl_sync(0xffffffffu, total, 0);
+  }
+  __syncwarp();
+  return isfinite(total) ? total : INFINITY;
+}
+// scratch doubles per warp for hv_nd_warp incl. the caller's point list
+__host__ __device__ inline size_t hv_warp_scratch_doubles(int n, int M) { return (size_t)3 * n * M + 2 * n + 16; }
+
+// k_hssp_contrib for more than three objectives: one warp per remaining candidate
+// (H({i}) - H(S limited by i), hssp.py:45-97).
+__global__ void __launch_bounds__(128)
+k_hssp_contrib_nd(const double* __restrict__ vals, int M, const int64_t* __restrict__ list,
+                  const int32_t* __restrict__ tie_pos, const int32_t* __restrict__ uniq, int nu,
+                  const uint8_t* __restrict__ removed, const double* __restrict__ ref,
+                  const HsspState* __restrict__ st, double* __restrict__ contrib, double* __restrict__ arena,
+                  size_t warp_stride, size_t lane_stride) {
+  const int lane = threadIdx.x & 31;
+  const int u = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (u >= nu) return;
+  if (removed[u]) {
+    if (lane == 0) contrib[u] = -INFINITY;
+    return;
+  }
+  const double* me = vals + list[tie_pos[uniq[u]]] * M;
+  double incl = 1.0;
+  for (int j = 0; j < M; ++j) incl = TPE_MUL(incl, TPE_SUB(ref[j], me[j]));
+  const int t = st->n_sel;
+  if (t == 0 || isinf(incl)) {
+    if (lane == 0) contrib[u] = incl;
+    return;
+  }
+  if (isinf(st->hv)) {
+    if (lane == 0) contrib[u] = INFINITY;
+    return;
+  }
+  double* wsb = arena + (size_t)u * warp_stride;
+  double* pts = wsb;                         // t * M
+  double* ws = wsb + (size_t)t * M;
+  double* lanes = wsb + hv_warp_scratch_doubles(t, M);
+  for (int q = lane; q < t * M; q += 32) {
+    const int j = q % M;
+    const double b = st->sel[q];
+    pts[q] = me[j] > b ? me[j] : b;
+  }
+  __syncwarp();
+  const double hv = hv_nd_warp(pts, t, M, ref, false, ws, lanes + (size_t)lane * lane_stride);
+  if (lane == 0) contrib[u] = TPE_SUB(incl, hv);
+}
+
 // Exact contribution of every remaining unique candidate given the selected set
 // (hssp.py:45-97 evaluated without the lazy skipping, which cannot change the argmax).
 __global__ void k_hssp_contrib(const double* __restrict__ vals, int M, const int64_t* __restrict__ list,
@@ -713,6 +876,105 @@ k_mo_weights3(const double* __restrict__ vals, const int64_t* __restrict__ rows,
     double* term = srt + c * 3;
     const double h = hv3_warp(pts, c, s_ref, srt, term, reinterpret_cast<int*>(term + c));
     if (lane == 0) s_contrib[s_front[p]] = TPE_SUB(hv, h);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mx = s_contrib[0];
+    for (int i = 1; i < nf; ++i) mx = (s_contrib[i] > mx || s_contrib[i] != s_contrib[i]) ? s_contrib[i] : mx;
+    s_max = fmax(mx, 1e-12);
+  }
+  __syncthreads();
+  if (tid < nf) w[s_map[tid]] = fmax(TPE_DIV(s_contrib[tid], s_max), 1e-12);
+}
+
+// k_mo_weights for more than three objectives: Pareto filter by one thread per point, every
+// hypervolume by one warp (hv_nd_warp); scratch in the global arena (per warp: warp_stride doubles).
+__global__ void __launch_bounds__(1024, 1)
+k_mo_weights_nd(const double* __restrict__ vals, int M, const int64_t* __restrict__ rows, int n,
+                const int8_t* __restrict__ cat, double* __restrict__ w, double* __restrict__ arena,
+                size_t warp_stride, size_t lane_stride) {
+  __shared__ double s_v[kMoMaxSet * kMoMaxM];   // feasible points, trial order
+  __shared__ double s_ps[kMoMaxSet * kMoMaxM];  // Pareto points, trial order
+  __shared__ double s_ref[kMoMaxM];
+  __shared__ double s_contrib[kMoMaxSet];
+  __shared__ int s_map[kMoMaxSet];
+  __shared__ int s_front[kMoMaxSet];
+  __shared__ uint8_t s_nd[kMoMaxSet];
+  __shared__ int s_nf, s_np;
+  __shared__ double s_hv, s_max;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    int nf = 0;
+    for (int i = 0; i < n; ++i) {
+      const bool feas = cat[rows[i]] != 2;
+      w[i] = feas ? 1.0 : 1e-12;
+      if (feas) {
+        for (int j = 0; j < M; ++j) s_v[nf * M + j] = vals[rows[i] * M + j];
+        s_map[nf++] = i;
+      }
+    }
+    s_nf = nf;
+    if (nf > 1) {
+      for (int j = 0; j < M; ++j) {
+        double worst = s_v[j];
+        for (int i = 1; i < nf; ++i) {
+          const double v = s_v[i * M + j];
+          worst = (v > worst || v != v) ? v : worst;
+        }
+        double r = fmax(TPE_MUL(1.1, worst), TPE_MUL(0.9, worst));
+        if (r == 0.0) r = 1e-12;
+        s_ref[j] = r;
+      }
+    }
+  }
+  __syncthreads();
+  const int nf = s_nf;
+  if (nf <= 1) return;
+  if (tid < nf) {
+    bool dom = false;
+    for (int q = 0; q < nf && !dom; ++q) dom = (q != tid) && dominates(s_v + q * M, s_v + tid * M, M);
+    s_nd[tid] = dom ? 0 : 1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int np = 0;
+    for (int i = 0; i < nf; ++i)
+      if (s_nd[i]) {
+        for (int j = 0; j < M; ++j) s_ps[np * M + j] = s_v[i * M + j];
+        s_front[np++] = i;
+      }
+    s_np = np;
+  }
+  if (tid < nf) s_contrib[tid] = 0.0;
+  __syncthreads();
+  const int np = s_np;
+  double* wsb = arena + (size_t)wid * warp_stride;
+  double* pts = wsb;
+  double* ws = wsb + (size_t)np * M;
+  double* lanes = wsb + hv_warp_scratch_doubles(np, M);
+  if (wid == 0) {
+    const double hv = hv_nd_warp(s_ps, np, M, s_ref, true, ws, lanes + (size_t)lane * lane_stride);
+    if (lane == 0) s_hv = hv;
+  }
+  __syncthreads();
+  const double hv = s_hv;
+  if (isinf(hv)) return;
+  for (int p = wid; p < np; p += 32) {
+    double incl = 1.0;
+    for (int j = 0; j < M; ++j) incl = TPE_MUL(incl, TPE_SUB(s_ref[j], s_ps[p * M + j]));
+    const int c = np - 1;
+    for (int q = lane; q < np; q += 32) {
+      if (q == p) continue;
+      const int d = q < p ? q : q - 1;
+      for (int j = 0; j < M; ++j) {
+        const double x = s_ps[q * M + j], y = s_ps[p * M + j];
+        pts[d * M + j] = x > y ? x : y;
+      }
+    }
+    __syncwarp();
+    const double h = hv_nd_warp(pts, c, M, s_ref, false, ws, lanes + (size_t)lane * lane_stride);
+    if (lane == 0) s_contrib[s_front[p]] = TPE_SUB(incl, h);
     __syncwarp();
   }
   __syncthreads();
