@@ -364,6 +364,45 @@ def test_tabulated_discrete_columns(eng, C, offgrid):
     close(eng.logpdf(0, pts), orc.mixture_log_pdf(s.mix_below, pts), 0, 1e-9)
 
 
+@pytest.mark.parametrize("P,n,C,n_below", [(5, 3, 8, 1), (8, 40, 100, 10), (12, 700, 24, 25), (20, 2500, 70, 40),
+                                            (33, 900, 130, 25), (64, 300, 24, 12), (9, 9, 300, 8)])
+def test_tensor_core_kernel_shapes(eng, P, n, C, n_below):
+    """Multivariate, all-continuous spaces go through k_logpdf_mma (P >= 5): ragged P (padding of the
+    k-steps), fewer kernels than one group of 8, padded candidate tiles, log-scaled columns, and the
+    magic-clip off so that sigma is not clamped.  log_pdf against the oracle at 1e-12."""
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(100 + P)
+    specs, params, cols = [], [], []
+    for j in range(P):
+        if j % 4 == 3:
+            specs.append(ParamSpec(kind=0, low=1e-3, high=50.0, log=True))
+            params.append(orc.Param("float", 1e-3, 50.0, None, True))
+            cols.append(np.exp(rs.uniform(np.log(1e-3), np.log(50.0), n)))
+        else:
+            lo, hi = -2.0 - j, 3.0 + 0.5 * j
+            specs.append(ParamSpec(kind=0, low=lo, high=hi))
+            params.append(orc.Param("float", lo, hi))
+            cols.append(rs.uniform(lo, hi, n))
+    X = np.stack(cols, 1)
+    cat = np.zeros(n, np.int8)
+    key = np.stack([rs.normal(size=n), np.zeros(n)], 1)
+    eng.set_space(specs)
+    eng.set_history(X, cat, key)
+    for clip in (True, False):
+        u = draw_uniforms(np.random.RandomState(7), C, 0, P)
+        x, acq, best = eng.suggest(list(range(P)), u, 1, n_below=n_below, n_candidates=C, multivariate=True,
+                                   magic_clip=clip)
+        if P <= 64:
+            assert eng.last_logpdf_kernel().startswith(("k_logpdf_mma", "k_logpdf_fast")), eng.last_logpdf_kernel()
+        smp, ll, lg = eng.get_candidates()
+        s = orc.suggest(X, cat, key, params, list(range(P)), orc.Config(multivariate=True, magic_clip=clip),
+                        n_below, C, np.random.RandomState(7))
+        close(smp, s.samples, 1e-12, 1e-12)
+        close(ll, s.logl, 1e-14, 1e-12)
+        close(lg, s.logg, 1e-14, 1e-12)
+        assert int(best[0]) == s.best
+
+
 def test_categorical_distance_func_tables(eng):
     """categorical_distance_func (parzen_estimator.py:152-160): rows exp(-(d / max d)^2 * coef)."""
     from optuna_b200.engine import ParamSpec
