@@ -867,11 +867,23 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
                                                                  e.dtab.as<double>());
       ctx->launch_counter++;
     }
-    k_logpdf_pairs<<<dim3((unsigned)Ct, (unsigned)nsplit), 256, (size_t)ctx->pc * sizeof(PairCol), st>>>(
-        ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
-        e.cst.as<double>(), K, kpt, e.tab.as<double>(), ctx->dtab_doubles ? e.cls.as<int32_t>() : nullptr,
-        ctx->dtab_doubles ? e.dtab.as<double>() : nullptr, ctx->dtab_doubles ? e.offgrid.as<int>() : nullptr,
-        ctx->oob.as<uint8_t>(), e.part.as<double2>(), ctx->ct_stride);
+    if (K >= 4096) {
+      constexpr int CB = 8;
+      k_logpdf_pairs<CB><<<dim3((unsigned)((Ct + CB - 1) / CB), (unsigned)nsplit), 256,
+                           (size_t)CB * ctx->pc * sizeof(PairCol) + (((size_t)ctx->pc + 7) & ~(size_t)7), st>>>(
+          ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
+          e.cst.as<double>(), K, kpt, e.tab.as<double>(), ctx->dtab_doubles ? e.cls.as<int32_t>() : nullptr,
+          ctx->dtab_doubles ? e.dtab.as<double>() : nullptr, ctx->dtab_doubles ? e.offgrid.as<int>() : nullptr,
+          ctx->oob.as<uint8_t>(), e.part.as<double2>(), ctx->ct_stride);
+    } else {
+      constexpr int CB = 1;
+      k_logpdf_pairs<CB><<<dim3((unsigned)((Ct + CB - 1) / CB), (unsigned)nsplit), 256,
+                           (size_t)CB * ctx->pc * sizeof(PairCol) + (((size_t)ctx->pc + 7) & ~(size_t)7), st>>>(
+          ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
+          e.cst.as<double>(), K, kpt, e.tab.as<double>(), ctx->dtab_doubles ? e.cls.as<int32_t>() : nullptr,
+          ctx->dtab_doubles ? e.dtab.as<double>() : nullptr, ctx->dtab_doubles ? e.offgrid.as<int>() : nullptr,
+          ctx->oob.as<uint8_t>(), e.part.as<double2>(), ctx->ct_stride);
+    }
     ctx->launch_counter++;
     ctx->last_kernel = "k_logpdf_pairs";
     if (after_main) CU(cudaEventRecord(after_main, st));

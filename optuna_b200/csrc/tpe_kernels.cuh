@@ -1010,90 +1010,124 @@ struct PairCol {
   double xv;
   const double* base;
 };
-__global__ void __launch_bounds__(256)
+// CB candidates per CTA: mu / sigma / class of a kernel are loaded once for all of them (CB = 8 for
+// large estimators, CB = 1 for the handful of kernels of l(x), where parallelism matters more)
+template <int CB>
+__global__ void __launch_bounds__(256, 2)
 k_logpdf_pairs(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols, int32_t pc,
                const double* __restrict__ mu, const double* __restrict__ sigma, const double* __restrict__ cst,
                int64_t K, int kpt, const double* __restrict__ tab, const int32_t* __restrict__ cls,
                const double* __restrict__ dtab, const int* __restrict__ offgrid, const uint8_t* __restrict__ oob,
                double2* __restrict__ part, int64_t ct_stride) {
-  extern __shared__ double s_dyn[];  // pc PairCol descriptors
-  __shared__ double s_m[8], s_s[8];
+  extern __shared__ double s_dyn[];  // CB * pc PairCol descriptors, then pc flag bytes
+  __shared__ double s_m[8][CB], s_s[8][CB];
   PairCol* s_col = reinterpret_cast<PairCol*>(s_dyn);
-  const int64_t ct = blockIdx.x;
+  uint8_t* s_need = reinterpret_cast<uint8_t*>(s_col + (size_t)CB * pc);  // 1: mu, 2: sigma, 4: class
+  const int64_t ct0 = (int64_t)blockIdx.x * CB;
   const int64_t k0 = (int64_t)blockIdx.y * 256 * kpt;
   const bool tables_ok = dtab != nullptr && offgrid != nullptr && *offgrid == 0;
-  const bool in_support = oob != nullptr && oob[ct] == 0;
-  for (int j = threadIdx.x; j < pc; j += 256) {
-    const double x = S[ct * pc + j];
-    const ColMeta cm = cols[j];
+  for (int j = threadIdx.x; j < pc; j += 256) s_need[j] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < CB * pc; t += 256) {
+    const int c = t / pc, j = t - c * pc;
+    const int64_t ct = ct0 + c;
     PairCol pcj;
-    pcj.kind = 2; pcj.stride = 0; pcj.gprior = 0; pcj.pad = 0; pcj.xv = x; pcj.base = nullptr;
-    if (cm.cls == COL_CAT) {
-      pcj.kind = 3;
-      pcj.stride = cm.nch;
-      pcj.gprior = cm.nch;
-      pcj.base = tab + cm.tab_off + (int64_t)(cm.nch + 1) * cm.nch + (int)x;
-    } else if (cm.cls == COL_CONT) {
-      if (in_support && cm.klow < cm.khigh) {
-        pcj.kind = 0;
-        pcj.xv = cm.log ? log(x) : x;
+    pcj.kind = 4; pcj.stride = 0; pcj.gprior = 0; pcj.pad = 0; pcj.xv = 0.0; pcj.base = nullptr;  // 4: no candidate
+    if (ct < Ct) {
+      const bool in_support = oob != nullptr && oob[ct] == 0;
+      const double x = S[ct * pc + j];
+      const ColMeta cm = cols[j];
+      pcj.kind = 2;
+      pcj.xv = x;
+      if (cm.cls == COL_CAT) {
+        pcj.kind = 3;
+        pcj.stride = cm.nch;
+        pcj.gprior = cm.nch;
+        pcj.base = tab + cm.tab_off + (int64_t)(cm.nch + 1) * cm.nch + (int)x;
+      } else if (cm.cls == COL_CONT) {
+        if (in_support && cm.klow < cm.khigh) {
+          pcj.kind = 0;
+          pcj.xv = cm.log ? log(x) : x;
+        }
+      } else if (cm.grid > 0 && tables_ok) {
+        int64_t row = -1;
+        if (Ct < cm.grid) {
+          row = ct;  // candidate-indexed table
+        } else {
+          const double h = rint(TPE_DIV(TPE_SUB(x, cm.low), cm.step));
+          if (h >= 0.0 && h < (double)cm.grid && TPE_ADD(cm.low, TPE_MUL(h, cm.step)) == x) row = (int64_t)h;
+        }
+        if (row >= 0) {
+          pcj.kind = 1;
+          pcj.stride = 1;
+          pcj.gprior = cm.grid;
+          pcj.base = dtab + cm.dtab_off + row * (cm.grid + 1);
+        }
       }
-    } else if (cm.grid > 0 && tables_ok) {
-      int64_t row = -1;
-      if (Ct < cm.grid) {
-        row = ct;  // candidate-indexed table
-      } else {
-        const double h = rint(TPE_DIV(TPE_SUB(x, cm.low), cm.step));
-        if (h >= 0.0 && h < (double)cm.grid && TPE_ADD(cm.low, TPE_MUL(h, cm.step)) == x) row = (int64_t)h;
-      }
-      if (row >= 0) {
-        pcj.kind = 1;
-        pcj.stride = 1;
-        pcj.gprior = cm.grid;
-        pcj.base = dtab + cm.dtab_off + row * (cm.grid + 1);
-      }
+      const int need = (pcj.kind == 1) ? 4 : ((pcj.kind == 3) ? 1 : 3);
+      atomicOr(reinterpret_cast<unsigned int*>(s_need) + (j >> 2), (unsigned int)need << (8 * (j & 3)));
     }
-    s_col[j] = pcj;
+    s_col[t] = pcj;
   }
   __syncthreads();
-  double m = -INFINITY, s = 0.0;
+  double m[CB], s[CB];
+#pragma unroll
+  for (int c = 0; c < CB; ++c) {
+    m[c] = -INFINITY;
+    s[c] = 0.0;
+  }
   for (int q = 0; q < kpt; ++q) {
     const int64_t k = k0 + (int64_t)q * 256 + threadIdx.x;
     if (k < K) {
       const bool is_prior = k == K - 1;
       const double* mu_k = mu + k * pc;
       const double* sg_k = sigma + k * pc;
-      double acc = 0.0;
+      double acc[CB];
+#pragma unroll
+      for (int c = 0; c < CB; ++c) acc[c] = 0.0;
       for (int j = 0; j < pc; ++j) {
-        const PairCol c = s_col[j];
-        if (c.kind == 0) {
-          const double z = TPE_DIV(TPE_SUB(c.xv, mu_k[j]), sg_k[j]);
-          acc += TPE_DIV(-TPE_MUL(z, z), 2.0);
-        } else if (c.kind == 1) {
-          acc += c.base[is_prior ? c.gprior : cls[k * pc + j]];
-        } else if (c.kind == 3) {
-          acc += c.base[(int64_t)(is_prior ? c.gprior : (int)mu_k[j]) * c.stride];
-        } else {
-          acc += cell_one_exact(cols[j], c.xv, mu_k[j], sg_k[j], is_prior, tab);
+        const int need = s_need[j];
+        const double mk = (need & 1) ? mu_k[j] : 0.0;
+        const double sk = (need & 2) ? sg_k[j] : 1.0;
+        const int ck = (need & 4) ? cls[k * pc + j] : 0;
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {
+          const PairCol d = s_col[c * pc + j];
+          if (d.kind == 0) {
+            const double z = TPE_DIV(TPE_SUB(d.xv, mk), sk);
+            acc[c] += TPE_DIV(-TPE_MUL(z, z), 2.0);
+          } else if (d.kind == 1) {
+            acc[c] += d.base[is_prior ? d.gprior : ck];
+          } else if (d.kind == 3) {
+            acc[c] += d.base[(int64_t)(is_prior ? d.gprior : (int)mk) * d.stride];
+          } else if (d.kind == 2) {
+            acc[c] += cell_one_exact(cols[j], d.xv, mk, sk, is_prior, tab);
+          }
         }
       }
-      const double L = cst[k] + acc;
-      lse_push(L, m, s);
+      const double ck0 = cst[k];
+#pragma unroll
+      for (int c = 0; c < CB; ++c) lse_push(ck0 + acc[c], m[c], s[c]);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
-    lse_merge(m2, s2, m, s);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    s_m[threadIdx.x >> 5] = m;
-    s_s[threadIdx.x >> 5] = s;
+  for (int c = 0; c < CB; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double m2 = __shfl_xor_sync(0xffffffffu, m[c], o), s2 = __shfl_xor_sync(0xffffffffu, s[c], o);
+      lse_merge(m2, s2, m[c], s[c]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_m[threadIdx.x >> 5][c] = m[c];
+      s_s[threadIdx.x >> 5][c] = s[c];
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) lse_merge(s_m[w], s_s[w], m, s);
-    part[(int64_t)blockIdx.y * ct_stride + ct] = make_double2(m, s);
+  if (threadIdx.x < CB && ct0 + threadIdx.x < Ct) {
+    const int c = threadIdx.x;
+    double mm = s_m[0][c], ss = s_s[0][c];
+    for (int w = 1; w < 8; ++w) lse_merge(s_m[w][c], s_s[w][c], mm, ss);
+    part[(int64_t)blockIdx.y * ct_stride + ct0 + c] = make_double2(mm, ss);
   }
 }
 
