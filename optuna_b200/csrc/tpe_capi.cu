@@ -108,6 +108,7 @@ struct tpe_ctx {
   DevBuf X, cat, key, vals;
   int32_t M = 1;                 // objectives (>= 2: MOTPE)
   std::vector<int8_t> cat_h;     // host mirror of the categories (MOTPE list building)
+  int64_t cat_cnt[4] = {0, 0, 0, 0};  // trials per category (sizes of the split without a read-back)
   int64_t N = 0;
   // MOTPE scratch
   DevBuf mo_list, mo_alive, mo_dom, mo_first, mo_rank, mo_ctr, mo_tie, mo_ntie, mo_lexpos, mo_isdup, mo_sorted,
@@ -343,6 +344,8 @@ int upload_history(tpe_ctx* ctx, const double* X, const int8_t* category, const 
     if (device_src) CU(cudaMemcpy(ctx->cat_h.data() + at, category, (size_t)n, cudaMemcpyDeviceToHost));
     else memcpy(ctx->cat_h.data() + at, category, (size_t)n);
   }
+  if (at == 0) ctx->cat_cnt[0] = ctx->cat_cnt[1] = ctx->cat_cnt[2] = ctx->cat_cnt[3] = 0;
+  for (int64_t i = at; i < total; ++i) ctx->cat_cnt[ctx->cat_h[(size_t)i] & 3]++;
   if (at == 0) ctx->M = 1;  // a fresh history is single-objective until values are supplied
   ctx->N = total;
   ctx->history_set = true;
@@ -1208,8 +1211,34 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
   int64_t counts[3];
-  CU(cudaMemcpyAsync(counts, ctx->counts.p, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  // Without missing parameters the sizes of the two sets follow from the category counts alone
+  // (sampler.py:686-722: whole categories in order, the cut inside one of them), which the host
+  // mirror knows: no read-back, the builds are queued while the split still runs.
+  // TPE_VERIFY_COUNTS=1 reads the device counts back as well and compares.
+  static const bool verify_counts = [] { const char* v = getenv("TPE_VERIFY_COUNTS"); return v && v[0] == '1'; }();
+  const bool predict = !need_rowok && ctx->M < 2 && (int64_t)ctx->cat_h.size() == N;
+  if (predict) {
+    const int64_t* cnt = ctx->cat_cnt;
+    int64_t remaining = std::max<int64_t>(cfg->n_below, 0), below = 0;
+    for (int c = 0; c < 3; ++c) {
+      const int64_t take = std::min(remaining, cnt[c]);
+      below += take;
+      remaining -= take;
+      if (take < cnt[c]) break;
+    }
+    counts[0] = counts[1] = below;
+    counts[2] = N - below;
+  }
+  if (!predict || verify_counts) {
+    int64_t dev[3];
+    CU(cudaMemcpyAsync(dev, ctx->counts.p, sizeof(dev), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (predict && (dev[0] != counts[0] || dev[1] != counts[1] || dev[2] != counts[2]))
+      return fail(ctx, TPE_E_STATE, "split sizes: host prediction (%lld, %lld, %lld) != device (%lld, %lld, %lld)",
+                  (long long)counts[0], (long long)counts[1], (long long)counts[2], (long long)dev[0],
+                  (long long)dev[1], (long long)dev[2]);
+    counts[0] = dev[0]; counts[1] = dev[1]; counts[2] = dev[2];
+  }
   ctx->info.n_below_all = counts[0];
   ctx->info.n_below_obs = counts[1];
   ctx->info.n_above_obs = counts[2];
