@@ -208,8 +208,12 @@ struct MmaInst {
   static void launch(dim3 grid, size_t sm, cudaStream_t st, const void* tab, const double* cst, int64_t Kf,
                      const double2* colprm, const double* xT, int64_t ct_stride, int64_t kps, double skip,
                      double2* part, unsigned long long* gmax) {
+    // near tier: within ln K + 17.5 of the reference max (see LseTier); TPE_TNEAR_DELTA shrinks it for
+    // timing experiments only (the accuracy bound no longer holds)
+    static const double delta = [] { const char* v = getenv("TPE_TNEAR_DELTA"); return v ? atof(v) : 0.0; }();
     k_logpdf_mma<PB, M, KG, NT, TK, ST, MINB, DBG><<<grid, NT, sm, st>>>(static_cast<const double*>(tab), cst, Kf, colprm,
-                                                                   xT, ct_stride, kps, skip, part, gmax);
+                                                                        xT, ct_stride, kps, skip, part, gmax,
+                                                                        skip - 12.5 - delta);
   }
   static cudaError_t prepare() {
     return cudaFuncSetAttribute(k_logpdf_mma<PB, M, KG, NT, TK, ST, MINB, DBG>,

@@ -1523,7 +1523,8 @@ template <int PB, int M, int KG, int NT, int TK, int ST, int MINB, int DBG = 0>
 __global__ void __launch_bounds__(NT, MINB)
 k_logpdf_mma(const double* __restrict__ tabm, const double* __restrict__ ckk, int64_t Kfp,
              const double2* __restrict__ colprm, const double* __restrict__ xT, int64_t ct_stride, int64_t kps,
-             double lse_skip, double2* __restrict__ part, unsigned long long* __restrict__ gmax) {
+             double lse_skip, double2* __restrict__ part, unsigned long long* __restrict__ gmax,
+             double lse_near) {
   static_assert(PB % 8 == 0 && TK % (8 * KG) == 0, "bad tiling");
   constexpr int NI = PB / 4;        // k-steps of the mma chain
   constexpr int CW = 8 * M;         // candidates per warp
@@ -1589,7 +1590,7 @@ k_logpdf_mma(const double* __restrict__ tabm, const double* __restrict__ ckk, in
   LseTier acc[M];
 #pragma unroll
   for (int m = 0; m < M; ++m) acc[m].init();
-  const float lim_skip = (float)lse_skip, lim_near = (float)(lse_skip - 12.5);
+  const float lim_skip = (float)lse_skip, lim_near = (float)lse_near;
 
   for (int t = 0; t < ntiles; ++t) {
     const int st = t % ST;
