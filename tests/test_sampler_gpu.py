@@ -159,3 +159,45 @@ def test_group_decomposed_search_space():
     assert names == [["kind", "x"], ["ya"], ["yb", "zb"]]
     with pytest.raises(ValueError):
         B200TPESampler(group=True)
+
+
+def test_prefetched_uniforms_give_the_same_suggestions():
+    """Asks large enough for the speculative uniform prefetch (>= 16384 uniforms per ask): consecutive
+    sample_relative calls (hits after the first), a foreign draw in between (drop), and close()
+    must all reproduce the suggestions computed from a plain same-seeded RandomState."""
+    from optuna_b200 import B200TPESampler, TPEEngine, mini
+    from optuna_b200.sampler import _UniformPrefetch, _spec_of
+    P, C, n = 16, 1024, 300
+    assert C * (1 + P) >= _UniformPrefetch.MIN_COUNT
+    rs = np.random.RandomState(2)
+    space = {f"x{j:02d}": mini.FloatDistribution(0.0, 1.0) for j in range(P)}
+    names = list(space)
+    X = rs.uniform(0, 1, (n, P))
+    loss = ((X - 0.4) ** 2).sum(1)
+    sampler = B200TPESampler(seed=11, n_ei_candidates=C, multivariate=True)
+    study = mini.create_study(sampler=sampler)
+    study._storage.trials = [mini.FrozenTrial(i, mini.TrialState.COMPLETE, value=float(loss[i]),
+                                              params=dict(zip(names, X[i].tolist())), distributions=space)
+                             for i in range(n)]
+    frozen = mini.FrozenTrial(n, mini.TrialState.RUNNING)
+    got = []
+    for it in range(5):
+        got.append(sampler.sample_relative(study, frozen, space))
+        if it == 2:
+            sampler._rng.rng.random_sample(3)  # someone else consumes from the generator
+    sampler.close()
+    got.append(sampler.sample_relative(study, frozen, space))  # engine and helper thread re-created
+    # the same through the engine with uniforms from a plain RandomState
+    eng = TPEEngine(0)
+    eng.set_space([_spec_of(nm, space[nm], {}) for nm in names])
+    eng.set_history(X, np.zeros(n, np.int8), np.stack([loss, np.zeros(n)], 1))
+    ref_rng = np.random.RandomState(11)
+    n_below = int(sampler._gamma(n))
+    for it in range(6):
+        u = ref_rng.random_sample(C * (1 + P))
+        x, _, _ = eng.suggest(list(range(P)), u, 1, n_below=n_below, n_candidates=C, multivariate=True)
+        assert [got[it][nm] for nm in names] == x[0].tolist(), it
+        if it == 2:
+            ref_rng.random_sample(3)
+    eng.close()
+    sampler.close()
