@@ -142,6 +142,18 @@ int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n
  * counterpart (its uniforms never leave the host, probability_distributions.py:86-152). */
 int tpe_stage_uniforms(tpe_ctx* ctx, const double* uniforms, int64_t count);
 
+/* Device-side uniforms: generate the next `count` outputs of numpy.random.RandomState.random_sample
+ * (MT19937, legacy 53-bit doubles) on the GPU, after discarding `skip` of them, straight into the
+ * buffer tpe_sample_and_select reads -- the exact stream the reference draws on the host
+ * (probability_distributions.py:87,100,138-144), without the host RNG (0.45 ms per config-2 ask) and
+ * without the upload.  key[624] / pos are RandomState.get_state()[1:3].  The following
+ * tpe_sample_and_select must be called with uniforms == NULL and count == n_asks * per_ask.
+ * tpe_rng_state returns the generator state after the (skip + count) draws, for set_state(). */
+int tpe_stage_uniforms_mt19937(tpe_ctx* ctx, const uint32_t* key, int32_t pos, int64_t skip, int64_t count);
+int tpe_rng_state(tpe_ctx* ctx, uint32_t* key_out, int32_t* pos_out);
+/* Inspection: the first `count` staged uniforms (device-generated or uploaded). */
+int tpe_get_uniforms(tpe_ctx* ctx, double* out, int64_t count);
+
 /* Page-locked host memory for buffers handed to tpe_sample_and_select / tpe_suggest (uniforms): a copy
  * from pinned memory is a true asynchronous DMA, a copy from pageable memory is staged by the host
  * thread first.  Optional; any host pointer is accepted everywhere. */

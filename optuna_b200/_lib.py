@@ -48,6 +48,9 @@ SYMBOLS = {
     "tpe_build": (C.c_int, [_P, _P, _P]),
     "tpe_sample_and_select": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     "tpe_stage_uniforms": (C.c_int, [_P, _P, C.c_int64]),
+    "tpe_stage_uniforms_mt19937": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64]),
+    "tpe_rng_state": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
+    "tpe_get_uniforms": (C.c_int, [_P, _P, C.c_int64]),
     "tpe_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),
     "tpe_host_free": (C.c_int, [_P, _P]),
     "tpe_suggest": (C.c_int, [_P, C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P]),

@@ -93,6 +93,8 @@ struct tpe_ctx {
   cudaEvent_t ev_u = nullptr;
   const double* u_staged = nullptr;
   int64_t u_staged_count = 0;
+  bool u_device_rng = false;     // U was filled by k_mt19937_uniform (tpe_stage_uniforms_mt19937)
+  DevBuf mt_state;               // 624 state words + pos
   cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;
   std::string err;
@@ -957,7 +959,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
                     &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
-                    &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
+                    &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
   ctx->est[1].release();
@@ -1310,7 +1312,8 @@ int tpe_build(tpe_ctx* ctx, const double* w_below, const double* w_above) {
 static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x, double* out_acq,
                                 int64_t* out_best) {
   if (!ctx->built) return fail(ctx, TPE_E_STATE, "tpe_build must precede tpe_sample_and_select");
-  if (!uniforms || n_asks <= 0 || !out_x) return fail(ctx, TPE_E_INVALID, "bad sample arguments");
+  if ((!uniforms && !ctx->u_device_rng) || n_asks <= 0 || !out_x)
+    return fail(ctx, TPE_E_INVALID, "bad sample arguments");
   if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;  // est[1] is joined by run_logpdf(ctx, 1)
   cudaStream_t st = ctx->stream;
   const int32_t C = ctx->cfg.n_candidates;
@@ -1323,7 +1326,13 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   CU(ctx->out_x.ensure((size_t)n_asks * ctx->pc * 8));
   CU(ctx->out_acq.ensure((size_t)n_asks * 8));
   CU(ctx->out_best.ensure((size_t)n_asks * 8));
-  if (ctx->u_staged == uniforms && ctx->u_staged_count == n_asks * per_ask) {
+  if (!uniforms) {
+    if (ctx->u_staged_count != n_asks * per_ask)
+      return fail(ctx, TPE_E_INVALID, "device-generated uniforms: %lld staged, %lld needed",
+                  (long long)ctx->u_staged_count, (long long)(n_asks * per_ask));
+    CU(cudaStreamWaitEvent(st, ctx->ev_u, 0));  // generated by tpe_stage_uniforms_mt19937
+    ctx->u_device_rng = false;
+  } else if (ctx->u_staged == uniforms && ctx->u_staged_count == n_asks * per_ask) {
     CU(cudaStreamWaitEvent(st, ctx->ev_u, 0));  // uploaded by tpe_suggest while the split ran
   } else {
     CU(cudaMemcpyAsync(ctx->U.p, uniforms, (size_t)n_asks * per_ask * 8, cudaMemcpyHostToDevice, st));
@@ -1372,6 +1381,53 @@ int tpe_sample_and_select(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, 
   if (!ctx) return TPE_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   return sample_select_locked(ctx, uniforms, n_asks, out_x, out_acq, out_best);
+}
+
+int tpe_stage_uniforms_mt19937(tpe_ctx* ctx, const uint32_t* key, int32_t pos, int64_t skip, int64_t count) {
+  if (!ctx || !key || pos < 0 || pos > 624 || skip < 0 || count <= 0) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  ctx->u_staged = nullptr;
+  ctx->u_device_rng = false;
+  CU(cudaStreamSynchronize(ctx->stream3));
+  CU(ctx->U.ensure((size_t)count * 8));
+  CU(ctx->mt_state.ensure(625 * 4));
+  uint32_t h[625];
+  memcpy(h, key, 624 * 4);
+  h[624] = (uint32_t)pos;
+  CU(cudaMemcpyAsync(ctx->mt_state.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream3));
+  k_mt19937_uniform<<<1, 256, 0, ctx->stream3>>>(ctx->mt_state.as<uint32_t>(),
+                                                 reinterpret_cast<int*>(ctx->mt_state.as<uint32_t>() + 624), skip,
+                                                 count, ctx->U.as<double>());
+  ctx->launch_counter++;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev_u, ctx->stream3));
+  ctx->u_staged_count = count;
+  ctx->u_device_rng = true;
+  return TPE_OK;
+}
+int tpe_rng_state(tpe_ctx* ctx, uint32_t* key_out, int32_t* pos_out) {
+  if (!ctx || !key_out || !pos_out) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  if (!ctx->mt_state.p) return fail(ctx, TPE_E_STATE, "tpe_stage_uniforms_mt19937 must precede tpe_rng_state");
+  uint32_t h[625];
+  CU(cudaMemcpyAsync(h, ctx->mt_state.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream3));
+  CU(cudaStreamSynchronize(ctx->stream3));
+  memcpy(key_out, h, 624 * 4);
+  *pos_out = (int32_t)h[624];
+  return TPE_OK;
+}
+
+int tpe_get_uniforms(tpe_ctx* ctx, double* out, int64_t count) {
+  if (!ctx || !out || count <= 0) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  if ((size_t)count * 8 > ctx->U.cap) return fail(ctx, TPE_E_INVALID, "only %zu uniforms are staged", ctx->U.cap / 8);
+  CU(cudaStreamSynchronize(ctx->stream3));
+  CU(cudaMemcpyAsync(out, ctx->U.p, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TPE_OK;
 }
 
 int tpe_host_alloc(tpe_ctx* ctx, size_t bytes, void** out) {

@@ -1791,6 +1791,95 @@ __global__ void k_finish_logpdf(const double2* __restrict__ part, int ns, int64_
 }
 
 // ================================================================================================
+// MT19937 on the device: the exact stream of numpy.random.RandomState.random_sample
+// (numpy/random/_mt19937.pyx + legacy double: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53), so that
+// the uniforms of an ask never exist on the host (reference: self._rng.rng draws in
+// probability_distributions.py:87,100,138-144).  One CTA: the 624-word state is regenerated block by
+// block (the twist of one block is three data-parallel phases of 227 / 227 / 170 words), tempered in
+// parallel and converted to doubles; the first `skip` doubles are generated and dropped (a rank that
+// owns a later slice of a batch of asks), the next `count` are written.  ~80 ns per block of 312
+// doubles; the final state goes back to the host generator.
+//   key [624] state words (in/out), pos_io: index of the next unused word of the state (624 = exhausted)
+// ================================================================================================
+__global__ void __launch_bounds__(256, 1)
+k_mt19937_uniform(uint32_t* __restrict__ key, int* __restrict__ pos_io, int64_t skip, int64_t count,
+                  double* __restrict__ out) {
+  __shared__ uint32_t mt[624];
+  __shared__ uint32_t tp[624];
+  __shared__ uint32_t carry;  // high part (a >> 5) of a double whose second word is in the next block
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 624; i += 256) mt[i] = key[i];
+  int start = *pos_io;          // first unused word of the current block
+  int64_t gw = 0;               // words consumed so far
+  const int64_t total_words = 2 * (skip + count);
+  __syncthreads();
+  int end_pos = start;
+  while (gw < total_words) {
+    if (start >= 624) {  // regenerate (in-place semantics of the sequential twist)
+      uint32_t v0 = 0, v1 = 0;
+      const int k = tid;
+      if (k < 227) {
+        const uint32_t y = (mt[k] & 0x80000000u) | (mt[k + 1] & 0x7fffffffu);
+        v0 = mt[k + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      __syncthreads();
+      if (k < 227) mt[k] = v0;
+      __syncthreads();
+      if (k < 227) {
+        const int j = 227 + k;
+        const uint32_t y = (mt[j] & 0x80000000u) | (mt[j + 1] & 0x7fffffffu);
+        v1 = mt[j - 227] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      __syncthreads();
+      if (k < 227) mt[227 + k] = v1;
+      __syncthreads();
+      if (k < 170) {
+        const int j = 454 + k;
+        const uint32_t y = (mt[j] & 0x80000000u) | (mt[(j + 1) % 624] & 0x7fffffffu);
+        v0 = mt[j - 227] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      __syncthreads();  // word 623 reads mt[0] (new) -- already final; nobody in this phase reads words >= 454 of others? (j + 1 is)
+      if (k < 170) mt[454 + k] = v0;
+      __syncthreads();
+      start = 0;
+    }
+    for (int i = tid; i < 624; i += 256) {
+      uint32_t y = mt[i];
+      y ^= y >> 11;
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= y >> 18;
+      tp[i] = y;
+    }
+    __syncthreads();
+    const int64_t avail = 624 - start;
+    const int64_t take = (total_words - gw < avail) ? (total_words - gw) : avail;
+    for (int64_t t = tid; t < take; t += 256) {
+      const int64_t w = gw + t;          // global word index; even = first word of a double
+      const int j = start + (int)t;
+      const int64_t d = w >> 1;
+      if ((w & 1) == 0) {
+        if (t + 1 < take) {
+          const uint32_t a = tp[j] >> 5, b = tp[j + 1] >> 6;
+          if (d >= skip) out[d - skip] = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+        } else {
+          carry = tp[j] >> 5;            // second word comes with the next block
+        }
+      } else if (t == 0) {               // completes the double started in the previous block
+        const uint32_t a = carry, b = tp[j] >> 6;
+        if (d >= skip) out[d - skip] = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+      }
+    }
+    gw += take;
+    end_pos = start + (int)take;
+    start = 624;
+    __syncthreads();
+  }
+  for (int i = tid; i < 624; i += 256) key[i] = mt[i];
+  if (tid == 0) *pos_io = end_pos;
+}
+
+// ================================================================================================
 // fp64 FMA peak probe (roofline denominator for the compute-bound grid kernel)
 // ================================================================================================
 __global__ void k_fp64_probe(double* out, int iters) {

@@ -171,14 +171,38 @@ class TPEEngine:
         self._check(self._lib.tpe_build(self._h, _ptr(wb), _ptr(wa)))
 
     def sample_and_select(self, uniforms, n_asks: int = 1):
-        u = _f64(uniforms).reshape(-1)
-        assert u.size == n_asks * self.uniforms_per_ask(), (u.size, n_asks, self.uniforms_per_ask())
+        """uniforms=None: consume the device-generated uniforms of ``stage_rng``."""
+        u = None
+        if uniforms is not None:
+            u = _f64(uniforms).reshape(-1)
+            assert u.size == n_asks * self.uniforms_per_ask(), (u.size, n_asks, self.uniforms_per_ask())
         x = np.empty((n_asks, self._pc), dtype=np.float64)
         acq = np.empty(n_asks, dtype=np.float64)
         best = np.empty(n_asks, dtype=np.int64)
         self._check(self._lib.tpe_sample_and_select(self._h, _ptr(u), int(n_asks), _ptr(x), _ptr(acq), _ptr(best)))
         self._last_asks = n_asks
         return x, acq, best
+
+    def stage_rng(self, rng: np.random.RandomState, count: int, skip: int = 0) -> None:
+        """Generate the next `count` outputs of ``rng.random_sample`` on the device (after dropping
+        `skip`); the following ``sample_and_select(None, n_asks)`` consumes them.  ``finish_rng(rng)``
+        then moves `rng` to the state after the draws."""
+        st = rng.get_state()
+        key = np.ascontiguousarray(st[1], dtype=np.uint32)
+        self._rng_tail = (st[0], st[3], st[4])
+        self._check(self._lib.tpe_stage_uniforms_mt19937(self._h, _ptr(key), int(st[2]), int(skip), int(count)))
+
+    def get_uniforms(self, count: int) -> np.ndarray:
+        out = np.empty(int(count), dtype=np.float64)
+        self._check(self._lib.tpe_get_uniforms(self._h, _ptr(out), int(count)))
+        return out
+
+    def finish_rng(self, rng: np.random.RandomState) -> None:
+        key = np.empty(624, dtype=np.uint32)
+        pos = C.c_int32()
+        self._check(self._lib.tpe_rng_state(self._h, _ptr(key), C.byref(pos)))
+        name, has_gauss, cached = self._rng_tail
+        rng.set_state((name, key, int(pos.value), has_gauss, cached))
 
     def pinned_empty(self, n: int) -> np.ndarray:
         """float64[n] in page-locked host memory (freed with the engine): copies from it are async DMAs."""

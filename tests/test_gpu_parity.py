@@ -470,3 +470,23 @@ def test_univariate_large_history_radix_sorted_bandwidths(eng):
             close(ll, s.logl, 0, tol)
             close(lg, s.logg, 0, tol)
             assert int(best[0]) == s.best
+
+
+@pytest.mark.parametrize("seed,pre,skip,count", [(0, 0, 0, 1000), (1, 7, 0, 311), (2, 623, 5, 313), (3, 100, 4096, 70000),
+                                                 (4, 1249, 0, 1), (5, 311, 311, 312), (6, 0, 0, 135168)])
+def test_device_mt19937_is_numpys_stream(eng, seed, pre, skip, count):
+    """k_mt19937_uniform reproduces RandomState.random_sample bit for bit (state blocks, odd positions,
+    doubles straddling a block boundary, dropped prefix) and returns the generator's end state."""
+    a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+    if pre:
+        a.randint(0, 2 ** 31 - 1, size=pre)  # one 32-bit word each: odd positions inside a block
+        b.randint(0, 2 ** 31 - 1, size=pre)
+    assert np.array_equal(a.get_state()[1], b.get_state()[1]) and a.get_state()[2] == b.get_state()[2]
+    eng.stage_rng(a, count, skip)
+    got = eng.get_uniforms(count)
+    want = b.random_sample(skip + count)[skip:]
+    assert np.array_equal(got, want)
+    eng.finish_rng(a)
+    sa, sb = a.get_state(), b.get_state()
+    assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
+    assert np.array_equal(a.random_sample(5), b.random_sample(5))
