@@ -402,9 +402,12 @@ def run_b200(args) -> None:
                  "span"], stage)},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": per_ask * 8,
-                    "d2h_bytes_per_step": N_PARAMS * 8 + 16 + 24, "steps": e2e_steps,
-                    "path": "B200TPESampler.sample_relative -> ctypes -> tpe_suggest"},
+            # inputs of one ask: the generator state (624 words + position; the uniforms themselves are
+            # produced on the device by the same MT19937), the column list and the config struct
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 625 * 4 + N_PARAMS * 4 + 32,
+                    "d2h_bytes_per_step": N_PARAMS * 8 + 16 + 24 + 625 * 4, "steps": e2e_steps,
+                    "path": "B200TPESampler.sample_relative -> ctypes -> tpe_prepare / tpe_stage_uniforms_mt19937 / "
+                            "tpe_build / tpe_sample_and_select / tpe_rng_state"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": 27532800, "traffic_source": "ncu --set full, profiles/r1_ncu_raw_logpdf_mma_final.txt "
                          "(dram__bytes_read.sum + dram__bytes_write.sum of this launch)",

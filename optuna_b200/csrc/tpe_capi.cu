@@ -94,7 +94,15 @@ struct tpe_ctx {
   const double* u_staged = nullptr;
   int64_t u_staged_count = 0;
   bool u_device_rng = false;     // U was filled by k_mt19937_uniform (tpe_stage_uniforms_mt19937)
-  DevBuf mt_state;               // 624 state words + pos
+  DevBuf mt_state;               // 624 state words + pos: generator state after the staged uniforms
+  // Speculation: while an ask is evaluated, the uniforms of the NEXT ask (same count) are generated from
+  // the end state into U2 / mt_spec.  The next tpe_stage_uniforms_mt19937 adopts them if the caller's
+  // generator is exactly in that state (mt_host, as returned by tpe_rng_state); otherwise they are dropped.
+  DevBuf U2, mt_spec;
+  cudaEvent_t ev_spec = nullptr;
+  bool spec_pending = false, mt_host_valid = false;
+  int64_t spec_count = 0;
+  uint32_t mt_host[625] = {0};   // host copy of mt_state, read back with the results of the ask
   cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;
   std::string err;
@@ -941,6 +949,7 @@ int tpe_ctx_create(int device, tpe_ctx** out) {
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_u, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_spec, cudaEventDisableTiming);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   *out = ctx;
@@ -959,7 +968,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
                     &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
-                    &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
+                    &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->U2, &ctx->mt_spec, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
   ctx->est[1].release();
@@ -968,6 +977,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_u) cudaEventDestroy(ctx->ev_u);
+  if (ctx->ev_spec) cudaEventDestroy(ctx->ev_spec);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
   cudaStreamDestroy(ctx->stream);
@@ -1326,6 +1336,7 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   CU(ctx->out_x.ensure((size_t)n_asks * ctx->pc * 8));
   CU(ctx->out_acq.ensure((size_t)n_asks * 8));
   CU(ctx->out_best.ensure((size_t)n_asks * 8));
+  const bool used_dev_rng = !uniforms;
   if (!uniforms) {
     if (ctx->u_staged_count != n_asks * per_ask)
       return fail(ctx, TPE_E_INVALID, "device-generated uniforms: %lld staged, %lld needed",
@@ -1348,6 +1359,26 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
       ctx->fast ? ctx->xT.as<double>() : nullptr, ctx->ct_stride, ctx->oob.as<uint8_t>());
   ctx->launch_counter++;
   CU(cudaEventRecord(ctx->ev[4], st));
+  if (used_dev_rng) {
+    // speculative draw for the next ask (same count) from the state this ask's draw ended in; runs on
+    // the side stream while the grid kernels of this ask run
+    static const bool spec_on = [] { const char* v = getenv("TPE_RNG_SPECULATE"); return !(v && v[0] == '0'); }();
+    const int64_t count = n_asks * per_ask;
+    if (spec_on) {
+      CU(ctx->U2.ensure((size_t)count * 8));
+      CU(ctx->mt_spec.ensure(625 * 4));
+      CU(cudaMemcpyAsync(ctx->mt_spec.p, ctx->mt_state.p, 625 * 4, cudaMemcpyDeviceToDevice, ctx->stream3));
+      k_mt19937_uniform<<<1, kMtThreads, 0, ctx->stream3>>>(
+          ctx->mt_spec.as<uint32_t>(), reinterpret_cast<int*>(ctx->mt_spec.as<uint32_t>() + 624), 0, count,
+          ctx->U2.as<double>());
+      ctx->launch_counter++;
+      CU(cudaEventRecord(ctx->ev_spec, ctx->stream3));
+      ctx->spec_pending = true;
+      ctx->spec_count = count;
+    }
+    // the generator's end state comes back with the results (tpe_rng_state then needs no device access)
+    CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, st));
+  }
   rc = run_logpdf(ctx, 0, Ct);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->ev[5], st));
@@ -1368,6 +1399,7 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
   if (out_best) CU(cudaMemcpyAsync(out_best, ctx->out_best.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (used_dev_rng) ctx->mt_host_valid = true;
   for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
   cudaEventElapsedTime(&ctx->ms[8], ctx->ev[0], ctx->ev[8]);
   ctx->launches = ctx->launch_counter;
@@ -1389,6 +1421,20 @@ int tpe_stage_uniforms_mt19937(tpe_ctx* ctx, const uint32_t* key, int32_t pos, i
   if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
   ctx->u_staged = nullptr;
   ctx->u_device_rng = false;
+  if (ctx->spec_pending && ctx->mt_host_valid && skip == 0 && count == ctx->spec_count &&
+      (uint32_t)pos == ctx->mt_host[624] && memcmp(key, ctx->mt_host, 624 * 4) == 0) {
+    // the caller's generator is where the previous ask left it: the speculative draw is this ask's
+    std::swap(ctx->U, ctx->U2);
+    std::swap(ctx->mt_state, ctx->mt_spec);
+    std::swap(ctx->ev_u, ctx->ev_spec);
+    ctx->spec_pending = false;
+    ctx->mt_host_valid = false;
+    ctx->u_staged_count = count;
+    ctx->u_device_rng = true;
+    return TPE_OK;
+  }
+  ctx->spec_pending = false;
+  ctx->mt_host_valid = false;
   CU(cudaStreamSynchronize(ctx->stream3));
   CU(ctx->U.ensure((size_t)count * 8));
   CU(ctx->mt_state.ensure(625 * 4));
@@ -1396,7 +1442,7 @@ int tpe_stage_uniforms_mt19937(tpe_ctx* ctx, const uint32_t* key, int32_t pos, i
   memcpy(h, key, 624 * 4);
   h[624] = (uint32_t)pos;
   CU(cudaMemcpyAsync(ctx->mt_state.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream3));
-  k_mt19937_uniform<<<1, 256, 0, ctx->stream3>>>(ctx->mt_state.as<uint32_t>(),
+  k_mt19937_uniform<<<1, kMtThreads, 0, ctx->stream3>>>(ctx->mt_state.as<uint32_t>(),
                                                  reinterpret_cast<int*>(ctx->mt_state.as<uint32_t>() + 624), skip,
                                                  count, ctx->U.as<double>());
   ctx->launch_counter++;
@@ -1411,14 +1457,16 @@ int tpe_rng_state(tpe_ctx* ctx, uint32_t* key_out, int32_t* pos_out) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
   if (!ctx->mt_state.p) return fail(ctx, TPE_E_STATE, "tpe_stage_uniforms_mt19937 must precede tpe_rng_state");
-  uint32_t h[625];
-  CU(cudaMemcpyAsync(h, ctx->mt_state.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream3));
-  CU(cudaStreamSynchronize(ctx->stream3));
-  memcpy(key_out, h, 624 * 4);
-  *pos_out = (int32_t)h[624];
+  if (!ctx->mt_host_valid) {  // not yet read back with the results of an ask
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_u, 0));
+    CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->mt_host_valid = true;
+  }
+  memcpy(key_out, ctx->mt_host, 624 * 4);
+  *pos_out = (int32_t)ctx->mt_host[624];
   return TPE_OK;
 }
-
 int tpe_get_uniforms(tpe_ctx* ctx, double* out, int64_t count) {
   if (!ctx || !out || count <= 0) return TPE_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);

@@ -1801,81 +1801,84 @@ __global__ void k_finish_logpdf(const double2* __restrict__ part, int ns, int64_
 // doubles; the final state goes back to the host generator.
 //   key [624] state words (in/out), pos_io: index of the next unused word of the state (624 = exhausted)
 // ================================================================================================
-__global__ void __launch_bounds__(256, 1)
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
+  const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+  return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+// Two state buffers (ping-pong) and two warp groups: warps 0-7 regenerate block b + 1 from block b in
+// three phases (one 256-thread named barrier each: every "old" read goes to the other buffer) while
+// warps 8-23 temper block b and write its doubles; one CTA-wide barrier per block.
+constexpr int kMtThreads = 768;
+__device__ __forceinline__ void mt_gen_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__global__ void __launch_bounds__(kMtThreads, 1)
 k_mt19937_uniform(uint32_t* __restrict__ key, int* __restrict__ pos_io, int64_t skip, int64_t count,
                   double* __restrict__ out) {
-  __shared__ uint32_t mt[624];
-  __shared__ uint32_t tp[624];
-  __shared__ uint32_t carry;  // high part (a >> 5) of a double whose second word is in the next block
+  __shared__ uint32_t buf[2][624];
+  __shared__ uint32_t carry;  // a >> 5 of a double whose second word is the first word of the next block
   const int tid = threadIdx.x;
-  for (int i = tid; i < 624; i += 256) mt[i] = key[i];
-  int start = *pos_io;          // first unused word of the current block
-  int64_t gw = 0;               // words consumed so far
+  const bool gen = tid < 256;
+  const int wt = tid - 256;     // writer index 0..511
+  for (int i = tid; i < 624; i += kMtThreads) buf[0][i] = key[i];
+  int cur = 0;                  // buffer holding the block the outputs are taken from
+  int start = *pos_io;          // first unused word of that block
+  int64_t gw = 0;               // words consumed before that block's [start, 624) range
   const int64_t total_words = 2 * (skip + count);
-  __syncthreads();
   int end_pos = start;
+  __syncthreads();
   while (gw < total_words) {
-    if (start >= 624) {  // regenerate (in-place semantics of the sequential twist)
-      uint32_t v0 = 0, v1 = 0;
-      const int k = tid;
-      if (k < 227) {
-        const uint32_t y = (mt[k] & 0x80000000u) | (mt[k + 1] & 0x7fffffffu);
-        v0 = mt[k + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    const int64_t avail = 624 - start;
+    const int take = (int)((total_words - gw < avail) ? (total_words - gw) : avail);
+    const bool more = gw + take < total_words;
+    const uint32_t* A = buf[cur];
+    uint32_t* B = buf[cur ^ 1];
+    if (gen) {
+      if (more) {
+        if (tid < 227) B[tid] = mt_twist(A[tid], A[tid + 1], A[tid + 397]);
+        mt_gen_barrier();
+        if (tid < 227) B[227 + tid] = mt_twist(A[227 + tid], A[228 + tid], B[tid]);
+        mt_gen_barrier();
+        if (tid < 170) {
+          const int j = 454 + tid;
+          B[j] = mt_twist(A[j], (j == 623) ? B[0] : A[j + 1], B[j - 227]);
+        }
       }
-      __syncthreads();
-      if (k < 227) mt[k] = v0;
-      __syncthreads();
-      if (k < 227) {
-        const int j = 227 + k;
-        const uint32_t y = (mt[j] & 0x80000000u) | (mt[j + 1] & 0x7fffffffu);
-        v1 = mt[j - 227] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    } else {
+      // words [start, start + take) of A are global words [gw, gw + take); a double = words (2d, 2d + 1)
+      const int odd = (int)(gw & 1);               // the first word completes the previous block's double
+      if (odd && wt == 0 && take > 0) {
+        const int64_t d = gw >> 1;
+        const uint32_t a = carry, b2 = mt_temper(A[start]) >> 6;
+        if (d >= skip) out[d - skip] = ((double)a * 67108864.0 + (double)b2) / 9007199254740992.0;
       }
-      __syncthreads();
-      if (k < 227) mt[227 + k] = v1;
-      __syncthreads();
-      if (k < 170) {
-        const int j = 454 + k;
-        const uint32_t y = (mt[j] & 0x80000000u) | (mt[(j + 1) % 624] & 0x7fffffffu);
-        v0 = mt[j - 227] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      const int pairs = (take - odd) / 2;           // whole doubles inside this block
+      for (int p = wt; p < pairs; p += 512) {
+        const int j = start + odd + 2 * p;
+        const int64_t d = (gw + odd) / 2 + p;
+        const uint32_t a = mt_temper(A[j]) >> 5, b2 = mt_temper(A[j + 1]) >> 6;
+        if (d >= skip) out[d - skip] = ((double)a * 67108864.0 + (double)b2) / 9007199254740992.0;
       }
-      __syncthreads();  // word 623 reads mt[0] (new) -- already final; nobody in this phase reads words >= 454 of others? (j + 1 is)
-      if (k < 170) mt[454 + k] = v0;
-      __syncthreads();
-      start = 0;
-    }
-    for (int i = tid; i < 624; i += 256) {
-      uint32_t y = mt[i];
-      y ^= y >> 11;
-      y ^= (y << 7) & 0x9d2c5680u;
-      y ^= (y << 15) & 0xefc60000u;
-      y ^= y >> 18;
-      tp[i] = y;
     }
     __syncthreads();
-    const int64_t avail = 624 - start;
-    const int64_t take = (total_words - gw < avail) ? (total_words - gw) : avail;
-    for (int64_t t = tid; t < take; t += 256) {
-      const int64_t w = gw + t;          // global word index; even = first word of a double
-      const int j = start + (int)t;
-      const int64_t d = w >> 1;
-      if ((w & 1) == 0) {
-        if (t + 1 < take) {
-          const uint32_t a = tp[j] >> 5, b = tp[j + 1] >> 6;
-          if (d >= skip) out[d - skip] = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
-        } else {
-          carry = tp[j] >> 5;            // second word comes with the next block
-        }
-      } else if (t == 0) {               // completes the double started in the previous block
-        const uint32_t a = carry, b = tp[j] >> 6;
-        if (d >= skip) out[d - skip] = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
-      }
-    }
+    // a trailing first-half word is published after the barrier (its reader, wt == 0 above, is done)
+    if (tid == 256 && take > 0 && ((take - (int)(gw & 1)) & 1)) carry = mt_temper(A[start + take - 1]) >> 5;
     gw += take;
-    end_pos = start + (int)take;
-    start = 624;
+    if (more) {
+      cur ^= 1;
+      start = 0;
+      end_pos = 0;
+    } else {
+      end_pos = start + take;
+    }
     __syncthreads();
   }
-  for (int i = tid; i < 624; i += 256) key[i] = mt[i];
+  for (int i = tid; i < 624; i += kMtThreads) key[i] = buf[cur][i];
   if (tid == 0) *pos_io = end_pos;
 }
 

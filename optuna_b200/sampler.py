@@ -118,85 +118,6 @@ class _History:
         self.groups_last = -1
 
 
-class _UniformPrefetch:
-    """Speculative draw of the NEXT ask's uniforms on a helper thread while the GPU evaluates the
-    current one (MT19937 needs ~0.45 ms for the 4096 x 33 doubles of a config-2 ask).
-
-    The draw is made from a private clone of the sampler's RandomState.  It is used only if, at the
-    next ask, the sampler's generator is still exactly in the state the clone started from (nobody
-    else consumed from it) and the same count is needed; the generator is then moved to the clone's
-    end state.  Otherwise the speculation is dropped and the uniforms are drawn as usual -- either
-    way the stream is the reference's.  With `alloc` (page-locked memory from the engine) the
-    numbers land in one of two alternating pinned buffers, so the upload is an asynchronous DMA."""
-
-    MIN_COUNT = 1 << 14  # below this a draw is cheaper than the hand-over
-
-    def __init__(self, alloc=None) -> None:
-        self._alloc = alloc
-        self._bufs: list[np.ndarray | None] = [None, None]
-        self._which = 0
-        self._clone = np.random.RandomState(0)
-        self._job = None           # (start_state, n, buffer index)
-        self._result = None        # (uniforms, end_state)
-        self._pending = False
-        self._go = threading.Event()
-        self._done = threading.Event()
-        self._stop = False
-        self._thread = threading.Thread(target=self._loop, name="tpe-rng", daemon=True)
-        self._thread.start()
-
-    @staticmethod
-    def _same(a, b) -> bool:
-        return a[0] == b[0] and a[2:] == b[2:] and np.array_equal(a[1], b[1])
-
-    def _loop(self) -> None:
-        while True:
-            self._go.wait()
-            self._go.clear()
-            if self._stop:
-                return
-            start, n, bi = self._job
-            self._clone.set_state(start)
-            u = self._clone.random_sample(n)
-            if self._alloc is not None:
-                buf = self._bufs[bi]
-                if buf is None or buf.size < n:
-                    buf = self._bufs[bi] = self._alloc(n)
-                out = buf[:n]
-                out[:] = u
-                u = out
-            self._result = (u, self._clone.get_state())
-            self._done.set()
-
-    def take(self, rng: np.random.RandomState, n: int):
-        if not self._pending:
-            return None
-        self._done.wait()
-        self._pending = False
-        u, end = self._result
-        start, n_job, _ = self._job
-        if n_job != n or not self._same(rng.get_state(), start):
-            return None
-        rng.set_state(end)
-        return u
-
-    def launch(self, rng: np.random.RandomState, n: int) -> None:
-        if self._pending:
-            self._done.wait()
-        self._which ^= 1
-        self._job = (rng.get_state(), n, self._which)
-        self._done.clear()
-        self._pending = True
-        self._go.set()
-
-    def close(self) -> None:
-        if self._pending:
-            self._done.wait()
-        self._stop = True
-        self._go.set()
-        self._thread.join(timeout=5)
-
-
 class B200TPESampler(BaseSampler):
     def __init__(
         self,
@@ -241,14 +162,12 @@ class B200TPESampler(BaseSampler):
         self._engine: TPEEngine | None = None
         self._hist = _History()
         self._lock = threading.RLock()
-        self._prefetch: _UniformPrefetch | None = None
 
     # -- pickling: device state is a cache re-creatable from the study ----------
     def __getstate__(self) -> dict:
         state = self.__dict__.copy()
         state["_engine"] = None
         state["_hist"] = _History()
-        state["_prefetch"] = None
         del state["_lock"]
         return state
 
@@ -257,10 +176,7 @@ class B200TPESampler(BaseSampler):
         self._lock = threading.RLock()
 
     def close(self) -> None:
-        """Stop the helper thread and release the device context (both are re-created on demand)."""
-        pf, self._prefetch = getattr(self, "_prefetch", None), None
-        if pf is not None:
-            pf.close()  # before the engine frees the pinned buffers the thread writes into
+        """Release the device context (re-created on demand)."""
         eng, self._engine = getattr(self, "_engine", None), None
         if eng is not None:
             eng.close()
@@ -433,12 +349,13 @@ class B200TPESampler(BaseSampler):
             multi = study._is_multi_objective()
             _, nb, na = eng.prepare(cols, **cfg)
             if self._weights is default_weights:
-                eng.build()
+                build = eng.build
             else:
-                eng.build(None if multi else _checked_weights(self._weights, nb), _checked_weights(self._weights, na))
-            # ask-by-ask draws are consecutive stretches of one stream: one call yields the same numbers
-            u = self._rng.rng.random_sample(n_asks * self._n_ei_candidates * (1 + len(search_space)))
-            x, _, _ = eng.sample_and_select(u, n_asks)
+                wb = None if multi else _checked_weights(self._weights, nb)
+                wa = _checked_weights(self._weights, na)
+                build = lambda: eng.build(wb, wa)  # noqa: E731
+            # ask-by-ask draws are consecutive stretches of one stream: one generation yields the same numbers
+            x = self._sample_and_select(eng, search_space, n_asks, build)
         names = list(search_space)
         return [{name: search_space[name].to_external_repr(float(x[a, j])) for j, name in enumerate(names)}
                 for a in range(n_asks)]
@@ -520,35 +437,33 @@ class B200TPESampler(BaseSampler):
         h.n_finished = sum(t.state != TrialState.RUNNING for t in trials) if self._constant_liar else len(trials)
         return h.n_finished, [h.columns[name] for name in search_space]
 
+    #: asks needing at least this many uniforms have them generated on the device
+    DEVICE_RNG_MIN = 4096
+
     def _draw_uniforms(self, search_space: dict[str, BaseDistribution]) -> np.ndarray:
         """The uniforms one reference `_sample` consumes, in its order: C for `rng.choice`, C per
         categorical column, then an (n_numeric, C) block (probability_distributions.py:87,100,138-144).
         `rand`, `choice` and `uniform(0, 1)` all take consecutive `random_sample` outputs unchanged, so
         ONE call yields the identical stream (checked in tests/test_host_glue.py) at half the cost."""
-        n = self._n_ei_candidates * (1 + len(search_space))
-        rng = self._rng.rng
-        if n < _UniformPrefetch.MIN_COUNT:
-            return rng.random_sample(n)
-        u = self._prefetched_uniforms(search_space)
-        if u is None:
-            u = rng.random_sample(n)
-            # the next ask most often needs the same count: draw it while the device works on this one
-            self._prefetch.launch(rng, n)
-        return u
+        return self._rng.rng.random_sample(self._n_ei_candidates * (1 + len(search_space)))
 
-    def _prefetched_uniforms(self, search_space: dict[str, BaseDistribution],
-                             relaunch: bool = True) -> np.ndarray | None:
-        """The uniforms of this ask if the speculative draw made during the previous ask is valid."""
-        n = self._n_ei_candidates * (1 + len(search_space))
-        if n < _UniformPrefetch.MIN_COUNT:
-            return None
-        if self._prefetch is None:
-            self._prefetch = _UniformPrefetch(self._eng().pinned_empty)
+    def _sample_and_select(self, eng: TPEEngine, search_space: dict[str, BaseDistribution], n_asks: int,
+                           build) -> np.ndarray:
+        """Uniforms + stages 3-4.  Large asks: the library generates the generator's next outputs on the
+        GPU (k_mt19937_uniform, the same MT19937 stream bit for bit) while `build()` queues the
+        estimator builds, and the host generator is then moved to the state after the draws; small asks
+        draw on the host."""
+        n = n_asks * self._n_ei_candidates * (1 + len(search_space))
         rng = self._rng.rng
-        u = self._prefetch.take(rng, n)
-        if u is not None and relaunch:
-            self._prefetch.launch(rng, n)
-        return u
+        if n >= self.DEVICE_RNG_MIN:
+            eng.stage_rng(rng, n)
+            build()
+            x, _, _ = eng.sample_and_select(None, n_asks)
+            eng.finish_rng(rng)
+        else:
+            build()
+            x, _, _ = eng.sample_and_select(rng.random_sample(n), n_asks)
+        return x
 
     def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
         """TPESampler._sample (sampler.py:523-560)."""
@@ -562,22 +477,15 @@ class B200TPESampler(BaseSampler):
                                  f" but got {self._prior_weight}.")
             eng = self._eng()
             if self._weights is default_weights:
-                # split + estimator builds are queued on the GPU first; the host draws the uniforms
-                # (the reference's RNG stream, ~0.5 ms for 4096 x 33 doubles) while they run
-                # split (one host sync), then the estimator builds are queued; the uniforms were drawn
-                # speculatively during the previous ask (else: drawn now, while the builds run)
                 eng.prepare(cols, **cfg)
-                eng.build()
-                u = self._draw_uniforms(search_space)
-                x, _, _ = eng.sample_and_select(u, 1)
+                x = self._sample_and_select(eng, search_space, 1, eng.build)
             else:
                 _, nb, na = eng.prepare(cols, **cfg)
                 # multi-objective studies weight l(x) by hypervolume contributions (computed by the
                 # library); the user's weights function then only shapes g(x) (sampler.py:570-584)
                 wb = None if study._is_multi_objective() else _checked_weights(self._weights, nb)
-                eng.build(wb, _checked_weights(self._weights, na))
-                u = self._draw_uniforms(search_space)
-                x, _, _ = eng.sample_and_select(u, 1)
+                wa = _checked_weights(self._weights, na)
+                x = self._sample_and_select(eng, search_space, 1, lambda: eng.build(wb, wa))
         out = {}
         for j, (name, d) in enumerate(search_space.items()):
             out[name] = d.to_external_repr(float(x[0, j]))

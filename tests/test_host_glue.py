@@ -53,24 +53,3 @@ def test_sampler_constructor_contract():
     study = mini.create_study(sampler=B200TPESampler(seed=0, n_startup_trials=5))
     study.optimize(lambda t: t.suggest_float("x", 0, 1) + t.suggest_int("k", 1, 3), n_trials=5)
     assert len(study.trials) == 5 and study.sampler._engine is None
-
-
-def test_uniform_prefetch_keeps_the_reference_stream():
-    """The speculative next-ask draw (sampler._UniformPrefetch) must never change the numbers: hits
-    continue the stream, a foreign draw in between drops the speculation."""
-    from optuna_b200.sampler import _UniformPrefetch
-    r1, r2 = np.random.RandomState(5), np.random.RandomState(5)
-    pf = _UniformPrefetch()
-    n = 40000
-    hits = []
-    for it in range(6):
-        u = pf.take(r1, n if it != 4 else n + 1)
-        hits.append(u is not None)
-        if u is None:
-            u = r1.random_sample(n)
-        pf.launch(r1, n)
-        assert np.array_equal(u, r2.random_sample(n)), it
-        if it == 2:
-            assert np.array_equal(r1.random_sample(7), r2.random_sample(7))
-    pf.close()
-    assert hits == [False, True, True, False, False, True]

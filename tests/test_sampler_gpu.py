@@ -161,14 +161,14 @@ def test_group_decomposed_search_space():
         B200TPESampler(group=True)
 
 
-def test_prefetched_uniforms_give_the_same_suggestions():
-    """Asks large enough for the speculative uniform prefetch (>= 16384 uniforms per ask): consecutive
-    sample_relative calls (hits after the first), a foreign draw in between (drop), and close()
-    must all reproduce the suggestions computed from a plain same-seeded RandomState."""
+def test_device_generated_uniforms_give_the_same_suggestions():
+    """Asks large enough for the device MT19937 (>= DEVICE_RNG_MIN uniforms): consecutive
+    sample_relative calls, a foreign draw in between, and close() must all reproduce the suggestions
+    computed from host-drawn uniforms of a plain same-seeded RandomState."""
     from optuna_b200 import B200TPESampler, TPEEngine, mini
-    from optuna_b200.sampler import _UniformPrefetch, _spec_of
+    from optuna_b200.sampler import _spec_of
     P, C, n = 16, 1024, 300
-    assert C * (1 + P) >= _UniformPrefetch.MIN_COUNT
+    assert C * (1 + P) >= B200TPESampler.DEVICE_RNG_MIN
     rs = np.random.RandomState(2)
     space = {f"x{j:02d}": mini.FloatDistribution(0.0, 1.0) for j in range(P)}
     names = list(space)
@@ -186,8 +186,7 @@ def test_prefetched_uniforms_give_the_same_suggestions():
         if it == 2:
             sampler._rng.rng.random_sample(3)  # someone else consumes from the generator
     sampler.close()
-    got.append(sampler.sample_relative(study, frozen, space))  # engine and helper thread re-created
-    # the same through the engine with uniforms from a plain RandomState
+    got.append(sampler.sample_relative(study, frozen, space))  # engine re-created
     eng = TPEEngine(0)
     eng.set_space([_spec_of(nm, space[nm], {}) for nm in names])
     eng.set_history(X, np.zeros(n, np.int8), np.stack([loss, np.zeros(n)], 1))
@@ -199,5 +198,6 @@ def test_prefetched_uniforms_give_the_same_suggestions():
         assert [got[it][nm] for nm in names] == x[0].tolist(), it
         if it == 2:
             ref_rng.random_sample(3)
+    assert np.array_equal(sampler._rng.rng.random_sample(4), ref_rng.random_sample(4))
     eng.close()
     sampler.close()
