@@ -356,9 +356,15 @@ class B200TPESampler(BaseSampler):
                 build = lambda: eng.build(wb, wa)  # noqa: E731
             # ask-by-ask draws are consecutive stretches of one stream: one generation yields the same numbers
             x = self._sample_and_select(eng, search_space, n_asks, build)
+        # column-wise conversion (FloatDistribution.to_external_repr is the identity): 8192 x 32 values in
+        # a few ms instead of one Python call per value
         names = list(search_space)
-        return [{name: search_space[name].to_external_repr(float(x[a, j])) for j, name in enumerate(names)}
-                for a in range(n_asks)]
+        columns = []
+        for j, name in enumerate(names):
+            d = search_space[name]
+            col = x[:, j].tolist()
+            columns.append(col if isinstance(d, FloatDistribution) else [d.to_external_repr(v) for v in col])
+        return [dict(zip(names, row)) for row in zip(*columns)]
 
     def _rows(self, study, trials, names: list[str], dists: list[BaseDistribution]):
         sign = -1.0 if (not study._is_multi_objective() and study.direction == StudyDirection.MAXIMIZE) else 1.0
