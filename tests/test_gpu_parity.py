@@ -490,3 +490,38 @@ def test_device_mt19937_is_numpys_stream(eng, seed, pre, skip, count):
     sa, sb = a.get_state(), b.get_state()
     assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
     assert np.array_equal(a.random_sample(5), b.random_sample(5))
+
+
+def test_sharded_asks_with_device_uniforms_equal_the_full_batch(eng):
+    """Config-5 semantics with device-generated uniforms: every "rank" starts from the same generator
+    state, drops the uniforms of the earlier ranks' asks (skip) and evaluates its block; the blocks
+    concatenate to the result of one batch drawn on the host."""
+    from optuna_b200.dist import shard_asks
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(4)
+    n, P, C, n_asks = 500, 6, 700, 7          # 700 * 7 = 4900 uniforms per ask
+    X = rs.uniform(0, 1, (n, P))
+    key = np.stack([((X - 0.3) ** 2).sum(1), np.zeros(n)], 1)
+    eng.set_space([ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(P)])
+    eng.set_history(X, np.zeros(n, np.int8), key)
+    cfg = dict(n_below=30, n_candidates=C, multivariate=True)
+    per_ask = C * (1 + P)
+    full_rng = np.random.RandomState(77)
+    want, _, _ = eng.suggest(list(range(P)), full_rng.random_sample(n_asks * per_ask), n_asks, **cfg)
+    got = []
+    for world in (3,):
+        for rank in range(world):
+            start, count = shard_asks(n_asks, world, rank)
+            r = np.random.RandomState(77)
+            eng.prepare(list(range(P)), **cfg)
+            eng.build()
+            eng.stage_rng(r, count * per_ask, skip=start * per_ask)
+            x, _, _ = eng.sample_and_select(None, count)
+            eng.finish_rng(r)
+            got.append(x)
+            tail = (n_asks - start - count) * per_ask
+            if tail:
+                eng.stage_rng(r, 1, skip=tail - 1)
+                eng.finish_rng(r)
+            assert np.array_equal(r.random_sample(3), np.random.RandomState(77).random_sample(n_asks * per_ask + 3)[-3:])
+    assert np.array_equal(np.concatenate(got), want)
