@@ -5,9 +5,11 @@
 //   k_build_mv / k_mu / k_sigma_* / k_const / k_wraw..k_wnorm / k_cat_tables
 //                            optuna/samplers/_tpe/parzen_estimator.py:39-78, :132-251
 //   k_sample                 optuna/samplers/_tpe/probability_distributions.py:86-152
-//   k_logpdf_fast / k_logpdf_generic
+//   k_logpdf_mma (fp64 tensor-core grid, multivariate) / k_logpdf_fast (DFMA grid) /
+//   k_logpdf_pairs + k_disc_tables (mixed spaces) / k_logpdf_generic / k_logpdf_prior_fix
 //                            optuna/samplers/_tpe/probability_distributions.py:154-223,
 //                            optuna/samplers/_tpe/_truncnorm.py:286-297
+//   k_mt19937_uniform        numpy RandomState.random_sample as drawn in probability_distributions.py:87,100,138-144
 //   k_select                 optuna/samplers/_tpe/sampler.py:591-618
 #pragma once
 #include <cooperative_groups.h>

@@ -525,3 +525,30 @@ def test_sharded_asks_with_device_uniforms_equal_the_full_batch(eng):
                 eng.finish_rng(r)
             assert np.array_equal(r.random_sample(3), np.random.RandomState(77).random_sample(n_asks * per_ask + 3)[-3:])
     assert np.array_equal(np.concatenate(got), want)
+
+
+def test_staged_and_pinned_uniforms_change_nothing(eng):
+    """tpe_stage_uniforms / tpe_host_alloc are latency hints: same suggestion as the plain call."""
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(8)
+    n, P, C = 400, 5, 64
+    X = rs.uniform(-1, 1, (n, P))
+    key = np.stack([(X ** 2).sum(1), np.zeros(n)], 1)
+    eng.set_space([ParamSpec(kind=0, low=-1.0, high=1.0) for _ in range(P)])
+    eng.set_history(X, np.zeros(n, np.int8), key)
+    cfg = dict(n_below=20, n_candidates=C, multivariate=True)
+    u = np.random.RandomState(1).random_sample(C * (1 + P))
+    want, wacq, wbest = eng.suggest(list(range(P)), u, 1, **cfg)
+    pinned = eng.pinned_empty(u.size)
+    pinned[:] = u
+    eng.prepare(list(range(P)), **cfg)
+    staged = eng.stage_uniforms(pinned)
+    eng.build()
+    x, acq, best = eng.sample_and_select(staged, 1)
+    assert np.array_equal(x, want) and np.array_equal(acq, wacq) and np.array_equal(best, wbest)
+    # staging one buffer and passing another must fall back to a fresh upload
+    eng.prepare(list(range(P)), **cfg)
+    eng.stage_uniforms(np.zeros(u.size))
+    eng.build()
+    x2, _, _ = eng.sample_and_select(u, 1)
+    assert np.array_equal(x2, want)
