@@ -251,6 +251,8 @@ const FastCfg kMma32Variants[] = {
 };
 
 
+
+
 const FastCfg* pick_mma(int pb, int64_t Ct) {
   const bool small = Ct <= 64;
   if (pb == 32 && !small) {

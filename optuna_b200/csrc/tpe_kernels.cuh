@@ -1486,7 +1486,7 @@ struct LseTier {
     ffar += add;
     if (EXACT && __any_sync(0xffffffffu, any)) {
       // note: terms of this batch that were classified far against the old base stay far (exact
-      // enough by construction) even if a flush inside this loop raises base
+      // enough by construction) even if a flush below raises base
 #pragma unroll
       for (int i = 0; i < N; ++i)
         if (__any_sync(0xffffffffu, near[i])) park(L[i], near[i]);
