@@ -552,3 +552,78 @@ def test_staged_and_pinned_uniforms_change_nothing(eng):
     eng.build()
     x2, _, _ = eng.sample_and_select(u, 1)
     assert np.array_equal(x2, want)
+
+
+def _random_space(rs, P, kinds):
+    from optuna_b200.engine import ParamSpec
+    specs, params, draw = [], [], []
+    for j in range(P):
+        kind = kinds[rs.randint(len(kinds))]
+        if kind == "float":
+            lo = float(rs.uniform(-5, 0)); hi = lo + float(rs.uniform(0.5, 8))
+            specs.append(ParamSpec(kind=0, low=lo, high=hi)); params.append(orc.Param("float", lo, hi))
+            draw.append(lambda n, lo=lo, hi=hi: rs.uniform(lo, hi, n))
+        elif kind == "logfloat":
+            specs.append(ParamSpec(kind=0, low=1e-4, high=10.0, log=True)); params.append(orc.Param("float", 1e-4, 10.0, None, True))
+            draw.append(lambda n: np.exp(rs.uniform(np.log(1e-4), np.log(10.0), n)))
+        elif kind == "stepfloat":
+            specs.append(ParamSpec(kind=0, low=0.0, high=3.0, step=0.25)); params.append(orc.Param("float", 0.0, 3.0, 0.25))
+            draw.append(lambda n: rs.randint(0, 13, n) * 0.25)
+        elif kind == "int":
+            specs.append(ParamSpec(kind=1, low=-3, high=12, step=1)); params.append(orc.Param("int", -3.0, 12.0, 1.0))
+            draw.append(lambda n: rs.randint(-3, 13, n).astype(float))
+        elif kind == "logint":
+            specs.append(ParamSpec(kind=1, low=1, high=200, step=1, log=True)); params.append(orc.Param("int", 1.0, 200.0, 1.0, True))
+            draw.append(lambda n: np.round(np.exp(rs.uniform(0, np.log(200), n))))
+        else:
+            nch = int(rs.randint(2, 7))
+            specs.append(ParamSpec(kind=2, n_choices=nch)); params.append(orc.Param("cat", n_choices=nch))
+            draw.append(lambda n, nch=nch: rs.randint(0, nch, n).astype(float))
+    return specs, params, draw
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_random_spaces_against_the_oracle(eng, case):
+    """Differential test on random spaces: mixed parameter kinds, COMPLETE / PRUNED / infeasible / RUNNING
+    trials, rows lacking a parameter, small and large estimators (the large ones take the 8-candidate
+    tiling of the pair kernel, all-continuous ones the grid kernels), uni- and multivariate."""
+    rs = np.random.RandomState(1000 + case)
+    mv = case % 4 != 3
+    P = int(rs.randint(1, 9)) if mv else 1
+    kinds = [["float", "logfloat"], ["float", "int", "cat"], ["float", "logfloat", "stepfloat", "int", "logint", "cat"],
+             ["float"]][case % 4]
+    n = [60, 900, 5000, 300][case % 4]
+    C = int(rs.choice([8, 24, 100]))
+    specs, params, draw = _random_space(rs, P, kinds)
+    X = np.stack([d(n) for d in draw], 1)
+    if case % 5 == 1 and P > 1:     # some rows lack a parameter
+        X[rs.uniform(size=n) < 0.1, rs.randint(P)] = np.nan
+    cat = np.zeros(n, np.int8)
+    if case % 3 == 0:
+        cat = rs.choice([0, 0, 0, 1, 2, 3], size=n).astype(np.int8)
+    key = np.stack([rs.normal(size=n), rs.normal(size=n) * (cat == 1)], 1)
+    key[cat == 2, 0] = np.abs(key[cat == 2, 0]) + 0.1
+    n_below = int(rs.randint(1, min(40, n)))
+    eng.set_space(specs)
+    eng.set_history(X, cat, key)
+    cols = list(range(P))
+    ncat = sum(p.is_cat for p in params)
+    u = draw_uniforms(np.random.RandomState(case), C, ncat, P - ncat)
+    cfg = dict(n_below=n_below, n_candidates=C, multivariate=mv)
+    x, acq, best = eng.suggest(cols, u, 1, **cfg)
+    smp, ll, lg = eng.get_candidates()
+    s = orc.suggest(X, cat, key, params, cols, orc.Config(multivariate=mv, stable_sort=True), n_below, C,
+                    np.random.RandomState(case))
+    below, above = eng.get_split()
+    ob, keep_b = orc.observations(X, s.below, cols)
+    oa, keep_a = orc.observations(X, s.above, cols)
+    assert np.array_equal(below, s.below[keep_b]) and np.array_equal(above, s.above[keep_a])
+    for j, p in enumerate(params):
+        if p.is_cat or p.step is not None:
+            assert np.array_equal(smp[:, j], s.samples[:, j]), j
+        else:
+            close(smp[:, j], s.samples[:, j], 1e-12, 1e-12)
+    tol = 1e-9 if has_discrete(params) else 1e-12
+    close(ll, s.logl, 1e-14, tol)
+    close(lg, s.logg, 1e-14, tol)
+    assert int(best[0]) == s.best
