@@ -95,6 +95,11 @@ int tpe_history_set(tpe_ctx* ctx, const double* X, const int8_t* category, const
                     int64_t n);
 int tpe_history_append(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key,
                        int64_t n);
+/* Overwrite rows [at_row, at_row + n) in place: a RUNNING trial that has finished keeps its position
+ * (trial-number order) and only changes its category / key / parameters (constant_liar=True,
+ * sampler.py:526-535: RUNNING trials sit in the above set until they complete). */
+int tpe_history_update(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key, int64_t n,
+                       int64_t at_row);
 /* Same, with DEVICE pointers on ctx's device (used after an NCCL broadcast of the history). */
 int tpe_history_set_device(tpe_ctx* ctx, const double* dX, const int8_t* dcategory,
                            const double* dkey, int64_t n, const uint8_t* col_has_missing);

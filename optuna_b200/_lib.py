@@ -40,6 +40,7 @@ SYMBOLS = {
     "tpe_space_set": (C.c_int, [_P, C.POINTER(ParamDesc), C.c_int32, _P, _P]),
     "tpe_history_set": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "tpe_history_append": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
+    "tpe_history_update": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64]),
     "tpe_history_set_device": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     "tpe_history_set_values": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64]),
     "tpe_history_size": (C.c_int64, [_P]),

@@ -1054,6 +1054,33 @@ int tpe_history_append(tpe_ctx* ctx, const double* X, const int8_t* category, co
   return upload_history(ctx, X, category, key, n, ctx->N, false);
 }
 
+int tpe_history_update(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key, int64_t n,
+                       int64_t at_row) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->history_set) return fail(ctx, TPE_E_STATE, "tpe_history_set must precede tpe_history_update");
+  if (n < 0 || at_row < 0 || at_row + n > ctx->N || (n > 0 && (!X || !category || !key)))
+    return fail(ctx, TPE_E_INVALID, "tpe_history_update: rows [%lld, %lld) outside the history of %lld rows",
+                (long long)at_row, (long long)(at_row + n), (long long)ctx->N);
+  if (n == 0) return TPE_OK;
+  if (set_device(ctx)) return TPE_E_CUDA;
+  if ((int64_t)ctx->cat_h.size() != ctx->N)
+    return fail(ctx, TPE_E_STATE, "tpe_history_update needs a host-uploaded history");
+  scan_missing(ctx, X, n);
+  const int64_t P = (int64_t)ctx->space.size();
+  CU(cudaMemcpyAsync(ctx->X.as<double>() + at_row * P, X, (size_t)n * P * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->cat.as<int8_t>() + at_row, category, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->key.as<double>() + at_row * 2, key, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int64_t i = 0; i < n; ++i) {
+    ctx->cat_cnt[ctx->cat_h[(size_t)(at_row + i)] & 3]--;
+    ctx->cat_h[(size_t)(at_row + i)] = category[i];
+    ctx->cat_cnt[category[i] & 3]++;
+  }
+  ctx->prepared = ctx->built = ctx->sampled = false;
+  return TPE_OK;
+}
+
 int tpe_history_set_device(tpe_ctx* ctx, const double* dX, const int8_t* dcategory, const double* dkey, int64_t n,
                            const uint8_t* col_has_missing) {
   if (!ctx) return TPE_E_INVALID;

@@ -116,6 +116,13 @@ class TPEEngine:
         key = _f64(key, (-1, 2))
         self._check(self._lib.tpe_history_append(self._h, _ptr(X), _ptr(cat), _ptr(key), X.shape[0]))
 
+    def update_history(self, X, category, key, at_row: int) -> None:
+        """Overwrite rows [at_row, at_row + n) in place (a RUNNING trial that finished keeps its position)."""
+        X = _f64(X, (-1, self.n_params))
+        cat = np.ascontiguousarray(category, dtype=np.int8).reshape(-1)
+        key = _f64(key, (-1, 2))
+        self._check(self._lib.tpe_history_update(self._h, _ptr(X), _ptr(cat), _ptr(key), X.shape[0], int(at_row)))
+
     def set_values(self, values, at_row: int = 0) -> None:
         """Sign-normalised objective values [n, M] of history rows [at_row, at_row + n) (MOTPE)."""
         v = _f64(values)

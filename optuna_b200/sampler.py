@@ -108,6 +108,8 @@ class _History:
         self.sign = 1.0
         self.token: tuple | None = None
         self.n_finished = 0
+        # constant_liar: position -> trial number of the rows uploaded while the trial was RUNNING
+        self.running: dict[int, int] = {}
         # incremental intersection search space (optuna/search_space/intersection.py:14-55)
         self.inter: dict[str, BaseDistribution] | None = None
         self.inter_n = 0
@@ -396,18 +398,28 @@ class B200TPESampler(BaseSampler):
         return X, cat, key, vals
 
     def _sync(self, study, trial, search_space: dict[str, BaseDistribution]) -> tuple[int, list[int]]:
-        """Bring the device history up to date; returns (#finished trials, device columns)."""
+        """Bring the device history up to date; returns (#finished trials, device columns).
+
+        Rows are kept in trial-number order.  Finished trials are appended as they appear.  With
+        ``constant_liar`` the RUNNING trials (other than the one being sampled) are rows too
+        (sampler.py:526-535); a RUNNING row is re-uploaded in place at every ask (its parameters may still
+        grow) until the trial has finished, so an ask costs O(#running), not O(#trials)."""
         h = self._hist
         eng = self._eng()
         if self._constant_liar:
             states = (TrialState.COMPLETE, TrialState.PRUNED, TrialState.RUNNING)
-            trials = [t for t in study._get_trials(deepcopy=False, states=states, use_cache=False)
-                      if t.number != trial.number]
+            trials = study._get_trials(deepcopy=False, states=states, use_cache=False)
+            for i in range(len(trials) - 1, max(len(trials) - 4097, -1), -1):  # the current trial is recent
+                if trials[i].number == trial.number:
+                    trials = trials[:i] + trials[i + 1:]
+                    break
+            else:
+                trials = [t for t in trials if t.number != trial.number]
         else:
             trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
         token = (getattr(study, "_study_id", None), id(getattr(study, "_storage", None)),
                  tuple(getattr(study, "directions", ())))
-        rebuild = self._constant_liar or h.token != token
+        rebuild = h.token != token
         for name, d in search_space.items():
             j = h.columns.get(name)
             if j is None or h.dists[j] != d:
@@ -415,6 +427,8 @@ class B200TPESampler(BaseSampler):
         if not rebuild:
             if not (h.n <= len(trials) and (h.n == 0 or trials[h.n - 1].number == h.last_number)):
                 rebuild = True
+            elif any(trials[pos].number != num for pos, num in h.running.items()):
+                rebuild = True  # a RUNNING trial disappeared (FAIL): the positions have shifted
         if rebuild:
             names = list(h.columns) if h.token == token else []
             dists = list(h.dists) if h.token == token else []
@@ -432,15 +446,32 @@ class B200TPESampler(BaseSampler):
             eng.set_history(X, cat, key)
             if vals is not None:
                 eng.set_values(vals, 0)
-        elif len(trials) > h.n:
+            h.running = {i: t.number for i, t in enumerate(trials) if t.state == TrialState.RUNNING}
+            h.n_finished = len(trials) - len(h.running)
+        else:
             names = list(h.columns)
-            X, cat, key, vals = self._rows(study, trials[h.n:], names, h.dists)
-            eng.append_history(X, cat, key)
-            if vals is not None:
-                eng.set_values(vals, h.n)
+            for pos in sorted(h.running):  # refresh the rows of trials that were RUNNING at the last ask
+                t = trials[pos]
+                X, cat, key, vals = self._rows(study, [t], names, h.dists)
+                eng.update_history(X, cat, key, pos)
+                if vals is not None:
+                    eng.set_values(vals, pos)
+                if t.state != TrialState.RUNNING:
+                    del h.running[pos]
+                    h.n_finished += 1
+            if len(trials) > h.n:
+                fresh = trials[h.n:]
+                X, cat, key, vals = self._rows(study, fresh, names, h.dists)
+                eng.append_history(X, cat, key)
+                if vals is not None:
+                    eng.set_values(vals, h.n)
+                for i, t in enumerate(fresh):
+                    if t.state == TrialState.RUNNING:
+                        h.running[h.n + i] = t.number
+                    else:
+                        h.n_finished += 1
         h.n = len(trials)
         h.last_number = trials[-1].number if trials else -1
-        h.n_finished = sum(t.state != TrialState.RUNNING for t in trials) if self._constant_liar else len(trials)
         return h.n_finished, [h.columns[name] for name in search_space]
 
     #: asks needing at least this many uniforms have them generated on the device

@@ -201,3 +201,44 @@ def test_device_generated_uniforms_give_the_same_suggestions():
     assert np.array_equal(sampler._rng.rng.random_sample(4), ref_rng.random_sample(4))
     eng.close()
     sampler.close()
+
+
+def test_constant_liar_incremental_rows_equal_a_full_rebuild():
+    """constant_liar=True keeps RUNNING trials as rows that are refreshed in place (tpe_history_update)
+    and promoted when they finish; the suggestions must equal those of a sampler that re-uploads the
+    whole history at every ask -- including out-of-order tells and a failed trial (positions shift)."""
+    from optuna_b200 import B200TPESampler, mini
+
+    def obj(t):
+        x = t.suggest_float("x", -2, 2)
+        k = t.suggest_int("k", 0, 6)
+        return x * x + (k - 3) ** 2
+
+    def scenario(force_rebuild):
+        sampler = B200TPESampler(seed=5, multivariate=True, constant_liar=True, n_startup_trials=5)
+        if force_rebuild:
+            orig = sampler._sync
+
+            def sync(study, trial, space):
+                sampler._hist.token = None
+                return orig(study, trial, space)
+            sampler._sync = sync
+        s = mini.create_study(sampler=sampler)
+        s.optimize(obj, n_trials=10)
+        out = []
+        pending = [s.ask() for _ in range(5)]
+        vals = [obj(t) for t in pending]
+        out += [dict(t.params) for t in pending]
+        s.tell(pending[3], vals[3])                          # out of order
+        s.tell(pending[1], state=mini.TrialState.FAIL)       # disappears from the list
+        more = [s.ask() for _ in range(3)]
+        out += [dict(t.params) for t in more if obj(t) is not None]
+        s.tell(pending[0], vals[0])
+        last = [s.ask() for _ in range(2)]
+        out += [dict(t.params) for t in last if obj(t) is not None]
+        sampler.close()
+        return out
+
+    a, b = scenario(False), scenario(True)
+    assert a == b
+    assert len({tuple(sorted(p.items())) for p in a}) > 5
