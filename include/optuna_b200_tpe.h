@@ -27,7 +27,10 @@
 extern "C" {
 #endif
 
-#define TPE_ABI_VERSION 1
+/* 2: + tpe_history_update, tpe_stage_uniforms, tpe_stage_uniforms_mt19937, tpe_rng_state,
+ *      tpe_get_uniforms, tpe_host_alloc / tpe_host_free; tpe_sample_and_select accepts uniforms == NULL
+ *      after tpe_stage_uniforms_mt19937 */
+#define TPE_ABI_VERSION 2
 
 enum {
   TPE_OK = 0,

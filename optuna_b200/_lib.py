@@ -69,6 +69,9 @@ SYMBOLS = {
 _lib = None
 
 
+ABI_VERSION = 2  # include/optuna_b200_tpe.h TPE_ABI_VERSION
+
+
 def load() -> C.CDLL:
     """Load libtpe_b200.so and bind every declared symbol.  Raises if the library is absent."""
     global _lib
@@ -83,7 +86,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.tpe_abi_version() != 1:
-        raise RuntimeError("libtpe_b200.so ABI version mismatch")
+    if lib.tpe_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libtpe_b200.so has ABI version {lib.tpe_abi_version()}, this package needs {ABI_VERSION}: "
+                           "rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
     _lib = lib
     return lib
