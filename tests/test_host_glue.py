@@ -11,7 +11,7 @@ from tests._util import draw_uniforms
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
-    assert lib.tpe_abi_version() == 1
+    assert lib.tpe_abi_version() == _lib.ABI_VERSION == 2
     import os, re
     hdr = open(os.path.join(os.path.dirname(_lib.LIB_PATH), "..", "include", "optuna_b200_tpe.h")).read()
     declared = set(re.findall(r"\b(tpe_[a-z0-9_]+)\s*\(", hdr)) - {"tpe_ctx"}
