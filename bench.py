@@ -393,6 +393,39 @@ def run_b200(args) -> None:
                                       "suggestions_per_s": n_asks / be,
                                       "path": "B200TPESampler.sample_relative_batch (device MT19937)"}
         bs.close()
+    # ---- config 5: 8192 concurrent asks (default n_ei_candidates = 24) sharded over the ranks -----------
+    # every rank evaluates its block of asks on uniforms its GPU generates from the shared generator state
+    # (MT19937 stream of one sampler consumed sequentially, the reference's semantics); results all-gathered
+    config5 = None
+    if not args.no_extras:
+        from optuna_b200.dist import shard_asks, sharded_asks_device_rng
+        n_asks5, c5 = 8192, 24
+        per_ask5 = c5 * (1 + N_PARAMS)
+        cfg5 = dict(cfg, n_candidates=c5)
+        for rep in range(2):
+            rng5 = np.random.RandomState(6)
+            barrier()
+            t0 = time.perf_counter()
+            eng.prepare(cols, **cfg5)
+            eng.build()
+            if world > 1:
+                res5 = sharded_asks_device_rng(eng, rng5, n_asks5, per_ask5, gather=True)
+            else:
+                eng.stage_rng(rng5, n_asks5 * per_ask5)
+                res5, _, _ = eng.sample_and_select(None, n_asks5)
+                eng.finish_rng(rng5)
+            torch.cuda.synchronize()
+            barrier()
+            dt5 = time.perf_counter() - t0
+        assert res5.shape == (n_asks5, N_PARAMS)
+        if world > 1:
+            t = torch.tensor([dt5], dtype=torch.float64, device=torch.device("cuda", local))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt5 = float(t[0])
+        config5 = {"n_asks": n_asks5, "n_ei_candidates": c5, "ms": dt5 * 1e3, "suggestions_per_s": n_asks5 / dt5,
+                   "asks_per_rank": shard_asks(n_asks5, world, 0)[1],
+                   "path": "tpe_prepare / tpe_build / tpe_stage_uniforms_mt19937(skip) / tpe_sample_and_select per "
+                           "rank + all_gather of the [8192, 32] results"}
     if rank == 0:
         peak, peak_src = measured_peaks()
         k_ms = float(stage[5]) / args.steps  # main log-density kernel under g(x)
@@ -445,6 +478,8 @@ def run_b200(args) -> None:
         }
         if extras:
             line["extras"] = extras
+        if config5:
+            line["config5"] = config5
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(X, loss)
         print(json.dumps(line), flush=True)

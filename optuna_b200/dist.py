@@ -102,29 +102,34 @@ def sharded_asks(n_asks: int, per_ask: int, uniforms, compute: Callable[[np.ndar
 def sharded_asks_device_rng(engine, rng: np.random.RandomState, n_asks: int, per_ask: int, gather: bool = True):
     """Like `sharded_asks`, but no rank ever holds the uniforms on the host: every rank starts from the
     same generator state (shared seed) and the library generates the stream on its GPU, dropping the
-    uniforms of the asks that belong to earlier ranks (`skip`).  Afterwards every rank's `rng` is moved
-    to the state after ALL n_asks draws, as if one process had drawn them.  The engine must have been
-    prepared and built; returns [count or n_asks, P]."""
+    uniforms of the asks that belong to earlier ranks (`skip`).  The rank owning the last block ends in
+    the state after ALL n_asks draws and broadcasts it (2.5 KB), so that every rank's `rng` continues as
+    if one process had drawn everything.  The engine must have been prepared and built; returns
+    [count or n_asks, P]."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(), dist.get_rank()
     start, count = shard_asks(n_asks, world, rank)
-    end_state = rng.get_state()
     if count > 0:
         engine.stage_rng(rng, count * per_ask, skip=start * per_ask)
         mine, _, _ = engine.sample_and_select(None, count)
+        engine.finish_rng(rng)
     else:
         mine = np.zeros((0, engine._pc))
-    # the common end state: advance a clone on rank 0's device would need the tail too; drawing and
-    # discarding on the host is O(n_asks * per_ask) -- instead generate-and-drop the remainder on the device
-    tail = (n_asks - start - count) * per_ask
-    if count > 0:
-        engine.finish_rng(rng)
-    if tail > 0:
-        engine.stage_rng(rng, 1, skip=tail - 1)
-        engine.finish_rng(rng)
-    del end_state
+    # common end state: the last rank with work has it
+    owner = max(r for r in range(world) if shard_asks(n_asks, world, r)[1] > 0) if n_asks > 0 else 0
+    st = rng.get_state()
+    pack = torch.empty(625, dtype=torch.int64)
+    if rank == owner:
+        pack[:624] = torch.from_numpy(np.asarray(st[1], dtype=np.int64))
+        pack[624] = int(st[2])
+    nccl = dist.get_backend() == "nccl"
+    if nccl:
+        pack = pack.cuda()
+    dist.broadcast(pack, src=owner)
+    pack = pack.cpu().numpy()
+    rng.set_state((st[0], pack[:624].astype(np.uint32), int(pack[624]), st[3], st[4]))
     mine = np.asarray(mine, dtype=np.float64).reshape(count, -1)
     if not gather:
         return mine
@@ -132,7 +137,7 @@ def sharded_asks_device_rng(engine, rng: np.random.RandomState, n_asks: int, per
     most = shard_asks(n_asks, world, 0)[1]
     pad = torch.zeros((most, width), dtype=torch.float64)
     pad[:count] = torch.from_numpy(mine)
-    if dist.get_backend() == "nccl":
+    if nccl:
         pad = pad.cuda()
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad)
