@@ -627,3 +627,30 @@ def test_random_spaces_against_the_oracle(eng, case):
     close(ll, s.logl, 1e-14, tol)
     close(lg, s.logg, 1e-14, tol)
     assert int(best[0]) == s.best
+
+
+def test_tensor_core_kernel_with_massive_ties(eng):
+    """Thousands of identical observations: every kernel term of g(x) is within a few units of the max
+    (the exact "near" tier sees all of them, the fp32 "far" tier none), plus a cluster far away that is
+    dropped entirely.  log_pdf must still match the oracle at 1e-12."""
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(12)
+    P, C = 8, 96
+    base = rs.uniform(0.2, 0.8, (5, P))
+    X = np.concatenate([np.repeat(base, 600, axis=0), np.repeat(rs.uniform(0.0, 0.05, (1, P)), 200, axis=0)])
+    n = X.shape[0]
+    key = np.stack([((X - 0.5) ** 2).sum(1) + 1e-9 * np.arange(n), np.zeros(n)], 1)
+    specs = [ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(P)]
+    params = [orc.Param("float", 0.0, 1.0) for _ in range(P)]
+    eng.set_space(specs)
+    eng.set_history(X, np.zeros(n, np.int8), key)
+    u = draw_uniforms(np.random.RandomState(2), C, 0, P)
+    x, acq, best = eng.suggest(list(range(P)), u, 1, n_below=20, n_candidates=C, multivariate=True)
+    assert eng.last_logpdf_kernel().startswith("k_logpdf_mma")
+    smp, ll, lg = eng.get_candidates()
+    s = orc.suggest(X, np.zeros(n, np.int8), key, params, list(range(P)), orc.Config(multivariate=True), 20, C,
+                    np.random.RandomState(2))
+    close(smp, s.samples, 1e-12, 1e-12)
+    close(ll, s.logl, 1e-14, 1e-12)
+    close(lg, s.logg, 1e-14, 1e-12)
+    assert int(best[0]) == s.best
