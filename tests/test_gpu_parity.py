@@ -276,12 +276,13 @@ def test_error_contract(eng):
         eng.set_space([ParamSpec(kind=0, low=2.0, high=1.0)])
 
 
-def test_config3_shape_mixed_64_params_against_oracle(eng):
+@pytest.mark.parametrize("n", [4000, 50_000])
+def test_config3_shape_mixed_64_params_against_oracle(eng, n):
     """BASELINE config 3 layout (24 float + 8 log-float + 8 step-float + 8 int + 4 log-int +
-    12 categorical, multivariate) at N = 4000 so that the oracle finishes in seconds."""
+    12 categorical, multivariate) at N = 4000 and at the full N = 50 000 (chunked oracle)."""
     from optuna_b200.engine import ParamSpec
     rs = np.random.RandomState(0)
-    n, C = 4000, 24
+    C = 24
     specs, params, cols = [], [], []
     for _ in range(24):
         specs.append(ParamSpec(kind=0, low=0.0, high=1.0)); params.append(orc.Param("float", 0.0, 1.0))
@@ -311,7 +312,7 @@ def test_config3_shape_mixed_64_params_against_oracle(eng):
     x, acq, best = eng.suggest(list(range(64)), u, 1, n_below=25, n_candidates=C, multivariate=True)
     smp, ll, lg = eng.get_candidates()
     s = orc.suggest(X, cat, key, params, list(range(64)), orc.Config(multivariate=True), 25, C,
-                    np.random.RandomState(9))
+                    np.random.RandomState(9), chunk_rows=2 if n > 10_000 else None)
     for j, p in enumerate(params):
         if p.is_cat or p.step is not None:
             assert np.array_equal(smp[:, j], s.samples[:, j]), j
