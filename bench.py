@@ -362,6 +362,9 @@ def run_b200(args) -> None:
         ucfg = dict(cfg, multivariate=False)
         ru = np.random.RandomState(5)
         for rep in range(2):
+            # a new trial = a new history version (zero-row append): the split is shared by the 32 calls
+            # of one trial, never across trials
+            eng.append_history(np.zeros((0, N_PARAMS)), np.zeros(0, np.int8), np.zeros((0, 2)))
             t0 = time.perf_counter()
             for j in range(N_PARAMS):
                 eng.suggest([j], ru.random_sample(N_CAND * 2), 1, **ucfg)
