@@ -1834,6 +1834,39 @@ k_mt19937_uniform(uint32_t* __restrict__ key, int* __restrict__ pos_io, int64_t 
   const int64_t total_words = 2 * (skip + count);
   int end_pos = start;
   __syncthreads();
+  // blocks that lie entirely inside the dropped prefix: the generator warps alone walk the recurrence
+  // (three named barriers per block), the writers rejoin at the first block that is needed
+  {
+    const int64_t drop_words = 2 * skip;
+    int blocks = 0;
+    if (gw + (624 - start) <= drop_words && gw + (624 - start) < total_words) {
+      blocks = 1 + (int)((drop_words - (gw + (624 - start))) / 624);
+      // the block reached after `blocks` regenerations must still be needed
+      while (blocks > 0 && gw + (624 - start) + (int64_t)(blocks - 1) * 624 >= total_words) --blocks;
+    }
+    if (blocks > 0) {
+      if (gen) {
+        for (int bl = 0; bl < blocks; ++bl) {
+          const uint32_t* A = buf[(cur + bl) & 1];
+          uint32_t* B = buf[(cur + bl + 1) & 1];
+          if (tid < 227) B[tid] = mt_twist(A[tid], A[tid + 1], A[tid + 397]);
+          mt_gen_barrier();
+          if (tid < 227) B[227 + tid] = mt_twist(A[227 + tid], A[228 + tid], B[tid]);
+          mt_gen_barrier();
+          if (tid < 170) {
+            const int j = 454 + tid;
+            B[j] = mt_twist(A[j], (j == 623) ? B[0] : A[j + 1], B[j - 227]);
+          }
+          mt_gen_barrier();
+        }
+      }
+      gw += (624 - start) + (int64_t)(blocks - 1) * 624;
+      cur = (cur + blocks) & 1;
+      start = 0;
+      end_pos = 0;
+      __syncthreads();
+    }
+  }
   while (gw < total_words) {
     const int64_t avail = 624 - start;
     const int take = (int)((total_words - gw < avail) ? (total_words - gw) : avail);
@@ -1878,8 +1911,10 @@ k_mt19937_uniform(uint32_t* __restrict__ key, int* __restrict__ pos_io, int64_t 
     } else {
       end_pos = start + take;
     }
-    __syncthreads();
+    // no second barrier: `carry` is written and read by the same thread (tid 256), and the next block's
+    // writes go to the buffer whose readers all passed the barrier above
   }
+  __syncthreads();
   for (int i = tid; i < 624; i += kMtThreads) key[i] = buf[cur][i];
   if (tid == 0) *pos_io = end_pos;
 }
