@@ -1393,6 +1393,10 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   } else if (ctx->u_staged == uniforms && ctx->u_staged_count == n_asks * per_ask) {
     CU(cudaStreamWaitEvent(st, ctx->ev_u, 0));  // uploaded by tpe_suggest while the split ran
   } else {
+    if (ctx->u_device_rng) {  // a device draw nobody consumed is still writing U on the side stream
+      CU(cudaStreamWaitEvent(st, ctx->ev_u, 0));
+      ctx->u_device_rng = false;
+    }
     CU(cudaMemcpyAsync(ctx->U.p, uniforms, (size_t)n_asks * per_ask * 8, cudaMemcpyHostToDevice, st));
   }
   ctx->u_staged = nullptr;
