@@ -1380,8 +1380,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 //   else  dropped
 // With tnear = ln K + 17.5 and skip = ln K + 30 the result stays inside the fp64-parity budget
 // whatever the data: each far term is <= e^-tnear of the max term, there are <= K of them and each
-// carries <= 6e-6 relative error (fp32 rounding of L - base, MUFU, <= 32-term fp32 runs), so the
-// far tier adds <= 6e-6 * K * e^-tnear = 1.5e-13 relative to the sum; dropped terms add <= 1e-13.
+// carries <= 7.5e-6 relative error (fp32 rounding of L - base: 1.9e-6 for |L - base| < 64; rounding of
+// the product with log2 e and of that constant: 3.2e-6; ex2.approx: 2.4e-7; fp32 runs of <= 32 terms:
+// 1.9e-6), so the far tier adds <= 7.5e-6 * K * e^-tnear = 1.9e-13 relative to the sum; dropped terms
+// add <= 1e-13.
 // At config 2 ~80 % of the terms inside the skip window are far: the exact folds (a full fp64 exp
 // each, executed by the whole warp) become ~5x rarer.
 struct LseTier {
