@@ -1615,6 +1615,9 @@ k_logpdf_mma(const double* __restrict__ tabm, const double* __restrict__ ckk, in
           acc[m].roll();
           acc[m].sync_global(gmax + wbase + 8 * m + g);
         }
+      } else if ((kg & 15) == 0) {  // long tiles (small PB): keep the fp32 runs at <= 32 terms
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[m].roll();
       }
       const double2* fb = reinterpret_cast<const double2*>(tile + (size_t)kg * 8 * PB) + lane;
       double d0[KG][M], d1[KG][M];
