@@ -156,7 +156,9 @@ int tpe_stage_uniforms(tpe_ctx* ctx, const double* uniforms, int64_t count);
  * (probability_distributions.py:87,100,138-144), without the host RNG (0.45 ms per config-2 ask) and
  * without the upload.  key[624] / pos are RandomState.get_state()[1:3].  The following
  * tpe_sample_and_select must be called with uniforms == NULL and count == n_asks * per_ask.
- * tpe_rng_state returns the generator state after the (skip + count) draws, for set_state(). */
+ * tpe_rng_state returns the generator state after the (skip + count) draws, for set_state().
+ * key == NULL continues from the state the previous staged draw ended in (it is kept on the device), so a
+ * caller that owns the generator exclusively can defer get_state()/set_state() until somebody else needs it. */
 int tpe_stage_uniforms_mt19937(tpe_ctx* ctx, const uint32_t* key, int32_t pos, int64_t skip, int64_t count);
 int tpe_rng_state(tpe_ctx* ctx, uint32_t* key_out, int32_t* pos_out);
 /* Inspection: the first `count` staged uniforms (device-generated or uploaded). */

@@ -1467,13 +1467,17 @@ int tpe_sample_and_select(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, 
 }
 
 int tpe_stage_uniforms_mt19937(tpe_ctx* ctx, const uint32_t* key, int32_t pos, int64_t skip, int64_t count) {
-  if (!ctx || !key || pos < 0 || pos > 624 || skip < 0 || count <= 0) return TPE_E_INVALID;
+  // key == NULL: continue from the state the previous staged draw ended in (kept on the device)
+  if (!ctx || (key && (pos < 0 || pos > 624)) || skip < 0 || count <= 0) return TPE_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  if (!key && !ctx->mt_state.p)
+    return fail(ctx, TPE_E_STATE, "tpe_stage_uniforms_mt19937(key = NULL) needs a previous staged draw to continue");
   ctx->u_staged = nullptr;
   ctx->u_device_rng = false;
-  if (ctx->spec_pending && ctx->mt_host_valid && skip == 0 && count == ctx->spec_count &&
-      (uint32_t)pos == ctx->mt_host[624] && memcmp(key, ctx->mt_host, 624 * 4) == 0) {
+  const bool same_state = !key || (ctx->mt_host_valid && (uint32_t)pos == ctx->mt_host[624] &&
+                                   memcmp(key, ctx->mt_host, 624 * 4) == 0);
+  if (ctx->spec_pending && skip == 0 && count == ctx->spec_count && same_state) {
     // the caller's generator is where the previous ask left it: the speculative draw is this ask's
     std::swap(ctx->U, ctx->U2);
     std::swap(ctx->mt_state, ctx->mt_spec);
@@ -1489,10 +1493,12 @@ int tpe_stage_uniforms_mt19937(tpe_ctx* ctx, const uint32_t* key, int32_t pos, i
   CU(cudaStreamSynchronize(ctx->stream3));
   CU(ctx->U.ensure((size_t)count * 8));
   CU(ctx->mt_state.ensure(625 * 4));
-  uint32_t h[625];
-  memcpy(h, key, 624 * 4);
-  h[624] = (uint32_t)pos;
-  CU(cudaMemcpyAsync(ctx->mt_state.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream3));
+  if (key) {
+    uint32_t h[625];
+    memcpy(h, key, 624 * 4);
+    h[624] = (uint32_t)pos;
+    CU(cudaMemcpyAsync(ctx->mt_state.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream3));
+  }
   k_mt19937_uniform<<<1, kMtThreads, 0, ctx->stream3>>>(ctx->mt_state.as<uint32_t>(),
                                                  reinterpret_cast<int*>(ctx->mt_state.as<uint32_t>() + 624), skip,
                                                  count, ctx->U.as<double>());

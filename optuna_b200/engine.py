@@ -190,10 +190,14 @@ class TPEEngine:
         self._last_asks = n_asks
         return x, acq, best
 
-    def stage_rng(self, rng: np.random.RandomState, count: int, skip: int = 0) -> None:
+    def stage_rng(self, rng: np.random.RandomState | None, count: int, skip: int = 0) -> None:
         """Generate the next `count` outputs of ``rng.random_sample`` on the device (after dropping
         `skip`); the following ``sample_and_select(None, n_asks)`` consumes them.  ``finish_rng(rng)``
-        then moves `rng` to the state after the draws."""
+        then moves `rng` to the state after the draws.  ``rng=None`` continues from the state the
+        previous staged draw ended in (the host generator is then stale until ``finish_rng``)."""
+        if rng is None:
+            self._check(self._lib.tpe_stage_uniforms_mt19937(self._h, None, 0, int(skip), int(count)))
+            return
         st = rng.get_state()
         key = np.ascontiguousarray(st[1], dtype=np.uint32)
         self._rng_tail = (st[0], st[3], st[4])

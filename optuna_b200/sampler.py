@@ -120,6 +120,39 @@ class _History:
         self.groups_last = -1
 
 
+class _DeviceSyncedRng:
+    """The sampler's ``LazyRandomState`` whose MT19937 state may temporarily be newer on the device.
+
+    Large asks draw their uniforms on the GPU; instead of copying the generator state back into the host
+    ``RandomState`` after every ask (get_state + set_state cost 80 us), the state stays on the device
+    and the next ask continues from it.  Any access to ``.rng`` -- an ask drawn on the host, reseeding,
+    pickling, somebody reading ``sampler._rng.rng`` -- first brings the host generator up to date."""
+
+    def __init__(self, inner) -> None:
+        self._inner = inner
+        self._engine = None  # the engine holding a newer state, if any
+
+    @property
+    def rng(self) -> np.random.RandomState:
+        eng, self._engine = self._engine, None
+        if eng is not None:
+            eng.finish_rng(self._inner.rng)
+        return self._inner.rng
+
+    def on_device(self, eng) -> bool:
+        return self._engine is not None and self._engine is eng
+
+    def mark_device(self, eng) -> None:
+        self._engine = eng
+
+    def __getstate__(self) -> dict:
+        self.rng  # flush
+        return {"_inner": self._inner, "_engine": None}
+
+    def __setstate__(self, state: dict) -> None:
+        self.__dict__.update(state)
+
+
 class B200TPESampler(BaseSampler):
     def __init__(
         self,
@@ -158,7 +191,7 @@ class B200TPESampler(BaseSampler):
         self._constant_liar = constant_liar
         self._constraints_func = constraints_func
         self._cat_dist_funcs = categorical_distance_func or {}
-        self._rng = LazyRandomState(seed)
+        self._rng = _DeviceSyncedRng(LazyRandomState(seed))
         self._startup_rng = LazyRandomState(seed)  # the embedded RandomSampler's own state (sampler.py:348-349)
         self._device = device
         self._engine: TPEEngine | None = None
@@ -181,6 +214,9 @@ class B200TPESampler(BaseSampler):
         """Release the device context (re-created on demand)."""
         eng, self._engine = getattr(self, "_engine", None), None
         if eng is not None:
+            rng = getattr(self, "_rng", None)
+            if rng is not None:
+                rng.rng  # bring the host generator up to date before the device state goes away
             eng.close()
         self._hist = _History()
 
@@ -491,15 +527,17 @@ class B200TPESampler(BaseSampler):
         estimator builds, and the host generator is then moved to the state after the draws; small asks
         draw on the host."""
         n = n_asks * self._n_ei_candidates * (1 + len(search_space))
-        rng = self._rng.rng
         if n >= self.DEVICE_RNG_MIN:
-            eng.stage_rng(rng, n)
+            if self._rng.on_device(eng):
+                eng.stage_rng(None, n)            # continue from the state the previous ask ended in
+            else:
+                eng.stage_rng(self._rng.rng, n)
             build()
             x, _, _ = eng.sample_and_select(None, n_asks)
-            eng.finish_rng(rng)
+            self._rng.mark_device(eng)            # the host generator is brought up to date on demand
         else:
             build()
-            x, _, _ = eng.sample_and_select(rng.random_sample(n), n_asks)
+            x, _, _ = eng.sample_and_select(self._rng.rng.random_sample(n), n_asks)
         return x
 
     def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
