@@ -79,8 +79,12 @@ __global__ void k_mo_first_lookup(const double* __restrict__ vals, int M, const 
     uint32_t slot = (uint32_t)mo_hash(me, M) & mask;
     for (;;) {
       const int cur = table[slot];
+      if (cur == i || cur == kMoEmpty) {  // own entry (also the only match of a vector holding a NaN) / not found
+        first = true;
+        break;
+      }
       if (mo_same(vals + list[cur] * M, me, M)) {
-        first = cur == i;
+        first = false;  // an identical vector with a smaller position owns the slot
         break;
       }
       slot = (slot + 1) & mask;
