@@ -460,7 +460,7 @@ def run_b200(args) -> None:
                     "path": "B200TPESampler.sample_relative -> ctypes -> tpe_prepare / tpe_stage_uniforms_mt19937 / "
                             "tpe_build / tpe_sample_and_select / tpe_rng_state"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": 27532800, "traffic_source": "ncu --set full, profiles/r1_ncu_raw_logpdf_mma_final.txt "
+                         "traffic": 27546880, "traffic_source": "ncu --set full, profiles/r1_ncu_raw_logpdf_mma_final.txt "
                          "(dram__bytes_read.sum + dram__bytes_write.sum of this launch)",
                          "peak_source": peak_src, "kernel": kernel_name,
                          "kernel_ms": k_ms, "algorithmic_bytes": algorithmic_bytes(),
