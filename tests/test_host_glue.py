@@ -53,3 +53,32 @@ def test_sampler_constructor_contract():
     study = mini.create_study(sampler=B200TPESampler(seed=0, n_startup_trials=5))
     study.optimize(lambda t: t.suggest_float("x", 0, 1) + t.suggest_int("k", 1, 3), n_trials=5)
     assert len(study.trials) == 5 and study.sampler._engine is None
+
+
+def test_device_synced_rng_flushes_on_access_and_pickle():
+    """sampler._DeviceSyncedRng: while the newer MT19937 state lives on the device, any access to
+    `.rng` (and pickling) first copies it back -- here with a stand-in engine."""
+    import pickle
+    from optuna_b200.mini import LazyRandomState
+    from optuna_b200.sampler import _DeviceSyncedRng
+
+    class FakeEngine:
+        def __init__(self, end_state):
+            self.end_state, self.calls = end_state, 0
+
+        def finish_rng(self, rng):
+            self.calls += 1
+            rng.set_state(self.end_state)
+
+    ahead = np.random.RandomState(3)
+    ahead.random_sample(1000)                      # what the device would have drawn
+    proxy = _DeviceSyncedRng(LazyRandomState(3))
+    eng = FakeEngine(ahead.get_state())
+    assert not proxy.on_device(eng)
+    proxy.mark_device(eng)
+    assert proxy.on_device(eng) and not proxy.on_device(object())
+    clone = pickle.loads(pickle.dumps(proxy))      # pickling flushes
+    assert eng.calls == 1 and not proxy.on_device(eng)
+    want = ahead.random_sample(4)
+    assert np.array_equal(clone.rng.random_sample(4), want)
+    assert np.array_equal(proxy.rng.random_sample(4), want) and eng.calls == 1
