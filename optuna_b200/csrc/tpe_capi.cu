@@ -1264,7 +1264,7 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
     int64_t* d_a = ctx->est[1].rows.as<int64_t>();
     int64_t* d_c = ctx->counts.as<int64_t>();
     void* args[] = {&n_i, &d_cat, &d_key, &nb, &rowok, &pre_member, &d_wk, &d_b, &d_p, &d_a, &d_c};
-    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (N + 2047) / 2048));
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (N + 1023) / 1024));
     CU(cudaLaunchCooperativeKernel((const void*)k_split_coop, dim3(G), dim3(512), args, 0, ctx->stream));
     ctx->launch_counter++;
     ctx->split_valid = plain;
