@@ -44,7 +44,17 @@ enum {
 enum { TPE_KIND_FLOAT = 0, TPE_KIND_INT = 1, TPE_KIND_CAT = 2 };
 
 /* Trial groups of TPESampler._split_trials (optuna/samplers/_tpe/sampler.py:686-722). */
-enum { TPE_CAT_COMPLETE = 0, TPE_CAT_PRUNED = 1, TPE_CAT_INFEASIBLE = 2, TPE_CAT_RUNNING = 3 };
+enum {
+  TPE_CAT_COMPLETE = 0,
+  TPE_CAT_PRUNED = 1,
+  TPE_CAT_INFEASIBLE = 2,
+  TPE_CAT_RUNNING = 3,
+  /* A row that takes part in neither set: the placeholder of a trial the sampler must not see yet (WAITING,
+   * RUNNING without constant_liar, the trial being sampled itself -- sampler.py:526-535 filters it out) or ever
+   * (FAIL).  Keeps row index == position in the study's trial list, so that a trial finishing late is one
+   * tpe_history_update in place instead of a re-upload. */
+  TPE_CAT_EXCLUDED = 4
+};
 
 typedef struct tpe_ctx tpe_ctx;
 
@@ -98,9 +108,10 @@ int tpe_history_set(tpe_ctx* ctx, const double* X, const int8_t* category, const
                     int64_t n);
 int tpe_history_append(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key,
                        int64_t n);
-/* Overwrite rows [at_row, at_row + n) in place: a RUNNING trial that has finished keeps its position
- * (trial-number order) and only changes its category / key / parameters (constant_liar=True,
- * sampler.py:526-535: RUNNING trials sit in the above set until they complete). */
+/* Overwrite rows [at_row, at_row + n) in place: a trial that has finished keeps its position (trial-number order)
+ * and only changes its category / key / parameters (a TPE_CAT_EXCLUDED placeholder becoming COMPLETE; with
+ * constant_liar=True, sampler.py:526-535, a RUNNING row of the above set).  at_row <= current size; a write that
+ * runs past the end extends the history, so "the previous trial finished + the next one started" is one call. */
 int tpe_history_update(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key, int64_t n,
                        int64_t at_row);
 /* Same, with DEVICE pointers on ctx's device (used after an NCCL broadcast of the history). */

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libtpe_b200.so")
 
 TPE_OK, TPE_E_INVALID, TPE_E_CUDA, TPE_E_STATE, TPE_E_NOMEM = 0, -1, -2, -3, -4
 KIND_FLOAT, KIND_INT, KIND_CAT = 0, 1, 2
-CAT_COMPLETE, CAT_PRUNED, CAT_INFEASIBLE, CAT_RUNNING = 0, 1, 2, 3
+CAT_COMPLETE, CAT_PRUNED, CAT_INFEASIBLE, CAT_RUNNING, CAT_EXCLUDED = 0, 1, 2, 3, 4
 
 
 class ParamDesc(C.Structure):

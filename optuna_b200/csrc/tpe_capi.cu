@@ -118,7 +118,7 @@ struct tpe_ctx {
   DevBuf X, cat, key, vals;
   int32_t M = 1;                 // objectives (>= 2: MOTPE)
   std::vector<int8_t> cat_h;     // host mirror of the categories (MOTPE list building)
-  int64_t cat_cnt[4] = {0, 0, 0, 0};  // trials per category (sizes of the split without a read-back)
+  int64_t cat_cnt[5] = {0, 0, 0, 0, 0};  // trials per category incl. TPE_CAT_EXCLUDED (sizes of the split without a read-back)
   // the split depends on the history and n_below only (not on the selected columns, unless rows lack
   // parameters): consecutive tpe_prepare calls on the same history -- the P sample_independent calls of a
   // univariate trial -- reuse it
@@ -179,6 +179,9 @@ int fail(tpe_ctx* c, int code, const char* fmt, ...) {
       return fail(ctx, e_ == cudaErrorMemoryAllocation ? TPE_E_NOMEM : TPE_E_CUDA, "%s failed: %s (%s:%d)", \
                   #call, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
   } while (0)
+
+// slot of a history category in cat_cnt: anything outside 0..3 is TPE_CAT_EXCLUDED
+inline int cat_slot(int8_t c) { return (c >= 0 && c <= 3) ? c : 4; }
 
 inline int grid_for(int64_t work, int threads, int cap) {
   int64_t g = (work + threads - 1) / threads;
@@ -366,8 +369,8 @@ int upload_history(tpe_ctx* ctx, const double* X, const int8_t* category, const 
     if (device_src) CU(cudaMemcpy(ctx->cat_h.data() + at, category, (size_t)n, cudaMemcpyDeviceToHost));
     else memcpy(ctx->cat_h.data() + at, category, (size_t)n);
   }
-  if (at == 0) ctx->cat_cnt[0] = ctx->cat_cnt[1] = ctx->cat_cnt[2] = ctx->cat_cnt[3] = 0;
-  for (int64_t i = at; i < total; ++i) ctx->cat_cnt[ctx->cat_h[(size_t)i] & 3]++;
+  if (at == 0) ctx->cat_cnt[0] = ctx->cat_cnt[1] = ctx->cat_cnt[2] = ctx->cat_cnt[3] = ctx->cat_cnt[4] = 0;
+  for (int64_t i = at; i < total; ++i) ctx->cat_cnt[cat_slot(ctx->cat_h[(size_t)i])]++;
   if (at == 0) ctx->M = 1;  // a fresh history is single-objective until values are supplied
   ctx->N = total;
   ctx->history_set = true;
@@ -1067,24 +1070,36 @@ int tpe_history_update(tpe_ctx* ctx, const double* X, const int8_t* category, co
   if (!ctx) return TPE_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->history_set) return fail(ctx, TPE_E_STATE, "tpe_history_set must precede tpe_history_update");
-  if (n < 0 || at_row < 0 || at_row + n > ctx->N || (n > 0 && (!X || !category || !key)))
-    return fail(ctx, TPE_E_INVALID, "tpe_history_update: rows [%lld, %lld) outside the history of %lld rows",
+  if (n < 0 || at_row < 0 || at_row > ctx->N || (n > 0 && (!X || !category || !key)))
+    return fail(ctx, TPE_E_INVALID, "tpe_history_update: rows [%lld, %lld) do not continue the history of %lld rows",
                 (long long)at_row, (long long)(at_row + n), (long long)ctx->N);
   if (n == 0) return TPE_OK;
+  if (at_row + n >= (1ll << 31) - 4096) return fail(ctx, TPE_E_INVALID, "history too long");
   if (set_device(ctx)) return TPE_E_CUDA;
   if ((int64_t)ctx->cat_h.size() != ctx->N)
     return fail(ctx, TPE_E_STATE, "tpe_history_update needs a host-uploaded history");
   scan_missing(ctx, X, n);
   const int64_t P = (int64_t)ctx->space.size();
+  const int64_t total = std::max(ctx->N, at_row + n);
+  if (total > ctx->N) {  // the write runs past the end: the history grows (rows [at_row, N) are overwritten)
+    CU(ctx->X.grow((size_t)total * P * 8, (size_t)ctx->N * P * 8, ctx->stream));
+    CU(ctx->cat.grow((size_t)total, (size_t)ctx->N, ctx->stream));
+    CU(ctx->key.grow((size_t)total * 16, (size_t)ctx->N * 16, ctx->stream));
+    if (ctx->M >= 2)
+      CU(ctx->vals.grow((size_t)total * ctx->M * 8, (size_t)ctx->N * ctx->M * 8, ctx->stream));
+  }
   CU(cudaMemcpyAsync(ctx->X.as<double>() + at_row * P, X, (size_t)n * P * 8, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->cat.as<int8_t>() + at_row, category, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->key.as<double>() + at_row * 2, key, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->cat_h.resize((size_t)total, (int8_t)TPE_CAT_EXCLUDED);
   for (int64_t i = 0; i < n; ++i) {
-    ctx->cat_cnt[ctx->cat_h[(size_t)(at_row + i)] & 3]--;
-    ctx->cat_h[(size_t)(at_row + i)] = category[i];
-    ctx->cat_cnt[category[i] & 3]++;
+    const int64_t r = at_row + i;
+    if (r < ctx->N) ctx->cat_cnt[cat_slot(ctx->cat_h[(size_t)r])]--;
+    ctx->cat_h[(size_t)r] = category[i];
+    ctx->cat_cnt[cat_slot(category[i])]++;
   }
+  ctx->N = total;
   ctx->prepared = ctx->built = ctx->sampled = false;
   ctx->hist_version++;
   return TPE_OK;
@@ -1111,8 +1126,10 @@ int tpe_history_set_values(tpe_ctx* ctx, const double* values, int64_t n, int32_
     return fail(ctx, TPE_E_INVALID, "bad values range");
   if (at_row > 0 && n_objectives != ctx->M) return fail(ctx, TPE_E_INVALID, "n_objectives changed");
   if (set_device(ctx)) return TPE_E_CUDA;
-  CU(ctx->vals.grow((size_t)std::max<int64_t>(ctx->N, 1) * n_objectives * 8, (size_t)at_row * n_objectives * 8,
-                    ctx->stream));
+  // a partial write keeps every row already there (rows after the written range included)
+  const size_t keep = (n_objectives == ctx->M && at_row > 0)
+                          ? std::min(ctx->vals.cap, (size_t)ctx->N * n_objectives * 8) : 0;
+  CU(ctx->vals.grow((size_t)std::max<int64_t>(ctx->N, 1) * n_objectives * 8, keep, ctx->stream));
   if (n > 0)
     CU(cudaMemcpyAsync(ctx->vals.as<double>() + at_row * n_objectives, values, (size_t)n * n_objectives * 8,
                        cudaMemcpyHostToDevice, ctx->stream));
@@ -1290,7 +1307,7 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
       if (take < cnt[c]) break;
     }
     counts[0] = counts[1] = below;
-    counts[2] = N - below;
+    counts[2] = N - cnt[4] - below;  // TPE_CAT_EXCLUDED rows are in neither set
   }
   if (!predict || verify_counts) {
     int64_t dev[3];

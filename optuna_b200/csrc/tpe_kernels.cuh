@@ -80,7 +80,10 @@ k_split_coop(int n, const int8_t* __restrict__ cat, const double* __restrict__ k
   // ---- category sizes ---------------------------------------------------------------------------
   if (tid < 4) s_base[tid] = 0;
   __syncthreads();
-  for (int i = lo_i + tid; i < hi_i; i += blockDim.x) atomicAdd(&s_base[cat[i] & 3], 1);
+  for (int i = lo_i + tid; i < hi_i; i += blockDim.x) {
+    const int c = cat[i];
+    if (c >= 0 && c <= 3) atomicAdd(&s_base[c], 1);  // TPE_CAT_EXCLUDED rows belong to neither set
+  }
   __syncthreads();
   if (tid < 4 && s_base[tid]) atomicAdd(&wk->cat_count[tid], s_base[tid]);
   grid.sync();
@@ -148,7 +151,7 @@ k_split_coop(int n, const int8_t* __restrict__ cat, const double* __restrict__ k
   auto classify = [&](int i) -> int {
     const int c = cat[i];
     if (c == 0 && pre_member != nullptr) return pre_member[i] ? 2 : 0;
-    if (c >= 3 || c > thr_cat) return 0;
+    if (c >= 3 || c < 0 || c > thr_cat) return 0;
     if (c < thr_cat) return 2;
     if (need <= 0 && !take_all_eq) return 0;
     uint64_t h, l;
@@ -185,7 +188,7 @@ k_split_coop(int n, const int8_t* __restrict__ cat, const double* __restrict__ k
       const int i = t0 + tid;
       const bool v = i < hi_i;
       const int cls = v ? classify(i) : 0;
-      const bool ok = v && (row_ok == nullptr || row_ok[i] != 0);
+      const bool ok = v && (row_ok == nullptr || row_ok[i] != 0) && (unsigned)cat[i] <= 3u;
       // ordered rank helpers (512 threads = 16 warps)
       auto rank = [&](bool f, int& total) -> int {
         const unsigned m = __ballot_sync(0xffffffffu, f);

@@ -117,17 +117,20 @@ class TPEEngine:
         self._check(self._lib.tpe_history_append(self._h, _ptr(X), _ptr(cat), _ptr(key), X.shape[0]))
 
     def update_history(self, X, category, key, at_row: int) -> None:
-        """Overwrite rows [at_row, at_row + n) in place (a RUNNING trial that finished keeps its position)."""
+        """Overwrite rows [at_row, at_row + n) in place (a trial that finished keeps its position); a write
+        past the end extends the history."""
         X = _f64(X, (-1, self.n_params))
         cat = np.ascontiguousarray(category, dtype=np.int8).reshape(-1)
         key = _f64(key, (-1, 2))
         self._check(self._lib.tpe_history_update(self._h, _ptr(X), _ptr(cat), _ptr(key), X.shape[0], int(at_row)))
 
-    def set_values(self, values, at_row: int = 0) -> None:
-        """Sign-normalised objective values [n, M] of history rows [at_row, at_row + n) (MOTPE)."""
+    def set_values(self, values, at_row: int = 0, n_objectives: int | None = None) -> None:
+        """Sign-normalised objective values [n, M] of history rows [at_row, at_row + n) (MOTPE).  Pass
+        `n_objectives` when n may be 0 (the shape of an empty array does not say)."""
         v = _f64(values)
-        v = v.reshape(v.shape[0], -1)
-        self._check(self._lib.tpe_history_set_values(self._h, _ptr(v), v.shape[0], v.shape[1], int(at_row)))
+        m = int(n_objectives) if n_objectives is not None else (v.shape[1] if v.ndim == 2 else 1)
+        v = v.reshape(-1, m)
+        self._check(self._lib.tpe_history_set_values(self._h, _ptr(v), v.shape[0], m, int(at_row)))
 
     def set_history_device(self, dX: int, dcat: int, dkey: int, n: int, col_has_missing=None) -> None:
         miss = None if col_has_missing is None else np.ascontiguousarray(col_has_missing, dtype=np.uint8)

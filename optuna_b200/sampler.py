@@ -20,12 +20,14 @@ from typing import Any, Callable, Sequence
 import numpy as np
 
 from . import _lib
-from ._compat import (CONSTRAINTS_KEY, RELATIVE_PARAMS_KEY, SYSTEM_ATTR_MAX_LENGTH, BaseDistribution,
-                      BaseSampler, CategoricalDistribution, FloatDistribution, IntDistribution,
-                      LazyRandomState, StudyDirection, TrialState, random_independent)
+from ._compat import (CONSTRAINTS_KEY, RELATIVE_PARAMS_KEY, SYSTEM_ATTR_MAX_LENGTH, _INDEPENDENT_SAMPLING_WARNING_TEMPLATE,
+                      BaseDistribution, BaseSampler, CategoricalDistribution, FloatDistribution, InMemoryStorage,
+                      IntDistribution, LazyRandomState, RandomSampler, StudyDirection, TrialState,
+                      _process_constraints_after_trial, get_logger, optuna_warn, warn_experimental_argument)
 from .engine import ParamSpec, TPEEngine
 
 EPS = 1e-12
+_logger = get_logger("optuna.samplers.optuna_b200")  # a child of optuna's root logger: same handlers / verbosity
 
 
 def default_gamma(x: int) -> int:
@@ -77,8 +79,8 @@ def _infeasible_score(trial) -> float:
     """sampler.py:803-813"""
     con = trial.system_attrs.get(CONSTRAINTS_KEY)
     if con is None:
-        warnings.warn(f"Trial {trial.number} does not have constraint values."
-                      " It will be treated as a lower priority than other trials.")
+        optuna_warn(f"Trial {trial.number} does not have constraint values."
+                    " It will be treated as a lower priority than other trials.")
         return float("inf")
     return sum(v for v in con if v > 0)
 
@@ -96,28 +98,148 @@ def _spec_of(name: str, d: BaseDistribution, dist_funcs: dict) -> ParamSpec:
     return ParamSpec(kind=_lib.KIND_FLOAT, low=d.low, high=d.high, step=d.step, log=bool(d.log))
 
 
+class _Reset(Exception):
+    """The study's trial list is not an extension of what the log has seen (another study behind the same ids)."""
+
+
 class _History:
-    """Device-resident trial history kept in step with the study (replaces the per-call
-    FrozenTrial walks of sampler.py:511-521 and :686-722)."""
+    """The study's trial list followed incrementally, and its mirror on the device.
+
+    Replaces the per-call FrozenTrial walks of the reference -- ``study._get_trials(states=...)`` filters
+    (study/study.py:269-287, O(N) each, three per ask in sampler.py:449-535), ``_get_internal_repr``
+    (:511-521), ``_split_trials`` (:686-722), ``IntersectionSearchSpace._calculate``
+    (search_space/intersection.py:14-55) and ``_GroupDecomposedSearchSpace.calculate``
+    (search_space/group_decomposed.py:45-68) -- by O(#changes) work per ask.
+
+    Row r of the log (and of the device history) is the r-th trial of the study's list, i.e. trial number r:
+    COMPLETE / PRUNED trials carry their sort key, everything the sampler must not see (WAITING, FAIL, RUNNING
+    without ``constant_liar``, the trial being sampled) is a TPE_CAT_EXCLUDED placeholder, so a trial that
+    finishes later -- in any order -- is one in-place row update.
+
+    Two ways to learn what changed since the last look:
+      * ``InMemoryStorage`` (everything in this process): O(1) probes through the storage's public API --
+        ``get_trial`` of the few unfinished trials (the storage replaces a FrozenTrial object whenever it changes:
+        an unchanged object means an unchanged trial) and ``get_trial_id_from_study_id_trial_number`` for numbers
+        not seen yet.  No O(N) list copy per ask.
+      * any other storage: ``study._get_trials(deepcopy=False, use_cache=...)`` (all states -- the call is O(1) on
+        the study's per-trial cache once the storage has answered) and the same scan of unfinished + new rows.
+    """
 
     def __init__(self) -> None:
+        # ---- log (host only) ----
+        self.storage = None            # strong reference: a recycled id() can never alias another storage
+        self.token: tuple | None = None
+        self.rows = 0
+        self.numbers: list[int] = []
+        self.pending: dict[int, list] = {}     # row -> [trial_id, FrozenTrial object at the last look]
+        self.n_finished = 0                    # COMPLETE + PRUNED trials (sampler.py:449-456, :538)
+        self.all_dists: dict[str, BaseDistribution] = {}   # latest distribution of every parameter seen
+        self.seen_params: set[str] = set()
+        self.inter: dict[str, BaseDistribution] | None = None
+        self.groups: list[dict[str, BaseDistribution]] = []
+        self.group_backlog: list[tuple[int, dict]] = []
+        self.last_list: list | None = None     # trial list of the last generic poll (valid during one sync)
+        # ---- device mirror ----
         self.columns: dict[str, int] = {}
         self.dists: list[BaseDistribution] = []
-        self.n = 0
-        self.last_number = -1
-        self.sign = 1.0
-        self.token: tuple | None = None
-        self.n_finished = 0
-        # constant_liar: position -> trial number of the rows uploaded while the trial was RUNNING
-        self.running: dict[int, int] = {}
-        # incremental intersection search space (optuna/search_space/intersection.py:14-55)
-        self.inter: dict[str, BaseDistribution] | None = None
-        self.inter_n = 0
-        self.inter_last = -1
-        # incremental group decomposition (optuna/search_space/group_decomposed.py:14-68)
-        self.groups: list[dict[str, BaseDistribution]] = []
-        self.groups_n = 0
-        self.groups_last = -1
+        self.dev_token: tuple | None = None
+        self.dev_rows = 0
+        self.dev_cat: dict[int, int] = {}      # category uploaded for the rows still pending
+        self.backlog: dict[int, Any] = {}      # row -> FrozenTrial: changes the log has seen, the device has not
+
+    # -- log ---------------------------------------------------------------------------------------------
+    def _account(self, t) -> None:
+        """A trial seen finished for the first time."""
+        if t.state != TrialState.COMPLETE and t.state != TrialState.PRUNED:
+            return  # FAIL: in no estimator, in no search space
+        self.n_finished += 1
+        d = t.distributions
+        self.all_dists.update(d)
+        self.seen_params.update(t.params)
+        if self.inter is None:
+            self.inter = dict(d)
+        elif self.inter:
+            inter = self.inter
+            if not (len(d) == len(inter) and all(d.get(k) is v for k, v in inter.items())):
+                self.inter = {k: v for k, v in inter.items() if d.get(k) == v}
+        self.group_backlog.append((t.number, d))
+
+    def poll(self, study, use_cache: bool) -> list[tuple[int, Any]]:
+        """(row, FrozenTrial) of every row that is new or whose trial changed since the last poll, ascending."""
+        st, sid = study._storage, study._study_id
+        token = (sid, tuple(study.directions))
+        if self.storage is not st or self.token != token:
+            self.__init__()
+            self.storage, self.token = st, token
+        changed: list[tuple[int, Any]] = []
+        fast = type(st) is InMemoryStorage and self.rows > 0
+        trials = None
+        if not fast:
+            trials = study._get_trials(deepcopy=False, use_cache=use_cache)
+            if len(trials) < self.rows or (self.rows and trials[self.rows - 1].number != self.numbers[-1]):
+                raise _Reset()
+        self.last_list = trials
+        for row, slot in list(self.pending.items()):
+            t = st.get_trial(slot[0]) if fast else trials[row]
+            if t is slot[1]:
+                continue
+            if t.number != self.numbers[row]:
+                raise _Reset()
+            changed.append((row, t))
+            if t.state.is_finished():
+                del self.pending[row]
+                self._account(t)
+            else:
+                slot[1] = t
+        while True:
+            row = self.rows
+            if fast:
+                try:
+                    tid = st.get_trial_id_from_study_id_trial_number(sid, row)
+                except KeyError:
+                    break
+                t = st.get_trial(tid)
+            else:
+                if row >= len(trials):
+                    break
+                t = trials[row]
+                tid = t._trial_id
+            self.rows += 1
+            self.numbers.append(t.number)
+            changed.append((row, t))
+            if t.state.is_finished():
+                self._account(t)
+            else:
+                self.pending[row] = [tid, t]
+        return changed
+
+    def all_trials(self, study, use_cache: bool) -> list:
+        """Every trial the log has seen, as a list (device rebuilds only: O(N))."""
+        trials = self.last_list
+        if trials is None:  # fast polls keep no list; a fresh one (a cached one may be older than the log)
+            trials = study._get_trials(deepcopy=False, use_cache=False)
+        return trials[: self.rows]
+
+    def intersection(self) -> dict[str, BaseDistribution]:
+        return dict(sorted((self.inter or {}).items(), key=lambda kv: kv[0]))
+
+    def group_spaces(self) -> list[dict[str, BaseDistribution]]:
+        """_GroupDecomposedSearchSpace.calculate (group_decomposed.py:45-68).  The reference re-adds the
+        distributions of every finished trial, in trial order, at each call; adding a trial twice changes nothing
+        (its parameters already are a union of groups), so adding the trials that finished since the last call,
+        in trial order, gives the same list of groups in the same order."""
+        backlog, self.group_backlog = sorted(self.group_backlog, key=lambda e: e[0]), []
+        for _, dist in backlog:
+            left = set(dist)
+            nxt: list[dict[str, BaseDistribution]] = []
+            for sub in self.groups:
+                keys = set(sub)
+                nxt.append({name: sub[name] for name in keys & left})
+                nxt.append({name: sub[name] for name in keys - left})
+                left -= keys
+            nxt.append({name: dist[name] for name in left})
+            self.groups = [g for g in nxt if g]
+        return [dict(g) for g in self.groups]
 
 
 class _DeviceSyncedRng:
@@ -154,6 +276,13 @@ class _DeviceSyncedRng:
 
 
 class B200TPESampler(BaseSampler):
+    """``optuna.samplers.TPESampler`` (sampler.py:72-385) with the numeric path on a B200.  Same constructor
+    arguments (+ ``device``), same plugin methods, same suggestions for the same seed."""
+
+    #: what answers the array-level calls -- the CUDA library; no fallback.  (The seam mirrors the reference's
+    #: ``_parzen_estimator_cls``, sampler.py:358-359; tests plug the CPU oracle in here to check the host glue.)
+    _engine_cls = TPEEngine
+
     def __init__(
         self,
         *,
@@ -175,9 +304,8 @@ class B200TPESampler(BaseSampler):
         device: int = 0,
     ) -> None:
         if not consider_prior:
-            warnings.warn("`consider_prior` is deprecated; it falls back to `True`.", FutureWarning)
-        if group and not multivariate:
-            raise ValueError("``group`` option can only be enabled when ``multivariate`` is enabled.")
+            optuna_warn("`consider_prior` has been deprecated in v4.3.0 and automatically falls back to `True`.",
+                        FutureWarning)
         self._prior_weight = prior_weight
         self._magic_clip = consider_magic_clip
         self._endpoints = consider_endpoints
@@ -192,17 +320,31 @@ class B200TPESampler(BaseSampler):
         self._constraints_func = constraints_func
         self._cat_dist_funcs = categorical_distance_func or {}
         self._rng = _DeviceSyncedRng(LazyRandomState(seed))
-        self._startup_rng = LazyRandomState(seed)  # the embedded RandomSampler's own state (sampler.py:348-349)
+        self._random_sampler = RandomSampler(seed=seed)  # startup trials (sampler.py:348-349, :471-474)
         self._device = device
         self._engine: TPEEngine | None = None
         self._hist = _History()
+        self._groups_now: list[dict[str, BaseDistribution]] = []
         self._lock = threading.RLock()
+        if multivariate:
+            warn_experimental_argument("multivariate")
+        if group:
+            if not multivariate:
+                raise ValueError("``group`` option can only be enabled when ``multivariate`` is enabled.")
+            warn_experimental_argument("group")
+        if constant_liar:
+            warn_experimental_argument("constant_liar")
+        if constraints_func is not None:
+            warn_experimental_argument("constraints_func")
+        if categorical_distance_func is not None:
+            warn_experimental_argument("categorical_distance_func")
 
     # -- pickling: device state is a cache re-creatable from the study ----------
     def __getstate__(self) -> dict:
         state = self.__dict__.copy()
         state["_engine"] = None
         state["_hist"] = _History()
+        state["_groups_now"] = []
         del state["_lock"]
         return state
 
@@ -218,7 +360,9 @@ class B200TPESampler(BaseSampler):
             if rng is not None:
                 rng.rng  # bring the host generator up to date before the device state goes away
             eng.close()
-        self._hist = _History()
+        h = getattr(self, "_hist", None)
+        if h is not None:
+            h.dev_token, h.dev_rows, h.dev_cat = None, 0, {}
 
     def __del__(self) -> None:  # pragma: no cover
         try:
@@ -234,30 +378,41 @@ class B200TPESampler(BaseSampler):
 
     def reseed_rng(self) -> None:
         self._rng.rng.seed()
-        self._startup_rng.rng.seed()
+        self._random_sampler.reseed_rng()
 
     # -- plugin surface -------------------------------------------------------------------------------
+    def _poll(self, study) -> list[tuple[int, Any]]:
+        """Bring the log up to date.  ``use_cache`` as the reference passes it (sampler.py:392, :528)."""
+        h = self._hist
+        use_cache = self._multivariate or not self._constant_liar
+        try:
+            return h.poll(study, use_cache)
+        except _Reset:
+            h.storage = None  # forget everything and read the list afresh
+            return h.poll(study, use_cache)
+
     def infer_relative_search_space(self, study, trial) -> dict[str, BaseDistribution]:
         if not self._multivariate:
             return {}
-        if self._group:
-            with self._lock:
-                groups = self._group_spaces(study)
-            out: dict[str, BaseDistribution] = {}
-            for sub in groups:
-                for name, d in sorted(sub.items()):
-                    if not d.single():
-                        out[name] = d
-            return out
         with self._lock:
-            space = self._intersection(study)
+            self._note_changes(self._poll(study))
+            if self._group:
+                self._groups_now = self._hist.group_spaces()
+                out: dict[str, BaseDistribution] = {}
+                for sub in self._groups_now:
+                    for name, d in sorted(sub.items()):  # sorted: the reference's order (sampler.py:400-404)
+                        if not d.single():
+                            out[name] = d
+                return out
+            space = self._hist.intersection()
         return {k: d for k, d in space.items() if not d.single()}
 
     def sample_relative(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
         if self._group:
-            # one joint suggestion per group of parameters that always appear together (sampler.py:417-431)
+            # one joint suggestion per group of parameters that always appear together (sampler.py:417-431);
+            # the search space may be smaller than what was inferred (PartialFixedSampler, _partial_fixed.py:65-84)
             with self._lock:
-                groups = [dict(g) for g in self._hist.groups]
+                groups = [dict(g) for g in self._groups_now]
             params: dict[str, Any] = {}
             for sub in groups:
                 part = {name: d for name, d in sorted(sub.items()) if not d.single() and name in search_space}
@@ -265,6 +420,7 @@ class B200TPESampler(BaseSampler):
         else:
             params = self._sample_relative(study, trial, search_space)
         if params != {} and self._constant_liar:
+            # share the relative parameters with the other workers (sampler.py:435-443)
             text = json.dumps(params)
             for i in range(0, len(text), SYSTEM_ATTR_MAX_LENGTH):
                 study._storage.set_trial_system_attr(trial._trial_id,
@@ -275,42 +431,43 @@ class B200TPESampler(BaseSampler):
     def _sample_relative(self, study, trial, search_space) -> dict[str, Any]:
         if search_space == {}:
             return {}
-        trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
-        if len(trials) < self._n_startup_trials:
-            return {}
-        return self._sample(study, trial, search_space)
+        with self._lock:
+            self._note_changes(self._poll(study))
+            if self._hist.n_finished < self._n_startup_trials:
+                return {}
+            return self._sample(study, trial, search_space)
 
     def sample_independent(self, study, trial, param_name: str, param_distribution: BaseDistribution) -> Any:
-        trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
-        if len(trials) < self._n_startup_trials:
-            return random_independent(self._startup_rng.rng, param_distribution)
-        if self._warn_independent_sampling and self._multivariate:
-            if any(param_name in t.params for t in trials):
-                warnings.warn(f"The parameter '{param_name}' in trial#{trial.number} is sampled independently "
-                              "instead of being sampled by multivariate TPE sampler (dynamic search space is "
-                              "not supported for `multivariate=True`).")
-        return self._sample(study, trial, {param_name: param_distribution})[param_name]
+        with self._lock:
+            self._note_changes(self._poll(study))
+            startup = self._hist.n_finished < self._n_startup_trials
+            seen = param_name in self._hist.seen_params
+        if startup:
+            return self._random_sampler.sample_independent(study, trial, param_name, param_distribution)
+        if self._warn_independent_sampling and self._multivariate and seen:
+            # not at the first sampling of `param_name` (sampler.py:476-489)
+            _logger.warning(_INDEPENDENT_SAMPLING_WARNING_TEMPLATE.format(
+                param_name=param_name, trial_number=trial.number,
+                independent_sampler_name=self._random_sampler.__class__.__name__,
+                sampler_name=self.__class__.__name__,
+                fallback_reason="dynamic search space is not supported for `multivariate=True`"))
+        with self._lock:
+            return self._sample(study, trial, {param_name: param_distribution})[param_name]
 
     def before_trial(self, study, trial) -> None:
-        pass
+        self._random_sampler.before_trial(study, trial)
 
     def after_trial(self, study, trial, state, values) -> None:
+        """sampler.py:666-676: constraints are evaluated once, here, and stored with the trial."""
         assert state in (TrialState.COMPLETE, TrialState.FAIL, TrialState.PRUNED)
-        if self._constraints_func is None or state not in (TrialState.COMPLETE, TrialState.PRUNED):
-            return
-        con = None
-        try:
-            out = self._constraints_func(trial)
-            if not isinstance(out, (tuple, list)):
-                warnings.warn("Constraints should be a sequence of floats.")
-            con = tuple(out)
-        finally:
-            study._storage.set_trial_system_attr(trial._trial_id, CONSTRAINTS_KEY, con)
+        if self._constraints_func is not None:
+            _process_constraints_after_trial(self._constraints_func, study, trial, state)
+        self._random_sampler.after_trial(study, trial, state, values)
 
     # -- host glue -------------------------------------------------------------------------------------
     def _eng(self) -> TPEEngine:
         if self._engine is None:
-            self._engine = TPEEngine(self._device)
+            self._engine = self._engine_cls(self._device)
         return self._engine
 
     def _get_params(self, trial) -> dict[str, Any]:
@@ -328,40 +485,6 @@ class B200TPESampler(BaseSampler):
         params.update(trial.params)
         return params
 
-    def _intersection(self, study) -> dict[str, BaseDistribution]:
-        h = self._hist
-        trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
-        fresh = not (h.inter_n <= len(trials) and (h.inter_n == 0 or trials[h.inter_n - 1].number == h.inter_last))
-        if fresh:
-            h.inter, h.inter_n = None, 0
-        for t in trials[h.inter_n:]:
-            if h.inter is None:
-                h.inter = dict(t.distributions)
-            else:
-                h.inter = {k: d for k, d in h.inter.items() if k in t.distributions and d == t.distributions[k]}
-        h.inter_n = len(trials)
-        h.inter_last = trials[-1].number if trials else -1
-        return dict(sorted((h.inter or {}).items(), key=lambda kv: kv[0]))
-
-    def _group_spaces(self, study) -> list[dict[str, BaseDistribution]]:
-        h = self._hist
-        trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
-        if not (h.groups_n <= len(trials) and (h.groups_n == 0 or trials[h.groups_n - 1].number == h.groups_last)):
-            h.groups, h.groups_n = [], 0
-        for t in trials[h.groups_n:]:
-            left = set(t.distributions)
-            nxt: list[dict[str, BaseDistribution]] = []
-            for sub in h.groups:
-                keys = set(sub)
-                nxt.append({name: sub[name] for name in keys & left})
-                nxt.append({name: sub[name] for name in keys - left})
-                left -= keys
-            nxt.append({name: t.distributions[name] for name in left})
-            h.groups = [g for g in nxt if g]
-        h.groups_n = len(trials)
-        h.groups_last = trials[-1].number if trials else -1
-        return [dict(g) for g in h.groups]
-
     def sample_relative_batch(self, study, search_space: dict[str, BaseDistribution], n_asks: int) -> list[dict]:
         """`n_asks` joint suggestions against the current (frozen) history in ONE device call.
 
@@ -375,12 +498,12 @@ class B200TPESampler(BaseSampler):
                              "(constant-liar asks depend on each other)")
         if search_space == {} or n_asks <= 0:
             return [{} for _ in range(max(n_asks, 0))]
-        trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
-        if len(trials) < self._n_startup_trials:
-            return [{} for _ in range(n_asks)]
         with self._lock:
-            n_finished, cols = self._sync(study, None, search_space)
-            cfg = dict(n_below=int(self._gamma(n_finished)), n_candidates=self._n_ei_candidates,
+            self._note_changes(self._poll(study))
+            if self._hist.n_finished < self._n_startup_trials:
+                return [{} for _ in range(n_asks)]
+            cols = self._sync(study, None, search_space)
+            cfg = dict(n_below=int(self._gamma(self._hist.n_finished)), n_candidates=self._n_ei_candidates,
                        multivariate=self._multivariate, prior_weight=self._prior_weight,
                        magic_clip=self._magic_clip, endpoints=self._endpoints)
             eng = self._eng()
@@ -404,71 +527,71 @@ class B200TPESampler(BaseSampler):
             columns.append(col if isinstance(d, FloatDistribution) else [d.to_external_repr(v) for v in col])
         return [dict(zip(names, row)) for row in zip(*columns)]
 
-    def _rows(self, study, trials, names: list[str], dists: list[BaseDistribution]):
-        sign = -1.0 if (not study._is_multi_objective() and study.direction == StudyDirection.MAXIMIZE) else 1.0
+    def _rows(self, study, trials, names: list[str], dists: list[BaseDistribution], current: int | None):
+        """History rows of `trials` (the arrays tpe_history_set / tpe_history_update take): internal
+        representation of the parameters (NaN = absent), category and the reference's sort key inside it
+        (sampler.py:686-722, :735-742, :782-821), objective values for multi-objective studies."""
+        multi = study._is_multi_objective()
+        sign = -1.0 if (not multi and study.direction == StudyDirection.MAXIMIZE) else 1.0
         n, p = len(trials), len(names)
         X = np.full((n, p), np.nan)
-        cat = np.zeros(n, dtype=np.int8)
+        cat = np.full(n, _lib.CAT_EXCLUDED, dtype=np.int8)
         key = np.zeros((n, 2))
-        multi = study._is_multi_objective()
         signs = np.asarray([-1.0 if d == StudyDirection.MAXIMIZE else 1.0 for d in study.directions])
         vals = np.full((n, len(signs)), np.inf) if multi else None
+        index = {name: j for j, name in enumerate(names)}
+        complete, pruned, running = TrialState.COMPLETE, TrialState.PRUNED, TrialState.RUNNING
+        constrained = self._constraints_func is not None
         for i, t in enumerate(trials):
-            params = self._get_params(t)
-            for j, name in enumerate(names):
-                if name in params:
-                    X[i, j] = dists[j].to_internal_repr(params[name])
-            if t.state == TrialState.RUNNING:
+            state = t.state
+            if state == running:
+                # constant liar: the other workers' trials sit in g(x) (sampler.py:526-535, :695-698)
+                if not self._constant_liar or t.number == current:
+                    continue
                 cat[i] = _lib.CAT_RUNNING
-            elif self._constraints_func is not None and (score := _infeasible_score(t)) > 0:
+            elif state != complete and state != pruned:
+                continue  # WAITING, FAIL
+            elif constrained and (score := _infeasible_score(t)) > 0:
                 cat[i] = _lib.CAT_INFEASIBLE
                 key[i, 0] = score
-            elif t.state == TrialState.COMPLETE:
+            elif state == complete:
                 cat[i] = _lib.CAT_COMPLETE
                 key[i, 0] = sign * t.value if not multi else 0.0
             else:
                 cat[i] = _lib.CAT_PRUNED
                 key[i] = _pruned_key(t, sign) if not multi else (1, 0.0)
+            row = X[i]
+            for name, value in self._get_params(t).items():
+                j = index.get(name)
+                if j is not None:
+                    row[j] = dists[j].to_internal_repr(value)
             if multi and t.values is not None:
                 vals[i] = signs * np.asarray(t.values, dtype=float)
         return X, cat, key, vals
 
-    def _sync(self, study, trial, search_space: dict[str, BaseDistribution]) -> tuple[int, list[int]]:
-        """Bring the device history up to date; returns (#finished trials, device columns).
+    def _note_changes(self, changed: list[tuple[int, Any]]) -> None:
+        """What a poll found goes to the device at the next sync (many polls never get there: startup
+        trials, search-space queries)."""
+        if changed:
+            self._hist.backlog.update(changed)
 
-        Rows are kept in trial-number order.  Finished trials are appended as they appear.  With
-        ``constant_liar`` the RUNNING trials (other than the one being sampled) are rows too
-        (sampler.py:526-535); a RUNNING row is re-uploaded in place at every ask (its parameters may still
-        grow) until the trial has finished, so an ask costs O(#running), not O(#trials)."""
+    def _sync(self, study, trial, search_space: dict[str, BaseDistribution]) -> list[int]:
+        """Bring the device history up to date with the log (the caller has polled); returns the device
+        columns of `search_space`.  O(#rows that changed) unless a column is new: then the history is
+        re-uploaded once with a column for every parameter the study has used so far."""
         h = self._hist
         eng = self._eng()
-        if self._constant_liar:
-            states = (TrialState.COMPLETE, TrialState.PRUNED, TrialState.RUNNING)
-            trials = study._get_trials(deepcopy=False, states=states, use_cache=False)
-            for i in range(len(trials) - 1, max(len(trials) - 4097, -1), -1):  # the current trial is recent
-                if trials[i].number == trial.number:
-                    trials = trials[:i] + trials[i + 1:]
-                    break
-            else:
-                trials = [t for t in trials if t.number != trial.number]
-        else:
-            trials = study._get_trials(deepcopy=False, states=(TrialState.COMPLETE, TrialState.PRUNED), use_cache=True)
-        token = (getattr(study, "_study_id", None), id(getattr(study, "_storage", None)),
-                 tuple(getattr(study, "directions", ())))
-        rebuild = h.token != token
+        current = None if trial is None else trial.number
+        rebuild = h.dev_token != (id(h.storage), h.token) or h.dev_rows > h.rows
         for name, d in search_space.items():
             j = h.columns.get(name)
             if j is None or h.dists[j] != d:
                 rebuild = True
-        if not rebuild:
-            if not (h.n <= len(trials) and (h.n == 0 or trials[h.n - 1].number == h.last_number)):
-                rebuild = True
-            elif any(trials[pos].number != num for pos, num in h.running.items()):
-                rebuild = True  # a RUNNING trial disappeared (FAIL): the positions have shifted
+        backlog = h.backlog
         if rebuild:
-            names = list(h.columns) if h.token == token else []
-            dists = list(h.dists) if h.token == token else []
-            for name, d in search_space.items():
+            names = list(h.columns) if h.dev_token == (id(h.storage), h.token) else []
+            dists = list(h.dists) if names else []
+            for name, d in list(h.all_dists.items()) + list(search_space.items()):
                 if name in names:
                     dists[names.index(name)] = d
                 else:
@@ -476,39 +599,58 @@ class B200TPESampler(BaseSampler):
                     dists.append(d)
             h.columns = {name: j for j, name in enumerate(names)}
             h.dists = dists
-            h.token = token
+            h.dev_token = (id(h.storage), h.token)
             eng.set_space([_spec_of(nm, d, self._cat_dist_funcs) for nm, d in zip(names, dists)])
-            X, cat, key, vals = self._rows(study, trials, names, dists)
+            trials = h.all_trials(study, self._multivariate or not self._constant_liar)
+            X, cat, key, vals = self._rows(study, trials, names, dists, current)
             eng.set_history(X, cat, key)
             if vals is not None:
-                eng.set_values(vals, 0)
-            h.running = {i: t.number for i, t in enumerate(trials) if t.state == TrialState.RUNNING}
-            h.n_finished = len(trials) - len(h.running)
-        else:
+                eng.set_values(vals, 0, len(study.directions))
+            h.dev_rows = len(trials)
+            h.dev_cat = {row: int(cat[row]) for row in h.pending if row < h.dev_rows}
+            backlog.clear()
+            return [h.columns[name] for name in search_space]
+        # constant liar: which unfinished rows sit in g(x) depends on who is asking
+        if self._constant_liar:
+            for row, slot in h.pending.items():
+                if row in backlog:
+                    continue
+                t = slot[1]
+                want = _lib.CAT_RUNNING if (t.state == TrialState.RUNNING and t.number != current) else _lib.CAT_EXCLUDED
+                if h.dev_cat.get(row, _lib.CAT_EXCLUDED) != want:
+                    backlog[row] = t
+        # an unfinished trial nobody may see stays an EXCLUDED placeholder however often its object changes
+        # (every suggest_* of a running trial replaces it): nothing to upload
+        for row in [r for r in backlog if r < h.dev_rows and r in h.pending
+                    and h.dev_cat.get(r, _lib.CAT_EXCLUDED) == _lib.CAT_EXCLUDED]:
+            t = backlog[row]
+            if not (self._constant_liar and t.state == TrialState.RUNNING and t.number != current):
+                del backlog[row]
+        if backlog:
             names = list(h.columns)
-            for pos in sorted(h.running):  # refresh the rows of trials that were RUNNING at the last ask
-                t = trials[pos]
-                X, cat, key, vals = self._rows(study, [t], names, h.dists)
-                eng.update_history(X, cat, key, pos)
+            rows = sorted(backlog)
+            i = 0
+            while i < len(rows):  # contiguous runs: one tpe_history_update each (it may extend the history)
+                j = i + 1
+                while j < len(rows) and rows[j] == rows[j - 1] + 1:
+                    j += 1
+                at = rows[i]
+                if at > h.dev_rows:  # rows nobody reported (cannot happen: new rows are reported in order)
+                    raise RuntimeError(f"history rows {h.dev_rows}..{at} were never uploaded")
+                run = [backlog[r] for r in rows[i:j]]
+                X, cat, key, vals = self._rows(study, run, names, h.dists, current)
+                eng.update_history(X, cat, key, at)
                 if vals is not None:
-                    eng.set_values(vals, pos)
-                if t.state != TrialState.RUNNING:
-                    del h.running[pos]
-                    h.n_finished += 1
-            if len(trials) > h.n:
-                fresh = trials[h.n:]
-                X, cat, key, vals = self._rows(study, fresh, names, h.dists)
-                eng.append_history(X, cat, key)
-                if vals is not None:
-                    eng.set_values(vals, h.n)
-                for i, t in enumerate(fresh):
-                    if t.state == TrialState.RUNNING:
-                        h.running[h.n + i] = t.number
+                    eng.set_values(vals, at, len(study.directions))
+                for r, c in zip(rows[i:j], cat):
+                    if r in h.pending:
+                        h.dev_cat[r] = int(c)
                     else:
-                        h.n_finished += 1
-        h.n = len(trials)
-        h.last_number = trials[-1].number if trials else -1
-        return h.n_finished, [h.columns[name] for name in search_space]
+                        h.dev_cat.pop(r, None)
+                h.dev_rows = max(h.dev_rows, at + len(run))
+                i = j
+            backlog.clear()
+        return [h.columns[name] for name in search_space]
 
     #: asks needing at least this many uniforms have them generated on the device
     DEVICE_RNG_MIN = 4096
@@ -523,44 +665,43 @@ class B200TPESampler(BaseSampler):
     def _sample_and_select(self, eng: TPEEngine, search_space: dict[str, BaseDistribution], n_asks: int,
                            build) -> np.ndarray:
         """Uniforms + stages 3-4.  Large asks: the library generates the generator's next outputs on the
-        GPU (k_mt19937_uniform, the same MT19937 stream bit for bit) while `build()` queues the
-        estimator builds, and the host generator is then moved to the state after the draws; small asks
-        draw on the host."""
+        GPU (k_mt19937_uniform, the same MT19937 stream bit for bit) while the estimator builds run, and the
+        host generator is moved to the state after the draws on demand; small asks draw on the host.  The
+        estimators are built (and validated) BEFORE the generator moves, as in the reference (sampler.py:544-553):
+        an ask that fails in the build leaves the stream untouched."""
         n = n_asks * self._n_ei_candidates * (1 + len(search_space))
+        build()
         if n >= self.DEVICE_RNG_MIN:
             if self._rng.on_device(eng):
                 eng.stage_rng(None, n)            # continue from the state the previous ask ended in
             else:
                 eng.stage_rng(self._rng.rng, n)
-            build()
+            self._rng.mark_device(eng)            # from here on the device holds the newer state
             x, _, _ = eng.sample_and_select(None, n_asks)
-            self._rng.mark_device(eng)            # the host generator is brought up to date on demand
         else:
-            build()
             x, _, _ = eng.sample_and_select(self._rng.rng.random_sample(n), n_asks)
         return x
 
     def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
-        """TPESampler._sample (sampler.py:523-560)."""
-        with self._lock:
-            n_finished, cols = self._sync(study, trial, search_space)
-            n_below = self._gamma(n_finished)
-            cfg = dict(n_below=int(n_below), n_candidates=self._n_ei_candidates, multivariate=self._multivariate,
-                       prior_weight=self._prior_weight, magic_clip=self._magic_clip, endpoints=self._endpoints)
-            if self._prior_weight < 0:
-                raise ValueError("A non-negative value must be specified for prior_weight,"
-                                 f" but got {self._prior_weight}.")
-            eng = self._eng()
-            if self._weights is default_weights:
-                eng.prepare(cols, **cfg)
-                x = self._sample_and_select(eng, search_space, 1, eng.build)
-            else:
-                _, nb, na = eng.prepare(cols, **cfg)
-                # multi-objective studies weight l(x) by hypervolume contributions (computed by the
-                # library); the user's weights function then only shapes g(x) (sampler.py:570-584)
-                wb = None if study._is_multi_objective() else _checked_weights(self._weights, nb)
-                wa = _checked_weights(self._weights, na)
-                x = self._sample_and_select(eng, search_space, 1, lambda: eng.build(wb, wa))
+        """TPESampler._sample (sampler.py:523-560).  The caller holds the lock and has polled."""
+        cols = self._sync(study, trial, search_space)
+        n_below = self._gamma(self._hist.n_finished)
+        cfg = dict(n_below=int(n_below), n_candidates=self._n_ei_candidates, multivariate=self._multivariate,
+                   prior_weight=self._prior_weight, magic_clip=self._magic_clip, endpoints=self._endpoints)
+        if self._prior_weight < 0:
+            raise ValueError("A non-negative value must be specified for prior_weight,"
+                             f" but got {self._prior_weight}.")
+        eng = self._eng()
+        if self._weights is default_weights:
+            eng.prepare(cols, **cfg)
+            x = self._sample_and_select(eng, search_space, 1, eng.build)
+        else:
+            _, nb, na = eng.prepare(cols, **cfg)
+            # multi-objective studies weight l(x) by hypervolume contributions (computed by the
+            # library); the user's weights function then only shapes g(x) (sampler.py:570-584)
+            wb = None if study._is_multi_objective() else _checked_weights(self._weights, nb)
+            wa = _checked_weights(self._weights, na)
+            x = self._sample_and_select(eng, search_space, 1, lambda: eng.build(wb, wa))
         out = {}
         for j, (name, d) in enumerate(search_space.items()):
             out[name] = d.to_external_repr(float(x[0, j]))

@@ -78,21 +78,6 @@ def test_motpe_suggestions_match_reference(eng):
         np.testing.assert_allclose(ret, g[t + "ret"], rtol=1e-11, atol=1e-12)
 
 
-def test_motpe_through_the_sampler_plugin():
-    """4-objective study driven by study.optimize (BASELINE config 4 in miniature)."""
-    from optuna_b200 import B200TPESampler, mini
-
-    def obj(t):
-        x = [t.suggest_float(f"x{j}", 0, 1) for j in range(4)]
-        return [sum((xi - c) ** 2 for xi in x) for c in (0.2, 0.4, 0.6, 0.8)]
-
-    for mv in (False, True):
-        s = mini.create_study(sampler=B200TPESampler(seed=5, multivariate=mv), directions=["minimize"] * 4)
-        s.optimize(obj, n_trials=40)
-        assert len(s.trials) == 40
-        assert all(0 <= v <= 1 for t in s.trials for v in t.params.values())
-
-
 def test_mo_rank_properties_at_scale(eng):
     """Config-4 shape (N = 20 000, 4 objectives): the selected below set is exactly what the oracle
     selects (ranks by peeling + HSSP on the tie rank)."""

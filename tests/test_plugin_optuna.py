@@ -1,0 +1,403 @@
+"""B200TPESampler behind the reference's OWN ``Study`` (unmodified optuna, oracle/_ref), compared live with
+``optuna.samplers.TPESampler`` driven through the same calls with the same seed.
+
+Every scenario runs twice: with the CPU oracle answering the array-level calls (checks the host glue -- trial
+log, device mirror, search spaces, RNG hand-over -- anywhere) and, marked ``gpu``, with libtpe_b200.so (the
+product).  Reference behaviour: optuna/samplers/_tpe/sampler.py:386-560, the conformance suite
+optuna/testing/pytest_samplers.py:81-540, boundary cases of SURVEY.md section 8b."""
+import math
+import pickle
+import warnings
+
+import numpy as np
+import pytest
+
+optuna = pytest.importorskip("optuna")
+from optuna.samplers import TPESampler  # noqa: E402
+from optuna.trial import TrialState  # noqa: E402
+
+from tests._util import load  # noqa: E402
+
+warnings.filterwarnings("ignore", category=optuna.exceptions.ExperimentalWarning)
+
+
+def same(pa, pb, tol=1e-9):
+    """Suggested parameter dicts: ints / categorical choices exact, floats to `tol` relative."""
+    assert pa.keys() == pb.keys(), (pa, pb)
+    for k in pa:
+        a, b = pa[k], pb[k]
+        if isinstance(b, float):
+            assert type(a) is float and abs(a - b) <= tol * max(1.0, abs(b)), (k, a, b)
+        else:
+            assert type(a) is type(b) and a == b, (k, a, b)
+
+
+def run_both(make_sampler, objective, n_trials, study_kw=None, ties=False, **kw):
+    """study.optimize on both samplers; returns (ours, reference) studies after comparing every trial.
+    ties: the scenario repeats numeric observations (see conftest.make_sampler.reference)."""
+    study_kw = study_kw or {}
+    a = optuna.create_study(sampler=make_sampler(**kw), **study_kw)
+    b = optuna.create_study(sampler=make_sampler.reference(ties, **kw), **study_kw)
+    a.optimize(objective, n_trials=n_trials)
+    b.optimize(objective, n_trials=n_trials)
+    assert len(a.trials) == len(b.trials) == n_trials
+    for ta, tb in zip(a.trials, b.trials):
+        assert ta.state == tb.state
+        same(ta.params, tb.params)
+    return a, b
+
+
+def branin(t):
+    x = t.suggest_float("x", -5, 10)
+    y = t.suggest_float("y", 0, 15)
+    return ((y - 5.1 / (4 * math.pi**2) * x * x + 5 / math.pi * x - 6) ** 2
+            + 10 * (1 - 1 / (8 * math.pi)) * math.cos(x) + 10)
+
+
+def mixed(t):
+    a = t.suggest_float("a", -1.0, 1.0)
+    b = t.suggest_float("b", 1e-3, 10.0, log=True)
+    c = t.suggest_float("c", 0.0, 2.0, step=0.25)
+    d = t.suggest_int("d", -3, 7)
+    e = t.suggest_int("e", 1, 64, log=True)
+    f = t.suggest_int("f", 0, 30, step=5)
+    g = t.suggest_categorical("g", ["p", "q", None, 3])
+    assert type(a) is float and type(b) is float and type(c) is float
+    assert type(d) is int and type(e) is int and type(f) is int
+    v = a * a + math.log(b) ** 2 + c + d * 0.1 + abs(e - 8) * 0.05 + f * 0.01 + (g == "p")
+    if t.number % 7 == 3:
+        t.report(v, 1)
+        t.report(v * 0.9, 3)
+        raise optuna.TrialPruned()
+    return v
+
+
+@pytest.mark.parametrize("mv", [False, True])
+def test_branin_200_trials_is_the_reference_trajectory(make_sampler, mv):
+    """BASELINE config 1: same seed => same 200-trial trajectory as optuna.samplers.TPESampler -- the live one
+    and the committed golden (tests/golden/branin.npz, generated from the reference by oracle/gen_golden.py)."""
+    study = optuna.create_study(sampler=make_sampler(seed=0, multivariate=mv))
+    study.optimize(branin, n_trials=200)
+    g = load("branin.npz")
+    ref = g[f"branin_{'mv' if mv else 'uni'}/xy"]
+    xy = np.asarray([[t.params["x"], t.params["y"]] for t in study.trials])
+    assert np.array_equal(xy[:10], ref[:10])  # startup trials: RandomSampler's stream, bit-identical
+    np.testing.assert_allclose(xy, ref, rtol=1e-9, atol=1e-9)
+    if not mv:
+        assert abs(study.best_value - 0.4069652013131506) < 1e-9
+    live = optuna.create_study(sampler=TPESampler(seed=0, multivariate=mv))
+    live.optimize(branin, n_trials=60)
+    for ta, tb in zip(study.trials, live.trials):
+        same(ta.params, tb.params)
+
+
+@pytest.mark.parametrize("mv", [False, True])
+@pytest.mark.parametrize("direction", ["minimize", "maximize"])
+def test_mixed_space_with_pruned_trials(make_sampler, mv, direction):
+    run_both(make_sampler, mixed, 45, {"direction": direction}, ties=True, seed=3, multivariate=mv, n_startup_trials=5)
+
+
+def test_custom_gamma_weights_and_constraints(make_sampler):
+    def obj(t):
+        x = t.suggest_float("x", -3, 3)
+        k = t.suggest_int("k", 0, 4)
+        t.set_user_attr("c", x - 1.0)
+        if t.number % 5 == 4:
+            t.report(abs(x), 1)
+            raise optuna.TrialPruned()
+        return x * x + k
+
+    kw = dict(seed=1, gamma=lambda n: max(1, n // 4), weights=lambda n: np.arange(1, n + 1) ** 0.5,
+              constraints_func=lambda tr: (tr.user_attrs["c"], -1.0), n_startup_trials=5)
+    a, b = run_both(make_sampler, obj, 40, ties=True, **kw)
+    assert [t.system_attrs.get("constraints") for t in a.trials] == [t.system_attrs.get("constraints") for t in b.trials]
+    with pytest.raises(ValueError):
+        bad = optuna.create_study(sampler=make_sampler(seed=1, weights=lambda n: -np.ones(n), n_startup_trials=2))
+        bad.optimize(lambda t: t.suggest_float("x", 0, 1), n_trials=5)
+    with pytest.raises(ValueError):  # samplers/_base.py:253-254
+        nan = optuna.create_study(sampler=make_sampler(seed=1, constraints_func=lambda tr: (float("nan"),)))
+        nan.optimize(lambda t: t.suggest_float("x", 0, 1), n_trials=2)
+
+
+def test_hyperopt_parameters_and_endpoints(make_sampler):
+    kw = dict(TPESampler.hyperopt_parameters(), seed=9, consider_endpoints=True, consider_magic_clip=False,
+              prior_weight=0.5)
+    from optuna_b200.sampler import B200TPESampler, default_weights, hyperopt_default_gamma
+    mine = B200TPESampler.hyperopt_parameters()
+    assert mine.keys() == TPESampler.hyperopt_parameters().keys()
+    kw_a = dict(kw, gamma=hyperopt_default_gamma, weights=default_weights)
+    a = optuna.create_study(sampler=make_sampler(**kw_a))
+    b = optuna.create_study(sampler=make_sampler.reference(True, **(kw_a if make_sampler.kind == "cuda" else kw)))
+    a.optimize(mixed, n_trials=50)
+    b.optimize(mixed, n_trials=50)
+    for ta, tb in zip(a.trials, b.trials):
+        same(ta.params, tb.params)
+
+
+def test_constant_liar_batches_out_of_order_tells_and_failures(make_sampler):
+    """constant_liar=True (sampler.py:435-443, :493-509, :526-535): RUNNING trials -- their relative parameters
+    relayed through system attrs -- sit in g(x); tells arrive out of order; a trial fails."""
+    def obj(t):
+        x = t.suggest_float("x", -2, 2)
+        k = t.suggest_int("k", 0, 6)
+        c = t.suggest_categorical("c", ["u", "v", "w"])
+        return x * x + (k - 3) ** 2 + (c == "v")
+
+    def scenario(sampler):
+        s = optuna.create_study(sampler=sampler)
+        s.optimize(obj, n_trials=10)
+        out = []
+        pending = [s.ask() for _ in range(5)]
+        vals = [obj(t) for t in pending]
+        out += [dict(t.params) for t in pending]
+        s.tell(pending[3], vals[3])                        # out of order
+        s.tell(pending[1], state=TrialState.FAIL)          # never counts
+        more = [s.ask() for _ in range(3)]
+        out += [dict(t.params) for t in more if obj(t) is not None]
+        s.tell(pending[0], vals[0])
+        last = [s.ask() for _ in range(2)]
+        out += [dict(t.params) for t in last if obj(t) is not None]
+        assert any("tpe:relative_params:0" in t.system_attrs for t in s.trials[10:]) == sampler._multivariate
+        return out
+
+    for mv in (True, False):
+        kw = dict(seed=5, multivariate=mv, constant_liar=True, n_startup_trials=5)
+        got, want = scenario(make_sampler(**kw)), scenario(make_sampler.reference(True, **kw))
+        assert len(got) == len(want) == 10
+        for pa, pb in zip(got, want):
+            same(pa, pb)
+        assert len({tuple(sorted(p.items())) for p in got}) > 5
+
+
+def test_group_decomposed_conditional_space(make_sampler):
+    """group=True (sampler.py:394-405, :417-431; search_space/group_decomposed.py:14-68)."""
+    def obj(t):
+        kind = t.suggest_categorical("kind", ["a", "b"])
+        x = t.suggest_float("x", -1, 1)
+        if kind == "a":
+            return x * x + t.suggest_float("ya", 0, 2)
+        return x * x + (t.suggest_int("yb", 0, 5) - 2) ** 2 + t.suggest_float("zb", 1e-2, 1, log=True)
+
+    a, b = run_both(make_sampler, obj, 50, seed=4, multivariate=True, group=True, n_startup_trials=6)
+    names = sorted(sorted(g) for g in a.sampler._groups_now)
+    assert names == [["kind", "x"], ["ya"], ["yb", "zb"]]
+    assert [sorted(g) for g in a.sampler._groups_now] == [sorted(g) for g in b.sampler._search_space_group.search_spaces]
+    from optuna_b200 import B200TPESampler
+    with pytest.raises(ValueError):
+        B200TPESampler(group=True)
+
+
+def test_conditional_space_without_group_warns_and_matches(make_sampler):
+    def obj(t):
+        kind = t.suggest_categorical("kind", ["a", "b"])
+        x = t.suggest_float("x", -1, 1)
+        y = t.suggest_float("ya", 0, 2) if kind == "a" else t.suggest_int("yb", 0, 5)
+        return x * x + y
+
+    run_both(make_sampler, obj, 40, seed=8, multivariate=True, n_startup_trials=6)
+    run_both(make_sampler, obj, 40, ties=True, seed=8, multivariate=False, n_startup_trials=6)
+
+
+def test_categorical_distance_func(make_sampler):
+    def obj(t):
+        a = t.suggest_categorical("a", [0, 1, 2, 3])
+        x = t.suggest_float("x", -2, 2)
+        return (a - 2) ** 2 + x * x
+
+    run_both(make_sampler, obj, 35, seed=2, multivariate=True, n_startup_trials=4,
+             categorical_distance_func={"a": lambda p, q: abs(p - q)})
+
+
+@pytest.mark.parametrize("n_obj", [2, 3, 4])
+def test_motpe_through_the_study(make_sampler, n_obj):
+    """MOTPE (sampler.py:745-779, :824-863) with mixed directions; univariate and multivariate."""
+    cs = [0.2, 0.4, 0.6, 0.8][:n_obj]
+    dirs = ["minimize", "maximize", "minimize", "minimize"][:n_obj]
+
+    def obj(t):
+        xs = [t.suggest_float(f"x{j}", 0, 1) for j in range(3)]
+        out = [sum((x - c) ** 2 for x in xs) for c in cs]
+        out[1] = -out[1] if n_obj > 1 else out[1]
+        return out
+
+    for mv in (False, True):
+        run_both(make_sampler, obj, 40, {"directions": dirs}, seed=5, multivariate=mv)
+
+
+def test_dynamic_range_and_single_distributions(make_sampler):
+    """pytest_samplers.py:243-345: a parameter whose range changes between trials (independent sampling) and
+    distributions holding a single value."""
+    def obj(t):
+        hi = 5 + t.number % 3
+        x = t.suggest_int("x", -hi, hi)
+        s = t.suggest_float("s", 1.0, 1.0)
+        c = t.suggest_categorical("c", ["only"])
+        return x * x + s + (c == "only")
+
+    for mv in (False, True):
+        run_both(make_sampler, obj, 30, ties=True, seed=6, multivariate=mv, n_startup_trials=4)
+
+
+def test_enqueued_added_and_failed_trials(make_sampler):
+    """WAITING trials (study.enqueue_trial), trials added from outside (study.add_trials) and exceptions in the
+    objective: rows nobody may see yet / ever must not disturb the log."""
+    def obj(t):
+        x = t.suggest_float("x", -3, 3)
+        y = t.suggest_int("y", 0, 9)
+        if t.number % 6 == 5:
+            raise RuntimeError("boom")
+        return (x - 1) ** 2 + y
+
+    def scenario(sampler):
+        s = optuna.create_study(sampler=sampler)
+        s.optimize(obj, n_trials=12, catch=(RuntimeError,))
+        s.enqueue_trial({"x": 0.5, "y": 3})
+        s.enqueue_trial({"x": -0.5})
+        s.optimize(obj, n_trials=6, catch=(RuntimeError,))
+        dist = {"x": optuna.distributions.FloatDistribution(-3, 3), "y": optuna.distributions.IntDistribution(0, 9)}
+        s.add_trials([optuna.trial.create_trial(value=float(i), params={"x": 0.1 * i, "y": i}, distributions=dist)
+                      for i in range(4)])
+        s.optimize(obj, n_trials=10, catch=(RuntimeError,))
+        return s
+
+    for mv in (False, True):
+        kw = dict(seed=12, multivariate=mv, n_startup_trials=5)
+        a, b = scenario(make_sampler(**kw)), scenario(make_sampler.reference(True, **kw))
+        assert [t.state for t in a.trials] == [t.state for t in b.trials]
+        for ta, tb in zip(a.trials, b.trials):
+            same(ta.params, tb.params)
+
+
+def test_partial_fixed_sampler_and_hyperband_wrapper(make_sampler):
+    """PartialFixedSampler hands sample_relative a subset of the inferred space (_partial_fixed.py:65-84);
+    HyperbandPruner hands the sampler a _BracketStudy that whitelists a few attributes
+    (pruners/_hyperband.py:273-324) -- a fresh wrapper per call."""
+    def obj(t):
+        x = t.suggest_float("x", -2, 2)
+        y = t.suggest_float("y", -2, 2)
+        for step in range(4):
+            t.report((x * x + y * y) * (1 + 0.1 * (3 - step)), step)
+            if t.should_prune():
+                raise optuna.TrialPruned()
+        return x * x + y * y
+
+    def scenario(base):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fixed = optuna.samplers.PartialFixedSampler({"y": 0.25}, base)
+        s = optuna.create_study(sampler=fixed, pruner=optuna.pruners.HyperbandPruner(min_resource=1, max_resource=4),
+                                study_name="hb")
+        s.optimize(obj, n_trials=40)
+        return s
+
+    for mv in (False, True):
+        kw = dict(seed=21, multivariate=mv, n_startup_trials=5)
+        a, b = scenario(make_sampler(**kw)), scenario(TPESampler(**kw))
+        assert [t.state for t in a.trials] == [t.state for t in b.trials]
+        assert all(t.params.get("y", 0.25) == 0.25 for t in a.trials)
+        for ta, tb in zip(a.trials, b.trials):
+            same(ta.params, tb.params)
+
+
+def test_one_sampler_shared_by_n_jobs_threads(make_sampler):
+    """study/_optimize.py:87-121: one sampler object, n_jobs threads; reseed_rng per thread (:142-143)."""
+    s = optuna.create_study(sampler=make_sampler(seed=2, multivariate=True, n_startup_trials=8))
+    s.optimize(mixed, n_trials=60, n_jobs=4)
+    done = [t for t in s.trials if t.state in (TrialState.COMPLETE, TrialState.PRUNED)]
+    assert len(s.trials) == 60 and len(done) == 60
+    h = s.sampler._hist
+    s.sampler.sample_independent(s, optuna.trial.create_trial(value=0.0), "a", optuna.distributions.FloatDistribution(-1.0, 1.0))
+    assert h.n_finished == 60 and not [r for r in h.pending if h.pending[r][1].state.is_finished()]
+
+
+def test_pickled_study_and_sampler_continue_identically(make_sampler):
+    """study/study.py:99-107: a study pickles with its sampler; the device state is a cache."""
+    def obj(t):
+        return (t.suggest_float("x", 0, 1) - 0.3) ** 2 + t.suggest_int("k", 0, 5) * 0.01
+
+    a = optuna.create_study(sampler=make_sampler(seed=11))
+    a.optimize(obj, n_trials=20)
+    clone = pickle.loads(pickle.dumps(a))
+    assert clone.sampler._engine is None
+    clone.sampler._engine_cls = type(a.sampler)._engine_cls
+    a.optimize(obj, n_trials=10)
+    clone.optimize(obj, n_trials=10)
+    assert [t.params for t in a.trials] == [t.params for t in clone.trials]
+    clone.sampler.close()
+    b = optuna.create_study(sampler=make_sampler.reference(True, seed=11))
+    b.optimize(obj, n_trials=30)
+    for ta, tb in zip(a.trials, b.trials):
+        same(ta.params, tb.params)
+
+
+def test_sync_cost_is_proportional_to_the_changes(make_sampler):
+    """per ask the history mirror receives the rows that changed, not the history."""
+    if make_sampler.kind != "oracle":
+        pytest.skip("call log of the stand-in engine")
+    s = optuna.create_study(sampler=make_sampler(seed=0, multivariate=True, n_startup_trials=5))
+    s.optimize(branin, n_trials=40)
+    calls = s.sampler._engine.calls
+    assert [c[0] for c in calls].count("set_history") == 1
+    ups = [c[1] for c in calls if c[0] == "update_history"]
+    assert len(ups) == 40 - 5 - 1 and max(ups) <= 2
+    eng = s.sampler._engine
+    X, cat, key, _ = s.sampler._rows(s, s.get_trials(deepcopy=False), list(s.sampler._hist.columns),
+                                     s.sampler._hist.dists, None)
+    n = eng.history_size
+    assert n >= 39 and np.array_equal(eng.cat[:39], cat[:39]) and np.array_equal(eng.key[:39], key[:39])
+    assert np.array_equal(np.nan_to_num(eng.X[:39], nan=-7.0), np.nan_to_num(X[:39], nan=-7.0))
+
+
+def test_batched_ask_equals_sequential_asks(make_sampler):
+    """BASELINE config 5 semantics: ask_batch(n) == n sequential study.ask() with no tell between."""
+    from optuna_b200.batch import ask_batch
+
+    def obj(t):
+        return sum((t.suggest_float(f"x{j}", 0, 1) - 0.3) ** 2 for j in range(5)) + t.suggest_int("k", 0, 9) * 0.01
+
+    def warm(sampler):
+        s = optuna.create_study(sampler=sampler)
+        s.optimize(obj, n_trials=30)
+        return s
+
+    kw = dict(seed=7, multivariate=True, n_ei_candidates=32)
+    a, b = warm(make_sampler(**kw)), warm(make_sampler.reference(**kw))
+    batch = ask_batch(a, 50)
+    seq = [b.ask() for _ in range(50)]
+    pa = [[t.suggest_float(f"x{j}", 0, 1) for j in range(5)] + [t.suggest_int("k", 0, 9)] for t in batch]
+    pb = [[t.suggest_float(f"x{j}", 0, 1) for j in range(5)] + [t.suggest_int("k", 0, 9)] for t in seq]
+    np.testing.assert_allclose(pa, pb, rtol=1e-9, atol=0)
+    assert len({tuple(p) for p in pa}) > 40  # different uniforms per ask
+
+
+def test_device_generated_uniforms_give_the_reference_suggestions(make_sampler):
+    """Asks large enough for the device MT19937 (>= DEVICE_RNG_MIN uniforms): consecutive asks, a foreign draw in
+    between and close() must all reproduce what the reference computes from its host RandomState."""
+    from optuna_b200 import B200TPESampler
+    P, C, n = 16, 1024, 300
+    assert C * (1 + P) >= B200TPESampler.DEVICE_RNG_MIN
+    rs = np.random.RandomState(2)
+    space = {f"x{j:02d}": optuna.distributions.FloatDistribution(0.0, 1.0) for j in range(P)}
+    names = list(space)
+    X = rs.uniform(0, 1, (n, P))
+    loss = ((X - 0.4) ** 2).sum(1)
+    hist = [optuna.trial.create_trial(value=float(loss[i]), params=dict(zip(names, X[i].tolist())), distributions=space)
+            for i in range(n)]
+
+    def run(sampler):
+        study = optuna.create_study(sampler=sampler)
+        study.add_trials(hist)
+        got = []
+        for it in range(6):
+            t = study.ask()
+            got.append([t.suggest_float(nm, 0.0, 1.0) for nm in names])
+            if it == 2:
+                sampler._rng.rng.random_sample(3)  # someone else consumes from the generator
+            if it == 4 and hasattr(sampler, "close"):
+                sampler.close()                    # engine re-created at the next ask
+        return got, sampler._rng.rng.random_sample(4)
+
+    kw = dict(seed=11, n_ei_candidates=C, multivariate=True)
+    (got, tail), (want, tail_ref) = run(make_sampler(**kw)), run(make_sampler.reference(**kw))
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=0)
+    assert np.array_equal(tail, tail_ref)  # the generator ends in the reference's state
