@@ -13,11 +13,15 @@ the C x K x P grid + argmax.  Nothing is cached between steps.
            history already in HBM; time = wall clock between device synchronisations around the K
            steps (each call ends with a stream sync), max over ranks; the CUDA-event time of the same
            steps is reported as ``device_ms_per_step``.
-``e2e``    the same metric through the plugin a user calls -- B200TPESampler.sample_relative(study,
-           trial, search_space) on a 100k-trial study: host uniforms (numpy RandomState, the
-           reference's RNG order) -> H2D, result D2H, to_external_repr.
-``--impl reference``  the reference algorithm on the host cores (oracle port of the NumPy path; the
-           reference is pure Python and does not travel to the GPU box), bounded sample per step.
+``e2e``    the same metric through the call a user makes: the UNMODIFIED optuna package (oracle/_ref,
+           the reference itself) drives ``B200TPESampler`` -- ``optuna.create_study(sampler=...)`` with the
+           100k trials added by ``study.add_trials``, then per step ``trial = study.ask()``, 32 x
+           ``trial.suggest_float`` (the first one triggers infer_relative_search_space + sample_relative),
+           ``study.tell(trial, value)``: every step appends a trial, so every step also ingests one.
+           optuna's own per-trial bookkeeping is inside the timed region.
+``--impl reference``  the reference ITSELF on the host cores: optuna's own ``_split_trials``,
+           ``_ParzenEstimator`` and ``log_pdf`` (oracle/_ref, unmodified) on the same 100k-trial study;
+           each step is a bounded sample (see run_reference).
 """
 from __future__ import annotations
 
@@ -41,7 +45,8 @@ METRIC = "TPE suggestions/sec at 100k-trial history, 32 params"
 UNIT = "suggestions/s"
 
 
-def synthetic_history(n=N_TRIALS, p=N_PARAMS):
+def synthetic_history(n=None, p=N_PARAMS):
+    n = N_TRIALS if n is None else n
     rs = np.random.RandomState(0)
     X = rs.uniform(0, 1, (n, p))
     loss = ((X - 0.5) ** 2).sum(1)
@@ -146,96 +151,151 @@ def measured_peaks() -> tuple[float, str]:
 
 
 # -------------------------------------------------------------------------------------------------
-# CPU legs (oracle port of the reference's NumPy path)
+# the reference as the caller (e2e) and as the CPU baseline (unmodified optuna from oracle/_ref)
 # -------------------------------------------------------------------------------------------------
-def _pool_eval(ma, mb, rows):
-    from oracle import tpe_oracle as orc
-    return orc.mixture_log_pdf(mb, rows).sum() + orc.mixture_log_pdf(ma, rows).sum()
+WORKLOAD = "c2: N=100000 trials x P=32 float params, C=4096 candidates, multivariate TPE"
+CONFIG = {"workload": WORKLOAD, "n_trials": N_TRIALS, "n_params": N_PARAMS, "n_ei_candidates": N_CAND,
+          "l2": "inputs larger than L2: every step rebuilds the 51 MB g(x) kernel table (126 MB L2; the split / "
+                "build kernels in between evict it)"}
+NAMES = [f"x{j:02d}" for j in range(N_PARAMS)]
 
 
-def cpu_step(X, loss, procs: int, pool=None, ra: int = 1, rb: int = 3) -> dict:
-    """One bounded sample of a reference suggestion (oracle port of the NumPy path).
+def import_optuna():
+    """The reference package: an installed optuna, else the copy under oracle/_ref (oracle/build_ref.py)."""
+    from oracle import build_ref, ref
+    build_ref.build()
+    if not ref.enable():
+        raise RuntimeError("optuna is not importable and oracle/_ref is absent (run `python oracle/build_ref.py`)")
+    import optuna
+    optuna.logging.set_verbosity(optuna.logging.ERROR)
+    import warnings
+    warnings.filterwarnings("ignore", category=optuna.exceptions.ExperimentalWarning)
+    return optuna
 
-    split + both estimator builds + all 4096 candidate draws are executed in full.  log_pdf is
-    evaluated on `ra` and then on `rb` candidates per process: the difference gives the
-    per-candidate slope, the remainder the per-call fixed cost (the (K, P) normalisers), and
-    full_s = fixed + intercept + slope * 4096 is what one un-chunked, all-cores evaluation would
-    take if its 105 GB temporaries fitted in memory -- the most favourable reading for the CPU.
-    """
-    from oracle import tpe_oracle as orc
-    n, p = X.shape
-    cat = np.zeros(n, np.int8)
-    key = np.stack([loss, np.zeros(n)], 1)
-    params = [orc.Param("float", 0.0, 1.0) for _ in range(p)]
-    cfg = orc.Config(multivariate=True)
-    t0 = time.perf_counter()
-    below, above = orc.split_trials(cat, key, orc.default_gamma(n))
-    mb = orc.build_mixture(X[below], params, cfg)
-    ma = orc.build_mixture(X[above], params, cfg)
-    t1 = time.perf_counter()
-    cand = orc.mixture_sample(mb, np.random.RandomState(1), N_CAND)
-    t2 = time.perf_counter()
 
-    def timed(rows_per_proc: int) -> float:
-        s = time.perf_counter()
-        if pool is None:
-            _pool_eval(ma, mb, cand[:rows_per_proc])
-        else:
-            chunks = [cand[i * rows_per_proc:(i + 1) * rows_per_proc] for i in range(procs)]
-            pool.starmap(_pool_eval, [(ma, mb, c) for c in chunks])
-        return time.perf_counter() - s
+def build_study(optuna, sampler, X, loss):
+    """optuna.create_study + study.add_trials of the synthetic history."""
+    space = {name: optuna.distributions.FloatDistribution(0.0, 1.0) for name in NAMES}
+    study = optuna.create_study(sampler=sampler)
+    study.add_trials([optuna.trial.create_trial(value=float(loss[i]), params=dict(zip(NAMES, X[i].tolist())),
+                                                distributions=space) for i in range(X.shape[0])])
+    return study, space
 
-    ta, tb = timed(ra), timed(rb)
-    slope = max(tb - ta, 1e-9) / ((rb - ra) * procs)  # seconds per candidate with all processes busy
-    intercept = max(ta - slope * ra * procs, 0.0)
-    fixed = t2 - t0
-    return {"build_s": t1 - t0, "sample_s": t2 - t1, "logpdf_s": ta + tb, "slope_s": slope,
-            "intercept_s": intercept, "full_s": fixed + intercept + slope * N_CAND}
+
+class ReferenceSuggestion:
+    """One c2 suggestion by the reference's own code, cut into the pieces a bounded sample needs.
+
+    `fixed()` runs, once and in full, what `TPESampler._sample` (sampler.py:523-553) does before the grid:
+    study._get_trials, _split_trials, both _build_parzen_estimator calls and mpe_below.sample(rng, 4096).
+    `chunk(lo, hi)` evaluates rows [lo, hi) of the 4096 candidates under both estimators with the reference's
+    `_ParzenEstimator.log_pdf` -- the chunked-candidate driver BASELINE.md section 3 prescribes, because the
+    un-chunked call needs a 105 GB (C, K, P) temporary.  The grid is linear in the candidate count, so
+    full_s = fixed_s + chunk_s / rows * 4096 / processes."""
+
+    def __init__(self, optuna, study, space):
+        from optuna.samplers._tpe import sampler as ref_sampler
+        self.optuna, self.mod, self.study, self.space = optuna, ref_sampler, study, space
+        self.sampler = optuna.samplers.TPESampler(seed=1, n_ei_candidates=N_CAND, multivariate=True)
+
+    def fixed(self) -> dict:
+        s, st = self.sampler, self.optuna.trial.TrialState
+        t0 = time.perf_counter()
+        trials = self.study._get_trials(deepcopy=False, states=(st.COMPLETE, st.PRUNED), use_cache=False)
+        below, above = self.mod._split_trials(self.study, trials, s._gamma(len(trials)), False)
+        t1 = time.perf_counter()
+        self.mpe_below = s._build_parzen_estimator(self.study, self.space, below, handle_below=True)
+        self.mpe_above = s._build_parzen_estimator(self.study, self.space, above, handle_below=False)
+        t2 = time.perf_counter()
+        self.samples = self.mpe_below.sample(s._rng.rng, N_CAND)
+        t3 = time.perf_counter()
+        return {"split_s": t1 - t0, "build_s": t2 - t1, "sample_s": t3 - t2, "fixed_s": t3 - t0}
+
+    def chunk(self, lo: int, hi: int) -> float:
+        part = {k: v[lo:hi] for k, v in self.samples.items()}
+        return float((self.mpe_below.log_pdf(part) - self.mpe_above.log_pdf(part)).sum())
+
+
+_REF: ReferenceSuggestion | None = None
+
+
+def _ref_chunk(args):
+    return _REF.chunk(*args)
 
 
 def run_reference(args) -> None:
+    """`--impl reference`: the reference itself (oracle/_ref) on the host cores, c2.
+
+    Setup (untimed): the 100k-trial study; one full run of the fixed part of a suggestion (split, both
+    estimator builds, 4096 draws -- single process, like the reference).  Each STEP (timed) evaluates
+    `rows` candidates per process under l(x) and g(x) with the reference's log_pdf in `procs` forked processes
+    (NumPy's elementwise kernels are single-threaded: this is how the reference can use the host's cores at
+    all).  ms_per_step is the wall time of that step; `value` is the suggestion rate this implies for the whole
+    4096-candidate suggestion (formula in `extrapolation`) -- a full one takes hours, BASELINE.md section 2."""
+    global _REF
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    optuna = import_optuna()
     X, loss = synthetic_history()
+    t0 = time.perf_counter()
+    study, space = build_study(optuna, optuna.samplers.RandomSampler(seed=0), X, loss)
+    setup_s = time.perf_counter() - t0
+    _REF = ReferenceSuggestion(optuna, study, space)
+    fixed = _REF.fixed()
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))
-    ctx = mp.get_context("fork")
+    rows = 4   # per process and step: 4 x 25.6 MB per (K, P) temporary; the per-call overhead is < 10 % of a chunk
     times = []
-    with ctx.Pool(procs) as pool:
+    with mp.get_context("fork").Pool(procs) as pool:
         for i in range(args.warmup + args.steps):
-            r = cpu_step(X, loss, procs, pool)
+            base = (i * procs * rows) % (N_CAND - procs * rows)
+            t0 = time.perf_counter()
+            pool.map(_ref_chunk, [(base + q * rows, base + (q + 1) * rows) for q in range(procs)])
             if i >= args.warmup:
-                times.append(r)
-    full = float(np.mean([r["full_s"] for r in times]))
-    val = 1.0 / full
+                times.append(time.perf_counter() - t0)
+    step_s = float(np.mean(times))
+    per_cand_s = step_s / (procs * rows)          # seconds per candidate with every process busy
+    full_s = fixed["fixed_s"] + per_cand_s * N_CAND
+    val = 1.0 / full_s
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "c2: N=100000 trials x P=32 float params, C=4096 candidates, multivariate TPE",
-                   "n_trials": N_TRIALS, "n_params": N_PARAMS, "n_ei_candidates": N_CAND},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": (f"oracle port of the NumPy path, {procs} processes: split + both estimator builds + "
-                                    f"4096 candidate draws in full; log_pdf timed on 1 and on 3 candidates per process, "
-                                    "per-candidate slope x 4096 + per-call fixed cost")},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(CONFIG),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "reference",
+                         "sample": (f"unmodified optuna (oracle/_ref): fixed part of one suggestion run once in full "
+                                    f"({fixed['fixed_s']:.1f} s: _split_trials {fixed['split_s']:.1f}, two "
+                                    f"_ParzenEstimator builds {fixed['build_s']:.1f}, 4096 draws {fixed['sample_s']:.1f}); "
+                                    f"each step = _ParzenEstimator.log_pdf of {rows} candidate(s) x {procs} processes "
+                                    f"under l(x) and g(x) ({step_s:.2f} s)")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "stages_s": {k: float(np.mean([r[k] for r in times]))
-                     for k in ("build_s", "sample_s", "logpdf_s", "slope_s", "intercept_s")},
+        "measured": dict(fixed, step_s=step_s, candidates_per_step=procs * rows, processes=procs,
+                         study_setup_s=setup_s, host_cores=cores),
+        "extrapolation": {"full_suggestion_s": full_s,
+                          "formula": "fixed_s + step_s / candidates_per_step * 4096 (the grid is linear in the "
+                                     "candidate count; the un-chunked call needs a 105 GB temporary)",
+                          "fraction_of_a_suggestion_per_step": procs * rows / N_CAND},
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg(X, loss) -> dict:
-    """Single-process oracle timing on a bounded sample (what a user of the reference gets: NumPy
-    elementwise kernels are single-threaded)."""
-    r = cpu_step(X, loss, procs=1, pool=None, ra=2, rb=6)
-    return {"value": 1.0 / r["full_s"], "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": ("oracle port, 1 process (NumPy elementwise kernels are single-threaded): split + builds + "
-                       f"4096 draws in full ({r['build_s']:.1f}s + {r['sample_s']:.1f}s); log_pdf timed on 2 and 6 "
-                       f"candidates ({r['logpdf_s']:.1f}s): {r['slope_s']:.2f}s per candidate x 4096 + "
-                       f"{r['intercept_s']:.1f}s per call -> {r['full_s']:.0f}s per suggestion")}
+def cpu_baseline_leg(optuna, study, space) -> dict:
+    """The reference on ONE core (what a user of the reference gets: NumPy elementwise kernels are
+    single-threaded) -- bounded sample: fixed part once, log_pdf of 2 and then 6 candidates."""
+    ref = ReferenceSuggestion(optuna, study, space)
+    fixed = ref.fixed()
+    ref.chunk(8, 9)  # first-touch / lazy-import cost of the first call is not the reference's steady state
+    t0 = time.perf_counter()
+    ref.chunk(0, 2)
+    t1 = time.perf_counter()
+    ref.chunk(2, 8)
+    t2 = time.perf_counter()
+    per = (t2 - t0) / 8.0
+    full = fixed["fixed_s"] + per * N_CAND
+    return {"value": 1.0 / full, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": (f"unmodified optuna (oracle/_ref), 1 process: _split_trials + both _ParzenEstimator builds + 4096 "
+                       f"draws in full ({fixed['fixed_s']:.1f} s); log_pdf under l(x) and g(x) of 8 of the 4096 candidates "
+                       f"({t2 - t0:.1f} s, {per:.2f} s per candidate) -> {full:.0f} s per suggestion")}
 
 
 # -------------------------------------------------------------------------------------------------
@@ -245,7 +305,7 @@ def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from optuna_b200 import B200TPESampler, ParamSpec, TPEEngine, mini
+    from optuna_b200 import ParamSpec, TPEEngine
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -320,25 +380,33 @@ def run_b200(args) -> None:
         wall, dev_ms = float(t[0]), float(t[1])
     value = world * args.steps / wall
 
-    # ---- end to end through the sampler plugin (host buffers, copies inside the timed region) ----
-    space = {f"x{j:02d}": mini.FloatDistribution(0.0, 1.0) for j in range(N_PARAMS)}
+    # ---- end to end: optuna's own Study drives the plugin (host buffers, copies inside the timed region) ----
+    optuna = import_optuna()
+    from optuna_b200 import B200TPESampler
     sampler = B200TPESampler(seed=1 + rank, n_ei_candidates=N_CAND, multivariate=True, device=local)
-    study = mini.create_study(sampler=sampler)
-    names = list(space)
-    trials = []
-    for i in range(N_TRIALS):
-        t = mini.FrozenTrial(i, mini.TrialState.COMPLETE, value=float(loss[i]),
-                             params=dict(zip(names, X[i].tolist())), distributions=space)
-        trials.append(t)
-    study._storage.trials = trials
-    frozen = mini.FrozenTrial(N_TRIALS, mini.TrialState.RUNNING)
+    t0 = time.perf_counter()
+    study, space = build_study(optuna, sampler, X, loss)
+    study_setup_s = time.perf_counter() - t0
+
+    def one_trial():
+        trial = study.ask()
+        x = [trial.suggest_float(name, 0.0, 1.0) for name in NAMES]
+        study.tell(trial, sum((v - 0.5) ** 2 for v in x))
+        return x
+
     e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    one_trial()                      # first ask: the one-time walk + upload of the 100k-trial history
+    first_ask_s = time.perf_counter() - t0
     for _ in range(max(2, min(args.warmup, 3))):
-        sampler.sample_relative(study, frozen, space)
+        one_trial()
     barrier()
+    sync_s = dev_s = 0.0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = sampler.sample_relative(study, frozen, space)
+        out = one_trial()
+        sync_s += sampler.last_ask_s[0]
+        dev_s += sampler.last_ask_s[1]
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     barrier()
@@ -348,7 +416,13 @@ def run_b200(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_wall = float(t[0])
     e2e_value = world * e2e_steps / e2e_wall
-    assert len(out) == N_PARAMS and all(0.0 <= v <= 1.0 for v in out.values())
+    assert len(out) == N_PARAMS and all(0.0 <= v <= 1.0 for v in out)
+    assert len(study.get_trials(deepcopy=False)) == N_TRIALS + 1 + max(2, min(args.warmup, 3)) + e2e_steps
+    e2e_host = {"per_trial_ms": e2e_wall / e2e_steps * 1e3,
+                "history_sync_ms": sync_s / e2e_steps * 1e3,       # trial-log poll + row uploads (B200TPESampler._sync)
+                "device_calls_ms": dev_s / e2e_steps * 1e3,        # prepare / build / uniforms / sample+select, read-back
+                "optuna_ms": (e2e_wall - sync_s - dev_s) / e2e_steps * 1e3,  # Study.ask / 32 x suggest_float / tell
+                "first_ask_s": first_ask_s, "study_setup_s": study_setup_s}
 
     # ---- extras (rank 0, N=1 only): other shapes of the same path, not the headline ------------------
     extras = {}
@@ -385,17 +459,17 @@ def run_b200(args) -> None:
         # the same batch end to end through the plugin: uniforms generated on the device (MT19937 stream
         # of the sampler's RandomState), results converted to parameter dicts
         bs = B200TPESampler(seed=3, n_ei_candidates=24, multivariate=True, device=local)
-        bstudy = mini.create_study(sampler=bs)
-        bstudy._storage.trials = trials
+        study.sampler = bs              # the same optuna study, asked through a fresh sampler
         for rep in range(2):
             t0 = time.perf_counter()
-            res = bs.sample_relative_batch(bstudy, space, n_asks)
+            res = bs.sample_relative_batch(study, space, n_asks)
             be = time.perf_counter() - t0
         assert len(res) == n_asks and len(res[0]) == N_PARAMS
         extras["batched_asks_e2e"] = {"n_asks": n_asks, "n_ei_candidates": 24, "ms": be * 1e3,
                                       "suggestions_per_s": n_asks / be,
                                       "path": "B200TPESampler.sample_relative_batch (device MT19937)"}
         bs.close()
+        study.sampler = sampler
     # ---- config 5: 8192 concurrent asks (default n_ei_candidates = 24) sharded over the ranks -----------
     # every rank evaluates its block of asks on uniforms its GPU generates from the shared generator state
     # (MT19937 stream of one sampler consumed sequentially, the reference's semantics); results all-gathered
@@ -442,11 +516,8 @@ def run_b200(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c2: N=100000 trials x P=32 float params, C=4096 candidates, multivariate TPE",
-                       "n_trials": N_TRIALS, "n_params": N_PARAMS, "n_ei_candidates": N_CAND,
-                       "parallelism": f"{world} independent asks per step, history replicated by one NCCL broadcast",
-                       "l2": "inputs larger than L2: the g(x) kernel table is 51 MB/launch and every step rebuilds it "
-                             "(126 MB L2; split/build kernels in between evict it)"},
+            "config": dict(CONFIG),
+            "parallelism": f"{world} independent asks per step, history replicated by one NCCL broadcast",
             "device_ms_per_step": dev_ms / args.steps,
             "stage_ms": {k: float(v) / args.steps for k, v in zip(
                 ["split", "build", "h2d", "sample", "logpdf_below", "logpdf_above_main", "logpdf_fixup", "select",
@@ -455,10 +526,17 @@ def run_b200(args) -> None:
             "clocks": clk,
             # inputs of one ask: the generator state (624 words + position; the uniforms themselves are
             # produced on the device by the same MT19937), the column list and the config struct
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 625 * 4 + N_PARAMS * 4 + 32,
+            # inputs of one step: the rows that changed (the trial that finished + the placeholder of the new one:
+            # 2 x (32 params + 2 key doubles + 1 category byte)), the column list and the config struct; the
+            # generator state travels only when somebody else drew from it
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * (N_PARAMS * 8 + 16 + 1) + N_PARAMS * 4 + 32,
                     "d2h_bytes_per_step": N_PARAMS * 8 + 16 + 24 + 625 * 4, "steps": e2e_steps,
-                    "path": "B200TPESampler.sample_relative -> ctypes -> tpe_prepare / tpe_stage_uniforms_mt19937 / "
-                            "tpe_build / tpe_sample_and_select / tpe_rng_state"},
+                    "path": "optuna.create_study(sampler=B200TPESampler) + study.add_trials(100k) ; per step study.ask() "
+                            "-> 32 x trial.suggest_float -> [infer_relative_search_space, sample_relative -> ctypes -> "
+                            "tpe_history_update / tpe_prepare / tpe_build / tpe_stage_uniforms_mt19937 / "
+                            "tpe_sample_and_select] -> study.tell",
+                    "caller": f"optuna {optuna.__version__} ({os.path.relpath(os.path.dirname(optuna.__file__), ROOT)})",
+                    "host": e2e_host},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": 27546880, "traffic_source": "ncu --set full, profiles/r1_ncu_raw_logpdf_mma_final.txt "
                          "(dram__bytes_read.sum + dram__bytes_write.sum of this launch)",
@@ -484,7 +562,7 @@ def run_b200(args) -> None:
         if config5:
             line["config5"] = config5
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_leg(X, loss)
+            line["cpu_baseline"] = cpu_baseline_leg(optuna, study, space)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
@@ -499,7 +577,13 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the univariate / batched / cold extras")
+    ap.add_argument("--n-trials", type=int, default=N_TRIALS, help="development only: a shorter history (the line then "
+                    "says so in config.n_trials); the benchmark is the default")
     args = ap.parse_args()
+    if args.n_trials != N_TRIALS:
+        globals()["N_TRIALS"] = args.n_trials
+        CONFIG["n_trials"] = args.n_trials
+        CONFIG["workload"] += f" [DEVELOPMENT RUN: n_trials={args.n_trials}]"
     if args.impl == "reference":
         run_reference(args)
     else:

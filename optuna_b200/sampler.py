@@ -14,7 +14,7 @@ from __future__ import annotations
 import json
 import math
 import threading
-import warnings
+import time
 from typing import Any, Callable, Sequence
 
 import numpy as np
@@ -684,7 +684,17 @@ class B200TPESampler(BaseSampler):
 
     def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
         """TPESampler._sample (sampler.py:523-560).  The caller holds the lock and has polled."""
+        t0 = time.perf_counter()
         cols = self._sync(study, trial, search_space)
+        t1 = time.perf_counter()
+        try:
+            return self._sample_synced(study, cols, search_space)
+        finally:
+            # wall time of the last ask: history sync (host walk + row uploads) / everything after it
+            # (prepare, build, uniforms, sampling + grids + argmax, read-back, to_external_repr)
+            self.last_ask_s = (t1 - t0, time.perf_counter() - t1)
+
+    def _sample_synced(self, study, cols: list[int], search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
         n_below = self._gamma(self._hist.n_finished)
         cfg = dict(n_below=int(n_below), n_candidates=self._n_ei_candidates, multivariate=self._multivariate,
                    prior_weight=self._prior_weight, magic_clip=self._magic_clip, endpoints=self._endpoints)
