@@ -330,14 +330,21 @@ def run_b200(args) -> None:
             tk.copy_(torch.from_numpy(key))
             tc.copy_(torch.from_numpy(cat))
         flat = torch.cat([tX.view(-1), tk.view(-1)])
+        dist.broadcast(torch.zeros(1, device=dev), 0)   # NCCL communicator set-up is not the broadcast
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
         dist.broadcast(flat, 0)
         dist.broadcast(tc, 0)
+        torch.cuda.synchronize()
+        bcast_ms = (time.perf_counter() - t0) * 1e3
         tX = flat[: N_TRIALS * N_PARAMS].view(N_TRIALS, N_PARAMS).contiguous()
         tk = flat[N_TRIALS * N_PARAMS:].view(N_TRIALS, 2).contiguous()
         torch.cuda.synchronize()
         eng.set_history_device(tX.data_ptr(), tc.data_ptr(), tk.data_ptr(), N_TRIALS, np.zeros(N_PARAMS, np.uint8))
     else:
         eng.set_history(X, cat, key)
+        bcast_ms = None
 
     cols = list(range(N_PARAMS))
     cfg = dict(n_below=min(math.ceil(0.1 * N_TRIALS), 25), n_candidates=N_CAND, multivariate=True)
@@ -486,7 +493,8 @@ def run_b200(args) -> None:
             eng.prepare(cols, **cfg5)
             eng.build()
             if world > 1:
-                res5 = sharded_asks_device_rng(eng, rng5, n_asks5, per_ask5, gather=True)
+                tm5 = {}
+                res5 = sharded_asks_device_rng(eng, rng5, n_asks5, per_ask5, gather=True, timing=tm5)
             else:
                 eng.stage_rng(rng5, n_asks5 * per_ask5)
                 res5, _, _ = eng.sample_and_select(None, n_asks5)
@@ -500,9 +508,13 @@ def run_b200(args) -> None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt5 = float(t[0])
         config5 = {"n_asks": n_asks5, "n_ei_candidates": c5, "ms": dt5 * 1e3, "suggestions_per_s": n_asks5 / dt5,
-                   "asks_per_rank": shard_asks(n_asks5, world, 0)[1],
-                   "path": "tpe_prepare / tpe_build / tpe_stage_uniforms_mt19937(skip) / tpe_sample_and_select per "
-                           "rank + all_gather of the [8192, 32] results"}
+                   "asks_per_rank": shard_asks(n_asks5, world, 0)[1], "scaling": "strong",
+                   "path": "per rank: tpe_prepare / tpe_build / tpe_stage_uniforms_mt19937(skip: jump-ahead) / "
+                           "tpe_sample_and_select(out_x = NULL); then ncclBroadcast of the generator end state and "
+                           "ncclAllGather of the [8192, 32] results straight from the contexts' device buffers"}
+        if world > 1:
+            config5["rank0_compute_ms"] = tm5["compute_s"] * 1e3
+            config5["rank0_collectives_ms"] = tm5["collectives_s"] * 1e3
     if rank == 0:
         peak, peak_src = measured_peaks()
         k_ms = float(stage[5]) / args.steps  # main log-density kernel under g(x)
@@ -561,6 +573,10 @@ def run_b200(args) -> None:
             line["extras"] = extras
         if config5:
             line["config5"] = config5
+        if bcast_ms is not None:
+            line["history_broadcast"] = {"ms": bcast_ms, "bytes": N_TRIALS * (N_PARAMS + 2) * 8 + N_TRIALS,
+                                         "note": "one ncclBroadcast of the frozen history (X and keys as one fp64 buffer, "
+                                                 "categories as int8), before the timed region"}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(optuna, study, space)
         print(json.dumps(line), flush=True)

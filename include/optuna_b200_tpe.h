@@ -30,7 +30,9 @@ extern "C" {
 /* 2: + tpe_history_update, tpe_stage_uniforms, tpe_stage_uniforms_mt19937, tpe_rng_state,
  *      tpe_get_uniforms, tpe_host_alloc / tpe_host_free; tpe_sample_and_select accepts uniforms == NULL
  *      after tpe_stage_uniforms_mt19937 */
-#define TPE_ABI_VERSION 2
+/* 3: + TPE_CAT_EXCLUDED; tpe_history_update may extend the history; tpe_sample_and_select accepts out_x == NULL
+ *      (results stay on the device: tpe_result_device_ptrs); tpe_rng_state_device */
+#define TPE_ABI_VERSION 3
 
 enum {
   TPE_OK = 0,
@@ -143,11 +145,16 @@ int tpe_build(tpe_ctx* ctx, const double* w_below, const double* w_above);
  *   uniforms [n_asks, C * (1 + n_cat + n_num)] per ask in the reference's RNG order
  *            (probability_distributions.py:87,100,138-144): C for rng.choice, then C per
  *            categorical param in column order, then an [n_num, C] block.
- *   out_x    [n_asks, n_cols] chosen candidate (internal representation)
+ *   out_x    [n_asks, n_cols] chosen candidate (internal representation); NULL = leave the results on the device
+ *            (tpe_result_device_ptrs): a multi-GPU caller gathers them with NCCL without a host bounce
  *   out_acq  [n_asks] its acquisition value (may be NULL)
  *   out_best [n_asks] its candidate index (may be NULL) */
 int tpe_sample_and_select(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x,
                           double* out_acq, int64_t* out_best);
+
+/* Device pointers of the results of the last tpe_sample_and_select: out_x [n_asks, n_cols], out_acq [n_asks],
+ * out_best [n_asks] (valid until the next call on the context; the work has completed when that call returned). */
+int tpe_result_device_ptrs(tpe_ctx* ctx, double** out_x, double** out_acq, int64_t** out_best);
 
 /* One-call convenience = prepare + build + sample_and_select (TPESampler._sample, sampler.py:523-560). */
 int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
@@ -172,6 +179,10 @@ int tpe_stage_uniforms(tpe_ctx* ctx, const double* uniforms, int64_t count);
  * caller that owns the generator exclusively can defer get_state()/set_state() until somebody else needs it. */
 int tpe_stage_uniforms_mt19937(tpe_ctx* ctx, const uint32_t* key, int32_t pos, int64_t skip, int64_t count);
 int tpe_rng_state(tpe_ctx* ctx, uint32_t* key_out, int32_t* pos_out);
+/* The same state where it lives: 625 words (key[624], pos) in device memory.  For multi-GPU plumbing -- the rank that
+ * drew the LAST stretch of a batch broadcasts its end state into every rank's buffer (NCCL, device to device), so all
+ * ranks continue as one generator that drew everything (optuna_b200/dist.py).  The library forgets its host copy. */
+int tpe_rng_state_device(tpe_ctx* ctx, uint32_t** state625);
 /* Inspection: the first `count` staged uniforms (device-generated or uploaded). */
 int tpe_get_uniforms(tpe_ctx* ctx, double* out, int64_t count);
 

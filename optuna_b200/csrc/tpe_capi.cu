@@ -99,6 +99,8 @@ struct tpe_ctx {
   // the end state into U2 / mt_spec.  The next tpe_stage_uniforms_mt19937 adopts them if the caller's
   // generator is exactly in that state (mt_host, as returned by tpe_rng_state); otherwise they are dropped.
   DevBuf U2, mt_spec;
+  DevBuf mt_jump, mt_tmp;        // jump-ahead polynomials (kMtJumpTable) / end state of the multi-CTA generator
+  bool mt_jump_ready = false;
   cudaEvent_t ev_spec = nullptr;
   bool spec_pending = false, mt_host_valid = false;
   int64_t spec_count = 0;
@@ -131,7 +133,7 @@ struct tpe_ctx {
       mo_uniq, mo_nuniq, mo_ref, mo_removed, mo_contrib, mo_state, mo_arena, mo_chosen, mo_diag, mo_w, mo_table, mo_sample,
       mo_surv, mo_nsurv;
   bool mo_weights_ready = false;
-  std::vector<uint8_t> col_missing;
+  std::vector<uint8_t> col_missing, col_oor;
   bool history_set = false;
 
   // current call
@@ -335,6 +337,37 @@ const FastCfg* pick_fast(int mode, int pb, int64_t Ct) {
   for (int i = 0; i < 7; ++i)
     if (tabs[i].pb == pb) return &tabs[i];
   return nullptr;
+}
+
+// `count` outputs of the MT19937 stream after dropping `skip`, from the 625-word device state `state` (updated in
+// place to the state after the draws).  Short stretches: one CTA walks the recurrence (k_mt19937_uniform).  Long
+// ones (a batch of asks, or a rank's slice far into the batch): every CTA jumps to its own chunk
+// (k_mt19937_uniform_mc) -- no serial prefix walk.
+int launch_mt(tpe_ctx* ctx, cudaStream_t st, uint32_t* state, int64_t skip, int64_t count, double* out) {
+  static const int64_t mc_min = [] { const char* v = getenv("TPE_MT_MC_MIN"); return v ? atoll(v) : (int64_t)400000; }();
+  if (skip + count < mc_min) {
+    k_mt19937_uniform<<<1, kMtThreads, 0, st>>>(state, reinterpret_cast<int*>(state + 624), skip, count, out);
+    ctx->launch_counter++;
+    CU(cudaGetLastError());
+    return TPE_OK;
+  }
+  if (!ctx->mt_jump_ready) {
+    CU(ctx->mt_jump.ensure(sizeof(kMtJumpTable)));
+    CU(ctx->mt_tmp.ensure(625 * 4));
+    CU(cudaMemcpyAsync(ctx->mt_jump.p, kMtJumpTable, sizeof(kMtJumpTable), cudaMemcpyHostToDevice, st));
+    CU(cudaFuncSetAttribute(k_mt19937_uniform_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMtJumpSmem));
+    ctx->mt_jump_ready = true;
+  }
+  const int64_t G = std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (count + 16383) / 16384));
+  const int64_t chunk = round_up<int64_t>((count + G - 1) / G, 256);
+  const int64_t grid = (count + chunk - 1) / chunk;
+  k_mt19937_uniform_mc<<<(unsigned)grid, kMtThreads, kMtJumpSmem, st>>>(state, skip, count, chunk, ctx->mt_jump.as<uint32_t>(),
+                                                                       kMtJumpKMin, kMtJumpKMax, out,
+                                                                       ctx->mt_tmp.as<uint32_t>());
+  ctx->launch_counter++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(state, ctx->mt_tmp.p, 625 * 4, cudaMemcpyDeviceToDevice, st));
+  return TPE_OK;
 }
 
 int join_above(tpe_ctx* ctx) {
@@ -584,11 +617,21 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
   return TPE_OK;
 }
 
-void scan_missing(tpe_ctx* ctx, const double* X, int64_t n) {
+// Host scan of uploaded rows: which columns have absent values (the split then needs the row filter) and which
+// hold observations outside the column's current [low, high] (legal: optuna lets a range change between trials;
+// the a-priori rounding bound of the tensor-core grid kernel assumes |mu''| <= range / (2 sigma), so such columns
+// take the elementwise kernel).  TPE_CAT_EXCLUDED placeholders are in no estimator and do not count.
+void scan_missing(tpe_ctx* ctx, const double* X, const int8_t* category, int64_t n) {
   const int64_t P = (int64_t)ctx->space.size();
-  for (int64_t i = 0; i < n; ++i)
-    for (int64_t j = 0; j < P; ++j)
-      if (X[i * P + j] != X[i * P + j]) ctx->col_missing[j] = 1;
+  for (int64_t i = 0; i < n; ++i) {
+    if (category && cat_slot(category[i]) == 4) continue;
+    for (int64_t j = 0; j < P; ++j) {
+      const double v = X[i * P + j];
+      if (v != v) { ctx->col_missing[j] = 1; continue; }
+      const tpe_param_desc& d = ctx->space[j];
+      if (d.kind != TPE_KIND_CAT && (v < d.low || v > d.high)) ctx->col_oor[j] = 1;
+    }
+  }
 }
 
 bool mma_enabled() {
@@ -614,7 +657,9 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
   if (ctx->fast_mode == 1) CU(e.tabp.ensure((size_t)K * ctx->pb * 16 + 16));
   if (ctx->fast_mode == 2) CU(e.tabc.ensure((size_t)K * ctx->pb * 8 + 16));
   if (ctx->fast) CU(e.colprm.ensure((size_t)ctx->pb * 16));
-  e.mma = ctx->fast_mode == 2 && ctx->pb >= 8 && mma_enabled();
+  bool in_range = true;  // every selected column's observations lie inside its current [low, high]
+  for (const ColMeta& cm : ctx->cols_h) in_range = in_range && !ctx->col_oor[cm.src];
+  e.mma = ctx->fast_mode == 2 && ctx->pb >= 8 && in_range && mma_enabled();
   if (e.mma) {
     CU(e.tabm.ensure((size_t)k_alloc * ctx->pb * 8));
     CU(e.hb.ensure((size_t)k_alloc * 8));
@@ -980,7 +1025,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
                     &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
-                    &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->U2, &ctx->mt_spec, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
+                    &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->U2, &ctx->mt_spec, &ctx->mt_jump, &ctx->mt_tmp, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
   ctx->est[1].release();
@@ -1035,6 +1080,7 @@ int tpe_space_set(tpe_ctx* ctx, const tpe_param_desc* params, int32_t n_params, 
     if (end) CU(cudaMemcpy(ctx->cat_dist.p, cat_dist, (size_t)end * 8, cudaMemcpyHostToDevice));
   }
   ctx->col_missing.assign(n_params, 0);
+  ctx->col_oor.assign(n_params, 0);
   ctx->N = 0;
   ctx->history_set = false;
   ctx->prepared = ctx->built = ctx->sampled = false;
@@ -1050,7 +1096,8 @@ int tpe_history_set(tpe_ctx* ctx, const double* X, const int8_t* category, const
   if (n >= (1ll << 31) - 4096) return fail(ctx, TPE_E_INVALID, "history too long");
   if (set_device(ctx)) return TPE_E_CUDA;
   std::fill(ctx->col_missing.begin(), ctx->col_missing.end(), 0);
-  scan_missing(ctx, X, n);
+  std::fill(ctx->col_oor.begin(), ctx->col_oor.end(), 0);
+  scan_missing(ctx, X, category, n);
   return upload_history(ctx, X, category, key, n, 0, false);
 }
 
@@ -1061,7 +1108,7 @@ int tpe_history_append(tpe_ctx* ctx, const double* X, const int8_t* category, co
   if (n < 0 || (n > 0 && (!X || !category || !key))) return fail(ctx, TPE_E_INVALID, "bad history arguments");
   if (ctx->N + n >= (1ll << 31) - 4096) return fail(ctx, TPE_E_INVALID, "history too long");
   if (set_device(ctx)) return TPE_E_CUDA;
-  scan_missing(ctx, X, n);
+  scan_missing(ctx, X, category, n);
   return upload_history(ctx, X, category, key, n, ctx->N, false);
 }
 
@@ -1078,7 +1125,7 @@ int tpe_history_update(tpe_ctx* ctx, const double* X, const int8_t* category, co
   if (set_device(ctx)) return TPE_E_CUDA;
   if ((int64_t)ctx->cat_h.size() != ctx->N)
     return fail(ctx, TPE_E_STATE, "tpe_history_update needs a host-uploaded history");
-  scan_missing(ctx, X, n);
+  scan_missing(ctx, X, category, n);
   const int64_t P = (int64_t)ctx->space.size();
   const int64_t total = std::max(ctx->N, at_row + n);
   if (total > ctx->N) {  // the write runs past the end: the history grows (rows [at_row, N) are overwritten)
@@ -1113,6 +1160,9 @@ int tpe_history_set_device(tpe_ctx* ctx, const double* dX, const int8_t* dcatego
   if (n < 0 || (n > 0 && (!dX || !dcategory || !dkey))) return fail(ctx, TPE_E_INVALID, "bad history arguments");
   if (set_device(ctx)) return TPE_E_CUDA;
   for (size_t j = 0; j < ctx->col_missing.size(); ++j) ctx->col_missing[j] = col_has_missing ? col_has_missing[j] : 1;
+  // a history adopted from device memory is not scanned on the host: treat every column as possibly out of range
+  // unless the caller vouches for it through col_has_missing (the broadcast path of optuna_b200/dist.py does)
+  std::fill(ctx->col_oor.begin(), ctx->col_oor.end(), col_has_missing ? 0 : 1);
   return upload_history(ctx, dX, dcategory, dkey, n, 0, true);
 }
 
@@ -1386,7 +1436,7 @@ int tpe_build(tpe_ctx* ctx, const double* w_below, const double* w_above) {
 static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x, double* out_acq,
                                 int64_t* out_best) {
   if (!ctx->built) return fail(ctx, TPE_E_STATE, "tpe_build must precede tpe_sample_and_select");
-  if ((!uniforms && !ctx->u_device_rng) || n_asks <= 0 || !out_x)
+  if ((!uniforms && !ctx->u_device_rng) || n_asks <= 0)
     return fail(ctx, TPE_E_INVALID, "bad sample arguments");
   if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;  // est[1] is joined by run_logpdf(ctx, 1)
   cudaStream_t st = ctx->stream;
@@ -1436,10 +1486,7 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
       CU(ctx->U2.ensure((size_t)count * 8));
       CU(ctx->mt_spec.ensure(625 * 4));
       CU(cudaMemcpyAsync(ctx->mt_spec.p, ctx->mt_state.p, 625 * 4, cudaMemcpyDeviceToDevice, ctx->stream3));
-      k_mt19937_uniform<<<1, kMtThreads, 0, ctx->stream3>>>(
-          ctx->mt_spec.as<uint32_t>(), reinterpret_cast<int*>(ctx->mt_spec.as<uint32_t>() + 624), 0, count,
-          ctx->U2.as<double>());
-      ctx->launch_counter++;
+      if (int rc2 = launch_mt(ctx, ctx->stream3, ctx->mt_spec.as<uint32_t>(), 0, count, ctx->U2.as<double>())) return rc2;
       CU(cudaEventRecord(ctx->ev_spec, ctx->stream3));
       ctx->spec_pending = true;
       ctx->spec_count = count;
@@ -1463,7 +1510,7 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   ctx->launch_counter += 2;
   CU(cudaEventRecord(ctx->ev[8], st));
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_asks * ctx->pc * 8, cudaMemcpyDeviceToHost, st));
+  if (out_x) CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_asks * ctx->pc * 8, cudaMemcpyDeviceToHost, st));
   if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
   if (out_best) CU(cudaMemcpyAsync(out_best, ctx->out_best.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -1516,11 +1563,7 @@ int tpe_stage_uniforms_mt19937(tpe_ctx* ctx, const uint32_t* key, int32_t pos, i
     h[624] = (uint32_t)pos;
     CU(cudaMemcpyAsync(ctx->mt_state.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream3));
   }
-  k_mt19937_uniform<<<1, kMtThreads, 0, ctx->stream3>>>(ctx->mt_state.as<uint32_t>(),
-                                                 reinterpret_cast<int*>(ctx->mt_state.as<uint32_t>() + 624), skip,
-                                                 count, ctx->U.as<double>());
-  ctx->launch_counter++;
-  CU(cudaGetLastError());
+  if (int rc = launch_mt(ctx, ctx->stream3, ctx->mt_state.as<uint32_t>(), skip, count, ctx->U.as<double>())) return rc;
   CU(cudaEventRecord(ctx->ev_u, ctx->stream3));
   ctx->u_staged_count = count;
   ctx->u_device_rng = true;
@@ -1539,6 +1582,27 @@ int tpe_rng_state(tpe_ctx* ctx, uint32_t* key_out, int32_t* pos_out) {
   }
   memcpy(key_out, ctx->mt_host, 624 * 4);
   *pos_out = (int32_t)ctx->mt_host[624];
+  return TPE_OK;
+}
+int tpe_result_device_ptrs(tpe_ctx* ctx, double** out_x, double** out_acq, int64_t** out_best) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->sampled) return fail(ctx, TPE_E_STATE, "tpe_sample_and_select must precede tpe_result_device_ptrs");
+  if (out_x) *out_x = ctx->out_x.as<double>();
+  if (out_acq) *out_acq = ctx->out_acq.as<double>();
+  if (out_best) *out_best = ctx->out_best.as<int64_t>();
+  return TPE_OK;
+}
+int tpe_rng_state_device(tpe_ctx* ctx, uint32_t** state625) {
+  if (!ctx || !state625) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  if (!ctx->mt_state.p) return fail(ctx, TPE_E_STATE, "tpe_stage_uniforms_mt19937 must precede tpe_rng_state_device");
+  CU(cudaStreamSynchronize(ctx->stream3));  // the generator that last wrote the state
+  // the caller may overwrite the state (a broadcast from the rank that drew last): forget what the host knows
+  ctx->mt_host_valid = false;
+  ctx->spec_pending = false;
+  *state625 = ctx->mt_state.as<uint32_t>();
   return TPE_OK;
 }
 int tpe_get_uniforms(tpe_ctx* ctx, double* out, int64_t count) {

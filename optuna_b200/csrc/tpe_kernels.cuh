@@ -18,6 +18,7 @@
 
 #include "tpe_common.cuh"
 #include "tpe_math.cuh"
+#include "mt_jump_table.inc"
 
 namespace tpe {
 
@@ -1925,6 +1926,185 @@ k_mt19937_uniform(uint32_t* __restrict__ key, int* __restrict__ pos_io, int64_t 
   __syncthreads();
   for (int i = tid; i < 624; i += kMtThreads) key[i] = buf[cur][i];
   if (tid == 0) *pos_io = end_pos;
+}
+
+// ================================================================================================
+// Multi-CTA MT19937: jump-ahead.  The state transition is linear over GF(2) with a primitive characteristic
+// polynomial phi (degree 19937), so advancing by J words is multiplication by g_J = x^J mod phi, and in terms of
+// the word sequence the generator emits:  x_{J+j} = XOR_{i : g_J[i] = 1} x_{i+j}  for every j >= 1 (Haramoto et
+// al. 2008; derivation and the table generator: tools/gen_mt_jump.py).  The table holds g = x^(2^k - 1) mod phi,
+// so one application moves a 624-word key by exactly 2^k words:  new[j'] = XOR_i g_i W[i + j' + 1].
+//
+// k_mt19937_uniform_mc: CTA c produces doubles [c * chunk, (c + 1) * chunk) of the requested stretch.  It jumps
+// from the caller's state to the 512-word boundary below its first word (one table polynomial per set bit of the
+// distance) and then runs the same block generator as the single-CTA kernel.  A rank that owns a later slice of a
+// batch (`skip`) no longer walks the prefix: 8.6 ms for the 6.5 M uniforms of 8192 asks on one CTA becomes
+// ~15 jumps of ~50 us plus 1/G of the stream.
+//
+// One jump = (a) 32 more blocks generated into a 33 x 624-word shared buffer (W[0..623] = key), (b) the GF(2)
+// convolution with the lanes on the output axis: lane l owns outputs 20 l .. 20 l + 19 in registers, warp w walks
+// the polynomial words w, w + 24, ...; per polynomial word a 51-word window of W is loaded once (13 x LDS.128,
+// conflict-free at a 20-word lane stride) and every set bit costs 20 register XORs; (c) XOR-reduction over the
+// 24 warps.
+// ================================================================================================
+constexpr int kMtJumpWords = 33 * 624;          // W[0 .. 20591]: needs up to W[19936 + 624]
+constexpr int kMtJumpPad = 64;                  // windows of the last lane / last polynomial word run past the end
+constexpr int kMtJumpOut = 20;                  // outputs per lane
+constexpr size_t kMtJumpSmem = (size_t)(4 + kMtJumpWords + kMtJumpPad) * 4 + (size_t)24 * 640 * 4 + 2 * 624 * 4 + 16;
+
+// generator warps only (tid < 256): block `A + 624` from block `A`
+__device__ __forceinline__ void mt_next_block(const uint32_t* A, uint32_t* B, int tid) {
+  if (tid < 227) B[tid] = mt_twist(A[tid], A[tid + 1], A[tid + 397]);
+  mt_gen_barrier();
+  if (tid < 227) B[227 + tid] = mt_twist(A[227 + tid], A[228 + tid], B[tid]);
+  mt_gen_barrier();
+  if (tid < 170) {
+    const int j = 454 + tid;
+    B[j] = mt_twist(A[j], (j == 623) ? B[0] : A[j + 1], B[j - 227]);
+  }
+  mt_gen_barrier();
+}
+
+// W: shared, W[0..623] holds the key on entry and the key advanced by 2^k words on exit (all 768 threads call).
+// `red`: 24 x 640 words of shared scratch.  W must be 16-byte aligned at W + 1 (see the caller's layout).
+__device__ __forceinline__ void mt_jump_apply(uint32_t* W, uint32_t* red, const uint32_t* __restrict__ g) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 256)
+    for (int b = 1; b < 33; ++b) mt_next_block(W + 624 * (b - 1), W + 624 * b, tid);
+  __syncthreads();
+  uint32_t acc[kMtJumpOut];
+#pragma unroll
+  for (int q = 0; q < kMtJumpOut; ++q) acc[q] = 0u;
+  for (int ib = warp; ib < 624; ib += 24) {
+    const uint32_t G = __ldg(g + ib);
+    if (G == 0u) continue;
+    // window: W[32 ib + 20 lane + 1 + (0 .. 51)]
+    uint32_t win[52];
+    const uint4* src = reinterpret_cast<const uint4*>(W + 1 + 32 * ib + kMtJumpOut * lane);
+#pragma unroll
+    for (int v = 0; v < 13; ++v) {
+      const uint4 x = src[v];
+      win[4 * v] = x.x; win[4 * v + 1] = x.y; win[4 * v + 2] = x.z; win[4 * v + 3] = x.w;
+    }
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      if ((G >> t) & 1u) {   // uniform over the warp
+#pragma unroll
+        for (int q = 0; q < kMtJumpOut; ++q) acc[q] ^= win[t + q];
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kMtJumpOut; ++q) red[warp * 640 + kMtJumpOut * lane + q] = acc[q];
+  __syncthreads();
+  if (tid < 624) {
+    uint32_t v = 0u;
+#pragma unroll
+    for (int w = 0; w < 24; ++w) v ^= red[w * 640 + tid];
+    W[tid] = v;
+  }
+  __syncthreads();
+}
+
+// The block generator of k_mt19937_uniform on caller-provided shared buffers (buf[2][624], carry); all 768 threads.
+// Produces doubles [0, count) from the state (buf[0], start); returns the buffer index and position of the end state.
+__device__ __forceinline__ void mt_emit(uint32_t (*buf)[624], uint32_t* carry, int start, int64_t count,
+                                        double* __restrict__ out, int& cur_out, int& end_out) {
+  const int tid = threadIdx.x;
+  const bool gen = tid < 256;
+  const int wt = tid - 256;
+  int cur = 0, end_pos = start;
+  int64_t gw = 0;
+  const int64_t total_words = 2 * count;
+  while (gw < total_words) {
+    const int64_t avail = 624 - start;
+    const int take = (int)((total_words - gw < avail) ? (total_words - gw) : avail);
+    const bool more = gw + take < total_words;
+    const uint32_t* A = buf[cur];
+    uint32_t* B = buf[cur ^ 1];
+    if (gen) {
+      if (more) {
+        if (tid < 227) B[tid] = mt_twist(A[tid], A[tid + 1], A[tid + 397]);
+        mt_gen_barrier();
+        if (tid < 227) B[227 + tid] = mt_twist(A[227 + tid], A[228 + tid], B[tid]);
+        mt_gen_barrier();
+        if (tid < 170) {
+          const int j = 454 + tid;
+          B[j] = mt_twist(A[j], (j == 623) ? B[0] : A[j + 1], B[j - 227]);
+        }
+      }
+    } else {
+      const int odd = (int)(gw & 1);
+      if (odd && wt == 0 && take > 0) {
+        const int64_t d = gw >> 1;
+        const uint32_t a = *carry, b2 = mt_temper(A[start]) >> 6;
+        out[d] = ((double)a * 67108864.0 + (double)b2) / 9007199254740992.0;
+      }
+      const int pairs = (take - odd) / 2;
+      for (int p = wt; p < pairs; p += 512) {
+        const int j = start + odd + 2 * p;
+        const int64_t d = (gw + odd) / 2 + p;
+        const uint32_t a = mt_temper(A[j]) >> 5, b2 = mt_temper(A[j + 1]) >> 6;
+        out[d] = ((double)a * 67108864.0 + (double)b2) / 9007199254740992.0;
+      }
+    }
+    __syncthreads();
+    if (tid == 256 && take > 0 && ((take - (int)(gw & 1)) & 1)) *carry = mt_temper(A[start + take - 1]) >> 5;
+    gw += take;
+    if (more) {
+      cur ^= 1;
+      start = 0;
+      end_pos = 0;
+    } else {
+      end_pos = start + take;
+    }
+  }
+  __syncthreads();
+  cur_out = cur;
+  end_out = end_pos;
+}
+
+// key_in[625] = 624 state words + position (read-only: every CTA starts from it); key_out[625] = the state after
+// the (skip + count) draws, written by the CTA that produces the last double.  jump_table: kMtJumpTable on the device.
+__global__ void __launch_bounds__(kMtThreads, 1)
+k_mt19937_uniform_mc(const uint32_t* __restrict__ key_in, int64_t skip, int64_t count, int64_t chunk,
+                     const uint32_t* __restrict__ jump_table, int kmin, int kmax, double* __restrict__ out,
+                     uint32_t* __restrict__ key_out) {
+  extern __shared__ __align__(16) uint32_t mt_smem[];
+  uint32_t* W = mt_smem + 3;                               // W + 1 is 16-byte aligned
+  uint32_t* red = mt_smem + 4 + kMtJumpWords + kMtJumpPad;
+  uint32_t (*buf)[624] = reinterpret_cast<uint32_t (*)[624]>(red + 24 * 640);
+  uint32_t* carry = red + 24 * 640 + 2 * 624;
+  const int tid = threadIdx.x;
+  const int64_t first = (int64_t)blockIdx.x * chunk;
+  const int64_t mine = (count - first < chunk) ? (count - first) : chunk;
+  if (mine <= 0) return;
+  for (int i = tid; i < 624; i += kMtThreads) W[i] = key_in[i];
+  for (int i = tid; i < kMtJumpPad; i += kMtThreads) W[kMtJumpWords + i] = 0u;
+  // numpy regenerates its 624-word state block by block from the seed, and key_in is such a block: the CTA first
+  // jumps to the largest multiple of 512 below the block that holds its first word (one polynomial per set bit),
+  // then slides the window forward to that block -- so the walk that follows, and the end state, sit on numpy's
+  // own block grid (the state handed back to RandomState.set_state is the one numpy itself would hold)
+  const int64_t w0 = (int64_t)key_in[624] + 2 * (skip + first);   // first word of this CTA, relative to key[0]
+  const int64_t blk = (w0 >= 624) ? ((w0 - 1) / 624) * 624 : 0;   // numpy: a block is replaced only when a word beyond it is needed
+  const int64_t dist = blk & ~(int64_t)511;
+  const int shift = (int)(blk - dist);                            // 0..511
+  const int start = (int)(w0 - blk);                              // 0..624
+  __syncthreads();
+  for (int k = kmin; k <= kmax; ++k)
+    if ((dist >> k) & 1) mt_jump_apply(W, red, jump_table + (size_t)(k - kmin) * 624);
+  if (shift > 0) {
+    if (tid < 256) mt_next_block(W, W + 624, tid);
+    __syncthreads();
+  }
+  for (int i = tid; i < 624; i += kMtThreads) buf[0][i] = W[shift + i];
+  __syncthreads();
+  int cur, end_pos;
+  mt_emit(buf, carry, start, mine, out + first, cur, end_pos);
+  if (first + mine >= count) {
+    for (int i = tid; i < 624; i += kMtThreads) key_out[i] = buf[cur][i];
+    if (tid == 0) key_out[624] = (uint32_t)end_pos;
+  }
 }
 
 // ================================================================================================

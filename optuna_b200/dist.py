@@ -99,47 +99,96 @@ def sharded_asks(n_asks: int, per_ask: int, uniforms, compute: Callable[[np.ndar
     return np.concatenate(rows, axis=0)
 
 
-def sharded_asks_device_rng(engine, rng: np.random.RandomState, n_asks: int, per_ask: int, gather: bool = True):
-    """Like `sharded_asks`, but no rank ever holds the uniforms on the host: every rank starts from the
-    same generator state (shared seed) and the library generates the stream on its GPU, dropping the
-    uniforms of the asks that belong to earlier ranks (`skip`).  The rank owning the last block ends in
-    the state after ALL n_asks draws and broadcasts it (2.5 KB), so that every rank's `rng` continues as
-    if one process had drawn everything.  The engine must have been prepared and built; returns
-    [count or n_asks, P]."""
+class _DeviceArray:
+    """A raw device pointer as something ``torch.as_tensor`` wraps without a copy (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape: tuple, typestr: str) -> None:
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def device_view(ptr: int, shape: tuple, typestr: str, device):
+    import torch
+    return torch.as_tensor(_DeviceArray(ptr, shape, typestr), device=device)
+
+
+def sharded_asks_device_rng(engine, rng: np.random.RandomState, n_asks: int, per_ask: int, gather: bool = True,
+                            timing: dict | None = None):
+    """Like `sharded_asks`, but nothing touches the host between the generator state going in and the gathered
+    suggestions coming out:
+
+      * every rank starts from the same generator state (shared seed) and the library JUMPS to the uniforms of its
+        own asks (multi-CTA MT19937 with jump-ahead polynomials: no walk over the earlier ranks' prefix);
+      * the results stay in the context's device buffer (tpe_sample_and_select with out_x = NULL) and are gathered
+        by NCCL straight from it (all_gather_into_tensor on [most, P] blocks);
+      * the rank owning the last block ends in the state after ALL n_asks draws and broadcasts it device to device
+        into every rank's generator state (2.5 KB), so that every rank continues as if one process had drawn
+        everything; `rng` is brought up to date from there.
+
+    The engine must have been prepared and built; returns [n_asks, P] (gather) or this rank's [count, P]."""
+    import time
+
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(), dist.get_rank()
     start, count = shard_asks(n_asks, world, rank)
-    if count > 0:
-        engine.stage_rng(rng, count * per_ask, skip=start * per_ask)
-        mine, _, _ = engine.sample_and_select(None, count)
-        engine.finish_rng(rng)
-    else:
-        mine = np.zeros((0, engine._pc))
-    # common end state: the last rank with work has it
-    owner = max(r for r in range(world) if shard_asks(n_asks, world, r)[1] > 0) if n_asks > 0 else 0
-    st = rng.get_state()
-    pack = torch.empty(625, dtype=torch.int64)
-    if rank == owner:
-        pack[:624] = torch.from_numpy(np.asarray(st[1], dtype=np.int64))
-        pack[624] = int(st[2])
     nccl = dist.get_backend() == "nccl"
-    if nccl:
-        pack = pack.cuda()
-    dist.broadcast(pack, src=owner)
-    pack = pack.cpu().numpy()
-    rng.set_state((st[0], pack[:624].astype(np.uint32), int(pack[624]), st[3], st[4]))
-    mine = np.asarray(mine, dtype=np.float64).reshape(count, -1)
-    if not gather:
-        return mine
-    width = mine.shape[1] if count else int(engine._pc)
-    most = shard_asks(n_asks, world, 0)[1]
-    pad = torch.zeros((most, width), dtype=torch.float64)
-    pad[:count] = torch.from_numpy(mine)
-    if nccl:
-        pad = pad.cuda()
-    outs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(outs, pad)
-    rows = [outs[r][: shard_asks(n_asks, world, r)[1]].cpu().numpy() for r in range(world)]
-    return np.concatenate(rows, axis=0)
+    pc = int(engine._pc)
+    t0 = time.perf_counter()
+    if not nccl:  # gloo (CPU tests of the plumbing): same partition, host tensors
+        if count > 0:
+            engine.stage_rng(rng, count * per_ask, skip=start * per_ask)
+            mine, _, _ = engine.sample_and_select(None, count)
+            engine.finish_rng(rng)
+        else:
+            mine = np.zeros((0, pc))
+        owner = max(r for r in range(world) if shard_asks(n_asks, world, r)[1] > 0) if n_asks > 0 else 0
+        st = rng.get_state()
+        pack = torch.empty(625, dtype=torch.int64)
+        if rank == owner:
+            pack[:624] = torch.from_numpy(np.asarray(st[1], dtype=np.int64))
+            pack[624] = int(st[2])
+        dist.broadcast(pack, src=owner)
+        pack = pack.numpy()
+        rng.set_state((st[0], pack[:624].astype(np.uint32), int(pack[624]), st[3], st[4]))
+        mine = np.asarray(mine, dtype=np.float64).reshape(count, -1)
+        if not gather:
+            return mine
+        most = shard_asks(n_asks, world, 0)[1]
+        pad = torch.zeros((most, pc), dtype=torch.float64)
+        pad[:count] = torch.from_numpy(mine)
+        outs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(outs, pad)
+        return np.concatenate([outs[r][: shard_asks(n_asks, world, r)[1]].numpy() for r in range(world)], axis=0)
+
+    dev = torch.device("cuda", engine.device)
+    assert count > 0, "more ranks than asks"
+    engine.stage_rng(rng, count * per_ask, skip=start * per_ask)
+    px = engine.sample_and_select_device(count)          # returns when this rank's asks are done (stream sync)
+    t1 = time.perf_counter()
+    owner = max(r for r in range(world) if shard_asks(n_asks, world, r)[1] > 0)
+    state = device_view(engine.rng_state_device(), (625,), "<u4", dev).view(torch.int32)
+    dist.broadcast(state, src=owner)
+    mine = device_view(px, (count, pc), "<f8", dev)
+    out = None
+    if gather:
+        most = shard_asks(n_asks, world, 0)[1]
+        if count == most:
+            block = mine
+        else:
+            block = torch.zeros((most, pc), dtype=torch.float64, device=dev)
+            block[:count] = mine
+        allb = torch.empty((world, most, pc), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allb.view(-1), block.reshape(-1))
+        if n_asks == world * most:
+            out = allb.view(n_asks, pc).cpu().numpy()
+        else:
+            out = np.concatenate([allb[r, : shard_asks(n_asks, world, r)[1]].cpu().numpy() for r in range(world)], axis=0)
+    else:
+        out = mine.cpu().numpy()
+    torch.cuda.current_stream(dev).synchronize()      # the broadcast has landed in the engine's generator state
+    engine.finish_rng(rng)
+    if timing is not None:
+        timing["compute_s"] = t1 - t0
+        timing["collectives_s"] = time.perf_counter() - t1
+    return out

@@ -193,6 +193,21 @@ class TPEEngine:
         self._last_asks = n_asks
         return x, acq, best
 
+    def sample_and_select_device(self, n_asks: int = 1) -> int:
+        """Like ``sample_and_select(None, n_asks)`` but the results stay on the device; returns the device
+        address of out_x [n_asks, n_cols] fp64 (valid until the next call on this engine)."""
+        self._check(self._lib.tpe_sample_and_select(self._h, None, int(n_asks), None, None, None))
+        self._last_asks = n_asks
+        px = C.c_void_p()
+        self._check(self._lib.tpe_result_device_ptrs(self._h, C.byref(px), None, None))
+        return int(px.value)
+
+    def rng_state_device(self) -> int:
+        """Device address of the generator state (625 uint32) kept by ``stage_rng``; see tpe_rng_state_device."""
+        p = C.c_void_p()
+        self._check(self._lib.tpe_rng_state_device(self._h, C.byref(p)))
+        return int(p.value)
+
     def stage_rng(self, rng: np.random.RandomState | None, count: int, skip: int = 0) -> None:
         """Generate the next `count` outputs of ``rng.random_sample`` on the device (after dropping
         `skip`); the following ``sample_and_select(None, n_asks)`` consumes them.  ``finish_rng(rng)``

@@ -282,6 +282,9 @@ class B200TPESampler(BaseSampler):
     #: what answers the array-level calls -- the CUDA library; no fallback.  (The seam mirrors the reference's
     #: ``_parzen_estimator_cls``, sampler.py:358-359; tests plug the CPU oracle in here to check the host glue.)
     _engine_cls = TPEEngine
+    #: test hook: called as _audit(trial, search_space, engine) after every device suggestion (the candidates and
+    #: both log-densities of the ask are still on the engine: engine.get_candidates())
+    _audit = None
 
     def __init__(
         self,
@@ -688,7 +691,10 @@ class B200TPESampler(BaseSampler):
         cols = self._sync(study, trial, search_space)
         t1 = time.perf_counter()
         try:
-            return self._sample_synced(study, cols, search_space)
+            out = self._sample_synced(study, cols, search_space)
+            if self._audit is not None:
+                self._audit(trial, search_space, self._eng())
+            return out
         finally:
             # wall time of the last ask: history sync (host walk + row uploads) / everything after it
             # (prepare, build, uniforms, sampling + grids + argmax, read-back, to_external_repr)

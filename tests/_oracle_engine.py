@@ -159,11 +159,16 @@ class OracleEngine:
             rng = _ReplayRng(u[a * per: (a + 1) * per])
             cand = orc.mixture_sample(self._mix_b, rng, self._C)
             assert rng.at == per
-            score = orc.mixture_log_pdf(self._mix_b, cand) - orc.mixture_log_pdf(self._mix_a, cand)
+            ll, lg = orc.mixture_log_pdf(self._mix_b, cand), orc.mixture_log_pdf(self._mix_a, cand)
+            self._last = (cand, ll, lg)
+            score = ll - lg
             best[a] = int(np.argmax(score))
             acq[a] = score[best[a]]
             x[a] = cand[best[a]]
         return x, acq, best
+
+    def get_candidates(self):
+        return self._last
 
     def close(self) -> None:
         pass

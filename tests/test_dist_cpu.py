@@ -61,3 +61,41 @@ def test_broadcast_and_sharded_asks_gloo_world2(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     a, b = np.load(tmp_path / "r0.npy"), np.load(tmp_path / "r1.npy")
     assert np.array_equal(a, b) and a.shape == (37, 2)
+
+
+def _rng_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    """sharded_asks_device_rng with the CPU oracle standing in for the CUDA engine (gloo): the ranks' blocks of
+    asks concatenate to the batch one process computes, and every rank's generator ends in the same state."""
+    import torch.distributed as dist
+    from optuna_b200.dist import sharded_asks_device_rng
+    from optuna_b200.engine import ParamSpec
+    from tests._oracle_engine import OracleEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rs = np.random.RandomState(3)
+    n, P, C, n_asks = 60, 3, 8, 7
+    X = rs.uniform(0, 1, (n, P))
+    eng = OracleEngine()
+    eng.set_space([ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(P)])
+    eng.set_history(X, np.zeros(n, np.int8), np.stack([((X - 0.4) ** 2).sum(1), np.zeros(n)], 1))
+    eng.prepare(list(range(P)), n_below=6, n_candidates=C, multivariate=True)
+    eng.build()
+    per_ask = C * (1 + P)
+    rng = np.random.RandomState(21)
+    got = sharded_asks_device_rng(eng, rng, n_asks, per_ask, gather=True)
+    ref_rng = np.random.RandomState(21)
+    want, _, _ = eng.sample_and_select(ref_rng.random_sample(n_asks * per_ask), n_asks)
+    assert np.array_equal(got, want)
+    assert np.array_equal(rng.random_sample(5), ref_rng.random_sample(5))  # one generator that drew everything
+    np.save(os.path.join(out_dir, f"g{rank}.npy"), got)
+    dist.destroy_process_group()
+
+
+def test_sharded_asks_with_engine_generated_uniforms_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_rng_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert np.array_equal(np.load(tmp_path / "g0.npy"), np.load(tmp_path / "g1.npy"))
