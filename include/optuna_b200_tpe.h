@@ -123,7 +123,9 @@ int tpe_history_set_device(tpe_ctx* ctx, const double* dX, const int8_t* dcatego
  * every objective is minimised (sampler.py:755).  values [n, n_objectives] row-major.  With
  * n_objectives >= 2 the COMPLETE group is split by non-domination rank + greedy hypervolume subset
  * selection (sampler.py:745-779) and l(x) is weighted by hypervolume contributions (:824-863)
- * unless tpe_build is given explicit below-weights.  n_objectives <= 8; at most 64 below trials. */
+ * unless tpe_build is given explicit below-weights.  n_objectives <= 16; any number of below trials (the exact
+ * hypervolumes run over the Pareto front of the below set / the selected subset only; their scratch is O(n^2 M) per
+ * warp, TPE_E_NOMEM beyond 16 GB). */
 int tpe_history_set_values(tpe_ctx* ctx, const double* values, int64_t n, int32_t n_objectives, int64_t at_row);
 int64_t tpe_history_size(tpe_ctx* ctx);
 /* Device pointers of the resident history (for the NCCL broadcast done by the host plumbing). */

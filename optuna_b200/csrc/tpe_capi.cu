@@ -131,7 +131,7 @@ struct tpe_ctx {
   // MOTPE scratch
   DevBuf mo_list, mo_alive, mo_dom, mo_first, mo_rank, mo_ctr, mo_tie, mo_ntie, mo_lexpos, mo_isdup, mo_sorted,
       mo_uniq, mo_nuniq, mo_ref, mo_removed, mo_contrib, mo_state, mo_arena, mo_chosen, mo_diag, mo_w, mo_table, mo_sample,
-      mo_surv, mo_nsurv;
+      mo_surv, mo_nsurv, mo_fv, mo_ps, mo_map, mo_front, mo_head;
   bool mo_weights_ready = false;
   std::vector<uint8_t> col_missing, col_oor;
   bool history_set = false;
@@ -147,7 +147,7 @@ struct tpe_ctx {
   bool fast = false;
   int fast_mode = 0;  // 0 generic, 1 PAIR (sigma per kernel), 2 CONST (sigma per column)
   tpe_split_info info{};
-  DevBuf row_ok, member, counts, split_work;
+  DevBuf row_ok, member, counts, split_work, below_all;
   Estimator est[2];
   DevBuf sort_val, sort_idx, sort_work;
 
@@ -436,8 +436,6 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
   CU(ctx->member.ensure((size_t)std::max<int64_t>(N, 1)));
   CU(cudaMemsetAsync(ctx->member.p, 0, (size_t)std::max<int64_t>(N, 1), st));
   if (m == 0) return TPE_OK;
-  if (m > kMoMaxSet)
-    return fail(ctx, TPE_E_INVALID, "MOTPE supports at most %d below trials (got %lld)", kMoMaxSet, (long long)m);
   if (m == nc) {
     std::vector<uint8_t> mem((size_t)N, 0);
     for (int64_t r : list) mem[(size_t)r] = 1;
@@ -457,7 +455,6 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
   CU(ctx->mo_ref.ensure(kMoMaxM * 8));
   CU(ctx->mo_contrib.ensure((size_t)nc * 8));
   CU(ctx->mo_diag.ensure((size_t)nc * 16));
-  CU(ctx->mo_state.ensure(sizeof(HsspState)));
   CU(ctx->mo_sample.ensure(256 * 4));
   CU(ctx->mo_surv.ensure((size_t)nc * 4));
   CU(ctx->mo_nsurv.ensure(16));
@@ -558,7 +555,13 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
           ctx->launch_counter++;
         }
       } else {
-        CU(cudaMemsetAsync(ctx->mo_state.p, 0, sizeof(HsspState), st));
+        CU(ctx->mo_state.ensure(hssp_bytes(subset, M)));
+        CU(cudaMemsetAsync(ctx->mo_state.p, 0, hssp_bytes(subset, M), st));
+        {
+          HsspState head{0.0, 0, subset};
+          CU(cudaMemcpyAsync(ctx->mo_state.p, &head, sizeof(head), cudaMemcpyHostToDevice, st));
+          CU(cudaStreamSynchronize(st));  // `head` is a stack object
+        }
         CU(cudaMemsetAsync(ctx->mo_removed.p, 0, (size_t)nc, st));
         if (M == 2) {
           k_hssp_2d<<<1, 256, 0, st>>>(vals, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu, subset,
@@ -574,9 +577,15 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
           // falls back to one thread per candidate when that would need more than 2 GB
           const size_t nd_lane_stride = hv_lane_doubles(subset, M);
           const size_t nd_warp_stride = hv_warp_scratch_doubles(subset, M) + 32 * nd_lane_stride;
-          const bool nd_warp = M > 3 && (size_t)nu * nd_warp_stride * 8 <= ((size_t)2 << 30);
+          const bool nd_warp = M > 3 && (size_t)nu * nd_warp_stride * 8 <= ((size_t)8 << 30);
+          const size_t stride3 = (size_t)(subset + 1) * 8 + 16;  // hv3_warp scratch per candidate beyond the shared-memory size
+          const bool big3 = M == 3 && subset + 1 > kMoMaxSet + 1;
+          if (!nd_warp && M > 3 && (size_t)nu * stride * 8 > ((size_t)32 << 30))
+            return fail(ctx, TPE_E_NOMEM, "MOTPE subset selection: %d candidates x %d picks in %d objectives need %zu GB of "
+                        "hypervolume scratch", nu, subset, M, ((size_t)nu * stride * 8) >> 30);
           if (nd_warp) CU(ctx->mo_arena.ensure((size_t)nu * nd_warp_stride * 8));
-          else if (!sstride) CU(ctx->mo_arena.ensure((size_t)nu * stride * 8));
+          else if (big3) CU(ctx->mo_arena.ensure((size_t)nu * stride3 * 8));
+          else if (!sstride && M != 3) CU(ctx->mo_arena.ensure((size_t)nu * stride * 8));
           if (csmem > 48 * 1024)
             CU(cudaFuncSetAttribute(k_hssp_contrib, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
           for (int t = 0; t < subset; ++t) {
@@ -584,7 +593,8 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
               k_hssp_contrib3<<<(nu + 3) / 4, 128, 0, st>>>(vals, dlist, ctx->mo_tie.as<int32_t>(),
                                                             ctx->mo_uniq.as<int32_t>(), nu,
                                                             ctx->mo_removed.as<uint8_t>(), ctx->mo_ref.as<double>(),
-                                                            ctx->mo_state.as<HsspState>(), ctx->mo_contrib.as<double>());
+                                                            ctx->mo_state.as<HsspState>(), ctx->mo_contrib.as<double>(),
+                                                            ctx->mo_arena.as<double>(), stride3);
             } else if (nd_warp) {
               k_hssp_contrib_nd<<<(nu + 3) / 4, 128, 0, st>>>(
                   vals, M, dlist, ctx->mo_tie.as<int32_t>(), ctx->mo_uniq.as<int32_t>(), nu,
@@ -602,8 +612,8 @@ int mo_select_complete(tpe_ctx* ctx, int64_t n_below, int64_t* taken) {
             ctx->launch_counter += 2;
           }
         }
-        CU(cudaMemcpyAsync(ctx->mo_chosen.p, (char*)ctx->mo_state.p + offsetof(HsspState, pick), (size_t)subset * 4,
-                           cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(ctx->mo_chosen.p, (char*)ctx->mo_state.p + sizeof(HsspState) + (size_t)subset * M * 8,
+                           (size_t)subset * 4, cudaMemcpyDeviceToDevice, st));
       }
     }
     if (!chosen_on_device)
@@ -743,33 +753,76 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
     // MOTPE: hypervolume weights of ALL below trials, then the rows holding every selected param
     // pick theirs through `pos` (weights_below[param_mask_below], sampler.py:570-576)
     const int nba = (int)ctx->info.n_below_all;
-    if (nba > kMoMaxSet)
-      return fail(ctx, TPE_E_INVALID, "MOTPE supports at most %d below trials (got %d)", kMoMaxSet, nba);
-    if (nba != n) return fail(ctx, TPE_E_INVALID, "MOTPE with partially missing parameters in the below set is not supported yet");
-    const size_t stride = (size_t)(nba + 2) * ctx->M + hv_arena_doubles(nba + 1, ctx->M);
-    const int sstride = mo_smem_stride(nba + 1, ctx->M);
-    const size_t wsmem = sstride ? (size_t)kMoMaxSet * sstride * 8 : 0;
-    if (!sstride) CU(ctx->mo_arena.ensure((size_t)(nba + 1) * stride * 8));
-    if (wsmem > 32 * 1024)
-      CU(cudaFuncSetAttribute(k_mo_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-    CU(ctx->mo_w.ensure((size_t)kMoMaxSet * 8));
-    if (ctx->M == 3) {
-      static const size_t w3smem = (size_t)32 * kHv3Scratch * 8;
-      CU(cudaFuncSetAttribute(k_mo_weights3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w3smem));
-      k_mo_weights3<<<1, 1024, w3smem, st>>>(ctx->vals.as<double>(), e.rows.as<int64_t>(), nba, ctx->cat.as<int8_t>(),
-                                             ctx->mo_w.as<double>());
-    } else if (ctx->M > 3) {
-      const size_t lane_stride = hv_lane_doubles(nba + 1, ctx->M);
-      const size_t warp_stride = hv_warp_scratch_doubles(nba + 1, ctx->M) + 32 * lane_stride;
-      CU(ctx->mo_arena.ensure((size_t)32 * warp_stride * 8));
-      k_mo_weights_nd<<<1, 1024, 0, st>>>(ctx->vals.as<double>(), ctx->M, e.rows.as<int64_t>(), nba,
-                                          ctx->cat.as<int8_t>(), ctx->mo_w.as<double>(), ctx->mo_arena.as<double>(),
-                                          warp_stride, lane_stride);
+    const int M = ctx->M;
+    const int64_t* brows = ctx->below_all.as<int64_t>();   // every below trial, trial order (k_split_coop)
+    CU(ctx->mo_w.ensure((size_t)std::max(nba, 1) * 8));
+    if (nba <= kMoMaxSet) {
+      // small below set (the default gamma caps it at 25): one CTA, everything staged in shared memory
+      const size_t stride = (size_t)(nba + 2) * M + hv_arena_doubles(nba + 1, M);
+      const int sstride = mo_smem_stride(nba + 1, M);
+      const size_t wsmem = sstride ? (size_t)kMoMaxSet * sstride * 8 : 0;
+      if (!sstride) CU(ctx->mo_arena.ensure((size_t)(nba + 1) * stride * 8));
+      if (wsmem > 32 * 1024)
+        CU(cudaFuncSetAttribute(k_mo_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+      if (M == 3) {
+        static const size_t w3smem = (size_t)32 * kHv3Scratch * 8;
+        CU(cudaFuncSetAttribute(k_mo_weights3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w3smem));
+        k_mo_weights3<<<1, 1024, w3smem, st>>>(ctx->vals.as<double>(), brows, nba, ctx->cat.as<int8_t>(),
+                                               ctx->mo_w.as<double>());
+      } else if (M > 3) {
+        const size_t lane_stride = hv_lane_doubles(nba + 1, M);
+        const size_t warp_stride = hv_warp_scratch_doubles(nba + 1, M) + 32 * lane_stride;
+        CU(ctx->mo_arena.ensure((size_t)32 * warp_stride * 8));
+        k_mo_weights_nd<<<1, 1024, 0, st>>>(ctx->vals.as<double>(), M, brows, nba, ctx->cat.as<int8_t>(),
+                                            ctx->mo_w.as<double>(), ctx->mo_arena.as<double>(), warp_stride, lane_stride);
+      } else {
+        k_mo_weights<<<1, kMoMaxSet, wsmem, st>>>(ctx->vals.as<double>(), M, brows, nba, ctx->cat.as<int8_t>(),
+                                                  ctx->mo_w.as<double>(), ctx->mo_arena.as<double>(), stride, sstride);
+      }
     } else {
-      k_mo_weights<<<1, kMoMaxSet, wsmem, st>>>(ctx->vals.as<double>(), ctx->M, e.rows.as<int64_t>(), nba,
-                                                ctx->cat.as<int8_t>(), ctx->mo_w.as<double>(),
-                                                ctx->mo_arena.as<double>(), stride, sstride);
+      // any size: global-memory kernels; the exact hypervolumes run over the Pareto front of the below set only
+      CU(ctx->mo_fv.ensure((size_t)nba * M * 8));
+      CU(ctx->mo_ps.ensure((size_t)nba * M * 8));
+      CU(ctx->mo_map.ensure((size_t)nba * 4));
+      CU(ctx->mo_front.ensure((size_t)nba * 4));
+      CU(ctx->mo_contrib.ensure((size_t)nba * 8));
+      CU(ctx->mo_head.ensure(sizeof(MowHead)));
+      k_mow_prep<<<1, 1024, 0, st>>>(ctx->vals.as<double>(), M, brows, nba, ctx->cat.as<int8_t>(), ctx->mo_w.as<double>(),
+                                     ctx->mo_fv.as<double>(), ctx->mo_map.as<int32_t>(), ctx->mo_ps.as<double>(),
+                                     ctx->mo_front.as<int32_t>(), ctx->mo_contrib.as<double>(), ctx->mo_head.as<MowHead>());
+      MowHead head{};
+      CU(cudaMemcpyAsync(&head, ctx->mo_head.p, sizeof(head), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      ctx->launch_counter++;
+      const int np = head.np;
+      if (head.nf > 1 && np > 0) {
+        size_t lane_stride = 0, warp_stride;
+        if (M > 3) {
+          lane_stride = hv_lane_doubles(np, M);
+          warp_stride = (size_t)np * M + hv_warp_scratch_doubles(np, M) + 32 * lane_stride;
+        } else {
+          warp_stride = (size_t)np * M + hv_arena_doubles(np, M) + (size_t)np * 8 + 64;
+        }
+        const size_t budget = (size_t)16 << 30;
+        int64_t warps = std::min<int64_t>(np, (int64_t)ctx->sm_count * 16);
+        warps = std::min<int64_t>(warps, (int64_t)(budget / (warp_stride * 8)));
+        if (warps < 1)
+          return fail(ctx, TPE_E_NOMEM, "MOTPE weights: a Pareto front of %d points in %d objectives needs %zu GB of exact-"
+                      "hypervolume scratch per warp", np, M, (warp_stride * 8) >> 30);
+        const int blocks = (int)((warps + 3) / 4);
+        CU(ctx->mo_arena.ensure((size_t)blocks * 4 * warp_stride * 8));
+        k_mow_hv<<<1, 128, 0, st>>>(ctx->mo_ps.as<double>(), ctx->mo_front.as<int32_t>(), M, ctx->mo_head.as<MowHead>(), np,
+                                    np, ctx->mo_contrib.as<double>(), ctx->mo_arena.as<double>(), warp_stride, lane_stride);
+        k_mow_hv<<<blocks, 128, 0, st>>>(ctx->mo_ps.as<double>(), ctx->mo_front.as<int32_t>(), M,
+                                         ctx->mo_head.as<MowHead>(), 0, np - 1, ctx->mo_contrib.as<double>(),
+                                         ctx->mo_arena.as<double>(), warp_stride, lane_stride);
+        k_mow_norm<<<1, 1024, 0, st>>>(ctx->mo_head.as<MowHead>(), ctx->mo_contrib.as<double>(), ctx->mo_map.as<int32_t>(),
+                                       ctx->mo_w.as<double>());
+        ctx->launch_counter += 3;
+      }
     }
+    w_pos = e.pos.as<int64_t>();   // an observation row picks the weight of its position among ALL below trials
+                                   // (weights_below[param_mask_below], sampler.py:570-576)
     ctx->launch_counter++;
     ctx->mo_weights_ready = true;
     w_dev = ctx->mo_w.as<double>();
@@ -1022,9 +1075,9 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   for (DevBuf* b : {&ctx->cat_dist, &ctx->X, &ctx->cat, &ctx->key, &ctx->vals, &ctx->mo_list, &ctx->mo_alive, &ctx->mo_dom,
                     &ctx->mo_first, &ctx->mo_rank, &ctx->mo_ctr, &ctx->mo_tie, &ctx->mo_ntie, &ctx->mo_lexpos,
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed, &ctx->mo_table,
-                    &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv,
+                    &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv, &ctx->mo_fv, &ctx->mo_ps, &ctx->mo_map, &ctx->mo_front, &ctx->mo_head,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
-                    &ctx->counts, &ctx->split_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
+                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->U2, &ctx->mt_spec, &ctx->mt_jump, &ctx->mt_tmp, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
@@ -1330,7 +1383,12 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
     int64_t* d_p = ctx->est[0].pos.as<int64_t>();
     int64_t* d_a = ctx->est[1].rows.as<int64_t>();
     int64_t* d_c = ctx->counts.as<int64_t>();
-    void* args[] = {&n_i, &d_cat, &d_key, &nb, &rowok, &pre_member, &d_wk, &d_b, &d_p, &d_a, &d_c};
+    int64_t* d_ball = nullptr;
+    if (ctx->M >= 2) {
+      CU(ctx->below_all.ensure((size_t)nal * 8));
+      d_ball = ctx->below_all.as<int64_t>();
+    }
+    void* args[] = {&n_i, &d_cat, &d_key, &nb, &rowok, &pre_member, &d_wk, &d_b, &d_p, &d_a, &d_c, &d_ball};
     const int G = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (N + 1023) / 1024));
     CU(cudaLaunchCooperativeKernel((const void*)k_split_coop, dim3(G), dim3(512), args, 0, ctx->stream));
     ctx->launch_counter++;

@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(512, 1)
 k_split_coop(int n, const int8_t* __restrict__ cat, const double* __restrict__ key, int64_t n_below,
              const uint8_t* __restrict__ row_ok, const uint8_t* __restrict__ pre_member, SplitWork* __restrict__ wk,
              int64_t* __restrict__ below_rows,
-             int64_t* __restrict__ below_pos, int64_t* __restrict__ above_rows, int64_t* __restrict__ counts) {
+             int64_t* __restrict__ below_pos, int64_t* __restrict__ above_rows, int64_t* __restrict__ counts,
+             int64_t* __restrict__ below_all_rows /* every below trial, also those lacking a selected parameter
+                                                    (the multi-objective weights are computed over all of them) */) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   __shared__ int s_hist[256];
   __shared__ int s_pick[3];
@@ -217,6 +219,7 @@ k_split_coop(int n, const int8_t* __restrict__ cat, const double* __restrict__ k
       const int r_b = rank(isb && ok, tot_b);
       const int r_a = rank(v && !isb && ok, tot_a);
       if (write) {
+        if (isb && below_all_rows != nullptr) below_all_rows[nb_all + r_all] = i;
         if (isb && ok) {
           below_rows[nbo + r_b] = i;
           below_pos[nbo + r_b] = nb_all + r_all;

@@ -10,8 +10,9 @@
 
 namespace tpe {
 
-constexpr int kMoMaxM = 8;       // objectives
-constexpr int kMoMaxSet = 64;    // points entering an exact hypervolume (below set / selected set)
+constexpr int kMoMaxM = 16;      // objectives (shared-memory staging of the small-set kernels; exact WFG beyond ~8 is slow anyway)
+constexpr int kMoMaxSet = 64;    // "small set": points staged in shared memory by the one-CTA kernels; larger sets take
+                                 // the global-memory kernels at the end of this file (no limit but memory)
 
 struct MoCounters {
   int covered_unique, covered_all, n_unique, pad;
@@ -256,13 +257,21 @@ k_mo_unique(int n, const int32_t* __restrict__ lexpos, const uint8_t* __restrict
   if (threadIdx.x == 0) *n_unique = cnt;
 }
 
+// Greedy-selection state in global memory: header, then sel[cap * M] (selected vectors, pick order), then
+// pick[cap] (tie-local index of the picks).  cap = subset size of this call.
 struct HsspState {
   double hv;            // hypervolume of the selected set (running sum of picked contributions)
   int n_sel;
-  int pad;
-  double sel[kMoMaxSet * kMoMaxM];  // selected vectors, pick order
-  int32_t pick[kMoMaxSet];          // tie-local index of the picks
+  int cap;
 };
+__host__ __device__ inline double* hssp_sel(HsspState* s) { return reinterpret_cast<double*>(s + 1); }
+__host__ __device__ inline const double* hssp_sel(const HsspState* s) { return reinterpret_cast<const double*>(s + 1); }
+__host__ __device__ inline int32_t* hssp_pick(HsspState* s, int M) {
+  return reinterpret_cast<int32_t*>(hssp_sel(s) + (size_t)s->cap * M);
+}
+__host__ __device__ inline size_t hssp_bytes(int cap, int M) {
+  return sizeof(HsspState) + (size_t)cap * M * 8 + (size_t)cap * 4 + 8;
+}
 
 // Warp-cooperative exact 3-D hypervolume of n <= kMoMaxSet + 1 mutually non-dominated points
 // (the assume_pareto branch of hypervolume()), bit-identical to it: the two stable insertion sorts
@@ -324,7 +333,8 @@ __global__ void __launch_bounds__(128)
 k_hssp_contrib3(const double* __restrict__ vals, const int64_t* __restrict__ list,
                 const int32_t* __restrict__ tie_pos, const int32_t* __restrict__ uniq, int nu,
                 const uint8_t* __restrict__ removed, const double* __restrict__ ref,
-                const HsspState* __restrict__ st, double* __restrict__ contrib) {
+                const HsspState* __restrict__ st, double* __restrict__ contrib, double* __restrict__ arena,
+                size_t arena_stride) {
   __shared__ double s_scr[4][kHv3Scratch];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int u = blockIdx.x * 4 + w;
@@ -345,11 +355,11 @@ k_hssp_contrib3(const double* __restrict__ vals, const int64_t* __restrict__ lis
     if (lane == 0) contrib[u] = INFINITY;
     return;
   }
-  double* pts = s_scr[w];
+  double* pts = (t + 1 <= kMoMaxSet + 1) ? s_scr[w] : arena + (size_t)u * arena_stride;
   double* srt = pts + (t + 1) * 3;
   double* term = srt + (t + 1) * 3;
   int* ord = reinterpret_cast<int*>(term + (t + 1));
-  for (int q = lane; q < t * 3; q += 32) pts[q] = st->sel[q];
+  for (int q = lane; q < t * 3; q += 32) pts[q] = hssp_sel(st)[q];
   if (lane < 3) pts[t * 3 + lane] = me[lane];
   __syncwarp();
   const double hv = hv3_warp(pts, t + 1, ref, srt, term, ord);
@@ -511,7 +521,7 @@ k_hssp_contrib_nd(const double* __restrict__ vals, int M, const int64_t* __restr
   double* lanes = wsb + hv_warp_scratch_doubles(t, M);
   for (int q = lane; q < t * M; q += 32) {
     const int j = q % M;
-    const double b = st->sel[q];
+    const double b = hssp_sel(st)[q];
     pts[q] = me[j] > b ? me[j] : b;
   }
   __syncwarp();
@@ -553,14 +563,14 @@ __global__ void k_hssp_contrib(const double* __restrict__ vals, int M, const int
   if (M <= 3) {
     // H(S + {i}) - H(S), assume_pareto (points of one non-domination rank are mutually non-dominated)
     for (int s = 0; s < t; ++s)
-      for (int j = 0; j < M; ++j) pts[s * M + j] = st->sel[s * M + j];
+      for (int j = 0; j < M; ++j) pts[s * M + j] = hssp_sel(st)[s * M + j];
     for (int j = 0; j < M; ++j) pts[t * M + j] = me[j];
     contrib[u] = TPE_SUB(hypervolume(pts, t + 1, M, ref, true, rest), st->hv);
   } else {
     // H({i}) - H(S limited by i)
     for (int s = 0; s < t; ++s)
       for (int j = 0; j < M; ++j) {
-        const double b = st->sel[s * M + j];
+        const double b = hssp_sel(st)[s * M + j];
         pts[s * M + j] = me[j] > b ? me[j] : b;
       }
     contrib[u] = TPE_SUB(incl, hypervolume(pts, t, M, ref, false, rest));
@@ -607,9 +617,9 @@ k_hssp_pick(const double* __restrict__ vals, int M, const int64_t* __restrict__ 
     const int u = s_idx[0];
     const int t = st->n_sel;
     st->hv = TPE_ADD(st->hv, s_val[0]);
-    st->pick[t] = uniq[u];
+    hssp_pick(st, M)[t] = uniq[u];
     const double* me = vals + list[tie_pos[uniq[u]]] * M;
-    for (int j = 0; j < M; ++j) st->sel[t * M + j] = me[j];
+    for (int j = 0; j < M; ++j) hssp_sel(st)[t * M + j] = me[j];
     st->n_sel = t + 1;
     removed[u] = 1;
   }
@@ -664,7 +674,7 @@ k_hssp_2d(const double* __restrict__ vals, const int64_t* __restrict__ list, con
     const double px = pj[0], py = pj[1];
     __syncthreads();
     if (threadIdx.x == 0) {
-      st->pick[t] = uniq[j];
+      hssp_pick(st, 2)[t] = uniq[j];
       st->n_sel = t + 1;
       removed[j] = 1;
     }
@@ -989,6 +999,168 @@ k_mo_weights_nd(const double* __restrict__ vals, int M, const int64_t* __restric
   }
   __syncthreads();
   if (tid < nf) w[s_map[tid]] = fmax(TPE_DIV(s_contrib[tid], s_max), 1e-12);
+}
+
+// ================================================================================================
+// Hypervolume weights of a below set of ANY size (sampler.py:824-863) -- global-memory version of k_mo_weights*.
+// Only the Pareto front of the feasible below trials enters a hypervolume (everything else gets contribution 0,
+// i.e. weight EPS), so the exact work is bounded by the size of that front, not by n_below: with gamma = 0.1 n at
+// 20 000 four-objective trials the below set has 2000 trials and its front 34 points.
+//   k_mow_prep   one CTA: feasibility, reference point, Pareto flags (thread per point), ordered compaction
+//   k_mow_hv     one warp per leave-one-out term (index np = nothing left out: the front's own hypervolume)
+//   k_mow_norm   weights = max(contrib / max(contrib), EPS)
+// ================================================================================================
+struct MowHead {
+  int nf, np;
+  double hv;
+  double ref[kMoMaxM];
+};
+
+__global__ void __launch_bounds__(1024, 1)
+k_mow_prep(const double* __restrict__ vals, int M, const int64_t* __restrict__ rows, int n, const int8_t* __restrict__ cat,
+           double* __restrict__ w, double* __restrict__ fv, int32_t* __restrict__ map, double* __restrict__ ps,
+           int32_t* __restrict__ front, double* __restrict__ contrib, MowHead* __restrict__ head) {
+  __shared__ int s_warp[32];
+  __shared__ double s_red[32];
+  __shared__ int s_nan;
+  const int tid = threadIdx.x;
+  // feasible points in trial order
+  int nf = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const bool feas = i < n && cat[rows[i]] != 2;
+    if (i < n) w[i] = feas ? 1.0 : 1e-12;
+    const int2 rr = block_rank_1024(feas, s_warp);
+    if (feas) {
+      for (int j = 0; j < M; ++j) fv[(size_t)(nf + rr.x) * M + j] = vals[rows[i] * M + j];
+      map[nf + rr.x] = i;
+    }
+    nf += rr.y;
+  }
+  __syncthreads();
+  if (tid == 0) { head->nf = nf; head->np = 0; head->hv = 0.0; }
+  if (nf <= 1) return;
+  // reference point: np.max per objective (NaN wins), 1.1 / 0.9 rule, 0 -> EPS (sampler.py:679-683)
+  for (int j = 0; j < M; ++j) {
+    if (tid == 0) s_nan = 0;
+    __syncthreads();
+    double mx = -INFINITY;
+    for (int i = tid; i < nf; i += 1024) {
+      const double v = fv[(size_t)i * M + j];
+      if (v != v) s_nan = 1;
+      else mx = v > mx ? v : mx;
+    }
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, mx, o); mx = t > mx ? t : mx; }
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      double worst = s_red[0];
+      for (int q = 1; q < 32; ++q) worst = s_red[q] > worst ? s_red[q] : worst;
+      if (s_nan) worst = NAN;
+      double r = fmax(TPE_MUL(1.1, worst), TPE_MUL(0.9, worst));
+      if (r == 0.0) r = 1e-12;
+      head->ref[j] = r;
+    }
+    __syncthreads();
+  }
+  // Pareto front of the feasible points, trial order
+  int np = 0;
+  for (int base = 0; base < nf; base += 1024) {
+    const int i = base + tid;
+    bool keep = false;
+    if (i < nf) {
+      bool dom = false;
+      for (int q = 0; q < nf && !dom; ++q) dom = (q != i) && dominates(fv + (size_t)q * M, fv + (size_t)i * M, M);
+      keep = !dom;
+      contrib[i] = 0.0;
+    }
+    const int2 rr = block_rank_1024(keep, s_warp);
+    if (keep) {
+      for (int j = 0; j < M; ++j) ps[(size_t)(np + rr.x) * M + j] = fv[(size_t)i * M + j];
+      front[np + rr.x] = i;
+    }
+    np += rr.y;
+  }
+  if (tid == 0) head->np = np;
+}
+
+// warp w of the grid evaluates terms p = first + w, first + w + nwarps, ...  (p == np: the whole front -> head->hv).
+// The other terms need head->hv: launch once with [np, np] and then with [0, np - 1].
+__global__ void __launch_bounds__(128)
+k_mow_hv(const double* __restrict__ ps, const int32_t* __restrict__ front, int M, MowHead* __restrict__ head,
+         int first, int last, double* __restrict__ contrib, double* __restrict__ arena, size_t warp_stride,
+         size_t lane_stride) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 4 + (threadIdx.x >> 5), nw = gridDim.x * 4;
+  const int np = head->np;
+  const double* ref = head->ref;
+  double* wsb = arena + (size_t)gw * warp_stride;
+  for (int p = first + gw; p <= last && p <= np; p += nw) {
+    const bool whole = p == np;
+    if (!whole && isinf(head->hv)) return;   // weights stay at 1 / EPS (sampler.py:846-849)
+    const int c = whole ? np : np - 1;
+    double* pts = wsb;
+    double val;
+    if (M <= 3) {
+      for (int q = lane; q < np; q += 32) {
+        if (q == p) continue;
+        const int d = (whole || q < p) ? q : q - 1;
+        for (int j = 0; j < M; ++j) pts[(size_t)d * M + j] = ps[(size_t)q * M + j];
+      }
+      __syncwarp();
+      double h;
+      if (M == 3) {
+        double* srt = pts + (size_t)c * 3;
+        double* term = srt + (size_t)c * 3;
+        h = hv3_warp(pts, c, ref, srt, term, reinterpret_cast<int*>(term + c));
+      } else {
+        h = 0.0;
+        if (lane == 0) h = hypervolume(pts, c, M, ref, true, pts + (size_t)c * M);
+        h = __shfl_sync(0xffffffffu, h, 0);
+      }
+      val = whole ? h : TPE_SUB(head->hv, h);
+    } else {
+      double* ws = wsb + (size_t)np * M;
+      double* lanes = wsb + (size_t)np * M + hv_warp_scratch_doubles(np, M);
+      if (whole) {
+        val = hv_nd_warp(ps, np, M, ref, true, ws, lanes + (size_t)lane * lane_stride);
+      } else {
+        double incl = 1.0;
+        for (int j = 0; j < M; ++j) incl = TPE_MUL(incl, TPE_SUB(ref[j], ps[(size_t)p * M + j]));
+        for (int q = lane; q < np; q += 32) {
+          if (q == p) continue;
+          const int d = q < p ? q : q - 1;
+          for (int j = 0; j < M; ++j) {
+            const double x = ps[(size_t)q * M + j], y = ps[(size_t)p * M + j];
+            pts[(size_t)d * M + j] = x > y ? x : y;
+          }
+        }
+        __syncwarp();
+        const double h = hv_nd_warp(pts, c, M, ref, false, ws, lanes + (size_t)lane * lane_stride);
+        val = TPE_SUB(incl, h);
+      }
+    }
+    if (lane == 0) {
+      if (whole) head->hv = val;
+      else contrib[front[p]] = val;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+k_mow_norm(const MowHead* __restrict__ head, const double* __restrict__ contrib, const int32_t* __restrict__ map,
+           double* __restrict__ w) {
+  __shared__ double s_max;
+  const int nf = head->nf;
+  if (nf <= 1 || isinf(head->hv)) return;
+  if (threadIdx.x == 0) {  // np.max: NaN wins; then max(., EPS)
+    double mx = contrib[0];
+    for (int i = 1; i < nf; ++i) mx = (contrib[i] > mx || contrib[i] != contrib[i]) ? contrib[i] : mx;
+    s_max = fmax(mx, 1e-12);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nf; i += 1024) w[map[i]] = fmax(TPE_DIV(contrib[i], s_max), 1e-12);
 }
 
 }  // namespace tpe

@@ -17,11 +17,11 @@ def eng():
     e.close()
 
 
-def _setup(eng, X, vals):
+def _setup(eng, X, vals, cat=None):
     from optuna_b200.engine import ParamSpec
     n, P = X.shape
     eng.set_space([ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(P)])
-    eng.set_history(X, np.zeros(n, np.int8), np.zeros((n, 2)))
+    eng.set_history(X, np.zeros(n, np.int8) if cat is None else cat, np.zeros((n, 2)))
     eng.set_values(vals, 0)
 
 
@@ -39,7 +39,7 @@ def test_mo_split_and_weights_match_reference(eng):
         below, above = eng.get_split()
         assert np.array_equal(below, want), (ci, below, want)
         assert info[0] == want.size
-        if 0 < want.size <= 64:
+        if 0 < want.size:
             eng.build()
             w = eng.get_mo_weights()
             ref = g[t + "w"]
@@ -55,10 +55,6 @@ def test_motpe_suggestions_match_reference(eng):
         X, vals = g[t + "X"], g[t + "values"]
         P = X.shape[1]
         _setup(eng, X, vals)
-        if n_below > 64:
-            with pytest.raises(ValueError):
-                eng.prepare(list(range(P)), n_below=n_below, n_candidates=C, multivariate=mv)
-            continue
         rng = np.random.RandomState(int(seed))
         calls = [list(range(P))] if mv else [[j] for j in range(P)]
         ret = []
@@ -94,3 +90,37 @@ def test_mo_rank_properties_at_scale(eng):
     assert below.size + above.size == n
     eng.build()
     np.testing.assert_allclose(eng.get_mo_weights(), mo.weights_below_mo(vals[want]), rtol=1e-9, atol=1e-15)
+
+
+@pytest.mark.parametrize("M", [2, 3, 4])
+def test_large_below_sets_gamma_ten_percent(eng, M):
+    """SURVEY.md 8d, config 4 with gamma = ceil(0.1 n): the below set has hundreds to thousands of trials -- no cap on
+    the device (the reference has none: sampler.py:745-779, :824-863, hssp.py:143-176).  Split and weights against the
+    oracle; rows lacking a selected parameter pick their weight by position (weights_below[param_mask_below])."""
+    rs = np.random.RandomState(M)
+    N, P = (20000, 8) if M == 4 else (6000, 4)
+    X = rs.uniform(0, 1, (N, P))
+    X[rs.uniform(size=N) < 0.1, 1] = np.nan           # conditional parameter: absent in 10 % of the trials
+    cs = np.array([0.2, 0.4, 0.6, 0.8])[:M]
+    vals = ((np.nan_to_num(X, nan=0.5)[:, None, :] - cs[None, :, None]) ** 2).sum(2)
+    cat = np.zeros(N, np.int8)
+    cat[rs.uniform(size=N) < 0.02] = 2                # a few infeasible trials (EPS weight when they end up below)
+    _setup(eng, X, vals, cat)
+    nb = int(np.ceil(0.1 * N))
+    info = eng.prepare([0, 1], n_below=nb, n_candidates=8, multivariate=True)
+    below, above = eng.get_split()
+    comp = np.flatnonzero(cat == 0)
+    want = comp[mo.split_complete_mo(vals[comp], min(nb, comp.size))]
+    assert info[0] == nb
+    rest = nb - want.size                              # filled from the infeasible group, by violation then trial order
+    infe = np.flatnonzero(cat == 2)[:rest]
+    all_below = np.sort(np.concatenate([want, infe]))
+    has = ~np.isnan(X[all_below][:, [0, 1]]).any(1)
+    assert np.array_equal(below, all_below[has])
+    eng.build()
+    w = eng.get_mo_weights()
+    ref = mo.weights_below_mo(vals[all_below], cat[all_below] != 2)
+    np.testing.assert_allclose(w, ref, rtol=1e-9, atol=1e-15)
+    wb = eng.get_mixture(0)[0]                         # mixture weights: the rows holding both parameters + prior
+    raw = np.append(ref[has], 1.0)
+    np.testing.assert_allclose(wb, raw / raw.sum(), rtol=1e-9, atol=1e-18)

@@ -174,7 +174,8 @@ def test_custom_gamma_weights_and_constraints(make_sampler):
     kw = dict(seed=1, gamma=lambda n: max(1, n // 4), weights=lambda n: np.arange(1, n + 1) ** 0.5,
               constraints_func=lambda tr: (tr.user_attrs["c"], -1.0), n_startup_trials=5)
     a, b = run_both(make_sampler, obj, 40, ties=True, **kw)
-    assert [t.system_attrs.get("constraints") for t in a.trials] == [t.system_attrs.get("constraints") for t in b.trials]
+    for ta, tb in zip(a.trials, b.trials):  # constraints are stored once, by after_trial (samplers/_base.py:242-268)
+        np.testing.assert_allclose(ta.system_attrs["constraints"], tb.system_attrs["constraints"], rtol=1e-9)
     with pytest.raises(ValueError):
         bad = optuna.create_study(sampler=make_sampler(seed=1, weights=lambda n: -np.ones(n), n_startup_trials=2))
         bad.optimize(lambda t: t.suggest_float("x", 0, 1), n_trials=5)
@@ -276,6 +277,24 @@ def test_motpe_through_the_study(make_sampler, n_obj):
 
     for mv in (False, True):
         run_both(make_sampler, obj, 40, {"directions": dirs}, seed=5, multivariate=mv)
+
+
+def test_motpe_with_conditional_parameters_and_constraints(make_sampler):
+    """Multi-objective + a parameter only some trials have + constraints: the hypervolume weights are computed over
+    ALL below trials and the trials lacking the parameter drop out afterwards (weights_below[param_mask_below],
+    sampler.py:570-576); infeasible below trials weigh EPS (:829-833)."""
+    def obj(t):
+        x = t.suggest_float("x", 0, 1)
+        y = t.suggest_float("y", 0, 1) if x > 0.4 else 0.5
+        t.set_user_attr("c", x + y - 1.4)
+        return (x - 0.2) ** 2 + (y - 0.7) ** 2, (x - 0.8) ** 2 + (y - 0.3) ** 2
+
+    for mv in (False, True):
+        run_both(make_sampler, obj, 45, {"directions": ["minimize", "minimize"]}, seed=3, multivariate=mv,
+                 n_startup_trials=8, constraints_func=lambda tr: (tr.user_attrs["c"],))
+    # a custom gamma puts most trials below: far more than the 25 of the default
+    run_both(make_sampler, obj, 90, {"directions": ["minimize", "minimize"]}, seed=4, multivariate=True,
+             n_startup_trials=8, gamma=lambda n: (3 * n) // 4)
 
 
 def test_dynamic_range_and_single_distributions(make_sampler):
