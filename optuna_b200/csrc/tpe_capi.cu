@@ -18,7 +18,14 @@
 #include "../../include/optuna_b200_tpe.h"
 #include "tpe_kernels.cuh"
 #include "tpe_motpe_kernels.cuh"
+// Lab build (-DTPE_LAB): the experimental grid kernels and the timing-attribution variants measured in
+// profiles/r1_variants.md / r2_variants.md, selectable by environment variables.  Some of them switch parts of the
+// log-sum-exp off (wrong results by design).  The product library contains none of them.
+#ifdef TPE_LAB
+#include "tpe_mma2.cuh"
+#include "tpe_mma3.cuh"
 #include "tpe_screen.cuh"
+#endif
 
 using namespace tpe;
 
@@ -231,7 +238,11 @@ struct MmaInst {
                      double2* part, unsigned long long* gmax) {
     // near tier: within ln K + 17.5 of the reference max (see LseTier); TPE_TNEAR_DELTA shrinks it for
     // timing experiments only (the accuracy bound no longer holds)
+#ifdef TPE_LAB
     static const double delta = [] { const char* v = getenv("TPE_TNEAR_DELTA"); return v ? atof(v) : 0.0; }();
+#else
+    constexpr double delta = 0.0;
+#endif
     k_logpdf_mma<PB, M, KG, NT, TK, ST, MINB, DBG><<<grid, NT, sm, st>>>(static_cast<const double*>(tab), cst, Kf, colprm,
                                                                         xT, ct_stride, kps, skip, part, gmax,
                                                                         skip - 12.5 - delta);
@@ -242,6 +253,59 @@ struct MmaInst {
   }
   static FastCfg cfg() { return FastCfg{PB, (NT / 32) * 8 * M, NT, TK, ST, MINB, smem, &launch, &prepare}; }
 };
+#ifdef TPE_LAB
+// round-2 kernel (tpe_mma2.cuh): OPT bit 0 = seeded base, bit 1 = pipelined classification
+template <int PB, int M, int KG, int NT, int TK, int ST, int MINB, int OPT>
+struct MmaInst2 {
+  static constexpr size_t smem = (size_t)ST * TK * PB * 8 + (size_t)ST * TK * 8 + (size_t)ST * 16;
+  static void launch(dim3 grid, size_t sm, cudaStream_t st, const void* tab, const double* cst, int64_t Kf,
+                     const double2* colprm, const double* xT, int64_t ct_stride, int64_t kps, double skip,
+                     double2* part, unsigned long long* gmax) {
+    // OPT bit 2 (budgeted log-sum-exp): the last argument is the fp32-tier budget of one lane, 2e-7 / (4 * k-splits)
+    const double last = (OPT & 4) ? 2e-7 / (4.0 * grid.y) : skip - 12.5;
+    k_logpdf_mma2<PB, M, KG, NT, TK, ST, MINB, OPT><<<grid, NT, sm, st>>>(static_cast<const double*>(tab), cst, Kf, colprm,
+                                                                         xT, ct_stride, kps, skip, part, gmax, last);
+  }
+  static cudaError_t prepare() {
+    return cudaFuncSetAttribute(k_logpdf_mma2<PB, M, KG, NT, TK, ST, MINB, OPT>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  static FastCfg cfg() { return FastCfg{PB, (NT / 32) * 8 * M, NT, TK, ST, MINB, smem, &launch, &prepare}; }
+};
+// warp-compacted exact tier (tpe_mma3.cuh)
+template <int PB, int KG, int NT, int TK, int ST, int MINB>
+struct MmaInst3 {
+  static constexpr size_t smem = (size_t)ST * TK * PB * 8 + (size_t)ST * TK * 8 + (size_t)ST * 16 + (size_t)(NT / 32) * kQWarpBytes;
+  static void launch(dim3 grid, size_t sm, cudaStream_t st, const void* tab, const double* cst, int64_t Kf,
+                     const double2* colprm, const double* xT, int64_t ct_stride, int64_t kps, double skip,
+                     double2* part, unsigned long long* gmax) {
+    k_logpdf_mma3<PB, KG, NT, TK, ST, MINB><<<grid, NT, sm, st>>>(static_cast<const double*>(tab), cst, Kf, colprm, xT,
+                                                                 ct_stride, kps, skip, part, gmax, skip - 12.5);
+  }
+  static cudaError_t prepare() {
+    return cudaFuncSetAttribute(k_logpdf_mma3<PB, KG, NT, TK, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem);
+  }
+  static FastCfg cfg() { return FastCfg{PB, (NT / 32) * 8, NT, TK, ST, MINB, smem, &launch, &prepare}; }
+};
+const FastCfg kMma32V3[] = {
+    MmaInst3<32, 2, 512, 128, 3, 2>::cfg(),  // i
+    MmaInst3<32, 4, 256, 128, 3, 2>::cfg(),  // j: 4 kernel groups in flight, 16 warps / SM
+    MmaInst3<32, 2, 256, 128, 3, 3>::cfg(),  // k: 3 CTAs x 8 warps
+};
+const FastCfg kMma32V2[] = {
+    MmaInst2<32, 1, 2, 512, 128, 3, 2, 1>::cfg(),  // 8: seed
+    MmaInst2<32, 1, 2, 512, 128, 3, 2, 3>::cfg(),  // 9: seed + pipe
+    MmaInst2<32, 1, 2, 512, 128, 3, 2, 2>::cfg(),  // a: pipe
+    MmaInst2<32, 1, 4, 256, 128, 3, 2, 3>::cfg(),  // b: seed + pipe, 4 kernel groups in flight, 16 warps / SM
+    MmaInst2<32, 1, 2, 256, 128, 3, 3, 3>::cfg(),  // c: seed + pipe, 3 CTAs x 8 warps
+    MmaInst2<32, 1, 2, 512, 128, 3, 2, 4>::cfg(),  // d: budgeted log-sum-exp
+    MmaInst2<32, 1, 2, 512, 128, 3, 2, 5>::cfg(),  // e: budgeted + seed
+    MmaInst2<32, 1, 4, 256, 128, 3, 2, 5>::cfg(),  // f: budgeted + seed, KG = 4, 16 warps / SM
+    MmaInst2<32, 1, 2, 512, 128, 3, 2, 8>::cfg(),  // g: near terms parked in a lane-private local-memory buffer
+    MmaInst2<32, 1, 2, 512, 128, 3, 2, 9>::cfg(),  // h: g + seed
+};
+#endif  // TPE_LAB
 // Measured at config 2 (profiles/r1_variants.md): 32 warps/SM with two kernel groups in flight per
 // warp is the best of the tilings tried (1.17 ms); two candidate groups per warp (M = 2) halve the
 // CTA count and lose.
@@ -254,22 +318,27 @@ const FastCfg kMmaSmall[] = {
     MmaInst<8, 1, 4, 64, 512, 3, 4>::cfg(), MmaInst<16, 1, 4, 64, 256, 3, 4>::cfg(),
     MmaInst<32, 1, 4, 64, 128, 3, 4>::cfg(), MmaInst<64, 1, 2, 64, 64, 3, 3>::cfg(),
 };
+#ifdef TPE_LAB
 const FastCfg kMma32Variants[] = {
     MmaInst<32, 1, 4, 256, 128, 3, 2>::cfg(), MmaInst<32, 1, 2, 256, 128, 3, 2>::cfg(),
     MmaInst<32, 1, 1, 512, 128, 3, 2>::cfg(), MmaInst<32, 1, 2, 256, 128, 2, 3>::cfg(),
     MmaInst<32, 1, 2, 512, 128, 3, 2>::cfg(), MmaInst<32, 1, 2, 512, 128, 3, 2, 1>::cfg(),
     MmaInst<32, 1, 2, 512, 128, 3, 2, 2>::cfg(), MmaInst<32, 1, 4, 256, 128, 3, 2, 1>::cfg(),
 };
-
-
-
+#endif  // TPE_LAB
 
 const FastCfg* pick_mma(int pb, int64_t Ct) {
   const bool small = Ct <= 64;
+#ifdef TPE_LAB
   if (pb == 32 && !small) {
     const char* v = getenv("TPE_MMA_VARIANT");
     if (v && v[0] >= '0' && v[0] <= '7') return &kMma32Variants[v[0] - '0'];
+    if (v && v[0] == '8') return &kMma32V2[0];
+    if (v && v[0] == '9') return &kMma32V2[1];
+    if (v && v[0] >= 'a' && v[0] <= 'h') return &kMma32V2[2 + (v[0] - 'a')];
+    if (v && v[0] >= 'i' && v[0] <= 'k') return &kMma32V3[v[0] - 'i'];
   }
+#endif
   const FastCfg* tabs = small ? kMmaSmall : kMmaBig;
   for (int i = 0; i < 4; ++i)
     if (tabs[i].pb == pb) return &tabs[i];
@@ -307,6 +376,7 @@ const FastCfg kPairSmall[] = {
     FastInst<16, 1, 1, 32, 32, 2, true, 1>::cfg(), FastInst<32, 1, 1, 32, 16, 2, true, 1>::cfg(),
     FastInst<64, 1, 1, 32, 8, 2, true, 1>::cfg(),
 };
+#ifdef TPE_LAB
 // tuning variants of the P = 32 CONST kernel, selectable with TPE_FAST_VARIANT=0..3 (experiments)
 const FastCfg kConst32Variants[] = {
     FastInst<32, 1, 1, 256, 128, 3, false, 2>::cfg(),  // 0: 1 candidate / lane, 16 warps / SM
@@ -320,6 +390,7 @@ const FastCfg kConst32Variants[] = {
     FastInst<32, 1, 1, 256, 128, 2, false, 2>::cfg(),  // 8: 2 stages
     FastInst<32, 1, 1, 512, 128, 3, false, 1>::cfg(),  // 9: 1 CTA x 16 warps
 };
+#endif  // TPE_LAB
 constexpr int kMaxFastP = 64;
 
 int pick_pb(int ncont) {
@@ -329,10 +400,12 @@ int pick_pb(int ncont) {
 }
 const FastCfg* pick_fast(int mode, int pb, int64_t Ct) {
   const bool small = Ct <= 128;
+#ifdef TPE_LAB
   if (mode == 2 && pb == 32 && !small) {
     const char* v = getenv("TPE_FAST_VARIANT");
     if (v && v[0] >= '0' && v[0] <= '9') return &kConst32Variants[v[0] - '0'];
   }
+#endif
   const FastCfg* tabs = (mode == 2) ? (small ? kConstSmall : kConstBig) : (small ? kPairSmall : kPairBig);
   for (int i = 0; i < 7; ++i)
     if (tabs[i].pb == pb) return &tabs[i];
@@ -889,6 +962,7 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
       nsplit = (ktiles + tiles_per - 1) / tiles_per;
       kps = tiles_per * fc->tk;
     }
+#ifdef TPE_LAB
     // fp32-screened variant (tpe_screen.cuh): multivariate, 17..32 continuous columns, many candidates
     // Experimental and OFF by default: correct (same parity tests) but 2.62 ms vs 2.40 ms for the exact
     // kernel at config 2 -- see profiles/r1_variants.md.  TPE_SCREEN=1 enables it.
@@ -940,6 +1014,9 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
       nsplit = sns;
       ctx->last_kernel = "k_logpdf_screen<fp32 screen + fp64 exact>";
     }
+#else
+    constexpr bool use_screen = false;
+#endif
     if (!use_screen) CU(e.part.ensure((size_t)(nsplit + 1) * ctx->ct_stride * 16));
     if (nsplit > 0 && !use_screen) {
       if (!ctx->prepared_cfgs.count(fc)) {
