@@ -31,7 +31,7 @@ extern "C" {
  *      tpe_get_uniforms, tpe_host_alloc / tpe_host_free; tpe_sample_and_select accepts uniforms == NULL
  *      after tpe_stage_uniforms_mt19937 */
 /* 3: + TPE_CAT_EXCLUDED; tpe_history_update may extend the history; tpe_sample_and_select accepts out_x == NULL
- *      (results stay on the device: tpe_result_device_ptrs); tpe_rng_state_device */
+ *      (results stay on the device: tpe_result_device_ptrs); tpe_rng_state_device; tpe_suggest_univariate_batch */
 #define TPE_ABI_VERSION 3
 
 enum {
@@ -162,6 +162,19 @@ int tpe_result_device_ptrs(tpe_ctx* ctx, double** out_x, double** out_acq, int64
 int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
                 const double* w_below, const double* w_above, const double* uniforms,
                 int64_t n_asks, double* out_x, double* out_acq, int64_t* out_best);
+
+/* Univariate TPE (multivariate = 0, the reference's default): the n_cols sample_independent calls of ONE trial
+ * (sampler.py:458-491, one TPESampler._sample per parameter) evaluated together.  Column cols[j] gets its own pair
+ * of 1-D estimators (the split is shared: it does not depend on the parameter), its own C candidates from
+ * uniforms[j * 2C, (j + 1) * 2C) -- C for rng.choice, then C for the value, the order a sequence of per-parameter
+ * calls consumes the generator -- and its own argmax; the columns run concurrently on the device.
+ * uniforms == NULL: the n_cols * 2C uniforms staged by tpe_stage_uniforms_mt19937.
+ * TPE_E_STATE ("not batchable") when the columns cannot share a split (a parameter absent from some trials) or the
+ * history is multi-objective: the caller then makes the per-parameter calls.
+ *   out_x [n_cols] chosen value per column (internal representation); out_acq, out_best [n_cols] may be NULL. */
+int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
+                                 const double* w_below, const double* w_above, const double* uniforms,
+                                 double* out_x, double* out_acq, int64_t* out_best);
 
 /* Optional: start the upload of the uniforms of the NEXT tpe_sample_and_select early (e.g. right
  * after tpe_prepare, so that the copy overlaps tpe_build).  `count` doubles are copied from

@@ -58,6 +58,7 @@ SYMBOLS = {
     "tpe_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),
     "tpe_host_free": (C.c_int, [_P, _P]),
     "tpe_suggest": (C.c_int, [_P, C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P]),
+    "tpe_suggest_univariate_batch": (C.c_int, [_P, C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "tpe_get_split_info": (C.c_int, [_P, C.POINTER(SplitInfo)]),
     "tpe_get_split": (C.c_int, [_P, _P, _P]),
     "tpe_get_mixture": (C.c_int, [_P, C.c_int, _P, _P, _P]),

@@ -34,7 +34,15 @@ namespace {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool owned = true;   // false: a view of another context's buffer (batched univariate sub-contexts)
+  void alias(void* q, size_t bytes) {
+    if (owned && p) cudaFree(p);
+    p = q;
+    cap = bytes;
+    owned = false;
+  }
   cudaError_t ensure(size_t bytes) {
+    if (!owned) { p = nullptr; cap = 0; owned = true; }
     if (bytes <= cap) return cudaSuccess;
     size_t want = std::max(bytes, cap + cap / 2);
     want = (want + 255) & ~(size_t)255;
@@ -63,9 +71,10 @@ struct DevBuf {
   template <class T>
   T* as() const { return reinterpret_cast<T*>(p); }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     cap = 0;
+    owned = true;
   }
 };
 
@@ -167,6 +176,12 @@ struct tpe_ctx {
   const char* last_kernel = "none";
   int32_t launch_counter = 0;
   std::set<const void*> prepared_cfgs;
+  // batched univariate suggestions (tpe_suggest_univariate_batch): one light sub-context per column -- own streams,
+  // own estimator / candidate buffers, views of this context's history and split
+  std::vector<tpe_ctx*> uni_sub;
+  cudaEvent_t ev_uni = nullptr;
+  bool is_sub = false;
+  int sort_cta_cap = 0;          // sub-contexts: CTAs of a cooperative sort (several sorts share the GPU)
 };
 
 namespace {
@@ -801,7 +816,8 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
         int32_t* ib = ia + K;
         SortWork* wk = ctx->sort_work.as<SortWork>();
         void* args[] = {&d_mu, &pc_i, &j_i, &n_i, &ka, &kb, &ia, &ib, &wk, &order};
-        const int G = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(ctx->sm_count, 160), (K + 1023) / 1024));
+        int G = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(ctx->sm_count, 160), (K + 1023) / 1024));
+        if (ctx->sort_cta_cap > 0) G = std::min(G, ctx->sort_cta_cap);
         CU(cudaLaunchCooperativeKernel((const void*)k_radix_sort_coop, dim3(G), dim3(512), args, 0, st));
         ctx->launch_counter++;
       }
@@ -1145,6 +1161,8 @@ int tpe_ctx_create(int device, tpe_ctx** out) {
 
 void tpe_ctx_destroy(tpe_ctx* ctx) {
   if (!ctx) return;
+  for (tpe_ctx* c : ctx->uni_sub) tpe_ctx_destroy(c);
+  ctx->uni_sub.clear();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
@@ -1165,6 +1183,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_u) cudaEventDestroy(ctx->ev_u);
   if (ctx->ev_spec) cudaEventDestroy(ctx->ev_spec);
+  if (ctx->ev_uni) cudaEventDestroy(ctx->ev_uni);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
   cudaStreamDestroy(ctx->stream);
@@ -1342,18 +1361,9 @@ int tpe_history_device_ptrs(tpe_ctx* ctx, double** dX, int8_t** dcategory, doubl
   return TPE_OK;
 }
 
-static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
-                          tpe_split_info* info) {
-  if (!ctx->history_set) return fail(ctx, TPE_E_STATE, "tpe_history_set must precede tpe_prepare");
-  if (!cfg || !cols || n_cols <= 0) return fail(ctx, TPE_E_INVALID, "bad prepare arguments");
-  if (cfg->prior_weight < 0)
-    return fail(ctx, TPE_E_INVALID, "A non-negative value must be specified for prior_weight, but got %g.",
-                cfg->prior_weight);
-  if (cfg->n_candidates <= 0) return fail(ctx, TPE_E_INVALID, "n_candidates must be positive");
-  if (set_device(ctx)) return TPE_E_CUDA;
-  ctx->cfg = *cfg;
-  ctx->launch_counter = 0;
-  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+// The selected columns of a call: kinds, kernel-space bounds, table offsets, which grid kernel family applies;
+// uploads the ColMeta array.  Returns (through need_rowok) whether any selected column has absent values.
+static int setup_columns(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols, bool* need_rowok_out) {
   const int P = (int)ctx->space.size();
   ctx->cols_h.clear();
   ctx->ncont = ctx->ndisc = ctx->ncat = ctx->nnum = 0;
@@ -1418,6 +1428,25 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
   CU(ctx->cols.ensure(sizeof(ColMeta) * n_cols));
   CU(cudaMemcpyAsync(ctx->cols.p, ctx->cols_h.data(), sizeof(ColMeta) * n_cols, cudaMemcpyHostToDevice, ctx->stream));
 
+  *need_rowok_out = need_rowok;
+  return TPE_OK;
+}
+
+static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
+                          tpe_split_info* info) {
+  if (!ctx->history_set) return fail(ctx, TPE_E_STATE, "tpe_history_set must precede tpe_prepare");
+  if (!cfg || !cols || n_cols <= 0) return fail(ctx, TPE_E_INVALID, "bad prepare arguments");
+  if (cfg->prior_weight < 0)
+    return fail(ctx, TPE_E_INVALID, "A non-negative value must be specified for prior_weight, but got %g.",
+                cfg->prior_weight);
+  if (cfg->n_candidates <= 0) return fail(ctx, TPE_E_INVALID, "n_candidates must be positive");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  ctx->cfg = *cfg;
+  ctx->launch_counter = 0;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  bool need_rowok = false;
+  if (int rc0 = setup_columns(ctx, cfg, cols, n_cols, &need_rowok)) return rc0;
+  const int P = (int)ctx->space.size();
   const int64_t N = ctx->N;
   const int64_t nal = std::max<int64_t>(N, 1);
   CU(ctx->counts.ensure(64));
@@ -1568,6 +1597,57 @@ int tpe_build(tpe_ctx* ctx, const double* w_below, const double* w_above) {
   return build_locked(ctx, w_below, w_above);
 }
 
+// Candidates, both log-density grids and the argmax of n_asks asks whose uniforms are resident in ctx->U: launches
+// only (ctx->stream); results in ctx->out_x / out_acq / out_best.
+static int launch_sample_select(tpe_ctx* ctx, int64_t n_asks, bool used_dev_rng, bool timed) {
+  cudaStream_t st = ctx->stream;
+  const int32_t C = ctx->cfg.n_candidates;
+  const int64_t Ct = n_asks * C;
+  const int64_t per_ask = (int64_t)C * (1 + ctx->ncat + ctx->nnum);
+  int rc = TPE_OK;
+  (void)per_ask;
+  if (timed) CU(cudaEventRecord(ctx->ev[3], st));
+  Estimator& eb = ctx->est[0];
+  k_sample<<<grid_for(Ct * ctx->pc, 128, ctx->sm_count * 16), 128, 0, st>>>(
+      ctx->U.as<double>(), n_asks, C, ctx->cols.as<ColMeta>(), ctx->pc, ctx->ncat, ctx->nnum, eb.cdf.as<double>(),
+      eb.K, eb.mu.as<double>(), eb.sigma.as<double>(), eb.tab.as<double>(), ctx->S.as<double>(),
+      ctx->fast ? ctx->xT.as<double>() : nullptr, ctx->ct_stride, ctx->oob.as<uint8_t>());
+  ctx->launch_counter++;
+  if (timed) CU(cudaEventRecord(ctx->ev[4], st));
+  if (used_dev_rng) {
+    // speculative draw for the next ask (same count) from the state this ask's draw ended in; runs on
+    // the side stream while the grid kernels of this ask run
+    static const bool spec_on = [] { const char* v = getenv("TPE_RNG_SPECULATE"); return !(v && v[0] == '0'); }();
+    const int64_t count = n_asks * per_ask;
+    if (spec_on) {
+      CU(ctx->U2.ensure((size_t)count * 8));
+      CU(ctx->mt_spec.ensure(625 * 4));
+      CU(cudaMemcpyAsync(ctx->mt_spec.p, ctx->mt_state.p, 625 * 4, cudaMemcpyDeviceToDevice, ctx->stream3));
+      if (int rc2 = launch_mt(ctx, ctx->stream3, ctx->mt_spec.as<uint32_t>(), 0, count, ctx->U2.as<double>())) return rc2;
+      CU(cudaEventRecord(ctx->ev_spec, ctx->stream3));
+      ctx->spec_pending = true;
+      ctx->spec_count = count;
+    }
+    // the generator's end state comes back with the results (tpe_rng_state then needs no device access)
+    CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, st));
+  }
+  rc = run_logpdf(ctx, 0, Ct);
+  if (rc) return rc;
+  if (timed) CU(cudaEventRecord(ctx->ev[5], st));
+  rc = run_logpdf(ctx, 1, Ct, timed ? ctx->ev[6] : nullptr);
+  if (rc) return rc;
+  if (timed) CU(cudaEventRecord(ctx->ev[7], st));
+  k_acq<<<grid_for(Ct * 32, 256, ctx->sm_count * 8), 256, 0, st>>>(
+      ctx->est[0].part.as<double2>(), ctx->est[0].nsplit, ctx->est[1].part.as<double2>(), ctx->est[1].nsplit,
+      ctx->ct_stride, ctx->fast ? ctx->oob.as<uint8_t>() : nullptr, ctx->est[0].fix.as<double2>(),
+      ctx->est[1].fix.as<double2>(), Ct, ctx->logl.as<double>(), ctx->logg.as<double>());
+  k_select<<<(unsigned)n_asks, 256, 0, st>>>(ctx->logl.as<double>(), ctx->logg.as<double>(), C, ctx->S.as<double>(),
+                                             ctx->pc, ctx->out_x.as<double>(), ctx->out_acq.as<double>(),
+                                             ctx->out_best.as<int64_t>());
+  ctx->launch_counter += 2;
+  return TPE_OK;
+}
+
 static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x, double* out_acq,
                                 int64_t* out_best) {
   if (!ctx->built) return fail(ctx, TPE_E_STATE, "tpe_build must precede tpe_sample_and_select");
@@ -1604,45 +1684,8 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   ctx->u_staged = nullptr;
   const int base_launches = ctx->launch_counter;
 
-  CU(cudaEventRecord(ctx->ev[3], st));
-  Estimator& eb = ctx->est[0];
-  k_sample<<<grid_for(Ct * ctx->pc, 128, ctx->sm_count * 16), 128, 0, st>>>(
-      ctx->U.as<double>(), n_asks, C, ctx->cols.as<ColMeta>(), ctx->pc, ctx->ncat, ctx->nnum, eb.cdf.as<double>(),
-      eb.K, eb.mu.as<double>(), eb.sigma.as<double>(), eb.tab.as<double>(), ctx->S.as<double>(),
-      ctx->fast ? ctx->xT.as<double>() : nullptr, ctx->ct_stride, ctx->oob.as<uint8_t>());
-  ctx->launch_counter++;
-  CU(cudaEventRecord(ctx->ev[4], st));
-  if (used_dev_rng) {
-    // speculative draw for the next ask (same count) from the state this ask's draw ended in; runs on
-    // the side stream while the grid kernels of this ask run
-    static const bool spec_on = [] { const char* v = getenv("TPE_RNG_SPECULATE"); return !(v && v[0] == '0'); }();
-    const int64_t count = n_asks * per_ask;
-    if (spec_on) {
-      CU(ctx->U2.ensure((size_t)count * 8));
-      CU(ctx->mt_spec.ensure(625 * 4));
-      CU(cudaMemcpyAsync(ctx->mt_spec.p, ctx->mt_state.p, 625 * 4, cudaMemcpyDeviceToDevice, ctx->stream3));
-      if (int rc2 = launch_mt(ctx, ctx->stream3, ctx->mt_spec.as<uint32_t>(), 0, count, ctx->U2.as<double>())) return rc2;
-      CU(cudaEventRecord(ctx->ev_spec, ctx->stream3));
-      ctx->spec_pending = true;
-      ctx->spec_count = count;
-    }
-    // the generator's end state comes back with the results (tpe_rng_state then needs no device access)
-    CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, st));
-  }
-  rc = run_logpdf(ctx, 0, Ct);
+  rc = launch_sample_select(ctx, n_asks, used_dev_rng, true);
   if (rc) return rc;
-  CU(cudaEventRecord(ctx->ev[5], st));
-  rc = run_logpdf(ctx, 1, Ct, ctx->ev[6]);
-  if (rc) return rc;
-  CU(cudaEventRecord(ctx->ev[7], st));
-  k_acq<<<grid_for(Ct * 32, 256, ctx->sm_count * 8), 256, 0, st>>>(
-      ctx->est[0].part.as<double2>(), ctx->est[0].nsplit, ctx->est[1].part.as<double2>(), ctx->est[1].nsplit,
-      ctx->ct_stride, ctx->fast ? ctx->oob.as<uint8_t>() : nullptr, ctx->est[0].fix.as<double2>(),
-      ctx->est[1].fix.as<double2>(), Ct, ctx->logl.as<double>(), ctx->logg.as<double>());
-  k_select<<<(unsigned)n_asks, 256, 0, st>>>(ctx->logl.as<double>(), ctx->logg.as<double>(), C, ctx->S.as<double>(),
-                                             ctx->pc, ctx->out_x.as<double>(), ctx->out_acq.as<double>(),
-                                             ctx->out_best.as<int64_t>());
-  ctx->launch_counter += 2;
   CU(cudaEventRecord(ctx->ev[8], st));
   CU(cudaGetLastError());
   if (out_x) CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_asks * ctx->pc * 8, cudaMemcpyDeviceToHost, st));
@@ -1807,6 +1850,146 @@ int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n
     ctx->u_staged = nullptr;
   }
   return rc;
+}
+
+// ---- the P sample_independent calls of one univariate trial, in one go -------------------------------------------
+static tpe_ctx* make_sub(tpe_ctx* parent) {
+  tpe_ctx* c = new tpe_ctx();
+  c->device = parent->device;
+  c->is_sub = true;
+  c->sm_count = parent->sm_count;
+  c->sort_cta_cap = std::max(8, parent->sm_count / 8);   // ~8 column sorts share the GPU at a time
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return nullptr;
+  }
+  for (auto& e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_u, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_spec, cudaEventDisableTiming);
+  return c;
+}
+
+int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
+                                 const double* w_below, const double* w_above, const double* uniforms, double* out_x,
+                                 double* out_acq, int64_t* out_best) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!cfg || !cols || n_cols <= 0 || !out_x) return fail(ctx, TPE_E_INVALID, "bad arguments");
+  if (cfg->multivariate) return fail(ctx, TPE_E_INVALID, "tpe_suggest_univariate_batch is for multivariate = 0");
+  if (ctx->M >= 2) return fail(ctx, TPE_E_STATE, "not batchable: multi-objective history (use the per-parameter calls)");
+  if (set_device(ctx)) return TPE_E_CUDA;
+  const int32_t C = cfg->n_candidates;
+  const int64_t per_col = 2ll * C, count = per_col * n_cols;
+  // uniforms: uploaded on the side stream now, or already generated there by tpe_stage_uniforms_mt19937
+  const bool dev_rng = uniforms == nullptr;
+  if (dev_rng) {
+    if (!ctx->u_device_rng || ctx->u_staged_count != count)
+      return fail(ctx, TPE_E_INVALID, "device-generated uniforms: %lld staged, %lld needed", (long long)ctx->u_staged_count,
+                  (long long)count);
+  } else {
+    if (ctx->u_device_rng) CU(cudaStreamSynchronize(ctx->stream3));
+    CU(ctx->U.ensure((size_t)count * 8));
+    CU(cudaMemcpyAsync(ctx->U.p, uniforms, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream3));
+    CU(cudaEventRecord(ctx->ev_u, ctx->stream3));
+  }
+  ctx->u_device_rng = false;
+  ctx->u_staged = nullptr;
+  // one split for every column (sampler.py:686-722 does not look at the parameters)
+  int rc = prepare_locked(ctx, cfg, cols, n_cols, nullptr);
+  if (rc) return rc;
+  for (const ColMeta& cm : ctx->cols_h)
+    if (ctx->col_missing[cm.src])
+      return fail(ctx, TPE_E_STATE, "not batchable: a selected parameter is absent from some trials (their estimators use "
+                  "different trials; use the per-parameter calls)");
+  for (int which = 0; which < 2; ++which) {   // _call_weights_func checks (parzen_estimator.py:88-109), once
+    const double* w = which == 0 ? w_below : w_above;
+    const int64_t n = ctx->est[which].n;
+    if (!w) continue;
+    double tot = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      if (w[i] < 0) return fail(ctx, TPE_E_INVALID, "The `weights` function is not allowed to return negative values.");
+      if (!isfinite(w[i])) return fail(ctx, TPE_E_INVALID, "The `weights`function is not allowed to return infinite or NaN values.");
+      tot += w[i];
+    }
+    if (n > 0 && tot <= 0) return fail(ctx, TPE_E_INVALID, "The `weight` function is not allowed to return all-zero values.");
+  }
+  if (!ctx->ev_uni) CU(cudaEventCreateWithFlags(&ctx->ev_uni, cudaEventDisableTiming));
+  CU(cudaEventRecord(ctx->ev_uni, ctx->stream));
+  CU(ctx->out_x.ensure((size_t)n_cols * 8));
+  CU(ctx->out_acq.ensure((size_t)n_cols * 8));
+  CU(ctx->out_best.ensure((size_t)n_cols * 8));
+  while ((int)ctx->uni_sub.size() < n_cols) {
+    tpe_ctx* c = make_sub(ctx);
+    if (!c) return fail(ctx, TPE_E_CUDA, "could not create the streams of a column context");
+    ctx->uni_sub.push_back(c);
+  }
+  int launches = ctx->launch_counter;
+  for (int j = 0; j < n_cols; ++j) {
+    tpe_ctx* sub = ctx->uni_sub[j];
+    sub->space = ctx->space;
+    sub->cat_dist_off = ctx->cat_dist_off;
+    sub->cat_dist.alias(ctx->cat_dist.p, ctx->cat_dist.cap);
+    sub->col_missing = ctx->col_missing;
+    sub->col_oor = ctx->col_oor;
+    sub->X.alias(ctx->X.p, ctx->X.cap);
+    sub->cat.alias(ctx->cat.p, ctx->cat.cap);
+    sub->key.alias(ctx->key.p, ctx->key.cap);
+    sub->N = ctx->N;
+    sub->M = 1;
+    sub->history_set = true;
+    sub->cfg = *cfg;
+    sub->launch_counter = 0;
+    bool rowok_unused = false;
+    rc = setup_columns(sub, cfg, cols + j, 1, &rowok_unused);
+    if (rc) { ctx->err = sub->err; return rc; }
+    for (int which = 0; which < 2; ++which) {
+      sub->est[which].rows.alias(ctx->est[which].rows.p, ctx->est[which].rows.cap);
+      sub->est[which].n = ctx->est[which].n;
+    }
+    sub->est[0].pos.alias(ctx->est[0].pos.p, ctx->est[0].pos.cap);
+    sub->info = ctx->info;
+    sub->prepared = true;
+    CU(cudaStreamWaitEvent(sub->stream, ctx->ev_uni, 0));
+    for (int which = 0; which < 2; ++which) {
+      rc = build_estimator(sub, which, which == 0 ? w_below : w_above, sub->stream);
+      if (rc) { ctx->err = sub->err; return rc; }
+    }
+    sub->built = true;
+    sub->U.alias(ctx->U.as<double>() + (size_t)j * per_col, (size_t)per_col * 8);
+    CU(cudaStreamWaitEvent(sub->stream, ctx->ev_u, 0));
+    sub->n_asks = 1;
+    rc = ensure_candidate_buffers(sub, C);
+    if (!rc) {
+      cudaError_t e1 = sub->out_x.ensure(8), e2 = sub->out_acq.ensure(8), e3 = sub->out_best.ensure(8);
+      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = fail(ctx, TPE_E_NOMEM, "out of device memory");
+    }
+    if (!rc) rc = launch_sample_select(sub, 1, false, false);
+    if (rc) { if (ctx->err.empty()) ctx->err = sub->err; return rc; }
+    CU(cudaMemcpyAsync(ctx->out_x.as<double>() + j, sub->out_x.p, 8, cudaMemcpyDeviceToDevice, sub->stream));
+    CU(cudaMemcpyAsync(ctx->out_acq.as<double>() + j, sub->out_acq.p, 8, cudaMemcpyDeviceToDevice, sub->stream));
+    CU(cudaMemcpyAsync(ctx->out_best.as<int64_t>() + j, sub->out_best.p, 8, cudaMemcpyDeviceToDevice, sub->stream));
+    CU(cudaEventRecord(sub->ev_join, sub->stream));
+    CU(cudaStreamWaitEvent(ctx->stream, sub->ev_join, 0));
+    launches += sub->launch_counter;
+  }
+  if (dev_rng) CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[8], ctx->stream));
+  CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_best) CU(cudaMemcpyAsync(out_best, ctx->out_best.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (dev_rng) ctx->mt_host_valid = true;
+  ctx->spec_pending = false;
+  for (int i = 0; i < 9; ++i) ctx->ms[i] = 0.0f;
+  cudaEventElapsedTime(&ctx->ms[8], ctx->ev[0], ctx->ev[8]);
+  ctx->launches = launches;
+  ctx->last_kernel = ctx->uni_sub[0]->last_kernel;
+  ctx->prepared = ctx->built = ctx->sampled = false;   // the per-column state lives in the column contexts
+  return TPE_OK;
 }
 
 int tpe_get_split_info(tpe_ctx* ctx, tpe_split_info* info) {

@@ -265,6 +265,25 @@ class TPEEngine:
         self._info = self.split_info()
         return x, acq, best
 
+    def suggest_univariate_batch(self, cols: Sequence[int], uniforms, w_below=None, w_above=None, **cfg):
+        """The per-parameter suggestions of one univariate trial together (tpe_suggest_univariate_batch);
+        uniforms=None consumes the device-generated uniforms of ``stage_rng(.., len(cols) * 2 * C)``.
+        Raises RuntimeError("... not batchable ...") when the columns cannot share a split."""
+        c = self._make_cfg(**cfg)
+        cols_a = np.ascontiguousarray([int(v) for v in cols], dtype=np.int32)
+        u = None
+        if uniforms is not None:
+            u = _f64(uniforms).reshape(-1)
+            assert u.size == len(cols_a) * 2 * c.n_candidates
+        wb = None if w_below is None else _f64(w_below)
+        wa = None if w_above is None else _f64(w_above)
+        x = np.empty(len(cols_a), dtype=np.float64)
+        acq = np.empty(len(cols_a), dtype=np.float64)
+        best = np.empty(len(cols_a), dtype=np.int64)
+        self._check(self._lib.tpe_suggest_univariate_batch(self._h, C.byref(c), _ptr(cols_a), len(cols_a), _ptr(wb),
+                                                           _ptr(wa), _ptr(u), _ptr(x), _ptr(acq), _ptr(best)))
+        return x, acq, best
+
     def split_info(self) -> tuple[int, int, int]:
         info = _lib.SplitInfo()
         self._check(self._lib.tpe_get_split_info(self._h, C.byref(info)))

@@ -253,9 +253,13 @@ class _DeviceSyncedRng:
     def __init__(self, inner) -> None:
         self._inner = inner
         self._engine = None  # the engine holding a newer state, if any
+        self._settle = None  # a batch of per-parameter draws served only in part: call before anyone looks
 
     @property
     def rng(self) -> np.random.RandomState:
+        settle, self._settle = self._settle, None
+        if settle is not None:
+            settle()
         eng, self._engine = self._engine, None
         if eng is not None:
             eng.finish_rng(self._inner.rng)
@@ -269,10 +273,31 @@ class _DeviceSyncedRng:
 
     def __getstate__(self) -> dict:
         self.rng  # flush
-        return {"_inner": self._inner, "_engine": None}
+        return {"_inner": self._inner, "_engine": None, "_settle": None}
 
     def __setstate__(self, state: dict) -> None:
         self.__dict__.update(state)
+
+
+class _UniPlan:
+    """Univariate TPE asks every parameter of a trial separately (sampler.py:458-491), one `_sample` each; the P
+    calls of a trial see the same history and differ only in the column and in the stretch of the generator they
+    consume.  The plan evaluates all of them at the FIRST call -- in the order the previous trial asked, with the
+    stretches of the stream in that order -- and the following calls are answered from it as long as they arrive
+    exactly as predicted (same name, same distribution, same history, generator untouched).  Anything else settles
+    the generator where the calls served so far would have left it and goes back to one call at a time."""
+
+    def __init__(self) -> None:
+        self.trial = None          # trial number the plan was made for
+        self.order: list = []      # [(name, distribution)] predicted call sequence
+        self.values: list = []     # external representation per call
+        self.next = 0
+        self.version = None        # history version the plan was computed on
+        self.calls_trial = None    # recording of the running trial's actual calls (the next trial's prediction)
+        self.calls: list = []
+        self.prev: list = []       # calls of the last completed recording
+        self.disabled = False      # the engine said "not batchable" for this space
+        self.on_device = None      # the engine whose generator state is the one after the whole batch
 
 
 class B200TPESampler(BaseSampler):
@@ -329,6 +354,7 @@ class B200TPESampler(BaseSampler):
         self._hist = _History()
         self._groups_now: list[dict[str, BaseDistribution]] = []
         self._lock = threading.RLock()
+        self._uni = _UniPlan()
         if multivariate:
             warn_experimental_argument("multivariate")
         if group:
@@ -348,6 +374,7 @@ class B200TPESampler(BaseSampler):
         state["_engine"] = None
         state["_hist"] = _History()
         state["_groups_now"] = []
+        state["_uni"] = _UniPlan()
         del state["_lock"]
         return state
 
@@ -455,7 +482,7 @@ class B200TPESampler(BaseSampler):
                 sampler_name=self.__class__.__name__,
                 fallback_reason="dynamic search space is not supported for `multivariate=True`"))
         with self._lock:
-            return self._sample(study, trial, {param_name: param_distribution})[param_name]
+            return self._sample_one(study, trial, param_name, param_distribution)
 
     def before_trial(self, study, trial) -> None:
         self._random_sampler.before_trial(study, trial)
@@ -684,6 +711,97 @@ class B200TPESampler(BaseSampler):
         else:
             x, _, _ = eng.sample_and_select(self._rng.rng.random_sample(n), n_asks)
         return x
+
+    #: per-parameter asks of a univariate trial are evaluated together from this many parameters on
+    UNI_BATCH_MIN = 2
+
+    def _sample_one(self, study, trial, name: str, dist: BaseDistribution) -> Any:
+        """One `sample_independent` past the startup trials.  The caller holds the lock and has polled."""
+        u = self._uni
+        h = self._hist
+        if u.calls_trial != trial.number:            # a new trial: the finished recording becomes the prediction
+            if u.calls_trial is not None:
+                u.prev = u.calls
+            u.calls_trial, u.calls = trial.number, []
+        u.calls.append((name, dist))
+        version = (id(h.storage), h.token, h.n_finished, len(h.pending) if self._constant_liar else 0)
+        if u.trial == trial.number and u.next < len(u.order):
+            if u.order[u.next] == (name, dist) and u.version == version and not self._finished_backlog():
+                value = u.values[u.next]
+                u.next += 1
+                if u.next == len(u.order):           # served completely: the generator is where the batch left it
+                    self._rng._settle = None
+                    if u.on_device is not None:
+                        self._rng.mark_device(u.on_device)
+                return value
+            self._rng.rng                            # not as predicted: settle the generator, then one at a time
+            u.trial = None
+        can_batch = (not u.disabled and not self._constant_liar and not study._is_multi_objective()
+                     and len(u.prev) >= self.UNI_BATCH_MIN and u.prev[0] == (name, dist) and len(u.calls) == 1
+                     and len({n for n, _ in u.prev}) == len(u.prev))
+        if can_batch:
+            try:
+                self._plan_trial(study, trial, version)
+            except RuntimeError as e:
+                if "not batchable" not in str(e):
+                    raise
+                u.disabled, u.trial = True, None
+            else:
+                u.next = 1
+                if len(u.order) == 1:
+                    self._rng._settle = None
+                return u.values[0]
+        return self._sample(study, trial, {name: dist})[name]
+
+    def _finished_backlog(self) -> bool:
+        """Did a trial other than the running ones change since the plan was made?"""
+        h = self._hist
+        return any(r not in h.pending for r in h.backlog)
+
+    def _plan_trial(self, study, trial, version) -> None:
+        """Evaluate every parameter of `self._uni.prev` for `trial` in one device call."""
+        u = self._uni
+        order = list(u.prev)
+        space = dict(order)
+        cols = self._sync(study, trial, space)
+        n = self._hist.n_finished
+        cfg = dict(n_below=int(self._gamma(n)), n_candidates=self._n_ei_candidates, multivariate=False,
+                   prior_weight=self._prior_weight, magic_clip=self._magic_clip, endpoints=self._endpoints)
+        if self._prior_weight < 0:
+            raise ValueError("A non-negative value must be specified for prior_weight,"
+                             f" but got {self._prior_weight}.")
+        eng = self._eng()
+        wb = wa = None
+        if self._weights is not default_weights:
+            _, nb, na = eng.prepare(cols[:1], **cfg)   # sizes of the two sets (the split does not depend on the column)
+            wb, wa = _checked_weights(self._weights, nb), _checked_weights(self._weights, na)
+        per = 2 * self._n_ei_candidates
+        count = per * len(order)
+        rng = self._rng.rng                            # host generator, up to date
+        st0 = rng.get_state()
+        try:
+            if count >= self.DEVICE_RNG_MIN:
+                eng.stage_rng(rng, count)              # the host object stays at st0 until the plan is served
+                x, _, _ = eng.suggest_univariate_batch(cols, None, wb, wa, **cfg)
+                u.on_device = eng
+            else:
+                x, _, _ = eng.suggest_univariate_batch(cols, rng.random_sample(count), wb, wa, **cfg)
+                u.on_device = None
+        except Exception:
+            rng.set_state(st0)                         # nothing was served: the generator has not moved
+            raise
+        u.trial, u.order, u.version = trial.number, order, version
+        u.values = [d.to_external_repr(float(v)) for (_, d), v in zip(order, x)]
+        u.next = 0
+
+        def settle() -> None:   # the generator after the calls served so far (and only those)
+            r = self._rng._inner.rng
+            r.set_state(st0)
+            if u.next:
+                r.random_sample(per * u.next)
+            self._rng._engine = None
+            u.trial = None
+        self._rng._settle = settle
 
     def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
         """TPESampler._sample (sampler.py:523-560).  The caller holds the lock and has polled."""

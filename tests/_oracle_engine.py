@@ -170,6 +170,23 @@ class OracleEngine:
     def get_candidates(self):
         return self._last
 
+    def suggest_univariate_batch(self, cols, uniforms, w_below=None, w_above=None, **cfg):
+        """The per-parameter calls of one trial, one after the other (what the batched CUDA entry must equal)."""
+        if self.vals is not None and self.vals.shape[1] >= 2:
+            raise RuntimeError("not batchable: multi-objective history")
+        if np.isnan(self.X[np.isin(self.cat, (0, 1, 2, 3))][:, list(cols)]).any():
+            raise RuntimeError("not batchable: a selected parameter is absent from some trials")
+        u = self._staged if uniforms is None else np.asarray(uniforms, dtype=np.float64).ravel()
+        per = 2 * int(cfg["n_candidates"])
+        x, acq, best = np.empty(len(cols)), np.empty(len(cols)), np.empty(len(cols), dtype=np.int64)
+        self.calls.append(("univariate_batch", len(cols)))
+        for j, c in enumerate(cols):
+            self.prepare([c], **cfg)
+            self.build(w_below, w_above)
+            xj, aj, bj = self.sample_and_select(u[j * per: (j + 1) * per], 1)
+            x[j], acq[j], best[j] = xj[0, 0], aj[0], bj[0]
+        return x, acq, best
+
     def close(self) -> None:
         pass
 

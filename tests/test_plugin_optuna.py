@@ -474,3 +474,44 @@ def test_device_generated_uniforms_give_the_reference_suggestions(make_sampler):
     (got, tail), (want, tail_ref) = run(make_sampler(**kw)), run(make_sampler.reference(**kw))
     np.testing.assert_allclose(got, want, rtol=1e-9, atol=0)
     assert np.array_equal(tail, tail_ref)  # the generator ends in the reference's state
+
+
+def test_univariate_plans_are_used_and_survive_surprises(make_sampler):
+    """Univariate TPE: the per-parameter asks of a trial are evaluated together in the order the previous trial
+    asked (B200TPESampler._plan_trial); the trajectory must stay the reference's when a trial asks in another
+    order, fails half way, or somebody else draws from the sampler's generator in between -- and when parameters
+    are missing from some trials (then the columns cannot share a split and nothing is batched)."""
+    def obj(t, holes=False):
+        n = t.number
+        names = ["a", "b", "c", "d"]
+        if n % 5 == 2:
+            names = ["b", "a", "c", "d"]              # another order
+        if holes and n % 7 == 3:
+            names = names[:2]                          # a trial without c and d
+        vals = {}
+        for i, nm in enumerate(names):
+            vals[nm] = t.suggest_float(nm, -1.0, 1.0) if nm != "d" else t.suggest_float(nm, 1e-3, 1.0, log=True)
+            if n % 6 == 4 and i == 1:
+                t.study.sampler._rng.rng.random_sample(3)   # a foreign draw in the middle of a trial
+            if not holes and n % 7 == 3 and i == 1:
+                raise RuntimeError("fails half way")   # FAIL: the rest of the plan is never asked for
+        if holes and n % 11 == 5:
+            vals["e"] = t.suggest_float("e", 0.0, 2.0)  # a parameter the plan did not expect
+        return sum(v * v for v in vals.values())
+
+    def scenario(holes, n_trials):
+        def run(sampler):
+            s = optuna.create_study(sampler=sampler)
+            s.optimize(lambda t: obj(t, holes), n_trials=n_trials, catch=(RuntimeError,))
+            return s
+        return run
+
+    a, _ = over_seeds(scenario(False, 60), make_sampler, False, dict(seed=17, n_startup_trials=6, n_ei_candidates=16))
+    if make_sampler.kind == "oracle":
+        batches = [c for c in a.sampler._engine.calls if c[0] == "univariate_batch"]
+        assert len(batches) > 25 and max(c[1] for c in batches) == 4
+    a, _ = over_seeds(scenario(True, 60), make_sampler, False, dict(seed=18, n_startup_trials=6, n_ei_candidates=16))
+    if make_sampler.kind == "oracle":
+        assert not [c for c in a.sampler._engine.calls if c[0] == "univariate_batch"] and a.sampler._uni.disabled
+    # large asks: the plan's uniforms come from the device generator (2 * 2048 * 4 >= DEVICE_RNG_MIN)
+    over_seeds(scenario(False, 24), make_sampler, False, dict(seed=3, n_startup_trials=6, n_ei_candidates=2048))
