@@ -793,6 +793,16 @@ class B200TPESampler(BaseSampler):
         u.trial, u.order, u.version = trial.number, order, version
         u.values = [d.to_external_repr(float(v)) for (_, d), v in zip(order, x)]
         u.next = 0
+        if self._audit is not None:
+            # test hook: the candidates / log-densities of every column, re-evaluated one column at a time on the
+            # same stretch of uniforms (the batched entry keeps only the winners)
+            uu = eng.get_uniforms(count) if u.on_device is not None else np.random.RandomState()
+            if u.on_device is None:
+                uu.set_state(st0)
+                uu = uu.random_sample(count)
+            for j, (nm, d) in enumerate(order):
+                eng.suggest(cols[j: j + 1], uu[j * per: (j + 1) * per], 1, wb, wa, **cfg)
+                self._audit(trial, {nm: d}, eng)
 
         def settle() -> None:   # the generator after the calls served so far (and only those)
             r = self._rng._inner.rng

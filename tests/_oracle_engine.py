@@ -170,6 +170,14 @@ class OracleEngine:
     def get_candidates(self):
         return self._last
 
+    def get_uniforms(self, count):
+        return np.asarray(self._staged[:count])
+
+    def suggest(self, cols, uniforms, n_asks=1, w_below=None, w_above=None, **cfg):
+        self.prepare(cols, **cfg)
+        self.build(w_below, w_above)
+        return self.sample_and_select(uniforms, n_asks)
+
     def suggest_univariate_batch(self, cols, uniforms, w_below=None, w_above=None, **cfg):
         """The per-parameter calls of one trial, one after the other (what the batched CUDA entry must equal)."""
         if self.vals is not None and self.vals.shape[1] >= 2:

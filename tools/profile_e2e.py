@@ -1,5 +1,7 @@
-"""cProfile of the end-to-end step of bench.py (optuna's Study -> B200TPESampler) at N = 100k."""
+"""Where the time of an end-to-end step goes (optuna's Study -> B200TPESampler -> libtpe_b200.so) at N = 100k:
+wall time of every engine call, of the sampler's sync, and a cProfile of 20 steps."""
 import cProfile
+import collections
 import os
 import pstats
 import sys
@@ -9,7 +11,21 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 
 optuna = bench.import_optuna()
-from optuna_b200 import B200TPESampler  # noqa: E402
+from optuna_b200 import B200TPESampler, TPEEngine  # noqa: E402
+
+acc = collections.defaultdict(float)
+cnt = collections.Counter()
+for name in ("update_history", "prepare", "build", "stage_rng", "sample_and_select", "set_history", "set_space"):
+    orig = getattr(TPEEngine, name)
+
+    def wrap(self, *a, _o=orig, _n=name, **k):
+        t0 = time.perf_counter()
+        try:
+            return _o(self, *a, **k)
+        finally:
+            acc[_n] += time.perf_counter() - t0
+            cnt[_n] += 1
+    setattr(TPEEngine, name, wrap)
 
 X, loss = bench.synthetic_history()
 s = B200TPESampler(seed=1, n_ei_candidates=bench.N_CAND, multivariate=True)
@@ -24,13 +40,21 @@ def one():
 
 for _ in range(4):
     one()
+acc.clear()
+cnt.clear()
+sync = dev = 0.0
 t0 = time.perf_counter()
-for _ in range(20):
+for _ in range(40):
     one()
-print("per trial ms", (time.perf_counter() - t0) / 20 * 1e3, "last sync/device s", s.last_ask_s)
+    sync += s.last_ask_s[0]
+    dev += s.last_ask_s[1]
+wall = time.perf_counter() - t0
+print("per trial ms %.3f | sampler sync %.3f | device calls %.3f" % (wall / 40 * 1e3, sync / 40 * 1e3, dev / 40 * 1e3))
+for k, v in sorted(acc.items(), key=lambda kv: -kv[1]):
+    print("  engine.%-20s %.3f ms per call x %d" % (k, v / max(cnt[k], 1) * 1e3, cnt[k]))
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(20):
     one()
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(30)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(25)
