@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <mutex>
+#include <thread>
 #include <set>
 #include <string>
 #include <vector>
@@ -18,6 +19,7 @@
 #include "../../include/optuna_b200_tpe.h"
 #include "tpe_kernels.cuh"
 #include "tpe_motpe_kernels.cuh"
+#include "tpe_uni.cuh"
 // Lab build (-DTPE_LAB): the experimental grid kernels and the timing-attribution variants measured in
 // profiles/r1_variants.md / r2_variants.md, selectable by environment variables.  Some of them switch parts of the
 // log-sum-exp off (wrong results by design).  The product library contains none of them.
@@ -84,11 +86,13 @@ struct Estimator {
   DevBuf tab32, tab64p, d32;   // fp32-screening copies (tpe_screen.cuh)
   DevBuf cls, dtab, offgrid;   // tabulated discrete columns (multivariate)
   DevBuf tabm, hb, ckk;        // tensor-core kernel: fragment-major table, |mu''|^2 / 2, cst - |mu''|^2 / 2
+  DevBuf uord, us32, usmi, usc, umeta;  // univariate 1-D grid (tpe_uni.cuh): sorted order and sorted tables
+  bool uni_ready = false;
   bool mma = false;            // tables above are valid for this build
   bool screen_ready = false;
   int nsplit = 0;
   void release() {
-    for (DevBuf* b : {&tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
+    for (DevBuf* b : {&uord, &us32, &usmi, &usc, &umeta, &tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
                       &part, &fix})
       b->release();
   }
@@ -161,6 +165,9 @@ struct tpe_ctx {
   int64_t tab_doubles = 0;
   int64_t dtab_doubles = 0;  // cell-mass tables of tabulated discrete columns
   bool fast = false;
+  bool uni_fast = false;   // one continuous column, univariate: the sorted 1-D grid kernel (tpe_uni.cuh)
+  bool cands_sorted = false;
+  DevBuf uxs, ucidx;
   int fast_mode = 0;  // 0 generic, 1 PAIR (sigma per kernel), 2 CONST (sigma per column)
   tpe_split_info info{};
   DevBuf row_ok, member, counts, split_work, below_all;
@@ -801,6 +808,9 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
       if (m2 <= 4096) {
         k_sort_small<<<1, 1024, 0, st>>>(e.mu.as<double>(), pc, j, (int)K, (int)m2, ctx->sort_idx.as<int32_t>());
         ctx->launch_counter++;
+      } else if (getenv("TPE_DEBUG_SKIP_SORT") && ctx->uni_fast && e.uord.cap >= (size_t)K * 4 && ctx->sort_idx.cap >= (size_t)K * 4) {
+        // timing experiment only: reuse the previous order
+        CU(cudaMemcpyAsync(ctx->sort_idx.p, e.uord.p, (size_t)K * 4, cudaMemcpyDeviceToDevice, st));
       } else {
         // cooperative stable radix sort (one launch instead of ~150 bitonic steps)
         CU(ctx->sort_val.ensure((size_t)K * 8 * 2));
@@ -825,6 +835,10 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
                                                          ctx->cols.as<ColMeta>(), pc, j, n, ctx->cfg.magic_clip,
                                                          ctx->cfg.endpoints, e.sigma.as<double>());
       ctx->launch_counter++;
+      if (ctx->uni_fast) {   // the 1-D grid walks the kernels in this order
+        CU(e.uord.ensure((size_t)K * 4));
+        CU(cudaMemcpyAsync(e.uord.p, ctx->sort_idx.p, (size_t)K * 4, cudaMemcpyDeviceToDevice, st));
+      }
     }
     k_const<<<grid_for(K * 32, 256, cap), 256, 0, st>>>(e.mu.as<double>(), e.sigma.as<double>(),
                                                         ctx->cols.as<ColMeta>(), pc, K, ctx->pb, ctx->fast_mode,
@@ -940,6 +954,19 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
                                     ctx->cat_dist.as<double>(), e.tab.as<double>());
     ctx->launch_counter++;
   }
+  e.uni_ready = false;
+  if (ctx->uni_fast) {
+    const int64_t ntiles = (K + kUniTile - 1) / kUniTile;
+    CU(e.us32.ensure((size_t)ntiles * kUniTile * 16));
+    CU(e.usmi.ensure((size_t)ntiles * kUniTile * 16));
+    CU(e.usc.ensure((size_t)ntiles * kUniTile * 8));
+    CU(e.umeta.ensure((size_t)ntiles * sizeof(UniTileMeta)));
+    k_uni_tables<<<(unsigned)ntiles, kUniTile, 0, st>>>(e.uord.as<int32_t>(), e.mu.as<double>(), e.sigma.as<double>(),
+                                                        e.cst.as<double>(), ctx->cols.as<ColMeta>(), K, e.us32.as<float4>(),
+                                                        e.usmi.as<double2>(), e.usc.as<double>(), e.umeta.as<UniTileMeta>());
+    ctx->launch_counter++;
+    e.uni_ready = true;
+  }
   CU(cudaGetLastError());
   return TPE_OK;
 }
@@ -951,6 +978,35 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
   cudaStream_t st = ctx->stream;
   if (which == 1 && join_above(ctx)) return TPE_E_CUDA;
   const int64_t K = e.K;
+  if (ctx->uni_fast && e.uni_ready && Ct <= 4096) {
+    // one continuous column, univariate: sorted candidates x sorted kernels (tpe_uni.cuh)
+    const int C = (int)Ct;
+    if (!ctx->cands_sorted) {
+      CU(ctx->uxs.ensure((size_t)round_up<int64_t>(C, 32) * 8));
+      CU(ctx->ucidx.ensure((size_t)round_up<int64_t>(C, 32) * 4));
+      k_uni_sort_cands<<<1, 1024, 0, st>>>(ctx->xT.as<double>(), C, ctx->cols.as<ColMeta>(), ctx->uxs.as<double>(),
+                                           ctx->ucidx.as<int32_t>());
+      ctx->launch_counter++;
+      ctx->cands_sorted = true;
+    }
+    CU(e.part.ensure((size_t)2 * ctx->ct_stride * 16));
+    const double skip = std::min(46.0, log((double)std::max<int64_t>(K, 1)) + 30.0);
+    k_uni_grid<<<(unsigned)((C + 31) / 32), kUniWarps * 32, 0, st>>>(e.us32.as<float4>(), e.usmi.as<double2>(),
+                                                                     e.usc.as<double>(), e.umeta.as<UniTileMeta>(), K,
+                                                                     ctx->uxs.as<double>(), ctx->ucidx.as<int32_t>(), C, skip,
+                                                                     e.part.as<double2>());
+    ctx->launch_counter++;
+    ctx->last_kernel = "k_uni_grid<sorted 1-D>";
+    if (after_main) CU(cudaEventRecord(after_main, st));
+    CU(e.fix.ensure((size_t)ctx->ct_stride * 16));
+    k_logpdf_prior_fix<<<(unsigned)((Ct * 32 + 255) / 256), 256, 0, st>>>(
+        ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
+        e.cst.as<double>(), K, e.tab.as<double>(), nullptr, ctx->oob.as<uint8_t>(), e.fix.as<double2>());
+    ctx->launch_counter++;
+    e.nsplit = 1;
+    CU(cudaGetLastError());
+    return TPE_OK;
+  }
   if (ctx->fast) {
     const bool cst_mode = ctx->fast_mode == 2;
     // tensor-core kernel unless the expanded square would lose more than 5e-13 (see k_logpdf_mma)
@@ -1114,6 +1170,7 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
 
 int ensure_candidate_buffers(tpe_ctx* ctx, int64_t Ct) {
   ctx->Ct = Ct;
+  ctx->cands_sorted = false;
   ctx->ct_stride = round_up<int64_t>(Ct, 1024);
   CU(ctx->S.ensure((size_t)ctx->ct_stride * ctx->pc * 8));
   CU(ctx->oob.ensure((size_t)ctx->ct_stride));
@@ -1172,7 +1229,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed, &ctx->mo_table,
                     &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv, &ctx->mo_fv, &ctx->mo_ps, &ctx->mo_map, &ctx->mo_front, &ctx->mo_head,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
-                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
+                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->uxs, &ctx->ucidx, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->U2, &ctx->mt_spec, &ctx->mt_jump, &ctx->mt_tmp, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
@@ -1425,6 +1482,8 @@ static int setup_columns(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, 
   ctx->fast = (ctx->ndisc == 0 && ctx->ncat == 0 && ctx->ncont <= kMaxFastP);
   ctx->pb = ctx->fast ? pick_pb(ctx->ncont) : 0;
   ctx->fast_mode = ctx->fast ? (cfg->multivariate ? 2 : 1) : 0;
+  static const bool uni_on = [] { const char* v = getenv("TPE_UNI_FAST"); return !(v && v[0] == '0'); }();
+  ctx->uni_fast = uni_on && !cfg->multivariate && n_cols == 1 && ctx->ncont == 1;
   CU(ctx->cols.ensure(sizeof(ColMeta) * n_cols));
   CU(cudaMemcpyAsync(ctx->cols.p, ctx->cols_h.data(), sizeof(ColMeta) * n_cols, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -1928,8 +1987,20 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
     ctx->uni_sub.push_back(c);
   }
   int launches = ctx->launch_counter;
-  for (int j = 0; j < n_cols; ++j) {
+  // Issuing ~20 launches per column is host work (~10 us each through 32 streams): the columns are independent,
+  // so a few host threads issue them side by side.  Each column context is touched by exactly one thread.
+  auto issue_column = [&](int j) -> int {
     tpe_ctx* sub = ctx->uni_sub[j];
+    int rc = TPE_OK;
+    sub->err.clear();
+#define CUS(call)                                                                                            \
+    do {                                                                                                       \
+      cudaError_t e_ = (call);                                                                                 \
+      if (e_ != cudaSuccess)                                                                                   \
+        return fail(sub, e_ == cudaErrorMemoryAllocation ? TPE_E_NOMEM : TPE_E_CUDA, "%s failed: %s (%s:%d)", \
+                    #call, cudaGetErrorString(e_), __FILE__, __LINE__);                                        \
+    } while (0)
+    CUS(cudaSetDevice(ctx->device));
     sub->space = ctx->space;
     sub->cat_dist_off = ctx->cat_dist_off;
     sub->cat_dist.alias(ctx->cat_dist.p, ctx->cat_dist.cap);
@@ -1945,7 +2016,7 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
     sub->launch_counter = 0;
     bool rowok_unused = false;
     rc = setup_columns(sub, cfg, cols + j, 1, &rowok_unused);
-    if (rc) { ctx->err = sub->err; return rc; }
+    if (rc) return rc;
     for (int which = 0; which < 2; ++which) {
       sub->est[which].rows.alias(ctx->est[which].rows.p, ctx->est[which].rows.cap);
       sub->est[which].n = ctx->est[which].n;
@@ -1953,28 +2024,48 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
     sub->est[0].pos.alias(ctx->est[0].pos.p, ctx->est[0].pos.cap);
     sub->info = ctx->info;
     sub->prepared = true;
-    CU(cudaStreamWaitEvent(sub->stream, ctx->ev_uni, 0));
+    CUS(cudaStreamWaitEvent(sub->stream, ctx->ev_uni, 0));
     for (int which = 0; which < 2; ++which) {
       rc = build_estimator(sub, which, which == 0 ? w_below : w_above, sub->stream);
-      if (rc) { ctx->err = sub->err; return rc; }
+      if (rc) return rc;
     }
     sub->built = true;
     sub->U.alias(ctx->U.as<double>() + (size_t)j * per_col, (size_t)per_col * 8);
-    CU(cudaStreamWaitEvent(sub->stream, ctx->ev_u, 0));
+    CUS(cudaStreamWaitEvent(sub->stream, ctx->ev_u, 0));
     sub->n_asks = 1;
     rc = ensure_candidate_buffers(sub, C);
-    if (!rc) {
-      cudaError_t e1 = sub->out_x.ensure(8), e2 = sub->out_acq.ensure(8), e3 = sub->out_best.ensure(8);
-      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = fail(ctx, TPE_E_NOMEM, "out of device memory");
+    if (rc) return rc;
+    CUS(sub->out_x.ensure(8));
+    CUS(sub->out_acq.ensure(8));
+    CUS(sub->out_best.ensure(8));
+    rc = launch_sample_select(sub, 1, false, false);
+    if (rc) return rc;
+    CUS(cudaMemcpyAsync(ctx->out_x.as<double>() + j, sub->out_x.p, 8, cudaMemcpyDeviceToDevice, sub->stream));
+    CUS(cudaMemcpyAsync(ctx->out_acq.as<double>() + j, sub->out_acq.p, 8, cudaMemcpyDeviceToDevice, sub->stream));
+    CUS(cudaMemcpyAsync(ctx->out_best.as<int64_t>() + j, sub->out_best.p, 8, cudaMemcpyDeviceToDevice, sub->stream));
+    CUS(cudaEventRecord(sub->ev_join, sub->stream));
+#undef CUS
+    return TPE_OK;
+  };
+  static const int n_threads_env = [] { const char* v = getenv("TPE_UNI_THREADS"); return v ? atoi(v) : 6; }();
+  const int T = std::max(1, std::min(n_threads_env, (int)n_cols));
+  std::vector<int> rcs((size_t)n_cols, TPE_OK);
+  if (T == 1) {
+    for (int j = 0; j < n_cols; ++j) rcs[(size_t)j] = issue_column(j);
+  } else {
+    std::vector<std::thread> pool;
+    for (int w = 0; w < T; ++w)
+      pool.emplace_back([&, w] { for (int j = w; j < n_cols; j += T) rcs[(size_t)j] = issue_column(j); });
+    for (auto& th : pool) th.join();
+  }
+  for (int j = 0; j < n_cols; ++j) {
+    if (rcs[(size_t)j]) {
+      ctx->err = ctx->uni_sub[(size_t)j]->err;
+      for (int q = 0; q < n_cols; ++q) cudaStreamSynchronize(ctx->uni_sub[(size_t)q]->stream);
+      return rcs[(size_t)j];
     }
-    if (!rc) rc = launch_sample_select(sub, 1, false, false);
-    if (rc) { if (ctx->err.empty()) ctx->err = sub->err; return rc; }
-    CU(cudaMemcpyAsync(ctx->out_x.as<double>() + j, sub->out_x.p, 8, cudaMemcpyDeviceToDevice, sub->stream));
-    CU(cudaMemcpyAsync(ctx->out_acq.as<double>() + j, sub->out_acq.p, 8, cudaMemcpyDeviceToDevice, sub->stream));
-    CU(cudaMemcpyAsync(ctx->out_best.as<int64_t>() + j, sub->out_best.p, 8, cudaMemcpyDeviceToDevice, sub->stream));
-    CU(cudaEventRecord(sub->ev_join, sub->stream));
-    CU(cudaStreamWaitEvent(ctx->stream, sub->ev_join, 0));
-    launches += sub->launch_counter;
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->uni_sub[(size_t)j]->ev_join, 0));
+    launches += ctx->uni_sub[(size_t)j]->launch_counter;
   }
   if (dev_rng) CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev[8], ctx->stream));

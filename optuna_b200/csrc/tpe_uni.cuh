@@ -1,0 +1,297 @@
+// Univariate TPE (multivariate = 0, the reference's default): the 1-D mixture grid.
+//
+// One suggestion per parameter: log l(x) and log g(x) of C candidates under 1-D mixtures of K kernels
+// (probability_distributions.py:154-223 with a single parameter).  At config 2 that is P = 32 grids of
+// 4096 x 100 000 (candidate, kernel) pairs per trial -- as many pairs as the multivariate grid has cells, but now
+// EVERY pair carries its own exponential.  What makes the 1-D case cheap again is that both axes can be sorted:
+// with the kernels ordered by mu (the order the bandwidth computation needs anyway, parzen_estimator.py:196-218)
+// and the candidates ordered by x,
+//   * a warp owns 32 neighbouring candidates; a tile of 128 neighbouring kernels can be dismissed for all of them
+//     with one comparison:  L <= max_tile(cst) - (dist / max_tile(sigma))^2 / 2,  dist = gap between the tile's mu
+//     range and the warp's x range -- an upper bound that is exact arithmetic, no approximation;
+//   * inside the tiles that remain, an fp32 evaluation with a rigorous rounding bound dismisses single pairs, and
+//     the pairs that survive are evaluated in fp64 by lanes that mostly survive TOGETHER (neighbouring x);
+//   * every warp walks ALL tiles itself (no k-split: the running max of a candidate is found in the tile under it,
+//     first), so far tiles are dismissed against the true scale of the sum, not against a slice-local max.
+// The log-sum-exp is the two-tier one of the multivariate kernels: terms within ln K + 17.5 of the running max in
+// fp64 (LseTier::exp_neg), terms down to ln K + 30 below it through MUFU.EX2 in fp32, the rest dropped; same bounds.
+#pragma once
+#include "tpe_kernels.cuh"
+
+namespace tpe {
+
+constexpr int kUniTile = 128;
+
+struct UniTileMeta {
+  double mu_lo, mu_hi;   // range of (mu - ctr) over the tile
+  double smax, cmax;     // largest sigma, largest constant (ln w - ln sqrt(2 pi) - M(a, b) - ln sigma)
+};
+
+// Sorted tables of one estimator column: position j holds kernel order[j].
+//   s32[j] = (m'' = (mu - ctr) / sigma, 1 / sigma, cst, w) in fp32, w = rounding bound of the fp32 z (see k_uni_grid)
+//   smi[j] = (m'', 1 / sigma), sc[j] = cst in fp64 (the PAIR table of k_const / k_logpdf_fast, re-ordered)
+__global__ void __launch_bounds__(kUniTile)
+k_uni_tables(const int32_t* __restrict__ order, const double* __restrict__ mu, const double* __restrict__ sigma,
+             const double* __restrict__ cst, const ColMeta* __restrict__ cols, int64_t K, float4* __restrict__ s32,
+             double2* __restrict__ smi, double* __restrict__ sc, UniTileMeta* __restrict__ meta) {
+  __shared__ double r_lo[4], r_hi[4], r_s[4], r_c[4];
+  const ColMeta cm = cols[0];
+  const double ctr = TPE_MUL(0.5, TPE_ADD(cm.klow, cm.khigh));
+  const double half = 0.5 * (cm.khigh - cm.klow);
+  const int64_t pos = (int64_t)blockIdx.x * kUniTile + threadIdx.x;
+  double lo = INFINITY, hi = -INFINITY, sm = 0.0, cmx = -INFINITY;
+  if (pos < K) {
+    const int64_t k = order[pos];
+    const double m = mu[k], s = sigma[k], c = cst[k];
+    const double inv = TPE_DIV(1.0, s);
+    const double mm = TPE_MUL(TPE_SUB(m, ctr), inv);
+    smi[pos] = make_double2(mm, inv);
+    sc[pos] = c;
+    // |z_fp32 - z| <= 2^-24 (2 |x'| inv + |m''| + |z|) <= 2^-22 Z with Z = (range / 2) inv >= |x' inv|, |m''|
+    const float w = __double2float_ru(half * inv * 2.5e-7);
+    s32[pos] = make_float4(__double2float_rn(mm), __double2float_rn(inv), __double2float_rn(c), w);
+    lo = hi = m - ctr;
+    sm = s;
+    cmx = c;
+  } else {
+    smi[pos] = make_double2(0.0, 0.0);
+    sc[pos] = -INFINITY;
+    s32[pos] = make_float4(0.0f, 0.0f, -INFINITY, 0.0f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    sm = fmax(sm, __shfl_xor_sync(0xffffffffu, sm, o));
+    cmx = fmax(cmx, __shfl_xor_sync(0xffffffffu, cmx, o));
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { r_lo[w] = lo; r_hi[w] = hi; r_s[w] = sm; r_c[w] = cmx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    UniTileMeta t;
+    t.mu_lo = fmin(fmin(r_lo[0], r_lo[1]), fmin(r_lo[2], r_lo[3]));
+    t.mu_hi = fmax(fmax(r_hi[0], r_hi[1]), fmax(r_hi[2], r_hi[3]));
+    t.smax = fmax(fmax(r_s[0], r_s[1]), fmax(r_s[2], r_s[3]));
+    t.cmax = fmax(fmax(r_c[0], r_c[1]), fmax(r_c[2], r_c[3]));
+    meta[blockIdx.x] = t;
+  }
+}
+
+// The candidates of one ask in ascending kernel-space order: xs[i] = x' = x - ctr of the i-th smallest,
+// cidx[i] = its index.  One CTA of 1024 threads, bitonic sort in shared memory (C <= 4096), ties by index.
+__global__ void __launch_bounds__(1024, 1)
+k_uni_sort_cands(const double* __restrict__ xT, int C, const ColMeta* __restrict__ cols, double* __restrict__ xs,
+                 int32_t* __restrict__ cidx) {
+  __shared__ double sv[4096];
+  __shared__ int32_t si[4096];
+  const ColMeta cm = cols[0];
+  const double ctr = TPE_MUL(0.5, TPE_ADD(cm.klow, cm.khigh));
+  int m2 = 32;
+  while (m2 < C) m2 <<= 1;
+  for (int i = threadIdx.x; i < m2; i += 1024) {
+    sv[i] = (i < C) ? xT[i] - ctr : INFINITY;
+    si[i] = (i < C) ? i : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int k = 2; k <= m2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < m2; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const double a = sv[i], b = sv[l];
+          const int ia = si[i], ib = si[l];
+          const bool a_gt_b = (a > b) || (a == b && ia > ib) || (a != a && b == b);
+          const bool up = (i & k) == 0;
+          if (up ? a_gt_b : !a_gt_b) {
+            sv[i] = b; sv[l] = a;
+            si[i] = ib; si[l] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < m2; i += 1024) {
+    if (i < ((C + 31) & ~31)) {
+      xs[i] = (i < C) ? sv[i] : NAN;   // padding lanes of the last warp: never pass a test
+      cidx[i] = (i < C) ? si[i] : -1;
+    }
+  }
+}
+
+// e^x for -700 <= x <= 700 in ~17 instructions: x = (64 n + j) ln2 / 64 + r, |r| <= ln2 / 128;
+// e^x = 2^n * 2^(j/64) * P5(r) with a 64-entry table in shared memory (filled by the CTA: exp2(j / 64), 1 ulp) and a
+// degree-5 Taylor polynomial (truncation 3.5e-17).  The two-term Cody-Waite reduction is exact for |x| < 700
+// (ln2_hi / 64 keeps 21 trailing zero bits).  Relative error <= 3e-16.
+__device__ __forceinline__ double uni_exp(double x, const double* __restrict__ tab64) {
+  const double t = fma(x, 92.332482616893656768, 6755399441055744.0);
+  const int ni = __double2loint(t);
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, -1.08304246932675596327e-02, x);
+  r = fma(nf, -2.98158582698529328128e-12, r);
+  double p = 8.33333333333333333333e-03;
+  p = fma(p, r, 4.16666666666666666667e-02);
+  p = fma(p, r, 1.66666666666666666667e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double y = tab64[ni & 63] * p;
+  return __hiloint2double(__double2hiint(y) + ((ni >> 6) << 20), __double2loint(y));
+}
+
+// part[cidx] = (reference, sum of e^(L - reference)) of the 1-D mixture for every candidate.
+// CTA = 8 warps on the SAME 32 neighbouring candidates (lane = candidate): warp w takes the tiles at distance
+// w, w + 8, ... on either side of the tile under the candidates.  Every lane sums e^(L - ref) against a FIXED
+// reference (its largest term in the tile under it: within a few nats of its true max), so the exponentials of
+// different kernels do not depend on each other: four kernels are evaluated at a time on four accumulators (the
+// fp64 polynomial chains interleave), and the eight partial sums add up in a fixed order.  A term 600 nats above
+// the reference moves it (exact, never seen on real data).  Every term within `skip` of the running max is
+// evaluated in fp64 -- there is no fp32 tier here; pairs and whole tiles that cannot reach that window are
+// dismissed by the two rigorous bounds described at the top of this file.
+constexpr int kUniWarps = 8;
+__global__ void __launch_bounds__(kUniWarps * 32)
+k_uni_grid(const float4* __restrict__ s32, const double2* __restrict__ smi, const double* __restrict__ sc,
+           const UniTileMeta* __restrict__ meta, int64_t K, const double* __restrict__ xs,
+           const int32_t* __restrict__ cidx, int C, double lse_skip, double2* __restrict__ part) {
+  __shared__ double s_ref[kUniWarps][32];
+  __shared__ double s_sum[kUniWarps][32];
+  // one staged tile per warp: the three table slices are fetched with 10 independent coalesced loads per lane
+  // (the latency is paid once per tile, not once per kernel) and then read back as broadcasts
+  __shared__ __align__(16) float4 t_32[kUniWarps][kUniTile];
+  __shared__ __align__(16) double2 t_mi[kUniWarps][kUniTile];
+  __shared__ double t_c[kUniWarps][kUniTile];
+  __shared__ double s_e64[64];
+  if (threadIdx.x < 64) s_e64[threadIdx.x] = exp2((double)threadIdx.x * 0.015625);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;      // sorted position of this lane's candidate
+  const double x = xs[i];                    // NaN for the padding lanes of the last group
+  const bool live = x == x;
+  const float xf = __double2float_rn(x);
+  const int ntiles = (int)((K + kUniTile - 1) / kUniTile);
+  const unsigned valid = __ballot_sync(0xffffffffu, live);
+  const double xlo = __shfl_sync(0xffffffffu, x, __ffs(valid) - 1);
+  const double xhi = __shfl_sync(0xffffffffu, x, 31 - __clz(valid));
+  const double skip = lse_skip;
+  // the tile under the candidates
+  int tstart = 0;
+  {
+    int lo = 0, hi = ntiles - 1;             // first tile whose mu range does not lie entirely below xlo
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (meta[mid].mu_hi < xlo) lo = mid + 1; else hi = mid;
+    }
+    tstart = lo;
+  }
+  // reference: the largest term of that tile (all 8 warps: 16 kernels each)
+  {
+    double mx = -INFINITY;
+    const int64_t j0 = (int64_t)tstart * kUniTile + warp * (kUniTile / kUniWarps);
+    for (int q = 0; q < kUniTile / kUniWarps; ++q) {
+      const double2 mi = __ldg(smi + j0 + q);
+      const double tt = fma(x, mi.y, -mi.x);
+      const double L = fma(-0.5 * tt, tt, __ldg(sc + j0 + q));
+      mx = (L > mx) ? L : mx;
+    }
+    s_ref[warp][lane] = mx;
+  }
+  __syncthreads();
+  double ref = s_ref[0][lane];
+#pragma unroll
+  for (int w = 1; w < kUniWarps; ++w) ref = fmax(ref, s_ref[w][lane]);
+  if (!(ref > -INFINITY)) ref = -INFINITY;   // an all-padding tile cannot happen for tstart; NaN x stays dead
+  double mrun = ref;                         // lower bound of the candidate's max (it IS one of its terms)
+  float thrf = __double2float_rd(mrun - skip);
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+
+  auto do_tile = [&](int t) {
+    const int64_t j0 = (int64_t)t * kUniTile;
+    __syncwarp();                            // the previous tile has been consumed
+#pragma unroll
+    for (int q = lane; q < kUniTile; q += 32) {
+      t_32[warp][q] = __ldg(s32 + j0 + q);
+      t_mi[warp][q] = __ldg(smi + j0 + q);
+      t_c[warp][q] = __ldg(sc + j0 + q);
+    }
+    __syncwarp();
+    for (int q = 0; q < kUniTile; q += 4) {
+      bool pass[4];
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 v = t_32[warp][q + u];
+        const float tf = fmaf(xf, v.y, -v.x);
+        const float Lf = fmaf(-0.5f * tf, tf, v.z);
+        const float ub = fmaf(fabsf(tf) + 1.0f, v.w, Lf) + 2.5e-7f * (fabsf(v.z) + fabsf(Lf));
+        pass[u] = !(ub < thrf) && live;      // cannot be dismissed in fp32
+        any = any || pass[u];
+      }
+      if (!__any_sync(0xffffffffu, any)) continue;
+      double L[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double2 mi = t_mi[warp][q + u];
+        const double tt = fma(x, mi.y, -mi.x);
+        L[u] = fma(-0.5 * tt, tt, t_c[warp][q + u]);
+      }
+      double big = fmax(fmax(L[0], L[1]), fmax(L[2], L[3]));
+      big = live ? big : -INFINITY;
+      if (__any_sync(0xffffffffu, big > ref + 600.0)) {   // never on real data: keep the sums finite
+        if (big > ref + 600.0) {
+          const double sc2 = uni_exp(fmax(ref - big, -700.0), s_e64);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] *= sc2;
+          ref = big;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double d = L[u] - mrun;
+        const bool take = pass[u] && d > -skip;            // L = -inf (padding), NaN: compare false
+        // a term taken against the OLD running max may lie far below a reference this very group has just moved
+        const double e = uni_exp(take ? fmax(L[u] - ref, -700.0) : 0.0, s_e64);
+        acc[u] += take ? e : 0.0;
+      }
+      if (big > mrun) {
+        mrun = big;
+        thrf = __double2float_rd(mrun - skip);
+      }
+    }
+  };
+  for (int dt = warp; dt < ntiles; dt += kUniWarps) {
+    for (int side = 0; side < 2; ++side) {
+      const int t = side == 0 ? tstart + dt : tstart - 1 - dt;
+      if (t < 0 || t >= ntiles) continue;
+      if (t != tstart) {
+        const UniTileMeta tm = meta[t];
+        // L <= cmax - (dist / smax)^2 / 2 for every kernel of the tile and every candidate of the warp
+        const double dist = fmax(fmax(tm.mu_lo - xhi, xlo - tm.mu_hi), 0.0) * (1.0 - 1e-12);
+        const double z = dist / tm.smax;
+        const double ub = tm.cmax - 0.5 * z * z + 1e-9;
+        double thr = live ? mrun - skip : INFINITY;   // against the LOWEST threshold of the warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) thr = fmin(thr, __shfl_xor_sync(0xffffffffu, thr, o));
+        if (ub < thr) continue;
+      }
+      do_tile(t);
+    }
+  }
+  // the eight partial sums refer to (possibly) different references only if one was moved: bring them to the largest
+  s_ref[warp][lane] = ref;
+  s_sum[warp][lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (warp == 0 && live) {
+    double r = s_ref[0][lane];
+#pragma unroll
+    for (int w = 1; w < kUniWarps; ++w) r = fmax(r, s_ref[w][lane]);
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < kUniWarps; ++w) {
+      const double rw = s_ref[w][lane];
+      tot += (rw == r) ? s_sum[w][lane] : s_sum[w][lane] * uni_exp(fmax(rw - r, -700.0), s_e64);
+    }
+    part[cidx[i]] = (r > -INFINITY) ? make_double2(r, tot) : make_double2(-INFINITY, 0.0);
+  }
+}
+
+}  // namespace tpe
