@@ -46,7 +46,9 @@ struct DevBuf {
   cudaError_t ensure(size_t bytes) {
     if (!owned) { p = nullptr; cap = 0; owned = true; }
     if (bytes <= cap) return cudaSuccess;
-    size_t want = std::max(bytes, cap + cap / 2);
+    // 12 % headroom: a study grows by one trial per suggestion, and a cudaFree + cudaMalloc of a 50 MB table in the
+    // middle of an ask costs milliseconds (and synchronises the device)
+    size_t want = std::max(bytes + bytes / 8, cap + cap / 2);
     want = (want + 255) & ~(size_t)255;
     if (p) cudaFree(p);
     p = nullptr;
