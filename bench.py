@@ -466,6 +466,54 @@ def run_b200(args) -> None:
         extras["univariate_trial_ms"] = unib * 1e3
         extras["univariate_suggestions_per_s"] = 1.0 / unib
         extras["univariate_device_ms"] = float(eng.last_timing()[0][8])
+        # config 4: MOTPE, 20 000 trials x 8 floats, 4 objectives, C = 24 -- with the default gamma (25 below trials)
+        # and with gamma = ceil(0.1 n) (2000 below trials: rank peeling + HSSP over a 150-point tie rank + hypervolume
+        # weights over the below set's Pareto front), next to the reference's own split + weights on the same values
+        try:
+            n4, p4 = 20_000, 8
+            r4 = np.random.RandomState(4)
+            X4 = r4.uniform(0, 1, (n4, p4))
+            v4 = ((X4[:, None, :] - np.array([0.2, 0.4, 0.6, 0.8])[None, :, None]) ** 2).sum(2)
+            e4 = TPEEngine(local)
+            e4.set_space([ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(p4)])
+            e4.set_history(X4, np.zeros(n4, np.int8), np.zeros((n4, 2)))
+            e4.set_values(v4, 0)
+            mo = {}
+            for tag, nb in (("default_gamma", 25), ("gamma_10pct", int(math.ceil(0.1 * n4)))):
+                u4 = np.random.RandomState(7).random_sample(24 * (1 + p4))
+                for rep in range(3):
+                    t0 = time.perf_counter()
+                    e4.suggest(list(range(p4)), u4, 1, n_below=nb, n_candidates=24, multivariate=True)
+                    dt = time.perf_counter() - t0
+                mo[tag] = {"n_below": nb, "suggestion_ms": dt * 1e3}
+            e4.close()
+            from optuna.samplers._tpe import sampler as ref_tpe
+            from optuna.study._multi_objective import _fast_non_domination_rank
+
+            class _S:  # what _calculate_weights_below_for_multi_objective reads from a study / a trial
+                directions = [optuna.study.StudyDirection.MINIMIZE] * 4
+
+            class _T:
+                def __init__(self, v):
+                    self.values = list(v)
+            for tag in mo:
+                nb = mo[tag]["n_below"]
+                t0 = time.perf_counter()
+                ranks = _fast_non_domination_rank(v4, n_below=nb)
+                uq, cnts = np.unique(ranks, return_counts=True)
+                last = int(np.max(uq[np.cumsum(cnts) <= nb], initial=-1))
+                idx = np.arange(n4)
+                bel = idx[ranks <= last]
+                tie = ranks == last + 1
+                if bel.size < nb:
+                    sel = ref_tpe._solve_hssp_with_cache(tuple(v4[tie].ravel()), tuple(idx[tie]), nb - bel.size,
+                                                         tuple(ref_tpe._get_reference_point(v4[tie])))
+                    bel = np.sort(np.append(bel, sel))
+                ref_tpe._calculate_weights_below_for_multi_objective(_S(), [_T(v) for v in v4[bel]], None)
+                mo[tag]["reference_split_and_weights_ms"] = (time.perf_counter() - t0) * 1e3
+            extras["motpe_c4"] = mo
+        except Exception as e:  # an extra must never take the headline down
+            extras["motpe_c4"] = {"error": repr(e)}
         # config-5 shape: 8192 concurrent asks with the default n_ei_candidates = 24, one device call
         bcfg = dict(cfg, n_candidates=24)
         n_asks = 8192

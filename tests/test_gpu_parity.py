@@ -701,3 +701,97 @@ def test_univariate_batch_equals_the_per_parameter_calls(eng):
     eng.set_history(Xm, np.zeros(n, np.int8), key)
     with pytest.raises(RuntimeError, match="not batchable"):
         eng.suggest_univariate_batch([0, 2], np.zeros(2 * 2 * 24), n_below=25, n_candidates=24, multivariate=False)
+
+
+def test_config2_full_size_against_the_precomputed_oracle_fixture(eng):
+    """BASELINE config 2 at full size: log l(x) and log g(x) of 256 points -- the first 256 candidates the oracle draws
+    -- against tests/golden/c2_logpdf.npz (oracle/gen_c2_fixture.py: the chunked oracle, ~6 min of CPU, so it is
+    committed rather than recomputed).  tpe_logpdf evaluates the SAME points (bit for bit) with the same grid
+    kernels a suggestion uses; 1e-12 absolute."""
+    from optuna_b200.engine import ParamSpec
+    g = load("c2_logpdf.npz")
+    N, P = 100_000, 32
+    rs = np.random.RandomState(0)
+    X = rs.uniform(0, 1, (N, P))
+    key = np.stack([((X - 0.5) ** 2).sum(1), np.zeros(N)], 1)
+    eng.set_space([ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(P)])
+    eng.set_history(X, np.zeros(N, np.int8), key)
+    eng.prepare(list(range(P)), n_below=orc.default_gamma(N), n_candidates=4096, multivariate=True)
+    below, _ = eng.get_split()
+    assert np.array_equal(below, g["below"])
+    eng.build()
+    lg = eng.logpdf(1, g["x"])
+    assert eng.last_logpdf_kernel().startswith("k_logpdf_mma")
+    ll = eng.logpdf(0, g["x"])
+    assert g["x"].shape == (256, P)
+    close(lg, g["logg"], 0, 1e-12)
+    close(ll, g["logl"], 0, 1e-12)
+    # ... and inside a suggestion (same seed => the candidates are these points to 1e-12): the 256 values again
+    u = draw_uniforms(np.random.RandomState(1), 4096, 0, P)
+    eng.suggest(list(range(P)), u, 1, n_below=orc.default_gamma(N), n_candidates=4096, multivariate=True)
+    smp, ll2, lg2 = eng.get_candidates()
+    close(smp[:256], g["x"], 1e-12, 1e-12)
+    close(lg2[:256], g["logg"], 0, 2e-12)   # the points differ by <= 1e-12 relative: |d log g / dx| <~ 1e2 each
+    close(ll2[:256], g["logl"], 0, 2e-12)
+
+
+def test_far_tier_worst_case_every_term_just_below_the_exact_window(eng):
+    """The fp32 ("far") tier of the tensor-core kernel is bounded for the case that ALL K terms sit just below the
+    exact window (ln K + 17.5 under the max): build exactly that -- one kernel at the query point, every other kernel
+    on a sphere around it whose radius puts its term 0.01 nats outside the window -- plus the mirror case 0.01 nats
+    inside (every term exact), and a sphere just inside / outside the drop line (ln K + 30).  1e-12 absolute."""
+    from optuna_b200.engine import ParamSpec
+    P, n = 8, 20_000
+    rs = np.random.RandomState(5)
+    specs = [ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(P)]
+    params = [orc.Param("float", 0.0, 1.0) for _ in range(P)]
+    cfg = orc.Config(multivariate=True)
+    x0 = np.full(P, 0.5)
+    sigma = max(0.2 * n ** (-1.0 / (P + 4)), 1.0 / min(100.0, 1.0 + n + 1))     # parzen_estimator.py:187-228, range 1
+    K = n + 1
+    for gap in (np.log(K) + 17.5 + 0.01, np.log(K) + 17.5 - 0.01, np.log(K) + 30.0 - 0.01, np.log(K) + 30.0 + 0.01):
+        r = sigma * np.sqrt(2.0 * gap)                                           # |x0 - mu|^2 / (2 sigma^2) = gap
+        d = rs.normal(size=(n - 1, P))
+        d *= (r / np.linalg.norm(d, axis=1))[:, None]
+        X = np.concatenate([x0[None, :], x0[None, :] + d])
+        assert X.min() > 0 and X.max() < 1
+        # all in the above set: 25 dummy best trials far away take the below slots
+        Xall = np.concatenate([rs.uniform(0.0, 0.02, (25, P)), X])
+        keyv = np.concatenate([np.full(25, -1.0), np.ones(n)])
+        key = np.stack([keyv, np.zeros(n + 25)], 1)
+        eng.set_space(specs)
+        eng.set_history(Xall, np.zeros(n + 25, np.int8), key)
+        eng.prepare(list(range(P)), n_below=25, n_candidates=64, multivariate=True)
+        eng.build(None, np.ones(n))                                              # equal weights: equal terms
+        pts = np.stack([x0, x0 + 1e-3, x0 - 2e-3 * np.arange(P) / P])
+        got = eng.logpdf(1, pts)
+        assert eng.last_logpdf_kernel().startswith("k_logpdf_mma")
+        cfg_w = orc.Config(multivariate=True, weights=lambda k: np.ones(k))
+        ma = orc.build_mixture(X, params, cfg_w)
+        close(got, orc.mixture_log_pdf(ma, pts), 0, 1e-12)
+
+
+def test_nan_cells_and_nan_wins_argmax(eng):
+    """_truncnorm.logpdf returns nan where a == b (a parameter whose low == high, _truncnorm.py:286-297); the
+    acquisition is then nan for every candidate and np.argmax returns the first index (sampler.py:603-618: NaN
+    wins).  Same on the device: k_select."""
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(9)
+    n, C = 300, 32
+    X = np.stack([rs.uniform(-1, 1, n), np.full(n, 2.5), rs.uniform(0, 4, n)], 1)
+    key = np.stack([(X[:, 0] ** 2 + X[:, 2]), np.zeros(n)], 1)
+    specs = [ParamSpec(kind=0, low=-1.0, high=1.0), ParamSpec(kind=0, low=2.5, high=2.5), ParamSpec(kind=0, low=0.0, high=4.0)]
+    params = [orc.Param("float", -1.0, 1.0), orc.Param("float", 2.5, 2.5), orc.Param("float", 0.0, 4.0)]
+    eng.set_space(specs)
+    eng.set_history(X, np.zeros(n, np.int8), key)
+    for mv, cols in ((True, [0, 1, 2]), (False, [1]), (True, [0, 2])):
+        u = draw_uniforms(np.random.RandomState(4), C, 0, len(cols))
+        with np.errstate(all="ignore"):
+            s = orc.suggest(X, np.zeros(n, np.int8), key, params, cols, orc.Config(multivariate=mv), 25, C,
+                            np.random.RandomState(4))
+        x, acq, best = eng.suggest(cols, u, 1, n_below=25, n_candidates=C, multivariate=mv)
+        smp, ll, lg = eng.get_candidates()
+        assert np.array_equal(np.isnan(ll - lg), np.isnan(s.acq)), (mv, cols)
+        assert int(best[0]) == s.best, (mv, cols, best, s.best)
+        if 1 in cols:
+            assert np.isnan(s.acq).all() and s.best == 0 and np.isnan(acq[0])
