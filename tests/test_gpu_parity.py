@@ -751,8 +751,7 @@ def test_far_tier_worst_case_every_term_just_below_the_exact_window(eng):
     K = n + 1
     for gap in (np.log(K) + 17.5 + 0.01, np.log(K) + 17.5 - 0.01, np.log(K) + 30.0 - 0.01, np.log(K) + 30.0 + 0.01):
         r = sigma * np.sqrt(2.0 * gap)                                           # |x0 - mu|^2 / (2 sigma^2) = gap
-        d = rs.normal(size=(n - 1, P))
-        d *= (r / np.linalg.norm(d, axis=1))[:, None]
+        d = rs.choice([-1.0, 1.0], size=(n - 1, P)) * (r / np.sqrt(P))        # on the sphere, every coordinate inside (0, 1)
         X = np.concatenate([x0[None, :], x0[None, :] + d])
         assert X.min() > 0 and X.max() < 1
         # all in the above set: 25 dummy best trials far away take the below slots
