@@ -612,8 +612,8 @@ def run_b200(args) -> None:
                     "caller": f"optuna {optuna.__version__} ({os.path.relpath(os.path.dirname(optuna.__file__), ROOT)})",
                     "host": e2e_host},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": 27546880, "traffic_source": "ncu --set full, profiles/r1_ncu_raw_logpdf_mma_final.txt "
-                         "(dram__bytes_read.sum + dram__bytes_write.sum of this launch)",
+                         "traffic": 27560960, "traffic_source": "ncu --set full, profiles/r2_ncu_raw_logpdf_mma.txt "
+                         "(dram__bytes_read.sum 27 523 328 + dram__bytes_write.sum 37 632 of this launch)",
                          "peak_source": peak_src, "kernel": kernel_name,
                          "kernel_ms": k_ms, "algorithmic_bytes": algorithmic_bytes(),
                          "note": "the C x K x P grid reuses every history byte C=4096 times from shared memory, so "
