@@ -32,7 +32,8 @@ extern "C" {
  *      after tpe_stage_uniforms_mt19937 */
 /* 3: + TPE_CAT_EXCLUDED; tpe_history_update may extend the history; tpe_sample_and_select accepts out_x == NULL
  *      (results stay on the device: tpe_result_device_ptrs); tpe_rng_state_device; tpe_suggest_univariate_batch */
-#define TPE_ABI_VERSION 3
+/* 4: + tpe_sample_and_select_async / tpe_collect */
+#define TPE_ABI_VERSION 4
 
 enum {
   TPE_OK = 0,
@@ -153,6 +154,15 @@ int tpe_build(tpe_ctx* ctx, const double* w_below, const double* w_above);
  *   out_best [n_asks] its candidate index (may be NULL) */
 int tpe_sample_and_select(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x,
                           double* out_acq, int64_t* out_best);
+
+/* The same in two halves: tpe_sample_and_select_async queues the work (and the copy of the results into page-locked
+ * memory of the context) and returns; tpe_collect waits for it and hands the results out.  A caller that knows the
+ * next suggestion's inputs early -- the sampler at `tell` time: the history with the finished trial, the generator
+ * where the last ask left it (BaseSampler.after_trial, optuna/samplers/_base.py:178-203, runs before the next
+ * Study.ask) -- overlaps the device work with its own host work; results are those of tpe_sample_and_select.
+ * `uniforms` is read before tpe_sample_and_select_async returns.  Any tpe_prepare abandons uncollected results. */
+int tpe_sample_and_select_async(tpe_ctx* ctx, const double* uniforms, int64_t n_asks);
+int tpe_collect(tpe_ctx* ctx, double* out_x, double* out_acq, int64_t* out_best);
 
 /* Device pointers of the results of the last tpe_sample_and_select: out_x [n_asks, n_cols], out_acq [n_asks],
  * out_best [n_asks] (valid until the next call on the context; the work has completed when that call returned). */

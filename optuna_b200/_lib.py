@@ -53,6 +53,8 @@ SYMBOLS = {
     "tpe_stage_uniforms_mt19937": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64]),
     "tpe_rng_state": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "tpe_rng_state_device": (C.c_int, [_P, C.POINTER(_P)]),
+    "tpe_sample_and_select_async": (C.c_int, [_P, _P, C.c_int64]),
+    "tpe_collect": (C.c_int, [_P, _P, _P, _P]),
     "tpe_result_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "tpe_get_uniforms": (C.c_int, [_P, _P, C.c_int64]),
     "tpe_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -73,7 +75,7 @@ SYMBOLS = {
 _lib = None
 
 
-ABI_VERSION = 3  # include/optuna_b200_tpe.h TPE_ABI_VERSION
+ABI_VERSION = 4  # include/optuna_b200_tpe.h TPE_ABI_VERSION
 
 
 def load() -> C.CDLL:

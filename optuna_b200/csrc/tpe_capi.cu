@@ -190,7 +190,23 @@ struct tpe_ctx {
   std::vector<tpe_ctx*> uni_sub;
   cudaEvent_t ev_uni = nullptr;
   bool is_sub = false;
+  bool deferred = false;         // tpe_sample_and_select_async issued, tpe_collect not yet called
+  bool issued_dev_rng = false;
+  void* res_host = nullptr;      // page-locked staging of deferred results
+  size_t res_host_cap = 0;
   int sort_cta_cap = 0;          // sub-contexts: CTAs of a cooperative sort (several sorts share the GPU)
+  // incremental sorted orders (univariate batch): the parent compares the above rows of this call with the previous
+  // call's; every column context then updates its order instead of sorting (k_rows_delta / k_order_update)
+  uint64_t hist_lineage = 0;     // changes whenever rows the estimators can see are replaced (not on appends)
+  DevBuf uni_prev_rows, uni_mode, uni_work;
+  int64_t uni_prev_n = -1;
+  uint64_t uni_prev_lineage = 0;
+  const int* uni_mode_ptr = nullptr;   // sub-contexts: the parent's mode word, or nullptr (always sort)
+  uint64_t uni_seq = 0;                // batch calls so far (sub-contexts: the running call's number)
+  uint64_t uni_ord_seq = 0;            // sub-contexts: the call that left the cached order of est[1] ...
+  uint64_t uni_ord_lineage = 0;        // ... and what else it belongs to
+  int32_t uni_ord_col = -1;
+  int64_t uni_ord_K = -1;
 };
 
 namespace {
@@ -810,9 +826,6 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
       if (m2 <= 4096) {
         k_sort_small<<<1, 1024, 0, st>>>(e.mu.as<double>(), pc, j, (int)K, (int)m2, ctx->sort_idx.as<int32_t>());
         ctx->launch_counter++;
-      } else if (getenv("TPE_DEBUG_SKIP_SORT") && ctx->uni_fast && e.uord.cap >= (size_t)K * 4 && ctx->sort_idx.cap >= (size_t)K * 4) {
-        // timing experiment only: reuse the previous order
-        CU(cudaMemcpyAsync(ctx->sort_idx.p, e.uord.p, (size_t)K * 4, cudaMemcpyDeviceToDevice, st));
       } else {
         // cooperative stable radix sort (one launch instead of ~150 bitonic steps)
         CU(ctx->sort_val.ensure((size_t)K * 8 * 2));
@@ -827,7 +840,22 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
         int32_t* ia = order + K;
         int32_t* ib = ia + K;
         SortWork* wk = ctx->sort_work.as<SortWork>();
-        void* args[] = {&d_mu, &pc_i, &j_i, &n_i, &ka, &kb, &ia, &ib, &wk, &order};
+        // column contexts of a univariate batch: the previous trial's order, if it belongs to this column of this
+        // history and the set has the same size or one observation more, is updated instead (the sort then returns
+        // at once unless the parent found the rows changed otherwise)
+        const int* run_flag = nullptr;
+        if (which == 1 && ctx->uni_fast && ctx->uni_mode_ptr != nullptr && ctx->uni_ord_seq + 1 == ctx->uni_seq &&
+            ctx->uni_ord_lineage == ctx->hist_lineage &&
+            ctx->uni_ord_col == ctx->cols_h[0].src && (ctx->uni_ord_K == K || ctx->uni_ord_K == K - 1) &&
+            e.uord.cap >= (size_t)ctx->uni_ord_K * 4) {
+          run_flag = ctx->uni_mode_ptr;
+          CU(ctx->uni_work.ensure(16));
+          CU(cudaMemsetAsync(ctx->uni_work.p, 0, 16, st));
+          k_order_update<<<grid_for(ctx->uni_ord_K, 256, ctx->sm_count), 256, 0, st>>>(
+              run_flag, e.uord.as<int32_t>(), (int)ctx->uni_ord_K, (int)K, e.mu.as<double>(), order, ctx->uni_work.as<int>());
+          ctx->launch_counter++;
+        }
+        void* args[] = {&d_mu, &pc_i, &j_i, &n_i, &ka, &kb, &ia, &ib, &wk, &order, &run_flag};
         int G = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(ctx->sm_count, 160), (K + 1023) / 1024));
         if (ctx->sort_cta_cap > 0) G = std::min(G, ctx->sort_cta_cap);
         CU(cudaLaunchCooperativeKernel((const void*)k_radix_sort_coop, dim3(G), dim3(512), args, 0, st));
@@ -838,8 +866,14 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
                                                          ctx->cfg.endpoints, e.sigma.as<double>());
       ctx->launch_counter++;
       if (ctx->uni_fast) {   // the 1-D grid walks the kernels in this order
-        CU(e.uord.ensure((size_t)K * 4));
+        CU(e.uord.ensure((size_t)(K + 1024) * 4));   // room to grow without a reallocation (the old order is read above)
         CU(cudaMemcpyAsync(e.uord.p, ctx->sort_idx.p, (size_t)K * 4, cudaMemcpyDeviceToDevice, st));
+        if (which == 1) {
+          ctx->uni_ord_seq = ctx->uni_seq;
+          ctx->uni_ord_lineage = ctx->hist_lineage;
+          ctx->uni_ord_col = ctx->cols_h[0].src;
+          ctx->uni_ord_K = K;
+        }
       }
     }
     k_const<<<grid_for(K * 32, 256, cap), 256, 0, st>>>(e.mu.as<double>(), e.sigma.as<double>(),
@@ -1231,11 +1265,12 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed, &ctx->mo_table,
                     &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv, &ctx->mo_fv, &ctx->mo_ps, &ctx->mo_map, &ctx->mo_front, &ctx->mo_head,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
-                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->uxs, &ctx->ucidx, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
+                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->uxs, &ctx->ucidx, &ctx->uni_prev_rows, &ctx->uni_mode, &ctx->uni_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->U2, &ctx->mt_spec, &ctx->mt_jump, &ctx->mt_tmp, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
   ctx->est[1].release();
+  if (ctx->res_host) cudaFreeHost(ctx->res_host);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -1289,6 +1324,7 @@ int tpe_space_set(tpe_ctx* ctx, const tpe_param_desc* params, int32_t n_params, 
   }
   ctx->col_missing.assign(n_params, 0);
   ctx->col_oor.assign(n_params, 0);
+  ctx->hist_lineage++;
   ctx->N = 0;
   ctx->history_set = false;
   ctx->prepared = ctx->built = ctx->sampled = false;
@@ -1305,6 +1341,7 @@ int tpe_history_set(tpe_ctx* ctx, const double* X, const int8_t* category, const
   if (set_device(ctx)) return TPE_E_CUDA;
   std::fill(ctx->col_missing.begin(), ctx->col_missing.end(), 0);
   std::fill(ctx->col_oor.begin(), ctx->col_oor.end(), 0);
+  ctx->hist_lineage++;
   scan_missing(ctx, X, category, n);
   return upload_history(ctx, X, category, key, n, 0, false);
 }
@@ -1350,7 +1387,10 @@ int tpe_history_update(tpe_ctx* ctx, const double* X, const int8_t* category, co
   ctx->cat_h.resize((size_t)total, (int8_t)TPE_CAT_EXCLUDED);
   for (int64_t i = 0; i < n; ++i) {
     const int64_t r = at_row + i;
-    if (r < ctx->N) ctx->cat_cnt[cat_slot(ctx->cat_h[(size_t)r])]--;
+    if (r < ctx->N) {
+      if (cat_slot(ctx->cat_h[(size_t)r]) != 4) ctx->hist_lineage++;   // a row the estimators could see is replaced
+      ctx->cat_cnt[cat_slot(ctx->cat_h[(size_t)r])]--;
+    }
     ctx->cat_h[(size_t)r] = category[i];
     ctx->cat_cnt[cat_slot(category[i])]++;
   }
@@ -1367,6 +1407,7 @@ int tpe_history_set_device(tpe_ctx* ctx, const double* dX, const int8_t* dcatego
   if (ctx->space.empty()) return fail(ctx, TPE_E_STATE, "tpe_space_set must precede tpe_history_set_device");
   if (n < 0 || (n > 0 && (!dX || !dcategory || !dkey))) return fail(ctx, TPE_E_INVALID, "bad history arguments");
   if (set_device(ctx)) return TPE_E_CUDA;
+  ctx->hist_lineage++;
   for (size_t j = 0; j < ctx->col_missing.size(); ++j) ctx->col_missing[j] = col_has_missing ? col_has_missing[j] : 1;
   // a history adopted from device memory is not scanned on the host: treat every column as possibly out of range
   // unless the caller vouches for it through col_has_missing (the broadcast path of optuna_b200/dist.py does)
@@ -1383,6 +1424,7 @@ int tpe_history_set_values(tpe_ctx* ctx, const double* values, int64_t n, int32_
   if (n < 0 || at_row < 0 || at_row + n > ctx->N || (n > 0 && !values))
     return fail(ctx, TPE_E_INVALID, "bad values range");
   if (at_row > 0 && n_objectives != ctx->M) return fail(ctx, TPE_E_INVALID, "n_objectives changed");
+  ctx->hist_lineage++;
   if (set_device(ctx)) return TPE_E_CUDA;
   // a partial write keeps every row already there (rows after the written range included)
   const size_t keep = (n_objectives == ctx->M && at_row > 0)
@@ -1504,6 +1546,7 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
   if (set_device(ctx)) return TPE_E_CUDA;
   ctx->cfg = *cfg;
   ctx->launch_counter = 0;
+  ctx->deferred = false;   // a new sequence abandons results nobody collected
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   bool need_rowok = false;
   if (int rc0 = setup_columns(ctx, cfg, cols, n_cols, &need_rowok)) return rc0;
@@ -1709,8 +1752,9 @@ static int launch_sample_select(tpe_ctx* ctx, int64_t n_asks, bool used_dev_rng,
   return TPE_OK;
 }
 
-static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x, double* out_acq,
-                                int64_t* out_best) {
+// Everything of tpe_sample_and_select up to the last kernel.  defer: the results are also copied into the
+// context's page-locked staging area and nothing is waited for (tpe_sample_and_select_async).
+static int sample_select_issue(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, bool defer) {
   if (!ctx->built) return fail(ctx, TPE_E_STATE, "tpe_build must precede tpe_sample_and_select");
   if ((!uniforms && !ctx->u_device_rng) || n_asks <= 0)
     return fail(ctx, TPE_E_INVALID, "bad sample arguments");
@@ -1720,6 +1764,7 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
   const int64_t Ct = n_asks * C;
   const int64_t per_ask = (int64_t)C * (1 + ctx->ncat + ctx->nnum);
   ctx->n_asks = n_asks;
+  ctx->deferred = false;
   int rc = ensure_candidate_buffers(ctx, Ct);
   if (rc) return rc;
   CU(ctx->U.ensure((size_t)n_asks * per_ask * 8));
@@ -1743,23 +1788,50 @@ static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_
     CU(cudaMemcpyAsync(ctx->U.p, uniforms, (size_t)n_asks * per_ask * 8, cudaMemcpyHostToDevice, st));
   }
   ctx->u_staged = nullptr;
-  const int base_launches = ctx->launch_counter;
-
   rc = launch_sample_select(ctx, n_asks, used_dev_rng, true);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->ev[8], st));
   CU(cudaGetLastError());
-  if (out_x) CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_asks * ctx->pc * 8, cudaMemcpyDeviceToHost, st));
-  if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
-  if (out_best) CU(cudaMemcpyAsync(out_best, ctx->out_best.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  if (used_dev_rng) ctx->mt_host_valid = true;
+  ctx->issued_dev_rng = used_dev_rng;
+  if (defer) {
+    const size_t need = (size_t)n_asks * (ctx->pc + 2) * 8;
+    if (ctx->res_host_cap < need) {
+      if (ctx->res_host) cudaFreeHost(ctx->res_host);
+      ctx->res_host = nullptr;
+      ctx->res_host_cap = 0;
+      CU(cudaHostAlloc(&ctx->res_host, need + 4096, cudaHostAllocDefault));
+      ctx->res_host_cap = need + 4096;
+    }
+    char* h = static_cast<char*>(ctx->res_host);
+    CU(cudaMemcpyAsync(h, ctx->out_x.p, (size_t)n_asks * ctx->pc * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h + (size_t)n_asks * ctx->pc * 8, ctx->out_acq.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h + (size_t)n_asks * (ctx->pc + 1) * 8, ctx->out_best.p, (size_t)n_asks * 8,
+                       cudaMemcpyDeviceToHost, st));
+    ctx->deferred = true;
+  }
+  return TPE_OK;
+}
+
+static int sample_select_finish(tpe_ctx* ctx) {
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->issued_dev_rng) ctx->mt_host_valid = true;
   for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
   cudaEventElapsedTime(&ctx->ms[8], ctx->ev[0], ctx->ev[8]);
   ctx->launches = ctx->launch_counter;
-  (void)base_launches;
   ctx->sampled = true;
+  ctx->deferred = false;
   return TPE_OK;
+}
+
+static int sample_select_locked(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x, double* out_acq,
+                                int64_t* out_best) {
+  int rc = sample_select_issue(ctx, uniforms, n_asks, false);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  if (out_x) CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_asks * ctx->pc * 8, cudaMemcpyDeviceToHost, st));
+  if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
+  if (out_best) CU(cudaMemcpyAsync(out_best, ctx->out_best.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
+  return sample_select_finish(ctx);
 }
 
 int tpe_sample_and_select(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double* out_x, double* out_acq,
@@ -1767,6 +1839,27 @@ int tpe_sample_and_select(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, 
   if (!ctx) return TPE_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   return sample_select_locked(ctx, uniforms, n_asks, out_x, out_acq, out_best);
+}
+
+int tpe_sample_and_select_async(tpe_ctx* ctx, const double* uniforms, int64_t n_asks) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return sample_select_issue(ctx, uniforms, n_asks, true);
+}
+
+int tpe_collect(tpe_ctx* ctx, double* out_x, double* out_acq, int64_t* out_best) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->deferred) return fail(ctx, TPE_E_STATE, "tpe_collect needs a pending tpe_sample_and_select_async");
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  const int64_t n_asks = ctx->n_asks;
+  int rc = sample_select_finish(ctx);
+  if (rc) return rc;
+  const char* h = static_cast<const char*>(ctx->res_host);
+  if (out_x) memcpy(out_x, h, (size_t)n_asks * ctx->pc * 8);
+  if (out_acq) memcpy(out_acq, h + (size_t)n_asks * ctx->pc * 8, (size_t)n_asks * 8);
+  if (out_best) memcpy(out_best, h + (size_t)n_asks * (ctx->pc + 1) * 8, (size_t)n_asks * 8);
+  return TPE_OK;
 }
 
 int tpe_stage_uniforms_mt19937(tpe_ctx* ctx, const uint32_t* key, int32_t pos, int64_t skip, int64_t count) {
@@ -1978,6 +2071,25 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
     }
     if (n > 0 && tot <= 0) return fail(ctx, TPE_E_INVALID, "The `weight` function is not allowed to return all-zero values.");
   }
+  {
+    // how the above set differs from the previous call's (the column contexts then update their sorted orders
+    // instead of sorting: k_order_update); the answer stays on the device
+    const int64_t n_new = ctx->est[1].n;
+    int cand = 2;
+    if (ctx->uni_prev_n >= 0 && ctx->uni_prev_lineage == ctx->hist_lineage)
+      cand = n_new == ctx->uni_prev_n ? 0 : n_new == ctx->uni_prev_n + 1 ? 1 : 2;
+    CU(ctx->uni_mode.ensure(16));
+    CU(cudaMemsetAsync(ctx->uni_mode.p, 0, 4, ctx->stream));
+    k_rows_delta<<<cand == 2 ? 1 : grid_for(std::max<int64_t>(ctx->uni_prev_n, 1), 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+        ctx->est[1].rows.as<int64_t>(), ctx->uni_prev_rows.as<int64_t>(), cand == 2 ? 0 : ctx->uni_prev_n, cand,
+        ctx->uni_mode.as<int>());
+    ctx->launch_counter++;
+    CU(ctx->uni_prev_rows.ensure((size_t)(n_new + 1) * 8));
+    CU(cudaMemcpyAsync(ctx->uni_prev_rows.p, ctx->est[1].rows.p, (size_t)n_new * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->uni_prev_n = n_new;
+    ctx->uni_prev_lineage = ctx->hist_lineage;
+    ctx->uni_seq++;
+  }
   if (!ctx->ev_uni) CU(cudaEventCreateWithFlags(&ctx->ev_uni, cudaEventDisableTiming));
   CU(cudaEventRecord(ctx->ev_uni, ctx->stream));
   CU(ctx->out_x.ensure((size_t)n_cols * 8));
@@ -2012,6 +2124,9 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
     sub->cat.alias(ctx->cat.p, ctx->cat.cap);
     sub->key.alias(ctx->key.p, ctx->key.cap);
     sub->N = ctx->N;
+    sub->hist_lineage = ctx->hist_lineage;
+    sub->uni_seq = ctx->uni_seq;
+    sub->uni_mode_ptr = ctx->uni_mode.as<int>();
     sub->M = 1;
     sub->history_set = true;
     sub->cfg = *cfg;

@@ -338,7 +338,10 @@ struct SortWork {
 __global__ void __launch_bounds__(512, 1)
 k_radix_sort_coop(const double* __restrict__ mu, int32_t pc, int j_col, int n, uint64_t* __restrict__ key_a,
                   uint64_t* __restrict__ key_b, int32_t* __restrict__ idx_a, int32_t* __restrict__ idx_b,
-                  SortWork* __restrict__ wk, int32_t* __restrict__ order) {
+                  SortWork* __restrict__ wk, int32_t* __restrict__ order, const int* __restrict__ run_flag) {
+  // run_flag != nullptr: the order may already have been brought up to date incrementally (k_order_update);
+  // every CTA reads the same word before the first grid.sync
+  if (run_flag != nullptr && *run_flag < 2) return;
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   __shared__ int s_hist[256];
   __shared__ int s_base[256];
@@ -418,6 +421,62 @@ k_radix_sort_coop(const double* __restrict__ mu, int32_t pc, int j_col, int n, u
     int32_t* ti = iin; iin = iout; iout = ti;
   }
   for (int i = lo + tid; i < hi; i += blockDim.x) order[i] = iin[i];
+}
+
+// Incremental maintenance of a column's sorted order between two suggestions (univariate TPE): the above set of the
+// next trial is almost always the previous one plus the trial that has just finished.
+//   k_rows_delta : mode = 0 rows identical, 1 exactly one row appended at the end, >= 2 anything else (sort again)
+//   k_order_update: mode 0 copies the order; mode 1 inserts the new observation (index n_old; the prior kernel moves
+//                   from index n_old to n_old + 1) at its place -- every old element shifts by one iff the new key is
+//                   smaller (ties by index, like the stable radix sort), the new element lands behind the elements
+//                   that did not shift.
+__global__ void k_rows_delta(const int64_t* __restrict__ rows_new, const int64_t* __restrict__ rows_old, int64_t n_old,
+                             int cand, int* __restrict__ mode /* zeroed */) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && cand) atomicOr(mode, cand);
+  if (cand == 2) return;
+  bool diff = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_old; i += (int64_t)gridDim.x * blockDim.x)
+    diff |= rows_new[i] != rows_old[i];
+  if (diff) atomicOr(mode, 2);   // mode >= 2: sort
+}
+__global__ void __launch_bounds__(256)
+k_order_update(const int* __restrict__ mode, const int32_t* __restrict__ old_order, int K_old, int K_new,
+               const double* __restrict__ mu, int32_t* __restrict__ out, int* __restrict__ work) {
+  const int m = *mode;
+  if (m >= 2) return;
+  if (m == 0) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < K_old; p += gridDim.x * blockDim.x) out[p] = old_order[p];
+    return;
+  }
+  __shared__ int s_cnt;
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int n_old = K_old - 1;                       // index of the new observation (and the prior's old index)
+  const uint64_t v = order_bits(mu[n_old]);
+  int mine = 0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < K_old; p += gridDim.x * blockDim.x) {
+    const int e = old_order[p];
+    const int ne = (e == n_old) ? n_old + 1 : e;
+    const uint64_t key = order_bits(mu[ne]);
+    const bool shift = (v < key) || (v == key && n_old < ne);
+    out[p + (shift ? 1 : 0)] = ne;
+    mine += shift ? 0 : 1;
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_cnt) atomicAdd(&work[0], s_cnt);
+    __threadfence();
+    s_last = atomicAdd(&work[1], 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    out[*reinterpret_cast<volatile int*>(&work[0])] = n_old;
+  }
+  (void)K_new;
 }
 
 // Whole bitonic sort in shared memory for m2 <= 4096 (one CTA of 1024 threads).

@@ -193,6 +193,31 @@ class TPEEngine:
         self._last_asks = n_asks
         return x, acq, best
 
+    def sample_and_select_async(self, uniforms, n_asks: int = 1) -> None:
+        """Queue ``sample_and_select`` and return; ``collect()`` waits and returns the results."""
+        u = None
+        if uniforms is not None:
+            u = _f64(uniforms).reshape(-1)
+            assert u.size == n_asks * self.uniforms_per_ask(), (u.size, n_asks, self.uniforms_per_ask())
+        self._check(self._lib.tpe_sample_and_select_async(self._h, _ptr(u), int(n_asks)))
+        self._last_asks = n_asks
+
+    def collect(self):
+        n_asks = self._last_asks
+        x = np.empty((n_asks, self._pc), dtype=np.float64)
+        acq = np.empty(n_asks, dtype=np.float64)
+        best = np.empty(n_asks, dtype=np.int64)
+        self._check(self._lib.tpe_collect(self._h, _ptr(x), _ptr(acq), _ptr(best)))
+        return x, acq, best
+
+    def rng_snapshot(self) -> tuple:
+        """The generator state the device holds (after the last staged draw) as ``RandomState.set_state`` takes it."""
+        key = np.empty(624, dtype=np.uint32)
+        pos = C.c_int32()
+        self._check(self._lib.tpe_rng_state(self._h, _ptr(key), C.byref(pos)))
+        name, has_gauss, cached = self._rng_tail
+        return (name, key, int(pos.value), has_gauss, cached)
+
     def sample_and_select_device(self, n_asks: int = 1) -> int:
         """Like ``sample_and_select(None, n_asks)`` but the results stay on the device; returns the device
         address of out_x [n_asks, n_cols] fp64 (valid until the next call on this engine)."""
@@ -208,7 +233,7 @@ class TPEEngine:
         self._check(self._lib.tpe_rng_state_device(self._h, C.byref(p)))
         return int(p.value)
 
-    def stage_rng(self, rng: np.random.RandomState | None, count: int, skip: int = 0) -> None:
+    def stage_rng(self, rng: np.random.RandomState | None, count: int, skip: int = 0, state=None) -> None:
         """Generate the next `count` outputs of ``rng.random_sample`` on the device (after dropping
         `skip`); the following ``sample_and_select(None, n_asks)`` consumes them.  ``finish_rng(rng)``
         then moves `rng` to the state after the draws.  ``rng=None`` continues from the state the
@@ -216,7 +241,7 @@ class TPEEngine:
         if rng is None:
             self._check(self._lib.tpe_stage_uniforms_mt19937(self._h, None, 0, int(skip), int(count)))
             return
-        st = rng.get_state()
+        st = rng.get_state() if state is None else state
         key = np.ascontiguousarray(st[1], dtype=np.uint32)
         self._rng_tail = (st[0], st[3], st[4])
         self._check(self._lib.tpe_stage_uniforms_mt19937(self._h, _ptr(key), int(st[2]), int(skip), int(count)))

@@ -146,6 +146,8 @@ class _History:
         self.dev_rows = 0
         self.dev_cat: dict[int, int] = {}      # category uploaded for the rows still pending
         self.backlog: dict[int, Any] = {}      # row -> FrozenTrial: changes the log has seen, the device has not
+        self.dev_pred: dict[int, Any] = {}     # row -> _Told: uploaded at `tell` time, before the storage showed it
+        self.dev_version = 0                   # counts the uploads that change what the estimators see
 
     # -- log ---------------------------------------------------------------------------------------------
     def _account(self, t) -> None:
@@ -279,6 +281,36 @@ class _DeviceSyncedRng:
         self.__dict__.update(state)
 
 
+class _Told:
+    """A trial as it will look once ``Study.tell`` has stored it: ``after_trial`` (samplers/_base.py:178-203) is
+    handed the trial, its final state and values just BEFORE the storage records them (study/_tell.py:163-169).
+    Quacks like the FrozenTrial ``_rows`` reads."""
+
+    def __init__(self, trial, state, values) -> None:
+        self.number = trial.number
+        self.state = state
+        self.values = None if values is None else [float(v) for v in values]
+        self.value = self.values[0] if self.values is not None and len(self.values) == 1 else None
+        self.params = dict(trial.params)
+        self.distributions = dict(trial.distributions)
+        self.intermediate_values = dict(trial.intermediate_values)
+        self.system_attrs = dict(trial.system_attrs)
+        self.confirmed = False
+
+    def matches(self, t) -> bool:
+        """Is the stored trial exactly what was uploaded for it?"""
+        return (t.state == self.state and t.values == self.values and t.params == self.params
+                and t.distributions == self.distributions and t.intermediate_values == self.intermediate_values)
+
+
+class _Ahead:
+    """A suggestion whose device work was queued at ``tell`` time (``B200TPESampler._look_ahead``)."""
+
+    def __init__(self, told, space, cols, cfg, dev_version, eng, dev_rng, cancel) -> None:
+        self.told, self.space, self.cols, self.cfg = told, space, cols, cfg
+        self.dev_version, self.eng, self.dev_rng, self.cancel = dev_version, eng, dev_rng, cancel
+
+
 class _UniPlan:
     """Univariate TPE asks every parameter of a trial separately (sampler.py:458-491), one `_sample` each; the P
     calls of a trial see the same history and differ only in the column and in the stretch of the generator they
@@ -355,6 +387,10 @@ class B200TPESampler(BaseSampler):
         self._groups_now: list[dict[str, BaseDistribution]] = []
         self._lock = threading.RLock()
         self._uni = _UniPlan()
+        self._ahead: _Ahead | None = None
+        self._last_space: dict[str, BaseDistribution] | None = None
+        self.ahead_stats = [0, 0]   # look-ahead suggestions [served, discarded]
+        self.last_tell_s = 0.0
         if multivariate:
             warn_experimental_argument("multivariate")
         if group:
@@ -375,6 +411,8 @@ class B200TPESampler(BaseSampler):
         state["_hist"] = _History()
         state["_groups_now"] = []
         state["_uni"] = _UniPlan()
+        state["_ahead"] = None
+        state["_last_space"] = None
         del state["_lock"]
         return state
 
@@ -384,6 +422,8 @@ class B200TPESampler(BaseSampler):
 
     def close(self) -> None:
         """Release the device context (re-created on demand)."""
+        if getattr(self, "_ahead", None) is not None:
+            self._drop_ahead()
         eng, self._engine = getattr(self, "_engine", None), None
         if eng is not None:
             rng = getattr(self, "_rng", None)
@@ -493,6 +533,11 @@ class B200TPESampler(BaseSampler):
         if self._constraints_func is not None:
             _process_constraints_after_trial(self._constraints_func, study, trial, state)
         self._random_sampler.after_trial(study, trial, state, values)
+        if self.LOOK_AHEAD and self._last_space is not None and self._engine is not None:
+            t0 = time.perf_counter()
+            with self._lock:
+                self._look_ahead(study, trial, state, values)
+            self.last_tell_s = time.perf_counter() - t0   # row upload + queueing the next suggestion
 
     # -- host glue -------------------------------------------------------------------------------------
     def _eng(self) -> TPEEngine:
@@ -529,6 +574,7 @@ class B200TPESampler(BaseSampler):
         if search_space == {} or n_asks <= 0:
             return [{} for _ in range(max(n_asks, 0))]
         with self._lock:
+            self._drop_ahead()
             self._note_changes(self._poll(study))
             if self._hist.n_finished < self._n_startup_trials:
                 return [{} for _ in range(n_asks)]
@@ -638,8 +684,21 @@ class B200TPESampler(BaseSampler):
                 eng.set_values(vals, 0, len(study.directions))
             h.dev_rows = len(trials)
             h.dev_cat = {row: int(cat[row]) for row in h.pending if row < h.dev_rows}
+            h.dev_pred.clear()
+            h.dev_version += 1
             backlog.clear()
             return [h.columns[name] for name in search_space]
+        # rows uploaded at `tell` time: confirmed by what the storage shows now, or put back
+        if h.dev_pred:
+            for row, told in list(h.dev_pred.items()):
+                t = backlog.get(row)
+                if t is not None and told.matches(t):
+                    del backlog[row]                 # the device holds exactly this row already
+                    told.confirmed = True
+                    h.dev_cat.pop(row, None)
+                elif t is None and row in h.pending:
+                    backlog[row] = h.pending[row][1]  # not stored (yet): the device gets back what the log shows
+            h.dev_pred.clear()
         # constant liar: which unfinished rows sit in g(x) depends on who is asking
         if self._constant_liar:
             for row, slot in h.pending.items():
@@ -657,30 +716,50 @@ class B200TPESampler(BaseSampler):
             if not (self._constant_liar and t.state == TrialState.RUNNING and t.number != current):
                 del backlog[row]
         if backlog:
-            names = list(h.columns)
-            rows = sorted(backlog)
-            i = 0
-            while i < len(rows):  # contiguous runs: one tpe_history_update each (it may extend the history)
-                j = i + 1
-                while j < len(rows) and rows[j] == rows[j - 1] + 1:
-                    j += 1
-                at = rows[i]
-                if at > h.dev_rows:  # rows nobody reported (cannot happen: new rows are reported in order)
-                    raise RuntimeError(f"history rows {h.dev_rows}..{at} were never uploaded")
-                run = [backlog[r] for r in rows[i:j]]
-                X, cat, key, vals = self._rows(study, run, names, h.dists, current)
-                eng.update_history(X, cat, key, at)
-                if vals is not None:
-                    eng.set_values(vals, at, len(study.directions))
-                for r, c in zip(rows[i:j], cat):
-                    if r in h.pending:
-                        h.dev_cat[r] = int(c)
-                    else:
-                        h.dev_cat.pop(r, None)
-                h.dev_rows = max(h.dev_rows, at + len(run))
-                i = j
+            # unfinished trials nobody may see, past the end of the device history: nothing to upload -- a later row
+            # that is written brings them along (_upload fills the gap from the log)
+            for row in sorted(backlog, reverse=True):
+                t = backlog[row]
+                if row < h.dev_rows or t.state.is_finished() or (
+                        self._constant_liar and t.state == TrialState.RUNNING and t.number != current):
+                    break
+                del backlog[row]
+            self._upload(study, eng, backlog, current)
             backlog.clear()
         return [h.columns[name] for name in search_space]
+
+    def _upload(self, study, eng, items: dict[int, Any], current: int | None) -> None:
+        """Rows -> device, one tpe_history_update per contiguous run (a run may extend the history; rows between
+        the device's end and the run are the placeholders of unfinished trials the log knows)."""
+        h = self._hist
+        names = list(h.columns)
+        rows = sorted(items)
+        if rows and rows[0] > h.dev_rows:
+            gap = {r: h.pending[r][1] for r in range(h.dev_rows, rows[0])}  # KeyError: a finished row was skipped
+            items = {**gap, **items}
+            rows = sorted(items)
+        i = 0
+        while i < len(rows):
+            j = i + 1
+            while j < len(rows) and rows[j] == rows[j - 1] + 1:
+                j += 1
+            at = rows[i]
+            run = [items[r] for r in rows[i:j]]
+            X, cat, key, vals = self._rows(study, run, names, h.dists, current)
+            if (cat != _lib.CAT_EXCLUDED).any() or any(
+                    r < h.dev_rows and (r not in h.pending or h.dev_cat.get(r, _lib.CAT_EXCLUDED) != _lib.CAT_EXCLUDED)
+                    for r in rows[i:j]):
+                h.dev_version += 1                   # (placeholders coming and going change nothing anyone sees)
+            eng.update_history(X, cat, key, at)
+            if vals is not None:
+                eng.set_values(vals, at, len(study.directions))
+            for r, c in zip(rows[i:j], cat):
+                if r in h.pending:
+                    h.dev_cat[r] = int(c)
+                else:
+                    h.dev_cat.pop(r, None)
+            h.dev_rows = max(h.dev_rows, at + len(run))
+            i = j
 
     #: asks needing at least this many uniforms have them generated on the device
     DEVICE_RNG_MIN = 4096
@@ -717,6 +796,7 @@ class B200TPESampler(BaseSampler):
 
     def _sample_one(self, study, trial, name: str, dist: BaseDistribution) -> Any:
         """One `sample_independent` past the startup trials.  The caller holds the lock and has polled."""
+        self._drop_ahead()
         u = self._uni
         h = self._hist
         if u.calls_trial != trial.number:            # a new trial: the finished recording becomes the prediction
@@ -828,15 +908,21 @@ class B200TPESampler(BaseSampler):
             # (prepare, build, uniforms, sampling + grids + argmax, read-back, to_external_repr)
             self.last_ask_s = (t1 - t0, time.perf_counter() - t1)
 
+    def _cfg(self, n_finished: int) -> dict:
+        return dict(n_below=int(self._gamma(n_finished)), n_candidates=self._n_ei_candidates,
+                    multivariate=self._multivariate, prior_weight=self._prior_weight, magic_clip=self._magic_clip,
+                    endpoints=self._endpoints)
+
     def _sample_synced(self, study, cols: list[int], search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
-        n_below = self._gamma(self._hist.n_finished)
-        cfg = dict(n_below=int(n_below), n_candidates=self._n_ei_candidates, multivariate=self._multivariate,
-                   prior_weight=self._prior_weight, magic_clip=self._magic_clip, endpoints=self._endpoints)
+        cfg = self._cfg(self._hist.n_finished)
         if self._prior_weight < 0:
             raise ValueError("A non-negative value must be specified for prior_weight,"
                              f" but got {self._prior_weight}.")
         eng = self._eng()
-        if self._weights is default_weights:
+        x = self._take_ahead(eng, cols, search_space, cfg)
+        if x is not None:
+            pass
+        elif self._weights is default_weights:
             eng.prepare(cols, **cfg)
             x = self._sample_and_select(eng, search_space, 1, eng.build)
         else:
@@ -846,7 +932,108 @@ class B200TPESampler(BaseSampler):
             wb = None if study._is_multi_objective() else _checked_weights(self._weights, nb)
             wa = _checked_weights(self._weights, na)
             x = self._sample_and_select(eng, search_space, 1, lambda: eng.build(wb, wa))
+        self._last_space = search_space
         out = {}
         for j, (name, d) in enumerate(search_space.items()):
             out[name] = d.to_external_repr(float(x[0, j]))
         return out
+
+    # -- look-ahead: the next suggestion is computed while the study finishes `tell` and starts `ask` ----------
+    #: queue the next joint suggestion at `tell` time (multivariate TPE; see _look_ahead)
+    LOOK_AHEAD = True
+
+    def _drop_ahead(self) -> None:
+        a, self._ahead = self._ahead, None
+        if a is not None:
+            self.ahead_stats[1] += 1
+            if self._rng._settle is a.cancel:
+                self._rng._settle = None
+                a.cancel()
+
+    def _take_ahead(self, eng, cols, search_space, cfg):
+        """The suggestion queued at `tell` time, if this ask is the one it was computed for: the very columns and
+        configuration, the finished trial stored exactly as it was uploaded, nothing else the estimators see
+        changed since, the generator untouched.  Otherwise the generator goes back to where it was."""
+        a, self._ahead = self._ahead, None
+        if a is None:
+            return None
+        ok = (a.told.confirmed and a.eng is eng and a.dev_version == self._hist.dev_version and a.cols == cols
+              and a.cfg == cfg and self._rng._settle is a.cancel
+              and list(a.space.items()) == list(search_space.items()))
+        if not ok:
+            self.ahead_stats[1] += 1
+            if self._rng._settle is a.cancel:
+                self._rng._settle = None
+                a.cancel()
+            return None
+        self._rng._settle = None
+        x, _, _ = eng.collect()
+        if a.dev_rng:
+            self._rng.mark_device(eng)
+        self.ahead_stats[0] += 1
+        return x
+
+    def _look_ahead(self, study, trial, state, values) -> None:
+        """Called from `after_trial`: the trial, its final state and values are known, the storage records them
+        right after (study/_tell.py:163-169).  In a sequential loop everything the next ask will compute is
+        determined at this point -- the history plus this trial, the same search space, the generator where the
+        last ask left it -- so the row is uploaded and the whole suggestion queued on the device now; it runs while
+        optuna stores the trial and creates the next one, and `sample_relative` collects it after checking that the
+        ask really is the predicted one (`_take_ahead`).  Joint sampling with the default weights only; anything
+        out of the ordinary (constraints, constant liar, groups, a failed trial, a changed space) just skips it."""
+        self._drop_ahead()
+        if not (self._multivariate and not self._group and not self._constant_liar and self._constraints_func is None
+                and self._weights is default_weights and self._prior_weight >= 0
+                and (state == TrialState.COMPLETE or state == TrialState.PRUNED)):
+            return
+        h = self._hist
+        space = self._last_space
+        d = trial.distributions
+        if any(d.get(k) != v for k, v in space.items()):
+            return                                   # the intersection search space shrinks with this trial
+        self._note_changes(self._poll(study))
+        if h.n_finished + 1 < self._n_startup_trials:
+            return
+        row = trial.number
+        cols = self._sync(study, None, space)
+        if row >= h.rows or row not in h.pending or h.numbers[row] != trial.number:
+            return
+        eng = self._eng()
+        told = _Told(trial, state, values)
+        self._upload(study, eng, {row: told}, None)
+        h.dev_pred[row] = told                       # (_upload kept its category in dev_cat: the row is pending)
+        cfg = self._cfg(h.n_finished + 1)
+        n = self._n_ei_candidates * (1 + len(space))
+        rng = self._rng
+        if rng._settle is not None:
+            rng.rng                                  # a half-served batch of per-parameter draws: settle it first
+        inner = rng._inner
+        snap = None
+        try:
+            eng.prepare(cols, **cfg)
+            eng.build()
+            dev_rng = n >= self.DEVICE_RNG_MIN
+            if dev_rng and rng.on_device(eng):
+                snap = eng.rng_snapshot()            # where the last ask left the generator (no device access)
+                eng.stage_rng(None, n)
+                eng.sample_and_select_async(None, 1)
+            elif dev_rng:
+                r = rng.rng
+                snap = r.get_state()
+                eng.stage_rng(r, n, state=snap)
+                eng.sample_and_select_async(None, 1)
+            else:
+                r = rng.rng
+                snap = r.get_state()
+                eng.sample_and_select_async(r.random_sample(n), 1)
+        except Exception:                            # the ask will run into it again, and report it
+            if snap is not None:
+                inner.rng.set_state(snap)
+                rng._engine = None
+            return
+
+        def cancel() -> None:                        # nobody took the suggestion: the draws never happened
+            inner.rng.set_state(snap)
+            rng._engine = None
+        rng._settle = cancel
+        self._ahead = _Ahead(told, space, cols, cfg, h.dev_version, eng, dev_rng, cancel)

@@ -138,10 +138,10 @@ class OracleEngine:
         self._mix_a = orc.build_mixture(self._obs_a, self._sub, self._cfg,
                                         None if w_above is None else np.asarray(w_above, dtype=np.float64))
 
-    def stage_rng(self, rng, count: int, skip: int = 0) -> None:
+    def stage_rng(self, rng, count: int, skip: int = 0, state=None) -> None:
         if rng is not None:
             self._rng_src = np.random.RandomState()
-            self._rng_src.set_state(rng.get_state())
+            self._rng_src.set_state(rng.get_state() if state is None else state)
         if skip:
             self._rng_src.random_sample(skip)
         self._staged = self._rng_src.random_sample(count)
@@ -166,6 +166,17 @@ class OracleEngine:
             acq[a] = score[best[a]]
             x[a] = cand[best[a]]
         return x, acq, best
+
+    def sample_and_select_async(self, uniforms, n_asks: int = 1) -> None:
+        self._deferred = self.sample_and_select(uniforms, n_asks)
+
+    def collect(self):
+        out, self._deferred = self._deferred, None
+        assert out is not None, "collect without sample_and_select_async"
+        return out
+
+    def rng_snapshot(self):
+        return self._rng_src.get_state()
 
     def get_candidates(self):
         return self._last

@@ -703,6 +703,86 @@ def test_univariate_batch_equals_the_per_parameter_calls(eng):
         eng.suggest_univariate_batch([0, 2], np.zeros(2 * 2 * 24), n_below=25, n_candidates=24, multivariate=False)
 
 
+def test_univariate_batch_incremental_orders_equal_fresh_sorts(eng):
+    """Between two univariate batch calls the column contexts keep each column's sorted order and bring it up to date
+    (identical rows: reuse; one trial appended: insert) instead of sorting again.  A long-lived engine fed one trial
+    at a time must answer bit-identically to a fresh engine that sorts from scratch, through every kind of change:
+    plain appends (continuous columns and step columns full of ties), a trial that enters the below set and pushes
+    another one into the above set, repeated calls without a change, a changed column list, a RUNNING row that
+    completes later, and an overwritten visible row."""
+    from optuna_b200 import TPEEngine
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(77)
+    specs = [ParamSpec(kind=0, low=-1.0, high=2.0), ParamSpec(kind=0, low=0.0, high=3.0, step=0.25),
+             ParamSpec(kind=1, low=0, high=20, step=1), ParamSpec(kind=0, low=1e-3, high=10.0, log=True)]
+    P, n0, C = len(specs), 6000, 64
+
+    def draw(n):
+        return np.stack([rs.uniform(-1, 2, n), rs.randint(0, 13, n) * 0.25, rs.randint(0, 21, n).astype(float),
+                         np.exp(rs.uniform(np.log(1e-3), np.log(10), n))], 1)
+
+    X = draw(n0)
+    cat = np.zeros(n0, np.int8)
+    key = np.stack([rs.uniform(1, 2, n0), np.zeros(n0)], 1)
+    cfg = dict(n_below=25, n_candidates=C, multivariate=False)
+    eng.set_space(specs)
+    eng.set_history(X, cat, key)
+    fresh = TPEEngine(0)
+    step = [0]
+
+    def check(cols):
+        step[0] += 1
+        u = np.random.RandomState(1000 + step[0]).random_sample(len(cols) * 2 * C)
+        got = eng.suggest_univariate_batch(cols, u, **cfg)
+        fresh.set_space(specs)
+        fresh.set_history(X, cat, key)
+        want = fresh.suggest_univariate_batch(cols, u, **cfg)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w), (step[0], g, w)
+
+    try:
+        allc = list(range(P))
+        check(allc)
+        check(allc)                                     # nothing changed: the orders are reused
+        for i in range(12):                             # plain appends (worse than the below set)
+            x1 = draw(1)
+            k1 = np.array([[rs.uniform(1, 2), 0.0]])
+            eng.append_history(x1, np.zeros(1, np.int8), k1)
+            X, cat, key = np.concatenate([X, x1]), np.concatenate([cat, np.zeros(1, np.int8)]), np.concatenate([key, k1])
+            check(allc)
+        x1, k1 = draw(1), np.array([[0.5, 0.0]])          # enters the below set; another trial moves to the above set
+        eng.append_history(x1, np.zeros(1, np.int8), k1)
+        X, cat, key = np.concatenate([X, x1]), np.concatenate([cat, np.zeros(1, np.int8)]), np.concatenate([key, k1])
+        check(allc)
+        check([0, 2])                                   # fewer columns ...
+        x1, k1 = draw(1), np.array([[1.5, 0.0]])
+        eng.append_history(x1, np.zeros(1, np.int8), k1)
+        X, cat, key = np.concatenate([X, x1]), np.concatenate([cat, np.zeros(1, np.int8)]), np.concatenate([key, k1])
+        check([2, 0, 3])                                # ... then other columns in other slots, one of them stale
+        check(allc)
+        # a RUNNING placeholder (excluded), a later trial finishing before it, then the placeholder completing
+        r_run = len(cat)
+        eng.append_history(np.full((1, P), np.nan), np.full(1, 4, np.int8), np.zeros((1, 2)))
+        X, cat, key = np.concatenate([X, np.full((1, P), np.nan)]), np.concatenate([cat, np.full(1, 4, np.int8)]), \
+            np.concatenate([key, np.zeros((1, 2))])
+        check(allc)
+        x1, k1 = draw(1), np.array([[1.7, 0.0]])
+        eng.append_history(x1, np.zeros(1, np.int8), k1)
+        X, cat, key = np.concatenate([X, x1]), np.concatenate([cat, np.zeros(1, np.int8)]), np.concatenate([key, k1])
+        check(allc)
+        x1, k1 = draw(1), np.array([[1.2, 0.0]])          # the placeholder completes: a row in the MIDDLE appears
+        eng.update_history(x1, np.zeros(1, np.int8), k1, r_run)
+        X[r_run], cat[r_run], key[r_run] = x1[0], 0, k1[0]
+        check(allc)
+        x1, k1 = draw(1), np.array([[1.9, 0.0]])          # a visible row is overwritten: same sizes, other values
+        eng.update_history(x1, np.zeros(1, np.int8), k1, 100)
+        X[100], key[100] = x1[0], k1[0]
+        check(allc)
+        check(allc)
+    finally:
+        fresh.close()
+
+
 def test_config2_full_size_against_the_precomputed_oracle_fixture(eng):
     """BASELINE config 2 at full size: log l(x) and log g(x) of 256 points -- the first 256 candidates the oracle draws
     -- against tests/golden/c2_logpdf.npz (oracle/gen_c2_fixture.py: the chunked oracle, ~6 min of CPU, so it is

@@ -412,13 +412,77 @@ def test_sync_cost_is_proportional_to_the_changes(make_sampler):
     calls = s.sampler._engine.calls
     assert [c[0] for c in calls].count("set_history") == 1
     ups = [c[1] for c in calls if c[0] == "update_history"]
-    assert len(ups) == 40 - 5 - 1 and max(ups) <= 2
+    # one row per trial: uploaded at `tell` time together with the look-ahead suggestion (the placeholder of the
+    # running trial never travels on its own)
+    assert len(ups) in (40 - 5, 40 - 5 + 1) and max(ups) <= 2, ups
+    assert s.sampler.ahead_stats[0] >= 40 - 5 - 2, s.sampler.ahead_stats
     eng = s.sampler._engine
     X, cat, key, _ = s.sampler._rows(s, s.get_trials(deepcopy=False), list(s.sampler._hist.columns),
                                      s.sampler._hist.dists, None)
     n = eng.history_size
     assert n >= 39 and np.array_equal(eng.cat[:39], cat[:39]) and np.array_equal(eng.key[:39], key[:39])
     assert np.array_equal(np.nan_to_num(eng.X[:39], nan=-7.0), np.nan_to_num(X[:39], nan=-7.0))
+
+
+def test_look_ahead_suggestions_are_the_reference_suggestions(make_sampler):
+    """B200TPESampler queues the next joint suggestion at `tell` time (after_trial knows the trial's final state
+    before the storage does, study/_tell.py:163-169) and `sample_relative` collects it -- if and only if the ask is
+    the predicted one.  One scenario walks through what can come between a tell and the next ask: nothing (served),
+    a foreign draw from the sampler's generator, a second tell, asks without tells, a trial told to the sampler but
+    never stored, a pruned and a failed trial, a trial with fewer parameters (the search space shrinks), and the
+    MAXIMIZE direction; C is chosen so that the generator lives on the device for one half of the seeds' asks."""
+    from optuna.trial import TrialState as TS
+
+    def obj_params(t, small=False):
+        x = t.suggest_float("x", -2.0, 2.0)
+        k = t.suggest_int("k", 0, 6)
+        if small:
+            return -(x * x) - 0.1 * k
+        y = t.suggest_float("y", 1e-2, 10.0, log=True)
+        c = t.suggest_categorical("c", ["a", "b", "c"])
+        return -(x * x) - 0.1 * k - math.log(y) ** 2 - (c == "b")
+
+    served = []
+
+    def scenario(sampler):
+        s = optuna.create_study(sampler=sampler, direction="maximize")
+        for _ in range(12):                               # startup + plain sequential loop
+            t = s.ask()
+            s.tell(t, obj_params(t))
+        sampler._rng.rng.random_sample(5)                 # somebody else draws between a tell and the ask
+        t = s.ask()
+        s.tell(t, obj_params(t))
+        t1, t2 = s.ask(), s.ask()                         # asks without tells, then two tells in a row
+        v1, v2 = obj_params(t1), obj_params(t2)
+        s.tell(t2, v2)
+        s.tell(t1, v1)
+        t = s.ask()
+        obj_params(t)
+        frozen = s._storage.get_trial(t._trial_id)
+        sampler.after_trial(s, frozen, TS.COMPLETE, [123.0])   # told to the sampler, never stored (still RUNNING)
+        u = s.ask()
+        s.tell(u, obj_params(u))
+        s.tell(t, state=TS.FAIL)
+        t = s.ask()
+        obj_params(t)
+        t.report(0.5, 0)
+        t.report(-0.25, 2)
+        s.tell(t, state=TS.PRUNED)
+        for _ in range(3):
+            t = s.ask()
+            s.tell(t, obj_params(t))
+        t = s.ask()
+        s.tell(t, obj_params(t, small=True))              # the intersection search space shrinks
+        for _ in range(4):
+            t = s.ask()
+            s.tell(t, obj_params(t))
+        if hasattr(sampler, "ahead_stats"):
+            served.append(tuple(sampler.ahead_stats))
+        return s
+
+    for C in (24, 2048):   # uniforms drawn on the host / on the device (>= DEVICE_RNG_MIN with 4 parameters)
+        over_seeds(scenario, make_sampler, True, dict(seed=31, multivariate=True, n_startup_trials=6, n_ei_candidates=C))
+    assert served and all(ok >= 8 and dropped >= 4 for ok, dropped in served), served
 
 
 def test_batched_ask_equals_sequential_asks(make_sampler):
