@@ -89,12 +89,14 @@ struct Estimator {
   DevBuf cls, dtab, offgrid;   // tabulated discrete columns (multivariate)
   DevBuf tabm, hb, ckk;        // tensor-core kernel: fragment-major table, |mu''|^2 / 2, cst - |mu''|^2 / 2
   DevBuf uord, us32, usmi, usc, umeta;  // univariate 1-D grid (tpe_uni.cuh): sorted order and sorted tables
+  DevBuf ucoef, ubox, ubstart;          // ... and the fast Gauss transform of the floor-bandwidth kernels
+  bool fgt = false;
   bool uni_ready = false;
   bool mma = false;            // tables above are valid for this build
   bool screen_ready = false;
   int nsplit = 0;
   void release() {
-    for (DevBuf* b : {&uord, &us32, &usmi, &usc, &umeta, &tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
+    for (DevBuf* b : {&uord, &us32, &usmi, &usc, &umeta, &ucoef, &ubox, &ubstart, &tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
                       &part, &fix})
       b->release();
   }
@@ -997,10 +999,25 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
     CU(e.usmi.ensure((size_t)ntiles * kUniTile * 16));
     CU(e.usc.ensure((size_t)ntiles * kUniTile * 8));
     CU(e.umeta.ensure((size_t)ntiles * sizeof(UniTileMeta)));
+    // large estimators: the kernels at the bandwidth floor go through the fast Gauss transform (k_fgt_*)
+    static const int64_t fgt_min = [] { const char* v = getenv("TPE_FGT_MIN_K"); return v ? atoll(v) : 1024ll; }();
+    e.fgt = ctx->cfg.magic_clip && K >= fgt_min;
+    if (e.fgt) {
+      CU(e.ucoef.ensure((size_t)kFgtMaxBoxes * kFgtTerms * 8));
+      CU(e.ubox.ensure((size_t)kFgtMaxBoxes * sizeof(FgtBox)));
+      CU(e.ubstart.ensure((size_t)(kFgtMaxBoxes + 1) * 4));
+    }
     k_uni_tables<<<(unsigned)ntiles, kUniTile, 0, st>>>(e.uord.as<int32_t>(), e.mu.as<double>(), e.sigma.as<double>(),
                                                         e.cst.as<double>(), ctx->cols.as<ColMeta>(), K, e.us32.as<float4>(),
-                                                        e.usmi.as<double2>(), e.usc.as<double>(), e.umeta.as<UniTileMeta>());
+                                                        e.usmi.as<double2>(), e.usc.as<double>(), e.umeta.as<UniTileMeta>(),
+                                                        e.fgt ? 1 : 0, ctx->cfg.magic_clip, e.ubstart.as<int32_t>());
     ctx->launch_counter++;
+    if (e.fgt) {
+      k_fgt_coeff<<<kFgtMaxBoxes, 128, 0, st>>>(e.uord.as<int32_t>(), e.mu.as<double>(), e.sigma.as<double>(),
+                                                e.cst.as<double>(), ctx->cols.as<ColMeta>(), K, ctx->cfg.magic_clip,
+                                                e.ubstart.as<int32_t>(), e.ucoef.as<double>(), e.ubox.as<FgtBox>());
+      ctx->launch_counter++;
+    }
     e.uni_ready = true;
   }
   CU(cudaGetLastError());
@@ -1032,14 +1049,21 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
                                                                      ctx->uxs.as<double>(), ctx->ucidx.as<int32_t>(), C, skip,
                                                                      e.part.as<double2>());
     ctx->launch_counter++;
-    ctx->last_kernel = "k_uni_grid<sorted 1-D>";
+    if (e.fgt) {
+      k_fgt_eval<<<(unsigned)((C * 32 + 255) / 256), 256, 0, st>>>(
+          e.ucoef.as<double>(), e.ubox.as<FgtBox>(), e.ubstart.as<int32_t>(), e.us32.as<float4>(), e.usmi.as<double2>(),
+          e.usc.as<double>(), e.mu.as<double>(), e.sigma.as<double>(), e.cst.as<double>(), ctx->cols.as<ColMeta>(), K,
+          ctx->cfg.magic_clip, ctx->xT.as<double>(), C, e.part.as<double2>() + ctx->ct_stride);
+      ctx->launch_counter++;
+    }
+    ctx->last_kernel = e.fgt ? "k_uni_grid<sorted 1-D> + k_fgt_eval" : "k_uni_grid<sorted 1-D>";
     if (after_main) CU(cudaEventRecord(after_main, st));
     CU(e.fix.ensure((size_t)ctx->ct_stride * 16));
     k_logpdf_prior_fix<<<(unsigned)((Ct * 32 + 255) / 256), 256, 0, st>>>(
         ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
         e.cst.as<double>(), K, e.tab.as<double>(), nullptr, ctx->oob.as<uint8_t>(), e.fix.as<double2>());
     ctx->launch_counter++;
-    e.nsplit = 1;
+    e.nsplit = e.fgt ? 2 : 1;
     CU(cudaGetLastError());
     return TPE_OK;
   }

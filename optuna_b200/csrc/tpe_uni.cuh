@@ -22,6 +22,27 @@ namespace tpe {
 
 constexpr int kUniTile = 128;
 
+// e^x for -700 <= x <= 700 in ~17 instructions: x = (64 n + j) ln2 / 64 + r, |r| <= ln2 / 128;
+// e^x = 2^n * 2^(j/64) * P5(r) with a 64-entry table in shared memory (filled by the CTA: exp2(j / 64), 1 ulp) and a
+// degree-5 Taylor polynomial (truncation 3.5e-17).  The two-term Cody-Waite reduction is exact for |x| < 700
+// (ln2_hi / 64 keeps 21 trailing zero bits).  Relative error <= 3e-16.
+__device__ __forceinline__ double uni_exp(double x, const double* __restrict__ tab64) {
+  const double t = fma(x, 92.332482616893656768, 6755399441055744.0);
+  const int ni = __double2loint(t);
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, -1.08304246932675596327e-02, x);
+  r = fma(nf, -2.98158582698529328128e-12, r);
+  double p = 8.33333333333333333333e-03;
+  p = fma(p, r, 4.16666666666666666667e-02);
+  p = fma(p, r, 1.66666666666666666667e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double y = tab64[ni & 63] * p;
+  return __hiloint2double(__double2hiint(y) + ((ni >> 6) << 20), __double2loint(y));
+}
+
+
 struct UniTileMeta {
   double mu_lo, mu_hi;   // range of (mu - ctr) over the tile
   double smax, cmax;     // largest sigma, largest constant (ln w - ln sqrt(2 pi) - M(a, b) - ln sigma)
@@ -30,15 +51,44 @@ struct UniTileMeta {
 // Sorted tables of one estimator column: position j holds kernel order[j].
 //   s32[j] = (m'' = (mu - ctr) / sigma, 1 / sigma, cst, w) in fp32, w = rounding bound of the fp32 z (see k_uni_grid)
 //   smi[j] = (m'', 1 / sigma), sc[j] = cst in fp64 (the PAIR table of k_const / k_logpdf_fast, re-ordered)
+// fgt != 0 (large estimators, see k_fgt_coeff): kernels whose bandwidth is the clip floor are summed by the fast
+// Gauss transform; here they are muted in the screening table (cst = -inf: never pass) and left out of cmax, so
+// k_uni_grid evaluates the others only.  bstart[q] = first sorted position whose box index is >= q.
+struct FgtGeom {
+  double klow, scale, bw;   // scale = sigma_floor * sqrt(2); box width bw = scale / 4
+  double lo;                // sigma_floor
+  int nb;
+  __device__ __forceinline__ void init(const ColMeta& cm, int64_t n, bool magic_clip) {
+    double hi;
+    sigma_limits(cm, n, magic_clip, lo, hi);
+    klow = cm.klow;
+    scale = lo * 1.4142135623730951;
+    bw = 0.25 * scale;
+    const double q = ceil(hi / bw);
+    nb = (q < 1.0) ? 1 : ((q > 287.0) ? 287 : (int)q);
+  }
+  __device__ __forceinline__ int box_of(double m) const {
+    const double q = floor((m - klow) / bw);
+    return (q < 0.0) ? 0 : ((q >= (double)nb) ? nb - 1 : (int)q);
+  }
+  __device__ __forceinline__ double centre(int b) const { return klow + ((double)b + 0.5) * bw; }
+};
+constexpr int kFgtMaxBoxes = 288;
+constexpr int kFgtTerms = 24;          // Taylor terms per box (remainder <= 4e-14 of the box's own sum for |y| <= 9)
+constexpr double kFgtYmax = 9.0;       // boxes further away (in units of sigma_floor * sqrt 2) are summed directly
+
 __global__ void __launch_bounds__(kUniTile)
 k_uni_tables(const int32_t* __restrict__ order, const double* __restrict__ mu, const double* __restrict__ sigma,
              const double* __restrict__ cst, const ColMeta* __restrict__ cols, int64_t K, float4* __restrict__ s32,
-             double2* __restrict__ smi, double* __restrict__ sc, UniTileMeta* __restrict__ meta) {
+             double2* __restrict__ smi, double* __restrict__ sc, UniTileMeta* __restrict__ meta, int fgt,
+             int magic_clip, int32_t* __restrict__ bstart) {
   __shared__ double r_lo[4], r_hi[4], r_s[4], r_c[4];
   const ColMeta cm = cols[0];
   const double ctr = TPE_MUL(0.5, TPE_ADD(cm.klow, cm.khigh));
   const double half = 0.5 * (cm.khigh - cm.klow);
   const int64_t pos = (int64_t)blockIdx.x * kUniTile + threadIdx.x;
+  FgtGeom g;
+  if (fgt) g.init(cm, K - 1, magic_clip != 0);
   double lo = INFINITY, hi = -INFINITY, sm = 0.0, cmx = -INFINITY;
   if (pos < K) {
     const int64_t k = order[pos];
@@ -47,12 +97,20 @@ k_uni_tables(const int32_t* __restrict__ order, const double* __restrict__ mu, c
     const double mm = TPE_MUL(TPE_SUB(m, ctr), inv);
     smi[pos] = make_double2(mm, inv);
     sc[pos] = c;
+    const bool regular = fgt && k != K - 1 && s == g.lo;
     // |z_fp32 - z| <= 2^-24 (2 |x'| inv + |m''| + |z|) <= 2^-22 Z with Z = (range / 2) inv >= |x' inv|, |m''|
     const float w = __double2float_ru(half * inv * 2.5e-7);
-    s32[pos] = make_float4(__double2float_rn(mm), __double2float_rn(inv), __double2float_rn(c), w);
+    s32[pos] = make_float4(__double2float_rn(mm), __double2float_rn(inv), regular ? -INFINITY : __double2float_rn(c), w);
     lo = hi = m - ctr;
     sm = s;
-    cmx = c;
+    cmx = regular ? -INFINITY : c;
+    if (fgt) {
+      const int b = g.box_of(m);
+      const int bprev = pos > 0 ? g.box_of(mu[order[pos - 1]]) : -1;
+      for (int q = bprev + 1; q <= b; ++q) bstart[q] = (int32_t)pos;
+      if (pos == K - 1)
+        for (int q = b + 1; q <= g.nb; ++q) bstart[q] = (int32_t)K;
+    }
   } else {
     smi[pos] = make_double2(0.0, 0.0);
     sc[pos] = -INFINITY;
@@ -76,6 +134,168 @@ k_uni_tables(const int32_t* __restrict__ order, const double* __restrict__ mu, c
     t.cmax = fmax(fmax(r_c[0], r_c[1]), fmax(r_c[2], r_c[3]));
     meta[blockIdx.x] = t;
   }
+}
+
+// ---- fast Gauss transform for the kernels at the bandwidth floor -------------------------------------------------
+// With thousands of observations nearly every kernel of a 1-D estimator has sigma = sigma_floor = range / 100
+// (parzen_estimator.py:220-228: the neighbour gaps are far smaller).  Their part of the mixture,
+//     sum_j exp(c_j) exp(-(x - mu_j)^2 / (2 sigma^2)),
+// is a Gauss transform with ONE bandwidth.  Boxes of width sigma sqrt(2) / 4 along the axis; for the sources of box B
+// (centre c_B, t_j = (mu_j - c_B) / (sigma sqrt 2), |t_j| <= 1/8) and a target y = (x - c_B) / (sigma sqrt 2):
+//     exp(-(y - t)^2) = exp(-y^2) sum_n H_n(y) t^n / n!          (generating function of the Hermite polynomials)
+//     box sum         = exp(ref_B - y^2) sum_n A_n H_n(y),   A_n = sum_j exp(c_j - ref_B) t_j^n / n!
+// so a candidate costs (boxes in reach) x kFgtTerms multiply-adds instead of one exponential per kernel in reach.
+// Truncation after 24 terms: remainder <= |h_24(u)| |t|^24 / 24! with h_n = H_n exp(-u^2); by Cramer's bound
+// (|h_n(u)| <= 1.09 2^(n/2) sqrt(n!) exp(-u^2 / 2)) that is <= 1e-18 of the box's own sum for |y| <= 7, and with
+// |H_n(u)| <= (2u)^n beyond the last zero (u >= 7) it is <= (2 |y| / 8)^24 / 24! exp(|y| / 2) <= 4e-14 up to
+// |y| = 9 (kFgtYmax); boxes further out that still matter (a candidate far from every observation) are summed
+// directly.  A box is left out when its upper bound A_0 exp(ref - (|y| - 1/8)^2) lies 30 + ln(#boxes) below the
+// largest lower bound A_0 exp(ref - (|y| + 1/8)^2) of any box or below the prior kernel's term: together <= 1e-13 of
+// the sum, the truncation rule the pair kernels use.  Everything is summed in a fixed order.
+struct FgtBox {
+  double ref;     // largest c_j of the box's floor-bandwidth kernels (-inf: none)
+  double lnw;     // ref + ln A_0
+};
+
+// grid = boxes, 128 threads
+__global__ void __launch_bounds__(128)
+k_fgt_coeff(const int32_t* __restrict__ order, const double* __restrict__ mu, const double* __restrict__ sigma,
+            const double* __restrict__ cst, const ColMeta* __restrict__ cols, int64_t K, int magic_clip,
+            const int32_t* __restrict__ bstart, double* __restrict__ coef, FgtBox* __restrict__ box) {
+  __shared__ double s_red[4][kFgtTerms];
+  __shared__ double s_ref;
+  FgtGeom g;
+  g.init(cols[0], K - 1, magic_clip != 0);
+  const int b = blockIdx.x;
+  if (b >= g.nb) {
+    if (threadIdx.x == 0) box[b] = FgtBox{-INFINITY, -INFINITY};
+    return;
+  }
+  const int p0 = bstart[b], p1 = bstart[b + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double ref = -INFINITY;
+  for (int p = p0 + threadIdx.x; p < p1; p += 128) {
+    const int k = order[p];
+    if (k != K - 1 && sigma[k] == g.lo) ref = fmax(ref, cst[k]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ref = fmax(ref, __shfl_xor_sync(0xffffffffu, ref, o));
+  if (lane == 0) s_red[warp][0] = ref;
+  __syncthreads();
+  if (threadIdx.x == 0) s_ref = fmax(fmax(s_red[0][0], s_red[1][0]), fmax(s_red[2][0], s_red[3][0]));
+  __syncthreads();
+  ref = s_ref;
+  __syncthreads();
+  double a[kFgtTerms];
+#pragma unroll
+  for (int n = 0; n < kFgtTerms; ++n) a[n] = 0.0;
+  const double cb = g.centre(b), inv = 1.0 / g.scale;
+  for (int p = p0 + threadIdx.x; p < p1; p += 128) {
+    const int k = order[p];
+    if (k == K - 1 || sigma[k] != g.lo) continue;
+    const double t = (mu[k] - cb) * inv;
+    double pw = exp(cst[k] - ref);
+#pragma unroll
+    for (int n = 0; n < kFgtTerms; ++n) {
+      a[n] += pw;
+      pw *= t * (1.0 / (double)(n + 1));
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < kFgtTerms; ++n) {
+    double v = a[n];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp][n] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kFgtTerms) {
+    const int n = threadIdx.x;
+    const double v = (s_red[0][n] + s_red[1][n]) + (s_red[2][n] + s_red[3][n]);
+    coef[(size_t)b * kFgtTerms + n] = v;
+    if (n == 0) box[b] = FgtBox{ref, (ref > -INFINITY) ? ref + log(v) : -INFINITY};
+  }
+}
+
+// part[c] = (reference, sum) of the floor-bandwidth kernels for candidate c; one warp per candidate.
+//   xT [C] kernel-space coordinate of the candidates (log applied), in ask order
+__global__ void __launch_bounds__(256)
+k_fgt_eval(const double* __restrict__ coef, const FgtBox* __restrict__ box, const int32_t* __restrict__ bstart,
+           const float4* __restrict__ s32, const double2* __restrict__ smi, const double* __restrict__ sc,
+           const double* __restrict__ mu,
+           const double* __restrict__ sigma, const double* __restrict__ cst, const ColMeta* __restrict__ cols,
+           int64_t K, int magic_clip, const double* __restrict__ xT, int C, double2* __restrict__ part) {
+  __shared__ double s_e64[64];
+  if (threadIdx.x < 64) s_e64[threadIdx.x] = exp2((double)threadIdx.x * 0.015625);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int c = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (c >= C) return;
+  const ColMeta cm = cols[0];
+  FgtGeom g;
+  g.init(cm, K - 1, magic_clip != 0);
+  const double x = xT[c];
+  const double inv = 1.0 / g.scale;
+  // floor of the scale: the prior kernel's term (it is summed by k_uni_grid; here it only decides what is negligible)
+  double best;
+  {
+    const double zp = (x - mu[K - 1]) / sigma[K - 1];
+    best = cst[K - 1] - 0.5 * zp * zp;
+    if (!(best > -INFINITY)) best = -INFINITY;
+  }
+  for (int b = lane; b < g.nb; b += 32) {
+    const FgtBox bx = box[b];
+    if (!(bx.lnw > -INFINITY)) continue;
+    const double y = fabs((x - g.centre(b)) * inv) + 0.125;
+    best = fmax(best, bx.lnw - y * y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (!(best > -INFINITY)) {                    // NaN candidate / no kernels at all
+    if (lane == 0) part[c] = make_double2(-INFINITY, 0.0);
+    return;
+  }
+  const double drop = 30.0 + log((double)g.nb);
+  const double ctr = TPE_MUL(0.5, TPE_ADD(cm.klow, cm.khigh));
+  double sum = 0.0;
+  for (int b = lane; b < g.nb; b += 32) {
+    const FgtBox bx = box[b];
+    if (!(bx.lnw > -INFINITY)) continue;
+    const double y = (x - g.centre(b)) * inv;
+    const double ay = fabs(y);
+    const double near = fmax(ay - 0.125, 0.0);
+    if (bx.lnw - near * near < best - drop) continue;
+    if (ay <= kFgtYmax) {
+      const double* __restrict__ a = coef + (size_t)b * kFgtTerms;
+      // sum_n A_n H_n(y):  H_0 = 1, H_1 = 2y, H_(n+1) = 2y H_n - 2n H_(n-1)
+      const double y2 = 2.0 * y;
+      double hm = 1.0, h = y2;
+      double acc = fma(a[1], h, a[0]);
+#pragma unroll
+      for (int n = 1; n < kFgtTerms - 1; ++n) {
+        const double hn = fma(y2, h, -2.0 * (double)n * hm);
+        hm = h;
+        h = hn;
+        acc = fma(a[n + 1], h, acc);
+      }
+      sum += acc * uni_exp(fmax(bx.ref - y * y - best, -700.0), s_e64);
+    } else {
+      // a candidate far from this box that still counts (nothing nearer): its kernels one by one
+      const int p0 = bstart[b], p1 = bstart[b + 1];
+      const double xc = x - ctr;
+      double part_sum = 0.0;
+      for (int p = p0; p < p1; ++p) {
+        if (s32[p].z > -INFINITY) continue;     // not at the floor: k_uni_grid has it
+        const double2 mi = smi[p];
+        const double tt = fma(xc, mi.y, -mi.x);
+        part_sum += uni_exp(fmax(fma(-0.5 * tt, tt, sc[p]) - best, -700.0), s_e64);
+      }
+      sum += part_sum;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) part[c] = (sum > 0.0) ? make_double2(best, sum) : make_double2(-INFINITY, 0.0);
 }
 
 // The candidates of one ask in ascending kernel-space order: xs[i] = x' = x - ctr of the i-th smallest,
@@ -118,26 +338,6 @@ k_uni_sort_cands(const double* __restrict__ xT, int C, const ColMeta* __restrict
       cidx[i] = (i < C) ? si[i] : -1;
     }
   }
-}
-
-// e^x for -700 <= x <= 700 in ~17 instructions: x = (64 n + j) ln2 / 64 + r, |r| <= ln2 / 128;
-// e^x = 2^n * 2^(j/64) * P5(r) with a 64-entry table in shared memory (filled by the CTA: exp2(j / 64), 1 ulp) and a
-// degree-5 Taylor polynomial (truncation 3.5e-17).  The two-term Cody-Waite reduction is exact for |x| < 700
-// (ln2_hi / 64 keeps 21 trailing zero bits).  Relative error <= 3e-16.
-__device__ __forceinline__ double uni_exp(double x, const double* __restrict__ tab64) {
-  const double t = fma(x, 92.332482616893656768, 6755399441055744.0);
-  const int ni = __double2loint(t);
-  const double nf = t - 6755399441055744.0;
-  double r = fma(nf, -1.08304246932675596327e-02, x);
-  r = fma(nf, -2.98158582698529328128e-12, r);
-  double p = 8.33333333333333333333e-03;
-  p = fma(p, r, 4.16666666666666666667e-02);
-  p = fma(p, r, 1.66666666666666666667e-01);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  const double y = tab64[ni & 63] * p;
-  return __hiloint2double(__double2hiint(y) + ((ni >> 6) << 20), __double2loint(y));
 }
 
 // part[cidx] = (reference, sum of e^(L - reference)) of the 1-D mixture for every candidate.
@@ -223,7 +423,7 @@ k_uni_grid(const float4* __restrict__ s32, const double2* __restrict__ smi, cons
         const float tf = fmaf(xf, v.y, -v.x);
         const float Lf = fmaf(-0.5f * tf, tf, v.z);
         const float ub = fmaf(fabsf(tf) + 1.0f, v.w, Lf) + 2.5e-7f * (fabsf(v.z) + fabsf(Lf));
-        pass[u] = !(ub < thrf) && live;      // cannot be dismissed in fp32
+        pass[u] = !(ub < thrf) && live && v.z > -INFINITY;   // cannot be dismissed in fp32 (-inf: muted / padding)
         any = any || pass[u];
       }
       if (!__any_sync(0xffffffffu, any)) continue;

@@ -783,6 +783,51 @@ def test_univariate_batch_incremental_orders_equal_fresh_sorts(eng):
         fresh.close()
 
 
+@pytest.mark.parametrize("layout", ["dense", "clusters", "corner", "log"])
+def test_univariate_fast_gauss_transform_of_the_floor_bandwidth_kernels(eng, layout):
+    """Large 1-D estimators: the kernels whose bandwidth is the clip floor are summed by a fast Gauss transform
+    (k_fgt_coeff / k_fgt_eval), the others pair by pair (k_uni_grid).  log g at points all over the support --
+    between the observations, in gaps, far from every observation -- against the oracle: 1e-12, the float
+    tolerance of BASELINE.md section 3.  Layouts: every kernel at the floor; clusters with gaps (both kinds of
+    kernels, boxes without kernels); all observations in one corner (far boxes that still count, the prior
+    kernel taking over); a log-scaled column."""
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState({"dense": 1, "clusters": 2, "corner": 3, "log": 4}[layout])
+    n = 12_000
+    lo, hi, log = (-3.0, 5.0, False) if layout != "log" else (1e-4, 50.0, True)
+    if layout == "dense":
+        x = rs.uniform(lo, hi, n)
+    elif layout == "clusters":
+        x = np.concatenate([rs.normal(-2.0, 0.05, n // 2), rs.normal(1.0, 0.3, n // 2 - 40), rs.uniform(2.5, 5.0, 40)])
+        x = np.clip(x, lo, hi)
+    elif layout == "corner":
+        x = lo + (hi - lo) * 0.04 * rs.beta(2, 5, n)
+    else:
+        x = np.exp(rs.uniform(np.log(lo), np.log(hi), n))
+    key = np.stack([rs.uniform(size=n), np.zeros(n)], 1)
+    cat = np.zeros(n, np.int8)
+    eng.set_space([ParamSpec(kind=0, low=lo, high=hi, log=log)])
+    eng.set_history(x[:, None], cat, key)
+    prm = [orc.Param("float", lo, hi, None, log)]
+    pts = np.linspace(lo, hi, 1500) if not log else np.exp(np.linspace(np.log(lo), np.log(hi), 1500))
+    pts = np.concatenate([pts, x[:300], [lo, hi]])[:, None]
+    for prior_weight in (1.0, 1e-9):
+        cfg = orc.Config(multivariate=False, stable_sort=True, prior_weight=prior_weight)
+        eng.prepare([0], n_below=25, n_candidates=24, multivariate=False, prior_weight=prior_weight)
+        eng.build()
+        _, above = eng.get_split()
+        mix = orc.build_mixture(x[above][:, None], prm, cfg, None)
+        want = orc.mixture_log_pdf(mix, pts)
+        for lo_i in range(0, len(pts), 4096):
+            got = eng.logpdf(1, pts[lo_i: lo_i + 4096])
+            close(got, want[lo_i: lo_i + 4096], 0, 1e-12)
+        assert "k_fgt_eval" in eng.last_logpdf_kernel()
+        _, _, sg = eng.get_mixture(1)
+        floor = (np.log(hi) - np.log(lo) if log else hi - lo) / 100.0
+        at_floor = np.mean(np.isclose(sg[:-1, 0], floor, rtol=1e-14, atol=0))
+        assert (at_floor > 0.99) if layout in ("dense", "corner", "log") else (0.5 < at_floor < 0.999), at_floor
+
+
 def test_config2_full_size_against_the_precomputed_oracle_fixture(eng):
     """BASELINE config 2 at full size: log l(x) and log g(x) of 256 points -- the first 256 candidates the oracle draws
     -- against tests/golden/c2_logpdf.npz (oracle/gen_c2_fixture.py: the chunked oracle, ~6 min of CPU, so it is
