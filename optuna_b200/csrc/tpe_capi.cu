@@ -20,6 +20,7 @@
 #include "tpe_kernels.cuh"
 #include "tpe_motpe_kernels.cuh"
 #include "tpe_uni.cuh"
+#include "tpe_mixed.cuh"
 // Lab build (-DTPE_LAB): the experimental grid kernels and the timing-attribution variants measured in
 // profiles/r1_variants.md / r2_variants.md, selectable by environment variables.  Some of them switch parts of the
 // log-sum-exp off (wrong results by design).  The product library contains none of them.
@@ -91,12 +92,15 @@ struct Estimator {
   DevBuf uord, us32, usmi, usc, umeta;  // univariate 1-D grid (tpe_uni.cuh): sorted order and sorted tables
   DevBuf ucoef, ubox, ubstart;          // ... and the fast Gauss transform of the floor-bandwidth kernels
   bool fgt = false;
+  DevBuf mxc, mxd;                      // mixed spaces, many candidates (tpe_mixed.cuh): kernel-minor tables
+  bool mixed = false;
+  int64_t mix_kstride = 0;
   bool uni_ready = false;
   bool mma = false;            // tables above are valid for this build
   bool screen_ready = false;
   int nsplit = 0;
   void release() {
-    for (DevBuf* b : {&uord, &us32, &usmi, &usc, &umeta, &ucoef, &ubox, &ubstart, &tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
+    for (DevBuf* b : {&uord, &us32, &usmi, &usc, &umeta, &ucoef, &ubox, &ubstart, &mxc, &mxd, &tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
                       &part, &fix})
       b->release();
   }
@@ -157,7 +161,7 @@ struct tpe_ctx {
       mo_uniq, mo_nuniq, mo_ref, mo_removed, mo_contrib, mo_state, mo_arena, mo_chosen, mo_diag, mo_w, mo_table, mo_sample,
       mo_surv, mo_nsurv, mo_fv, mo_ps, mo_map, mo_front, mo_head;
   bool mo_weights_ready = false;
-  std::vector<uint8_t> col_missing, col_oor;
+  std::vector<uint8_t> col_missing, col_oor, col_offgrid;   // col_offgrid: a step column holds a value off its grid
   bool history_set = false;
 
   // current call
@@ -192,6 +196,11 @@ struct tpe_ctx {
   std::vector<tpe_ctx*> uni_sub;
   cudaEvent_t ev_uni = nullptr;
   bool is_sub = false;
+  bool mixed_ok = false;         // the selected columns suit k_logpdf_mixed (setup_columns)
+  std::vector<MixCol> mixcols_h;
+  DevBuf mixcols;
+  int mix_ncont = 0, mix_nd = 0, mix_tabd = 0;
+  bool user_points = false;      // the resident candidates came through tpe_logpdf, not from k_sample
   bool deferred = false;         // tpe_sample_and_select_async issued, tpe_collect not yet called
   bool issued_dev_rng = false;
   void* res_host = nullptr;      // page-locked staging of deferred results
@@ -755,6 +764,11 @@ void scan_missing(tpe_ctx* ctx, const double* X, const int8_t* category, int64_t
       if (v != v) { ctx->col_missing[j] = 1; continue; }
       const tpe_param_desc& d = ctx->space[j];
       if (d.kind != TPE_KIND_CAT && (v < d.low || v > d.high)) ctx->col_oor[j] = 1;
+      if (d.kind != TPE_KIND_CAT && d.has_step) {   // the test k_build_mv applies to tabulated columns
+        const double gsz = floor((d.high - d.low) / d.step + 0.5) + 1.0;
+        const double g = rint((v - d.low) / d.step);
+        if (!(g >= 0.0 && g < gsz && d.low + g * d.step == v)) ctx->col_offgrid[j] = 1;
+      }
     }
   }
 }
@@ -813,6 +827,18 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
         ctx->dtab_doubles ? e.cls.as<int32_t>() : nullptr, ctx->dtab_doubles ? e.offgrid.as<int>() : nullptr,
         e.mma ? e.tabm.as<double>() : nullptr, e.mma ? e.hb.as<double>() : nullptr);
     ctx->launch_counter++;
+    e.mixed = ctx->mixed_ok && K - 1 >= 2048;
+    if (e.mixed) {
+      const int ncp = (ctx->mix_ncont + 1) / 2, nd4 = (ctx->mix_nd + 3) / 4;
+      e.mix_kstride = round_up<int64_t>(K - 1, 32);
+      CU(e.mxc.ensure((size_t)std::max(ncp, 1) * e.mix_kstride * 16));
+      CU(e.mxd.ensure((size_t)std::max(nd4, 1) * e.mix_kstride * 8));
+      k_mixed_tables<<<grid_for(e.mix_kstride, 256, 1 << 20), 256, 0, st>>>(
+          ctx->mixcols.as<MixCol>(), ctx->mix_ncont, ctx->mix_nd, ctx->cols.as<ColMeta>(), pc, e.mu.as<double>(),
+          e.sigma.as<double>(), ctx->dtab_doubles ? e.cls.as<int32_t>() : nullptr, K - 1, e.mix_kstride,
+          e.mxc.as<double2>(), e.mxd.as<ushort4>());
+      ctx->launch_counter++;
+    }
   } else {
     k_mu<<<grid_for(K * pc, 256, cap), 256, 0, st>>>(ctx->X.as<double>(), (int32_t)ctx->space.size(),
                                                      e.rows.as<int64_t>(), n, ctx->cols.as<ColMeta>(), pc,
@@ -1024,6 +1050,17 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
   return TPE_OK;
 }
 
+// k_logpdf_mixed: candidates per CTA that fit the shared memory (0: none do), and the bytes they take
+size_t mixed_smem(const tpe_ctx* ctx, int CB) {
+  const int ncp = (ctx->mix_ncont + 1) / 2, nd4 = (ctx->mix_nd + 3) / 4;
+  return (size_t)CB * (2 * ncp + ctx->mix_tabd + 1) * 8 + (size_t)nd4 * 16 + 16;
+}
+int mixed_cb(const tpe_ctx* ctx) {
+  for (int CB : {8, 4, 2})
+    if (mixed_smem(ctx, CB) <= 200 * 1024) return CB;
+  return 0;
+}
+
 // log-density of the Ct resident candidates under estimator `which`: fills e.part (k-split
 // partials) and, for out-of-support candidates, e.fix.
 int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nullptr) {
@@ -1184,6 +1221,53 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     ctx->launch_counter++;
     if (cst_mode) nsplit += 1;
     e.nsplit = (int)nsplit;
+  } else if (e.mixed && !ctx->user_points && Ct >= 64 && mixed_cb(ctx) > 0) {
+    // mixed space, many candidates: kernel-minor tables, the candidates' table rows in shared memory (tpe_mixed.cuh)
+    if (ctx->dtab_doubles) {
+      int64_t rows_max = 1;
+      for (const ColMeta& cm : ctx->cols_h)
+        if (cm.grid > 0) rows_max = std::max<int64_t>(rows_max, (int64_t)std::min<int64_t>(Ct, cm.grid) * (cm.grid + 1));
+      const unsigned gx = (unsigned)std::min<int64_t>((rows_max + 255) / 256, ctx->sm_count * 4);
+      k_disc_tables<<<dim3(gx, (unsigned)ctx->pc), 256, 0, st>>>(ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(),
+                                                                 e.sigma.as<double>(), K, ctx->S.as<double>(), Ct,
+                                                                 e.dtab.as<double>());
+      ctx->launch_counter++;
+    }
+    const int CB = mixed_cb(ctx);
+    const int64_t nx = (Ct + CB - 1) / CB;
+    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>(32, (2ll * ctx->sm_count + nx - 1) / nx));
+    const int64_t kps = round_up<int64_t>((K - 1 + nsplit - 1) / nsplit, 512);
+    nsplit = (K - 1 + kps - 1) / kps;
+    CU(e.part.ensure((size_t)(nsplit + 1) * ctx->ct_stride * 16));
+    CU(e.fix.ensure((size_t)ctx->ct_stride * 16));
+    const size_t smem = mixed_smem(ctx, CB);
+    const double skip = std::min(46.0, log((double)std::max<int64_t>(K, 1)) + 30.0);
+#define TPE_MIXED_LAUNCH(CBV)                                                                                          \
+    do {                                                                                                               \
+      static bool attr_done = false;                                                                                   \
+      if (!attr_done) {                                                                                                \
+        CU(cudaFuncSetAttribute(k_logpdf_mixed<CBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));        \
+        attr_done = true;                                                                                              \
+      }                                                                                                                \
+      k_logpdf_mixed<CBV><<<dim3((unsigned)nx, (unsigned)nsplit), 512, smem, st>>>(                                    \
+          ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, ctx->mixcols.as<MixCol>(), ctx->mix_ncont,        \
+          ctx->mix_nd, ctx->mix_tabd, e.sigma.as<double>(), e.cst.as<double>(), K - 1, e.mix_kstride, kps,             \
+          e.mxc.as<double2>(), e.mxd.as<ushort4>(), e.tab.as<double>(), e.dtab.as<double>(), ctx->oob.as<uint8_t>(),   \
+          skip, e.part.as<double2>(), ctx->ct_stride);                                                                 \
+    } while (0)
+    if (CB == 8) TPE_MIXED_LAUNCH(8);
+    else if (CB == 4) TPE_MIXED_LAUNCH(4);
+    else TPE_MIXED_LAUNCH(2);
+#undef TPE_MIXED_LAUNCH
+    ctx->launch_counter++;
+    ctx->last_kernel = "k_logpdf_mixed";
+    if (after_main) CU(cudaEventRecord(after_main, st));
+    k_logpdf_prior_fix<<<(unsigned)((Ct * 32 + 255) / 256), 256, 0, st>>>(
+        ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
+        e.cst.as<double>(), K, e.tab.as<double>(), e.part.as<double2>() + nsplit * ctx->ct_stride, ctx->oob.as<uint8_t>(),
+        e.fix.as<double2>(), 0);
+    ctx->launch_counter++;
+    e.nsplit = (int)nsplit + 1;
   } else {
     // pair-parallel generic kernel: grid = (candidates, kernel chunks of 256 * kpt)
     int kpt = 1;
@@ -1289,7 +1373,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed, &ctx->mo_table,
                     &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv, &ctx->mo_fv, &ctx->mo_ps, &ctx->mo_map, &ctx->mo_front, &ctx->mo_head,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
-                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->uxs, &ctx->ucidx, &ctx->uni_prev_rows, &ctx->uni_mode, &ctx->uni_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
+                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->mixcols, &ctx->uxs, &ctx->ucidx, &ctx->uni_prev_rows, &ctx->uni_mode, &ctx->uni_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->U2, &ctx->mt_spec, &ctx->mt_jump, &ctx->mt_tmp, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
@@ -1348,6 +1432,7 @@ int tpe_space_set(tpe_ctx* ctx, const tpe_param_desc* params, int32_t n_params, 
   }
   ctx->col_missing.assign(n_params, 0);
   ctx->col_oor.assign(n_params, 0);
+  ctx->col_offgrid.assign(n_params, 0);
   ctx->hist_lineage++;
   ctx->N = 0;
   ctx->history_set = false;
@@ -1365,6 +1450,7 @@ int tpe_history_set(tpe_ctx* ctx, const double* X, const int8_t* category, const
   if (set_device(ctx)) return TPE_E_CUDA;
   std::fill(ctx->col_missing.begin(), ctx->col_missing.end(), 0);
   std::fill(ctx->col_oor.begin(), ctx->col_oor.end(), 0);
+  std::fill(ctx->col_offgrid.begin(), ctx->col_offgrid.end(), 0);
   ctx->hist_lineage++;
   scan_missing(ctx, X, category, n);
   return upload_history(ctx, X, category, key, n, 0, false);
@@ -1436,6 +1522,7 @@ int tpe_history_set_device(tpe_ctx* ctx, const double* dX, const int8_t* dcatego
   // a history adopted from device memory is not scanned on the host: treat every column as possibly out of range
   // unless the caller vouches for it through col_has_missing (the broadcast path of optuna_b200/dist.py does)
   std::fill(ctx->col_oor.begin(), ctx->col_oor.end(), col_has_missing ? 0 : 1);
+  std::fill(ctx->col_offgrid.begin(), ctx->col_offgrid.end(), col_has_missing ? 0 : 1);
   return upload_history(ctx, dX, dcategory, dkey, n, 0, true);
 }
 
@@ -1552,6 +1639,37 @@ static int setup_columns(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, 
   ctx->fast_mode = ctx->fast ? (cfg->multivariate ? 2 : 1) : 0;
   static const bool uni_on = [] { const char* v = getenv("TPE_UNI_FAST"); return !(v && v[0] == '0'); }();
   ctx->uni_fast = uni_on && !cfg->multivariate && n_cols == 1 && ctx->ncont == 1;
+  // mixed spaces with many candidates: kernel-minor tables + per-candidate table rows in shared memory
+  static const bool mixed_on = [] { const char* v = getenv("TPE_MIXED"); return !(v && v[0] == '0'); }();
+  ctx->mixed_ok = mixed_on && cfg->multivariate && !ctx->fast && ctx->ndisc + ctx->ncat > 0 && ctx->ncont <= 128 &&
+                  ctx->ndisc + ctx->ncat <= 128;
+  ctx->mixcols_h.clear();
+  if (ctx->mixed_ok) {
+    int off = 0;
+    std::vector<MixCol> tail;
+    for (int j = 0; j < n_cols && ctx->mixed_ok; ++j) {
+      const ColMeta& cm = ctx->cols_h[j];
+      if (cm.cls == COL_CONT) {
+        ctx->mixcols_h.push_back(MixCol{j, 0, 0, 0});
+      } else if (cm.cls == COL_DISC) {
+        if (cm.grid <= 0 || cm.grid > 65535 || ctx->col_offgrid[cm.src]) ctx->mixed_ok = false;
+        tail.push_back(MixCol{j, 1, cm.grid, off});
+        off += cm.grid;
+      } else {
+        tail.push_back(MixCol{j, 2, cm.nch, off});
+        off += cm.nch;
+      }
+    }
+    ctx->mix_ncont = (int)ctx->mixcols_h.size();
+    ctx->mix_nd = (int)tail.size();
+    ctx->mix_tabd = off;
+    ctx->mixcols_h.insert(ctx->mixcols_h.end(), tail.begin(), tail.end());
+    if (ctx->mixed_ok) {
+      CU(ctx->mixcols.ensure(sizeof(MixCol) * ctx->mixcols_h.size()));
+      CU(cudaMemcpyAsync(ctx->mixcols.p, ctx->mixcols_h.data(), sizeof(MixCol) * ctx->mixcols_h.size(),
+                         cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
   CU(ctx->cols.ensure(sizeof(ColMeta) * n_cols));
   CU(cudaMemcpyAsync(ctx->cols.p, ctx->cols_h.data(), sizeof(ColMeta) * n_cols, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -1735,6 +1853,7 @@ static int launch_sample_select(tpe_ctx* ctx, int64_t n_asks, bool used_dev_rng,
   int rc = TPE_OK;
   (void)per_ask;
   if (timed) CU(cudaEventRecord(ctx->ev[3], st));
+  ctx->user_points = false;
   Estimator& eb = ctx->est[0];
   k_sample<<<grid_for(Ct * ctx->pc, 128, ctx->sm_count * 16), 128, 0, st>>>(
       ctx->U.as<double>(), n_asks, C, ctx->cols.as<ColMeta>(), ctx->pc, ctx->ncat, ctx->nnum, eb.cdf.as<double>(),
@@ -2144,6 +2263,7 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
     sub->cat_dist.alias(ctx->cat_dist.p, ctx->cat_dist.cap);
     sub->col_missing = ctx->col_missing;
     sub->col_oor = ctx->col_oor;
+    sub->col_offgrid = ctx->col_offgrid;
     sub->X.alias(ctx->X.p, ctx->X.cap);
     sub->cat.alias(ctx->cat.p, ctx->cat.cap);
     sub->key.alias(ctx->key.p, ctx->key.cap);
@@ -2281,6 +2401,7 @@ int tpe_logpdf(tpe_ctx* ctx, int which, const double* x, int64_t n, double* out)
   int rc = ensure_candidate_buffers(ctx, n);
   if (rc) return rc;
   ctx->sampled = false;
+  ctx->user_points = true;
   CU(cudaMemcpyAsync(ctx->S.p, x, (size_t)n * ctx->pc * 8, cudaMemcpyHostToDevice, st));
   k_prep_points<<<grid_for(n * ctx->pc, 256, ctx->sm_count * 8), 256, 0, st>>>(
       ctx->S.as<double>(), n, ctx->cols.as<ColMeta>(), ctx->pc, ctx->fast ? ctx->xT.as<double>() : nullptr,

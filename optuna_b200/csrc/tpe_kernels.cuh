@@ -982,7 +982,7 @@ __global__ void k_logpdf_prior_fix(const double* __restrict__ S, int64_t Ct, con
                                    int32_t pc, const double* __restrict__ mu, const double* __restrict__ sigma,
                                    const double* __restrict__ cst, int64_t K, const double* __restrict__ tab,
                                    double2* __restrict__ part_prior, const uint8_t* __restrict__ oob,
-                                   double2* __restrict__ fix) {
+                                   double2* __restrict__ fix, int do_fix = 1) {
   const int lane = threadIdx.x & 31;
   const int64_t ct = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (ct >= Ct) return;
@@ -994,7 +994,7 @@ __global__ void k_logpdf_prior_fix(const double* __restrict__ S, int64_t Ct, con
     acc = warp_sum(acc);
     if (lane == 0) part_prior[ct] = make_double2(cst[k] + acc, 1.0);
   }
-  if (oob[ct] != 0) {
+  if (do_fix && oob[ct] != 0) {
     double m = -INFINITY, s = 0.0;
     const double* xrow = S + ct * pc;
     for (int64_t k = lane; k < K; k += 32) {

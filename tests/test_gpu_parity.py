@@ -276,13 +276,15 @@ def test_error_contract(eng):
         eng.set_space([ParamSpec(kind=0, low=2.0, high=1.0)])
 
 
-@pytest.mark.parametrize("n", [4000, 50_000])
-def test_config3_shape_mixed_64_params_against_oracle(eng, n):
+@pytest.mark.parametrize("n,C", [(4000, 24), (50_000, 24), (4000, 160), (50_000, 96), (50_000, 4096)])
+def test_config3_shape_mixed_64_params_against_oracle(eng, n, C):
     """BASELINE config 3 layout (24 float + 8 log-float + 8 step-float + 8 int + 4 log-int +
-    12 categorical, multivariate) at N = 4000 and at the full N = 50 000 (chunked oracle)."""
+    12 categorical, multivariate) at N = 4000 and at the full N = 50 000 (chunked oracle).  From 64 candidates on
+    g(x) runs through k_logpdf_mixed (kernel-minor tables, table rows in shared memory); at C = 4096 the oracle is
+    replaced by the elementwise kernel k_logpdf_pairs on the same candidates (tpe_logpdf), which the smaller cases
+    pin to the oracle."""
     from optuna_b200.engine import ParamSpec
     rs = np.random.RandomState(0)
-    C = 24
     specs, params, cols = [], [], []
     for _ in range(24):
         specs.append(ParamSpec(kind=0, low=0.0, high=1.0)); params.append(orc.Param("float", 0.0, 1.0))
@@ -310,7 +312,14 @@ def test_config3_shape_mixed_64_params_against_oracle(eng, n):
     eng.set_history(X, cat, key)
     u = draw_uniforms(np.random.RandomState(9), C, 12, 52)
     x, acq, best = eng.suggest(list(range(64)), u, 1, n_below=25, n_candidates=C, multivariate=True)
+    assert eng.last_logpdf_kernel() == ("k_logpdf_mixed" if C >= 64 else "k_logpdf_pairs")
     smp, ll, lg = eng.get_candidates()
+    if C > 1000:
+        lg_pairs = np.concatenate([eng.logpdf(1, smp[i: i + 1024]) for i in range(0, C, 1024)])
+        assert eng.last_logpdf_kernel() == "k_logpdf_pairs"
+        close(lg, lg_pairs, 0, 1e-9)
+        assert int(best[0]) == int(np.argmax(ll - lg))
+        return
     s = orc.suggest(X, cat, key, params, list(range(64)), orc.Config(multivariate=True), 25, C,
                     np.random.RandomState(9), chunk_rows=2 if n > 10_000 else None)
     for j, p in enumerate(params):
