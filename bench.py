@@ -476,8 +476,9 @@ def run_b200(args) -> None:
                 eng.suggest([j], ru.random_sample(N_CAND * 2), 1, **ucfg)
             uni = time.perf_counter() - t0
         extras["univariate_trial_one_by_one_ms"] = uni * 1e3
-        for rep in range(3):
-            eng.append_history(np.zeros((0, N_PARAMS)), np.zeros(0, np.int8), np.zeros((0, 2)))
+        for rep in range(4):
+            # a trial has finished in between (one row more in the above set, as in a running study)
+            eng.append_history(ru.uniform(0, 1, (1, N_PARAMS)), np.zeros(1, np.int8), np.array([[1e9, 0.0]]))
             uu = ru.random_sample(N_PARAMS * N_CAND * 2)
             t0 = time.perf_counter()
             eng.suggest_univariate_batch(cols, uu, **ucfg)
@@ -533,6 +534,41 @@ def run_b200(args) -> None:
             extras["motpe_c4"] = mo
         except Exception as e:  # an extra must never take the headline down
             extras["motpe_c4"] = {"error": repr(e)}
+        # config 3: 64 mixed parameters (24 float, 8 log-float, 8 step-float, 8 int, 4 log-int, 12 categorical),
+        # N = 50 000, multivariate -- with the default n_ei_candidates and with 4096 candidates (k_logpdf_mixed)
+        try:
+            n3 = 50_000
+            r3 = np.random.RandomState(0)
+            specs3, cols3 = [], []
+            for _ in range(24):
+                specs3.append(ParamSpec(kind=0, low=0.0, high=1.0)); cols3.append(r3.uniform(0, 1, n3))
+            for _ in range(8):
+                specs3.append(ParamSpec(kind=0, low=1e-5, high=1.0, log=True)); cols3.append(np.exp(r3.uniform(np.log(1e-5), 0, n3)))
+            for _ in range(8):
+                specs3.append(ParamSpec(kind=0, low=0.0, high=10.0, step=0.5)); cols3.append(r3.randint(0, 21, n3) * 0.5)
+            for _ in range(8):
+                specs3.append(ParamSpec(kind=1, low=0, high=100, step=1)); cols3.append(r3.randint(0, 101, n3).astype(float))
+            for _ in range(4):
+                specs3.append(ParamSpec(kind=1, low=1, high=1024, step=1, log=True))
+                cols3.append(np.round(np.exp(r3.uniform(0, np.log(1024), n3))))
+            for k in range(12):
+                specs3.append(ParamSpec(kind=2, n_choices=4 + k % 5)); cols3.append(r3.randint(0, 4 + k % 5, n3).astype(float))
+            e3 = TPEEngine(local)
+            e3.set_space(specs3)
+            e3.set_history(np.stack(cols3, 1), np.zeros(n3, np.int8), np.stack([r3.normal(size=n3), np.zeros(n3)], 1))
+            c3 = {"n_trials": n3, "n_params": 64}
+            for C3 in (24, 4096):
+                for rep in range(3):
+                    u3 = r3.random_sample(C3 * (1 + 64))
+                    t0 = time.perf_counter()
+                    e3.suggest(list(range(64)), u3, 1, n_below=25, n_candidates=C3, multivariate=True)
+                    dt = time.perf_counter() - t0
+                c3[f"c{C3}"] = {"suggestion_ms": dt * 1e3, "device_ms": float(e3.last_timing()[0][8]),
+                                "kernel": e3.last_logpdf_kernel()}
+            e3.close()
+            extras["config3"] = c3
+        except Exception as e:
+            extras["config3"] = {"error": repr(e)}
         # config-5 shape: 8192 concurrent asks with the default n_ei_candidates = 24, one device call
         bcfg = dict(cfg, n_candidates=24)
         n_asks = 8192
