@@ -21,6 +21,7 @@
 #include "tpe_motpe_kernels.cuh"
 #include "tpe_uni.cuh"
 #include "tpe_mixed.cuh"
+#include "tpe_tcscreen.cuh"
 // Lab build (-DTPE_LAB): the experimental grid kernels and the timing-attribution variants measured in
 // profiles/r1_variants.md / r2_variants.md, selectable by environment variables.  Some of them switch parts of the
 // log-sum-exp off (wrong results by design).  The product library contains none of them.
@@ -92,6 +93,9 @@ struct Estimator {
   DevBuf uord, us32, usmi, usc, umeta;  // univariate 1-D grid (tpe_uni.cuh): sorted order and sorted tables
   DevBuf ucoef, ubox, ubstart;          // ... and the fast Gauss transform of the floor-bandwidth kernels
   bool fgt = false;
+  DevBuf tcs_h, tcs_ak, tcs_ak64;       // bf16 tensor-core screen of the multivariate grid (tpe_tcscreen.cuh)
+  bool tcs = false;
+  int64_t tcs_kpad = 0;
   DevBuf mxc, mxd;                      // mixed spaces, many candidates (tpe_mixed.cuh): kernel-minor tables
   bool mixed = false;
   int64_t mix_kstride = 0;
@@ -100,7 +104,7 @@ struct Estimator {
   bool screen_ready = false;
   int nsplit = 0;
   void release() {
-    for (DevBuf* b : {&uord, &us32, &usmi, &usc, &umeta, &ucoef, &ubox, &ubstart, &mxc, &mxd, &tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
+    for (DevBuf* b : {&uord, &us32, &usmi, &usc, &umeta, &ucoef, &ubox, &ubstart, &mxc, &mxd, &tcs_h, &tcs_ak, &tcs_ak64, &tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
                       &part, &fix})
       b->release();
   }
@@ -789,12 +793,12 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
   CU(e.mu.ensure((size_t)K * pc * 8));
   CU(e.sigma.ensure((size_t)K * pc * 8));
   CU(e.cst_part.ensure((size_t)K * 8));
-  CU(e.cst.ensure((size_t)k_alloc * 8));
+  CU(e.cst.ensure((size_t)(k_alloc + kTcsTile) * 8));   // (+ one tile: k_tcs copies whole tiles)
   CU(e.w.ensure((size_t)K * 8));
   CU(e.logw.ensure((size_t)K * 8));
   CU(e.cdf.ensure((size_t)K * 8));
   if (ctx->fast_mode == 1) CU(e.tabp.ensure((size_t)K * ctx->pb * 16 + 16));
-  if (ctx->fast_mode == 2) CU(e.tabc.ensure((size_t)K * ctx->pb * 8 + 16));
+  if (ctx->fast_mode == 2) CU(e.tabc.ensure((size_t)(K + kTcsTile) * ctx->pb * 8 + 16));
   if (ctx->fast) CU(e.colprm.ensure((size_t)ctx->pb * 16));
   bool in_range = true;  // every selected column's observations lie inside its current [low, high]
   for (const ColMeta& cm : ctx->cols_h) in_range = in_range && !ctx->col_oor[cm.src];
@@ -1018,6 +1022,21 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
                                     ctx->cat_dist.as<double>(), e.tab.as<double>());
     ctx->launch_counter++;
   }
+  // Experimental and OFF by default (TPE_TCS=1): correct (same parity tests) but 1.9 ms against 1.17 ms for
+  // k_logpdf_mma at config 2 -- the bf16 screen itself takes 0.13 ms, the exact evaluation of the 8.9 % survivors on
+  // the CUDA cores the rest (profiles/r2_variants.md, section 4)
+  static const bool tcs_on = [] { const char* v = getenv("TPE_TCS"); return v && v[0] == '1'; }();
+  e.tcs = tcs_on && e.mma && K - 1 >= 1024 && (ctx->pb == 16 || ctx->pb == 32 || ctx->pb == 64);
+  if (e.tcs) {
+    e.tcs_kpad = round_up<int64_t>(K - 1, kTcsTile);
+    CU(e.tcs_h.ensure((size_t)e.tcs_kpad * (ctx->pb + 8) * 2));
+    CU(e.tcs_ak.ensure((size_t)e.tcs_kpad * 4));
+    CU(e.tcs_ak64.ensure((size_t)e.tcs_kpad * 8));
+    k_tcs_tables<<<grid_for(e.tcs_kpad, 256, 1 << 20), 256, 0, st>>>(
+        e.tabc.as<double>(), e.cst.as<double>(), K - 1, e.tcs_kpad, ctx->pb,
+        reinterpret_cast<__nv_bfloat16*>(e.tcs_h.p), e.tcs_ak.as<float>(), e.tcs_ak64.as<double>());
+    ctx->launch_counter++;
+  }
   e.uni_ready = false;
   if (ctx->uni_fast) {
     const int64_t ntiles = (K + kUniTile - 1) / kUniTile;
@@ -1131,12 +1150,83 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
       nsplit = (ktiles + tiles_per - 1) / tiles_per;
       kps = tiles_per * fc->tk;
     }
+    // bf16 tensor-core screen + exact survivors (tpe_tcscreen.cuh): many candidates, rounding bound small enough
+    bool use_tcs = false;
+    if (e.tcs && cst_mode && Ct >= 256) {
+      const double nobs = (double)std::max<int64_t>(e.n, 1);
+      double fac = 0.2 * pow(nobs, -1.0 / (ctx->pc + 4));
+      if (ctx->cfg.magic_clip) fac = std::max(fac, 1.0 / std::min(100.0, 1.0 + (double)K));
+      fac = std::min(std::max(fac, 1e-9), 1.0);
+      const double rho = 0.5 / fac, pr2 = ctx->pb * rho * rho;
+      const double delta = pr2 * (1.0 / 256 + 1.0 / 65536 + (ctx->pb + 2) * 5.97e-8) * 1.02 + 2e-3;
+      if (delta <= 6.0 && pr2 * 2.3e-16 <= 5e-13) {   // (the second: conditioning of the expanded square, as for k_logpdf_mma)
+        use_tcs = true;
+        const int pb = ctx->pb;
+        const size_t smem_sum = pb == 16 ? sizeof(TcsSmem<16>) : pb == 32 ? sizeof(TcsSmem<32>) : sizeof(TcsSmem<64>);
+        const size_t smem_max = pb == 16 ? offsetof(TcsSmem<16>, b64) : pb == 32 ? offsetof(TcsSmem<32>, b64) : offsetof(TcsSmem<64>, b64);
+        const int64_t tctiles = (Ct + kTcsRows - 1) / kTcsRows, tktiles = e.tcs_kpad / kTcsTile;
+        const int64_t slots = (int64_t)ctx->sm_count * (smem_sum <= 113 * 1024 ? 2 : 1);
+        int64_t tns = std::max<int64_t>(1, std::min<int64_t>(tktiles, slots / tctiles));
+        const int64_t tiles_per = (tktiles + tns - 1) / tns;
+        tns = (tktiles + tiles_per - 1) / tiles_per;
+        const int64_t tkps = tiles_per * kTcsTile;
+        CU(e.part.ensure((size_t)(tns + 1) * ctx->ct_stride * 16));
+        CU(ctx->x64s.ensure((size_t)ctx->ct_stride * pb * 8));
+        CU(ctx->e32s.ensure((size_t)ctx->ct_stride * 4));
+        CU(ctx->x32s.ensure((size_t)ctx->ct_stride * 8));   // (-|x''|^2 / 2 in fp64)
+        CU(ctx->gmax.ensure((size_t)ctx->ct_stride * 4));
+        k_tcs_xprep<<<grid_for(ctx->ct_stride, 256, 1 << 20), 256, 0, st>>>(
+            ctx->xT.as<double>(), e.colprm.as<double2>(), ctx->ct_stride, pb, ctx->x64s.as<double>(),
+            ctx->e32s.as<float>(), ctx->x32s.as<double>(), ctx->gmax.as<int>());
+        const double skip_t = std::min(46.0, log((double)std::max<int64_t>(K, 1)) + 30.0);
+        const float window = (float)(skip_t + 2.0 * delta);
+        // TPE_TCS_STATS=1 (diagnostics): count the survivors of every launch and print them
+        static const bool tcs_stats_on = [] { const char* v = getenv("TPE_TCS_STATS"); return v && v[0] == '1'; }();
+        unsigned long long* tcs_stats = nullptr;
+        if (tcs_stats_on) {
+          CU(ctx->lse_gmax.ensure(64));
+          CU(cudaMemsetAsync(ctx->lse_gmax.p, 0, 8, st));
+          tcs_stats = ctx->lse_gmax.as<unsigned long long>();
+        }
+#define TPE_TCS_LAUNCH(PBV)                                                                                            \
+        do {                                                                                                           \
+          static bool attr_done = false;                                                                               \
+          if (!attr_done) {                                                                                            \
+            CU(cudaFuncSetAttribute(k_tcs<PBV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));   \
+            CU(cudaFuncSetAttribute(k_tcs<PBV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum));    \
+            attr_done = true;                                                                                          \
+          }                                                                                                            \
+          k_tcs<PBV, false><<<dim3((unsigned)tctiles, (unsigned)tns), kTcsNT, smem_max, st>>>(                         \
+              reinterpret_cast<const __nv_bfloat16*>(e.tcs_h.p), e.tcs_ak.as<float>(), e.tabc.as<double>(),            \
+              e.tcs_ak64.as<double>(), e.tcs_kpad, tkps, ctx->x64s.as<double>(), ctx->e32s.as<float>(),               \
+              ctx->x32s.as<double>(), ctx->gmax.as<int>(), Ct, ctx->ct_stride, window, e.part.as<double2>(), tcs_stats);                                                       \
+          k_tcs<PBV, true><<<dim3((unsigned)tctiles, (unsigned)tns), kTcsNT, smem_sum, st>>>(                          \
+              reinterpret_cast<const __nv_bfloat16*>(e.tcs_h.p), e.tcs_ak.as<float>(), e.tabc.as<double>(),            \
+              e.tcs_ak64.as<double>(), e.tcs_kpad, tkps, ctx->x64s.as<double>(), ctx->e32s.as<float>(),               \
+              ctx->x32s.as<double>(), ctx->gmax.as<int>(), Ct, ctx->ct_stride, window, e.part.as<double2>(), tcs_stats);                                                       \
+        } while (0)
+        if (pb == 16) TPE_TCS_LAUNCH(16);
+        else if (pb == 32) TPE_TCS_LAUNCH(32);
+        else TPE_TCS_LAUNCH(64);
+#undef TPE_TCS_LAUNCH
+        ctx->launch_counter += 3;
+        if (tcs_stats_on) {
+          unsigned long long hs = 0;
+          CU(cudaMemcpyAsync(&hs, tcs_stats, 8, cudaMemcpyDeviceToHost, st));
+          CU(cudaStreamSynchronize(st));
+          fprintf(stderr, "[tpe] k_tcs: %llu survivors of %lld x %lld cells (%.2f %%), window %.2f\n", hs, (long long)Ct,
+                  (long long)(K - 1), 100.0 * (double)hs / ((double)Ct * (double)(K - 1)), (double)window);
+        }
+        nsplit = tns;
+        ctx->last_kernel = "k_tcs<bf16 screen + exact survivors>";
+      }
+    }
 #ifdef TPE_LAB
     // fp32-screened variant (tpe_screen.cuh): multivariate, 17..32 continuous columns, many candidates
     // Experimental and OFF by default: correct (same parity tests) but 2.62 ms vs 2.40 ms for the exact
     // kernel at config 2 -- see profiles/r1_variants.md.  TPE_SCREEN=1 enables it.
     static const bool screen_on = [] { const char* v = getenv("TPE_SCREEN"); return v && v[0] == '1'; }();
-    const bool use_screen = cst_mode && !use_mma && ctx->pb == kScrP && Ct > 128 && Kf > 0 && screen_on;
+    const bool use_screen = !use_tcs && cst_mode && !use_mma && ctx->pb == kScrP && Ct > 128 && Kf > 0 && screen_on;
     if (use_screen) {
       const int64_t sctiles = (Ct + kScrCands - 1) / kScrCands;
       const int64_t sktiles = (Kf + kScrTK - 1) / kScrTK;
@@ -1186,8 +1276,8 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
 #else
     constexpr bool use_screen = false;
 #endif
-    if (!use_screen) CU(e.part.ensure((size_t)(nsplit + 1) * ctx->ct_stride * 16));
-    if (nsplit > 0 && !use_screen) {
+    if (!use_screen && !use_tcs) CU(e.part.ensure((size_t)(nsplit + 1) * ctx->ct_stride * 16));
+    if (nsplit > 0 && !use_screen && !use_tcs) {
       if (!ctx->prepared_cfgs.count(fc)) {
         CU(fc->prepare());
         ctx->prepared_cfgs.insert(fc);
@@ -1204,7 +1294,8 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
                  use_mma ? ctx->lse_gmax.as<unsigned long long>() : nullptr);
       ctx->launch_counter++;
     }
-    if (use_mma && !use_screen)
+    if (use_tcs) {
+    } else if (use_mma && !use_screen)
       ctx->last_kernel = (fc->nt >= 256) ? "k_logpdf_mma<big>" : "k_logpdf_mma<small>";
     else if (!use_screen)
       ctx->last_kernel = cst_mode ? ((fc->nt >= 256) ? "k_logpdf_fast<const,big>" : "k_logpdf_fast<const,small>")

@@ -6,6 +6,10 @@ mu / sigma / weights <= 1e-15 relative (sigma of multivariate kernels goes throu
 categorical columns; discrete columns carry the reference's own ill-conditioning
  so they get 1e-9.
 """
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -216,7 +220,7 @@ def test_config2_shape_against_chunked_oracle(eng):
     rng = np.random.RandomState(1)
     u = draw_uniforms(rng, C, 0, P)
     x, acq, best = eng.suggest(list(range(P)), u, 1, n_below=n_below, n_candidates=C, multivariate=True)
-    assert eng.last_logpdf_kernel().startswith(("k_logpdf_mma", "k_logpdf_fast", "k_logpdf_screen"))
+    assert eng.last_logpdf_kernel().startswith(("k_tcs", "k_logpdf_mma", "k_logpdf_fast", "k_logpdf_screen"))
     smp, ll, lg = eng.get_candidates()
     params = [orc.Param("float", 0.0, 1.0) for _ in range(P)]
     cfg = orc.Config(multivariate=True)
@@ -375,7 +379,10 @@ def test_tabulated_discrete_columns(eng, C, offgrid):
 
 
 @pytest.mark.parametrize("P,n,C,n_below", [(5, 3, 8, 1), (8, 40, 100, 10), (12, 700, 24, 25), (20, 2500, 70, 40),
-                                            (33, 900, 130, 25), (64, 300, 24, 12), (9, 9, 300, 8)])
+                                            (33, 900, 130, 25), (64, 300, 24, 12), (9, 9, 300, 8),
+                                            # 256 candidates and more (with TPE_TCS=1: the bf16-screened grid k_tcs, P padded to 16 / 32 / 64)
+                                            (12, 3000, 300, 25), (16, 129, 256, 10), (27, 6000, 700, 25),
+                                            (32, 1500, 1030, 30), (40, 2100, 520, 25), (64, 5000, 384, 25)])
 def test_tensor_core_kernel_shapes(eng, P, n, C, n_below):
     """Multivariate, all-continuous spaces go through k_logpdf_mma (P >= 5): ragged P (padding of the
     k-steps), fewer kernels than one group of 8, padded candidate tiles, log-scaled columns, and the
@@ -403,7 +410,9 @@ def test_tensor_core_kernel_shapes(eng, P, n, C, n_below):
         x, acq, best = eng.suggest(list(range(P)), u, 1, n_below=n_below, n_candidates=C, multivariate=True,
                                    magic_clip=clip)
         if P <= 64:
-            assert eng.last_logpdf_kernel().startswith(("k_logpdf_mma", "k_logpdf_fast")), eng.last_logpdf_kernel()
+            assert eng.last_logpdf_kernel().startswith(("k_tcs", "k_logpdf_mma", "k_logpdf_fast")), eng.last_logpdf_kernel()
+        if C >= 256 and P >= 9 and clip and n >= 1100 and os.environ.get("TPE_TCS") == "1":
+            assert eng.last_logpdf_kernel().startswith("k_tcs"), eng.last_logpdf_kernel()
         smp, ll, lg = eng.get_candidates()
         s = orc.suggest(X, cat, key, params, list(range(P)), orc.Config(multivariate=True, magic_clip=clip),
                         n_below, C, np.random.RandomState(7))
@@ -411,6 +420,21 @@ def test_tensor_core_kernel_shapes(eng, P, n, C, n_below):
         close(ll, s.logl, 1e-14, 1e-12)
         close(lg, s.logg, 1e-14, 1e-12)
         assert int(best[0]) == s.best
+
+
+def test_bf16_screened_grid_variant_passes_the_same_parity_tests():
+    """TPE_TCS=1 routes the multivariate grid of large all-continuous estimators through k_tcs (bf16 tensor-core
+    screen with a rigorous rounding bound + exact fp64 evaluation of the survivors, tpe_tcscreen.cuh) -- slower than
+    the fp64 tensor-core kernel and therefore off by default, but kept correct: the shape sweep, the full-size
+    config-2 fixture and the massive-ties case run again in a process with the switch on."""
+    if os.environ.get("TPE_TCS") == "1":
+        pytest.skip("already inside the TPE_TCS=1 run")
+    env = dict(os.environ, TPE_TCS="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
+                        "tensor_core_kernel_shapes or precomputed_oracle_fixture or massive_ties or config2_shape"],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
 
 
 def test_categorical_distance_func_tables(eng):
@@ -656,7 +680,7 @@ def test_tensor_core_kernel_with_massive_ties(eng):
     eng.set_history(X, np.zeros(n, np.int8), key)
     u = draw_uniforms(np.random.RandomState(2), C, 0, P)
     x, acq, best = eng.suggest(list(range(P)), u, 1, n_below=20, n_candidates=C, multivariate=True)
-    assert eng.last_logpdf_kernel().startswith("k_logpdf_mma")
+    assert eng.last_logpdf_kernel().startswith(("k_tcs", "k_logpdf_mma"))
     smp, ll, lg = eng.get_candidates()
     s = orc.suggest(X, np.zeros(n, np.int8), key, params, list(range(P)), orc.Config(multivariate=True), 20, C,
                     np.random.RandomState(2))
@@ -855,7 +879,7 @@ def test_config2_full_size_against_the_precomputed_oracle_fixture(eng):
     assert np.array_equal(below, g["below"])
     eng.build()
     lg = eng.logpdf(1, g["x"])
-    assert eng.last_logpdf_kernel().startswith("k_logpdf_mma")
+    assert eng.last_logpdf_kernel().startswith(("k_tcs", "k_logpdf_mma"))
     ll = eng.logpdf(0, g["x"])
     assert g["x"].shape == (256, P)
     close(lg, g["logg"], 0, 1e-12)
@@ -898,7 +922,7 @@ def test_far_tier_worst_case_every_term_just_below_the_exact_window(eng):
         eng.build(None, np.ones(n))                                              # equal weights: equal terms
         pts = np.stack([x0, x0 + 1e-3, x0 - 2e-3 * np.arange(P) / P])
         got = eng.logpdf(1, pts)
-        assert eng.last_logpdf_kernel().startswith("k_logpdf_mma")
+        assert eng.last_logpdf_kernel().startswith(("k_tcs", "k_logpdf_mma"))
         cfg_w = orc.Config(multivariate=True, weights=lambda k: np.ones(k))
         ma = orc.build_mixture(X, params, cfg_w)
         close(got, orc.mixture_log_pdf(ma, pts), 0, 1e-12)
