@@ -22,6 +22,7 @@
 #include "tpe_uni.cuh"
 #include "tpe_mixed.cuh"
 #include "tpe_tcscreen.cuh"
+#include "tpe_unib.cuh"
 // Lab build (-DTPE_LAB): the experimental grid kernels and the timing-attribution variants measured in
 // profiles/r1_variants.md / r2_variants.md, selectable by environment variables.  Some of them switch parts of the
 // log-sum-exp off (wrong results by design).  The product library contains none of them.
@@ -91,7 +92,7 @@ struct Estimator {
   DevBuf cls, dtab, offgrid;   // tabulated discrete columns (multivariate)
   DevBuf tabm, hb, ckk;        // tensor-core kernel: fragment-major table, |mu''|^2 / 2, cst - |mu''|^2 / 2
   DevBuf uord, us32, usmi, usc, umeta;  // univariate 1-D grid (tpe_uni.cuh): sorted order and sorted tables
-  DevBuf ucoef, ubox, ubstart;          // ... and the fast Gauss transform of the floor-bandwidth kernels
+  DevBuf ucoef, ubox, ubstart, utlist;  // ... and the fast Gauss transform of the floor-bandwidth kernels
   bool fgt = false;
   DevBuf tcs_h, tcs_ak, tcs_ak64;       // bf16 tensor-core screen of the multivariate grid (tpe_tcscreen.cuh)
   bool tcs = false;
@@ -104,7 +105,7 @@ struct Estimator {
   bool screen_ready = false;
   int nsplit = 0;
   void release() {
-    for (DevBuf* b : {&uord, &us32, &usmi, &usc, &umeta, &ucoef, &ubox, &ubstart, &mxc, &mxd, &tcs_h, &tcs_ak, &tcs_ak64, &tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
+    for (DevBuf* b : {&uord, &us32, &usmi, &usc, &umeta, &ucoef, &ubox, &ubstart, &utlist, &mxc, &mxd, &tcs_h, &tcs_ak, &tcs_ak64, &tabm, &hb, &ckk, &cls, &dtab, &offgrid, &tab32, &tab64p, &d32, &rows, &pos, &wstage, &wpart, &w, &logw, &cdf, &mu, &sigma, &cst_part, &cst, &tabp, &tabc, &colprm, &tab,
                       &part, &fix})
       b->release();
   }
@@ -200,6 +201,14 @@ struct tpe_ctx {
   std::vector<tpe_ctx*> uni_sub;
   cudaEvent_t ev_uni = nullptr;
   bool is_sub = false;
+  // staged univariate batch (tpe_unib.cuh): one arena carved per call + the sorted orders kept between calls
+  DevBuf ub_arena, ub_ord_a, ub_ord_b, ub_wstage;
+  int ub_ord_cur = 0;                  // which of ub_ord_a / ub_ord_b holds the latest above orders
+  uint64_t ub_ord_seq = 0, ub_ord_lineage = 0;
+  int64_t ub_ord_K = -1, ub_ord_ks = 0;
+  std::vector<int32_t> ub_ord_cols;
+  std::vector<ColMeta> ub_cols_h;
+  int ub_sort_g = 0;
   bool mixed_ok = false;         // the selected columns suit k_logpdf_mixed (setup_columns)
   std::vector<MixCol> mixcols_h;
   DevBuf mixcols;
@@ -1048,7 +1057,7 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
     static const int64_t fgt_min = [] { const char* v = getenv("TPE_FGT_MIN_K"); return v ? atoll(v) : 1024ll; }();
     e.fgt = ctx->cfg.magic_clip && K >= fgt_min;
     if (e.fgt) {
-      CU(e.ucoef.ensure((size_t)kFgtMaxBoxes * kFgtTerms * 8));
+      CU(e.ucoef.ensure((size_t)kFgtMaxBoxes * kFgtRow * 8));
       CU(e.ubox.ensure((size_t)kFgtMaxBoxes * sizeof(FgtBox)));
       CU(e.ubstart.ensure((size_t)(kFgtMaxBoxes + 1) * 4));
     }
@@ -1061,7 +1070,9 @@ int build_estimator(tpe_ctx* ctx, int which, const double* w_host, cudaStream_t 
       k_fgt_coeff<<<kFgtMaxBoxes, 128, 0, st>>>(e.uord.as<int32_t>(), e.mu.as<double>(), e.sigma.as<double>(),
                                                 e.cst.as<double>(), ctx->cols.as<ColMeta>(), K, ctx->cfg.magic_clip,
                                                 e.ubstart.as<int32_t>(), e.ucoef.as<double>(), e.ubox.as<FgtBox>());
-      ctx->launch_counter++;
+      CU(e.utlist.ensure((size_t)(ntiles + 1) * 4));
+      k_uni_tile_list<<<1, 256, 0, st>>>(e.umeta.as<UniTileMeta>(), (int)ntiles, e.utlist.as<int32_t>());
+      ctx->launch_counter += 2;
     }
     e.uni_ready = true;
   }
@@ -1103,10 +1114,15 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     k_uni_grid<<<(unsigned)((C + 31) / 32), kUniWarps * 32, 0, st>>>(e.us32.as<float4>(), e.usmi.as<double2>(),
                                                                      e.usc.as<double>(), e.umeta.as<UniTileMeta>(), K,
                                                                      ctx->uxs.as<double>(), ctx->ucidx.as<int32_t>(), C, skip,
-                                                                     e.part.as<double2>());
+                                                                     e.part.as<double2>(), e.fgt ? e.utlist.as<int32_t>() : nullptr);
     ctx->launch_counter++;
     if (e.fgt) {
-      k_fgt_eval<<<(unsigned)((C * 32 + 255) / 256), 256, 0, st>>>(
+      static bool fgt_attr = false;
+      if (!fgt_attr) {
+        CU(cudaFuncSetAttribute(k_fgt_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFgtEvalSmem));
+        fgt_attr = true;
+      }
+      k_fgt_eval<<<(unsigned)((C + kFgtCands - 1) / kFgtCands), 256, kFgtEvalSmem, st>>>(
           e.ucoef.as<double>(), e.ubox.as<FgtBox>(), e.ubstart.as<int32_t>(), e.us32.as<float4>(), e.usmi.as<double2>(),
           e.usc.as<double>(), e.mu.as<double>(), e.sigma.as<double>(), e.cst.as<double>(), ctx->cols.as<ColMeta>(), K,
           ctx->cfg.magic_clip, ctx->xT.as<double>(), C, e.part.as<double2>() + ctx->ct_stride);
@@ -1421,6 +1437,244 @@ int ensure_candidate_buffers(tpe_ctx* ctx, int64_t Ct) {
 
 }  // namespace
 
+
+// ---- univariate batch, stage by stage over all columns (tpe_unib.cuh) ---------------------------------------------------
+struct Carver {
+  char* base = nullptr;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+struct UbPtrs {
+  double *mu[2], *sigma[2], *cstp[2], *cst[2], *w[2], *logw[2], *cdf, *wpart, *zero, *cstscr, *sc[2], *coef;
+  int32_t *ord0, *bstart, *cidx, *sidx, *tlist;
+  float4* s32[2];
+  double2 *smi[2], *part[2], *fix[2];
+  UniTileMeta* meta[2];
+  FgtBox* box;
+  double *S, *xT, *xs, *logl, *logg;
+  uint8_t* oob;
+  uint64_t* skeys;
+  SortWork* swk;
+  int* work;
+  ColMeta* cols;
+};
+static void ub_carve(Carver& c, UbPtrs& p, int P, const int64_t ks[2], int64_t cs, bool big_sort) {
+  for (int w = 0; w < 2; ++w) {
+    p.mu[w] = c.take<double>((size_t)P * ks[w]);
+    p.sigma[w] = c.take<double>((size_t)P * ks[w]);
+    p.cstp[w] = c.take<double>((size_t)P * ks[w]);
+    p.cst[w] = c.take<double>((size_t)P * ks[w]);
+    p.w[w] = c.take<double>((size_t)ks[w]);
+    p.logw[w] = c.take<double>((size_t)ks[w]);
+    p.s32[w] = c.take<float4>((size_t)P * ks[w]);
+    p.smi[w] = c.take<double2>((size_t)P * ks[w]);
+    p.sc[w] = c.take<double>((size_t)P * ks[w]);
+    p.meta[w] = c.take<UniTileMeta>((size_t)P * (ks[w] / kUniTile));
+    p.part[w] = c.take<double2>((size_t)P * 2 * cs);
+    p.fix[w] = c.take<double2>((size_t)P * cs);
+  }
+  p.cdf = c.take<double>((size_t)ks[0]);
+  p.wpart = c.take<double>(1024);
+  p.zero = c.take<double>((size_t)ks[1]);
+  p.cstscr = c.take<double>((size_t)ks[1]);
+  p.ord0 = c.take<int32_t>((size_t)P * ks[0]);
+  p.bstart = c.take<int32_t>((size_t)P * (kFgtMaxBoxes + 1));
+  p.tlist = c.take<int32_t>((size_t)P * (ks[1] / kUniTile + 1));
+  p.coef = c.take<double>((size_t)P * kFgtMaxBoxes * kFgtRow);
+  p.box = c.take<FgtBox>((size_t)P * kFgtMaxBoxes);
+  p.S = c.take<double>((size_t)P * cs);
+  p.xT = c.take<double>((size_t)P * cs);
+  p.xs = c.take<double>((size_t)P * cs);
+  p.cidx = c.take<int32_t>((size_t)P * cs);
+  p.logl = c.take<double>((size_t)P * cs);
+  p.logg = c.take<double>((size_t)P * cs);
+  p.oob = c.take<uint8_t>((size_t)P * cs);
+  p.work = c.take<int>((size_t)P * 4);
+  p.cols = c.take<ColMeta>((size_t)P);
+  if (big_sort) {
+    p.skeys = c.take<uint64_t>((size_t)P * 2 * ks[1]);
+    p.sidx = c.take<int32_t>((size_t)P * 2 * ks[1]);
+    p.swk = c.take<SortWork>((size_t)P);
+  } else {
+    p.skeys = nullptr;
+    p.sidx = nullptr;
+    p.swk = nullptr;
+  }
+}
+
+// The caller (tpe_suggest_univariate_batch) has run the split, checked the weights and compared the above rows with
+// the previous call's (ctx->uni_mode); U holds the uniforms [n_cols][2 C] (ctx->ev_u).  Results into ctx->out_*.
+static int uni_batch_staged(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t P, const double* w_below,
+                            const double* w_above) {
+  cudaStream_t st = ctx->stream;
+  const int32_t C = cfg->n_candidates;
+  const int64_t n[2] = {ctx->est[0].n, ctx->est[1].n};
+  const int64_t K[2] = {n[0] + 1, n[1] + 1};
+  const int64_t ks[2] = {round_up<int64_t>(K[0] + 160, 1024), round_up<int64_t>(K[1] + 160, 1024)};
+  const int64_t cs = round_up<int64_t>(C, 1024);
+  const bool big_sort = K[1] > 4096 || K[0] > 4096;
+  Carver c0;
+  UbPtrs p{};
+  ub_carve(c0, p, P, ks, cs, big_sort);
+  CU(ctx->ub_arena.ensure(c0.off + 4096));
+  Carver c;
+  c.base = static_cast<char*>(ctx->ub_arena.p);
+  ub_carve(c, p, P, ks, cs, big_sort);
+  UbDims d[2];
+  for (int w = 0; w < 2; ++w) {
+    d[w].ks = ks[w];
+    d[w].cs = cs;
+    d[w].pall = (int32_t)ctx->space.size();
+  }
+  // every column as the only one of its context (setup_columns with one column: slot and RNG rank 0)
+  ctx->ub_cols_h.assign(ctx->cols_h.begin(), ctx->cols_h.begin() + P);
+  for (ColMeta& cm : ctx->ub_cols_h) {
+    cm.slot = 0;
+    cm.num_rank = 0;
+  }
+  CU(cudaMemcpyAsync(p.cols, ctx->ub_cols_h.data(), sizeof(ColMeta) * P, cudaMemcpyHostToDevice, st));
+  const ColMeta* dcols = p.cols;
+  const int cap = ctx->sm_count * 8;
+  const unsigned Pu = (unsigned)P;
+  CU(cudaMemsetAsync(p.zero, 0, (size_t)ks[1] * 8, st));
+  CU(cudaMemsetAsync(p.oob, 0, (size_t)P * cs, st));
+  CU(cudaMemsetAsync(p.work, 0, (size_t)P * 16, st));
+  // the above orders of the previous call, if they belong to this one
+  DevBuf& ord_new_buf = ctx->ub_ord_cur == 0 ? ctx->ub_ord_b : ctx->ub_ord_a;
+  DevBuf& ord_old_buf = ctx->ub_ord_cur == 0 ? ctx->ub_ord_a : ctx->ub_ord_b;
+  CU(ord_new_buf.ensure((size_t)P * ks[1] * 4));
+  const bool inc = K[1] > 4096 && ctx->ub_ord_seq + 1 == ctx->uni_seq && ctx->ub_ord_lineage == ctx->hist_lineage &&
+                   (ctx->ub_ord_K == K[1] || ctx->ub_ord_K == K[1] - 1) && ctx->ub_ord_ks == ks[1] &&
+                   ord_old_buf.cap >= (size_t)P * ks[1] * 4 && ctx->ub_ord_cols.size() == (size_t)P &&
+                   std::equal(cols, cols + P, ctx->ub_ord_cols.begin());
+  int32_t* ord[2] = {p.ord0, ord_new_buf.as<int32_t>()};
+  for (int w = 0; w < 2; ++w) {
+    const double* wh = w == 0 ? w_below : w_above;
+    kb_mu<<<dim3((unsigned)grid_for(K[w], 256, cap), Pu), 256, 0, st>>>(ctx->X.as<double>(), d[w],
+                                                                        ctx->est[w].rows.as<int64_t>(), n[w], dcols, p.mu[w]);
+    int64_t m2 = 1;
+    while (m2 < K[w]) m2 <<= 1;
+    if (m2 <= 4096) {
+      kb_sort_small<<<dim3(1, Pu), 1024, 0, st>>>(p.mu[w], d[w], (int)K[w], (int)m2, ord[w]);
+    } else {
+      const int* run_flag = nullptr;
+      if (w == 1 && inc) {
+        run_flag = ctx->uni_mode.as<int>();
+        kb_order_update<<<dim3((unsigned)grid_for(ctx->ub_ord_K, 256, ctx->sm_count), Pu), 256, 0, st>>>(
+            run_flag, ord_old_buf.as<int32_t>(), d[1], (int)ctx->ub_ord_K, (int)K[1], p.mu[1], ord[1], p.work);
+        ctx->launch_counter++;
+      }
+      if (ctx->ub_sort_g == 0) {
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_radix_sort, 512, 0));
+        ctx->ub_sort_g = std::max(1, occ) * ctx->sm_count;
+      }
+      const int G = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(160, ctx->ub_sort_g / P), (K[w] + 1023) / 1024));
+      if (G * P > ctx->ub_sort_g) return fail(ctx, TPE_E_STATE, "not batchable: %d columns exceed the cooperative sort", P);
+      const double* a_mu = p.mu[w];
+      UbDims a_d = d[w];
+      int a_n = (int)K[w];
+      uint64_t* a_keys = p.skeys;
+      int32_t* a_idx = p.sidx;
+      SortWork* a_wk = p.swk;
+      int32_t* a_order = ord[w];
+      void* args[] = {&a_mu, &a_d, &a_n, &a_keys, &a_idx, &a_wk, &a_order, &run_flag};
+      CU(cudaLaunchCooperativeKernel((const void*)kb_radix_sort, dim3((unsigned)G, Pu), dim3(512), args, 0, st));
+    }
+    kb_sigma_uni<<<dim3((unsigned)grid_for(K[w], 256, cap), Pu), 256, 0, st>>>(
+        p.mu[w], ord[w], d[w], dcols, n[w], cfg->magic_clip, cfg->endpoints, p.sigma[w]);
+    kb_const<<<dim3((unsigned)grid_for(K[w], 256, cap), Pu), 256, 0, st>>>(p.mu[w], p.sigma[w], d[w], dcols, K[w], p.cstp[w]);
+    // mixture weights: the same for every column
+    const double* w_dev = nullptr;
+    if (wh != nullptr && n[w] > 0) {
+      CU(ctx->ub_wstage.ensure((size_t)(n[0] + n[1] + 2) * 8));
+      double* dst = ctx->ub_wstage.as<double>() + (w == 0 ? 0 : n[0] + 1);
+      CU(cudaMemcpyAsync(dst, wh, (size_t)n[w] * 8, cudaMemcpyHostToDevice, st));
+      w_dev = dst;
+    }
+    const int64_t k_alloc = round_up<int64_t>(K[w] + 32, 32);
+    const int nparts = grid_for(K[w], 2048, ctx->sm_count * 2);
+    if (nparts == 1) {
+      k_weights_one<<<1, 256, 0, st>>>(w_dev, nullptr, n[w], cfg->prior_weight, p.w[w], p.logw[w], p.zero, p.cstscr,
+                                       w == 0 ? p.cdf : nullptr, k_alloc, nullptr, nullptr);
+      ctx->launch_counter += 1;
+    } else {
+      k_wraw<<<nparts, 256, 0, st>>>(w_dev, nullptr, n[w], cfg->prior_weight, p.w[w], p.wpart);
+      k_wfinal<<<grid_for(k_alloc, 256, ctx->sm_count * 4), 256, 0, st>>>(p.wpart, nparts, n[w], p.w[w], p.logw[w], p.zero,
+                                                                          p.cstscr, w == 0 ? p.cdf : nullptr, k_alloc,
+                                                                          nullptr, nullptr);
+      k_wnorm<<<grid_for(K[w], 256, ctx->sm_count * 4), 256, 0, st>>>(p.wpart, nparts, K[w], p.w[w]);
+      ctx->launch_counter += 3;
+    }
+    kb_cst<<<dim3((unsigned)grid_for(ks[w], 256, cap), Pu), 256, 0, st>>>(p.cstp[w], p.logw[w], d[w], K[w], p.cst[w]);
+    static const int64_t fgt_min = [] { const char* v = getenv("TPE_FGT_MIN_K"); return v ? atoll(v) : 1024ll; }();
+    const bool fgt = cfg->magic_clip && K[w] >= fgt_min;
+    const unsigned ntiles = (unsigned)((K[w] + kUniTile - 1) / kUniTile);
+    kb_uni_tables<<<dim3(ntiles, Pu), kUniTile, 0, st>>>(ord[w], p.mu[w], p.sigma[w], p.cst[w], d[w], dcols, K[w], p.s32[w],
+                                                         p.smi[w], p.sc[w], p.meta[w], fgt ? 1 : 0, cfg->magic_clip, p.bstart);
+    if (fgt) {
+      if (w == 0) return fail(ctx, TPE_E_STATE, "not batchable: a below set of %lld trials", (long long)n[0]);
+      kb_fgt_coeff<<<dim3(kFgtMaxBoxes, Pu), 128, 0, st>>>(ord[w], p.mu[w], p.sigma[w], p.cst[w], d[w], dcols, K[w],
+                                                           cfg->magic_clip, p.bstart, p.coef, p.box);
+      kb_uni_tile_list<<<dim3(1, Pu), 256, 0, st>>>(p.meta[w], d[w], (int)ntiles, p.tlist);
+      ctx->launch_counter += 2;
+    }
+    ctx->launch_counter += 6;
+  }
+  // candidates of every column from its l(x), both log-densities, the argmax
+  CU(cudaStreamWaitEvent(st, ctx->ev_u, 0));
+  kb_sample<<<dim3((unsigned)grid_for((int64_t)C, 128, ctx->sm_count * 16), Pu), 128, 0, st>>>(
+      ctx->U.as<double>(), C, d[0], dcols, p.cdf, K[0], p.mu[0], p.sigma[0], p.S, p.xT, p.oob);
+  kb_uni_sort_cands<<<dim3(1, Pu), 1024, 0, st>>>(p.xT, C, d[0], dcols, p.xs, p.cidx);
+  const unsigned ngrp = (unsigned)((C + 31) / 32);
+  static const int64_t fgt_min2 = [] { const char* v = getenv("TPE_FGT_MIN_K"); return v ? atoll(v) : 1024ll; }();
+  int nsl[2] = {1, 1};
+  for (int w = 0; w < 2; ++w) {
+    const double skip = std::min(46.0, log((double)std::max<int64_t>(K[w], 1)) + 30.0);
+    const bool fgt_w = cfg->magic_clip && K[w] >= fgt_min2;
+    kb_uni_grid<<<dim3(ngrp, Pu), kUniWarps * 32, 0, st>>>(p.s32[w], p.smi[w], p.sc[w], p.meta[w], d[w], K[w], p.xs, p.cidx, C,
+                                                           skip, p.part[w], fgt_w ? p.tlist : nullptr);
+    if (fgt_w) {
+      static bool fgt_attr = false;
+      if (!fgt_attr) {
+        CU(cudaFuncSetAttribute(kb_fgt_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFgtEvalSmem));
+        fgt_attr = true;
+      }
+      kb_fgt_eval<<<dim3((unsigned)((C + kFgtCands - 1) / kFgtCands), Pu), 256, kFgtEvalSmem, st>>>(
+          p.coef, p.box, p.bstart, p.s32[w], p.smi[w], p.sc[w], p.mu[w], p.sigma[w], p.cst[w], d[w], dcols, K[w],
+          cfg->magic_clip, p.xT, C, p.part[w]);
+      nsl[w] = 2;
+      ctx->launch_counter++;
+    }
+    kb_prior_fix<<<dim3((unsigned)(((int64_t)C * 32 + 255) / 256), Pu), 256, 0, st>>>(p.S, C, d[w], dcols, p.mu[w], p.sigma[w],
+                                                                                     p.cst[w], K[w], p.oob, p.fix[w]);
+    ctx->launch_counter += 2;
+  }
+  kb_acq2<<<dim3((unsigned)((C + 255) / 256), Pu), 256, 0, st>>>(
+      p.part[0], nsl[0], p.part[1], nsl[1], d[0], p.oob, p.fix[0], p.fix[1], C, p.logl, p.logg);
+  kb_select<<<dim3(1, Pu), 256, 0, st>>>(p.logl, p.logg, C, d[0], p.S, ctx->out_x.as<double>(), ctx->out_acq.as<double>(),
+                                         ctx->out_best.as<int64_t>());
+  ctx->launch_counter += 4;
+  CU(cudaGetLastError());
+  // what the next call may start from
+  ctx->ub_ord_cur ^= 1;
+  ctx->ub_ord_seq = ctx->uni_seq;
+  ctx->ub_ord_lineage = ctx->hist_lineage;
+  ctx->ub_ord_K = K[1];
+  ctx->ub_ord_ks = ks[1];
+  ctx->ub_ord_cols.assign(cols, cols + P);
+  ctx->last_kernel = (cfg->magic_clip && K[1] >= fgt_min2) ? "k_uni_grid<sorted 1-D> + k_fgt_eval (staged)"
+                                                           : "k_uni_grid<sorted 1-D> (staged)";
+  return TPE_OK;
+}
+
+
 // =================================================================================================
 extern "C" {
 
@@ -1464,7 +1718,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed, &ctx->mo_table,
                     &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv, &ctx->mo_fv, &ctx->mo_ps, &ctx->mo_map, &ctx->mo_front, &ctx->mo_head,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
-                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->mixcols, &ctx->uxs, &ctx->ucidx, &ctx->uni_prev_rows, &ctx->uni_mode, &ctx->uni_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
+                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->mixcols, &ctx->ub_arena, &ctx->ub_ord_a, &ctx->ub_ord_b, &ctx->ub_wstage, &ctx->uxs, &ctx->ucidx, &ctx->uni_prev_rows, &ctx->uni_mode, &ctx->uni_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->U2, &ctx->mt_spec, &ctx->mt_jump, &ctx->mt_tmp, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
@@ -2241,6 +2495,7 @@ int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n
 }
 
 // ---- the P sample_independent calls of one univariate trial, in one go -------------------------------------------
+
 static tpe_ctx* make_sub(tpe_ctx* parent) {
   tpe_ctx* c = new tpe_ctx();
   c->device = parent->device;
@@ -2329,6 +2584,28 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
   CU(ctx->out_x.ensure((size_t)n_cols * 8));
   CU(ctx->out_acq.ensure((size_t)n_cols * 8));
   CU(ctx->out_best.ensure((size_t)n_cols * 8));
+  // all columns continuous: stage by stage over all of them (one launch per stage)
+  static const bool staged_on = [] { const char* v = getenv("TPE_UNI_STAGED"); return !(v && v[0] == '0'); }();
+  bool staged = staged_on && C <= 4096 && n_cols >= 2;
+  for (const ColMeta& cm : ctx->cols_h) staged = staged && cm.cls == COL_CONT;
+  if (staged) {
+    ctx->launch_counter = 0;
+    rc = uni_batch_staged(ctx, cfg, cols, n_cols, w_below, w_above);
+    if (rc) return rc;
+    if (dev_rng) CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[8], ctx->stream));
+    CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_best) CU(cudaMemcpyAsync(out_best, ctx->out_best.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (dev_rng) ctx->mt_host_valid = true;
+    ctx->spec_pending = false;
+    for (int i = 0; i < 9; ++i) ctx->ms[i] = 0.0f;
+    cudaEventElapsedTime(&ctx->ms[8], ctx->ev[0], ctx->ev[8]);
+    ctx->launches = ctx->launch_counter;
+    ctx->prepared = ctx->built = ctx->sampled = false;
+    return TPE_OK;
+  }
   while ((int)ctx->uni_sub.size() < n_cols) {
     tpe_ctx* c = make_sub(ctx);
     if (!c) return fail(ctx, TPE_E_CUDA, "could not create the streams of a column context");

@@ -254,7 +254,7 @@ k_split_coop(int n, const int8_t* __restrict__ cat, const double* __restrict__ k
 // ================================================================================================
 // mu[k][j] for the n observation kernels and the prior kernel (k = n).  Categorical columns store
 // the observed choice index (prior: nch).
-__global__ void k_mu(const double* __restrict__ X, int32_t pall, const int64_t* __restrict__ rows, int64_t n,
+__device__ __forceinline__ void d_mu(const double* __restrict__ X, int32_t pall, const int64_t* __restrict__ rows, int64_t n,
                      const ColMeta* __restrict__ cols, int32_t pc, double* __restrict__ mu) {
   const int64_t total = (n + 1) * pc;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -271,6 +271,9 @@ __global__ void k_mu(const double* __restrict__ X, int32_t pall, const int64_t* 
     mu[t] = v;
   }
 }
+__global__ void
+k_mu(const double* __restrict__ X, int32_t pall, const int64_t* __restrict__ rows, int64_t n,
+                     const ColMeta* __restrict__ cols, int32_t pc, double* __restrict__ mu) { d_mu(X, pall, rows, n, cols, pc, mu); }
 
 // Bandwidth limits of parzen_estimator.py:220-228.
 __device__ __forceinline__ void sigma_limits(const ColMeta& cm, int64_t n, bool magic_clip, double& lo, double& hi) {
@@ -306,7 +309,7 @@ __global__ void k_sigma_mv(const ColMeta* __restrict__ cols, int32_t pc, int64_t
 
 // univariate: neighbour gaps in the sorted order of mu U {prior mu} (parzen_estimator.py:196-218).
 // order[j] = index (0..n, n = prior) of the j-th smallest value of column `j_col`.
-__global__ void k_sigma_uni(const double* __restrict__ mu, const int32_t* __restrict__ order,
+__device__ __forceinline__ void d_sigma_uni(const double* __restrict__ mu, const int32_t* __restrict__ order,
                             const ColMeta* __restrict__ cols, int32_t pc, int j_col, int64_t n, int magic_clip,
                             int endpoints, double* __restrict__ sigma) {
   const ColMeta cm = cols[j_col];
@@ -327,6 +330,10 @@ __global__ void k_sigma_uni(const double* __restrict__ mu, const int32_t* __rest
     sigma[me * pc + j_col] = (me == n) ? hi : g;
   }
 }
+__global__ void
+k_sigma_uni(const double* __restrict__ mu, const int32_t* __restrict__ order,
+                            const ColMeta* __restrict__ cols, int32_t pc, int j_col, int64_t n, int magic_clip,
+                            int endpoints, double* __restrict__ sigma) { d_sigma_uni(mu, order, cols, pc, j_col, n, magic_clip, endpoints, sigma); }
 
 // Stable LSD radix sort of one estimator column (cooperative launch, 8 passes of 8 bits) for the
 // univariate bandwidths: order[j] = index of the j-th smallest (value, index).  Each CTA owns a
@@ -335,8 +342,7 @@ __global__ void k_sigma_uni(const double* __restrict__ mu, const int32_t* __rest
 struct SortWork {
   int hist[256][160];  // [digit][cta]
 };
-__global__ void __launch_bounds__(512, 1)
-k_radix_sort_coop(const double* __restrict__ mu, int32_t pc, int j_col, int n, uint64_t* __restrict__ key_a,
+__device__ __forceinline__ void d_radix_sort_coop(const double* __restrict__ mu, int32_t pc, int j_col, int n, uint64_t* __restrict__ key_a,
                   uint64_t* __restrict__ key_b, int32_t* __restrict__ idx_a, int32_t* __restrict__ idx_b,
                   SortWork* __restrict__ wk, int32_t* __restrict__ order, const int* __restrict__ run_flag) {
   // run_flag != nullptr: the order may already have been brought up to date incrementally (k_order_update);
@@ -422,6 +428,10 @@ k_radix_sort_coop(const double* __restrict__ mu, int32_t pc, int j_col, int n, u
   }
   for (int i = lo + tid; i < hi; i += blockDim.x) order[i] = iin[i];
 }
+__global__ void __launch_bounds__(512, 1)
+k_radix_sort_coop(const double* __restrict__ mu, int32_t pc, int j_col, int n, uint64_t* __restrict__ key_a,
+                  uint64_t* __restrict__ key_b, int32_t* __restrict__ idx_a, int32_t* __restrict__ idx_b,
+                  SortWork* __restrict__ wk, int32_t* __restrict__ order, const int* __restrict__ run_flag) { d_radix_sort_coop(mu, pc, j_col, n, key_a, key_b, idx_a, idx_b, wk, order, run_flag); }
 
 // Incremental maintenance of a column's sorted order between two suggestions (univariate TPE): the above set of the
 // next trial is almost always the previous one plus the trial that has just finished.
@@ -439,8 +449,7 @@ __global__ void k_rows_delta(const int64_t* __restrict__ rows_new, const int64_t
     diff |= rows_new[i] != rows_old[i];
   if (diff) atomicOr(mode, 2);   // mode >= 2: sort
 }
-__global__ void __launch_bounds__(256)
-k_order_update(const int* __restrict__ mode, const int32_t* __restrict__ old_order, int K_old, int K_new,
+__device__ __forceinline__ void d_order_update(const int* __restrict__ mode, const int32_t* __restrict__ old_order, int K_old, int K_new,
                const double* __restrict__ mu, int32_t* __restrict__ out, int* __restrict__ work) {
   const int m = *mode;
   if (m >= 2) return;
@@ -478,10 +487,12 @@ k_order_update(const int* __restrict__ mode, const int32_t* __restrict__ old_ord
   }
   (void)K_new;
 }
+__global__ void __launch_bounds__(256)
+k_order_update(const int* __restrict__ mode, const int32_t* __restrict__ old_order, int K_old, int K_new,
+               const double* __restrict__ mu, int32_t* __restrict__ out, int* __restrict__ work) { d_order_update(mode, old_order, K_old, K_new, mu, out, work); }
 
 // Whole bitonic sort in shared memory for m2 <= 4096 (one CTA of 1024 threads).
-__global__ void __launch_bounds__(1024, 1)
-k_sort_small(const double* __restrict__ mu, int32_t pc, int j_col, int m, int m2, int32_t* __restrict__ order) {
+__device__ __forceinline__ void d_sort_small(const double* __restrict__ mu, int32_t pc, int j_col, int m, int m2, int32_t* __restrict__ order) {
   __shared__ double sv[4096];
   __shared__ int32_t si[4096];
   for (int i = threadIdx.x; i < m2; i += 1024) {
@@ -516,6 +527,8 @@ k_sort_small(const double* __restrict__ mu, int32_t pc, int j_col, int m, int m2
   }
   for (int i = threadIdx.x; i < m; i += 1024) order[i] = si[i];
 }
+__global__ void __launch_bounds__(1024, 1)
+k_sort_small(const double* __restrict__ mu, int32_t pc, int j_col, int m, int m2, int32_t* __restrict__ order) { d_sort_small(mu, pc, j_col, m, m2, order); }
 
 // Per-(kernel, column) constants.  One warp per kernel; lanes stride over columns.
 //   continuous: c = ln sqrt(2 pi) + M(a, b) + ln sigma      (a, b = normalised support)
@@ -808,7 +821,7 @@ __global__ void k_cat_tables(const ColMeta* __restrict__ cols, int32_t pc, int64
 // One thread per (candidate, column).  S[ct][j] = sampled value (internal representation),
 // xT[slot][ct] = kernel-space value of continuous columns (ln x for log columns) for the fast
 // log-density kernel, oob[ct] = 1 if a continuous value left [low, high] through rounding.
-__global__ void k_sample(const double* __restrict__ U, int64_t n_asks, int32_t C, const ColMeta* __restrict__ cols,
+__device__ __forceinline__ void d_sample(const double* __restrict__ U, int64_t n_asks, int32_t C, const ColMeta* __restrict__ cols,
                          int32_t pc, int32_t ncat, int32_t nnum, const double* __restrict__ cdf, int64_t Kb,
                          const double* __restrict__ mu, const double* __restrict__ sigma,
                          const double* __restrict__ tab, double* __restrict__ S, double* __restrict__ xT,
@@ -863,6 +876,12 @@ __global__ void k_sample(const double* __restrict__ U, int64_t n_asks, int32_t C
     S[ct * pc + j] = out;
   }
 }
+__global__ void
+k_sample(const double* __restrict__ U, int64_t n_asks, int32_t C, const ColMeta* __restrict__ cols,
+                         int32_t pc, int32_t ncat, int32_t nnum, const double* __restrict__ cdf, int64_t Kb,
+                         const double* __restrict__ mu, const double* __restrict__ sigma,
+                         const double* __restrict__ tab, double* __restrict__ S, double* __restrict__ xT,
+                         int64_t ct_stride, uint8_t* __restrict__ oob) { d_sample(U, n_asks, C, cols, pc, ncat, nnum, cdf, Kb, mu, sigma, tab, S, xT, ct_stride, oob); }
 
 // For tpe_logpdf on caller-supplied points: fill xT / oob from S.
 __global__ void k_prep_points(const double* __restrict__ S, int64_t n, const ColMeta* __restrict__ cols, int32_t pc,
@@ -978,7 +997,7 @@ __global__ void k_logpdf_generic(const double* __restrict__ S, int64_t Ct, const
 //    same cell formula as the generic path, summed by a shuffle tree -> one more partial row;
 //  * fix-up: a candidate outside [low, high] (rounding of ppf * sigma + mu; flagged by k_sample) is
 //    re-evaluated exactly against every kernel, lanes over the kernels.
-__global__ void k_logpdf_prior_fix(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols,
+__device__ __forceinline__ void d_logpdf_prior_fix(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols,
                                    int32_t pc, const double* __restrict__ mu, const double* __restrict__ sigma,
                                    const double* __restrict__ cst, int64_t K, const double* __restrict__ tab,
                                    double2* __restrict__ part_prior, const uint8_t* __restrict__ oob,
@@ -1009,6 +1028,12 @@ __global__ void k_logpdf_prior_fix(const double* __restrict__ S, int64_t Ct, con
     if (lane == 0) fix[ct] = make_double2(m, s);
   }
 }
+__global__ void
+k_logpdf_prior_fix(const double* __restrict__ S, int64_t Ct, const ColMeta* __restrict__ cols,
+                                   int32_t pc, const double* __restrict__ mu, const double* __restrict__ sigma,
+                                   const double* __restrict__ cst, int64_t K, const double* __restrict__ tab,
+                                   double2* __restrict__ part_prior, const uint8_t* __restrict__ oob,
+                                   double2* __restrict__ fix, int do_fix = 1) { d_logpdf_prior_fix(S, Ct, cols, pc, mu, sigma, cst, K, tab, part_prior, oob, fix, do_fix); }
 
 // Mixture weights of a small estimator (K <= 2048, i.e. the below set) in ONE launch: the bodies of
 // k_wraw, k_wfinal and k_wnorm with a single CTA (same summation order as their one-part case).
@@ -1754,7 +1779,7 @@ k_logpdf_mma(const double* __restrict__ tabm, const double* __restrict__ ckk, in
 // Grid-wide pass: logl/logg = merge of the k-split partials (or the fix-up value for
 // out-of-support candidates), written for every candidate.  One warp per candidate: lanes stride
 // over the partial rows (a single small ask has > 1000 of them), then a shuffle merge.
-__global__ void k_acq(const double2* __restrict__ part_l, int nsl, const double2* __restrict__ part_g, int nsg,
+__device__ __forceinline__ void d_acq(const double2* __restrict__ part_l, int nsl, const double2* __restrict__ part_g, int nsg,
                       int64_t ct_stride, const uint8_t* __restrict__ oob, const double2* __restrict__ fix_l,
                       const double2* __restrict__ fix_g, int64_t Ct, double* __restrict__ logl,
                       double* __restrict__ logg) {
@@ -1790,10 +1815,14 @@ __global__ void k_acq(const double2* __restrict__ part_l, int nsl, const double2
     }
   }
 }
+__global__ void
+k_acq(const double2* __restrict__ part_l, int nsl, const double2* __restrict__ part_g, int nsg,
+                      int64_t ct_stride, const uint8_t* __restrict__ oob, const double2* __restrict__ fix_l,
+                      const double2* __restrict__ fix_g, int64_t Ct, double* __restrict__ logl,
+                      double* __restrict__ logg) { d_acq(part_l, nsl, part_g, nsg, ct_stride, oob, fix_l, fix_g, Ct, logl, logg); }
 
 // One CTA per ask: acq = logl - logg, best = first maximum (NaN wins, like np.argmax).
-__global__ void __launch_bounds__(256)
-k_select(const double* __restrict__ logl, const double* __restrict__ logg, int32_t C, const double* __restrict__ S,
+__device__ __forceinline__ void d_select(const double* __restrict__ logl, const double* __restrict__ logg, int32_t C, const double* __restrict__ S,
          int32_t pc, double* __restrict__ out_x, double* __restrict__ out_acq, int64_t* __restrict__ out_best) {
   __shared__ double s_val[256];
   __shared__ int s_idx[256];
@@ -1843,6 +1872,9 @@ k_select(const double* __restrict__ logl, const double* __restrict__ logg, int32
   }
   for (int j = tid; j < pc; j += 256) out_x[ask * pc + j] = S[(ask * C + bi) * pc + j];
 }
+__global__ void __launch_bounds__(256)
+k_select(const double* __restrict__ logl, const double* __restrict__ logg, int32_t C, const double* __restrict__ S,
+         int32_t pc, double* __restrict__ out_x, double* __restrict__ out_acq, int64_t* __restrict__ out_best) { d_select(logl, logg, C, S, pc, out_x, out_acq, out_best); }
 
 // Merge k-split partials into final log-densities (tpe_logpdf entry point).
 __global__ void k_finish_logpdf(const double2* __restrict__ part, int ns, int64_t ct_stride,

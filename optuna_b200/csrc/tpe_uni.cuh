@@ -76,9 +76,11 @@ struct FgtGeom {
 constexpr int kFgtMaxBoxes = 288;
 constexpr int kFgtTerms = 24;          // Taylor terms per box (remainder <= 4e-14 of the box's own sum for |y| <= 9)
 constexpr double kFgtYmax = 9.0;       // boxes further away (in units of sigma_floor * sqrt 2) are summed directly
+constexpr int kFgtRow = 25;            // k_fgt_eval: padded coefficient row in shared memory
+constexpr int kFgtCands = 128;         // k_fgt_eval: candidates per block
+constexpr size_t kFgtEvalSmem = (64 + (size_t)kFgtMaxBoxes * kFgtRow) * 8 + (size_t)kFgtMaxBoxes * 16;
 
-__global__ void __launch_bounds__(kUniTile)
-k_uni_tables(const int32_t* __restrict__ order, const double* __restrict__ mu, const double* __restrict__ sigma,
+__device__ __forceinline__ void d_uni_tables(const int32_t* __restrict__ order, const double* __restrict__ mu, const double* __restrict__ sigma,
              const double* __restrict__ cst, const ColMeta* __restrict__ cols, int64_t K, float4* __restrict__ s32,
              double2* __restrict__ smi, double* __restrict__ sc, UniTileMeta* __restrict__ meta, int fgt,
              int magic_clip, int32_t* __restrict__ bstart) {
@@ -135,6 +137,41 @@ k_uni_tables(const int32_t* __restrict__ order, const double* __restrict__ mu, c
     meta[blockIdx.x] = t;
   }
 }
+__global__ void __launch_bounds__(kUniTile)
+k_uni_tables(const int32_t* __restrict__ order, const double* __restrict__ mu, const double* __restrict__ sigma,
+             const double* __restrict__ cst, const ColMeta* __restrict__ cols, int64_t K, float4* __restrict__ s32,
+             double2* __restrict__ smi, double* __restrict__ sc, UniTileMeta* __restrict__ meta, int fgt,
+             int magic_clip, int32_t* __restrict__ bstart) { d_uni_tables(order, mu, sigma, cst, cols, K, s32, smi, sc, meta, fgt, magic_clip, bstart); }
+
+// The tiles that hold a kernel k_uni_grid has to evaluate itself (cmax > -inf), ascending: with the fast Gauss transform
+// on these are a handful (the prior, sparse regions), and the grid walks this list instead of all tiles.
+// One block of 256 threads; list[0] = count, list[1 ..] = tile indices.
+__device__ __forceinline__ void d_uni_tile_list(const UniTileMeta* __restrict__ meta, int ntiles, int32_t* __restrict__ list) {
+  __shared__ int s_cnt[256];
+  const int per = (ntiles + 255) / 256;
+  const int t0 = threadIdx.x * per, t1 = min(ntiles, t0 + per);
+  int cnt = 0;
+  for (int t = t0; t < t1; ++t) cnt += meta[t].cmax > -INFINITY ? 1 : 0;
+  s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < 256; ++i) {
+      const int v = s_cnt[i];
+      s_cnt[i] = run;
+      run += v;
+    }
+    list[0] = run;
+  }
+  __syncthreads();
+  int at = s_cnt[threadIdx.x];
+  for (int t = t0; t < t1; ++t)
+    if (meta[t].cmax > -INFINITY) list[1 + at++] = t;
+}
+__global__ void __launch_bounds__(256)
+k_uni_tile_list(const UniTileMeta* __restrict__ meta, int ntiles, int32_t* __restrict__ list) {
+  d_uni_tile_list(meta, ntiles, list);
+}
 
 // ---- fast Gauss transform for the kernels at the bandwidth floor -------------------------------------------------
 // With thousands of observations nearly every kernel of a 1-D estimator has sigma = sigma_floor = range / 100
@@ -158,8 +195,7 @@ struct FgtBox {
 };
 
 // grid = boxes, 128 threads
-__global__ void __launch_bounds__(128)
-k_fgt_coeff(const int32_t* __restrict__ order, const double* __restrict__ mu, const double* __restrict__ sigma,
+__device__ __forceinline__ void d_fgt_coeff(const int32_t* __restrict__ order, const double* __restrict__ mu, const double* __restrict__ sigma,
             const double* __restrict__ cst, const ColMeta* __restrict__ cols, int64_t K, int magic_clip,
             const int32_t* __restrict__ bstart, double* __restrict__ coef, FgtBox* __restrict__ box) {
   __shared__ double s_red[4][kFgtTerms];
@@ -212,28 +248,38 @@ k_fgt_coeff(const int32_t* __restrict__ order, const double* __restrict__ mu, co
   if (threadIdx.x < kFgtTerms) {
     const int n = threadIdx.x;
     const double v = (s_red[0][n] + s_red[1][n]) + (s_red[2][n] + s_red[3][n]);
-    coef[(size_t)b * kFgtTerms + n] = v;
+    coef[(size_t)b * kFgtRow + n] = v;
     if (n == 0) box[b] = FgtBox{ref, (ref > -INFINITY) ? ref + log(v) : -INFINITY};
   }
 }
+__global__ void __launch_bounds__(128)
+k_fgt_coeff(const int32_t* __restrict__ order, const double* __restrict__ mu, const double* __restrict__ sigma,
+            const double* __restrict__ cst, const ColMeta* __restrict__ cols, int64_t K, int magic_clip,
+            const int32_t* __restrict__ bstart, double* __restrict__ coef, FgtBox* __restrict__ box) { d_fgt_coeff(order, mu, sigma, cst, cols, K, magic_clip, bstart, coef, box); }
 
-// part[c] = (reference, sum) of the floor-bandwidth kernels for candidate c; one warp per candidate.
+// part[c] = (reference, sum) of the floor-bandwidth kernels for candidate c.  A block takes kFgtCands candidates of one
+// column (one warp per candidate, eight at a time) and stages the column's coefficients and box table in shared memory
+// first (rows padded to 25 doubles: a half-warp reading 16 consecutive boxes touches 16 different bank pairs).
 //   xT [C] kernel-space coordinate of the candidates (log applied), in ask order
-__global__ void __launch_bounds__(256)
-k_fgt_eval(const double* __restrict__ coef, const FgtBox* __restrict__ box, const int32_t* __restrict__ bstart,
+__device__ __forceinline__ void d_fgt_eval(const double* __restrict__ coef, const FgtBox* __restrict__ box, const int32_t* __restrict__ bstart,
            const float4* __restrict__ s32, const double2* __restrict__ smi, const double* __restrict__ sc,
            const double* __restrict__ mu,
            const double* __restrict__ sigma, const double* __restrict__ cst, const ColMeta* __restrict__ cols,
            int64_t K, int magic_clip, const double* __restrict__ xT, int C, double2* __restrict__ part) {
-  __shared__ double s_e64[64];
-  if (threadIdx.x < 64) s_e64[threadIdx.x] = exp2((double)threadIdx.x * 0.015625);
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int c = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-  if (c >= C) return;
+  extern __shared__ __align__(16) double s_fgt[];
+  double* s_e64 = s_fgt;                                    // [64]
+  double* s_coef = s_fgt + 64;                              // [nb][kFgtRow]
   const ColMeta cm = cols[0];
   FgtGeom g;
   g.init(cm, K - 1, magic_clip != 0);
+  FgtBox* s_box = reinterpret_cast<FgtBox*>(s_coef + (size_t)kFgtMaxBoxes * kFgtRow);   // [nb]
+  if (threadIdx.x < 64) s_e64[threadIdx.x] = exp2((double)threadIdx.x * 0.015625);
+  for (int i = threadIdx.x; i < g.nb * kFgtRow; i += blockDim.x) s_coef[i] = coef[i];   // (rows padded to kFgtRow)
+  for (int i = threadIdx.x; i < g.nb; i += blockDim.x) s_box[i] = box[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int c_end = min(C, (int)(blockIdx.x + 1) * kFgtCands);
+  for (int c = blockIdx.x * kFgtCands + (threadIdx.x >> 5); c < c_end; c += (int)(blockDim.x >> 5)) {
   const double x = xT[c];
   const double inv = 1.0 / g.scale;
   // floor of the scale: the prior kernel's term (it is summed by k_uni_grid; here it only decides what is negligible)
@@ -244,7 +290,7 @@ k_fgt_eval(const double* __restrict__ coef, const FgtBox* __restrict__ box, cons
     if (!(best > -INFINITY)) best = -INFINITY;
   }
   for (int b = lane; b < g.nb; b += 32) {
-    const FgtBox bx = box[b];
+    const FgtBox bx = s_box[b];
     if (!(bx.lnw > -INFINITY)) continue;
     const double y = fabs((x - g.centre(b)) * inv) + 0.125;
     best = fmax(best, bx.lnw - y * y);
@@ -253,20 +299,20 @@ k_fgt_eval(const double* __restrict__ coef, const FgtBox* __restrict__ box, cons
   for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
   if (!(best > -INFINITY)) {                    // NaN candidate / no kernels at all
     if (lane == 0) part[c] = make_double2(-INFINITY, 0.0);
-    return;
+    continue;
   }
   const double drop = 30.0 + log((double)g.nb);
   const double ctr = TPE_MUL(0.5, TPE_ADD(cm.klow, cm.khigh));
   double sum = 0.0;
   for (int b = lane; b < g.nb; b += 32) {
-    const FgtBox bx = box[b];
+    const FgtBox bx = s_box[b];
     if (!(bx.lnw > -INFINITY)) continue;
     const double y = (x - g.centre(b)) * inv;
     const double ay = fabs(y);
     const double near = fmax(ay - 0.125, 0.0);
     if (bx.lnw - near * near < best - drop) continue;
     if (ay <= kFgtYmax) {
-      const double* __restrict__ a = coef + (size_t)b * kFgtTerms;
+      const double* __restrict__ a = s_coef + (size_t)b * kFgtRow;
       // sum_n A_n H_n(y):  H_0 = 1, H_1 = 2y, H_(n+1) = 2y H_n - 2n H_(n-1)
       const double y2 = 2.0 * y;
       double hm = 1.0, h = y2;
@@ -296,12 +342,18 @@ k_fgt_eval(const double* __restrict__ coef, const FgtBox* __restrict__ box, cons
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if (lane == 0) part[c] = (sum > 0.0) ? make_double2(best, sum) : make_double2(-INFINITY, 0.0);
+  }
 }
+__global__ void __launch_bounds__(256)
+k_fgt_eval(const double* __restrict__ coef, const FgtBox* __restrict__ box, const int32_t* __restrict__ bstart,
+           const float4* __restrict__ s32, const double2* __restrict__ smi, const double* __restrict__ sc,
+           const double* __restrict__ mu,
+           const double* __restrict__ sigma, const double* __restrict__ cst, const ColMeta* __restrict__ cols,
+           int64_t K, int magic_clip, const double* __restrict__ xT, int C, double2* __restrict__ part) { d_fgt_eval(coef, box, bstart, s32, smi, sc, mu, sigma, cst, cols, K, magic_clip, xT, C, part); }
 
 // The candidates of one ask in ascending kernel-space order: xs[i] = x' = x - ctr of the i-th smallest,
 // cidx[i] = its index.  One CTA of 1024 threads, bitonic sort in shared memory (C <= 4096), ties by index.
-__global__ void __launch_bounds__(1024, 1)
-k_uni_sort_cands(const double* __restrict__ xT, int C, const ColMeta* __restrict__ cols, double* __restrict__ xs,
+__device__ __forceinline__ void d_uni_sort_cands(const double* __restrict__ xT, int C, const ColMeta* __restrict__ cols, double* __restrict__ xs,
                  int32_t* __restrict__ cidx) {
   __shared__ double sv[4096];
   __shared__ int32_t si[4096];
@@ -339,6 +391,9 @@ k_uni_sort_cands(const double* __restrict__ xT, int C, const ColMeta* __restrict
     }
   }
 }
+__global__ void __launch_bounds__(1024, 1)
+k_uni_sort_cands(const double* __restrict__ xT, int C, const ColMeta* __restrict__ cols, double* __restrict__ xs,
+                 int32_t* __restrict__ cidx) { d_uni_sort_cands(xT, C, cols, xs, cidx); }
 
 // part[cidx] = (reference, sum of e^(L - reference)) of the 1-D mixture for every candidate.
 // CTA = 8 warps on the SAME 32 neighbouring candidates (lane = candidate): warp w takes the tiles at distance
@@ -350,10 +405,10 @@ k_uni_sort_cands(const double* __restrict__ xT, int C, const ColMeta* __restrict
 // evaluated in fp64 -- there is no fp32 tier here; pairs and whole tiles that cannot reach that window are
 // dismissed by the two rigorous bounds described at the top of this file.
 constexpr int kUniWarps = 8;
-__global__ void __launch_bounds__(kUniWarps * 32)
-k_uni_grid(const float4* __restrict__ s32, const double2* __restrict__ smi, const double* __restrict__ sc,
+__device__ __forceinline__ void d_uni_grid(const float4* __restrict__ s32, const double2* __restrict__ smi, const double* __restrict__ sc,
            const UniTileMeta* __restrict__ meta, int64_t K, const double* __restrict__ xs,
-           const int32_t* __restrict__ cidx, int C, double lse_skip, double2* __restrict__ part) {
+           const int32_t* __restrict__ cidx, int C, double lse_skip, double2* __restrict__ part,
+           const int32_t* __restrict__ tlist) {
   __shared__ double s_ref[kUniWarps][32];
   __shared__ double s_sum[kUniWarps][32];
   // one staged tile per warp: the three table slices are fetched with 10 independent coalesced loads per lane
@@ -458,9 +513,19 @@ k_uni_grid(const float4* __restrict__ s32, const double2* __restrict__ smi, cons
       }
     }
   };
-  for (int dt = warp; dt < ntiles; dt += kUniWarps) {
-    for (int side = 0; side < 2; ++side) {
-      const int t = side == 0 ? tstart + dt : tstart - 1 - dt;
+  // tlist != nullptr: only the listed tiles hold kernels this kernel evaluates (ascending; the tile under the
+  // candidates comes first in any case: the running maxima start there)
+  const int nlist = tlist != nullptr ? tlist[0] : 0;
+  const int nwalk = tlist != nullptr ? nlist + 1 : ntiles;
+  for (int dt = warp; dt < nwalk; dt += kUniWarps) {
+    for (int side = 0; side < (tlist != nullptr ? 1 : 2); ++side) {
+      int t;
+      if (tlist != nullptr) {
+        t = dt == 0 ? tstart : tlist[dt];
+        if (dt != 0 && t == tstart) continue;
+      } else {
+        t = side == 0 ? tstart + dt : tstart - 1 - dt;
+      }
       if (t < 0 || t >= ntiles) continue;
       if (t != tstart) {
         const UniTileMeta tm = meta[t];
@@ -493,5 +558,10 @@ k_uni_grid(const float4* __restrict__ s32, const double2* __restrict__ smi, cons
     part[cidx[i]] = (r > -INFINITY) ? make_double2(r, tot) : make_double2(-INFINITY, 0.0);
   }
 }
+__global__ void __launch_bounds__(kUniWarps * 32)
+k_uni_grid(const float4* __restrict__ s32, const double2* __restrict__ smi, const double* __restrict__ sc,
+           const UniTileMeta* __restrict__ meta, int64_t K, const double* __restrict__ xs,
+           const int32_t* __restrict__ cidx, int C, double lse_skip, double2* __restrict__ part,
+           const int32_t* __restrict__ tlist) { d_uni_grid(s32, smi, sc, meta, K, xs, cidx, C, lse_skip, part, tlist); }
 
 }  // namespace tpe

@@ -736,7 +736,8 @@ def test_univariate_batch_equals_the_per_parameter_calls(eng):
         eng.suggest_univariate_batch([0, 2], np.zeros(2 * 2 * 24), n_below=25, n_candidates=24, multivariate=False)
 
 
-def test_univariate_batch_incremental_orders_equal_fresh_sorts(eng):
+@pytest.mark.parametrize("all_continuous", [False, True])
+def test_univariate_batch_incremental_orders_equal_fresh_sorts(eng, all_continuous):
     """Between two univariate batch calls the column contexts keep each column's sorted order and bring it up to date
     (identical rows: reuse; one trial appended: insert) instead of sorting again.  A long-lived engine fed one trial
     at a time must answer bit-identically to a fresh engine that sorts from scratch, through every kind of change:
@@ -746,11 +747,20 @@ def test_univariate_batch_incremental_orders_equal_fresh_sorts(eng):
     from optuna_b200 import TPEEngine
     from optuna_b200.engine import ParamSpec
     rs = np.random.RandomState(77)
-    specs = [ParamSpec(kind=0, low=-1.0, high=2.0), ParamSpec(kind=0, low=0.0, high=3.0, step=0.25),
-             ParamSpec(kind=1, low=0, high=20, step=1), ParamSpec(kind=0, low=1e-3, high=10.0, log=True)]
+    # all_continuous: the staged path (one launch per stage over all columns, tpe_unib.cuh); otherwise one column
+    # context per column (discrete columns take the general kernels)
+    if all_continuous:
+        specs = [ParamSpec(kind=0, low=-1.0, high=2.0), ParamSpec(kind=0, low=0.0, high=3.0),
+                 ParamSpec(kind=0, low=0.0, high=20.0), ParamSpec(kind=0, low=1e-3, high=10.0, log=True)]
+    else:
+        specs = [ParamSpec(kind=0, low=-1.0, high=2.0), ParamSpec(kind=0, low=0.0, high=3.0, step=0.25),
+                 ParamSpec(kind=1, low=0, high=20, step=1), ParamSpec(kind=0, low=1e-3, high=10.0, log=True)]
     P, n0, C = len(specs), 6000, 64
 
     def draw(n):
+        if all_continuous:   # (the third column repeats values: ties in a continuous column)
+            return np.stack([rs.uniform(-1, 2, n), rs.uniform(0, 3, n), rs.randint(0, 21, n).astype(float),
+                             np.exp(rs.uniform(np.log(1e-3), np.log(10), n))], 1)
         return np.stack([rs.uniform(-1, 2, n), rs.randint(0, 13, n) * 0.25, rs.randint(0, 21, n).astype(float),
                          np.exp(rs.uniform(np.log(1e-3), np.log(10), n))], 1)
 
