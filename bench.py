@@ -486,6 +486,27 @@ def run_b200(args) -> None:
         extras["univariate_trial_ms"] = unib * 1e3
         extras["univariate_suggestions_per_s"] = 1.0 / unib
         extras["univariate_device_ms"] = float(eng.last_timing()[0][8])
+        # the same through optuna's Study: the reference's default sampler mode (multivariate=False), 32
+        # sample_independent calls per trial answered from one batched device call (B200TPESampler._plan_trial)
+        try:
+            usampler = B200TPESampler(seed=11, n_ei_candidates=N_CAND, multivariate=False, device=local)
+            study.sampler = usampler
+            for rep in range(3):
+                one_trial()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_uni = 20
+            for rep in range(n_uni):
+                one_trial()
+            torch.cuda.synchronize()
+            ue = (time.perf_counter() - t0) / n_uni
+            extras["univariate_e2e"] = {"trial_ms": ue * 1e3, "trials_per_s": 1.0 / ue, "trials": n_uni,
+                                        "path": "optuna Study.ask -> 32 x trial.suggest_float -> sample_independent "
+                                                "-> tpe_suggest_univariate_batch (first call of the trial) -> study.tell"}
+            study.sampler = sampler
+            usampler.close()
+        except Exception as e:
+            extras["univariate_e2e"] = {"error": repr(e)}
         # config 4: MOTPE, 20 000 trials x 8 floats, 4 objectives, C = 24 -- with the default gamma (25 below trials)
         # and with gamma = ceil(0.1 n) (2000 below trials: rank peeling + HSSP over a 150-point tie rank + hypervolume
         # weights over the below set's Pareto front), next to the reference's own split + weights on the same values

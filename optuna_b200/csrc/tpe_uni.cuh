@@ -454,6 +454,7 @@ __device__ __forceinline__ void d_uni_grid(const float4* __restrict__ s32, const
   double ref = s_ref[0][lane];
 #pragma unroll
   for (int w = 1; w < kUniWarps; ++w) ref = fmax(ref, s_ref[w][lane]);
+  __syncthreads();                           // s_ref is written again at the end (a warp without tiles gets there at once)
   if (!(ref > -INFINITY)) ref = -INFINITY;   // an all-padding tile cannot happen for tstart; NaN x stays dead
   double mrun = ref;                         // lower bound of the candidate's max (it IS one of its terms)
   float thrf = __double2float_rd(mrun - skip);
