@@ -501,8 +501,11 @@ def run_b200(args) -> None:
             torch.cuda.synchronize()
             ue = (time.perf_counter() - t0) / n_uni
             extras["univariate_e2e"] = {"trial_ms": ue * 1e3, "trials_per_s": 1.0 / ue, "trials": n_uni,
+                                        "look_ahead": list(usampler.ahead_stats),
                                         "path": "optuna Study.ask -> 32 x trial.suggest_float -> sample_independent "
-                                                "-> tpe_suggest_univariate_batch (first call of the trial) -> study.tell"}
+                                                "(the first call of a trial collects the batch queued when the last "
+                                                "trial was told: tpe_collect_univariate) -> study.tell [after_trial -> "
+                                                "tpe_history_update / tpe_suggest_univariate_batch_async]"}
             study.sampler = sampler
             usampler.close()
         except Exception as e:

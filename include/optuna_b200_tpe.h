@@ -33,7 +33,8 @@ extern "C" {
 /* 3: + TPE_CAT_EXCLUDED; tpe_history_update may extend the history; tpe_sample_and_select accepts out_x == NULL
  *      (results stay on the device: tpe_result_device_ptrs); tpe_rng_state_device; tpe_suggest_univariate_batch */
 /* 4: + tpe_sample_and_select_async / tpe_collect */
-#define TPE_ABI_VERSION 4
+/* 5: + tpe_suggest_univariate_batch_async / tpe_collect_univariate */
+#define TPE_ABI_VERSION 5
 
 enum {
   TPE_OK = 0,
@@ -185,6 +186,14 @@ int tpe_suggest(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n
 int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
                                  const double* w_below, const double* w_above, const double* uniforms,
                                  double* out_x, double* out_acq, int64_t* out_best);
+
+/* The same in two halves (as tpe_sample_and_select_async / tpe_collect): queue the whole batch and return; collect
+ * waits and hands the results out.  Only for trials whose selected parameters are all continuous (the path that runs
+ * stage by stage over all columns); TPE_E_STATE "not batchable asynchronously" otherwise.  `uniforms`, `w_below` and
+ * `w_above` are read before the call returns. */
+int tpe_suggest_univariate_batch_async(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
+                                       const double* w_below, const double* w_above, const double* uniforms);
+int tpe_collect_univariate(tpe_ctx* ctx, double* out_x, double* out_acq, int64_t* out_best);
 
 /* Optional: start the upload of the uniforms of the NEXT tpe_sample_and_select early (e.g. right
  * after tpe_prepare, so that the copy overlaps tpe_build).  `count` doubles are copied from

@@ -61,6 +61,8 @@ SYMBOLS = {
     "tpe_host_free": (C.c_int, [_P, _P]),
     "tpe_suggest": (C.c_int, [_P, C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P]),
     "tpe_suggest_univariate_batch": (C.c_int, [_P, C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "tpe_suggest_univariate_batch_async": (C.c_int, [_P, C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P]),
+    "tpe_collect_univariate": (C.c_int, [_P, _P, _P, _P]),
     "tpe_get_split_info": (C.c_int, [_P, C.POINTER(SplitInfo)]),
     "tpe_get_split": (C.c_int, [_P, _P, _P]),
     "tpe_get_mixture": (C.c_int, [_P, C.c_int, _P, _P, _P]),
@@ -75,7 +77,7 @@ SYMBOLS = {
 _lib = None
 
 
-ABI_VERSION = 4  # include/optuna_b200_tpe.h TPE_ABI_VERSION
+ABI_VERSION = 5  # include/optuna_b200_tpe.h TPE_ABI_VERSION
 
 
 def load() -> C.CDLL:

@@ -137,7 +137,8 @@ struct tpe_ctx {
   cudaEvent_t ev_spec = nullptr;
   bool spec_pending = false, mt_host_valid = false;
   int64_t spec_count = 0;
-  uint32_t mt_host[625] = {0};   // host copy of mt_state, read back with the results of the ask
+  uint32_t* mt_host = nullptr;   // page-locked host copy of mt_state (625 words), read back with the results of the ask
+                                 // (page-locked: a copy into pageable memory would make the asynchronous entry points wait)
   cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;
   std::string err;
@@ -207,7 +208,6 @@ struct tpe_ctx {
   uint64_t ub_ord_seq = 0, ub_ord_lineage = 0;
   int64_t ub_ord_K = -1, ub_ord_ks = 0;
   std::vector<int32_t> ub_ord_cols;
-  std::vector<ColMeta> ub_cols_h;
   int ub_sort_g = 0;
   bool mixed_ok = false;         // the selected columns suit k_logpdf_mixed (setup_columns)
   std::vector<MixCol> mixcols_h;
@@ -215,6 +215,8 @@ struct tpe_ctx {
   int mix_ncont = 0, mix_nd = 0, mix_tabd = 0;
   bool user_points = false;      // the resident candidates came through tpe_logpdf, not from k_sample
   bool deferred = false;         // tpe_sample_and_select_async issued, tpe_collect not yet called
+  int64_t deferred_uni = 0;      // tpe_suggest_univariate_batch_async issued (columns), not yet collected
+  bool deferred_uni_rng = false;
   bool issued_dev_rng = false;
   void* res_host = nullptr;      // page-locked staging of deferred results
   size_t res_host_cap = 0;
@@ -1532,13 +1534,8 @@ static int uni_batch_staged(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* col
     d[w].cs = cs;
     d[w].pall = (int32_t)ctx->space.size();
   }
-  // every column as the only one of its context (setup_columns with one column: slot and RNG rank 0)
-  ctx->ub_cols_h.assign(ctx->cols_h.begin(), ctx->cols_h.begin() + P);
-  for (ColMeta& cm : ctx->ub_cols_h) {
-    cm.slot = 0;
-    cm.num_rank = 0;
-  }
-  CU(cudaMemcpyAsync(p.cols, ctx->ub_cols_h.data(), sizeof(ColMeta) * P, cudaMemcpyHostToDevice, st));
+  kb_cols<<<(P + 63) / 64, 64, 0, st>>>(ctx->cols.as<ColMeta>(), P, p.cols);   // (on the device: a copy from pageable
+                                                                               // host memory would wait for the split)
   const ColMeta* dcols = p.cols;
   const int cap = ctx->sm_count * 8;
   const unsigned Pu = (unsigned)P;
@@ -1701,6 +1698,13 @@ int tpe_ctx_create(int device, tpe_ctx** out) {
   cudaEventCreateWithFlags(&ctx->ev_spec, cudaEventDisableTiming);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  void* mh = nullptr;
+  if (cudaHostAlloc(&mh, 625 * 4, cudaHostAllocDefault) != cudaSuccess) {
+    tpe_ctx_destroy(ctx);
+    return TPE_E_NOMEM;
+  }
+  memset(mh, 0, 625 * 4);
+  ctx->mt_host = static_cast<uint32_t*>(mh);
   *out = ctx;
   return TPE_OK;
 }
@@ -1724,6 +1728,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   ctx->est[0].release();
   ctx->est[1].release();
   if (ctx->res_host) cudaFreeHost(ctx->res_host);
+  if (ctx->mt_host) cudaFreeHost(ctx->mt_host);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -2034,6 +2039,7 @@ static int prepare_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols,
   ctx->cfg = *cfg;
   ctx->launch_counter = 0;
   ctx->deferred = false;   // a new sequence abandons results nobody collected
+  ctx->deferred_uni = 0;
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   bool need_rowok = false;
   if (int rc0 = setup_columns(ctx, cfg, cols, n_cols, &need_rowok)) return rc0;
@@ -2221,7 +2227,7 @@ static int launch_sample_select(tpe_ctx* ctx, int64_t n_asks, bool used_dev_rng,
       ctx->spec_count = count;
     }
     // the generator's end state comes back with the results (tpe_rng_state then needs no device access)
-    CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, (size_t)625 * 4, cudaMemcpyDeviceToHost, st));
   }
   rc = run_logpdf(ctx, 0, Ct);
   if (rc) return rc;
@@ -2396,7 +2402,7 @@ int tpe_rng_state(tpe_ctx* ctx, uint32_t* key_out, int32_t* pos_out) {
   if (!ctx->mt_state.p) return fail(ctx, TPE_E_STATE, "tpe_stage_uniforms_mt19937 must precede tpe_rng_state");
   if (!ctx->mt_host_valid) {  // not yet read back with the results of an ask
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_u, 0));
-    CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, (size_t)625 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->mt_host_valid = true;
   }
@@ -2516,12 +2522,11 @@ static tpe_ctx* make_sub(tpe_ctx* parent) {
   return c;
 }
 
-int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
-                                 const double* w_below, const double* w_above, const double* uniforms, double* out_x,
-                                 double* out_acq, int64_t* out_best) {
-  if (!ctx) return TPE_E_INVALID;
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  if (!cfg || !cols || n_cols <= 0 || !out_x) return fail(ctx, TPE_E_INVALID, "bad arguments");
+static int uni_batch_locked(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
+                            const double* w_below, const double* w_above, const double* uniforms, double* out_x,
+                            double* out_acq, int64_t* out_best, bool defer) {
+  if (!cfg || !cols || n_cols <= 0 || (!out_x && !defer)) return fail(ctx, TPE_E_INVALID, "bad arguments");
+  ctx->deferred_uni = 0;
   if (cfg->multivariate) return fail(ctx, TPE_E_INVALID, "tpe_suggest_univariate_batch is for multivariate = 0");
   if (ctx->M >= 2) return fail(ctx, TPE_E_STATE, "not batchable: multi-objective history (use the per-parameter calls)");
   if (set_device(ctx)) return TPE_E_CUDA;
@@ -2592,8 +2597,28 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
     ctx->launch_counter = 0;
     rc = uni_batch_staged(ctx, cfg, cols, n_cols, w_below, w_above);
     if (rc) return rc;
-    if (dev_rng) CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dev_rng) CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, (size_t)625 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev[8], ctx->stream));
+    if (defer) {   // results into the page-locked staging area; tpe_collect_univariate waits and hands them out
+      const size_t need = (size_t)n_cols * 3 * 8;
+      if (ctx->res_host_cap < need) {
+        if (ctx->res_host) cudaFreeHost(ctx->res_host);
+        ctx->res_host = nullptr;
+        ctx->res_host_cap = 0;
+        CU(cudaHostAlloc(&ctx->res_host, need + 4096, cudaHostAllocDefault));
+        ctx->res_host_cap = need + 4096;
+      }
+      char* h = static_cast<char*>(ctx->res_host);
+      CU(cudaMemcpyAsync(h, ctx->out_x.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(h + (size_t)n_cols * 8, ctx->out_acq.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(h + (size_t)n_cols * 16, ctx->out_best.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->deferred_uni = n_cols;
+      ctx->deferred_uni_rng = dev_rng;
+      ctx->spec_pending = false;
+      ctx->launches = ctx->launch_counter;
+      ctx->prepared = ctx->built = ctx->sampled = false;
+      return TPE_OK;
+    }
     CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_best) CU(cudaMemcpyAsync(out_best, ctx->out_best.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2606,6 +2631,9 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
     ctx->prepared = ctx->built = ctx->sampled = false;
     return TPE_OK;
   }
+  if (defer)
+    return fail(ctx, TPE_E_STATE, "not batchable asynchronously: only trials whose parameters are all continuous are "
+                "evaluated stage by stage");
   while ((int)ctx->uni_sub.size() < n_cols) {
     tpe_ctx* c = make_sub(ctx);
     if (!c) return fail(ctx, TPE_E_CUDA, "could not create the streams of a column context");
@@ -2696,7 +2724,7 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
     CU(cudaStreamWaitEvent(ctx->stream, ctx->uni_sub[(size_t)j]->ev_join, 0));
     launches += ctx->uni_sub[(size_t)j]->launch_counter;
   }
-  if (dev_rng) CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, sizeof(ctx->mt_host), cudaMemcpyDeviceToHost, ctx->stream));
+  if (dev_rng) CU(cudaMemcpyAsync(ctx->mt_host, ctx->mt_state.p, (size_t)625 * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev[8], ctx->stream));
   CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2709,6 +2737,40 @@ int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t
   ctx->launches = launches;
   ctx->last_kernel = ctx->uni_sub[0]->last_kernel;
   ctx->prepared = ctx->built = ctx->sampled = false;   // the per-column state lives in the column contexts
+  return TPE_OK;
+}
+
+int tpe_suggest_univariate_batch(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
+                                 const double* w_below, const double* w_above, const double* uniforms, double* out_x,
+                                 double* out_acq, int64_t* out_best) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return uni_batch_locked(ctx, cfg, cols, n_cols, w_below, w_above, uniforms, out_x, out_acq, out_best, false);
+}
+
+int tpe_suggest_univariate_batch_async(tpe_ctx* ctx, const tpe_cfg* cfg, const int32_t* cols, int32_t n_cols,
+                                       const double* w_below, const double* w_above, const double* uniforms) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return uni_batch_locked(ctx, cfg, cols, n_cols, w_below, w_above, uniforms, nullptr, nullptr, nullptr, true);
+}
+
+int tpe_collect_univariate(tpe_ctx* ctx, double* out_x, double* out_acq, int64_t* out_best) {
+  if (!ctx) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ctx->deferred_uni <= 0)
+    return fail(ctx, TPE_E_STATE, "tpe_collect_univariate needs a pending tpe_suggest_univariate_batch_async");
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  const int64_t n = ctx->deferred_uni;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->deferred_uni = 0;
+  if (ctx->deferred_uni_rng) ctx->mt_host_valid = true;
+  for (int i = 0; i < 9; ++i) ctx->ms[i] = 0.0f;
+  cudaEventElapsedTime(&ctx->ms[8], ctx->ev[0], ctx->ev[8]);
+  const char* h = static_cast<const char*>(ctx->res_host);
+  if (out_x) memcpy(out_x, h, (size_t)n * 8);
+  if (out_acq) memcpy(out_acq, h + (size_t)n * 8, (size_t)n * 8);
+  if (out_best) memcpy(out_best, h + (size_t)n * 16, (size_t)n * 8);
   return TPE_OK;
 }
 

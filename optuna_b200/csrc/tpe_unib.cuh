@@ -14,6 +14,15 @@ struct UbDims {
   int32_t pall;    // columns of the history matrix
 };
 
+// every column as the only one of its context (setup_columns with one column: slot and RNG rank 0)
+__global__ void kb_cols(const ColMeta* __restrict__ in, int n, ColMeta* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  ColMeta cm = in[j];
+  cm.slot = 0;
+  cm.num_rank = 0;
+  out[j] = cm;
+}
 __global__ void kb_mu(const double* __restrict__ X, UbDims d, const int64_t* __restrict__ rows, int64_t n,
                       const ColMeta* __restrict__ cols, double* __restrict__ mu) {
   d_mu(X, d.pall, rows, n, cols + blockIdx.y, 1, mu + blockIdx.y * d.ks);

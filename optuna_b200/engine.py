@@ -309,6 +309,28 @@ class TPEEngine:
                                                            _ptr(wa), _ptr(u), _ptr(x), _ptr(acq), _ptr(best)))
         return x, acq, best
 
+    def suggest_univariate_batch_async(self, cols: Sequence[int], uniforms, w_below=None, w_above=None, **cfg) -> None:
+        """Queue ``suggest_univariate_batch`` and return; ``collect_univariate()`` waits and returns the results."""
+        c = self._make_cfg(**cfg)
+        cols_a = np.ascontiguousarray([int(v) for v in cols], dtype=np.int32)
+        u = None
+        if uniforms is not None:
+            u = _f64(uniforms).reshape(-1)
+            assert u.size == len(cols_a) * 2 * c.n_candidates
+        wb = None if w_below is None else _f64(w_below)
+        wa = None if w_above is None else _f64(w_above)
+        self._check(self._lib.tpe_suggest_univariate_batch_async(self._h, C.byref(c), _ptr(cols_a), len(cols_a), _ptr(wb),
+                                                                 _ptr(wa), _ptr(u)))
+        self._uni_pending = len(cols_a)
+
+    def collect_univariate(self):
+        n = self._uni_pending
+        x = np.empty(n, dtype=np.float64)
+        acq = np.empty(n, dtype=np.float64)
+        best = np.empty(n, dtype=np.int64)
+        self._check(self._lib.tpe_collect_univariate(self._h, _ptr(x), _ptr(acq), _ptr(best)))
+        return x, acq, best
+
     def split_info(self) -> tuple[int, int, int]:
         info = _lib.SplitInfo()
         self._check(self._lib.tpe_get_split_info(self._h, C.byref(info)))

@@ -300,15 +300,18 @@ class _Told:
     def matches(self, t) -> bool:
         """Is the stored trial exactly what was uploaded for it?"""
         return (t.state == self.state and t.values == self.values and t.params == self.params
-                and t.distributions == self.distributions and t.intermediate_values == self.intermediate_values)
+                and t.distributions == self.distributions and t.intermediate_values == self.intermediate_values
+                and t.system_attrs.get(CONSTRAINTS_KEY) == self.system_attrs.get(CONSTRAINTS_KEY))
 
 
 class _Ahead:
     """A suggestion whose device work was queued at ``tell`` time (``B200TPESampler._look_ahead``)."""
 
-    def __init__(self, told, space, cols, cfg, dev_version, eng, dev_rng, cancel) -> None:
+    def __init__(self, told, space, cols, cfg, dev_version, eng, dev_rng, cancel, kind="joint", **extra) -> None:
         self.told, self.space, self.cols, self.cfg = told, space, cols, cfg
         self.dev_version, self.eng, self.dev_rng, self.cancel = dev_version, eng, dev_rng, cancel
+        self.kind = kind                 # "joint": one sample_relative; "uni": the per-parameter calls of a trial
+        self.__dict__.update(extra)      # uni: order, wb, wa, snap
 
 
 class _UniPlan:
@@ -533,10 +536,14 @@ class B200TPESampler(BaseSampler):
         if self._constraints_func is not None:
             _process_constraints_after_trial(self._constraints_func, study, trial, state)
         self._random_sampler.after_trial(study, trial, state, values)
-        if self.LOOK_AHEAD and self._last_space is not None and self._engine is not None:
+        if self.LOOK_AHEAD and self._engine is not None:
             t0 = time.perf_counter()
             with self._lock:
-                self._look_ahead(study, trial, state, values)
+                if self._multivariate:
+                    if self._last_space is not None:
+                        self._look_ahead(study, trial, state, values)
+                else:
+                    self._look_ahead_uni(study, trial, state, values)
             self.last_tell_s = time.perf_counter() - t0   # row upload + queueing the next suggestion
 
     # -- host glue -------------------------------------------------------------------------------------
@@ -796,7 +803,10 @@ class B200TPESampler(BaseSampler):
 
     def _sample_one(self, study, trial, name: str, dist: BaseDistribution) -> Any:
         """One `sample_independent` past the startup trials.  The caller holds the lock and has polled."""
-        self._drop_ahead()
+        a = self._ahead
+        if a is not None and a.kind != "uni":
+            self._drop_ahead()
+            a = None
         u = self._uni
         h = self._hist
         if u.calls_trial != trial.number:            # a new trial: the finished recording becomes the prediction
@@ -805,6 +815,10 @@ class B200TPESampler(BaseSampler):
             u.calls_trial, u.calls = trial.number, []
         u.calls.append((name, dist))
         version = (id(h.storage), h.token, h.n_finished, len(h.pending) if self._constant_liar else 0)
+        if a is not None:                            # the batch of this trial was queued when the last one was told
+            if len(u.calls) == 1 and self._adopt_uni_ahead(study, trial, a, name, dist, version):
+                return u.values[0]
+            self._drop_ahead()
         if u.trial == trial.number and u.next < len(u.order):
             if u.order[u.next] == (name, dist) and u.version == version and not self._finished_backlog():
                 value = u.values[u.next]
@@ -870,6 +884,14 @@ class B200TPESampler(BaseSampler):
         except Exception:
             rng.set_state(st0)                         # nothing was served: the generator has not moved
             raise
+        self._install_plan(trial, version, order, cols, cfg, wb, wa, x, st0)
+
+    def _install_plan(self, trial, version, order, cols, cfg, wb, wa, x, st0) -> None:
+        """The batch has been evaluated (x: the winners per column, st0: the generator before its draws)."""
+        u = self._uni
+        eng = self._eng()
+        per = 2 * self._n_ei_candidates
+        count = per * len(order)
         u.trial, u.order, u.version = trial.number, order, version
         u.values = [d.to_external_repr(float(v)) for (_, d), v in zip(order, x)]
         u.next = 0
@@ -892,6 +914,104 @@ class B200TPESampler(BaseSampler):
             self._rng._engine = None
             u.trial = None
         self._rng._settle = settle
+
+    def _look_ahead_uni(self, study, trial, state, values) -> None:
+        """`_look_ahead` for univariate TPE: the per-parameter calls of the NEXT trial, predicted to repeat this
+        trial's, are queued as one batch now (tpe_suggest_univariate_batch_async); the first `sample_independent` of
+        the next trial adopts it if the trial was stored as uploaded, the call is the predicted one and nobody touched
+        the generator (`_adopt_uni_ahead`)."""
+        self._drop_ahead()
+        u = self._uni
+        if not (not self._constant_liar and not u.disabled and self._prior_weight >= 0
+                and (state == TrialState.COMPLETE or state == TrialState.PRUNED) and not study._is_multi_objective()
+                and u.calls_trial == trial.number and len(u.calls) >= self.UNI_BATCH_MIN
+                and len({n for n, _ in u.calls}) == len(u.calls)):
+            return
+        h = self._hist
+        order = list(u.calls)
+        space = dict(order)
+        self._note_changes(self._poll(study))
+        if h.n_finished + 1 < self._n_startup_trials:
+            return
+        rng = self._rng
+        if rng._settle is not None:
+            rng.rng                                  # a half-served plan: settle the generator first
+        row = trial.number
+        cols = self._sync(study, None, space)
+        if row >= h.rows or row not in h.pending or h.numbers[row] != trial.number:
+            return
+        eng = self._eng()
+        told = _Told(trial, state, values)
+        if self._constraints_func is not None:
+            told.system_attrs[CONSTRAINTS_KEY] = study._storage.get_trial_system_attrs(trial._trial_id).get(CONSTRAINTS_KEY)
+        self._upload(study, eng, {row: told}, None)
+        h.dev_pred[row] = told
+        cfg = dict(n_below=int(self._gamma(h.n_finished + 1)), n_candidates=self._n_ei_candidates, multivariate=False,
+                   prior_weight=self._prior_weight, magic_clip=self._magic_clip, endpoints=self._endpoints)
+        per = 2 * self._n_ei_candidates
+        count = per * len(order)
+        inner = rng._inner
+        snap = None
+        wb = wa = None
+        try:
+            if self._weights is not default_weights:
+                _, nb, na = eng.prepare(cols[:1], **cfg)
+                wb, wa = _checked_weights(self._weights, nb), _checked_weights(self._weights, na)
+            if count >= self.DEVICE_RNG_MIN:
+                if rng.on_device(eng):
+                    snap = eng.rng_snapshot()
+                    eng.stage_rng(None, count)
+                else:
+                    r = rng.rng
+                    snap = r.get_state()
+                    eng.stage_rng(r, count, state=snap)
+                eng.suggest_univariate_batch_async(cols, None, wb, wa, **cfg)
+                on_device = eng
+            else:
+                r = rng.rng
+                snap = r.get_state()
+                eng.suggest_univariate_batch_async(cols, r.random_sample(count), wb, wa, **cfg)
+                on_device = None
+        except Exception:                            # e.g. "not batchable asynchronously": the ask plans as before
+            if snap is not None:
+                inner.rng.set_state(snap)
+                rng._engine = None
+            return
+
+        def cancel() -> None:
+            inner.rng.set_state(snap)
+            rng._engine = None
+        rng._settle = cancel
+        self._ahead = _Ahead(told, space, cols, cfg, h.dev_version, eng, on_device is not None, cancel, kind="uni",
+                             order=order, wb=wb, wa=wa, snap=snap, on_device=on_device)
+
+    def _adopt_uni_ahead(self, study, trial, a, name, dist, version) -> bool:
+        """First `sample_independent` of a trial with a batch queued at `tell` time: take it if it is this trial's."""
+        self._ahead = None
+        h = self._hist
+        cols = self._sync(study, trial, dict(a.order))
+        cfg = dict(n_below=int(self._gamma(h.n_finished)), n_candidates=self._n_ei_candidates, multivariate=False,
+                   prior_weight=self._prior_weight, magic_clip=self._magic_clip, endpoints=self._endpoints)
+        ok = (a.told.confirmed and a.eng is self._engine and a.dev_version == h.dev_version and a.cols == cols
+              and a.cfg == cfg and a.order[0] == (name, dist) and self._rng._settle is a.cancel)
+        if not ok:
+            self.ahead_stats[1] += 1
+            if self._rng._settle is a.cancel:
+                self._rng._settle = None
+                a.cancel()
+            return False
+        self._rng._settle = None
+        x, _, _ = a.eng.collect_univariate()
+        u = self._uni
+        u.on_device = a.on_device                     # (host draws: the generator already stands after the batch)
+        self._install_plan(trial, version, a.order, cols, cfg, a.wb, a.wa, x, a.snap)
+        u.next = 1
+        if len(u.order) == 1:
+            self._rng._settle = None
+            if u.on_device is not None:
+                self._rng.mark_device(u.on_device)
+        self.ahead_stats[0] += 1
+        return True
 
     def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
         """TPESampler._sample (sampler.py:523-560).  The caller holds the lock and has polled."""
@@ -957,7 +1077,7 @@ class B200TPESampler(BaseSampler):
         a, self._ahead = self._ahead, None
         if a is None:
             return None
-        ok = (a.told.confirmed and a.eng is eng and a.dev_version == self._hist.dev_version and a.cols == cols
+        ok = (a.kind == "joint" and a.told.confirmed and a.eng is eng and a.dev_version == self._hist.dev_version and a.cols == cols
               and a.cfg == cfg and self._rng._settle is a.cancel
               and list(a.space.items()) == list(search_space.items()))
         if not ok:
@@ -979,11 +1099,10 @@ class B200TPESampler(BaseSampler):
         determined at this point -- the history plus this trial, the same search space, the generator where the
         last ask left it -- so the row is uploaded and the whole suggestion queued on the device now; it runs while
         optuna stores the trial and creates the next one, and `sample_relative` collects it after checking that the
-        ask really is the predicted one (`_take_ahead`).  Joint sampling with the default weights only; anything
-        out of the ordinary (constraints, constant liar, groups, a failed trial, a changed space) just skips it."""
+        ask really is the predicted one (`_take_ahead`).  Joint sampling only; anything out of the ordinary (constant
+        liar, groups, a failed trial, a changed space) just skips it."""
         self._drop_ahead()
-        if not (self._multivariate and not self._group and not self._constant_liar and self._constraints_func is None
-                and self._weights is default_weights and self._prior_weight >= 0
+        if not (self._multivariate and not self._group and not self._constant_liar and self._prior_weight >= 0
                 and (state == TrialState.COMPLETE or state == TrialState.PRUNED)):
             return
         h = self._hist
@@ -1000,6 +1119,8 @@ class B200TPESampler(BaseSampler):
             return
         eng = self._eng()
         told = _Told(trial, state, values)
+        if self._constraints_func is not None:       # after_trial has just stored them (samplers/_base.py:241-267)
+            told.system_attrs[CONSTRAINTS_KEY] = study._storage.get_trial_system_attrs(trial._trial_id).get(CONSTRAINTS_KEY)
         self._upload(study, eng, {row: told}, None)
         h.dev_pred[row] = told                       # (_upload kept its category in dev_cat: the row is pending)
         cfg = self._cfg(h.n_finished + 1)
@@ -1010,9 +1131,18 @@ class B200TPESampler(BaseSampler):
         inner = rng._inner
         snap = None
         try:
-            eng.prepare(cols, **cfg)
-            eng.build()
             dev_rng = n >= self.DEVICE_RNG_MIN
+            staged = None
+            if not dev_rng:                          # host draws: uploaded on the side stream before anything is queued
+                r = rng.rng                          # (a copy from pageable memory waits for the work queued before it)
+                snap = r.get_state()
+                staged = eng.stage_uniforms(r.random_sample(n))
+            _, nb, na = eng.prepare(cols, **cfg)
+            if self._weights is default_weights:
+                eng.build()
+            else:                                    # as _sample_synced (sampler.py:570-584)
+                eng.build(None if study._is_multi_objective() else _checked_weights(self._weights, nb),
+                          _checked_weights(self._weights, na))
             if dev_rng and rng.on_device(eng):
                 snap = eng.rng_snapshot()            # where the last ask left the generator (no device access)
                 eng.stage_rng(None, n)
@@ -1023,9 +1153,7 @@ class B200TPESampler(BaseSampler):
                 eng.stage_rng(r, n, state=snap)
                 eng.sample_and_select_async(None, 1)
             else:
-                r = rng.rng
-                snap = r.get_state()
-                eng.sample_and_select_async(r.random_sample(n), 1)
+                eng.sample_and_select_async(staged, 1)
         except Exception:                            # the ask will run into it again, and report it
             if snap is not None:
                 inner.rng.set_state(snap)

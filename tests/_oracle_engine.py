@@ -167,6 +167,9 @@ class OracleEngine:
             x[a] = cand[best[a]]
         return x, acq, best
 
+    def stage_uniforms(self, uniforms):
+        return np.asarray(uniforms, dtype=np.float64).ravel()
+
     def sample_and_select_async(self, uniforms, n_asks: int = 1) -> None:
         self._deferred = self.sample_and_select(uniforms, n_asks)
 
@@ -205,6 +208,14 @@ class OracleEngine:
             xj, aj, bj = self.sample_and_select(u[j * per: (j + 1) * per], 1)
             x[j], acq[j], best[j] = xj[0, 0], aj[0], bj[0]
         return x, acq, best
+
+    def suggest_univariate_batch_async(self, cols, uniforms, w_below=None, w_above=None, **cfg) -> None:
+        self._uni_deferred = self.suggest_univariate_batch(cols, uniforms, w_below, w_above, **cfg)
+
+    def collect_univariate(self):
+        out, self._uni_deferred = self._uni_deferred, None
+        assert out is not None, "collect_univariate without suggest_univariate_batch_async"
+        return out
 
     def close(self) -> None:
         pass

@@ -147,6 +147,8 @@ def test_branin_200_trials_is_the_reference_trajectory(make_sampler, mv):
     xy = np.asarray([[t.params["x"], t.params["y"]] for t in study.trials])
     assert np.array_equal(xy[:10], ref[:10])  # startup trials: RandomSampler's stream, bit-identical
     np.testing.assert_allclose(xy, ref, rtol=1e-9, atol=1e-9)
+    # ... computed ahead: the joint suggestion / the batch of per-parameter suggestions is queued when a trial is told
+    assert study.sampler.ahead_stats[0] >= 180, study.sampler.ahead_stats
     if not mv:
         assert abs(study.best_value - 0.4069652013131506) < 1e-9
     live = optuna.create_study(sampler=TPESampler(seed=0, multivariate=mv))
@@ -175,6 +177,12 @@ def test_custom_gamma_weights_and_constraints(make_sampler):
               constraints_func=lambda tr: (tr.user_attrs["c"], -1.0), n_startup_trials=5)
     a, b = run_both(make_sampler, obj, 40, ties=True, **kw)
     for ta, tb in zip(a.trials, b.trials):  # constraints are stored once, by after_trial (samplers/_base.py:242-268)
+        np.testing.assert_allclose(ta.system_attrs["constraints"], tb.system_attrs["constraints"], rtol=1e-9)
+    # joint sampling: the suggestions are queued at `tell` time also with constraints and custom weights (the
+    # constraints of the trial being told are read back from the storage, the weights evaluated then)
+    a, b = run_both(make_sampler, obj, 40, ties=True, multivariate=True, **dict(kw, seed=3))
+    assert a.sampler.ahead_stats[0] >= 25, a.sampler.ahead_stats
+    for ta, tb in zip(a.trials, b.trials):
         np.testing.assert_allclose(ta.system_attrs["constraints"], tb.system_attrs["constraints"], rtol=1e-9)
     with pytest.raises(ValueError):
         bad = optuna.create_study(sampler=make_sampler(seed=1, weights=lambda n: -np.ones(n), n_startup_trials=2))
@@ -483,6 +491,71 @@ def test_look_ahead_suggestions_are_the_reference_suggestions(make_sampler):
     for C in (24, 2048):   # uniforms drawn on the host / on the device (>= DEVICE_RNG_MIN with 4 parameters)
         over_seeds(scenario, make_sampler, True, dict(seed=31, multivariate=True, n_startup_trials=6, n_ei_candidates=C))
     assert served and all(ok >= 8 and dropped >= 4 for ok, dropped in served), served
+    # univariate TPE: the batch of per-parameter suggestions of the next trial is queued at `tell` time (the CUDA
+    # engine does so for all-continuous trials only; this scenario then simply plans at the first ask)
+    del served[:]
+    for C in (24, 1024):
+        over_seeds(scenario, make_sampler, True, dict(seed=47, multivariate=False, n_startup_trials=6, n_ei_candidates=C))
+    if make_sampler.kind == "oracle":
+        assert served and all(ok >= 6 for ok, _ in served), served
+
+
+def test_univariate_look_ahead_with_continuous_parameters(make_sampler):
+    """All-continuous univariate trials (what the CUDA engine evaluates stage by stage and can queue at `tell` time):
+    sequential loop, a foreign draw, two tells in a row, a trial told but never stored, a pruned trial, a trial that
+    asks its parameters in another order, one that asks fewer -- against the reference sampler, with host-drawn and
+    device-generated uniforms."""
+    from optuna.trial import TrialState as TS
+
+    def ask3(t, order=("x", "y", "z")):
+        d = {"x": lambda: t.suggest_float("x", -2.0, 2.0), "y": lambda: t.suggest_float("y", 1e-2, 10.0, log=True),
+             "z": lambda: t.suggest_float("z", 0.0, 1.0)}
+        v = {k: d[k]() for k in order}
+        return v.get("x", 0.0) ** 2 + math.log(v.get("y", 1.0)) ** 2 + (v.get("z", 0.3) - 0.3) ** 2
+
+    stats = []
+
+    def scenario(sampler):
+        s = optuna.create_study(sampler=sampler)
+        for _ in range(12):
+            t = s.ask()
+            s.tell(t, ask3(t))
+        sampler._rng.rng.random_sample(3)
+        t = s.ask()
+        s.tell(t, ask3(t))
+        t1, t2 = s.ask(), s.ask()
+        v1, v2 = ask3(t1), ask3(t2)
+        s.tell(t2, v2)
+        s.tell(t1, v1)
+        t = s.ask()
+        ask3(t)
+        sampler.after_trial(s, s._storage.get_trial(t._trial_id), TS.COMPLETE, [0.001])   # never stored
+        u = s.ask()
+        s.tell(u, ask3(u))
+        s.tell(t, state=TS.FAIL)
+        t = s.ask()
+        ask3(t)
+        t.report(0.5, 0)
+        s.tell(t, state=TS.PRUNED)
+        for _ in range(3):
+            t = s.ask()
+            s.tell(t, ask3(t))
+        t = s.ask()
+        s.tell(t, ask3(t, ("z", "x", "y")))                 # another order: the prediction fails at the first call
+        t = s.ask()
+        s.tell(t, ask3(t, ("z", "x", "y")))
+        t = s.ask()
+        s.tell(t, ask3(t, ("z", "x")))                      # fewer calls than predicted: the generator is settled
+        for _ in range(4):
+            t = s.ask()
+            s.tell(t, ask3(t))
+        if hasattr(sampler, "ahead_stats"):
+            stats.append(tuple(sampler.ahead_stats))
+        return s
+
+    for C in (24, 1024):   # 3 x 2 x 1024 uniforms >= DEVICE_RNG_MIN: generated on the device
+        over_seeds(scenario, make_sampler, True, dict(seed=5, multivariate=False, n_startup_trials=6, n_ei_candidates=C))
+    assert stats and all(ok >= 10 and dropped >= 3 for ok, dropped in stats), stats
 
 
 def test_batched_ask_equals_sequential_asks(make_sampler):
