@@ -426,14 +426,16 @@ def run_b200(args) -> None:
     sampler.LOOK_AHEAD = True
     one_trial()
     barrier()
-    sync_s = dev_s = tell_s = 0.0
+    sync_s = dev_s = tell_s = spec_s = 0.0
     served0 = sampler.ahead_stats[0]
+    spec0 = list(sampler.spec_stats)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         out = one_trial()
         sync_s += sampler.last_ask_s[0]
         dev_s += sampler.last_ask_s[1]
         tell_s += sampler.last_tell_s
+        spec_s += sampler.last_spec_s
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     barrier()
@@ -448,10 +450,14 @@ def run_b200(args) -> None:
     assert len(study.get_trials(deepcopy=False)) == N_TRIALS + 3 + max(2, min(args.warmup, 3)) + 2 * e2e_steps
     e2e_host = {"per_trial_ms": e2e_wall / e2e_steps * 1e3,
                 "history_sync_ms": sync_s / e2e_steps * 1e3,       # in the ask: trial-log poll + row uploads (B200TPESampler._sync)
-                "wait_and_collect_ms": dev_s / e2e_steps * 1e3,    # in the ask: waiting for the suggestion queued at tell time, read-back
-                "tell_queue_ms": tell_s / e2e_steps * 1e3,         # in the tell: row upload + prepare / build / uniforms / sample+select queued
+                # in the ask: waiting for the queued suggestion + read-back, then queueing the NEXT one (speculate_queue_ms)
+                "wait_and_collect_ms": (dev_s - spec_s) / e2e_steps * 1e3,
+                "speculate_queue_ms": spec_s / e2e_steps * 1e3,    # row upload (worst key) + prepare / build / uniforms / sample+select queued
+                "tell_queue_ms": tell_s / e2e_steps * 1e3,         # in the tell: is the trial's outcome the assumed one? + its true row
                 "optuna_ms": (e2e_wall - sync_s - dev_s - tell_s) / e2e_steps * 1e3,  # Study.ask / 32 x suggest_float / tell
                 "look_ahead_served": served, "look_ahead_of": e2e_steps,
+                "speculations_confirmed": sampler.spec_stats[0] - spec0[0],
+                "speculations_abandoned": sampler.spec_stats[1] - spec0[1],
                 "per_trial_ms_without_look_ahead": plain_wall / e2e_steps * 1e3,
                 "first_ask_s": first_ask_s, "study_setup_s": study_setup_s}
 
@@ -679,17 +685,19 @@ def run_b200(args) -> None:
             "clocks": clk,
             # inputs of one ask: the generator state (624 words + position; the uniforms themselves are
             # produced on the device by the same MT19937), the column list and the config struct
-            # inputs of one step: the row that changed (the trial that finished: 32 params + 2 key doubles +
-            # 1 category byte), the column list and the config struct; the
+            # inputs of one step: the row that changed, twice (with the assumed and with the true key: 32 params +
+            # 2 key doubles + 1 category byte), the column list and the config struct; the
             # generator state travels only when somebody else drew from it
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (N_PARAMS * 8 + 16 + 1) + N_PARAMS * 4 + 32,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * (N_PARAMS * 8 + 16 + 1) + N_PARAMS * 4 + 32,
                     "d2h_bytes_per_step": N_PARAMS * 8 + 16 + 24 + 625 * 4, "steps": e2e_steps,
                     "path": "optuna.create_study(sampler=B200TPESampler) + study.add_trials(100k) ; per step study.ask() "
-                            "[infer_relative_search_space, sample_relative -> ctypes -> tpe_collect] -> 32 x "
-                            "trial.suggest_float -> study.tell [after_trial -> ctypes -> tpe_history_update (the "
-                            "finished trial's row) / tpe_prepare / tpe_build / tpe_stage_uniforms_mt19937 / "
-                            "tpe_sample_and_select_async: the next suggestion runs on the device while optuna stores "
-                            "the trial and creates the next one; every step is one full ask + tell, nothing skipped]",
+                            "[infer_relative_search_space, sample_relative -> ctypes -> tpe_collect, then "
+                            "tpe_history_update (this trial's row, worst key) / tpe_prepare / tpe_build / "
+                            "tpe_stage_uniforms_mt19937 / tpe_sample_and_select_async: the NEXT suggestion is queued "
+                            "assuming the trial will not enter the below set] -> 32 x trial.suggest_float -> "
+                            "study.tell [after_trial: assumption checked against the value, tpe_history_update (true "
+                            "key); if it failed the suggestion is recomputed now]; every step is one full ask + tell, "
+                            "nothing skipped",
                     "caller": f"optuna {optuna.__version__} ({os.path.relpath(os.path.dirname(optuna.__file__), ROOT)})",
                     "host": e2e_host},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

@@ -214,6 +214,12 @@ struct tpe_ctx {
   DevBuf mixcols;
   int mix_ncont = 0, mix_nd = 0, mix_tabd = 0;
   bool user_points = false;      // the resident candidates came through tpe_logpdf, not from k_sample
+  static constexpr size_t kUpSlot = 8192;     // page-locked staging of small history uploads (upload_history)
+  static constexpr int kUpSlots = 16;
+  void* up_host = nullptr;
+  cudaEvent_t up_ev[kUpSlots] = {};
+  bool up_used[kUpSlots] = {};
+  int up_next = 0;
   bool deferred = false;         // tpe_sample_and_select_async issued, tpe_collect not yet called
   int64_t deferred_uni = 0;      // tpe_suggest_univariate_batch_async issued (columns), not yet collected
   bool deferred_uni_rng = false;
@@ -522,6 +528,34 @@ int set_device(tpe_ctx* ctx, bool join = true) {
   return TPE_OK;
 }
 
+// A few rows from the host (the per-trial case) go through a slot of page-locked staging memory, without waiting: a
+// copy from pageable memory would first wait for everything queued on the stream, i.e. for a suggestion that was
+// queued ahead of time (tpe_sample_and_select_async) and must keep running while the caller goes on.
+bool rows_fit_staging(const tpe_ctx* ctx, int64_t n) {
+  return (size_t)n * ((size_t)ctx->space.size() * 8 + 16 + 1) + 64 <= tpe_ctx::kUpSlot;
+}
+int stage_rows(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key, int64_t n, int64_t at) {
+  const int64_t P = (int64_t)ctx->space.size();
+  if (!ctx->up_host) {
+    CU(cudaHostAlloc(&ctx->up_host, tpe_ctx::kUpSlot * tpe_ctx::kUpSlots, cudaHostAllocDefault));
+    for (auto& e : ctx->up_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const int slot = ctx->up_next;
+  ctx->up_next = (slot + 1) % tpe_ctx::kUpSlots;
+  if (ctx->up_used[slot]) CU(cudaEventSynchronize(ctx->up_ev[slot]));   // (its copies of kUpSlots uploads ago)
+  char* h = static_cast<char*>(ctx->up_host) + (size_t)slot * tpe_ctx::kUpSlot;
+  const size_t xb = (size_t)n * P * 8, kb = (size_t)n * 16;
+  memcpy(h, X, xb);
+  memcpy(h + xb, key, kb);
+  memcpy(h + xb + kb, category, (size_t)n);
+  CU(cudaMemcpyAsync(ctx->X.as<double>() + at * P, h, xb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->key.as<double>() + at * 2, h + xb, kb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->cat.as<int8_t>() + at, h + xb + kb, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaEventRecord(ctx->up_ev[slot], ctx->stream));
+  ctx->up_used[slot] = true;
+  return TPE_OK;
+}
+
 int upload_history(tpe_ctx* ctx, const double* X, const int8_t* category, const double* key, int64_t n,
                    int64_t at, bool device_src) {
   const int64_t P = (int64_t)ctx->space.size();
@@ -530,7 +564,9 @@ int upload_history(tpe_ctx* ctx, const double* X, const int8_t* category, const 
   CU(ctx->cat.grow((size_t)std::max<int64_t>(total, 1), (size_t)at, ctx->stream));
   CU(ctx->key.grow((size_t)std::max<int64_t>(total, 1) * 16, (size_t)at * 16, ctx->stream));
   const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (n > 0) {
+  if (n > 0 && !device_src && rows_fit_staging(ctx, n)) {
+    if (int rc = stage_rows(ctx, X, category, key, n, at)) return rc;
+  } else if (n > 0) {
     CU(cudaMemcpyAsync(ctx->X.as<double>() + at * P, X, (size_t)n * P * 8, kind, ctx->stream));
     CU(cudaMemcpyAsync(ctx->cat.as<int8_t>() + at, category, (size_t)n, kind, ctx->stream));
     CU(cudaMemcpyAsync(ctx->key.as<double>() + at * 2, key, (size_t)n * 16, kind, ctx->stream));
@@ -1729,6 +1765,9 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
   ctx->est[1].release();
   if (ctx->res_host) cudaFreeHost(ctx->res_host);
   if (ctx->mt_host) cudaFreeHost(ctx->mt_host);
+  if (ctx->up_host) cudaFreeHost(ctx->up_host);
+  for (auto& e : ctx->up_ev)
+    if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -1840,10 +1879,14 @@ int tpe_history_update(tpe_ctx* ctx, const double* X, const int8_t* category, co
     if (ctx->M >= 2)
       CU(ctx->vals.grow((size_t)total * ctx->M * 8, (size_t)ctx->N * ctx->M * 8, ctx->stream));
   }
-  CU(cudaMemcpyAsync(ctx->X.as<double>() + at_row * P, X, (size_t)n * P * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->cat.as<int8_t>() + at_row, category, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->key.as<double>() + at_row * 2, key, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  if (rows_fit_staging(ctx, n)) {
+    if (int rc = stage_rows(ctx, X, category, key, n, at_row)) return rc;
+  } else {
+    CU(cudaMemcpyAsync(ctx->X.as<double>() + at_row * P, X, (size_t)n * P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->cat.as<int8_t>() + at_row, category, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->key.as<double>() + at_row * 2, key, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
   ctx->cat_h.resize((size_t)total, (int8_t)TPE_CAT_EXCLUDED);
   for (int64_t i = 0; i < n; ++i) {
     const int64_t r = at_row + i;

@@ -11,6 +11,7 @@ argmax run on the GPU through the C ABI (include/optuna_b200_tpe.h).  There is n
 """
 from __future__ import annotations
 
+import bisect
 import json
 import math
 import threading
@@ -125,6 +126,9 @@ class _History:
         the study's per-trial cache once the storage has answered) and the same scan of unfinished + new rows.
     """
 
+    #: how many of the best sort keys are kept on the host (outcome speculation needs the n_below-th best)
+    BEST_KEYS = 64
+
     def __init__(self) -> None:
         # ---- log (host only) ----
         self.storage = None            # strong reference: a recycled id() can never alias another storage
@@ -133,6 +137,8 @@ class _History:
         self.numbers: list[int] = []
         self.pending: dict[int, list] = {}     # row -> [trial_id, FrozenTrial object at the last look]
         self.n_finished = 0                    # COMPLETE + PRUNED trials (sampler.py:449-456, :538)
+        self.n_complete = 0                    # COMPLETE trials of a single-objective study ...
+        self.best_keys: list[float] = []       # ... and the BEST_KEYS smallest of their sort keys, ascending
         self.all_dists: dict[str, BaseDistribution] = {}   # latest distribution of every parameter seen
         self.seen_params: set[str] = set()
         self.inter: dict[str, BaseDistribution] | None = None
@@ -155,6 +161,12 @@ class _History:
         if t.state != TrialState.COMPLETE and t.state != TrialState.PRUNED:
             return  # FAIL: in no estimator, in no search space
         self.n_finished += 1
+        if t.state == TrialState.COMPLETE and len(self.token[1]) == 1 and t.values is not None:
+            key = -t.values[0] if self.token[1][0] == StudyDirection.MAXIMIZE else t.values[0]
+            self.n_complete += 1
+            if len(self.best_keys) < self.BEST_KEYS or key < self.best_keys[-1]:
+                bisect.insort(self.best_keys, key)
+                del self.best_keys[self.BEST_KEYS:]
         d = t.distributions
         self.all_dists.update(d)
         self.seen_params.update(t.params)
@@ -393,6 +405,8 @@ class B200TPESampler(BaseSampler):
         self._ahead: _Ahead | None = None
         self._last_space: dict[str, BaseDistribution] | None = None
         self.ahead_stats = [0, 0]   # look-ahead suggestions [served, discarded]
+        self.spec_stats = [0, 0]    # outcome speculations [confirmed at tell time, abandoned]
+        self.last_spec_s = 0.0
         self.last_tell_s = 0.0
         if multivariate:
             warn_experimental_argument("multivariate")
@@ -508,7 +522,7 @@ class B200TPESampler(BaseSampler):
             self._note_changes(self._poll(study))
             if self._hist.n_finished < self._n_startup_trials:
                 return {}
-            return self._sample(study, trial, search_space)
+            return self._sample(study, trial, search_space, speculate=not self._group)
 
     def sample_independent(self, study, trial, param_name: str, param_distribution: BaseDistribution) -> Any:
         with self._lock:
@@ -1013,7 +1027,7 @@ class B200TPESampler(BaseSampler):
         self.ahead_stats[0] += 1
         return True
 
-    def _sample(self, study, trial, search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
+    def _sample(self, study, trial, search_space: dict[str, BaseDistribution], speculate: bool = False) -> dict[str, Any]:
         """TPESampler._sample (sampler.py:523-560).  The caller holds the lock and has polled."""
         t0 = time.perf_counter()
         cols = self._sync(study, trial, search_space)
@@ -1022,6 +1036,10 @@ class B200TPESampler(BaseSampler):
             out = self._sample_synced(study, cols, search_space)
             if self._audit is not None:
                 self._audit(trial, search_space, self._eng())
+            if speculate and self.LOOK_AHEAD and self.SPECULATE:
+                t2 = time.perf_counter()
+                self._speculate(study, trial, cols, search_space, out)
+                self.last_spec_s = time.perf_counter() - t2
             return out
         finally:
             # wall time of the last ask: history sync (host walk + row uploads) / everything after it
@@ -1101,6 +1119,334 @@ class B200TPESampler(BaseSampler):
         optuna stores the trial and creates the next one, and `sample_relative` collects it after checking that the
         ask really is the predicted one (`_take_ahead`).  Joint sampling only; anything out of the ordinary (constant
         liar, groups, a failed trial, a changed space) just skips it."""
+        if self._confirm_speculation(study, trial, state, values):
+            return
+        self._drop_ahead()
+        if not (self._multivariate and not self._group and not self._constant_liar and self._prior_weight >= 0
+                and (state == TrialState.COMPLETE or state == TrialState.PRUNED)):
+            return
+        h = self._hist
+        space = self._last_space
+        d = trial.distributions
+        if any(d.get(k) != v for k, v in space.items()):
+            return                                   # the intersection search space shrinks with this trial
+        self._note_changes(self._poll(study))
+        if h.n_finished + 1 < self._n_startup_trials:
+            return
+        row = trial.number
+        cols = self._sync(study, None, space)
+        if row >= h.rows or row not in h.pending or h.numbers[row] != trial.number:
+            return
+        eng = self._eng()
+        told = _Told(trial, state, values)
+        if self._constraints_func is not None:       # after_trial has just stored them (samplers/_base.py:241-267)
+            told.system_attrs[CONSTRAINTS_KEY] = study._storage.get_trial_system_attrs(trial._trial_id).get(CONSTRAINTS_KEY)
+        self._upload(study, eng, {row: told}, None)
+        h.dev_pred[row] = told                       # (_upload kept its category in dev_cat: the row is pending)
+        self._queue_ahead(study, cols, space, told, "joint")
+
+    def _confirm_speculation(self, study, trial, state, values) -> bool:
+        """`tell` time: did the trial end the way `_speculate` assumed?  Then the queued suggestion is the next one's;
+        the row gets its true key (queued behind the suggestion's kernels: it changes nothing they read)."""
+        a = self._ahead
+        if a is None or a.kind != "spec":
+            return False
+        h = self._hist
+        g = a.told
+        ok = (g.number == trial.number and state == TrialState.COMPLETE and values is not None and len(values) == 1
+              and self._rng._settle is a.cancel and a.dev_version == h.dev_version and a.eng is self._engine
+              and trial.params == g.params and trial.distributions == g.distributions)
+        if ok:
+            v = float(values[0])
+            key = -v if h.token[1][0] == StudyDirection.MAXIMIZE else v
+            ok = key >= g.threshold
+        if ok:
+            self._note_changes(self._poll(study))
+            ok = (trial.number in h.pending and not any(r not in h.pending for r in h.backlog)
+                  and h.n_finished + 1 == a.cfg_n_finished)
+        if not ok:
+            self.spec_stats[1] += 1
+            return False                             # (the caller drops it: the generator goes back)
+        told = _Told(trial, state, values)
+        self._upload(study, a.eng, {trial.number: told}, None)
+        h.dev_pred[trial.number] = told
+        a.told, a.kind, a.dev_version = told, "joint", h.dev_version
+        self.spec_stats[0] += 1
+        return True
+
+    def _queue_ahead(self, study, cols, space, told, kind) -> bool:
+        """Queue the joint suggestion of the ask after `told` (whose row is on the device) without waiting for it."""
+        h = self._hist
+        eng = self._eng()
+        cfg = self._cfg(h.n_finished + 1)
+        n = self._n_ei_candidates * (1 + len(space))
+        rng = self._rng
+        if rng._settle is not None:
+            rng.rng                                  # a half-served batch of per-parameter draws: settle it first
+        inner = rng._inner
+        snap = None
+        try:
+            dev_rng = n >= self.DEVICE_RNG_MIN
+            staged = None
+            if not dev_rng:                          # host draws: uploaded on the side stream before anything is queued
+                r = rng.rng                          # (a copy from pageable memory waits for the work queued before it)
+                snap = r.get_state()
+                staged = eng.stage_uniforms(r.random_sample(n))
+            _, nb, na = eng.prepare(cols, **cfg)
+            if self._weights is default_weights:
+                eng.build()
+            else:                                    # as _sample_synced (sampler.py:570-584)
+                eng.build(None if study._is_multi_objective() else _checked_weights(self._weights, nb),
+                          _checked_weights(self._weights, na))
+            if dev_rng and rng.on_device(eng):
+                snap = eng.rng_snapshot()            # where the last ask left the generator (no device access)
+                eng.stage_rng(None, n)
+                eng.sample_and_select_async(None, 1)
+            elif dev_rng:
+                r = rng.rng
+                snap = r.get_state()
+                eng.stage_rng(r, n, state=snap)
+                eng.sample_and_select_async(None, 1)
+            else:
+                eng.sample_and_select_async(staged, 1)
+        except Exception:                            # the ask will run into it again, and report it
+            if snap is not None:
+                inner.rng.set_state(snap)
+                rng._engine = None
+            return False
+
+        def cancel() -> None:                        # nobody took the suggestion: the draws never happened
+            inner.rng.set_state(snap)
+            rng._engine = None
+        rng._settle = cancel
+        self._ahead = _Ahead(told, space, cols, cfg, h.dev_version, eng, dev_rng, cancel, kind=kind,
+                             cfg_n_finished=h.n_finished + 1)
+        return True
+
+    #: queue the NEXT suggestion already when a suggestion has been handed out, assuming the trial will end up in the
+    #: above set (see _speculate)
+    SPECULATE = True
+
+    def _speculate(self, study, trial, cols, space, params) -> None:
+        """Outcome speculation.  The estimators of the next ask depend on the running trial only through the SET it
+        falls into: g(x) weights its kernels by position, not by value, and a trial whose value does not beat the
+        n_below-th best leaves l(x) untouched (sampler.py:686-722).  With 100k trials that is how all but ~25 in
+        100k trials end, so the next joint suggestion is queued right now -- the trial's row goes to the device as
+        COMPLETE with the worst possible key -- and runs while the objective is evaluated.  `_look_ahead` (at `tell`
+        time) keeps it only if the trial really ended that way: COMPLETE, exactly these parameters, a value that does
+        not enter the below set (`_History.best_keys`), nothing else changed, the generator untouched; otherwise the
+        generator goes back and the suggestion is computed with the true row.  Single-objective studies without
+        constraints, joint sampling."""
+        h = self._hist
+        if (self._constant_liar or self._constraints_func is not None or study._is_multi_objective()
+                or self._prior_weight < 0 or self._ahead is not None or trial is None):
+            return
+        n_below = int(self._gamma(h.n_finished + 1))
+        row = trial.number
+        if not (0 < n_below <= min(len(h.best_keys), h.n_complete) and row in h.pending and row < h.rows
+                and h.numbers[row] == trial.number and h.n_finished + 1 >= self._n_startup_trials and not h.backlog):
+            return
+        worst = float("-inf") if h.token[1][0] == StudyDirection.MAXIMIZE else float("inf")
+        guess = _Told(trial, TrialState.COMPLETE, [worst])
+        guess.params = dict(params)
+        guess.distributions = dict(space)
+        guess.threshold = h.best_keys[n_below - 1]
+        self._upload(study, self._eng(), {row: guess}, None)
+        h.dev_pred[row] = guess
+        self._queue_ahead(study, cols, space, guess, "spec")
+
+    def _look_ahead_uni(self, study, trial, state, values) -> None:
+        """`_look_ahead` for univariate TPE: the per-parameter calls of the NEXT trial, predicted to repeat this
+        trial's, are queued as one batch now (tpe_suggest_univariate_batch_async); the first `sample_independent` of
+        the next trial adopts it if the trial was stored as uploaded, the call is the predicted one and nobody touched
+        the generator (`_adopt_uni_ahead`)."""
+        self._drop_ahead()
+        u = self._uni
+        if not (not self._constant_liar and not u.disabled and self._prior_weight >= 0
+                and (state == TrialState.COMPLETE or state == TrialState.PRUNED) and not study._is_multi_objective()
+                and u.calls_trial == trial.number and len(u.calls) >= self.UNI_BATCH_MIN
+                and len({n for n, _ in u.calls}) == len(u.calls)):
+            return
+        h = self._hist
+        order = list(u.calls)
+        space = dict(order)
+        self._note_changes(self._poll(study))
+        if h.n_finished + 1 < self._n_startup_trials:
+            return
+        rng = self._rng
+        if rng._settle is not None:
+            rng.rng                                  # a half-served plan: settle the generator first
+        row = trial.number
+        cols = self._sync(study, None, space)
+        if row >= h.rows or row not in h.pending or h.numbers[row] != trial.number:
+            return
+        eng = self._eng()
+        told = _Told(trial, state, values)
+        if self._constraints_func is not None:
+            told.system_attrs[CONSTRAINTS_KEY] = study._storage.get_trial_system_attrs(trial._trial_id).get(CONSTRAINTS_KEY)
+        self._upload(study, eng, {row: told}, None)
+        h.dev_pred[row] = told
+        cfg = dict(n_below=int(self._gamma(h.n_finished + 1)), n_candidates=self._n_ei_candidates, multivariate=False,
+                   prior_weight=self._prior_weight, magic_clip=self._magic_clip, endpoints=self._endpoints)
+        per = 2 * self._n_ei_candidates
+        count = per * len(order)
+        inner = rng._inner
+        snap = None
+        wb = wa = None
+        try:
+            if self._weights is not default_weights:
+                _, nb, na = eng.prepare(cols[:1], **cfg)
+                wb, wa = _checked_weights(self._weights, nb), _checked_weights(self._weights, na)
+            if count >= self.DEVICE_RNG_MIN:
+                if rng.on_device(eng):
+                    snap = eng.rng_snapshot()
+                    eng.stage_rng(None, count)
+                else:
+                    r = rng.rng
+                    snap = r.get_state()
+                    eng.stage_rng(r, count, state=snap)
+                eng.suggest_univariate_batch_async(cols, None, wb, wa, **cfg)
+                on_device = eng
+            else:
+                r = rng.rng
+                snap = r.get_state()
+                eng.suggest_univariate_batch_async(cols, r.random_sample(count), wb, wa, **cfg)
+                on_device = None
+        except Exception:                            # e.g. "not batchable asynchronously": the ask plans as before
+            if snap is not None:
+                inner.rng.set_state(snap)
+                rng._engine = None
+            return
+
+        def cancel() -> None:
+            inner.rng.set_state(snap)
+            rng._engine = None
+        rng._settle = cancel
+        self._ahead = _Ahead(told, space, cols, cfg, h.dev_version, eng, on_device is not None, cancel, kind="uni",
+                             order=order, wb=wb, wa=wa, snap=snap, on_device=on_device)
+
+    def _adopt_uni_ahead(self, study, trial, a, name, dist, version) -> bool:
+        """First `sample_independent` of a trial with a batch queued at `tell` time: take it if it is this trial's."""
+        self._ahead = None
+        h = self._hist
+        cols = self._sync(study, trial, dict(a.order))
+        cfg = dict(n_below=int(self._gamma(h.n_finished)), n_candidates=self._n_ei_candidates, multivariate=False,
+                   prior_weight=self._prior_weight, magic_clip=self._magic_clip, endpoints=self._endpoints)
+        ok = (a.told.confirmed and a.eng is self._engine and a.dev_version == h.dev_version and a.cols == cols
+              and a.cfg == cfg and a.order[0] == (name, dist) and self._rng._settle is a.cancel)
+        if not ok:
+            self.ahead_stats[1] += 1
+            if self._rng._settle is a.cancel:
+                self._rng._settle = None
+                a.cancel()
+            return False
+        self._rng._settle = None
+        x, _, _ = a.eng.collect_univariate()
+        u = self._uni
+        u.on_device = a.on_device                     # (host draws: the generator already stands after the batch)
+        self._install_plan(trial, version, a.order, cols, cfg, a.wb, a.wa, x, a.snap)
+        u.next = 1
+        if len(u.order) == 1:
+            self._rng._settle = None
+            if u.on_device is not None:
+                self._rng.mark_device(u.on_device)
+        self.ahead_stats[0] += 1
+        return True
+
+    def _sample(self, study, trial, search_space: dict[str, BaseDistribution], speculate: bool = False) -> dict[str, Any]:
+        """TPESampler._sample (sampler.py:523-560).  The caller holds the lock and has polled."""
+        t0 = time.perf_counter()
+        cols = self._sync(study, trial, search_space)
+        t1 = time.perf_counter()
+        try:
+            out = self._sample_synced(study, cols, search_space)
+            if self._audit is not None:
+                self._audit(trial, search_space, self._eng())
+            if speculate and self.LOOK_AHEAD and self.SPECULATE:
+                t2 = time.perf_counter()
+                self._speculate(study, trial, cols, search_space, out)
+                self.last_spec_s = time.perf_counter() - t2
+            return out
+        finally:
+            # wall time of the last ask: history sync (host walk + row uploads) / everything after it
+            # (prepare, build, uniforms, sampling + grids + argmax, read-back, to_external_repr)
+            self.last_ask_s = (t1 - t0, time.perf_counter() - t1)
+
+    def _cfg(self, n_finished: int) -> dict:
+        return dict(n_below=int(self._gamma(n_finished)), n_candidates=self._n_ei_candidates,
+                    multivariate=self._multivariate, prior_weight=self._prior_weight, magic_clip=self._magic_clip,
+                    endpoints=self._endpoints)
+
+    def _sample_synced(self, study, cols: list[int], search_space: dict[str, BaseDistribution]) -> dict[str, Any]:
+        cfg = self._cfg(self._hist.n_finished)
+        if self._prior_weight < 0:
+            raise ValueError("A non-negative value must be specified for prior_weight,"
+                             f" but got {self._prior_weight}.")
+        eng = self._eng()
+        x = self._take_ahead(eng, cols, search_space, cfg)
+        if x is not None:
+            pass
+        elif self._weights is default_weights:
+            eng.prepare(cols, **cfg)
+            x = self._sample_and_select(eng, search_space, 1, eng.build)
+        else:
+            _, nb, na = eng.prepare(cols, **cfg)
+            # multi-objective studies weight l(x) by hypervolume contributions (computed by the
+            # library); the user's weights function then only shapes g(x) (sampler.py:570-584)
+            wb = None if study._is_multi_objective() else _checked_weights(self._weights, nb)
+            wa = _checked_weights(self._weights, na)
+            x = self._sample_and_select(eng, search_space, 1, lambda: eng.build(wb, wa))
+        self._last_space = search_space
+        out = {}
+        for j, (name, d) in enumerate(search_space.items()):
+            out[name] = d.to_external_repr(float(x[0, j]))
+        return out
+
+    # -- look-ahead: the next suggestion is computed while the study finishes `tell` and starts `ask` ----------
+    #: queue the next joint suggestion at `tell` time (multivariate TPE; see _look_ahead)
+    LOOK_AHEAD = True
+
+    def _drop_ahead(self) -> None:
+        a, self._ahead = self._ahead, None
+        if a is not None:
+            self.ahead_stats[1] += 1
+            if self._rng._settle is a.cancel:
+                self._rng._settle = None
+                a.cancel()
+
+    def _take_ahead(self, eng, cols, search_space, cfg):
+        """The suggestion queued at `tell` time, if this ask is the one it was computed for: the very columns and
+        configuration, the finished trial stored exactly as it was uploaded, nothing else the estimators see
+        changed since, the generator untouched.  Otherwise the generator goes back to where it was."""
+        a, self._ahead = self._ahead, None
+        if a is None:
+            return None
+        ok = (a.kind == "joint" and a.told.confirmed and a.eng is eng and a.dev_version == self._hist.dev_version and a.cols == cols
+              and a.cfg == cfg and self._rng._settle is a.cancel
+              and list(a.space.items()) == list(search_space.items()))
+        if not ok:
+            self.ahead_stats[1] += 1
+            if self._rng._settle is a.cancel:
+                self._rng._settle = None
+                a.cancel()
+            return None
+        self._rng._settle = None
+        x, _, _ = eng.collect()
+        if a.dev_rng:
+            self._rng.mark_device(eng)
+        self.ahead_stats[0] += 1
+        return x
+
+    def _look_ahead(self, study, trial, state, values) -> None:
+        """Called from `after_trial`: the trial, its final state and values are known, the storage records them
+        right after (study/_tell.py:163-169).  In a sequential loop everything the next ask will compute is
+        determined at this point -- the history plus this trial, the same search space, the generator where the
+        last ask left it -- so the row is uploaded and the whole suggestion queued on the device now; it runs while
+        optuna stores the trial and creates the next one, and `sample_relative` collects it after checking that the
+        ask really is the predicted one (`_take_ahead`).  Joint sampling only; anything out of the ordinary (constant
+        liar, groups, a failed trial, a changed space) just skips it."""
+        if self._confirm_speculation(study, trial, state, values):
+            return
         self._drop_ahead()
         if not (self._multivariate and not self._group and not self._constant_liar and self._prior_weight >= 0
                 and (state == TrialState.COMPLETE or state == TrialState.PRUNED)):
