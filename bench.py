@@ -492,6 +492,26 @@ def run_b200(args) -> None:
         extras["univariate_trial_ms"] = unib * 1e3
         extras["univariate_suggestions_per_s"] = 1.0 / unib
         extras["univariate_device_ms"] = float(eng.last_timing()[0][8])
+        # config 2 with the DEFAULT n_ei_candidates = 24 through optuna's Study (what most studies run)
+        try:
+            dsampler = B200TPESampler(seed=12, n_ei_candidates=24, multivariate=True, device=local)
+            study.sampler = dsampler
+            for rep in range(4):
+                one_trial()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_def = 40
+            for rep in range(n_def):
+                one_trial()
+            torch.cuda.synchronize()
+            de = (time.perf_counter() - t0) / n_def
+            extras["default_candidates_e2e"] = {"n_ei_candidates": 24, "trial_ms": de * 1e3, "suggestions_per_s": 1.0 / de,
+                                                "trials": n_def, "look_ahead": list(dsampler.ahead_stats),
+                                                "speculations": list(dsampler.spec_stats)}
+            study.sampler = sampler
+            dsampler.close()
+        except Exception as e:
+            extras["default_candidates_e2e"] = {"error": repr(e)}
         # the same through optuna's Study: the reference's default sampler mode (multivariate=False), 32
         # sample_independent calls per trial answered from one batched device call (B200TPESampler._plan_trial)
         try:
