@@ -553,11 +553,15 @@ class B200TPESampler(BaseSampler):
         if self.LOOK_AHEAD and self._engine is not None:
             t0 = time.perf_counter()
             with self._lock:
-                if self._multivariate:
-                    if self._last_space is not None:
-                        self._look_ahead(study, trial, state, values)
-                else:
-                    self._look_ahead_uni(study, trial, state, values)
+                try:
+                    if self._multivariate:
+                        if self._last_space is not None:
+                            self._look_ahead(study, trial, state, values)
+                    else:
+                        self._look_ahead_uni(study, trial, state, values)
+                except Exception as e:               # computing ahead is an optimisation: it must never break a `tell`
+                    _logger.debug(f"look-ahead abandoned: {e!r}")
+                    self._abandon_ahead()
             self.last_tell_s = time.perf_counter() - t0   # row upload + queueing the next suggestion
 
     # -- host glue -------------------------------------------------------------------------------------
@@ -1038,7 +1042,11 @@ class B200TPESampler(BaseSampler):
                 self._audit(trial, search_space, self._eng())
             if speculate and self.LOOK_AHEAD and self.SPECULATE:
                 t2 = time.perf_counter()
-                self._speculate(study, trial, cols, search_space, out)
+                try:
+                    self._speculate(study, trial, cols, search_space, out)
+                except Exception as e:               # ... nor an `ask` whose suggestion is already computed
+                    _logger.debug(f"speculation abandoned: {e!r}")
+                    self._abandon_ahead()
                 self.last_spec_s = time.perf_counter() - t2
             return out
         finally:
@@ -1079,6 +1087,18 @@ class B200TPESampler(BaseSampler):
     # -- look-ahead: the next suggestion is computed while the study finishes `tell` and starts `ask` ----------
     #: queue the next joint suggestion at `tell` time (multivariate TPE; see _look_ahead)
     LOOK_AHEAD = True
+
+    def _abandon_ahead(self) -> None:
+        """Something went wrong while computing ahead: forget it, put the generator back, and let the next ask
+        rebuild the device history from the study (nothing the device holds is trusted)."""
+        try:
+            self._drop_ahead()
+        except Exception:
+            self._ahead = None
+            self._rng._settle = None
+        h = self._hist
+        h.dev_token = None
+        h.dev_pred.clear()
 
     def _drop_ahead(self) -> None:
         a, self._ahead = self._ahead, None
@@ -1364,7 +1384,11 @@ class B200TPESampler(BaseSampler):
                 self._audit(trial, search_space, self._eng())
             if speculate and self.LOOK_AHEAD and self.SPECULATE:
                 t2 = time.perf_counter()
-                self._speculate(study, trial, cols, search_space, out)
+                try:
+                    self._speculate(study, trial, cols, search_space, out)
+                except Exception as e:               # ... nor an `ask` whose suggestion is already computed
+                    _logger.debug(f"speculation abandoned: {e!r}")
+                    self._abandon_ahead()
                 self.last_spec_s = time.perf_counter() - t2
             return out
         finally:

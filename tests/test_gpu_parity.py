@@ -871,6 +871,62 @@ def test_univariate_fast_gauss_transform_of_the_floor_bandwidth_kernels(eng, lay
         assert (at_floor > 0.99) if layout in ("dense", "corner", "log") else (0.5 < at_floor < 0.999), at_floor
 
 
+def test_asynchronous_entry_points_equal_the_blocking_ones(eng):
+    """tpe_sample_and_select_async / tpe_collect and tpe_suggest_univariate_batch_async / tpe_collect_univariate queue
+    the work and return; the results are those of the blocking calls bit for bit -- also when the caller uploads
+    history rows while the suggestion is still queued (a few rows travel through page-locked staging without
+    waiting; they land behind the queued kernels and change nothing those read)."""
+    from optuna_b200 import TPEEngine
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(21)
+    P, n, C = 6, 5000, 512
+    specs = [ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(P - 1)] + [ParamSpec(kind=0, low=1e-3, high=10.0, log=True)]
+    X = np.concatenate([rs.uniform(0, 1, (n, P - 1)), np.exp(rs.uniform(np.log(1e-3), np.log(10), (n, 1)))], 1)
+    key = np.stack([rs.uniform(size=n), np.zeros(n)], 1)
+    one = np.zeros(1, np.int8)
+    other = TPEEngine(0)
+    try:
+        for e in (eng, other):
+            e.set_space(specs)
+            e.set_history(X, np.zeros(n, np.int8), key)
+        cols = list(range(P))
+        for step, mv in enumerate((True, False)):
+            cfg = dict(n_below=25, n_candidates=C, multivariate=mv)
+            u = rs.random_sample(C * (1 + P))
+            want = other.suggest(cols, u, 1, **cfg)
+            eng.prepare(cols, **cfg)
+            eng.build()
+            eng.sample_and_select_async(u, 1)
+            # rows uploaded while the suggestion is queued: a new trial, and row 3 rewritten with its own content
+            row = np.concatenate([rs.uniform(0.1, 0.9, (1, P - 1)), [[0.5]]], 1)
+            k1 = np.array([[2.0 + step, 0.0]])
+            eng.append_history(row, one, k1)
+            eng.update_history(X[3:4], one, key[3:4], 3)
+            got = eng.collect()
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w)
+            other.append_history(row, one, k1)
+        # univariate batch (all parameters continuous: the path that runs stage by stage)
+        cfg = dict(n_below=25, n_candidates=C, multivariate=False)
+        for rep in range(3):
+            u = rs.random_sample(P * 2 * C)
+            want = other.suggest_univariate_batch(cols, u, **cfg)
+            eng.suggest_univariate_batch_async(cols, u, **cfg)
+            row = np.concatenate([rs.uniform(0.1, 0.9, (1, P - 1)), [[0.7]]], 1)
+            k1 = np.array([[5.0 + rep, 0.0]])
+            eng.append_history(row, one, k1)
+            got = eng.collect_univariate()
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w)
+            other.append_history(row, one, k1)
+        with pytest.raises(RuntimeError, match="pending"):
+            eng.collect()
+        with pytest.raises(RuntimeError, match="pending"):
+            eng.collect_univariate()
+    finally:
+        other.close()
+
+
 def test_config2_full_size_against_the_precomputed_oracle_fixture(eng):
     """BASELINE config 2 at full size: log l(x) and log g(x) of 256 points -- the first 256 candidates the oracle draws
     -- against tests/golden/c2_logpdf.npz (oracle/gen_c2_fixture.py: the chunked oracle, ~6 min of CPU, so it is
