@@ -640,7 +640,7 @@ class B200TPESampler(BaseSampler):
         key = np.zeros((n, 2))
         signs = np.asarray([-1.0 if d == StudyDirection.MAXIMIZE else 1.0 for d in study.directions])
         vals = np.full((n, len(signs)), np.inf) if multi else None
-        index = {name: j for j, name in enumerate(names)}
+        index = names if isinstance(names, dict) else {name: j for j, name in enumerate(names)}
         complete, pruned, running = TrialState.COMPLETE, TrialState.PRUNED, TrialState.RUNNING
         constrained = self._constraints_func is not None
         for i, t in enumerate(trials):
@@ -757,7 +757,9 @@ class B200TPESampler(BaseSampler):
         """Rows -> device, one tpe_history_update per contiguous run (a run may extend the history; rows between
         the device's end and the run are the placeholders of unfinished trials the log knows)."""
         h = self._hist
-        names = list(h.columns)
+        if not items:
+            return
+        names = h.columns                            # (name -> column: _rows takes the mapping as it is)
         rows = sorted(items)
         if rows and rows[0] > h.dev_rows:
             gap = {r: h.pending[r][1] for r in range(h.dev_rows, rows[0])}  # KeyError: a finished row was skipped
