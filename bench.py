@@ -682,6 +682,31 @@ def run_b200(args) -> None:
         if world > 1:
             config5["rank0_compute_ms"] = tm5["compute_s"] * 1e3
             config5["rank0_collectives_ms"] = tm5["collectives_s"] * 1e3
+    # ---- one suggestion over all GPUs: every rank evaluates g(x) over its slice of the above kernels, the
+    # per-candidate (max, sum) partials are all-gathered (16 B per candidate and rank), every rank finishes ----
+    kshard = None
+    if world > 1 and not args.no_extras:
+        from optuna_b200.dist import kernel_sharded_suggest
+        ks_steps = 20
+        uks = np.random.RandomState(77).random_sample((ks_steps + 3, per_ask))   # the same uniforms on every rank
+        eng.set_kernel_shard(rank, world)
+        for i in range(3):
+            kernel_sharded_suggest(eng, cols, uks[i], 1, **cfg)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(3, 3 + ks_steps):
+            xk, _, _ = kernel_sharded_suggest(eng, cols, uks[i], 1, **cfg)
+        torch.cuda.synchronize()
+        barrier()
+        dtk = (time.perf_counter() - t0) / ks_steps
+        eng.set_kernel_shard(0, 1)
+        xs, _, _ = eng.suggest(cols, uks[-1], 1, **cfg)
+        t = torch.tensor([dtk, 0.0 if np.array_equal(xs, xk) else 1.0], dtype=torch.float64, device=torch.device("cuda", local))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kshard = {"ms_per_suggestion": float(t[0]) * 1e3, "suggestions_per_s": 1.0 / float(t[0]),
+                  "equals_single_gpu_suggestion_on_every_rank": float(t[1]) == 0.0, "scaling": "strong",
+                  "path": "per rank: tpe_prepare / tpe_build / tpe_sample_and_partial (g(x) over 1/N of the kernels) -> "
+                          "ncclAllGather of the [N][4096] (max, sum) partials -> tpe_finish_from_partials"}
     if rank == 0:
         peak, peak_src = measured_peaks()
         k_ms = float(stage[5]) / args.steps  # main log-density kernel under g(x)
@@ -744,6 +769,8 @@ def run_b200(args) -> None:
             line["extras"] = extras
         if config5:
             line["config5"] = config5
+        if kshard:
+            line["kernel_sharded"] = kshard
         if bcast_ms is not None:
             line["history_broadcast"] = {"ms": bcast_ms, "bytes": N_TRIALS * (N_PARAMS + 2) * 8 + N_TRIALS,
                                          "note": "one ncclBroadcast of the frozen history (X and keys as one fp64 buffer, "

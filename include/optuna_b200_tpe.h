@@ -34,7 +34,8 @@ extern "C" {
  *      (results stay on the device: tpe_result_device_ptrs); tpe_rng_state_device; tpe_suggest_univariate_batch */
 /* 4: + tpe_sample_and_select_async / tpe_collect */
 /* 5: + tpe_suggest_univariate_batch_async / tpe_collect_univariate */
-#define TPE_ABI_VERSION 5
+/* 6: + tpe_set_kernel_shard / tpe_sample_and_partial / tpe_finish_from_partials */
+#define TPE_ABI_VERSION 6
 
 enum {
   TPE_OK = 0,
@@ -164,6 +165,20 @@ int tpe_sample_and_select(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, 
  * `uniforms` is read before tpe_sample_and_select_async returns.  Any tpe_prepare abandons uncollected results. */
 int tpe_sample_and_select_async(tpe_ctx* ctx, const double* uniforms, int64_t n_asks);
 int tpe_collect(tpe_ctx* ctx, double* out_x, double* out_acq, int64_t* out_best);
+
+/* ONE suggestion over several GPUs (the alternative for a single ask): every rank holds the whole
+ * history and builds both estimators (cheap), but evaluates g(x) -- the C x K x P grid -- only over its slice of the
+ * above kernels.  tpe_set_kernel_shard(rank, world) selects the slice for the following calls (world = 1: off).
+ * tpe_sample_and_partial replaces tpe_sample_and_select: candidates (every rank draws the same ones from the same
+ * uniforms), l(x) in full, g(x) over the slice, reduced to one (max, sum) pair per candidate:
+ *   *d_partials  device pointer, [n_asks * C] double2 padded to *stride pairs.
+ * The caller gathers the partials of all ranks into one device buffer [world][*stride] double2 (ncclAllGather) and
+ * calls tpe_finish_from_partials on every rank: log-sum-exp across ranks in rank order, acquisition, argmax -- the
+ * same numbers on every rank.  Multivariate suggestions over continuous parameters only (TPE_E_STATE otherwise). */
+int tpe_set_kernel_shard(tpe_ctx* ctx, int32_t rank, int32_t world);
+int tpe_sample_and_partial(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double** d_partials, int64_t* stride);
+int tpe_finish_from_partials(tpe_ctx* ctx, const double* d_gathered, int32_t world, double* out_x, double* out_acq,
+                             int64_t* out_best);
 
 /* Device pointers of the results of the last tpe_sample_and_select: out_x [n_asks, n_cols], out_acq [n_asks],
  * out_best [n_asks] (valid until the next call on the context; the work has completed when that call returned). */

@@ -55,6 +55,9 @@ SYMBOLS = {
     "tpe_rng_state_device": (C.c_int, [_P, C.POINTER(_P)]),
     "tpe_sample_and_select_async": (C.c_int, [_P, _P, C.c_int64]),
     "tpe_collect": (C.c_int, [_P, _P, _P, _P]),
+    "tpe_set_kernel_shard": (C.c_int, [_P, C.c_int32, C.c_int32]),
+    "tpe_sample_and_partial": (C.c_int, [_P, _P, C.c_int64, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "tpe_finish_from_partials": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "tpe_result_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "tpe_get_uniforms": (C.c_int, [_P, _P, C.c_int64]),
     "tpe_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -77,7 +80,7 @@ SYMBOLS = {
 _lib = None
 
 
-ABI_VERSION = 5  # include/optuna_b200_tpe.h TPE_ABI_VERSION
+ABI_VERSION = 6  # include/optuna_b200_tpe.h TPE_ABI_VERSION
 
 
 def load() -> C.CDLL:

@@ -220,6 +220,11 @@ struct tpe_ctx {
   cudaEvent_t up_ev[kUpSlots] = {};
   bool up_used[kUpSlots] = {};
   int up_next = 0;
+  // one suggestion over several GPUs: this context evaluates g(x) over its slice of the above kernels only
+  // (tpe_set_kernel_shard, tpe_sample_and_partial, tpe_finish_from_partials)
+  int32_t kshard_rank = 0, kshard_world = 1;
+  DevBuf kpart;
+  bool partial_ready = false;
   bool deferred = false;         // tpe_sample_and_select_async issued, tpe_collect not yet called
   int64_t deferred_uni = 0;      // tpe_suggest_univariate_batch_async issued (columns), not yet collected
   bool deferred_uni_rng = false;
@@ -1136,6 +1141,8 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
   cudaStream_t st = ctx->stream;
   if (which == 1 && join_above(ctx)) return TPE_E_CUDA;
   const int64_t K = e.K;
+  if (which == 1 && ctx->kshard_world > 1 && !(ctx->fast && ctx->fast_mode == 2))
+    return fail(ctx, TPE_E_STATE, "kernel sharding is for multivariate all-continuous suggestions");
   if (ctx->uni_fast && e.uni_ready && Ct <= 4096) {
     // one continuous column, univariate: sorted candidates x sorted kernels (tpe_uni.cuh)
     const int C = (int)Ct;
@@ -1191,7 +1198,17 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     }
     const FastCfg* fc = use_mma ? pick_mma(ctx->pb, Ct) : pick_fast(ctx->fast_mode, ctx->pb, Ct);
     // CONST tables exclude the prior kernel (its sigma differs); the mma table is padded to groups of 8
-    const int64_t Kf = use_mma ? round_up<int64_t>(K - 1, kMmaKPad) : (cst_mode ? K - 1 : K);
+    int64_t Kf = use_mma ? round_up<int64_t>(K - 1, kMmaKPad) : (cst_mode ? K - 1 : K);
+    // kernel sharding (g(x) only): this context takes the tiles [k_lo, k_hi) of the table; the prior kernel's slice
+    // belongs to rank 0
+    int64_t k_lo = 0;
+    const bool sharded = which == 1 && ctx->kshard_world > 1;
+    if (sharded) {
+      if (!cst_mode) return fail(ctx, TPE_E_STATE, "kernel sharding is for multivariate all-continuous suggestions");
+      const int64_t chunk = round_up<int64_t>((Kf + ctx->kshard_world - 1) / ctx->kshard_world, fc->tk);
+      k_lo = std::min(Kf, chunk * ctx->kshard_rank);
+      Kf = std::min(Kf, k_lo + chunk) - k_lo;
+    }
     const int tc = fc->cands_per_cta;
     const int64_t ctiles = (Ct + tc - 1) / tc;
     // k-splits: two full waves of resident CTAs for the big configurations
@@ -1206,7 +1223,7 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     }
     // bf16 tensor-core screen + exact survivors (tpe_tcscreen.cuh): many candidates, rounding bound small enough
     bool use_tcs = false;
-    if (e.tcs && cst_mode && Ct >= 256) {
+    if (e.tcs && cst_mode && Ct >= 256 && !sharded) {
       const double nobs = (double)std::max<int64_t>(e.n, 1);
       double fac = 0.2 * pow(nobs, -1.0 / (ctx->pc + 4));
       if (ctx->cfg.magic_clip) fac = std::max(fac, 1.0 / std::min(100.0, 1.0 + (double)K));
@@ -1340,9 +1357,12 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
         CU(ctx->lse_gmax.ensure((size_t)ctx->ct_stride * 8));
         CU(cudaMemsetAsync(ctx->lse_gmax.p, 0, (size_t)ctx->ct_stride * 8, st));
       }
+      // (both CONST tables are blocked by whole kernels -- the fragment-major one in groups of 8 -- so a slice that
+      // starts at a multiple of the tile is a plain offset)
       fc->launch(dim3((unsigned)ctiles, (unsigned)nsplit), fc->smem, st,
-                 use_mma ? (const void*)e.tabm.p : (cst_mode ? (const void*)e.tabc.p : (const void*)e.tabp.p),
-                 use_mma ? e.ckk.as<double>() : e.cst.as<double>(), Kf,
+                 use_mma ? (const void*)(e.tabm.as<double>() + k_lo * ctx->pb)
+                         : (cst_mode ? (const void*)(e.tabc.as<double>() + k_lo * ctx->pb) : (const void*)e.tabp.p),
+                 (use_mma ? e.ckk.as<double>() : e.cst.as<double>()) + k_lo, Kf,
                  e.colprm.as<double2>(), ctx->xT.as<double>(), ctx->ct_stride, kps,
                  std::min(46.0, log((double)std::max<int64_t>(K, 1)) + 30.0), e.part.as<double2>(),
                  use_mma ? ctx->lse_gmax.as<unsigned long long>() : nullptr);
@@ -1361,10 +1381,10 @@ int run_logpdf(tpe_ctx* ctx, int which, int64_t Ct, cudaEvent_t after_main = nul
     k_logpdf_prior_fix<<<(unsigned)((Ct * 32 + 255) / 256), 256, 0, st>>>(
         ctx->S.as<double>(), Ct, ctx->cols.as<ColMeta>(), ctx->pc, e.mu.as<double>(), e.sigma.as<double>(),
         e.cst.as<double>(), K, e.tab.as<double>(),
-        cst_mode ? e.part.as<double2>() + nsplit * ctx->ct_stride : nullptr, ctx->oob.as<uint8_t>(),
-        e.fix.as<double2>());
+        (cst_mode && !(sharded && ctx->kshard_rank != 0)) ? e.part.as<double2>() + nsplit * ctx->ct_stride : nullptr,
+        ctx->oob.as<uint8_t>(), e.fix.as<double2>());
     ctx->launch_counter++;
-    if (cst_mode) nsplit += 1;
+    if (cst_mode && !(sharded && ctx->kshard_rank != 0)) nsplit += 1;
     e.nsplit = (int)nsplit;
   } else if (e.mixed && !ctx->user_points && Ct >= 64 && mixed_cb(ctx) > 0) {
     // mixed space, many candidates: kernel-minor tables, the candidates' table rows in shared memory (tpe_mixed.cuh)
@@ -1758,7 +1778,7 @@ void tpe_ctx_destroy(tpe_ctx* ctx) {
                     &ctx->mo_isdup, &ctx->mo_sorted, &ctx->mo_uniq, &ctx->mo_nuniq, &ctx->mo_ref, &ctx->mo_removed, &ctx->mo_table,
                     &ctx->mo_sample, &ctx->mo_surv, &ctx->mo_nsurv, &ctx->mo_fv, &ctx->mo_ps, &ctx->mo_map, &ctx->mo_front, &ctx->mo_head,
                     &ctx->mo_contrib, &ctx->mo_state, &ctx->mo_arena, &ctx->mo_chosen, &ctx->mo_diag, &ctx->mo_w, &ctx->cols, &ctx->row_ok, &ctx->member,
-                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->mixcols, &ctx->ub_arena, &ctx->ub_ord_a, &ctx->ub_ord_b, &ctx->ub_wstage, &ctx->uxs, &ctx->ucidx, &ctx->uni_prev_rows, &ctx->uni_mode, &ctx->uni_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
+                    &ctx->counts, &ctx->split_work, &ctx->below_all, &ctx->kpart, &ctx->mixcols, &ctx->ub_arena, &ctx->ub_ord_a, &ctx->ub_ord_b, &ctx->ub_wstage, &ctx->uxs, &ctx->ucidx, &ctx->uni_prev_rows, &ctx->uni_mode, &ctx->uni_work, &ctx->sort_val, &ctx->sort_idx, &ctx->sort_work, &ctx->U, &ctx->S,
                     &ctx->xT, &ctx->x64s, &ctx->x32s, &ctx->e32s, &ctx->gmax, &ctx->lse_gmax, &ctx->mt_state, &ctx->U2, &ctx->mt_spec, &ctx->mt_jump, &ctx->mt_tmp, &ctx->oob, &ctx->logl, &ctx->logg, &ctx->out_x, &ctx->out_acq, &ctx->out_best})
     b->release();
   ctx->est[0].release();
@@ -2278,6 +2298,16 @@ static int launch_sample_select(tpe_ctx* ctx, int64_t n_asks, bool used_dev_rng,
   rc = run_logpdf(ctx, 1, Ct, timed ? ctx->ev[6] : nullptr);
   if (rc) return rc;
   if (timed) CU(cudaEventRecord(ctx->ev[7], st));
+  if (ctx->kshard_world > 1) {
+    // one (max, sum) per candidate over this context's slice of g(x); the caller gathers them from all ranks and
+    // finishes with tpe_finish_from_partials
+    CU(ctx->kpart.ensure((size_t)ctx->ct_stride * 16));
+    k_reduce_parts<<<grid_for(Ct, 256, ctx->sm_count * 8), 256, 0, st>>>(ctx->est[1].part.as<double2>(), ctx->est[1].nsplit,
+                                                                         ctx->ct_stride, Ct, ctx->kpart.as<double2>());
+    ctx->launch_counter++;
+    ctx->partial_ready = true;
+    return TPE_OK;
+  }
   k_acq<<<grid_for(Ct * 32, 256, ctx->sm_count * 8), 256, 0, st>>>(
       ctx->est[0].part.as<double2>(), ctx->est[0].nsplit, ctx->est[1].part.as<double2>(), ctx->est[1].nsplit,
       ctx->ct_stride, ctx->fast ? ctx->oob.as<uint8_t>() : nullptr, ctx->est[0].fix.as<double2>(),
@@ -2396,6 +2426,58 @@ int tpe_collect(tpe_ctx* ctx, double* out_x, double* out_acq, int64_t* out_best)
   if (out_x) memcpy(out_x, h, (size_t)n_asks * ctx->pc * 8);
   if (out_acq) memcpy(out_acq, h + (size_t)n_asks * ctx->pc * 8, (size_t)n_asks * 8);
   if (out_best) memcpy(out_best, h + (size_t)n_asks * (ctx->pc + 1) * 8, (size_t)n_asks * 8);
+  return TPE_OK;
+}
+
+int tpe_set_kernel_shard(tpe_ctx* ctx, int32_t rank, int32_t world) {
+  if (!ctx || world < 1 || rank < 0 || rank >= world) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->kshard_rank = rank;
+  ctx->kshard_world = world;
+  ctx->partial_ready = false;
+  return TPE_OK;
+}
+
+int tpe_sample_and_partial(tpe_ctx* ctx, const double* uniforms, int64_t n_asks, double** d_partials, int64_t* stride) {
+  if (!ctx || !d_partials) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ctx->kshard_world < 2) return fail(ctx, TPE_E_STATE, "tpe_set_kernel_shard(rank, world >= 2) must precede tpe_sample_and_partial");
+  int rc = sample_select_issue(ctx, uniforms, n_asks, false);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->issued_dev_rng) ctx->mt_host_valid = true;
+  *d_partials = ctx->kpart.as<double>();
+  if (stride) *stride = ctx->ct_stride;
+  return TPE_OK;
+}
+
+int tpe_finish_from_partials(tpe_ctx* ctx, const double* d_gathered, int32_t world, double* out_x, double* out_acq,
+                             int64_t* out_best) {
+  if (!ctx || !d_gathered || world < 1) return TPE_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->partial_ready) return fail(ctx, TPE_E_STATE, "tpe_sample_and_partial must precede tpe_finish_from_partials");
+  if (set_device(ctx, /*join=*/false)) return TPE_E_CUDA;
+  cudaStream_t st = ctx->stream;
+  const int64_t n_asks = ctx->n_asks, Ct = n_asks * ctx->cfg.n_candidates;
+  k_acq<<<grid_for(Ct * 32, 256, ctx->sm_count * 8), 256, 0, st>>>(
+      ctx->est[0].part.as<double2>(), ctx->est[0].nsplit, reinterpret_cast<const double2*>(d_gathered), world,
+      ctx->ct_stride, ctx->fast ? ctx->oob.as<uint8_t>() : nullptr, ctx->est[0].fix.as<double2>(),
+      ctx->est[1].fix.as<double2>(), Ct, ctx->logl.as<double>(), ctx->logg.as<double>());
+  k_select<<<(unsigned)n_asks, 256, 0, st>>>(ctx->logl.as<double>(), ctx->logg.as<double>(), ctx->cfg.n_candidates,
+                                             ctx->S.as<double>(), ctx->pc, ctx->out_x.as<double>(),
+                                             ctx->out_acq.as<double>(), ctx->out_best.as<int64_t>());
+  ctx->launch_counter += 2;
+  CU(cudaEventRecord(ctx->ev[8], st));
+  CU(cudaGetLastError());
+  if (out_x) CU(cudaMemcpyAsync(out_x, ctx->out_x.p, (size_t)n_asks * ctx->pc * 8, cudaMemcpyDeviceToHost, st));
+  if (out_acq) CU(cudaMemcpyAsync(out_acq, ctx->out_acq.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
+  if (out_best) CU(cudaMemcpyAsync(out_best, ctx->out_best.p, (size_t)n_asks * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&ctx->ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  cudaEventElapsedTime(&ctx->ms[8], ctx->ev[0], ctx->ev[8]);
+  ctx->launches = ctx->launch_counter;
+  ctx->partial_ready = false;
+  ctx->sampled = true;
   return TPE_OK;
 }
 

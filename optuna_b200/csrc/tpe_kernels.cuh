@@ -1821,6 +1821,20 @@ k_acq(const double2* __restrict__ part_l, int nsl, const double2* __restrict__ p
                       const double2* __restrict__ fix_g, int64_t Ct, double* __restrict__ logl,
                       double* __restrict__ logg) { d_acq(part_l, nsl, part_g, nsg, ct_stride, oob, fix_l, fix_g, Ct, logl, logg); }
 
+// (max, sum) per candidate over the k-split partials of ONE estimator, merged in slice order (what a rank of a
+// kernel-sharded suggestion contributes: tpe_sample_and_partial)
+__global__ void k_reduce_parts(const double2* __restrict__ part, int ns, int64_t ct_stride, int64_t Ct,
+                               double2* __restrict__ out) {
+  for (int64_t ct = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ct < Ct; ct += (int64_t)gridDim.x * blockDim.x) {
+    double m = -INFINITY, s = 0.0;
+    for (int i = 0; i < ns; ++i) {
+      const double2 v = part[(int64_t)i * ct_stride + ct];
+      lse_merge(v.x, v.y, m, s);
+    }
+    out[ct] = make_double2(m, s);
+  }
+}
+
 // One CTA per ask: acq = logl - logg, best = first maximum (NaN wins, like np.argmax).
 __device__ __forceinline__ void d_select(const double* __restrict__ logl, const double* __restrict__ logg, int32_t C, const double* __restrict__ S,
          int32_t pc, double* __restrict__ out_x, double* __restrict__ out_acq, int64_t* __restrict__ out_best) {

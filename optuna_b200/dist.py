@@ -192,3 +192,32 @@ def sharded_asks_device_rng(engine, rng: np.random.RandomState, n_asks: int, per
         timing["compute_s"] = t1 - t0
         timing["collectives_s"] = time.perf_counter() - t1
     return out
+
+
+def kernel_sharded_suggest(engine, cols, uniforms, n_asks: int = 1, gather=None, **cfg):
+    """ONE suggestion (or batch of asks) evaluated by all ranks together: every rank holds the whole history and
+    builds both estimators, evaluates g(x) over its slice of the above kernels (``tpe_set_kernel_shard``), the
+    per-candidate (max, sum) partials are all-gathered device to device (16 bytes per candidate and rank) and every
+    rank finishes with the same argmax (``tpe_finish_from_partials``).  SURVEY.md section 8e, the alternative for a
+    single ask: the grid of one config-2 suggestion shrinks by the number of GPUs.
+
+    ``gather(local: torch.Tensor) -> torch.Tensor [world, ...]`` defaults to ``dist.all_gather_into_tensor`` (NCCL);
+    tests pass their own to emulate several ranks on one device."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if gather is None and world == 1:
+        return engine.suggest(cols, uniforms, n_asks, **cfg)
+    engine.prepare(cols, **cfg)
+    engine.build()
+    ptr, stride = engine.sample_and_partial(uniforms, n_asks)
+    dev = torch.device("cuda", engine.device)
+    mine = device_view(ptr, (stride, 2), "<f8", dev)
+    if gather is None:
+        allp = torch.empty((world, stride, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allp.view(-1), mine.reshape(-1))
+    else:
+        allp = gather(mine)
+    torch.cuda.synchronize(dev)
+    return engine.finish_from_partials(allp.data_ptr(), allp.shape[0])

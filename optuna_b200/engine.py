@@ -218,6 +218,31 @@ class TPEEngine:
         name, has_gauss, cached = self._rng_tail
         return (name, key, int(pos.value), has_gauss, cached)
 
+    def set_kernel_shard(self, rank: int, world: int) -> None:
+        """This engine evaluates g(x) over slice `rank` of `world` of the above kernels (world = 1: off)."""
+        self._check(self._lib.tpe_set_kernel_shard(self._h, int(rank), int(world)))
+
+    def sample_and_partial(self, uniforms, n_asks: int = 1) -> tuple[int, int]:
+        """Candidates, l(x) and this engine's slice of g(x): (device address of the [n_asks * C] (max, sum) pairs,
+        their padded count)."""
+        u = None
+        if uniforms is not None:
+            u = _f64(uniforms).reshape(-1)
+            assert u.size == n_asks * self.uniforms_per_ask()
+        ptr, stride = C.c_void_p(), C.c_int64()
+        self._check(self._lib.tpe_sample_and_partial(self._h, _ptr(u), int(n_asks), C.byref(ptr), C.byref(stride)))
+        self._last_asks = n_asks
+        return int(ptr.value), int(stride.value)
+
+    def finish_from_partials(self, gathered_ptr: int, world: int):
+        n_asks = self._last_asks
+        x = np.empty((n_asks, self._pc), dtype=np.float64)
+        acq = np.empty(n_asks, dtype=np.float64)
+        best = np.empty(n_asks, dtype=np.int64)
+        self._check(self._lib.tpe_finish_from_partials(self._h, C.c_void_p(int(gathered_ptr)), int(world), _ptr(x), _ptr(acq),
+                                                       _ptr(best)))
+        return x, acq, best
+
     def sample_and_select_device(self, n_asks: int = 1) -> int:
         """Like ``sample_and_select(None, n_asks)`` but the results stay on the device; returns the device
         address of out_x [n_asks, n_cols] fp64 (valid until the next call on this engine)."""

@@ -927,6 +927,58 @@ def test_asynchronous_entry_points_equal_the_blocking_ones(eng):
         other.close()
 
 
+@pytest.mark.parametrize("world,n,P,C", [(2, 6000, 12, 512), (3, 5000, 32, 300), (4, 300, 9, 64), (2, 100_000, 32, 4096)])
+def test_kernel_sharded_suggestion_equals_the_single_context_one(eng, world, n, P, C):
+    """tpe_set_kernel_shard / tpe_sample_and_partial / tpe_finish_from_partials: `world` contexts (here on one device;
+    across GPUs the gather is one ncclAllGather, optuna_b200/dist.py) each evaluate g(x) over their slice of the above
+    kernels, the per-candidate (max, sum) partials are gathered and every context finishes with the suggestion the
+    single-context call computes: same candidate, acquisition value within 1e-12.  Uneven slices, slices without
+    kernels (fewer tiles than ranks) and the full config-2 size."""
+    import torch
+    from optuna_b200 import TPEEngine
+    from optuna_b200.dist import device_view
+    from optuna_b200.engine import ParamSpec
+    rs = np.random.RandomState(world * 7 + P)
+    specs = [ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(P)]
+    X = rs.uniform(0, 1, (n, P))
+    key = np.stack([((X - 0.5) ** 2).sum(1), np.zeros(n)], 1)
+    cols = list(range(P))
+    cfg = dict(n_below=25, n_candidates=C, multivariate=True)
+    u = rs.random_sample(C * (1 + P))
+    eng.set_space(specs)
+    eng.set_history(X, np.zeros(n, np.int8), key)
+    want_x, want_acq, want_best = eng.suggest(cols, u, 1, **cfg)
+    _, ll, lg = eng.get_candidates()
+    ranks = [TPEEngine(0) for _ in range(world)]
+    try:
+        parts = []
+        for r, e in enumerate(ranks):
+            e.set_space(specs)
+            e.set_history(X, np.zeros(n, np.int8), key)
+            e.set_kernel_shard(r, world)
+            e.prepare(cols, **cfg)
+            e.build()
+            ptr, stride = e.sample_and_partial(u, 1)
+            parts.append(device_view(ptr, (stride, 2), "<f8", torch.device("cuda", 0)))
+        gathered = torch.stack(parts).contiguous()
+        torch.cuda.synchronize()
+        for e in ranks:
+            x, acq, best = e.finish_from_partials(gathered.data_ptr(), world)
+            assert np.array_equal(x, want_x) and best[0] == want_best[0]
+            close(acq, want_acq, 0, 1e-12)
+            _, ll_r, lg_r = e.get_candidates()
+            close(lg_r, lg, 0, 1e-12)
+            assert np.array_equal(ll_r, ll)
+        with pytest.raises(RuntimeError, match="tpe_sample_and_partial must precede"):
+            ranks[0].finish_from_partials(gathered.data_ptr(), world)
+        ranks[0].set_kernel_shard(0, 1)                      # off again: the ordinary call
+        x, acq, best = ranks[0].suggest(cols, u, 1, **cfg)
+        assert np.array_equal(x, want_x) and acq[0] == want_acq[0]
+    finally:
+        for e in ranks:
+            e.close()
+
+
 def test_config2_full_size_against_the_precomputed_oracle_fixture(eng):
     """BASELINE config 2 at full size: log l(x) and log g(x) of 256 points -- the first 256 candidates the oracle draws
     -- against tests/golden/c2_logpdf.npz (oracle/gen_c2_fixture.py: the chunked oracle, ~6 min of CPU, so it is
