@@ -209,8 +209,19 @@ def kernel_sharded_suggest(engine, cols, uniforms, n_asks: int = 1, gather=None,
     rank = dist.get_rank() if dist.is_initialized() else 0
     if gather is None and world == 1:
         return engine.suggest(cols, uniforms, n_asks, **cfg)
+    if gather is None:
+        engine.set_kernel_shard(rank, world)
     engine.prepare(cols, **cfg)
     engine.build()
+    if hasattr(engine, "sample_and_partial_host"):       # an engine without a device (tests: the CPU oracle, gloo)
+        mine_h = torch.from_numpy(np.ascontiguousarray(engine.sample_and_partial_host(uniforms, n_asks)))
+        if gather is None:
+            blocks = [torch.empty_like(mine_h) for _ in range(world)]
+            dist.all_gather(blocks, mine_h)
+            allh = torch.stack(blocks)
+        else:
+            allh = gather(mine_h)
+        return engine.finish_from_partials_host(allh.numpy())
     ptr, stride = engine.sample_and_partial(uniforms, n_asks)
     dev = torch.device("cuda", engine.device)
     mine = device_view(ptr, (stride, 2), "<f8", dev)

@@ -209,6 +209,39 @@ class OracleEngine:
             x[j], acq[j], best[j] = xj[0, 0], aj[0], bj[0]
         return x, acq, best
 
+    # -- one suggestion over several ranks (tpe_set_kernel_shard / tpe_sample_and_partial / tpe_finish_from_partials) --
+    def set_kernel_shard(self, rank: int, world: int) -> None:
+        self._ks = (int(rank), int(world))
+
+    def sample_and_partial_host(self, uniforms, n_asks: int = 1) -> np.ndarray:
+        """(max, sum) per candidate of g(x) over this rank's slice of the above kernels; the prior kernel belongs to
+        rank 0 (as in the library)."""
+        assert n_asks == 1
+        rank, world = getattr(self, "_ks", (0, 1))
+        u = np.asarray(uniforms, dtype=np.float64).ravel()
+        cand = orc.mixture_sample(self._mix_b, _ReplayRng(u), self._C)
+        self._ks_cand, self._ks_ll = cand, orc.mixture_log_pdf(self._mix_b, cand)
+        K = self._mix_a.weights.size
+        chunk = -(-(K - 1) // world)
+        idx = list(range(min(K - 1, rank * chunk), min(K - 1, (rank + 1) * chunk))) + ([K - 1] if rank == 0 else [])
+        out = np.stack([np.full(self._C, -np.inf), np.zeros(self._C)], 1)
+        if idx:
+            m = self._mix_a
+            sub = orc.Mixture(m.weights[idx], m.params, {j: w[idx] for j, w in m.cat_w.items()},
+                              {j: v[idx] for j, v in m.mu.items()}, {j: v[idx] for j, v in m.sigma.items()})
+            out[:, 0], out[:, 1] = orc.mixture_log_pdf(sub, cand), 1.0
+        return out
+
+    def finish_from_partials_host(self, allp: np.ndarray):
+        m, s = allp[:, :, 0], allp[:, :, 1]
+        top = m.max(axis=0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lg = np.log((s * np.exp(m - top)).sum(axis=0)) + top
+        score = self._ks_ll - lg
+        self._last = (self._ks_cand, self._ks_ll, lg)
+        best = int(np.argmax(score))
+        return self._ks_cand[best][None], np.array([score[best]]), np.array([best])
+
     def suggest_univariate_batch_async(self, cols, uniforms, w_below=None, w_above=None, **cfg) -> None:
         self._uni_deferred = self.suggest_univariate_batch(cols, uniforms, w_below, w_above, **cfg)
 

@@ -99,3 +99,42 @@ def test_sharded_asks_with_engine_generated_uniforms_gloo_world2(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_rng_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert np.array_equal(np.load(tmp_path / "g0.npy"), np.load(tmp_path / "g1.npy"))
+
+
+def _kshard_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    """kernel_sharded_suggest with the CPU oracle standing in for the CUDA engine (gloo): g(x) summed over the ranks'
+    slices of the above kernels equals the single-process suggestion on every rank."""
+    import torch.distributed as dist
+    from optuna_b200.dist import kernel_sharded_suggest
+    from optuna_b200.engine import ParamSpec
+    from tests._oracle_engine import OracleEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rs = np.random.RandomState(5)
+    n, P, C = 90, 4, 16
+    X = rs.uniform(0, 1, (n, P))
+    X[:, 3] = rs.randint(0, 3, n)
+    eng = OracleEngine()
+    eng.set_space([ParamSpec(kind=0, low=0.0, high=1.0) for _ in range(3)] + [ParamSpec(kind=2, n_choices=3)])
+    eng.set_history(X, np.zeros(n, np.int8), np.stack([((X[:, :3] - 0.4) ** 2).sum(1), np.zeros(n)], 1))
+    cfg = dict(n_below=8, n_candidates=C, multivariate=True)
+    u = np.random.RandomState(9).random_sample(C * (1 + 1 + 3))
+    x, acq, best = kernel_sharded_suggest(eng, list(range(P)), u, 1, **cfg)
+    want = OracleEngine()
+    want.set_space(eng.specs)
+    want.set_history(X, np.zeros(n, np.int8), eng.key)
+    wx, wacq, wbest = want.suggest(list(range(P)), u, 1, **cfg)
+    assert np.array_equal(x, wx) and best[0] == wbest[0] and abs(acq[0] - wacq[0]) < 1e-12
+    np.save(os.path.join(out_dir, f"k{rank}.npy"), np.concatenate([x.ravel(), acq]))
+    dist.destroy_process_group()
+
+
+def test_kernel_sharded_suggestion_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_kshard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "k0.npy"), np.load(tmp_path / "k1.npy")
+    assert np.array_equal(a, b)
