@@ -18,7 +18,15 @@ the C x K x P grid + argmax.  Nothing is cached between steps.
            100k trials added by ``study.add_trials``, then per step ``trial = study.ask()``, 32 x
            ``trial.suggest_float`` (the first one triggers infer_relative_search_space + sample_relative),
            ``study.tell(trial, value)``: every step appends a trial, so every step also ingests one.
-           optuna's own per-trial bookkeeping is inside the timed region.
+           optuna's own per-trial bookkeeping is inside the timed region.  The sampler computes suggestions
+           ahead of the ask where the call order allows it (queued when the previous
+           suggestion has been handed out, confirmed at tell time); every step is still one full ask + tell and
+           ``e2e.host`` reports the same loop with that switched off (``per_trial_ms_without_look_ahead``), the
+           time the caller waits, and how many look-aheads / speculations were kept.
+``extras`` (N = 1)  other shapes of the same path: the default n_ei_candidates = 24 and univariate TPE through
+           optuna's Study, the batched univariate trial, config 3 (mixed, C = 24 / 4096), config 4 (MOTPE), batched asks.
+``config5`` 8192 asks sharded over the ranks (strong scaling); ``kernel_sharded`` (N > 1): ONE suggestion evaluated
+           by all ranks together (g(x) sharded over the kernels, one all-gather of per-candidate partials).
 ``--impl reference``  the reference ITSELF on the host cores: optuna's own ``_split_trials``,
            ``_ParzenEstimator`` and ``log_pdf`` (oracle/_ref, unmodified) on the same 100k-trial study;
            each step is a bounded sample (see run_reference).
