@@ -630,6 +630,72 @@ def test_random_event_sequences_match_the_reference(make_sampler, mv, events):
         assert sum(a.sampler.ahead_stats) >= 10, (a.sampler.ahead_stats, a.sampler.spec_stats)
 
 
+@pytest.mark.parametrize("kind", ["two_objectives", "constraints", "custom_gamma_weights", "endpoints_no_clip"])
+@pytest.mark.parametrize("events", [3, 4])
+def test_random_event_sequences_with_other_sampler_options(make_sampler, kind, events):
+    """The random walk of test_random_event_sequences_match_the_reference (joint sampling) with the options that change
+    what a suggestion computed ahead must respect: two objectives (look-ahead without outcome speculation, hypervolume
+    weights), constraints (read back from the storage at `tell` time), a custom gamma that grows the below set and
+    custom weights, endpoints without the magic clip.  Host glue only (the CPU oracle answers the engine calls)."""
+    if make_sampler.kind != "oracle":
+        pytest.skip("host-glue walk: the CPU oracle is the engine")
+    from optuna.trial import TrialState as TS
+    kw = dict(seed=300 + events, multivariate=True, n_startup_trials=5)
+    study_kw = {}
+    if kind == "two_objectives":
+        study_kw["directions"] = ["minimize", "maximize"]
+    elif kind == "constraints":
+        kw["constraints_func"] = lambda tr: (tr.params["x"] - 1.0, -0.5)
+    elif kind == "custom_gamma_weights":
+        kw.update(gamma=lambda n: max(1, n // 3), weights=lambda n: np.linspace(0.2, 1.0, n) if n else np.asarray([]))
+    else:
+        kw.update(consider_endpoints=True, consider_magic_clip=False, prior_weight=0.3)
+
+    def value(x, y, z, ev):
+        v = x * x + math.log(y) ** 2 + (z - 0.3) ** 2 + 0.05 * ev.standard_normal()
+        return [v, -abs(x) + z] if kind == "two_objectives" else v
+
+    def run_trial(t, ev):
+        return value(t.suggest_float("x", -2.0, 2.0), t.suggest_float("y", 1e-2, 10.0, log=True),
+                     t.suggest_float("z", 0.0, 1.0), ev)
+
+    def scenario(sampler):
+        ev = np.random.RandomState(2000 + events)
+        s = optuna.create_study(sampler=sampler, **study_kw)
+        for _ in range(40):
+            op = ev.choice(["trial", "trial", "trial", "batch", "fail", "good", "draw"] +
+                           ([] if kind == "two_objectives" else ["prune"]))
+            if op == "trial":
+                t = s.ask()
+                s.tell(t, run_trial(t, ev))
+            elif op == "batch":
+                ts = [s.ask() for _ in range(int(ev.randint(2, 4)))]
+                vs = [run_trial(t, ev) for t in ts]
+                for i in ev.permutation(len(ts)):
+                    s.tell(ts[i], vs[i])
+            elif op == "fail":
+                t = s.ask()
+                run_trial(t, ev)
+                s.tell(t, state=TS.FAIL)
+            elif op == "prune":
+                t = s.ask()
+                v = run_trial(t, ev)
+                t.report(v, 0)
+                s.tell(t, state=TS.PRUNED)
+            elif op == "good":
+                t = s.ask()
+                run_trial(t, ev)
+                g = -1.0 - ev.uniform()
+                s.tell(t, [g, 3.0] if kind == "two_objectives" else g)
+            else:
+                sampler._rng.rng.random_sample(int(ev.randint(1, 7)))
+        return s
+
+    a, b = over_seeds(scenario, make_sampler, True, kw)
+    assert [t.state for t in a.trials] == [t.state for t in b.trials]
+    assert sum(a.sampler.ahead_stats) >= 8, (a.sampler.ahead_stats, a.sampler.spec_stats)
+
+
 def test_batched_ask_equals_sequential_asks(make_sampler):
     """BASELINE config 5 semantics: ask_batch(n) == n sequential study.ask() with no tell between."""
     from optuna_b200.batch import ask_batch
