@@ -349,7 +349,13 @@ class _UniPlan:
 
 class B200TPESampler(BaseSampler):
     """``optuna.samplers.TPESampler`` (sampler.py:72-385) with the numeric path on a B200.  Same constructor
-    arguments (+ ``device``), same plugin methods, same suggestions for the same seed."""
+    arguments (+ ``device``), same plugin methods, same suggestions for the same seed.
+
+    Where the reference's call order allows it the device work of an ask is queued BEFORE the ask (DESIGN.md
+    section 1b): at `tell` time (``after_trial`` knows the finished trial before the storage does) and, for joint
+    sampling, already when the previous suggestion has been handed out, on the assumption -- checked at `tell` time --
+    that the running trial will not enter the below set.  An ask that is not the predicted one puts the generator
+    back and computes as the reference does; ``LOOK_AHEAD`` / ``SPECULATE`` switch both off."""
 
     #: what answers the array-level calls -- the CUDA library; no fallback.  (The seam mirrors the reference's
     #: ``_parzen_estimator_cls``, sampler.py:358-359; tests plug the CPU oracle in here to check the host glue.)
